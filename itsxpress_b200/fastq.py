@@ -1,0 +1,189 @@
+"""FASTQ ingest / emit in structure-of-arrays form.
+
+Replaces the Biopython ``SeqIO.parse(..., "fastq")`` / ``SeqIO.write(..., "fastq")`` calls on the
+reference's hot path (itsxpress/SeqSample.py:746-757, 912-945) with a vectorised numpy scanner that
+produces the flat byte buffers the C-ABI consumes (sequence bytes + offsets, quality bytes, titles).
+Semantics kept from Biopython: title = line after '@' right-stripped, id =
+first whitespace-delimited token, '+' line may repeat the title, len(seq) == len(qual) and quality
+characters in ASCII 33..126, otherwise ``ValueError``; output is ``@title\\nseq\\n+\\nqual\\n``.
+"""
+import gzip
+import io
+import os
+
+import numpy as np
+
+
+class FastqBatch:
+    """All records of one FASTQ file.
+
+    buf      : uint8 array, the decompressed file
+    t_off/t_len : title start (after '@') and right-stripped length
+    s_off/s_len : sequence start / length (q_off: quality start; same length)
+    """
+
+    __slots__ = ("buf", "t_off", "t_len", "s_off", "s_len", "q_off", "n")
+
+    def __init__(self, buf, t_off, t_len, s_off, s_len, q_off):
+        self.buf, self.t_off, self.t_len = buf, t_off, t_len
+        self.s_off, self.s_len, self.q_off = s_off, s_len, q_off
+        self.n = len(t_off)
+
+    # -- flat views for the device path -------------------------------------------------------
+    def seq_concat(self):
+        """(bytes uint8[total], off int64[n+1]) with the sequences packed back to back."""
+        return _gather(self.buf, self.s_off, self.s_len)
+
+    def qual_concat(self):
+        return _gather(self.buf, self.q_off, self.s_len)
+
+    def title(self, i):
+        o = int(self.t_off[i])
+        return self.buf[o:o + int(self.t_len[i])].tobytes().decode("ascii", "replace")
+
+    def ids(self):
+        """First whitespace-delimited token of every title (Biopython's record.id)."""
+        out = []
+        b = self.buf
+        for o, l in zip(self.t_off.tolist(), self.t_len.tolist()):
+            t = b[o:o + l].tobytes()
+            sp = t.split(None, 1)
+            out.append(sp[0].decode("ascii", "replace") if sp else "")
+        return out
+
+    def seq(self, i):
+        o = int(self.s_off[i])
+        return self.buf[o:o + int(self.s_len[i])].tobytes().decode("ascii")
+
+    def qual(self, i):
+        o = int(self.q_off[i])
+        return self.buf[o:o + int(self.s_len[i])].tobytes().decode("ascii")
+
+
+def _gather(buf, off, length):
+    n = len(off)
+    out_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(length, out=out_off[1:])
+    total = int(out_off[-1])
+    if n == 0:
+        return np.zeros(0, np.uint8), out_off
+    # index = repeat(start - out_start) + arange
+    delta = np.repeat(off.astype(np.int64) - out_off[:-1], length)
+    idx = delta + np.arange(total, dtype=np.int64)
+    return buf[idx], out_off
+
+
+def _open_bytes(path):
+    if path.endswith(".gz"):
+        with gzip.open(path, "rb") as f:
+            return f.read()
+    if path.endswith(".zst"):
+        from . import _zstd
+        with open(path, "rb") as f:
+            return _zstd.decompress(f.read())
+    with open(path, "rb") as f:
+        return f.read()
+
+
+def parse_bytes(data):
+    """Parse a whole (decompressed) 4-line FASTQ byte string into a FastqBatch."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    if buf.size == 0:
+        z = np.zeros(0, np.int64)
+        return FastqBatch(buf, z, z, z, z, z)
+    nl = np.flatnonzero(buf == 10)
+    if buf[-1] != 10:
+        nl = np.append(nl, buf.size)
+    starts = np.empty(len(nl), dtype=np.int64)
+    starts[0] = 0
+    starts[1:] = nl[:-1] + 1
+    ends = nl.astype(np.int64)
+    # strip trailing '\r'
+    cr = (ends > starts) & (buf[np.maximum(ends - 1, 0)] == 13)
+    ends = ends - cr
+    # drop trailing blank lines
+    nlines = len(starts)
+    while nlines > 0 and ends[nlines - 1] == starts[nlines - 1]:
+        nlines -= 1
+    starts, ends = starts[:nlines], ends[:nlines]
+    if nlines % 4 != 0:
+        raise ValueError("FASTQ is truncated or not in 4-line format")
+    t0, s0, p0, q0 = starts[0::4], starts[1::4], starts[2::4], starts[3::4]
+    t1, s1, p1, q1 = ends[0::4], ends[1::4], ends[2::4], ends[3::4]
+    if np.any(t1 == t0) or np.any(buf[t0] != ord("@")):
+        raise ValueError("Records in Fastq files should start with '@' character")
+    if np.any(p1 == p0) or np.any(buf[p0] != ord("+")):
+        raise ValueError("Expected '+' line in FASTQ record")
+    slen = s1 - s0
+    if np.any((q1 - q0) != slen):
+        raise ValueError("Lengths of sequence and quality values differs")
+    # '+' line may carry the title again; it must then be identical
+    rep = np.flatnonzero((p1 - p0) > 1)
+    for i in rep.tolist():
+        if buf[p0[i] + 1:p1[i]].tobytes().rstrip() != buf[t0[i] + 1:t1[i]].tobytes().rstrip():
+            raise ValueError("Sequence and quality captions differ.")
+    # right-strip titles (Biopython strips the title line)
+    tl = t1 - (t0 + 1)
+    if len(t0):
+        last = buf[np.maximum(t1 - 1, 0)]
+        ws = (tl > 0) & ((last == 32) | (last == 9))
+        while np.any(ws):
+            tl = tl - ws
+            last = buf[np.maximum(t0 + tl, 0)]
+            ws = (tl > 0) & ((last == 32) | (last == 9))
+    # quality range check (ASCII 33..126)
+    batch = FastqBatch(buf, t0 + 1, tl, s0, slen, q0)
+    if len(t0):
+        q, _ = batch.qual_concat()
+        if q.size and (q.min() < 33 or q.max() > 126):
+            raise ValueError("Invalid character in quality string")
+    return batch
+
+
+def read_fastq(path):
+    return parse_bytes(_open_bytes(path))
+
+
+def write_records(fh, batch, keep_idx, lo, hi):
+    """Write records ``keep_idx`` of ``batch`` sliced to [lo:hi) as 4-line FASTQ to binary handle fh."""
+    fh.write(format_records(batch, keep_idx, lo, hi))
+
+
+def format_records(batch, keep_idx, lo, hi):
+    """Vectorised FASTQ text assembly: returns bytes of '@title\\nseq\\n+\\nqual\\n' for each kept record."""
+    keep_idx = np.asarray(keep_idx, dtype=np.int64)
+    n = len(keep_idx)
+    if n == 0:
+        return b""
+    lo = np.asarray(lo, dtype=np.int64)
+    hi = np.asarray(hi, dtype=np.int64)
+    tl = batch.t_len[keep_idx].astype(np.int64)
+    sl = hi - lo
+    rec_len = 1 + tl + 1 + sl + 1 + 2 + sl + 1
+    rec_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(rec_len, out=rec_off[1:])
+    out = np.empty(int(rec_off[-1]), dtype=np.uint8)
+    base = rec_off[:-1]
+    out[base] = ord("@")
+    _scatter(out, base + 1, batch.buf, batch.t_off[keep_idx], tl)
+    p = base + 1 + tl
+    out[p] = 10
+    _scatter(out, p + 1, batch.buf, batch.s_off[keep_idx] + lo, sl)
+    p = p + 1 + sl
+    out[p] = 10
+    out[p + 1] = ord("+")
+    out[p + 2] = 10
+    _scatter(out, p + 3, batch.buf, batch.q_off[keep_idx] + lo, sl)
+    out[p + 3 + sl] = 10
+    return out.tobytes()
+
+
+def _scatter(dst, dst_off, src, src_off, length):
+    total = int(length.sum())
+    if total == 0:
+        return
+    ar = np.arange(total, dtype=np.int64)
+    cs = np.zeros(len(length) + 1, dtype=np.int64)
+    np.cumsum(length, out=cs[1:])
+    within = ar - np.repeat(cs[:-1], length)
+    dst[np.repeat(dst_off, length) + within] = src[np.repeat(src_off.astype(np.int64), length) + within]

@@ -1,0 +1,1072 @@
+/*
+ * ora_hmm.c -- CPU oracle: restatement of `hmmsearch --domtblout -T 10 --F1 1e-6 --F2 1e-6
+ * --F3 1e-6` as invoked by the reference (itsxpress/SeqSample.py:191-209).
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  HMMER (>=3.1b2, verified by the reference
+ * with 3.4) is an un-vendored third-party dependency that is absent from /root/reference;
+ * the algorithm below is restated from the published HMMER3 acceleration pipeline
+ * (MSV filter -> bias filter -> [Viterbi filter, never run when F1==F2] -> Forward ->
+ * Backward -> posterior-heuristic domain definition -> envelope rescoring with null2)
+ * and anchored on SURVEY.md Appendix A.  "parity unpinned" vs a real hmmsearch.
+ *
+ * Numerics: probability (odds-ratio) space fp32 with sparse rescaling (xE > 1e4), like
+ * HMMER's vector implementation; summation over model nodes is in plain ascending-k order
+ * (HMMER's 4-lane striped order differs by fp32 rounding only).  E-value maths in double.
+ */
+#define _GNU_SOURCE
+#include "oracle.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ctype.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define LOG2 0.69314718055994529
+#define NTRANS 7
+enum { T_MM = 0, T_MI, T_MD, T_IM, T_II, T_DM, T_DD };
+enum { EV_MMU = 0, EV_MLAMBDA, EV_VMU, EV_VLAMBDA, EV_FTAU, EV_FLAMBDA };
+
+typedef struct {
+    char   name[192];
+    int    M;
+    float *mat;  /* (M+1)*4 probabilities, row 0 unused */
+    float *t;    /* (M+1)*7 probabilities, row 0 = node 0 (begin) */
+    float  compo[4];
+    int    has_compo;
+    float  ev[6];
+    /* configured search profile (local, multihit), A.3 */
+    float *msc;  /* (M+1)*16 match log-odds (nats) */
+    float *e;    /* (M+1)*16 match odds = expf(msc) */
+    float *bm;   /* (M+2) B->M_k probability, index k */
+    float *tp;   /* (M+2)*7 transition probabilities out of node k (0 for k=0 and k>=M) */
+    /* MSV byte profile, A.4 step 1 */
+    uint8_t *cost; /* (M+1)*16 biased costs */
+    int     bias_b, base_b, tbm_b, tec_b;
+    float   scale_b;
+    /* bias filter 2-state HMM emission odds [code][state] */
+    float   eo[ORA_NCODE][2];
+} prof_t;
+
+struct ora_db {
+    int     n, cap;
+    prof_t *p;
+};
+
+static const int degen_mask[ORA_NCODE] = {1, 2, 4, 8, 5, 10, 3, 12, 6, 9, 11, 14, 7, 13, 15, 0};
+
+/* ------------------------------------------------------------------------ */
+/* p7_FLogsum: table-driven log(e^a + e^b), as HMMER (16000 entries, scale 1000) */
+#define LOGSUM_TBL 16000
+static float flogsum_lookup[LOGSUM_TBL];
+static int   flogsum_ready = 0;
+static void flogsum_init(void)
+{
+    if (flogsum_ready) return;
+    for (int i = 0; i < LOGSUM_TBL; i++)
+        flogsum_lookup[i] = (float)log(1. + exp((double)-i / 1000.0));
+    flogsum_ready = 1;
+}
+float ora_flogsum(float a, float b)
+{
+    flogsum_init();
+    const float max = a > b ? a : b;
+    const float min = a > b ? b : a;
+    return (min == -INFINITY || (max - min) >= 15.7f) ? max : max + flogsum_lookup[(int)((max - min) * 1000.0f)];
+}
+
+/* ------------------------------------------------------------------------ */
+int ora_digitize(const char *seq, int64_t L, uint8_t *dsq)
+{
+    static int8_t map[256];
+    static int    ready = 0;
+    if (!ready) {
+        memset(map, 15, sizeof(map));
+        const char *sym = "ACGTRYMKSWHBVDN";
+        for (int i = 0; sym[i]; i++) {
+            map[(unsigned char)sym[i]]          = (int8_t)i;
+            map[(unsigned char)tolower(sym[i])] = (int8_t)i;
+        }
+        map['U'] = map['u'] = 3;
+        map['X'] = map['x'] = 14;
+        ready = 1;
+    }
+    int bad = 0;
+    for (int64_t i = 0; i < L; i++) {
+        dsq[i] = (uint8_t)map[(unsigned char)seq[i]];
+        if (dsq[i] == 15) bad++;
+    }
+    return bad;
+}
+
+/* ------------------------------------------------------------------------ */
+/* HMMER3/f ASCII parser.  Values are -ln(p); '*' means p = 0.    */
+static float parse_prob(const char *tok)
+{
+    if (tok[0] == '*') return 0.0f;
+    return expf(-1.0f * (float)atof(tok));
+}
+
+static uint8_t unbiased_byteify(const prof_t *pf, float sc)
+{
+    sc = -1.0f * roundf(pf->scale_b * sc);
+    return (sc > 255.f) ? 255 : (uint8_t)sc;
+}
+static uint8_t biased_byteify(const prof_t *pf, float sc)
+{
+    sc = -1.0f * roundf(pf->scale_b * sc);
+    return (sc > 255.f - (float)pf->bias_b) ? 255 : (uint8_t)((uint8_t)sc + pf->bias_b);
+}
+
+static void configure_profile(prof_t *pf)
+{
+    const int M = pf->M;
+    pf->msc  = calloc((size_t)(M + 1) * 16, sizeof(float));
+    pf->e    = calloc((size_t)(M + 1) * 16, sizeof(float));
+    pf->bm   = calloc((size_t)(M + 2), sizeof(float));
+    pf->tp   = calloc((size_t)(M + 2) * 7, sizeof(float));
+    pf->cost = calloc((size_t)(M + 1) * 16, 1);
+
+    /* local entry distribution: occ[k] / sum_i occ[i]*(M-i+1) */
+    float *occ = calloc((size_t)M + 1, sizeof(float));
+    occ[0] = 0.f;
+    occ[1] = pf->t[0 * 7 + T_MI] + pf->t[0 * 7 + T_MM];
+    for (int k = 2; k <= M; k++)
+        occ[k] = occ[k - 1] * (pf->t[(k - 1) * 7 + T_MM] + pf->t[(k - 1) * 7 + T_MI]) +
+                 (1.0f - occ[k - 1]) * pf->t[(k - 1) * 7 + T_DM];
+    float Z = 0.f;
+    for (int k = 1; k <= M; k++) Z += occ[k] * (float)(M - k + 1);
+    for (int k = 1; k <= M; k++) {
+        float sc  = (float)log(occ[k] / Z);
+        pf->bm[k] = expf(sc);
+    }
+    free(occ);
+
+    /* transitions out of nodes 1..M-1 */
+    for (int k = 1; k < M; k++)
+        for (int s = 0; s < 7; s++) {
+            float sc          = (float)log(pf->t[k * 7 + s]);
+            pf->tp[k * 7 + s] = expf(sc);
+        }
+
+    /* match scores, degenerate codes = f-weighted mean of member scores (f uniform) */
+    for (int k = 1; k <= M; k++) {
+        float sc[16];
+        for (int x = 0; x < 4; x++) sc[x] = (float)log((double)pf->mat[k * 4 + x] / 0.25f);
+        for (int x = 4; x < 15; x++) {
+            float result = 0.f, denom = 0.f;
+            for (int y = 0; y < 4; y++)
+                if (degen_mask[x] & (1 << y)) {
+                    result += sc[y] * 0.25f;
+                    denom += 0.25f;
+                }
+            sc[x] = result / denom;
+        }
+        sc[15] = -INFINITY;
+        for (int x = 0; x < 16; x++) {
+            pf->msc[k * 16 + x] = sc[x];
+            pf->e[k * 16 + x]   = expf(sc[x]);
+        }
+    }
+
+    /* MSV byte costs */
+    float max = 0.0f;
+    for (int k = 1; k <= M; k++)
+        for (int x = 0; x < 4; x++)
+            if (pf->msc[k * 16 + x] > max) max = pf->msc[k * 16 + x];
+    pf->scale_b = (float)(3.0 / LOG2);
+    pf->base_b  = 190;
+    pf->bias_b  = 0;
+    pf->bias_b  = unbiased_byteify(pf, -1.0f * max);
+    for (int k = 1; k <= M; k++)
+        for (int x = 0; x < 16; x++) pf->cost[k * 16 + x] = biased_byteify(pf, pf->msc[k * 16 + x]);
+    pf->tbm_b = unbiased_byteify(pf, logf(2.0f / ((float)M * (float)(M + 1))));
+    pf->tec_b = unbiased_byteify(pf, logf(0.5f));
+
+    /* bias-filter HMM emission odds: state 0 = background, state 1 = model composition */
+    for (int x = 0; x < 4; x++) {
+        pf->eo[x][0] = 0.25f / 0.25f;
+        pf->eo[x][1] = pf->compo[x] / 0.25f;
+    }
+    for (int x = 4; x < 15; x++)
+        for (int s = 0; s < 2; s++) {
+            float num = 0.f, denom = 0.f;
+            for (int y = 0; y < 4; y++)
+                if (degen_mask[x] & (1 << y)) {
+                    num += (s == 0) ? 0.25f : pf->compo[y];
+                    denom += 0.25f;
+                }
+            pf->eo[x][s] = (denom > 0.f) ? num / denom : 0.f;
+        }
+    pf->eo[15][0] = pf->eo[15][1] = 1.0f;
+}
+
+static void prof_free(prof_t *pf)
+{
+    free(pf->mat); free(pf->t); free(pf->msc); free(pf->e);
+    free(pf->bm); free(pf->tp); free(pf->cost);
+}
+
+static int name_selected(const char *name, const char *const *prefixes, int nprefix)
+{
+    if (nprefix <= 0 || prefixes == NULL) return 1;
+    for (int i = 0; i < nprefix; i++)
+        if (strncmp(name, prefixes[i], strlen(prefixes[i])) == 0) return 1;
+    return 0;
+}
+
+static int read_floats(char *line, int skip_first, float *out, int n)
+{
+    char *save = NULL;
+    char *tok  = strtok_r(line, " \t\r\n", &save);
+    if (skip_first) tok = strtok_r(NULL, " \t\r\n", &save);
+    for (int i = 0; i < n; i++) {
+        if (!tok) return -1;
+        out[i] = parse_prob(tok);
+        tok    = strtok_r(NULL, " \t\r\n", &save);
+    }
+    return 0;
+}
+
+int ora_db_append(ora_db *db, const char *path, const char *const *prefixes, int nprefix)
+{
+    FILE *fp = fopen(path, "r");
+    if (!fp) return -1;
+    char   *line = NULL;
+    size_t  cap  = 0;
+    prof_t  cur;
+    int     in_rec = 0, added = 0;
+    memset(&cur, 0, sizeof(cur));
+    while (getline(&line, &cap, fp) > 0) {
+        if (strncmp(line, "HMMER3/", 7) == 0) {
+            memset(&cur, 0, sizeof(cur));
+            in_rec = 1;
+            continue;
+        }
+        if (!in_rec) continue;
+        if (strncmp(line, "NAME ", 5) == 0) {
+            char *s = line + 5;
+            while (*s == ' ') s++;
+            size_t n = strcspn(s, "\r\n");
+            while (n > 0 && isspace((unsigned char)s[n - 1])) n--;
+            if (n >= sizeof(cur.name)) n = sizeof(cur.name) - 1;
+            memcpy(cur.name, s, n);
+            cur.name[n] = 0;
+        } else if (strncmp(line, "LENG ", 5) == 0) {
+            cur.M = atoi(line + 5);
+        } else if (strncmp(line, "STATS LOCAL", 11) == 0) {
+            char  kind[32];
+            float a, b;
+            if (sscanf(line + 11, "%31s %f %f", kind, &a, &b) == 3) {
+                if (!strcmp(kind, "MSV")) { cur.ev[EV_MMU] = a; cur.ev[EV_MLAMBDA] = b; }
+                else if (!strcmp(kind, "VITERBI")) { cur.ev[EV_VMU] = a; cur.ev[EV_VLAMBDA] = b; }
+                else if (!strcmp(kind, "FORWARD")) { cur.ev[EV_FTAU] = a; cur.ev[EV_FLAMBDA] = b; }
+            }
+        } else if (strncmp(line, "HMM ", 4) == 0) {
+            /* main model section */
+            const int M = cur.M;
+            cur.mat = calloc((size_t)(M + 1) * 4, sizeof(float));
+            cur.t   = calloc((size_t)(M + 1) * 7, sizeof(float));
+            if (getline(&line, &cap, fp) <= 0) break; /* transition header line */
+            if (getline(&line, &cap, fp) <= 0) break;
+            char *s = line;
+            while (*s == ' ') s++;
+            if (strncmp(s, "COMPO", 5) == 0) {
+                read_floats(line, 1, cur.compo, 4);
+                cur.has_compo = 1;
+                if (getline(&line, &cap, fp) <= 0) break;
+            }
+            /* node 0 insert emissions (ignored: inserts are hard-wired to background) */
+            if (getline(&line, &cap, fp) <= 0) break;
+            read_floats(line, 0, cur.t + 0, 7); /* node 0 transitions */
+            for (int k = 1; k <= M; k++) {
+                if (getline(&line, &cap, fp) <= 0) break;
+                read_floats(line, 1, cur.mat + k * 4, 4);
+                if (getline(&line, &cap, fp) <= 0) break; /* insert emissions */
+                if (getline(&line, &cap, fp) <= 0) break;
+                read_floats(line, 0, cur.t + k * 7, 7);
+            }
+        } else if (strncmp(line, "//", 2) == 0) {
+            if (cur.mat && name_selected(cur.name, prefixes, nprefix)) {
+                if (db->n == db->cap) {
+                    db->cap = db->cap ? db->cap * 2 : 64;
+                    db->p   = realloc(db->p, (size_t)db->cap * sizeof(prof_t));
+                }
+                configure_profile(&cur);
+                db->p[db->n++] = cur;
+                added++;
+            } else {
+                free(cur.mat);
+                free(cur.t);
+            }
+            memset(&cur, 0, sizeof(cur));
+            in_rec = 0;
+        }
+    }
+    free(line);
+    fclose(fp);
+    return added;
+}
+
+ora_db *ora_db_load(const char *path, const char *const *prefixes, int nprefix)
+{
+    ora_db *db = calloc(1, sizeof(*db));
+    if (path && ora_db_append(db, path, prefixes, nprefix) < 0) {
+        free(db);
+        return NULL;
+    }
+    flogsum_init();
+    return db;
+}
+void ora_db_free(ora_db *db)
+{
+    if (!db) return;
+    for (int i = 0; i < db->n; i++) prof_free(&db->p[i]);
+    free(db->p);
+    free(db);
+}
+int         ora_db_count(const ora_db *db) { return db->n; }
+const char *ora_db_name(const ora_db *db, int p) { return db->p[p].name; }
+int         ora_db_M(const ora_db *db, int p) { return db->p[p].M; }
+void        ora_db_evparam(const ora_db *db, int p, float out6[6]) { memcpy(out6, db->p[p].ev, 6 * sizeof(float)); }
+void ora_db_raw(const ora_db *db, int p, float *mat, float *t, float *compo)
+{
+    const prof_t *pf = &db->p[p];
+    memcpy(mat, pf->mat, (size_t)(pf->M + 1) * 4 * sizeof(float));
+    memcpy(t, pf->t, (size_t)(pf->M + 1) * 7 * sizeof(float));
+    memcpy(compo, pf->compo, 4 * sizeof(float));
+}
+void ora_db_msv(const ora_db *db, int p, uint8_t *cost, int *scalars4)
+{
+    const prof_t *pf = &db->p[p];
+    memcpy(cost, pf->cost, (size_t)(pf->M + 1) * 16);
+    scalars4[0] = pf->bias_b; scalars4[1] = pf->base_b; scalars4[2] = pf->tbm_b; scalars4[3] = pf->tec_b;
+}
+
+void ora_default_params(ora_params *prm)
+{
+    prm->T = 10.0f;
+    prm->F1 = prm->F2 = prm->F3 = 1e-6;
+    prm->domE     = 10.0;
+    prm->nthreads = 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* statistics (Easel esl_gumbel_surv / esl_exp_surv / esl_exp_logsurv)           */
+static double gumbel_surv(double x, double mu, double lambda)
+{
+    double y  = lambda * (x - mu);
+    double ey = -exp(-y);
+    if (fabs(ey) < 5e-9) return -ey;
+    return 1 - exp(ey);
+}
+static double exp_surv(double x, double mu, double lambda)
+{
+    if (x < mu) return 1.0;
+    return exp(-lambda * (x - mu));
+}
+static double exp_logsurv(double x, double mu, double lambda)
+{
+    if (x < mu) return 0.0;
+    return -lambda * (x - mu);
+}
+
+float ora_nullsc(int L)
+{
+    float p1 = (float)L / (float)(L + 1);
+    return (float)((float)L * log((double)p1) + log(1. - (double)p1));
+}
+
+/* ------------------------------------------------------------------------ */
+/* A.4 step 1: MSV filter, unsigned-byte saturating arithmetic.  dsq is 0-based here. */
+static float msv_filter(const prof_t *pf, const uint8_t *dsq, int L, int *overflow, int *xJ_out)
+{
+    const int M = pf->M;
+    uint8_t   dp[512];
+    uint8_t  *mp = dp;
+    uint8_t  *heap = NULL;
+    if (M + 1 > 512) mp = heap = malloc((size_t)M + 1);
+    const int tjb  = unbiased_byteify(pf, logf(3.0f / (float)(L + 3)));
+    const int tjbm = (uint8_t)(tjb + pf->tbm_b);
+    const int bias = pf->bias_b, base = pf->base_b, tec = pf->tec_b;
+    for (int k = 0; k <= M; k++) mp[k] = 0;
+    int xJ = 0;
+    int xB = base - tjbm; if (xB < 0) xB = 0;
+    *overflow = 0;
+    for (int i = 0; i < L; i++) {
+        const uint8_t *cost = pf->cost + dsq[i];
+        int xE   = 0;
+        int prev = 0; /* M_{k-1}(i-1); M_0 = -inf = 0 */
+        for (int k = 1; k <= M; k++) {
+            int sv = prev > xB ? prev : xB;
+            sv += bias; if (sv > 255) sv = 255;
+            sv -= cost[k * 16]; if (sv < 0) sv = 0;
+            if (sv > xE) xE = sv;
+            prev  = mp[k];
+            mp[k] = (uint8_t)sv;
+        }
+        if (xE + bias >= 255) {
+            *overflow = 1;
+            if (xJ_out) *xJ_out = -1;
+            free(heap);
+            return INFINITY;
+        }
+        xE -= tec; if (xE < 0) xE = 0;
+        if (xE > xJ) xJ = xE;
+        xB = (base > xJ ? base : xJ) - tjbm; if (xB < 0) xB = 0;
+    }
+    free(heap);
+    if (xJ_out) *xJ_out = xJ;
+    float sc = ((float)(xJ - tjb) - (float)base);
+    sc /= pf->scale_b;
+    sc -= 3.0f;
+    return sc;
+}
+
+/* A.4 step 2: bias filter = 2-state HMM Forward (Easel esl_hmm_Forward semantics) */
+static float bias_filtersc(const prof_t *pf, const uint8_t *dsq, int L)
+{
+    const float L0 = 400.0f, L1 = (float)pf->M / 8.0f;
+    const float t00 = L0 / (L0 + 1.0f), t01 = 1.0f / (L0 + 1.0f);
+    const float t10 = 1.0f / (L1 + 1.0f), t11 = L1 / (L1 + 1.0f);
+    const float pi0 = 0.999f, pi1 = 0.001f;
+    float       logsc = 0.f, max, d0, d1;
+    if (L == 0) return 0.f;
+    d0  = pf->eo[dsq[0]][0] * pi0;
+    d1  = pf->eo[dsq[0]][1] * pi1;
+    max = 0.f;
+    if (d0 > max) max = d0;
+    if (d1 > max) max = d1;
+    d0 /= max; d1 /= max;
+    logsc += (float)log(max);
+    for (int i = 1; i < L; i++) {
+        float n0 = 0.f, n1 = 0.f;
+        n0 += d0 * t00; n0 += d1 * t10;
+        n1 += d0 * t01; n1 += d1 * t11;
+        n0 *= pf->eo[dsq[i]][0];
+        n1 *= pf->eo[dsq[i]][1];
+        max = 0.f;
+        if (n0 > max) max = n0;
+        if (n1 > max) max = n1;
+        d0 = n0 / max; d1 = n1 / max;
+        logsc += (float)log(max);
+    }
+    float end = 0.f;
+    end += d0 * 1.0f;
+    end += d1 * 1.0f;
+    logsc += (float)log(end);
+    float p1 = (float)L / (float)(L + 1);
+    return logsc + (float)L * logf(p1) + logf(1.f - p1);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Forward / Backward in odds space.  Row storage is optional (full != NULL).    */
+typedef struct {
+    float E_move, E_loop, N_loop, N_move; /* N, C, J share loop/move */
+} xf_t;
+
+static xf_t xf_multihit(int L)
+{
+    xf_t  x;
+    float pmove = (2.0f + 1.0f) / ((float)L + 2.0f + 1.0f);
+    x.N_move    = pmove;
+    x.N_loop    = 1.0f - pmove;
+    x.E_move    = expf(-(float)LOG2);
+    x.E_loop    = expf(-(float)LOG2);
+    return x;
+}
+static xf_t xf_unihit(int L)
+{
+    xf_t  x;
+    float pmove = (2.0f + 0.0f) / ((float)L + 2.0f + 0.0f);
+    x.N_move    = pmove;
+    x.N_loop    = 1.0f - pmove;
+    x.E_move    = 1.0f;
+    x.E_loop    = 0.0f;
+    return x;
+}
+
+typedef struct {
+    float *E, *N, *J, *B, *C, *S; /* (L+1) each */
+} specials_t;
+
+static specials_t specials_alloc(int L)
+{
+    specials_t s;
+    float     *buf = malloc((size_t)(L + 1) * 6 * sizeof(float));
+    s.E = buf; s.N = buf + (L + 1); s.J = buf + 2 * (L + 1);
+    s.B = buf + 3 * (L + 1); s.C = buf + 4 * (L + 1); s.S = buf + 5 * (L + 1);
+    return s;
+}
+static void specials_free(specials_t *s) { free(s->E); }
+
+/* dsq points at the first residue of the (sub)sequence; rows are 1..L.
+ * fullM/fullI (optional): (L+1)*(M+1) floats, row-major, for posterior decoding. */
+static float forward_engine(const prof_t *pf, const xf_t *xf, const uint8_t *dsq, int L,
+                            specials_t *sp, float *fullM, float *fullI)
+{
+    const int    M  = pf->M;
+    float       *Mx = calloc((size_t)(M + 2) * 3, sizeof(float));
+    float       *Ix = Mx + (M + 2), *Dx = Ix + (M + 2);
+    const float *tp = pf->tp, *bm = pf->bm;
+    float        xN = 1.f, xJ = 0.f, xC = 0.f, xE = 0.f, xB = xf->N_move;
+    float        totscale = 0.f;
+    sp->E[0] = 0.f; sp->N[0] = 1.f; sp->J[0] = 0.f; sp->B[0] = xB; sp->C[0] = 0.f; sp->S[0] = 1.f;
+    for (int i = 1; i <= L; i++) {
+        const float *er    = pf->e + dsq[i - 1];
+        float        mprev = 0.f, iprev = 0.f, dprev = 0.f; /* row i-1, node k-1 */
+        float        mcur = 0.f, dcur = 0.f;                /* row i,   node k-1 */
+        float        xEm = 0.f, xEd = 0.f;
+        for (int k = 1; k <= M; k++) {
+            const float *tk1 = tp + (k - 1) * 7; /* transitions out of node k-1 */
+            const float *tk  = tp + k * 7;
+            float        sv  = xB * bm[k];
+            sv               = fmaf(mprev, tk1[T_MM], sv);
+            sv               = fmaf(iprev, tk1[T_IM], sv);
+            sv               = fmaf(dprev, tk1[T_DM], sv);
+            sv               = sv * er[k * 16];
+            float dc         = fmaf(dcur, tk1[T_DD], mcur * tk1[T_MD]);
+            float mp = Mx[k], ip = Ix[k], dp = Dx[k];
+            float ic = fmaf(ip, tk[T_II], mp * tk[T_MI]);
+            Mx[k] = sv; Ix[k] = ic; Dx[k] = dc;
+            xEm += sv; xEd += dc;
+            mprev = mp; iprev = ip; dprev = dp;
+            mcur = sv; dcur = dc;
+        }
+        xE = xEm + xEd;
+        xN = xN * xf->N_loop;
+        xC = fmaf(xC, xf->N_loop, xE * xf->E_move);
+        xJ = fmaf(xJ, xf->N_loop, xE * xf->E_loop);
+        xB = fmaf(xJ, xf->N_move, xN * xf->N_move);
+        if (xE > 1.0e4f) {
+            xN = xN / xE; xC = xC / xE; xJ = xJ / xE; xB = xB / xE;
+            float inv = 1.0f / xE;
+            for (int k = 1; k <= M; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
+            sp->S[i] = xE;
+            totscale += (float)log((double)xE);
+            xE = 1.0f;
+        } else sp->S[i] = 1.0f;
+        sp->E[i] = xE; sp->N[i] = xN; sp->J[i] = xJ; sp->B[i] = xB; sp->C[i] = xC;
+        if (fullM) {
+            memcpy(fullM + (size_t)i * (M + 1), Mx, (size_t)(M + 1) * sizeof(float));
+            memcpy(fullI + (size_t)i * (M + 1), Ix, (size_t)(M + 1) * sizeof(float));
+        }
+    }
+    free(Mx);
+    return totscale + (float)log((double)(xC * xf->N_move));
+}
+
+/* Backward.  Uses the Forward scale factors fsp->S.  Writes backward specials to bsp.
+ * If fullM/fullI are given (Forward rows) it accumulates the unnormalised posterior sums
+ * needed by null2-by-expectation: accM[x] (x<4), accI, accN, accC, accJ.            */
+static float backward_engine(const prof_t *pf, const xf_t *xf, const uint8_t *dsq, int L,
+                             const specials_t *fsp, specials_t *bsp,
+                             const float *fullM, const float *fullI, float *acc /*[8]*/)
+{
+    const int    M   = pf->M;
+    float       *Mx  = calloc((size_t)(M + 3) * 4, sizeof(float));
+    float       *Ix  = Mx + (M + 3), *Dx = Ix + (M + 3), *mpe = Dx + (M + 3);
+    const float *tp  = pf->tp, *bm = pf->bm;
+    float        xJ = 0.f, xB = 0.f, xN = 0.f;
+    float        xC = xf->N_move;
+    float        xE = xC * xf->E_move;
+    float        totscale;
+    if (acc) for (int a = 0; a < 8; a++) acc[a] = 0.f;
+
+    /* row L */
+    Dx[M + 1] = 0.f;
+    for (int k = M; k >= 1; k--) {
+        const float *tk = tp + k * 7;
+        Dx[k] = fmaf(tk[T_DD], Dx[k + 1], xE);
+        Mx[k] = fmaf(tk[T_MD], Dx[k + 1], xE);
+        Ix[k] = 0.f;
+    }
+    {
+        float s = fsp->S[L];
+        if (s > 1.0f) {
+            xE = xE / s; xN = xN / s; xC = xC / s; xJ = xJ / s; xB = xB / s;
+            float inv = 1.0f / s;
+            for (int k = 1; k <= M; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
+        }
+        bsp->S[L] = s;
+        totscale  = (float)log((double)s);
+    }
+    bsp->E[L] = xE; bsp->N[L] = xN; bsp->J[L] = xJ; bsp->B[L] = xB; bsp->C[L] = xC;
+
+    for (int i = L; i >= 1; i--) {
+        if (acc) {
+            /* posterior contributions of row i (Forward row i x Backward row i) */
+            const float *fM = fullM + (size_t)i * (M + 1), *fI = fullI + (size_t)i * (M + 1);
+            const float *er = pf->e + dsq[i - 1]; (void)er;
+            float rM[4] = {0.f, 0.f, 0.f, 0.f}, rI = 0.f;
+            for (int k = 1; k <= M; k++) {
+                float pm = fM[k] * Mx[k];
+                rM[0]    = fmaf(pm, pf->e[k * 16 + 0], rM[0]);
+                rM[1]    = fmaf(pm, pf->e[k * 16 + 1], rM[1]);
+                rM[2]    = fmaf(pm, pf->e[k * 16 + 2], rM[2]);
+                rM[3]    = fmaf(pm, pf->e[k * 16 + 3], rM[3]);
+                rI       = fmaf(fI[k], Ix[k], rI);
+            }
+            float w = fsp->S[i];
+            for (int x = 0; x < 4; x++) acc[x] = fmaf(rM[x], w, acc[x]);
+            acc[4] = fmaf(rI, w, acc[4]);
+            acc[5] += fsp->N[i - 1] * xN * xf->N_loop;
+            acc[6] += fsp->C[i - 1] * xC * xf->N_loop;
+            acc[7] += fsp->J[i - 1] * xJ * xf->N_loop;
+        }
+        if (i == 1) break;
+        /* compute row i-1 from row i */
+        const int    r  = i - 1;
+        const float *er = pf->e + dsq[i - 1]; /* residue x_i (row i) */
+        xB = 0.f;
+        for (int k = 1; k <= M; k++) {
+            mpe[k] = Mx[k] * er[k * 16];
+            xB     = fmaf(mpe[k], bm[k], xB);
+        }
+        mpe[M + 1] = 0.f;
+        /* specials (need xB) */
+        xC = xC * xf->N_loop;
+        xJ = fmaf(xB, xf->N_move, xJ * xf->N_loop);
+        xN = fmaf(xB, xf->N_move, xN * xf->N_loop);
+        xE = fmaf(xC, xf->E_move, xJ * xf->E_loop);
+        Dx[M + 1] = 0.f;
+        for (int k = M; k >= 1; k--) {
+            const float *tk    = tp + k * 7;
+            float        mnext = mpe[k + 1];
+            float        ic    = fmaf(mnext, tk[T_IM], Ix[k] * tk[T_II]);
+            float        mc    = fmaf(mnext, tk[T_MM], Ix[k] * tk[T_MI]);
+            float        dc    = mnext * tk[T_DM];
+            dc                 = fmaf(Dx[k + 1], tk[T_DD], dc) + xE;
+            mc                 = fmaf(Dx[k + 1], tk[T_MD], mc) + xE;
+            Mx[k] = mc; Ix[k] = ic; Dx[k] = dc;
+        }
+        float s = fsp->S[r];
+        if (s > 1.0f) {
+            xE = xE / s; xN = xN / s; xC = xC / s; xJ = xJ / s; xB = xB / s;
+            float inv = 1.0f / s;
+            for (int k = 1; k <= M; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
+        }
+        bsp->S[r] = s;
+        totscale += (float)log((double)s);
+        bsp->E[r] = xE; bsp->N[r] = xN; bsp->J[r] = xJ; bsp->B[r] = xB; bsp->C[r] = xC;
+    }
+    /* row 0 */
+    {
+        const float *er = pf->e + dsq[0];
+        xB = 0.f;
+        for (int k = 1; k <= M; k++) xB = fmaf(Mx[k] * er[k * 16], bm[k], xB);
+        xN = fmaf(xB, xf->N_move, xN * xf->N_loop);
+        bsp->B[0] = xB; bsp->C[0] = 0.f; bsp->J[0] = 0.f; bsp->N[0] = xN; bsp->E[0] = 0.f; bsp->S[0] = 1.0f;
+    }
+    free(Mx);
+    return totscale + (float)log((double)xN);
+}
+
+/* p7_DomainDecoding (A.5): btot, etot, mocc from parser specials */
+static void domain_decoding(const xf_t *xf, int L, const specials_t *f, const specials_t *b,
+                            float *btot, float *etot, float *mocc)
+{
+    float scaleproduct = 1.0f / b->N[0];
+    btot[0] = etot[0] = mocc[0] = 0.f;
+    for (int i = 1; i <= L; i++) {
+        btot[i] = btot[i - 1] + (f->B[i - 1] * b->B[i - 1] * f->S[i - 1] * scaleproduct);
+        etot[i] = etot[i - 1] + (f->E[i] * b->E[i] * f->S[i] * scaleproduct);
+        float njcp = f->N[i - 1] * b->N[i] * xf->N_loop * scaleproduct;
+        njcp += f->J[i - 1] * b->J[i] * xf->N_loop * scaleproduct;
+        njcp += f->C[i - 1] * b->C[i] * xf->N_loop * scaleproduct;
+        mocc[i] = 1.f - njcp;
+    }
+}
+
+/* rescore one envelope i..j (1-based on the full sequence) in unihit mode */
+static void rescore_envelope(const prof_t *pf, const uint8_t *dsq, int L, int i, int j,
+                             float *n2sc, ora_dom *dom)
+{
+    const int  M  = pf->M;
+    const int  Ld = j - i + 1;
+    xf_t       xf = xf_unihit(L);
+    specials_t fs = specials_alloc(Ld), bs = specials_alloc(Ld);
+    float     *fM = malloc((size_t)(Ld + 1) * (M + 1) * 2 * sizeof(float));
+    float     *fI = fM + (size_t)(Ld + 1) * (M + 1);
+    float      acc[8];
+    float envsc = forward_engine(pf, &xf, dsq + (i - 1), Ld, &fs, fM, fI);
+    backward_engine(pf, &xf, dsq + (i - 1), Ld, &fs, &bs, fM, fI, acc);
+    float scaleproduct = 1.0f / bs.N[0];
+    float norm         = 1.0f / (float)Ld;
+    float null2[16];
+    float xfactor = (acc[5] + acc[6] + acc[7]) * scaleproduct * norm;
+    float isum    = acc[4] * scaleproduct * norm;
+    for (int x = 0; x < 4; x++) null2[x] = acc[x] * scaleproduct * norm + isum + xfactor;
+    for (int x = 4; x < 15; x++) {
+        float s = 0.f;
+        int   n = 0;
+        for (int y = 0; y < 4; y++)
+            if (degen_mask[x] & (1 << y)) { s += null2[y]; n++; }
+        null2[x] = s / (float)n;
+    }
+    null2[15] = 1.0f;
+    float domcorrection = 0.f;
+    for (int pos = i; pos <= j; pos++) {
+        float v = logf(null2[dsq[pos - 1]]);
+        if (n2sc) n2sc[pos] = v;
+        domcorrection += v;
+    }
+    dom->ienv = i; dom->jenv = j;
+    dom->envsc = envsc;
+    dom->domcorrection = domcorrection;
+    free(fM);
+    specials_free(&fs);
+    specials_free(&bs);
+}
+
+/* ------------------------------------------------------------------------ */
+int ora_pair_run(const ora_db *db, int p, const uint8_t *dsq, int L,
+                 const ora_params *prm, ora_pair *pr, ora_dom *doms, int domcap)
+{
+    const prof_t *pf = &db->p[p];
+    memset(pr, 0, sizeof(*pr));
+    pr->nullsc = ora_nullsc(L);
+    int xJ;
+    pr->usc          = msv_filter(pf, dsq, L, &pr->msv_overflow, &xJ);
+    pr->msv_xJ       = xJ;
+    float seq_score  = (float)((pr->usc - pr->nullsc) / LOG2);
+    pr->P_msv        = gumbel_surv(seq_score, pf->ev[EV_MMU], pf->ev[EV_MLAMBDA]);
+    if (pr->P_msv > prm->F1) return 0;
+    pr->pass_msv = 1;
+
+    pr->filtersc = bias_filtersc(pf, dsq, L);
+    seq_score    = (float)((pr->usc - pr->filtersc) / LOG2);
+    pr->P_bias   = gumbel_surv(seq_score, pf->ev[EV_MMU], pf->ev[EV_MLAMBDA]);
+    if (pr->P_bias > prm->F1) return 0;
+    pr->pass_bias = 1;
+    /* Viterbi filter runs only if P > F2; with F1 == F2 it is never executed (A.4 step 3). */
+    if (pr->P_bias > prm->F2) return 0;
+
+    xf_t       xf = xf_multihit(L);
+    specials_t fs = specials_alloc(L), bs = specials_alloc(L);
+    pr->fwdsc     = forward_engine(pf, &xf, dsq, L, &fs, NULL, NULL);
+    seq_score     = (float)((pr->fwdsc - pr->filtersc) / LOG2);
+    pr->P_fwd     = exp_surv(seq_score, pf->ev[EV_FTAU], pf->ev[EV_FLAMBDA]);
+    if (pr->P_fwd > prm->F3) { specials_free(&fs); specials_free(&bs); return 0; }
+    pr->pass_fwd = 1;
+
+    pr->bcksc = backward_engine(pf, &xf, dsq, L, &fs, &bs, NULL, NULL, NULL);
+
+    float *btot = malloc((size_t)(L + 1) * 4 * sizeof(float));
+    float *etot = btot + (L + 1), *mocc = etot + (L + 1), *n2sc = mocc + (L + 1);
+    domain_decoding(&xf, L, &fs, &bs, btot, etot, mocc);
+    for (int q = 0; q <= L; q++) n2sc[q] = 0.f;
+
+    const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
+    int i = -1, triggered = 0, ndom = 0;
+    for (int j = 1; j <= L; j++) {
+        if (!triggered) {
+            if (mocc[j] - (btot[j] - btot[j - 1]) < rt2) i = j;
+            else if (i == -1) i = j;
+            if (mocc[j] >= rt1) triggered = 1;
+        } else if (mocc[j] - (etot[j] - etot[j - 1]) < rt2) {
+            pr->nregions++;
+            float max = -1.0f;
+            for (int z = i; z <= j; z++) {
+                float a = etot[z] - etot[i - 1], b = btot[j] - btot[z - 1];
+                float expected_n = a < b ? a : b;
+                if (expected_n > max) max = expected_n;
+            }
+            int multi = (max >= rt3);
+            if (multi) pr->nmultidomain++;
+            if (ndom < domcap) {
+                ora_dom *d = &doms[ndom];
+                memset(d, 0, sizeof(*d));
+                /* NOTE: HMMER resolves multidomain regions by stochastic-traceback clustering
+                 * (200 samples, RNG seed 42).  That is not restated; the region is rescored as
+                 * one envelope and flagged (documented deviation). */
+                rescore_envelope(pf, dsq, L, i, j, n2sc, d);
+                d->prof = p;
+                d->is_multidomain = multi;
+                d->dom_idx = ndom;
+                ndom++;
+            }
+            i = -1;
+            triggered = 0;
+        }
+    }
+    pr->ndom = ndom;
+    specials_free(&fs);
+    specials_free(&bs);
+    if (ndom == 0) { free(btot); return 0; }
+
+    /* null2-corrected per-sequence score (A.4 step 6) */
+    float seqbias = 0.f;
+    for (int q = 0; q <= L; q++) seqbias += n2sc[q];
+    free(btot);
+    const float omega = 1.0f / 256.0f;
+    seqbias           = ora_flogsum(0.0f, (float)log((double)omega) + seqbias);
+    float pre_score   = (float)((pr->fwdsc - pr->nullsc) / LOG2);
+    float sscore      = (float)((pr->fwdsc - (pr->nullsc + seqbias)) / LOG2);
+    float sum_score = 0.0f, sbias = 0.0f;
+    int   Ld = 0;
+    for (int d = 0; d < ndom; d++)
+        if (doms[d].envsc - doms[d].domcorrection > 0.0f) {
+            sum_score += doms[d].envsc;
+            Ld += doms[d].jenv - doms[d].ienv + 1;
+            sbias += doms[d].domcorrection;
+        }
+    sbias = ora_flogsum(0.0f, (float)log((double)omega) + sbias);
+    sum_score += (float)((L - Ld) * log((double)((float)L / (float)(L + 3))));
+    float pre2_score = (float)((sum_score - pr->nullsc) / LOG2);
+    sum_score        = (float)((sum_score - (pr->nullsc + sbias)) / LOG2);
+    if (Ld > 0 && sum_score > sscore) { sscore = sum_score; pre_score = pre2_score; }
+    pr->seq_score = sscore;
+    pr->pre_score = pre_score;
+    pr->lnP       = exp_logsurv(sscore, pf->ev[EV_FTAU], pf->ev[EV_FLAMBDA]);
+    pr->reported  = (sscore >= prm->T);
+
+    for (int d = 0; d < ndom; d++) {
+        int   ld = doms[d].jenv - doms[d].ienv + 1;
+        float bs_ = doms[d].envsc + (float)((L - ld) * log((double)((float)L / (float)(L + 3))));
+        doms[d].dombias  = ora_flogsum(0.0f, (float)log((double)omega) + doms[d].domcorrection);
+        doms[d].bitscore = (float)((bs_ - (pr->nullsc + doms[d].dombias)) / LOG2);
+        doms[d].lnP      = exp_logsurv(doms[d].bitscore, pf->ev[EV_FTAU], pf->ev[EV_FLAMBDA]);
+    }
+    return ndom;
+}
+
+/* ------------------------------------------------------------------------ */
+/* stage accessors for parity tests */
+float ora_msv_score(const ora_db *db, int p, const uint8_t *dsq, int L, int *overflow)
+{
+    int ov, xJ;
+    float sc = msv_filter(&db->p[p], dsq, L, &ov, &xJ);
+    if (overflow) *overflow = ov;
+    return sc;
+}
+float ora_bias_filtersc(const ora_db *db, int p, const uint8_t *dsq, int L)
+{
+    return bias_filtersc(&db->p[p], dsq, L);
+}
+float ora_forward_score(const ora_db *db, int p, const uint8_t *dsq, int L)
+{
+    xf_t       xf = xf_multihit(L);
+    specials_t fs = specials_alloc(L);
+    float      sc = forward_engine(&db->p[p], &xf, dsq, L, &fs, NULL, NULL);
+    specials_free(&fs);
+    return sc;
+}
+float ora_backward_score(const ora_db *db, int p, const uint8_t *dsq, int L)
+{
+    xf_t       xf = xf_multihit(L);
+    specials_t fs = specials_alloc(L), bs = specials_alloc(L);
+    forward_engine(&db->p[p], &xf, dsq, L, &fs, NULL, NULL);
+    float sc = backward_engine(&db->p[p], &xf, dsq, L, &fs, &bs, NULL, NULL, NULL);
+    specials_free(&fs);
+    specials_free(&bs);
+    return sc;
+}
+int ora_forward_parser(const ora_db *db, int p, const uint8_t *dsq, int L,
+                       float *xE, float *xN, float *xJ, float *xB, float *xC, float *scale, float *fwdsc)
+{
+    xf_t       xf = xf_multihit(L);
+    specials_t fs = specials_alloc(L);
+    float      sc = forward_engine(&db->p[p], &xf, dsq, L, &fs, NULL, NULL);
+    size_t     n  = (size_t)(L + 1) * sizeof(float);
+    memcpy(xE, fs.E, n); memcpy(xN, fs.N, n); memcpy(xJ, fs.J, n);
+    memcpy(xB, fs.B, n); memcpy(xC, fs.C, n); memcpy(scale, fs.S, n);
+    if (fwdsc) *fwdsc = sc;
+    specials_free(&fs);
+    return 0;
+}
+int ora_domain_decoding(const ora_db *db, int p, const uint8_t *dsq, int L,
+                        float *btot, float *etot, float *mocc)
+{
+    xf_t       xf = xf_multihit(L);
+    specials_t fs = specials_alloc(L), bs = specials_alloc(L);
+    forward_engine(&db->p[p], &xf, dsq, L, &fs, NULL, NULL);
+    backward_engine(&db->p[p], &xf, dsq, L, &fs, &bs, NULL, NULL, NULL);
+    domain_decoding(&xf, L, &fs, &bs, btot, etot, mocc);
+    specials_free(&fs);
+    specials_free(&bs);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+typedef struct {
+    ora_dom *d;
+    int64_t  n, cap;
+} domvec_t;
+
+typedef struct {
+    int32_t seq;
+    int32_t first, ndom;
+    double  lnP;
+} hit_t;
+
+static int hit_cmp(const void *a, const void *b)
+{
+    const hit_t *x = a, *y = b;
+    if (x->lnP < y->lnP) return -1;
+    if (x->lnP > y->lnP) return 1;
+    return (x->seq < y->seq) ? -1 : (x->seq > y->seq);
+}
+
+int64_t ora_search(const ora_db *db, const uint8_t *codes, const int64_t *off, int64_t nseq,
+                   const ora_params *prm, ora_dom **rows_out, int32_t *nreported_per_profile,
+                   ora_stats *stats)
+{
+    const int P = db->n;
+    ora_stats st;
+    memset(&st, 0, sizeof(st));
+    st.npairs_total = (int64_t)P * nseq;
+    int nth = 1;
+#ifdef _OPENMP
+    nth = prm->nthreads > 0 ? prm->nthreads : omp_get_max_threads();
+#endif
+    /* per-profile hit lists, built per thread then merged */
+    domvec_t *tdoms = calloc((size_t)nth, sizeof(domvec_t));
+    typedef struct { hit_t *h; int64_t n, cap; int32_t prof; } hitrec_t;
+    /* hits carry their profile; we bucket afterwards */
+    typedef struct { hit_t h; int32_t prof; int32_t tid; } phit_t;
+    phit_t **thits = calloc((size_t)nth, sizeof(phit_t *));
+    int64_t *thn = calloc((size_t)nth, sizeof(int64_t)), *thcap = calloc((size_t)nth, sizeof(int64_t));
+    int64_t  n_msv = 0, n_bias = 0, n_fwd = 0, n_multi = 0;
+    double   msv_cells = 0, fwd_cells = 0, env_cells = 0;
+    (void)sizeof(hitrec_t);
+
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nth) \
+    reduction(+ : n_msv, n_bias, n_fwd, n_multi, msv_cells, fwd_cells, env_cells)
+    for (int64_t s = 0; s < nseq; s++) {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        const uint8_t *dsq = codes + off[s];
+        const int      L   = (int)(off[s + 1] - off[s]);
+        ora_dom        buf[64];
+        for (int p = 0; p < P; p++) {
+            ora_pair pr;
+            int      nd = ora_pair_run(db, p, dsq, L, prm, &pr, buf, 64);
+            msv_cells += (double)L * db->p[p].M;
+            if (pr.pass_msv) n_msv++;
+            if (pr.pass_bias) { n_bias++; fwd_cells += (double)L * db->p[p].M; }
+            if (pr.pass_fwd) n_fwd++;
+            n_multi += pr.nmultidomain;
+            if (nd > 0 && pr.reported) {
+                domvec_t *dv = &tdoms[tid];
+                if (dv->n + nd > dv->cap) {
+                    dv->cap = (dv->cap ? dv->cap * 2 : 1024) + nd;
+                    dv->d   = realloc(dv->d, (size_t)dv->cap * sizeof(ora_dom));
+                }
+                if (thn[tid] == thcap[tid]) {
+                    thcap[tid] = thcap[tid] ? thcap[tid] * 2 : 1024;
+                    thits[tid] = realloc(thits[tid], (size_t)thcap[tid] * sizeof(phit_t));
+                }
+                phit_t *ph = &thits[tid][thn[tid]++];
+                ph->h.seq = (int32_t)s; ph->h.first = (int32_t)dv->n; ph->h.ndom = nd; ph->h.lnP = pr.lnP;
+                ph->prof = p; ph->tid = tid;
+                for (int d = 0; d < nd; d++) {
+                    buf[d].seq = (int32_t)s;
+                    env_cells += (double)(buf[d].jenv - buf[d].ienv + 1) * db->p[p].M;
+                    dv->d[dv->n++] = buf[d];
+                }
+            }
+        }
+    }
+    st.n_past_msv = n_msv; st.n_past_bias = n_bias; st.n_past_fwd = n_fwd;
+    st.n_multidomain_regions = n_multi;
+    st.msv_cells = msv_cells; st.fwd_cells = fwd_cells; st.bck_cells = 0; st.env_cells = env_cells;
+
+    /* bucket hits per profile */
+    int64_t *cnt = calloc((size_t)P + 1, sizeof(int64_t));
+    int64_t  total_hits = 0;
+    for (int t = 0; t < nth; t++)
+        for (int64_t h = 0; h < thn[t]; h++) { cnt[thits[t][h].prof + 1]++; total_hits++; }
+    for (int p = 0; p < P; p++) cnt[p + 1] += cnt[p];
+    phit_t  *all  = malloc((size_t)(total_hits ? total_hits : 1) * sizeof(phit_t));
+    int64_t *fill = calloc((size_t)P, sizeof(int64_t));
+    for (int t = 0; t < nth; t++)
+        for (int64_t h = 0; h < thn[t]; h++) {
+            int p = thits[t][h].prof;
+            all[cnt[p] + fill[p]++] = thits[t][h];
+        }
+    /* rows */
+    int64_t  ndom_total = 0;
+    for (int t = 0; t < nth; t++) ndom_total += tdoms[t].n;
+    ora_dom *rows = malloc((size_t)(ndom_total ? ndom_total : 1) * sizeof(ora_dom));
+    int64_t  nrows = 0;
+    st.n_reported_pairs = total_hits;
+    st.ndom_total = ndom_total;
+    for (int p = 0; p < P; p++) {
+        int64_t nh   = cnt[p + 1] - cnt[p];
+        double  domZ = (double)nh; /* = nreported for this profile (A.4 step 7) */
+        if (nreported_per_profile) nreported_per_profile[p] = (int32_t)nh;
+        /* sort this profile's hits by lnP ascending, ties by sequence index */
+        hit_t *hs = malloc((size_t)(nh ? nh : 1) * sizeof(hit_t));
+        int32_t *tidv = malloc((size_t)(nh ? nh : 1) * sizeof(int32_t));
+        /* need tid to find domains; encode in a parallel sort via index */
+        int64_t *order = malloc((size_t)(nh ? nh : 1) * sizeof(int64_t));
+        for (int64_t h = 0; h < nh; h++) { hs[h] = all[cnt[p] + h].h; hs[h].first = (int32_t)h; }
+        qsort(hs, (size_t)nh, sizeof(hit_t), hit_cmp);
+        for (int64_t h = 0; h < nh; h++) {
+            const phit_t *ph = &all[cnt[p] + hs[h].first];
+            const ora_dom *src = tdoms[ph->tid].d + ph->h.first;
+            for (int d = 0; d < ph->h.ndom; d++) {
+                ora_dom r = src[d];
+                r.is_reported = (exp(r.lnP) * domZ <= prm->domE);
+                if (r.is_reported) { rows[nrows++] = r; st.ndom_reported++; }
+            }
+        }
+        free(hs); free(tidv); free(order);
+    }
+    for (int t = 0; t < nth; t++) { free(tdoms[t].d); free(thits[t]); }
+    free(tdoms); free(thits); free(thn); free(thcap); free(cnt); free(fill); free(all);
+    if (stats) *stats = st;
+    *rows_out = rows;
+    return nrows;
+}
+
+void ora_free(void *p) { free(p); }
+
+/* ------------------------------------------------------------------------ */
+/* printf("%6.1f") of an fp32 bit score, as integer tenths.  float*10 is exact in double;
+ * glibc rounds exact decimal ties to even, which is what rint() does on the tenths.   */
+int32_t ora_score10(float bits)
+{
+    double t = (double)bits * 10.0;
+    return (int32_t)rint(t);
+}
+
+/* ItsPosition (SeqSample.py:400-498): strict '>' keeps the first row on ties. */
+void ora_itspos(const ora_dom *rows, int64_t nrows, const int8_t *side_of_profile,
+                const int32_t *seqlen, int64_t nseq,
+                int32_t *start, int32_t *stop, int32_t *tlen,
+                int32_t *left_score10, int32_t *left_from, int32_t *left_to,
+                int32_t *right_score10, int32_t *right_from, int32_t *right_to)
+{
+    for (int64_t s = 0; s < nseq; s++) {
+        start[s] = stop[s] = tlen[s] = -1;
+        left_score10[s] = right_score10[s] = INT32_MIN;
+        left_from[s] = left_to[s] = right_from[s] = right_to[s] = -1;
+    }
+    for (int64_t r = 0; r < nrows; r++) {
+        const ora_dom *d = &rows[r];
+        int side = side_of_profile[d->prof];
+        if (side < 0) continue;
+        int32_t sc = ora_score10(d->bitscore);
+        int64_t s  = d->seq;
+        if (side == 0) {
+            if (left_score10[s] == INT32_MIN || sc > left_score10[s]) {
+                if (left_score10[s] == INT32_MIN) tlen[s] = seqlen[s];
+                left_score10[s] = sc; left_from[s] = d->ienv; left_to[s] = d->jenv;
+            }
+        } else {
+            if (right_score10[s] == INT32_MIN || sc > right_score10[s]) {
+                if (right_score10[s] == INT32_MIN) tlen[s] = seqlen[s];
+                right_score10[s] = sc; right_from[s] = d->ienv; right_to[s] = d->jenv;
+            }
+        }
+    }
+    for (int64_t s = 0; s < nseq; s++) {
+        if (left_score10[s] != INT32_MIN) start[s] = left_to[s];
+        if (right_score10[s] != INT32_MIN) stop[s] = right_from[s] - 1;
+    }
+}
