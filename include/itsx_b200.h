@@ -1,0 +1,193 @@
+/*
+ * itsx_b200.h -- C ABI of libitsx_b200.so, the B200 (sm_100a) implementation of the ITSxpress
+ * hot path:  exact dereplication -> profile-HMM search -> boundary selection -> trim/re-expand.
+ *
+ * Every entry point below replaces one process boundary / Python loop of the reference
+ * (citations are into the upstream tree, itsxpress/...):
+ *
+ *   itsx_profiles_*      create_runtime_hmm()                       main.py:176-231
+ *                        + hmmsearch's own reading of that file     SeqSample.py:191-209
+ *   itsx_derep*          `vsearch --fastx_uniques --strand both`    SeqSample.py:93-131 (argv :106-116)
+ *                        + Dedup.parse (read -> representative)     SeqSample.py:542-562
+ *   itsx_search*         `hmmsearch --domtblout -T 10 --F1 1e-6 --F2 1e-6 --F3 1e-6`
+ *                                                                  SeqSample.py:178-225 (argv :191-209)
+ *   itsx_hits            the domtbl rows ItsPosition.parse consumes SeqSample.py:431-461 (cols :445-450)
+ *   itsx_positions       ItsPosition._score / get_position          SeqSample.py:400-429, 463-498
+ *   itsx_trim_*          Dedup._get_trimmed_seq_generator /         SeqSample.py:792-884
+ *                        Dedup._get_paired_seq_generator            SeqSample.py:564-711
+ *
+ * Conventions: plain C, no callbacks, no exceptions across the boundary.  Functions return
+ * 0 on success and a negative ITSX_E* code on failure; itsx_last_error() gives the text.
+ * Host buffers are caller-owned; device memory is library-owned behind itsx_ctx (one ctx per
+ * host thread / per GPU).  There is NO CPU fallback: without a usable CUDA device
+ * itsx_create() fails with ITSX_ENODEV.
+ */
+#ifndef ITSX_B200_H
+#define ITSX_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ITSX_OK        0
+#define ITSX_ENODEV   -1   /* no CUDA device / wrong architecture */
+#define ITSX_ECUDA    -2   /* CUDA runtime error (text in itsx_last_error) */
+#define ITSX_EINVAL   -3   /* bad argument / call order */
+#define ITSX_EIO      -4   /* cannot read a profile file */
+#define ITSX_ECOLLIDE -5   /* unresolvable 64-bit key collision in derep (two independent hashes) */
+#define ITSX_ELIMIT   -6   /* a fixed capacity was exceeded (domains per hit, model length) */
+
+#define ITSX_MAXM      45  /* longest profile the DP kernels hold in registers (all ITSx_db profiles) */
+#define ITSX_MAXDOM     8  /* envelopes kept per (sequence, profile) hit */
+
+typedef struct itsx_ctx itsx_ctx;
+
+/* hmmsearch thresholds as the reference passes them (SeqSample.py:191-209) */
+typedef struct {
+    float  T;        /* -T 10        per-sequence bit-score threshold              */
+    double F1;       /* --F1 1e-6    MSV + bias filter P-value                      */
+    double F2;       /* --F2 1e-6    Viterbi filter (never runs when F1 == F2)      */
+    double F3;       /* --F3 1e-6    Forward filter P-value                         */
+    double domE;     /* 10.0         per-domain conditional E-value (hmmsearch default) */
+} itsx_search_params;
+
+/* one domtbl-equivalent row (only the fields ItsPosition reads, plus diagnostics) */
+typedef struct {
+    int32_t seq;           /* index of the target among the searched (unique) sequences */
+    int32_t prof;          /* index of the profile in load order (= runtime HMM file order) */
+    int32_t ienv, jenv;    /* env from / env to, 1-based inclusive  (domtbl cols 19, 20) */
+    int32_t tlen;          /* target length                         (domtbl col 2) */
+    int32_t dom_idx;       /* 0-based index of the domain within its hit */
+    float   bitscore;      /* domain bit score                      (domtbl col 13, before %.1f) */
+    float   envsc;         /* envelope Forward score, nats */
+    float   domcorrection; /* null2 correction, nats */
+    float   seq_score;     /* per-sequence bit score of the hit */
+    double  lnP;           /* ln P-value of the domain score */
+    double  seq_lnP;       /* ln P-value of the hit (row order key within a profile) */
+    int32_t is_multidomain;/* region was flagged multidomain (kept as one envelope) */
+    int32_t reported;      /* passes -T and domE (rows returned by itsx_hits always have 1) */
+} itsx_dom_row;
+
+/* counters of the last itsx_search (for GCUPS accounting and parity tests) */
+typedef struct {
+    int64_t n_seq, n_prof, n_pairs;
+    int64_t n_past_msv, n_past_bias, n_past_fwd, n_hits_reported;
+    int64_t n_domains, n_domains_reported, n_multidomain_regions, n_dom_overflow;
+    double  msv_cells, bias_rows, fwd_cells, bck_cells, env_cells;   /* DP cells actually computed */
+    /* device time per stage, milliseconds, CUDA events on the library's stream */
+    float   ms_msv, ms_bias, ms_fwd, ms_bck, ms_env, ms_final, ms_total;
+} itsx_search_stats;
+
+typedef struct {
+    int64_t n_reads, n_unique, n_collided;     /* n_collided: reads resolved by the second hash */
+    int64_t bytes_ascii;                       /* sequence bytes hashed */
+    float   ms_pack, ms_hash, ms_insert, ms_verify, ms_compact, ms_total;
+} itsx_derep_stats;
+
+/* ---- context ---------------------------------------------------------------------- */
+int  itsx_create(int device, itsx_ctx **out);
+void itsx_destroy(itsx_ctx *ctx);
+const char *itsx_last_error(const itsx_ctx *ctx);   /* ctx may be NULL: error of the last failed create */
+int  itsx_device_info(const itsx_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, int64_t *mem_bytes);
+void *itsx_stream(const itsx_ctx *ctx);             /* the cudaStream_t all work is enqueued on */
+int  itsx_sync(itsx_ctx *ctx);
+/* page-locked host staging buffers (for callers that want DMA-able inputs/outputs) */
+void *itsx_pinned_alloc(size_t bytes);
+void itsx_pinned_free(void *p);
+
+/* ---- profiles: replaces create_runtime_hmm + hmmsearch's file reader --------------- */
+int  itsx_profiles_clear(itsx_ctx *ctx);
+/* Append the profiles of a HMMER3/f ASCII file whose NAME starts with one of `prefixes`
+ * (nprefix == 0: all), in file order (main.py:217-229).  Returns the number appended. */
+int  itsx_profiles_append_file(itsx_ctx *ctx, const char *path, const char *const *prefixes, int nprefix);
+int  itsx_profiles_count(const itsx_ctx *ctx);
+const char *itsx_profile_name(const itsx_ctx *ctx, int p);
+int  itsx_profile_M(const itsx_ctx *ctx, int p);
+/* side[p]: 0 = left-boundary profile, 1 = right-boundary profile, -1 = ignored
+ * (ItsPosition's prefix dispatch, SeqSample.py:388-398). */
+int  itsx_profiles_set_sides(itsx_ctx *ctx, const int8_t *side, int n);
+/* configured MSV byte profile for parity tests: cost[(M+1)*16], scalars {bias, base, tbm, tec} */
+int  itsx_profile_msv(const itsx_ctx *ctx, int p, uint8_t *cost, int32_t *scalars4);
+
+/* ---- dereplication ------------------------------------------------------------------ */
+/* seq: reads packed back to back (ASCII, any case, IUPAC allowed); off[nreads+1].
+ * rep_index[i] = index of the first read of i's class {s, revcomp(s)}; strand[i] = 0 '+', 1 '-'
+ * (either output pointer may be NULL).  The reads and their representatives stay resident on
+ * the device for itsx_search / itsx_trim_*. */
+int  itsx_derep(itsx_ctx *ctx, const uint8_t *seq, const int64_t *off, int64_t nreads,
+                int32_t *rep_index, uint8_t *strand, int64_t *n_unique);
+/* clusters in first-occurrence order: first_read[u], abundance[u], u < n_unique */
+int  itsx_derep_clusters(itsx_ctx *ctx, int32_t *first_read, int32_t *abundance);
+int  itsx_derep_get_stats(const itsx_ctx *ctx, itsx_derep_stats *st);
+/* test hook: keep only the low `bits` bits of the 64-bit key (forces collisions); 64 = normal */
+int  itsx_derep_set_key_bits(itsx_ctx *ctx, int bits);
+
+/* ---- profile-HMM search --------------------------------------------------------------- */
+void itsx_search_default_params(itsx_search_params *prm);
+/* search the representatives of the last itsx_derep (device resident) */
+int  itsx_search(itsx_ctx *ctx, const itsx_search_params *prm);
+/* search caller-supplied sequences (the `_search(rep.fa)` entry): ASCII, off[nseq+1] */
+int  itsx_search_seqs(itsx_ctx *ctx, const uint8_t *seq, const int64_t *off, int64_t nseq,
+                      const itsx_search_params *prm);
+int  itsx_search_get_stats(const itsx_ctx *ctx, itsx_search_stats *st);
+/* reported rows in hmmsearch order (profile; ln P of the hit, then sequence index; domain
+ * position).  rows may be NULL to query *n. */
+int  itsx_hits(itsx_ctx *ctx, itsx_dom_row *rows, int64_t cap, int64_t *n);
+int  itsx_nreported(itsx_ctx *ctx, int32_t *per_profile);           /* domZ per profile */
+/* ItsPosition per searched sequence; -1 encodes None.  Any pointer may be NULL.
+ * score10 = the "%.1f"-printed score in integer tenths (INT32_MIN when absent). */
+int  itsx_positions(itsx_ctx *ctx, int32_t *start, int32_t *stop, int32_t *tlen,
+                    int32_t *left_score10, int32_t *left_from, int32_t *left_to,
+                    int32_t *right_score10, int32_t *right_from, int32_t *right_to);
+
+/* multi-GPU: add other ranks' per-profile reported-hit counts (domZ is global per hmmsearch
+ * run) between itsx_search_stage1 and itsx_search_stage2.  itsx_search == stage1 + stage2. */
+int  itsx_search_stage1(itsx_ctx *ctx, const itsx_search_params *prm);
+int  itsx_search_seqs_stage1(itsx_ctx *ctx, const uint8_t *seq, const int64_t *off, int64_t nseq,
+                             const itsx_search_params *prm);
+int  itsx_search_shard(itsx_ctx *ctx, int64_t first_unique, int64_t n_unique_local); /* restrict to a slice */
+int  itsx_nreported_set(itsx_ctx *ctx, const int32_t *per_profile_global);
+int  itsx_search_stage2(itsx_ctx *ctx);
+/* install a position table computed elsewhere (all-gathered shards / a test fixture) */
+int  itsx_positions_set(itsx_ctx *ctx, const int32_t *start, const int32_t *stop, const int32_t *tlen,
+                        int64_t n);
+
+/* ---- trim + re-expansion ---------------------------------------------------------------- */
+/* mode: 0 = single-end / merged record[start:stop]           (SeqSample.py:862)
+ *       2 = paired R1  [start:stop] or [start:] if stop>tlen  (SeqSample.py:639-645)
+ *       1 = paired R2  [tlen-stop : tlen-start]               (SeqSample.py:640,648-655)
+ * Bounds for every read of the last itsx_derep in input order; keep[i] = 1 iff the read's
+ * representative has both boundaries and start < stop (SeqSample.py:814-825).
+ * off_other: offsets of the R1/R2 file being sliced when it is not the dereplicated one
+ * (NULL: slice the dereplicated reads themselves).  Returns the number kept in *n_kept. */
+int  itsx_trim_bounds(itsx_ctx *ctx, int mode, const int64_t *off_other, int64_t nreads,
+                      uint8_t *keep, int32_t *lo, int32_t *hi, int64_t *n_kept);
+/* gather the kept slices of (seq, qual) into back-to-back output buffers on the device and copy
+ * them out: out_off[n_kept+1], out_seq/out_qual sized >= total (query with NULLs first via
+ * *total).  seq/qual: the records being sliced (host), off: their offsets. */
+int  itsx_trim_gather(itsx_ctx *ctx, int mode, const uint8_t *seq, const uint8_t *qual, const int64_t *off,
+                      int64_t nreads, int64_t *n_kept, int64_t *total,
+                      int32_t *kept_index, int64_t *out_off, uint8_t *out_seq, uint8_t *out_qual);
+
+/* ---- whole path, host buffers in / host buffers out (the call bench.py's e2e leg times) -- */
+typedef struct {
+    int64_t n_reads, n_unique, n_kept, out_bytes;
+    float   ms_h2d, ms_derep, ms_search, ms_trim, ms_d2h, ms_total;
+} itsx_run_stats;
+/* derep + search + positions + single-end trim.  Outputs: rep_index[nreads], keep[nreads],
+ * lo[nreads], hi[nreads] (any may be NULL). */
+int  itsx_run(itsx_ctx *ctx, const uint8_t *seq, const int64_t *off, int64_t nreads,
+              const itsx_search_params *prm, int32_t *rep_index, uint8_t *keep, int32_t *lo, int32_t *hi,
+              itsx_run_stats *st);
+/* the same with the reads already resident (uploaded by itsx_reads_upload): kernels only */
+int  itsx_reads_upload(itsx_ctx *ctx, const uint8_t *seq, const int64_t *off, int64_t nreads);
+int  itsx_run_resident(itsx_ctx *ctx, const itsx_search_params *prm, itsx_run_stats *st);
+/* number of kernel launches issued by this ctx so far (bench.py's gpu_launches) */
+int64_t itsx_launch_count(const itsx_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,386 @@
+"""ctypes binding of libitsx_b200.so (C ABI: include/itsx_b200.h).
+
+The library is the product: if it is missing or no B200 is present the calls below raise -- there
+is no CPU fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libitsx_b200.so")
+_LIB = None
+
+MAXM = 45
+MAXDOM = 8
+
+
+class ItsxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libitsx_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class SearchParams(C.Structure):
+    _fields_ = [("T", C.c_float), ("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double), ("domE", C.c_double)]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("n_seq", "n_prof", "n_pairs", "n_past_msv", "n_past_bias", "n_past_fwd",
+                                          "n_hits_reported", "n_domains", "n_domains_reported",
+                                          "n_multidomain_regions", "n_dom_overflow")] + \
+               [(n, C.c_double) for n in ("msv_cells", "bias_rows", "fwd_cells", "bck_cells", "env_cells")] + \
+               [(n, C.c_float) for n in ("ms_msv", "ms_bias", "ms_fwd", "ms_bck", "ms_env", "ms_final", "ms_total")]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class DerepStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("n_reads", "n_unique", "n_collided", "bytes_ascii")] + \
+               [(n, C.c_float) for n in ("ms_pack", "ms_hash", "ms_insert", "ms_verify", "ms_compact", "ms_total")]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class RunStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("n_reads", "n_unique", "n_kept", "out_bytes")] + \
+               [(n, C.c_float) for n in ("ms_h2d", "ms_derep", "ms_search", "ms_trim", "ms_d2h", "ms_total")]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+ROW_DTYPE = np.dtype([
+    ("seq", "<i4"), ("prof", "<i4"), ("ienv", "<i4"), ("jenv", "<i4"), ("tlen", "<i4"), ("dom_idx", "<i4"),
+    ("bitscore", "<f4"), ("envsc", "<f4"), ("domcorrection", "<f4"), ("seq_score", "<f4"),
+    ("lnP", "<f8"), ("seq_lnP", "<f8"), ("is_multidomain", "<i4"), ("reported", "<i4"),
+])
+
+# every symbol include/itsx_b200.h declares (tests check that the .so exports all of them)
+SYMBOLS = [
+    "itsx_create", "itsx_destroy", "itsx_last_error", "itsx_device_info", "itsx_stream", "itsx_sync",
+    "itsx_pinned_alloc", "itsx_pinned_free",
+    "itsx_profiles_clear", "itsx_profiles_append_file", "itsx_profiles_count", "itsx_profile_name", "itsx_profile_M",
+    "itsx_profiles_set_sides", "itsx_profile_msv",
+    "itsx_derep", "itsx_derep_clusters", "itsx_derep_get_stats", "itsx_derep_set_key_bits",
+    "itsx_search_default_params", "itsx_search", "itsx_search_seqs", "itsx_search_get_stats", "itsx_hits",
+    "itsx_nreported", "itsx_positions", "itsx_search_stage1", "itsx_search_seqs_stage1", "itsx_search_shard",
+    "itsx_nreported_set", "itsx_search_stage2", "itsx_positions_set",
+    "itsx_trim_bounds", "itsx_trim_gather", "itsx_run", "itsx_reads_upload", "itsx_run_resident",
+    "itsx_launch_count",
+]
+
+
+def lib():
+    """Load the shared library (built in-tree by itsxpress_b200.build)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libitsx_b200.so is not built: run `python -m itsxpress_b200.build` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.itsx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.itsx_destroy.argtypes = [vp]
+    L.itsx_destroy.restype = None
+    L.itsx_last_error.argtypes = [vp]
+    L.itsx_last_error.restype = C.c_char_p
+    L.itsx_device_info.argtypes = [vp, vp, vp, vp, vp]
+    L.itsx_stream.argtypes = [vp]
+    L.itsx_stream.restype = vp
+    L.itsx_sync.argtypes = [vp]
+    L.itsx_pinned_alloc.argtypes = [C.c_size_t]
+    L.itsx_pinned_alloc.restype = vp
+    L.itsx_pinned_free.argtypes = [vp]
+    L.itsx_pinned_free.restype = None
+    L.itsx_profiles_clear.argtypes = [vp]
+    L.itsx_profiles_append_file.argtypes = [vp, C.c_char_p, C.POINTER(C.c_char_p), C.c_int]
+    L.itsx_profiles_count.argtypes = [vp]
+    L.itsx_profile_name.argtypes = [vp, C.c_int]
+    L.itsx_profile_name.restype = C.c_char_p
+    L.itsx_profile_M.argtypes = [vp, C.c_int]
+    L.itsx_profiles_set_sides.argtypes = [vp, vp, C.c_int]
+    L.itsx_profile_msv.argtypes = [vp, C.c_int, vp, vp]
+    L.itsx_derep.argtypes = [vp, vp, vp, i64, vp, vp, vp]
+    L.itsx_derep_clusters.argtypes = [vp, vp, vp]
+    L.itsx_derep_get_stats.argtypes = [vp, C.POINTER(DerepStats)]
+    L.itsx_derep_set_key_bits.argtypes = [vp, C.c_int]
+    L.itsx_search_default_params.argtypes = [C.POINTER(SearchParams)]
+    L.itsx_search_default_params.restype = None
+    L.itsx_search.argtypes = [vp, C.POINTER(SearchParams)]
+    L.itsx_search_seqs.argtypes = [vp, vp, vp, i64, C.POINTER(SearchParams)]
+    L.itsx_search_get_stats.argtypes = [vp, C.POINTER(SearchStats)]
+    L.itsx_hits.argtypes = [vp, vp, i64, vp]
+    L.itsx_nreported.argtypes = [vp, vp]
+    L.itsx_positions.argtypes = [vp] + [vp] * 9
+    L.itsx_search_stage1.argtypes = [vp, C.POINTER(SearchParams)]
+    L.itsx_search_seqs_stage1.argtypes = [vp, vp, vp, i64, C.POINTER(SearchParams)]
+    L.itsx_search_shard.argtypes = [vp, i64, i64]
+    L.itsx_nreported_set.argtypes = [vp, vp]
+    L.itsx_search_stage2.argtypes = [vp]
+    L.itsx_positions_set.argtypes = [vp, vp, vp, vp, i64]
+    L.itsx_trim_bounds.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp]
+    L.itsx_trim_gather.argtypes = [vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    L.itsx_run.argtypes = [vp, vp, vp, i64, C.POINTER(SearchParams), vp, vp, vp, vp, C.POINTER(RunStats)]
+    L.itsx_reads_upload.argtypes = [vp, vp, vp, i64]
+    L.itsx_run_resident.argtypes = [vp, C.POINTER(SearchParams), C.POINTER(RunStats)]
+    L.itsx_launch_count.argtypes = [vp]
+    L.itsx_launch_count.restype = i64
+    _LIB = L
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def default_params():
+    prm = SearchParams()
+    lib().itsx_search_default_params(C.byref(prm))
+    return prm
+
+
+class PinnedBuffer:
+    """Page-locked host memory (cudaHostAlloc) viewed as numpy arrays; freed on close()/collection."""
+
+    def __init__(self, nbytes):
+        self.nbytes = max(1, int(nbytes))
+        self.ptr = lib().itsx_pinned_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("cudaHostAlloc failed")
+        self._buf = (C.c_char * self.nbytes).from_address(self.ptr)
+
+    def array(self, dtype=np.uint8, count=None, offset=0):
+        dtype = np.dtype(dtype)
+        if count is None:
+            count = (self.nbytes - offset) // dtype.itemsize
+        return np.frombuffer(self._buf, dtype=dtype, count=int(count), offset=int(offset))
+
+    def close(self):
+        if self.ptr:
+            lib().itsx_pinned_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU context (one per process / per device)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().itsx_create(int(device), C.byref(self._h))
+        if rc != 0:
+            raise ItsxError(rc, lib().itsx_last_error(None).decode())
+        self.device = device
+        self.names = []
+
+    def close(self):
+        if self._h:
+            lib().itsx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc < 0:
+            raise ItsxError(rc, lib().itsx_last_error(self._h).decode())
+        return rc
+
+    def device_info(self):
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        mem = C.c_int64()
+        self._chk(lib().itsx_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), mem_bytes=mem.value)
+
+    @property
+    def stream(self):
+        return lib().itsx_stream(self._h)
+
+    def sync(self):
+        self._chk(lib().itsx_sync(self._h))
+
+    def launch_count(self):
+        return int(lib().itsx_launch_count(self._h))
+
+    # ---- profiles --------------------------------------------------------------------------
+    def load_profiles(self, paths, prefixes=None, skip_missing=True):
+        """Profiles of the given HMMER3 files whose NAME starts with a prefix, in file order."""
+        L = lib()
+        self._chk(L.itsx_profiles_clear(self._h))
+        pre = [p.encode() for p in (prefixes or [])]
+        arr = (C.c_char_p * max(1, len(pre)))(*pre) if pre else None
+        if isinstance(paths, (str, bytes)):
+            paths = [paths]
+        for p in paths:
+            if skip_missing and not os.path.exists(p):
+                continue
+            self._chk(L.itsx_profiles_append_file(self._h, os.fsencode(p), arr, len(pre)))
+        n = L.itsx_profiles_count(self._h)
+        self.names = [L.itsx_profile_name(self._h, i).decode() for i in range(n)]
+        return n
+
+    def profile_M(self, p):
+        return lib().itsx_profile_M(self._h, p)
+
+    def set_sides(self, side):
+        side = np.ascontiguousarray(side, dtype=np.int8)
+        self._chk(lib().itsx_profiles_set_sides(self._h, _p(side), len(side)))
+
+    def set_sides_by_prefix(self, left_prefix, right_prefix):
+        side = np.full(len(self.names), -1, np.int8)
+        for i, nm in enumerate(self.names):
+            if nm.startswith(left_prefix):
+                side[i] = 0
+            elif nm.startswith(right_prefix):
+                side[i] = 1
+        self.set_sides(side)
+        return side
+
+    def profile_msv(self, p):
+        M = self.profile_M(p)
+        cost = np.zeros((M + 1, 16), np.uint8)
+        sc = np.zeros(4, np.int32)
+        self._chk(lib().itsx_profile_msv(self._h, p, _p(cost), _p(sc)))
+        return cost, dict(bias=int(sc[0]), base=int(sc[1]), tbm=int(sc[2]), tec=int(sc[3]))
+
+    # ---- derep ------------------------------------------------------------------------------
+    def derep(self, seq, off):
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        n = len(off) - 1
+        rep = np.empty(n, np.int32)
+        strand = np.empty(n, np.uint8)
+        nu = C.c_int64()
+        self._chk(lib().itsx_derep(self._h, _p(seq), _p(off), n, _p(rep), _p(strand), C.byref(nu)))
+        return rep, strand, int(nu.value)
+
+    def derep_clusters(self, n_unique):
+        first = np.empty(n_unique, np.int32)
+        ab = np.empty(n_unique, np.int32)
+        self._chk(lib().itsx_derep_clusters(self._h, _p(first), _p(ab)))
+        return first, ab
+
+    def derep_stats(self):
+        st = DerepStats()
+        self._chk(lib().itsx_derep_get_stats(self._h, C.byref(st)))
+        return st
+
+    def set_key_bits(self, bits):
+        self._chk(lib().itsx_derep_set_key_bits(self._h, int(bits)))
+
+    # ---- search -----------------------------------------------------------------------------
+    def search(self, params=None):
+        self._chk(lib().itsx_search(self._h, C.byref(params) if params is not None else None))
+
+    def search_seqs(self, seq, off, params=None):
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        self._nseq = len(off) - 1
+        self._chk(lib().itsx_search_seqs(self._h, _p(seq), _p(off), len(off) - 1,
+                                         C.byref(params) if params is not None else None))
+
+    def search_stage1(self, params=None):
+        self._chk(lib().itsx_search_stage1(self._h, C.byref(params) if params is not None else None))
+
+    def search_shard(self, first, n):
+        self._chk(lib().itsx_search_shard(self._h, int(first), int(n)))
+
+    def nreported(self):
+        out = np.zeros(max(1, len(self.names)), np.int32)
+        self._chk(lib().itsx_nreported(self._h, _p(out)))
+        return out[:len(self.names)]
+
+    def nreported_set(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.int32)
+        self._chk(lib().itsx_nreported_set(self._h, _p(arr)))
+
+    def search_stage2(self):
+        self._chk(lib().itsx_search_stage2(self._h))
+
+    def search_stats(self):
+        st = SearchStats()
+        self._chk(lib().itsx_search_get_stats(self._h, C.byref(st)))
+        return st
+
+    def hits(self):
+        n = C.c_int64()
+        self._chk(lib().itsx_hits(self._h, None, 0, C.byref(n)))
+        rows = np.zeros(n.value, dtype=ROW_DTYPE)
+        if n.value:
+            self._chk(lib().itsx_hits(self._h, _p(rows), n.value, C.byref(n)))
+        return rows
+
+    def positions(self, n):
+        names = ["start", "stop", "tlen", "left_score10", "left_from", "left_to", "right_score10", "right_from",
+                 "right_to"]
+        out = {k: np.empty(n, np.int32) for k in names}
+        self._chk(lib().itsx_positions(self._h, *[_p(out[k]) for k in names]))
+        return out
+
+    def positions_set(self, start, stop, tlen):
+        start, stop, tlen = (np.ascontiguousarray(a, dtype=np.int32) for a in (start, stop, tlen))
+        self._chk(lib().itsx_positions_set(self._h, _p(start), _p(stop), _p(tlen), len(start)))
+
+    # ---- trim -------------------------------------------------------------------------------
+    def trim_bounds(self, nreads, mode=0, off_other=None):
+        keep = np.empty(nreads, np.uint8)
+        lo = np.empty(nreads, np.int32)
+        hi = np.empty(nreads, np.int32)
+        nk = C.c_int64()
+        o = None if off_other is None else np.ascontiguousarray(off_other, dtype=np.int64)
+        self._chk(lib().itsx_trim_bounds(self._h, mode, _p(o), nreads, _p(keep), _p(lo), _p(hi), C.byref(nk)))
+        return keep, lo, hi, int(nk.value)
+
+    def trim_gather(self, nreads, mode=0, seq=None, qual=None, off=None):
+        """Returns (kept_index, out_off, out_seq, out_qual) with the slices packed back to back."""
+        nk, tot = C.c_int64(), C.c_int64()
+        seq = None if seq is None else np.ascontiguousarray(seq, dtype=np.uint8)
+        qual = None if qual is None else np.ascontiguousarray(qual, dtype=np.uint8)
+        off = None if off is None else np.ascontiguousarray(off, dtype=np.int64)
+        L = lib()
+        self._chk(L.itsx_trim_gather(self._h, mode, _p(seq), _p(qual), _p(off), nreads, C.byref(nk), C.byref(tot),
+                                     None, None, None, None))
+        ki = np.empty(nk.value, np.int32)
+        oo = np.empty(nk.value + 1, np.int64)
+        os_ = np.empty(tot.value, np.uint8)
+        oq = np.empty(tot.value, np.uint8) if qual is not None else None
+        self._chk(L.itsx_trim_gather(self._h, mode, _p(seq), _p(qual), _p(off), nreads, C.byref(nk), C.byref(tot),
+                                     _p(ki), _p(oo), _p(os_), _p(oq)))
+        return ki, oo, os_, oq
+
+    # ---- whole path ---------------------------------------------------------------------------
+    def run(self, seq, off, params=None, out=None):
+        """derep + search + positions + single-end trim bounds from host buffers."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        n = len(off) - 1
+        if out is None:
+            out = dict(rep=np.empty(n, np.int32), keep=np.empty(n, np.uint8), lo=np.empty(n, np.int32),
+                       hi=np.empty(n, np.int32))
+        st = RunStats()
+        self._chk(lib().itsx_run(self._h, _p(seq), _p(off), n, C.byref(params) if params is not None else None,
+                                 _p(out["rep"]), _p(out["keep"]), _p(out["lo"]), _p(out["hi"]), C.byref(st)))
+        return out, st
+
+    def reads_upload(self, seq, off):
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        self._chk(lib().itsx_reads_upload(self._h, _p(seq), _p(off), len(off) - 1))
+
+    def run_resident(self, params=None):
+        st = RunStats()
+        self._chk(lib().itsx_run_resident(self._h, C.byref(params) if params is not None else None, C.byref(st)))
+        return st

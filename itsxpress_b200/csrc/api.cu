@@ -1,0 +1,597 @@
+// api.cu -- the extern "C" surface of libitsx_b200.so (declared in include/itsx_b200.h): context,
+// profile loading, host<->device staging and the glue between the stage implementations in
+// derep.cu / search.cu / trim.cu.  No compute happens on the host: a missing or non-sm_100 device
+// makes itsx_create fail (there is no CPU fallback).
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include "itsx_internal.h"
+
+static thread_local std::string g_create_err;
+
+DevBuf::~DevBuf()
+{
+    if (p) cudaFree(p);
+}
+cudaError_t DevBuf::ensure(size_t bytes, bool keep, cudaStream_t st)
+{
+    if (bytes <= cap && p) return cudaSuccess;
+    size_t ncap = std::max(bytes, cap + cap / 2);
+    ncap = (ncap + 255) & ~(size_t)255;
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, ncap);
+    if (e != cudaSuccess) return e;
+    if (p) {
+        if (keep && cap) {
+            e = cudaMemcpyAsync(q, p, cap, cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) { cudaFree(q); return e; }
+        }
+        cudaFree(p);
+    }
+    p = q;
+    cap = ncap;
+    return cudaSuccess;
+}
+
+#define CHECK_CTX(c) do { if (!(c)) return ITSX_EINVAL; } while (0)
+
+extern "C" {
+
+int itsx_create(int device, itsx_ctx **out)
+{
+    if (!out) return ITSX_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return ITSX_ENODEV;
+    }
+    if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return ITSX_EINVAL; }
+    cudaDeviceProp pr;
+    if ((e = cudaGetDeviceProperties(&pr, device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return ITSX_ECUDA; }
+    if (pr.major != 10) {
+        g_create_err = "libitsx_b200 is built for sm_100a only; device is sm_" + std::to_string(pr.major * 10 + pr.minor);
+        return ITSX_ENODEV;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return ITSX_ECUDA; }
+    itsx_ctx *c = new itsx_ctx();
+    c->device = device;
+    c->sm_count = pr.multiProcessorCount;
+    c->cc_major = pr.major;
+    c->cc_minor = pr.minor;
+    c->mem_total = pr.totalGlobalMem;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        delete c;
+        return ITSX_ECUDA;
+    }
+    itsx_search_default_params(&c->prm);
+    *out = c;
+    return ITSX_OK;
+}
+
+void itsx_destroy(itsx_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto s : c->lanes) cudaStreamDestroy(s);
+    for (auto e : c->lane_ev) cudaEventDestroy(e);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *itsx_last_error(const itsx_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int itsx_device_info(const itsx_ctx *c, int *sm_count, int *cc_major, int *cc_minor, int64_t *mem_bytes)
+{
+    CHECK_CTX(c);
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    if (mem_bytes) *mem_bytes = (int64_t)c->mem_total;
+    return ITSX_OK;
+}
+void *itsx_stream(const itsx_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int itsx_sync(itsx_ctx *c)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ITSX_OK;
+}
+int64_t itsx_launch_count(const itsx_ctx *c) { return c ? c->launches : 0; }
+
+void *itsx_pinned_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void itsx_pinned_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// ---- profiles -------------------------------------------------------------------------------
+int itsx_profiles_clear(itsx_ctx *c)
+{
+    CHECK_CTX(c);
+    c->prof.clear();
+    c->side.clear();
+    c->prof_dirty = true;
+    return ITSX_OK;
+}
+int itsx_profiles_append_file(itsx_ctx *c, const char *path, const char *const *prefixes, int nprefix)
+{
+    CHECK_CTX(c);
+    if (!path) return ITSX_EINVAL;
+    int n = hmmfile_append(path, prefixes, nprefix, c->prof, c->err);
+    if (n < 0) return n;
+    for (size_t p = c->prof.size() - n; p < c->prof.size(); p++)
+        if (c->prof[p].M > ITSX_MAXM) {
+            c->err = "profile '" + c->prof[p].name + "' is longer than ITSX_MAXM";
+            c->prof.resize(c->prof.size() - n);
+            return ITSX_ELIMIT;
+        }
+    c->side.resize(c->prof.size(), -1);
+    c->prof_dirty = true;
+    return n;
+}
+int itsx_profiles_count(const itsx_ctx *c) { return c ? (int)c->prof.size() : 0; }
+const char *itsx_profile_name(const itsx_ctx *c, int p)
+{
+    return (c && p >= 0 && p < (int)c->prof.size()) ? c->prof[p].name.c_str() : nullptr;
+}
+int itsx_profile_M(const itsx_ctx *c, int p) { return (c && p >= 0 && p < (int)c->prof.size()) ? c->prof[p].M : -1; }
+int itsx_profiles_set_sides(itsx_ctx *c, const int8_t *side, int n)
+{
+    CHECK_CTX(c);
+    if (n != (int)c->prof.size()) { c->err = "set_sides: length differs from the profile count"; return ITSX_EINVAL; }
+    c->side.assign(side, side + n);
+    c->prof_dirty = true;
+    return ITSX_OK;
+}
+int itsx_profile_msv(const itsx_ctx *c, int p, uint8_t *cost, int32_t *sc)
+{
+    CHECK_CTX(c);
+    if (p < 0 || p >= (int)c->prof.size()) return ITSX_EINVAL;
+    const HostProfile &h = c->prof[p];
+    if (cost) memcpy(cost, h.cost.data(), h.cost.size());
+    if (sc) { sc[0] = h.bias_b; sc[1] = h.base_b; sc[2] = h.tbm_b; sc[3] = h.tec_b; }
+    return ITSX_OK;
+}
+
+// ---- reads / derep ---------------------------------------------------------------------------
+int itsx_reads_upload(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64_t nreads)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (nreads < 0 || (nreads > 0 && (!seq || !off))) { c->err = "reads_upload: null buffer"; return ITSX_EINVAL; }
+    const int64_t total = nreads ? off[nreads] : 0;
+    if (nreads && off[0] != 0) { c->err = "reads_upload: off[0] must be 0"; return ITSX_EINVAL; }
+    c->nreads = nreads;
+    c->total_bases = total;
+    c->n_unique = 0;
+    c->pos_valid = false;
+    const size_t padded = ((size_t)total + 15) / 16 * 16 + 32;
+    CUDA_TRY(c, c->d_ascii.ensure(padded));
+    CUDA_TRY(c, c->d_off.ensure((size_t)(nreads + 1) * 8));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_ascii.as<uint8_t>() + (size_t)total / 16 * 16, 'A', padded - (size_t)total / 16 * 16, c->stream));
+    if (total) CUDA_TRY(c, cudaMemcpyAsync(c->d_ascii.p, seq, (size_t)total, cudaMemcpyHostToDevice, c->stream));
+    if (nreads) CUDA_TRY(c, cudaMemcpyAsync(c->d_off.p, off, (size_t)(nreads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    else CUDA_TRY(c, cudaMemsetAsync(c->d_off.p, 0, 8, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ITSX_OK;
+}
+
+int itsx_derep(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64_t nreads,
+               int32_t *rep_index, uint8_t *strand, int64_t *n_unique)
+{
+    CHECK_CTX(c);
+    int rc = itsx_reads_upload(c, seq, off, nreads);
+    if (rc) return rc;
+    rc = derep_run(c);
+    if (rc) return rc;
+    if (nreads) {
+        if (rep_index) CUDA_TRY(c, cudaMemcpyAsync(rep_index, c->d_rep.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (strand) CUDA_TRY(c, cudaMemcpyAsync(strand, c->d_strand.p, (size_t)nreads, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    if (n_unique) *n_unique = c->n_unique;
+    // the representatives become the search set
+    c->shard_first = 0;
+    c->shard_n = -1;
+    return search_build_seqs_from_derep(c);
+}
+
+__global__ void abund_gather_kernel(const int32_t *__restrict__ first, const int32_t *__restrict__ abund_by_read,
+                                    int64_t nu, int32_t *__restrict__ out)
+{
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < nu) out[u] = abund_by_read[first[u]];
+}
+
+int itsx_derep_clusters(itsx_ctx *c, int32_t *first_read, int32_t *abundance)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int64_t nu = c->n_unique;
+    if (nu == 0) return ITSX_OK;
+    if (first_read) CUDA_TRY(c, cudaMemcpyAsync(first_read, c->d_first.p, (size_t)nu * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (abundance) {
+        CUDA_TRY(c, c->d_list.ensure((size_t)nu * 4));
+        abund_gather_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, c->stream>>>(c->d_first.as<int32_t>(), c->d_abund.as<int32_t>(), nu,
+                                                                                  c->d_list.as<int32_t>());
+        c->launches++;
+        CUDA_TRY(c, cudaMemcpyAsync(abundance, c->d_list.p, (size_t)nu * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ITSX_OK;
+}
+int itsx_derep_get_stats(const itsx_ctx *c, itsx_derep_stats *st)
+{
+    CHECK_CTX(c);
+    if (st) *st = c->dstats;
+    return ITSX_OK;
+}
+int itsx_derep_set_key_bits(itsx_ctx *c, int bits)
+{
+    CHECK_CTX(c);
+    if (bits < 1 || bits > 64) return ITSX_EINVAL;
+    c->key_bits = bits;
+    return ITSX_OK;
+}
+
+// ---- search ------------------------------------------------------------------------------------
+void itsx_search_default_params(itsx_search_params *prm)
+{
+    prm->T = 10.0f;
+    prm->F1 = prm->F2 = prm->F3 = 1e-6;
+    prm->domE = 10.0;
+}
+static int set_params(itsx_ctx *c, const itsx_search_params *prm)
+{
+    if (prm) c->prm = *prm;
+    else itsx_search_default_params(&c->prm);
+    if (c->prm.F2 < c->prm.F1) {
+        // the Viterbi filter would run for F1 < P <= ... only when F2 < F1; the reference never asks for it
+        c->err = "search: F2 < F1 (Viterbi filter stage) is not supported; the reference passes F1 == F2";
+        return ITSX_EINVAL;
+    }
+    return ITSX_OK;
+}
+int itsx_search_stage1(itsx_ctx *c, const itsx_search_params *prm)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = set_params(c, prm);
+    if (rc) return rc;
+    return search_stage1(c);
+}
+int itsx_search_seqs_stage1(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64_t nseq,
+                            const itsx_search_params *prm)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = set_params(c, prm);
+    if (rc) return rc;
+    rc = search_build_seqs_from_host(c, seq, off, nseq);
+    if (rc) return rc;
+    return search_stage1(c);
+}
+int itsx_search_shard(itsx_ctx *c, int64_t first_unique, int64_t n_local)
+{
+    CHECK_CTX(c);
+    c->shard_first = first_unique;
+    c->shard_n = n_local;
+    return ITSX_OK;
+}
+int itsx_nreported(itsx_ctx *c, int32_t *per_profile)
+{
+    CHECK_CTX(c);
+    if (!c->stage1_done) { c->err = "nreported before search"; return ITSX_EINVAL; }
+    if (per_profile) memcpy(per_profile, c->h_nrep.data(), c->h_nrep.size() * 4);
+    return ITSX_OK;
+}
+int itsx_nreported_set(itsx_ctx *c, const int32_t *g)
+{
+    CHECK_CTX(c);
+    if (!c->stage1_done) { c->err = "nreported_set before search stage1"; return ITSX_EINVAL; }
+    c->h_nrep.assign(g, g + c->prof.size());
+    return ITSX_OK;
+}
+int itsx_search_stage2(itsx_ctx *c)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return search_stage2(c);
+}
+int itsx_search(itsx_ctx *c, const itsx_search_params *prm)
+{
+    int rc = itsx_search_stage1(c, prm);
+    if (rc) return rc;
+    return itsx_search_stage2(c);
+}
+int itsx_search_seqs(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64_t nseq, const itsx_search_params *prm)
+{
+    int rc = itsx_search_seqs_stage1(c, seq, off, nseq, prm);
+    if (rc) return rc;
+    return itsx_search_stage2(c);
+}
+int itsx_search_get_stats(const itsx_ctx *c, itsx_search_stats *st)
+{
+    CHECK_CTX(c);
+    if (st) *st = c->sstats;
+    return ITSX_OK;
+}
+
+int itsx_hits(itsx_ctx *c, itsx_dom_row *rows, int64_t cap, int64_t *n)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->stage2_done) { c->err = "hits before search"; return ITSX_EINVAL; }
+    std::vector<DomRec> h((size_t)c->ndom);
+    if (c->ndom) {
+        CUDA_TRY(c, cudaMemcpyAsync(h.data(), c->d_doms.p, (size_t)c->ndom * sizeof(DomRec), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    std::vector<int64_t> idx;
+    idx.reserve(h.size());
+    for (int64_t i = 0; i < (int64_t)h.size(); i++)
+        if (h[i].pair_reported & 2) idx.push_back(i);
+    // hmmsearch row order: profile; hit ln P ascending, then target index; domain position
+    std::sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) {
+        const DomRec &x = h[a], &y = h[b];
+        if (x.prof != y.prof) return x.prof < y.prof;
+        if (x.seq_lnP != y.seq_lnP) return x.seq_lnP < y.seq_lnP;
+        if (x.seq != y.seq) return x.seq < y.seq;
+        return x.dom_idx < y.dom_idx;
+    });
+    if (n) *n = (int64_t)idx.size();
+    if (rows) {
+        const int64_t m = std::min<int64_t>(cap, (int64_t)idx.size());
+        for (int64_t i = 0; i < m; i++) {
+            const DomRec &r = h[idx[i]];
+            itsx_dom_row &o = rows[i];
+            o.seq = r.seq; o.prof = r.prof; o.ienv = r.ienv; o.jenv = r.jenv; o.tlen = r.tlen; o.dom_idx = r.dom_idx;
+            o.bitscore = r.bitscore; o.envsc = r.envsc; o.domcorrection = r.domcorrection; o.seq_score = r.seq_score;
+            o.lnP = r.lnP; o.seq_lnP = r.seq_lnP; o.is_multidomain = r.is_multidomain; o.reported = 1;
+        }
+    }
+    return ITSX_OK;
+}
+
+int itsx_positions(itsx_ctx *c, int32_t *start, int32_t *stop, int32_t *tlen,
+                   int32_t *lsc, int32_t *lfrom, int32_t *lto, int32_t *rsc, int32_t *rfrom, int32_t *rto)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->pos_valid) { c->err = "positions before search"; return ITSX_EINVAL; }
+    int32_t *outs[9] = {start, stop, tlen, lsc, lfrom, lto, rsc, rfrom, rto};
+    const int64_t n = c->npos;
+    if (n == 0) return ITSX_OK;
+    for (int k = 0; k < 9; k++)
+        if (outs[k])
+            CUDA_TRY(c, cudaMemcpyAsync(outs[k], c->d_pos.as<int32_t>() + (size_t)k * n, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ITSX_OK;
+}
+
+int itsx_positions_set(itsx_ctx *c, const int32_t *start, const int32_t *stop, const int32_t *tlen, int64_t n)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (n < 0 || (n && (!start || !stop || !tlen))) return ITSX_EINVAL;
+    c->npos = n;
+    CUDA_TRY(c, c->d_pos.ensure((size_t)std::max<int64_t>(n, 1) * 9 * 4));
+    if (n) {
+        CUDA_TRY(c, cudaMemsetAsync(c->d_pos.p, 0xff, (size_t)n * 9 * 4, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_pos.as<int32_t>(), start, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_pos.as<int32_t>() + n, stop, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_pos.as<int32_t>() + 2 * n, tlen, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    c->pos_valid = true;
+    return ITSX_OK;
+}
+
+// ---- trim ------------------------------------------------------------------------------------------
+static int check_trim(itsx_ctx *c, int mode, int64_t nreads)
+{
+    if (mode < 0 || mode > 2) { c->err = "trim: mode must be 0, 1 or 2"; return ITSX_EINVAL; }
+    if (nreads != c->nreads) { c->err = "trim: read count differs from the dereplicated set"; return ITSX_EINVAL; }
+    if (c->npos != c->n_unique) { c->err = "trim: position table does not cover every unique sequence"; return ITSX_EINVAL; }
+    return ITSX_OK;
+}
+
+int itsx_trim_bounds(itsx_ctx *c, int mode, const int64_t *off_other, int64_t nreads,
+                     uint8_t *keep, int32_t *lo, int32_t *hi, int64_t *n_kept)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = check_trim(c, mode, nreads);
+    if (rc) return rc;
+    static thread_local DevBuf t_off, t_keep, t_lo, t_hi;
+    CUDA_TRY(c, t_keep.ensure((size_t)nreads + 16));
+    CUDA_TRY(c, t_lo.ensure((size_t)nreads * 4 + 16));
+    CUDA_TRY(c, t_hi.ensure((size_t)nreads * 4 + 16));
+    const int64_t *d_off = nullptr;
+    if (off_other) {
+        CUDA_TRY(c, t_off.ensure((size_t)(nreads + 1) * 8));
+        CUDA_TRY(c, cudaMemcpyAsync(t_off.p, off_other, (size_t)(nreads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        d_off = t_off.as<int64_t>();
+    }
+    rc = trim_bounds_dev(c, mode, d_off, nreads, t_keep.as<uint8_t>(), t_lo.as<int32_t>(), t_hi.as<int32_t>(), n_kept);
+    if (rc) return rc;
+    if (nreads) {
+        if (keep) CUDA_TRY(c, cudaMemcpyAsync(keep, t_keep.p, (size_t)nreads, cudaMemcpyDeviceToHost, c->stream));
+        if (lo) CUDA_TRY(c, cudaMemcpyAsync(lo, t_lo.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (hi) CUDA_TRY(c, cudaMemcpyAsync(hi, t_hi.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    return ITSX_OK;
+}
+
+int itsx_trim_gather(itsx_ctx *c, int mode, const uint8_t *seq, const uint8_t *qual, const int64_t *off,
+                     int64_t nreads, int64_t *n_kept, int64_t *total,
+                     int32_t *kept_index, int64_t *out_off, uint8_t *out_seq, uint8_t *out_qual)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = check_trim(c, mode, nreads);
+    if (rc) return rc;
+    if (!n_kept || !total) return ITSX_EINVAL;
+    static thread_local DevBuf t_off, t_seq, t_qual, t_keep, t_lo, t_hi, t_ki, t_oo, t_os, t_oq;
+    cudaStream_t st = c->stream;
+    const bool query = !out_seq && !out_off && !kept_index;
+    CUDA_TRY(c, t_keep.ensure((size_t)nreads + 16));
+    CUDA_TRY(c, t_lo.ensure((size_t)nreads * 4 + 16));
+    CUDA_TRY(c, t_hi.ensure((size_t)nreads * 4 + 16));
+    const int64_t *d_off = nullptr;
+    const int64_t tot_in = (off && nreads) ? off[nreads] : 0;
+    if (off) {
+        CUDA_TRY(c, t_off.ensure((size_t)(nreads + 1) * 8));
+        CUDA_TRY(c, cudaMemcpyAsync(t_off.p, off, (size_t)(nreads + 1) * 8, cudaMemcpyHostToDevice, st));
+        d_off = t_off.as<int64_t>();
+    }
+    int64_t nk = 0;
+    rc = trim_bounds_dev(c, mode, d_off, nreads, t_keep.as<uint8_t>(), t_lo.as<int32_t>(), t_hi.as<int32_t>(), &nk);
+    if (rc) return rc;
+    if (query) {
+        int64_t tot = 0;
+        if (nreads) {
+            CUDA_TRY(c, cudaMemcpyAsync(&tot, c->d_list2.as<int64_t>() + nreads, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaStreamSynchronize(st));
+        }
+        *n_kept = nk;
+        *total = tot;
+        return ITSX_OK;
+    }
+    const uint8_t *d_seq = c->d_ascii.as<uint8_t>();
+    const uint8_t *d_qual = nullptr;
+    if (seq) {
+        CUDA_TRY(c, t_seq.ensure((size_t)tot_in + 16));
+        if (tot_in) CUDA_TRY(c, cudaMemcpyAsync(t_seq.p, seq, (size_t)tot_in, cudaMemcpyHostToDevice, st));
+        d_seq = t_seq.as<uint8_t>();
+    }
+    if (qual) {
+        const int64_t tq = off ? tot_in : c->total_bases;
+        CUDA_TRY(c, t_qual.ensure((size_t)tq + 16));
+        if (tq) CUDA_TRY(c, cudaMemcpyAsync(t_qual.p, qual, (size_t)tq, cudaMemcpyHostToDevice, st));
+        d_qual = t_qual.as<uint8_t>();
+    }
+    rc = trim_gather_dev(c, d_seq, d_qual, d_off ? d_off : c->d_off.as<int64_t>(), nreads, t_keep.as<uint8_t>(),
+                         t_lo.as<int32_t>(), t_hi.as<int32_t>(), n_kept, total, t_ki, t_oo, t_os, t_oq);
+    if (rc) return rc;
+    if (kept_index && *n_kept) CUDA_TRY(c, cudaMemcpyAsync(kept_index, t_ki.p, (size_t)*n_kept * 4, cudaMemcpyDeviceToHost, st));
+    if (out_off) CUDA_TRY(c, cudaMemcpyAsync(out_off, t_oo.p, (size_t)(*n_kept + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (out_seq && *total) CUDA_TRY(c, cudaMemcpyAsync(out_seq, t_os.p, (size_t)*total, cudaMemcpyDeviceToHost, st));
+    if (out_qual && d_qual && *total) CUDA_TRY(c, cudaMemcpyAsync(out_qual, t_oq.p, (size_t)*total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return ITSX_OK;
+}
+
+// ---- whole path ------------------------------------------------------------------------------------------
+static int run_device_part(itsx_ctx *c, const itsx_search_params *prm, itsx_run_stats *rs, DevBuf &keep, DevBuf &lo,
+                           DevBuf &hi, cudaEvent_t *ev)
+{
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, cudaEventRecord(ev[1], st));
+    int rc = derep_run(c);
+    if (rc) return rc;
+    c->shard_first = 0;
+    c->shard_n = -1;
+    rc = search_build_seqs_from_derep(c);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaEventRecord(ev[2], st));
+    rc = set_params(c, prm);
+    if (rc) return rc;
+    rc = search_stage1(c);
+    if (rc) return rc;
+    rc = search_stage2(c);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaEventRecord(ev[3], st));
+    const int64_t n = c->nreads;
+    CUDA_TRY(c, keep.ensure((size_t)n + 16));
+    CUDA_TRY(c, lo.ensure((size_t)n * 4 + 16));
+    CUDA_TRY(c, hi.ensure((size_t)n * 4 + 16));
+    int64_t nk = 0;
+    rc = trim_bounds_dev(c, 0, nullptr, n, keep.as<uint8_t>(), lo.as<int32_t>(), hi.as<int32_t>(), &nk);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaEventRecord(ev[4], st));
+    rs->n_reads = n;
+    rs->n_unique = c->n_unique;
+    rs->n_kept = nk;
+    if (n) {
+        int64_t tot = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&tot, c->d_list2.as<int64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        rs->out_bytes = tot;
+    }
+    return ITSX_OK;
+}
+
+int itsx_run(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64_t nreads, const itsx_search_params *prm,
+             int32_t *rep_index, uint8_t *keep, int32_t *lo, int32_t *hi, itsx_run_stats *out)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    static thread_local DevBuf t_keep, t_lo, t_hi;
+    itsx_run_stats rs{};
+    cudaEvent_t ev[6];
+    for (auto &e : ev) CUDA_TRY(c, cudaEventCreate(&e));
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, cudaEventRecord(ev[0], st));
+    int rc = itsx_reads_upload(c, seq, off, nreads);
+    if (!rc) rc = run_device_part(c, prm, &rs, t_keep, t_lo, t_hi, ev);
+    if (!rc && nreads) {
+        if (rep_index) CUDA_TRY(c, cudaMemcpyAsync(rep_index, c->d_rep.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, st));
+        if (keep) CUDA_TRY(c, cudaMemcpyAsync(keep, t_keep.p, (size_t)nreads, cudaMemcpyDeviceToHost, st));
+        if (lo) CUDA_TRY(c, cudaMemcpyAsync(lo, t_lo.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, st));
+        if (hi) CUDA_TRY(c, cudaMemcpyAsync(hi, t_hi.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (!rc) {
+        CUDA_TRY(c, cudaEventRecord(ev[5], st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&rs.ms_h2d, ev[0], ev[1]);
+        cudaEventElapsedTime(&rs.ms_derep, ev[1], ev[2]);
+        cudaEventElapsedTime(&rs.ms_search, ev[2], ev[3]);
+        cudaEventElapsedTime(&rs.ms_trim, ev[3], ev[4]);
+        cudaEventElapsedTime(&rs.ms_d2h, ev[4], ev[5]);
+        cudaEventElapsedTime(&rs.ms_total, ev[0], ev[5]);
+        if (out) *out = rs;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+int itsx_run_resident(itsx_ctx *c, const itsx_search_params *prm, itsx_run_stats *out)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    static thread_local DevBuf t_keep, t_lo, t_hi;
+    itsx_run_stats rs{};
+    cudaEvent_t ev[6];
+    for (auto &e : ev) CUDA_TRY(c, cudaEventCreate(&e));
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, cudaEventRecord(ev[0], st));
+    int rc = run_device_part(c, prm, &rs, t_keep, t_lo, t_hi, ev);
+    if (!rc) {
+        CUDA_TRY(c, cudaEventRecord(ev[5], st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&rs.ms_derep, ev[1], ev[2]);
+        cudaEventElapsedTime(&rs.ms_search, ev[2], ev[3]);
+        cudaEventElapsedTime(&rs.ms_trim, ev[3], ev[4]);
+        cudaEventElapsedTime(&rs.ms_total, ev[0], ev[5]);
+        if (out) *out = rs;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,1459 @@
+// search.cu -- profile-HMM search cascade on the GPU.
+//
+// Replaces `hmmsearch --domtblout -T 10 --F1 1e-6 --F2 1e-6 --F3 1e-6 --tformat fasta <hmm> rep.fa`
+// (reference call site itsxpress/SeqSample.py:178-225, argv :191-209) and ItsPosition's best-boundary
+// selection over the resulting table (SeqSample.py:400-429, 463-498).  Algorithm: SURVEY.md
+// Appendix A (HMMER3 acceleration pipeline restated).
+//
+// Mapping.  Every profile in ITSx_db has M <= 45 match states, so one (sequence, profile) comparison
+// is small: a whole DP row lives in ONE thread's registers.  All DP kernels are therefore
+// thread-per-pair with fully unrolled node loops -- no shuffles, no shared-memory DP rows:
+//   msv_kernel    u8-range MSV filter in s16x2 lanes (VIADDMNMX / VIMNMX3 DPX instructions), cost
+//                 tables of a tile of profiles staged once in shared memory, grid = sequence blocks x
+//                 profile tiles.  Integer-ALU bound.
+//   bias_kernel   2-state composition-bias Forward on MSV survivors.
+//   fb_kernel     fp32 Forward -> F3 test -> Backward -> posterior decoding -> region/envelope
+//                 definition, one launch per profile so that the transition coefficients are a
+//                 __grid_constant__ argument: every FFMA takes its coefficient from the constant bank
+//                 and the inner loop has no load except the per-residue emission (shared memory).
+//                 Parser specials go to a per-resident-warp scratch slab that stays in L2.
+//   env_kernel    unihit Forward/Backward/decoding of each envelope, null2 by expectation.
+//   final_kernel  per-hit and per-domain bit scores, P-values, -T threshold, reported-hit counts.
+//   select/best   domE threshold with the global domZ, ItsPosition arg-max per (sequence, side).
+// Floating-point order follows oracle/ora_hmm.c operation for operation (explicit fmaf, -fmad=false)
+// so that envelope coordinates -- thresholded fp32 posteriors -- are reproduced exactly.
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "itsx_internal.h"
+
+namespace {
+
+constexpr int MAXM = ITSX_MAXM;
+constexpr int KP = ITSX_KP;
+constexpr int MSV_TP = 32;                 // profiles per MSV tile (32 * 23 * 16 * 4 B = 47 KB smem)
+constexpr int MSV_THREADS = 128;
+constexpr int FB_THREADS = 128;
+constexpr int SPEC_C = 5;                  // parser specials kept per row
+constexpr int ENV_ROWF = 2 * (MAXM + 1) + 4;   // floats per envelope row: M[0..45], I[0..45], Eraw, N, J, C
+constexpr double kLn2 = 0.69314718055994529;
+
+inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// statistics (Easel esl_gumbel_surv / esl_exp_surv / esl_exp_logsurv)
+__device__ __forceinline__ double gumbel_surv(double x, double mu, double lambda)
+{
+    double y = lambda * (x - mu);
+    double ey = -exp(-y);
+    if (fabs(ey) < 5e-9) return -ey;
+    return 1 - exp(ey);
+}
+__device__ __forceinline__ double exp_surv(double x, double mu, double lambda)
+{
+    if (x < mu) return 1.0;
+    return exp(-lambda * (x - mu));
+}
+__device__ __forceinline__ double exp_logsurv(double x, double mu, double lambda)
+{
+    if (x < mu) return 0.0;
+    return -lambda * (x - mu);
+}
+__device__ __forceinline__ float flogsum(const float *__restrict__ tbl, float a, float b)
+{
+    const float mx = a > b ? a : b, mn = a > b ? b : a;
+    return (mn == -INFINITY || (mx - mn) >= 15.7f) ? mx : mx + tbl[(int)((mx - mn) * 1000.0f)];
+}
+__device__ __forceinline__ float logf_via_double(float x) { return (float)log((double)x); }
+
+// residue i (0-based) of a nibble-coded sequence
+__device__ __forceinline__ uint32_t residue_at(const uint32_t *__restrict__ w, int pos)
+{
+    return (w[pos >> 3] >> ((pos & 7) * 4)) & 15u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sequence store: ASCII -> nibble codes, one warp per sequence
+__global__ void seqlen_kernel(const int64_t *__restrict__ off, const int32_t *__restrict__ first, int64_t nseq,
+                              int32_t *__restrict__ len, int64_t *__restrict__ nwords)
+{
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nseq) return;
+    int64_t r = first ? first[u] : u;
+    int L = (int)(off[r + 1] - off[r]);
+    len[u] = L;
+    nwords[u] = (L + 7) >> 3;
+}
+__global__ void __launch_bounds__(256) seqcode_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off,
+                                                      const int32_t *__restrict__ first, int64_t nseq,
+                                                      const int64_t *__restrict__ woff, const uint8_t *__restrict__ lut,
+                                                      uint32_t *__restrict__ seqw)
+{
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = lut[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= nseq) return;
+    int64_t r = first ? first[u] : u;
+    const uint8_t *s = ascii + off[r];
+    const int L = (int)(off[r + 1] - off[r]);
+    const int nw = (L + 7) >> 3;
+    uint32_t *out = seqw + woff[u];
+    for (int j = lane; j < nw; j += 32) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            int p = j * 8 + t;
+            uint32_t code = p < L ? s_lut[s[p]] : 0u;
+            w |= code << (4 * t);
+        }
+        out[j] = w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: MSV filter.  State st[j] holds nodes (2j+1, 2j+2) as two s16 lanes with HMMER's u8 values.
+// Before the overflow test fires no lane can reach 255 - bias, so the u8 upper clamp of the reference
+// arithmetic never binds and   sv = max(max(M_{k-1}(i-1), xB) + (bias - cost), 0)   is exact.
+__global__ void __launch_bounds__(MSV_THREADS)
+msv_kernel(const uint32_t *__restrict__ seqw, const int64_t *__restrict__ woff, const int32_t *__restrict__ seqlen,
+           int64_t s0, int ns, const uint32_t *__restrict__ msvtab, const ProfScalars *__restrict__ pscal, int P,
+           const uint8_t *__restrict__ tjbtab, const float *__restrict__ nullsctab, double F1,
+           uint8_t *__restrict__ res, uint8_t *__restrict__ flag)
+{
+    extern __shared__ uint32_t s_tab[];    // [tile profiles][KP][16]
+    const int p0 = blockIdx.y * MSV_TP;
+    const int np = min(MSV_TP, P - p0);
+    for (int t = threadIdx.x; t < np * KP * 16; t += MSV_THREADS) s_tab[t] = msvtab[(size_t)p0 * KP * 16 + t];
+    __syncthreads();
+
+    const int sl = blockIdx.x * MSV_THREADS + threadIdx.x;
+    const bool valid = sl < ns;
+    const int64_t s = s0 + (valid ? sl : 0);
+    const int L = valid ? seqlen[s] : 0;
+    const uint32_t *w = seqw + woff[s];
+    int Lw = L;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) Lw = max(Lw, __shfl_xor_sync(0xffffffffu, Lw, o));
+    const int tjb = tjbtab[L];
+    const float nullsc = nullsctab[L];
+
+    for (int pl = 0; pl < np; pl++) {
+        const ProfScalars &ps = pscal[p0 + pl];
+        const int bias = ps.bias, base = ps.base, tec = ps.tec;
+        const int tjbm = (tjb + ps.tbm) & 255;
+        const int limit = 255 - bias;
+        const uint32_t *tab = s_tab + pl * KP * 16;
+        uint32_t st[KP];
+#pragma unroll
+        for (int j = 0; j < KP; j++) st[j] = 0u;
+        int xJ = 0, xB = max(base - tjbm, 0), resJ = 0;
+        bool ovf = false;
+        for (int wi = 0; wi * 8 < Lw; wi++) {
+            uint32_t word = (wi * 8 < L) ? w[wi] : 0u;
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int i = wi * 8 + r;
+                const uint32_t x = word & 15u;
+                word >>= 4;
+                const uint32_t *tx = tab + x;
+                const uint32_t xB2 = (uint32_t)xB * 0x00010001u;
+                uint32_t xE2 = 0u;
+#pragma unroll
+                for (int j = KP - 1; j >= 1; j--) {
+                    uint32_t sh = __byte_perm(st[j - 1], st[j], 0x5432);
+                    st[j] = __viaddmax_s16x2(__vmaxs2(sh, xB2), tx[j * 16], 0u);
+                }
+                st[0] = __viaddmax_s16x2(__vmaxs2(st[0] << 16, xB2), tx[0], 0u);
+#pragma unroll
+                for (int j = 0; j + 1 < KP; j += 2) xE2 = __vimax3_s16x2(xE2, st[j], st[j + 1]);
+                xE2 = __vmaxs2(xE2, st[KP - 1]);
+                int xE = max((int)(xE2 & 0xffffu), (int)(xE2 >> 16));
+                const bool act = i < L;
+                if (act && xE >= limit) ovf = true;
+                xE = max(xE - tec, 0);
+                xJ = max(xJ, xE);
+                xB = max(max(base, xJ) - tjbm, 0);
+                if (i == L - 1) resJ = xJ;
+            }
+            if (__all_sync(0xffffffffu, ovf || (wi * 8 + 8 >= L))) break;
+        }
+        if (valid) {
+            bool pass = true;
+            if (!ovf) {
+                float sc = ((float)(resJ - tjb) - (float)base);
+                sc /= ps.scale_b;
+                sc -= 3.0f;
+                float seq_score = (float)((double)(sc - nullsc) / kLn2);
+                pass = gumbel_surv((double)seq_score, (double)ps.ev[EV_MMU], (double)ps.ev[EV_MLAMBDA]) <= F1;
+            }
+            const size_t o = (size_t)(p0 + pl) * ns + sl;
+            res[o]  = ovf ? 255 : (uint8_t)resJ;
+            flag[o] = pass ? 1 : 0;
+        }
+    }
+}
+
+// lower_bound of p*ns in the sorted pair list, p = 0..P
+__global__ void bounds_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ n_ptr, int ns, int P,
+                              int32_t *__restrict__ bounds)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > P) return;
+    const int n = *n_ptr;
+    const long long key = (long long)p * ns;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if ((long long)list[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    bounds[p] = lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: bias filter -- 2-state HMM Forward with per-row rescaling (Easel esl_hmm_Forward semantics)
+__global__ void __launch_bounds__(128)
+bias_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ n_ptr, int64_t s0, int ns,
+            const uint32_t *__restrict__ seqw, const int64_t *__restrict__ woff, const int32_t *__restrict__ seqlen,
+            const ProfScalars *__restrict__ pscal, const uint8_t *__restrict__ res,
+            const uint8_t *__restrict__ tjbtab, double F1, float *__restrict__ filtersc, uint8_t *__restrict__ flag2,
+            unsigned long long *__restrict__ counters)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= *n_ptr) return;
+    const int idx = list[e];
+    const int p = idx / ns, sl = idx - p * ns;
+    const int64_t s = s0 + sl;
+    const int L = seqlen[s];
+    const uint32_t *w = seqw + woff[s];
+    const ProfScalars &ps = pscal[p];
+    const float L0 = 400.0f, L1 = (float)ps.M / 8.0f;
+    const float t00 = L0 / (L0 + 1.0f), t01 = 1.0f / (L0 + 1.0f);
+    const float t10 = 1.0f / (L1 + 1.0f), t11 = L1 / (L1 + 1.0f);
+    float logsc = 0.f, mx, d0, d1;
+    uint32_t x = residue_at(w, 0);
+    d0 = ps.eo[x][0] * 0.999f;
+    d1 = ps.eo[x][1] * 0.001f;
+    mx = 0.f;
+    if (d0 > mx) mx = d0;
+    if (d1 > mx) mx = d1;
+    d0 /= mx; d1 /= mx;
+    logsc += logf_via_double(mx);
+    for (int i = 1; i < L; i++) {
+        x = residue_at(w, i);
+        float n0 = 0.f, n1 = 0.f;
+        n0 += d0 * t00; n0 += d1 * t10;
+        n1 += d0 * t01; n1 += d1 * t11;
+        n0 *= ps.eo[x][0];
+        n1 *= ps.eo[x][1];
+        mx = 0.f;
+        if (n0 > mx) mx = n0;
+        if (n1 > mx) mx = n1;
+        d0 = n0 / mx; d1 = n1 / mx;
+        logsc += logf_via_double(mx);
+    }
+    float end = 0.f;
+    end += d0 * 1.0f;
+    end += d1 * 1.0f;
+    logsc += logf_via_double(end);
+    const float p1 = (float)L / (float)(L + 1);
+    const float fsc = logsc + (float)L * logf_via_double(p1) + logf_via_double(1.f - p1);
+    filtersc[e] = fsc;
+    bool pass = true;
+    const int r = res[(size_t)p * ns + sl];
+    if (r != 255) {
+        const int tjb = tjbtab[L];
+        float sc = ((float)(r - tjb) - (float)ps.base);
+        sc /= ps.scale_b;
+        sc -= 3.0f;
+        float seq_score = (float)((double)(sc - fsc) / kLn2);
+        pass = gumbel_surv((double)seq_score, (double)ps.ev[EV_MMU], (double)ps.ev[EV_MLAMBDA]) <= F1;
+    }
+    flag2[e] = pass ? 1 : 0;
+    if (L > 0) atomicAdd(&counters[CNT_BIAS_ROWS], (unsigned long long)L);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7-K9: Forward -> F3 -> Backward -> domain decoding -> regions.  One warp = one tile of 32 worklist
+// entries of the launch's profile; a warp walks tiles persistently and reuses its scratch slab
+// spec[row][5][lane] (coalesced 128-byte rows).
+struct FbArgs {
+    const int32_t *list;      // worklist (pair index = p*ns + sl), this profile's slice
+    const float   *filtersc;
+    int            count;
+    int64_t        s0;
+    int            ns, prof;
+    const uint32_t *seqw;
+    const int64_t  *woff;
+    const int32_t  *seqlen;
+    const float    *etab;     // [46][16] match odds of this profile
+    float          *spec;     // scratch: warps_total * (Lmax+1) * 5 * 32 floats
+    int             Lmax;
+    float           tau, lambda;
+    float           e_move;   // expf(-ln 2) as the host libm rounds it (E->C and E->J, multihit)
+    double          F3;
+    float          *fwdsc;    // out, per entry
+    float          *bcksc;
+    uint8_t        *ndom;     // out: number of envelopes (0 if the entry failed F3)
+    int32_t        *env;      // out: [entry][MAXDOM][2], jenv carries the multidomain flag in bit 30
+    unsigned long long *counters;
+};
+
+__device__ __forceinline__ void spec_decode(float eraw, float &E, float &S)
+{
+    if (eraw > 1.0e4f) { E = 1.0f; S = eraw; } else { E = eraw; S = 1.0f; }
+}
+
+__global__ void __launch_bounds__(FB_THREADS, 2)
+fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
+{
+    __shared__ float s_e[(MAXM + 1) * 16];
+    for (int t = threadIdx.x; t < (MAXM + 1) * 16; t += FB_THREADS) s_e[t] = a.etab[t];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp_in_grid = (blockIdx.x * FB_THREADS + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * FB_THREADS) >> 5;
+    const int ntiles = (a.count + 31) >> 5;
+    float *sp = a.spec + (size_t)warp_in_grid * (size_t)(a.Lmax + 1) * SPEC_C * 32 + lane;
+#define SPEC(row, c) sp[((size_t)(row) * SPEC_C + (c)) * 32]
+
+    for (int tile = warp_in_grid; tile < ntiles; tile += nwarps) {
+        const int ent = tile * 32 + lane;
+        const bool valid = ent < a.count;
+        int L = 0;
+        const uint32_t *w = a.seqw;
+        float filtersc = 0.f;
+        if (valid) {
+            const int idx = a.list[ent];
+            const int sl = idx - a.prof * a.ns;
+            const int64_t s = a.s0 + sl;
+            L = a.seqlen[s];
+            w = a.seqw + a.woff[s];
+            filtersc = a.filtersc[ent];
+        }
+        int Lw = L;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) Lw = max(Lw, __shfl_xor_sync(0xffffffffu, Lw, o));
+
+        // length model, multihit (nj = 1)
+        const float pmove = (2.0f + 1.0f) / ((float)L + 2.0f + 1.0f);
+        const float N_move = pmove, N_loop = 1.0f - pmove;
+        const float E_move = a.e_move, E_loop = a.e_move;
+
+        float Mx[MAXM + 2], Ix[MAXM + 2], Dx[MAXM + 2];
+#pragma unroll
+        for (int k = 0; k <= MAXM + 1; k++) Mx[k] = Ix[k] = Dx[k] = 0.f;
+
+        // ------------------------------ Forward ------------------------------
+        float xN = 1.f, xJ = 0.f, xC = 0.f, xE = 0.f, xB = N_move, totscale = 0.f;
+        if (valid) { SPEC(0, 0) = 0.f; SPEC(0, 1) = 1.f; SPEC(0, 2) = 0.f; SPEC(0, 3) = xB; SPEC(0, 4) = 0.f; }
+        for (int i = 1; i <= Lw; i++) {
+            if (i <= L) {
+                const float *er = s_e + residue_at(w, i - 1);
+                float mprev = 0.f, iprev = 0.f, dprev = 0.f, mcur = 0.f, dcur = 0.f, xEm = 0.f, xEd = 0.f;
+#pragma unroll
+                for (int k = 1; k <= MAXM; k++) {
+                    float sv = xB * pc.tp[k][T_BM];
+                    sv = fmaf(mprev, pc.tp[k - 1][T_MM], sv);
+                    sv = fmaf(iprev, pc.tp[k - 1][T_IM], sv);
+                    sv = fmaf(dprev, pc.tp[k - 1][T_DM], sv);
+                    sv = sv * er[k * 16];
+                    const float dc = fmaf(dcur, pc.tp[k - 1][T_DD], mcur * pc.tp[k - 1][T_MD]);
+                    const float mp = Mx[k], ip = Ix[k], dp = Dx[k];
+                    const float ic = fmaf(ip, pc.tp[k][T_II], mp * pc.tp[k][T_MI]);
+                    Mx[k] = sv; Ix[k] = ic; Dx[k] = dc;
+                    xEm += sv; xEd += dc;
+                    mprev = mp; iprev = ip; dprev = dp;
+                    mcur = sv; dcur = dc;
+                }
+                xE = xEm + xEd;
+                xN = xN * N_loop;
+                xC = fmaf(xC, N_loop, xE * E_move);
+                xJ = fmaf(xJ, N_loop, xE * E_loop);
+                xB = fmaf(xJ, N_move, xN * N_move);
+                const float eraw = xE;
+                if (xE > 1.0e4f) {
+                    xN = xN / xE; xC = xC / xE; xJ = xJ / xE; xB = xB / xE;
+                    const float inv = 1.0f / xE;
+#pragma unroll
+                    for (int k = 1; k <= MAXM; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
+                    totscale += logf_via_double(xE);
+                    xE = 1.0f;
+                }
+                SPEC(i, 0) = eraw; SPEC(i, 1) = xN; SPEC(i, 2) = xJ; SPEC(i, 3) = xB; SPEC(i, 4) = xC;
+            }
+        }
+        bool pass = false;
+        float fwdsc = 0.f;
+        if (valid) {
+            fwdsc = totscale + logf_via_double(xC * N_move);
+            const float seq_score = (float)((double)(fwdsc - filtersc) / kLn2);
+            pass = exp_surv((double)seq_score, (double)a.tau, (double)a.lambda) <= a.F3;
+            a.fwdsc[ent] = fwdsc;
+        }
+        {
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            int rows = valid ? L : 0;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
+            if (lane == 0) {
+                atomicAdd(&a.counters[CNT_FWD_ROWS], (unsigned long long)rows);
+                if (m) atomicAdd(&a.counters[CNT_PAST_FWD], (unsigned long long)__popc(m));
+            }
+            if (m == 0) {
+                if (valid) a.ndom[ent] = 0;
+                continue;
+            }
+        }
+        if (!pass) L = 0;   // inactive in the Backward sweep
+        Lw = L;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) Lw = max(Lw, __shfl_xor_sync(0xffffffffu, Lw, o));
+
+        // ------------------------------ Backward ------------------------------
+        // forward row i is held in f*_i while row i-1 is loaded; products go back in place:
+        //   SPEC(i,0) <- (fB[i-1]*bB[i-1])*fS[i-1]      SPEC(i,1) <- (fE[i]*bE[i])*fS[i]
+        //   SPEC(i,2..4) <- (fN|fJ|fC[i-1] * bN|bJ|bC[i]) * loop
+        float bJ = 0.f, bB = 0.f, bN = 0.f, bC = N_move, bE = bC * E_move, btotscale = 0.f;
+        float fE_i = 0.f, fS_i = 1.f;
+        if (pass) {
+            Dx[MAXM + 1] = 0.f;
+#pragma unroll
+            for (int k = MAXM; k >= 1; k--) {
+                Dx[k] = fmaf(pc.tp[k][T_DD], Dx[k + 1], bE);
+                Mx[k] = fmaf(pc.tp[k][T_MD], Dx[k + 1], bE);
+                Ix[k] = 0.f;
+            }
+            spec_decode(SPEC(L, 0), fE_i, fS_i);
+            if (fS_i > 1.0f) {
+                bE = bE / fS_i; bN = bN / fS_i; bC = bC / fS_i; bJ = bJ / fS_i; bB = bB / fS_i;
+                const float inv = 1.0f / fS_i;
+#pragma unroll
+                for (int k = 1; k <= MAXM; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
+            }
+            btotscale = logf_via_double(fS_i);
+        }
+        for (int i = Lw; i >= 1; i--) {
+            if (i <= L) {
+                // forward row i-1
+                const float fN_p = SPEC(i - 1, 1), fJ_p = SPEC(i - 1, 2), fB_p = SPEC(i - 1, 3), fC_p = SPEC(i - 1, 4);
+                float fE_p, fS_p;
+                spec_decode(SPEC(i - 1, 0), fE_p, fS_p);
+                // products that involve backward row i
+                SPEC(i, 1) = (fE_i * bE) * fS_i;
+                SPEC(i, 2) = (fN_p * bN) * N_loop;
+                SPEC(i, 3) = (fJ_p * bJ) * N_loop;
+                SPEC(i, 4) = (fC_p * bC) * N_loop;
+                if (i > 1) {
+                    const float *er = s_e + residue_at(w, i - 1);   // residue x_i
+                    bB = 0.f;
+#pragma unroll
+                    for (int k = 1; k <= MAXM; k++) {
+                        Mx[k] = Mx[k] * er[k * 16];
+                        bB = fmaf(Mx[k], pc.tp[k][T_BM], bB);
+                    }
+                    bC = bC * N_loop;
+                    bJ = fmaf(bB, N_move, bJ * N_loop);
+                    bN = fmaf(bB, N_move, bN * N_loop);
+                    bE = fmaf(bC, E_move, bJ * E_loop);
+                    Dx[MAXM + 1] = 0.f;
+                    float mnext = 0.f;
+#pragma unroll
+                    for (int k = MAXM; k >= 1; k--) {
+                        const float mpe_k = Mx[k];
+                        const float ic = fmaf(mnext, pc.tp[k][T_IM], Ix[k] * pc.tp[k][T_II]);
+                        float mc = fmaf(mnext, pc.tp[k][T_MM], Ix[k] * pc.tp[k][T_MI]);
+                        float dc = mnext * pc.tp[k][T_DM];
+                        dc = fmaf(Dx[k + 1], pc.tp[k][T_DD], dc) + bE;
+                        mc = fmaf(Dx[k + 1], pc.tp[k][T_MD], mc) + bE;
+                        Mx[k] = mc; Ix[k] = ic; Dx[k] = dc;
+                        mnext = mpe_k;
+                    }
+                    if (fS_p > 1.0f) {
+                        bE = bE / fS_p; bN = bN / fS_p; bC = bC / fS_p; bJ = bJ / fS_p; bB = bB / fS_p;
+                        const float inv = 1.0f / fS_p;
+#pragma unroll
+                        for (int k = 1; k <= MAXM; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
+                    }
+                    btotscale += logf_via_double(fS_p);
+                } else {
+                    // row 0: only B and N are live
+                    const float *er = s_e + residue_at(w, 0);
+                    bB = 0.f;
+#pragma unroll
+                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * er[k * 16], pc.tp[k][T_BM], bB);
+                    bN = fmaf(bB, N_move, bN * N_loop);
+                }
+                SPEC(i, 0) = (fB_p * bB) * fS_p;
+                fE_i = fE_p; fS_i = fS_p;
+            }
+        }
+
+        // ------------------------------ decoding + regions ------------------------------
+        int nd = 0;
+        if (pass) {
+            a.bcksc[ent] = btotscale + logf_via_double(bN);
+            const float scaleproduct = 1.0f / bN;
+            const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
+            float btot = 0.f, etot = 0.f;
+            int ri = -1;
+            bool triggered = false;
+            int nmulti = 0;
+            SPEC(0, 0) = 0.f; SPEC(0, 1) = 0.f;   // btot[0], etot[0]
+            for (int j = 1; j <= L; j++) {
+                const float db = SPEC(j, 0) * scaleproduct, de = SPEC(j, 1) * scaleproduct;
+                const float btot_p = btot, etot_p = etot;
+                btot = btot + db;
+                etot = etot + de;
+                float njcp = SPEC(j, 2) * scaleproduct;
+                njcp += SPEC(j, 3) * scaleproduct;
+                njcp += SPEC(j, 4) * scaleproduct;
+                const float mocc = 1.f - njcp;
+                SPEC(j, 0) = btot; SPEC(j, 1) = etot;
+                if (!triggered) {
+                    if (mocc - (btot - btot_p) < rt2) ri = j;
+                    else if (ri == -1) ri = j;
+                    if (mocc >= rt1) triggered = true;
+                } else if (mocc - (etot - etot_p) < rt2) {
+                    float mx = -1.0f;
+                    const float e0 = SPEC(ri - 1, 1);
+                    for (int z = ri; z <= j; z++) {
+                        const float x1 = SPEC(z, 1) - e0, x2 = btot - SPEC(z - 1, 0);
+                        const float en = x1 < x2 ? x1 : x2;
+                        if (en > mx) mx = en;
+                    }
+                    const int multi = mx >= rt3;
+                    nmulti += multi;
+                    if (nd < ITSX_MAXDOM) {
+                        a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 0] = ri;
+                        a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 1] = j | (multi << 30);
+                        nd++;
+                    } else {
+                        atomicAdd(&a.counters[CNT_DOM_OVERFLOW], 1ull);
+                    }
+                    ri = -1;
+                    triggered = false;
+                }
+            }
+            if (nmulti) atomicAdd(&a.counters[CNT_MULTI], (unsigned long long)nmulti);
+            atomicAdd(&a.counters[CNT_BCK_ROWS], (unsigned long long)L);
+        }
+        if (valid) a.ndom[ent] = (uint8_t)nd;
+    }
+#undef SPEC
+}
+
+// ------------------------------------------------------------------------------------------------
+// envelope worklist
+__global__ void ndom_widen_kernel(const uint8_t *__restrict__ ndom, int n, int32_t *__restrict__ out)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = ndom[e];
+    if (e == n) out[e] = 0;
+}
+__global__ void envwork_kernel(const uint8_t *__restrict__ ndom, const int32_t *__restrict__ envoff, int n,
+                               int32_t *__restrict__ work)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int nd = ndom[e], o = envoff[e];
+    for (int d = 0; d < nd; d++) work[o + d] = e * ITSX_MAXDOM + d;
+}
+__global__ void gather_bounds_kernel(const int32_t *__restrict__ envoff, const int32_t *__restrict__ bounds, int P,
+                                     int32_t *__restrict__ out)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p <= P) out[p] = envoff[bounds[p]];
+}
+
+// K10: envelope rescoring (unihit Forward, Backward, posterior decoding, null2 by expectation)
+struct EnvArgs {
+    const int32_t *work;      // this profile's slice of the envelope worklist: entry*MAXDOM + d
+    int            count;
+    const int32_t *list;      // whole pair list of the batch
+    const int32_t *env;
+    int64_t        s0;
+    int            ns, prof;
+    const uint32_t *seqw;
+    const int64_t  *woff;
+    const int32_t  *seqlen;
+    const float    *etab;
+    float          *scratch;  // warps_total * (Ldmax+1) * ENV_ROWF * 32 floats
+    int             Ldmax;
+    float          *out;      // [envelope][20]: envsc, domcorrection, null2[16], pad
+    int             out_base; // index of this slice's first envelope in the batch numbering
+    unsigned long long *counters;
+};
+
+__global__ void __launch_bounds__(FB_THREADS, 2)
+env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
+{
+    __shared__ float s_e[(MAXM + 1) * 16];
+    for (int t = threadIdx.x; t < (MAXM + 1) * 16; t += FB_THREADS) s_e[t] = a.etab[t];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp_in_grid = (blockIdx.x * FB_THREADS + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * FB_THREADS) >> 5;
+    const int ntiles = (a.count + 31) >> 5;
+    float *sc = a.scratch + (size_t)warp_in_grid * (size_t)(a.Ldmax + 1) * ENV_ROWF * 32 + lane;
+#define ROW(row, c) sc[((size_t)(row) * ENV_ROWF + (c)) * 32]
+    constexpr int C_I = MAXM + 1, C_E = 2 * (MAXM + 1), C_N = C_E + 1, C_J = C_E + 2, C_C = C_E + 3;
+
+    for (int tile = warp_in_grid; tile < ntiles; tile += nwarps) {
+        const int t = tile * 32 + lane;
+        const bool valid = t < a.count;
+        int L = 0, Ld = 0, ienv = 1;
+        const uint32_t *w = a.seqw;
+        if (valid) {
+            const int wk = a.work[t];
+            const int ent = wk / ITSX_MAXDOM, d = wk - ent * ITSX_MAXDOM;
+            const int idx = a.list[ent];
+            const int sl = idx - a.prof * a.ns;
+            const int64_t s = a.s0 + sl;
+            L = a.seqlen[s];
+            w = a.seqw + a.woff[s];
+            ienv = a.env[((size_t)ent * ITSX_MAXDOM + d) * 2 + 0];
+            const int jenv = a.env[((size_t)ent * ITSX_MAXDOM + d) * 2 + 1] & 0x3fffffff;
+            Ld = jenv - ienv + 1;
+        }
+        int Lw = Ld;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) Lw = max(Lw, __shfl_xor_sync(0xffffffffu, Lw, o));
+
+        // unihit length model for the full target length (nj = 0)
+        const float pmove = (2.0f + 0.0f) / ((float)L + 2.0f + 0.0f);
+        const float N_move = pmove, N_loop = 1.0f - pmove;
+        const float E_move = 1.0f, E_loop = 0.0f;
+
+        float Mx[MAXM + 2], Ix[MAXM + 2], Dx[MAXM + 2];
+#pragma unroll
+        for (int k = 0; k <= MAXM + 1; k++) Mx[k] = Ix[k] = Dx[k] = 0.f;
+
+        float xN = 1.f, xJ = 0.f, xC = 0.f, xE = 0.f, xB = N_move, totscale = 0.f;
+        if (valid) { ROW(0, C_E) = 0.f; ROW(0, C_N) = 1.f; ROW(0, C_J) = 0.f; ROW(0, C_C) = 0.f; }
+        for (int i = 1; i <= Lw; i++) {
+            if (i <= Ld) {
+                const float *er = s_e + residue_at(w, ienv - 1 + i - 1);
+                float mprev = 0.f, iprev = 0.f, dprev = 0.f, mcur = 0.f, dcur = 0.f, xEm = 0.f, xEd = 0.f;
+#pragma unroll
+                for (int k = 1; k <= MAXM; k++) {
+                    float sv = xB * pc.tp[k][T_BM];
+                    sv = fmaf(mprev, pc.tp[k - 1][T_MM], sv);
+                    sv = fmaf(iprev, pc.tp[k - 1][T_IM], sv);
+                    sv = fmaf(dprev, pc.tp[k - 1][T_DM], sv);
+                    sv = sv * er[k * 16];
+                    const float dc = fmaf(dcur, pc.tp[k - 1][T_DD], mcur * pc.tp[k - 1][T_MD]);
+                    const float mp = Mx[k], ip = Ix[k], dp = Dx[k];
+                    const float ic = fmaf(ip, pc.tp[k][T_II], mp * pc.tp[k][T_MI]);
+                    Mx[k] = sv; Ix[k] = ic; Dx[k] = dc;
+                    xEm += sv; xEd += dc;
+                    mprev = mp; iprev = ip; dprev = dp;
+                    mcur = sv; dcur = dc;
+                }
+                xE = xEm + xEd;
+                xN = xN * N_loop;
+                xC = fmaf(xC, N_loop, xE * E_move);
+                xJ = fmaf(xJ, N_loop, xE * E_loop);
+                xB = fmaf(xJ, N_move, xN * N_move);
+                const float eraw = xE;
+                if (xE > 1.0e4f) {
+                    xN = xN / xE; xC = xC / xE; xJ = xJ / xE; xB = xB / xE;
+                    const float inv = 1.0f / xE;
+#pragma unroll
+                    for (int k = 1; k <= MAXM; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
+                    totscale += logf_via_double(xE);
+                    xE = 1.0f;
+                }
+#pragma unroll
+                for (int k = 1; k <= MAXM; k++) { ROW(i, k) = Mx[k]; ROW(i, C_I + k) = Ix[k]; }
+                ROW(i, C_E) = eraw; ROW(i, C_N) = xN; ROW(i, C_J) = xJ; ROW(i, C_C) = xC;
+            }
+        }
+        const float envsc = totscale + logf_via_double(xC * N_move);
+
+        // Backward with posterior accumulation
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) acc[q] = 0.f;
+        float bJ = 0.f, bB = 0.f, bN = 0.f, bC = N_move, bE = bC * E_move;
+        if (valid) {
+            Dx[MAXM + 1] = 0.f;
+#pragma unroll
+            for (int k = MAXM; k >= 1; k--) {
+                Dx[k] = fmaf(pc.tp[k][T_DD], Dx[k + 1], bE);
+                Mx[k] = fmaf(pc.tp[k][T_MD], Dx[k + 1], bE);
+                Ix[k] = 0.f;
+            }
+            float fE, fS;
+            spec_decode(ROW(Ld, C_E), fE, fS);
+            if (fS > 1.0f) {
+                bE = bE / fS; bN = bN / fS; bC = bC / fS; bJ = bJ / fS; bB = bB / fS;
+                const float inv = 1.0f / fS;
+#pragma unroll
+                for (int k = 1; k <= MAXM; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
+            }
+        }
+        for (int i = Lw; i >= 1; i--) {
+            if (i <= Ld) {
+                float fE, fS;
+                spec_decode(ROW(i, C_E), fE, fS);
+                {
+                    float rM0 = 0.f, rM1 = 0.f, rM2 = 0.f, rM3 = 0.f, rI = 0.f;
+#pragma unroll
+                    for (int k = 1; k <= MAXM; k++) {
+                        const float pm = ROW(i, k) * Mx[k];
+                        rM0 = fmaf(pm, s_e[k * 16 + 0], rM0);
+                        rM1 = fmaf(pm, s_e[k * 16 + 1], rM1);
+                        rM2 = fmaf(pm, s_e[k * 16 + 2], rM2);
+                        rM3 = fmaf(pm, s_e[k * 16 + 3], rM3);
+                        rI = fmaf(ROW(i, C_I + k), Ix[k], rI);
+                    }
+                    acc[0] = fmaf(rM0, fS, acc[0]);
+                    acc[1] = fmaf(rM1, fS, acc[1]);
+                    acc[2] = fmaf(rM2, fS, acc[2]);
+                    acc[3] = fmaf(rM3, fS, acc[3]);
+                    acc[4] = fmaf(rI, fS, acc[4]);
+                    acc[5] += ROW(i - 1, C_N) * bN * N_loop;
+                    acc[6] += ROW(i - 1, C_C) * bC * N_loop;
+                    acc[7] += ROW(i - 1, C_J) * bJ * N_loop;
+                }
+                if (i > 1) {
+                    float fEp, fSp;
+                    spec_decode(ROW(i - 1, C_E), fEp, fSp);
+                    const float *er = s_e + residue_at(w, ienv - 1 + i - 1);
+                    bB = 0.f;
+#pragma unroll
+                    for (int k = 1; k <= MAXM; k++) {
+                        Mx[k] = Mx[k] * er[k * 16];
+                        bB = fmaf(Mx[k], pc.tp[k][T_BM], bB);
+                    }
+                    bC = bC * N_loop;
+                    bJ = fmaf(bB, N_move, bJ * N_loop);
+                    bN = fmaf(bB, N_move, bN * N_loop);
+                    bE = fmaf(bC, E_move, bJ * E_loop);
+                    Dx[MAXM + 1] = 0.f;
+                    float mnext = 0.f;
+#pragma unroll
+                    for (int k = MAXM; k >= 1; k--) {
+                        const float mpe_k = Mx[k];
+                        const float ic = fmaf(mnext, pc.tp[k][T_IM], Ix[k] * pc.tp[k][T_II]);
+                        float mc = fmaf(mnext, pc.tp[k][T_MM], Ix[k] * pc.tp[k][T_MI]);
+                        float dc = mnext * pc.tp[k][T_DM];
+                        dc = fmaf(Dx[k + 1], pc.tp[k][T_DD], dc) + bE;
+                        mc = fmaf(Dx[k + 1], pc.tp[k][T_MD], mc) + bE;
+                        Mx[k] = mc; Ix[k] = ic; Dx[k] = dc;
+                        mnext = mpe_k;
+                    }
+                    if (fSp > 1.0f) {
+                        bE = bE / fSp; bN = bN / fSp; bC = bC / fSp; bJ = bJ / fSp; bB = bB / fSp;
+                        const float inv = 1.0f / fSp;
+#pragma unroll
+                        for (int k = 1; k <= MAXM; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
+                    }
+                } else {
+                    const float *er = s_e + residue_at(w, ienv - 1);
+                    bB = 0.f;
+#pragma unroll
+                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * er[k * 16], pc.tp[k][T_BM], bB);
+                    bN = fmaf(bB, N_move, bN * N_loop);
+                }
+            }
+        }
+        if (valid) {
+            const float scaleproduct = 1.0f / bN;
+            const float norm = 1.0f / (float)Ld;
+            float null2[16];
+            const float xfactor = (acc[5] + acc[6] + acc[7]) * scaleproduct * norm;
+            const float isum = acc[4] * scaleproduct * norm;
+#pragma unroll
+            for (int x = 0; x < 4; x++) null2[x] = acc[x] * scaleproduct * norm + isum + xfactor;
+            const int degen[16] = {1, 2, 4, 8, 5, 10, 3, 12, 6, 9, 11, 14, 7, 13, 15, 0};
+#pragma unroll
+            for (int x = 4; x < 15; x++) {
+                float s = 0.f;
+                int n = 0;
+#pragma unroll
+                for (int y = 0; y < 4; y++)
+                    if (degen[x] & (1 << y)) { s += null2[y]; n++; }
+                null2[x] = s / (float)n;
+            }
+            null2[15] = 1.0f;
+            float *o = a.out + (size_t)(a.out_base + t) * 20;
+            o[0] = envsc;
+#pragma unroll
+            for (int x = 0; x < 16; x++) o[2 + x] = null2[x];
+            atomicAdd(&a.counters[CNT_ENV_ROWS], (unsigned long long)Ld);
+            atomicMax(&a.counters[CNT_MAX_ENVLEN], (unsigned long long)Ld);
+        }
+    }
+#undef ROW
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11a: per-hit and per-domain scores, -T threshold, reported-hit counts
+struct FinalArgs {
+    const int32_t *list;
+    int            n;         // entries in the batch
+    int64_t        s0;
+    int            ns;
+    const uint32_t *seqw;
+    const int64_t  *woff;
+    const int32_t  *seqlen;
+    const ProfScalars *pscal;
+    const float    *nullsctab;
+    const float    *logsum;
+    const float    *fwdsc;
+    const uint8_t  *ndom;
+    const int32_t  *envoff;
+    const int32_t  *env;
+    float          *envout;   // [envelope][20]; [1] receives domcorrection
+    float           T;
+    DomRec         *doms;     // output base for this batch
+    int32_t        *nrep;     // per profile
+    unsigned long long *counters;
+};
+
+__global__ void __launch_bounds__(128) final_kernel(const FinalArgs a)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n) return;
+    const int nd = a.ndom[e];
+    if (nd == 0) return;
+    const int idx = a.list[e];
+    const int p = idx / a.ns, sl = idx - p * a.ns;
+    const int64_t s = a.s0 + sl;
+    const int L = a.seqlen[s];
+    const uint32_t *w = a.seqw + a.woff[s];
+    const ProfScalars &ps = a.pscal[p];
+    const float nullsc = a.nullsctab[L];
+    const float fwdsc = a.fwdsc[e];
+    const int o0 = a.envoff[e];
+    const float omega = 1.0f / 256.0f;
+    const float lnomega = logf_via_double(omega);
+
+    // n2sc summed over the whole sequence (position order) and per envelope
+    float seqbias = 0.f;
+    for (int d = 0; d < nd; d++) {
+        float *o = a.envout + (size_t)(o0 + d) * 20;
+        const int ienv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
+        const int jenv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1] & 0x3fffffff;
+        float dc = 0.f;
+        for (int pos = ienv; pos <= jenv; pos++) {
+            const float v = logf(o[2 + residue_at(w, pos - 1)]);
+            dc += v;
+            seqbias += v;
+        }
+        o[1] = dc;
+    }
+    seqbias = flogsum(a.logsum, 0.0f, lnomega + seqbias);
+    float pre_score = (float)((double)(fwdsc - nullsc) / kLn2);
+    float sscore = (float)((double)(fwdsc - (nullsc + seqbias)) / kLn2);
+    float sum_score = 0.0f, sbias = 0.0f;
+    int Ldsum = 0;
+    for (int d = 0; d < nd; d++) {
+        const float *o = a.envout + (size_t)(o0 + d) * 20;
+        if (o[0] - o[1] > 0.0f) {
+            const int ienv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
+            const int jenv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1] & 0x3fffffff;
+            sum_score += o[0];
+            Ldsum += jenv - ienv + 1;
+            sbias += o[1];
+        }
+    }
+    sbias = flogsum(a.logsum, 0.0f, lnomega + sbias);
+    const double lratio = log((double)((float)L / (float)(L + 3)));
+    sum_score += (float)((L - Ldsum) * lratio);
+    float pre2 = (float)((double)(sum_score - nullsc) / kLn2);
+    sum_score = (float)((double)(sum_score - (nullsc + sbias)) / kLn2);
+    if (Ldsum > 0 && sum_score > sscore) { sscore = sum_score; pre_score = pre2; }
+    (void)pre_score;
+    const double seq_lnP = exp_logsurv((double)sscore, (double)ps.ev[EV_FTAU], (double)ps.ev[EV_FLAMBDA]);
+    const int reported = sscore >= a.T;
+    if (reported) {
+        atomicAdd(&a.nrep[p], 1);
+        atomicAdd(&a.counters[CNT_HITS_REPORTED], 1ull);
+    }
+    for (int d = 0; d < nd; d++) {
+        const float *o = a.envout + (size_t)(o0 + d) * 20;
+        const int ienv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
+        const int jraw = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1];
+        const int jenv = jraw & 0x3fffffff;
+        const int ld = jenv - ienv + 1;
+        const float bs = o[0] + (float)((L - ld) * lratio);
+        const float dombias = flogsum(a.logsum, 0.0f, lnomega + o[1]);
+        DomRec r;
+        r.seq = (int32_t)s; r.prof = p; r.ienv = ienv; r.jenv = jenv; r.tlen = L; r.dom_idx = d;
+        r.bitscore = (float)((double)(bs - (nullsc + dombias)) / kLn2);
+        r.envsc = o[0]; r.domcorrection = o[1]; r.seq_score = sscore;
+        r.lnP = exp_logsurv((double)r.bitscore, (double)ps.ev[EV_FTAU], (double)ps.ev[EV_FLAMBDA]);
+        r.seq_lnP = seq_lnP;
+        r.is_multidomain = (jraw >> 30) & 1;
+        r.pair_reported = reported;
+        a.doms[o0 + d] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K11b + K12: domE threshold with the global domZ, then ItsPosition's arg-max.
+// Row order of the reference table restricted to one target = (profile, domain index); the first row
+// wins ties on the printed score, so the key is (score10, NOT rank) under max.
+__device__ __forceinline__ int score10_of(float bits) { return (int)rint((double)bits * 10.0); }
+
+__global__ void select_kernel(DomRec *__restrict__ doms, int64_t n, const int32_t *__restrict__ nrep,
+                              const ProfScalars *__restrict__ pscal, double domE,
+                              unsigned long long *__restrict__ best, int64_t nseq, int64_t seq_first,
+                              unsigned long long *__restrict__ counters)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    DomRec &r = doms[t];
+    const int rep = r.pair_reported && (exp(r.lnP) * (double)nrep[r.prof] <= domE);
+    r.pair_reported = rep ? 3 : (r.pair_reported & 1);   // bit1: row is printed
+    if (!rep) return;
+    atomicAdd(&counters[CNT_DOM_REPORTED], 1ull);
+    const int side = pscal[r.prof].side;
+    if (side < 0) return;
+    const unsigned long long sc = (unsigned long long)(score10_of(r.bitscore) + (1 << 20));
+    const unsigned long long rank = (unsigned long long)r.prof * ITSX_MAXDOM + (unsigned long long)r.dom_idx;
+    const unsigned long long key = (sc << 40) | (0xFFFFFFFFFFull - rank);
+    atomicMax(&best[(size_t)side * nseq + (r.seq - seq_first)], key);
+}
+
+__global__ void best_kernel(const DomRec *__restrict__ doms, int64_t n, const ProfScalars *__restrict__ pscal,
+                            const unsigned long long *__restrict__ best, int64_t nseq, int64_t seq_first,
+                            int32_t *__restrict__ pos)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const DomRec &r = doms[t];
+    if (!(r.pair_reported & 2)) return;
+    const int side = pscal[r.prof].side;
+    if (side < 0) return;
+    const unsigned long long sc = (unsigned long long)(score10_of(r.bitscore) + (1 << 20));
+    const unsigned long long rank = (unsigned long long)r.prof * ITSX_MAXDOM + (unsigned long long)r.dom_idx;
+    const unsigned long long key = (sc << 40) | (0xFFFFFFFFFFull - rank);
+    const int64_t q = r.seq - seq_first;
+    if (best[(size_t)side * nseq + q] != key) return;
+    int32_t *b = pos + (size_t)(3 + 3 * side) * nseq;
+    b[q] = score10_of(r.bitscore);
+    b[nseq + q] = r.ienv;
+    b[2 * nseq + q] = r.jenv;
+    pos[2 * nseq + q] = r.tlen;
+    if (side == 0) pos[q] = r.jenv;             // start = left.to_pos            (SeqSample.py:480)
+    else pos[nseq + q] = r.ienv - 1;            // stop  = right.from_pos - 1      (SeqSample.py:484)
+}
+
+__global__ void pos_init_kernel(int32_t *pos, unsigned long long *best, int64_t nseq)
+{
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nseq) return;
+    pos[q] = pos[nseq + q] = pos[2 * nseq + q] = -1;
+    pos[3 * nseq + q] = pos[6 * nseq + q] = INT32_MIN;
+    pos[4 * nseq + q] = pos[5 * nseq + q] = pos[7 * nseq + q] = pos[8 * nseq + q] = -1;
+    best[q] = best[nseq + q] = 0ull;
+}
+
+}  // namespace
+
+// ==================================================================================================
+// host orchestration
+// ==================================================================================================
+int search_upload_profiles(itsx_ctx *c)
+{
+    if (!c->prof_dirty) return ITSX_OK;
+    const int P = (int)c->prof.size();
+    cudaStream_t st = c->stream;
+    std::vector<uint32_t> msvtab((size_t)std::max(P, 1) * KP * 16);
+    std::vector<float> etab((size_t)std::max(P, 1) * (MAXM + 1) * 16, 0.f);
+    std::vector<ProfScalars> ps((size_t)std::max(P, 1));
+    c->pconst.assign((size_t)P, ProfConst{});
+    for (int p = 0; p < P; p++) {
+        const HostProfile &h = c->prof[p];
+        if (h.M > MAXM) {
+            c->err = "profile '" + h.name + "' has more than ITSX_MAXM match states";
+            return ITSX_ELIMIT;
+        }
+        if (h.bias_b >= 60) {
+            c->err = "profile '" + h.name + "': MSV bias outside the range the s16x2 kernel is exact for";
+            return ITSX_ELIMIT;
+        }
+        for (int j = 0; j < KP; j++)
+            for (int x = 0; x < 16; x++) {
+                int v[2];
+                for (int q = 0; q < 2; q++) {
+                    const int k = 2 * j + 1 + q;
+                    v[q] = (k <= h.M) ? h.bias_b - (int)h.cost[k * 16 + x] : -20000;
+                }
+                msvtab[((size_t)p * KP + j) * 16 + x] = ((uint32_t)(uint16_t)(int16_t)v[0]) | ((uint32_t)(uint16_t)(int16_t)v[1] << 16);
+            }
+        for (int k = 1; k <= h.M; k++)
+            for (int x = 0; x < 16; x++) etab[((size_t)p * (MAXM + 1) + k) * 16 + x] = h.e[k * 16 + x];
+        ProfConst &pc = c->pconst[p];
+        memset(&pc, 0, sizeof(pc));
+        for (int k = 0; k <= h.M; k++) {
+            for (int s = 0; s < 7; s++) pc.tp[k][s] = h.tp[k * 7 + s];
+            pc.tp[k][T_BM] = h.bm[k];
+        }
+        ProfScalars &q = ps[p];
+        memset(&q, 0, sizeof(q));
+        q.M = h.M; q.bias = h.bias_b; q.base = h.base_b; q.tbm = h.tbm_b; q.tec = h.tec_b;
+        q.side = (p < (int)c->side.size()) ? c->side[p] : -1;
+        q.scale_b = h.scale_b;
+        for (int i = 0; i < 6; i++) q.ev[i] = h.ev[i];
+        for (int x = 0; x < 16; x++) { q.eo[x][0] = h.eo[x][0]; q.eo[x][1] = h.eo[x][1]; }
+    }
+    CUDA_TRY(c, c->d_msvtab.ensure(msvtab.size() * 4));
+    CUDA_TRY(c, c->d_etab.ensure(etab.size() * 4));
+    CUDA_TRY(c, c->d_pscal.ensure(ps.size() * sizeof(ProfScalars)));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_msvtab.p, msvtab.data(), msvtab.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_etab.p, etab.data(), etab.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_pscal.p, ps.data(), ps.size() * sizeof(ProfScalars), cudaMemcpyHostToDevice, st));
+    if (!c->d_logsum.p) {
+        std::vector<float> tbl(16000);
+        for (int i = 0; i < 16000; i++) tbl[i] = (float)log(1. + exp((double)-i / 1000.0));
+        CUDA_TRY(c, c->d_logsum.ensure(16000 * 4));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_logsum.p, tbl.data(), 16000 * 4, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    c->prof_dirty = false;
+    return ITSX_OK;
+}
+
+static int ensure_lut(itsx_ctx *c)
+{
+    if (c->d_lut.p) return ITSX_OK;
+    uint8_t lut[256];
+    memset(lut, 15, sizeof(lut));
+    const char *sym = "ACGTRYMKSWHBVDN";
+    for (int i = 0; sym[i]; i++) {
+        lut[(unsigned char)sym[i]] = (uint8_t)i;
+        lut[(unsigned char)(sym[i] + 32)] = (uint8_t)i;
+    }
+    lut['U'] = lut['u'] = 3;
+    lut['X'] = lut['x'] = 14;
+    CUDA_TRY(c, c->d_lut.ensure(256));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_lut.p, lut, 256, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ITSX_OK;
+}
+
+// lengths -> word offsets -> nibble codes; per-length tables (nullsc, tjb) computed on the host
+static int build_seqs(itsx_ctx *c, const uint8_t *d_ascii, const int64_t *d_off, const int32_t *d_first, int64_t nseq)
+{
+    cudaStream_t st = c->stream;
+    int rc = ensure_lut(c);
+    if (rc) return rc;
+    c->nseq = nseq;
+    c->pos_valid = false;
+    c->stage1_done = c->stage2_done = false;
+    c->Lmax = 0;
+    if (nseq == 0) return ITSX_OK;
+    CUDA_TRY(c, c->d_seqlen.ensure((size_t)nseq * 4));
+    CUDA_TRY(c, c->d_seqwoff.ensure((size_t)(nseq + 1) * 8));
+    CUDA_TRY(c, c->d_scan.ensure((size_t)(nseq + 1) * 8));
+    int64_t *nw = c->d_scan.as<int64_t>();
+    seqlen_kernel<<<nblk(nseq, 256), 256, 0, st>>>(d_off, d_first, nseq, c->d_seqlen.as<int32_t>(), nw);
+    CUDA_TRY(c, cudaMemsetAsync(nw + nseq, 0, 8, st));
+    size_t tmpb = 0, tmpb2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmpb, nw, c->d_seqwoff.as<int64_t>(), (int)nseq + 1, st);
+    CUDA_TRY(c, c->d_counters.ensure(64 * 8));
+    int32_t *d_max = (int32_t *)(c->d_counters.as<unsigned long long>() + 40);
+    cub::DeviceReduce::Max(nullptr, tmpb2, c->d_seqlen.as<int32_t>(), d_max, (int)nseq, st);
+    CUDA_TRY(c, c->d_tmp.ensure(std::max(tmpb, tmpb2)));
+    cub::DeviceScan::ExclusiveSum(c->d_tmp.p, tmpb, nw, c->d_seqwoff.as<int64_t>(), (int)nseq + 1, st);
+    cub::DeviceReduce::Max(c->d_tmp.p, tmpb2, c->d_seqlen.as<int32_t>(), d_max, (int)nseq, st);
+    int64_t totw = 0;
+    int32_t lmax = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&totw, c->d_seqwoff.as<int64_t>() + nseq, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(&lmax, d_max, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    c->Lmax = lmax;
+    CUDA_TRY(c, c->d_seqw.ensure((size_t)(totw + 8) * 4));
+    seqcode_kernel<<<nblk(nseq * 32, 256), 256, 0, st>>>(d_ascii, d_off, d_first, nseq, c->d_seqwoff.as<int64_t>(),
+                                                         c->d_lut.as<uint8_t>(), c->d_seqw.as<uint32_t>());
+    c->launches += 4;
+    // per-length tables
+    std::vector<float> nullsc((size_t)lmax + 1);
+    std::vector<uint8_t> tjb((size_t)lmax + 1);
+    const float scale_b = (float)(3.0 / kLn2);
+    for (int L = 0; L <= lmax; L++) {
+        float p1 = (float)L / (float)(L + 1);
+        nullsc[L] = (float)((float)L * log((double)p1) + log(1. - (double)p1));
+        tjb[L] = msv_unbiased_byteify(scale_b, logf(3.0f / (float)(L + 3)));
+    }
+    CUDA_TRY(c, c->d_nullsc.ensure(((size_t)lmax + 1) * 4));
+    CUDA_TRY(c, c->d_tjb.ensure((size_t)lmax + 1));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_nullsc.p, nullsc.data(), nullsc.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_tjb.p, tjb.data(), tjb.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    CUDA_TRY(c, cudaGetLastError());
+    return ITSX_OK;
+}
+
+int search_build_seqs_from_derep(itsx_ctx *c)
+{
+    return build_seqs(c, c->d_ascii.as<uint8_t>(), c->d_off.as<int64_t>(), c->d_first.as<int32_t>(), c->n_unique);
+}
+
+int search_build_seqs_from_host(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64_t nseq)
+{
+    // staged through separate buffers so that the reads of a previous itsx_derep stay resident
+    static thread_local DevBuf t_ascii, t_off;
+    const int64_t total = nseq ? off[nseq] : 0;
+    CUDA_TRY(c, t_ascii.ensure((size_t)total + 64));
+    CUDA_TRY(c, t_off.ensure((size_t)(nseq + 1) * 8));
+    if (total) CUDA_TRY(c, cudaMemcpyAsync(t_ascii.p, seq, (size_t)total, cudaMemcpyHostToDevice, c->stream));
+    if (nseq) CUDA_TRY(c, cudaMemcpyAsync(t_off.p, off, (size_t)(nseq + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    c->shard_first = 0;
+    c->shard_n = -1;
+    return build_seqs(c, t_ascii.as<uint8_t>(), t_off.as<int64_t>(), nullptr, nseq);
+}
+
+static int ensure_lanes(itsx_ctx *c, int n)
+{
+    while ((int)c->lanes.size() < n) {
+        cudaStream_t s;
+        cudaEvent_t e;
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->lanes.push_back(s);
+        c->lane_ev.push_back(e);
+    }
+    if (!c->ev_a) {
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+    }
+    return ITSX_OK;
+}
+
+int search_stage1(itsx_ctx *c)
+{
+    cudaStream_t st = c->stream;
+    int rc = search_upload_profiles(c);
+    if (rc) return rc;
+    const int P = (int)c->prof.size();
+    itsx_search_stats &ss = c->sstats;
+    ss = itsx_search_stats{};
+    c->ndom = 0;
+    c->stage1_done = c->stage2_done = false;
+    c->pos_valid = false;
+    const int64_t q0 = c->shard_first;
+    const int64_t qn = c->shard_n < 0 ? c->nseq - q0 : c->shard_n;
+    if (q0 < 0 || qn < 0 || q0 + qn > c->nseq) { c->err = "search: shard outside the sequence set"; return ITSX_EINVAL; }
+    ss.n_seq = qn; ss.n_prof = P; ss.n_pairs = qn * P;
+    CUDA_TRY(c, c->d_counters.ensure(64 * 8));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_counters.p, 0, 32 * 8, st));
+    CUDA_TRY(c, c->d_nrep.ensure((size_t)std::max(P, 1) * 4));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_nrep.p, 0, (size_t)std::max(P, 1) * 4, st));
+    c->h_nrep.assign((size_t)P, 0);
+    if (P == 0 || qn == 0) { c->stage1_done = true; return ITSX_OK; }
+    const int NLANE = 8;
+    rc = ensure_lanes(c, NLANE);
+    if (rc) return rc;
+    unsigned long long *cnt = c->d_counters.as<unsigned long long>();
+
+    cudaEvent_t ev[8];
+    for (auto &e : ev) CUDA_TRY(c, cudaEventCreate(&e));
+    float acc_ms[6] = {0, 0, 0, 0, 0, 0};
+    CUDA_TRY(c, cudaEventRecord(ev[0], st));
+
+    const int ntile_p = (P + MSV_TP - 1) / MSV_TP;
+    const size_t msv_smem = (size_t)MSV_TP * KP * 16 * 4;
+    CUDA_TRY(c, cudaFuncSetAttribute(msv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msv_smem));
+
+    int64_t chunk = std::min<int64_t>(qn, std::max<int64_t>(1024, (1LL << 30) / P));
+    chunk = std::min<int64_t>(chunk, 1LL << 22);
+    const int Lmax = c->Lmax;
+    // total residues of the shard, for cell accounting
+    double sumL = 0;
+    {
+        size_t tmpb = 0;
+        long long *d_sum = (long long *)(c->d_counters.as<unsigned long long>() + 41);
+        cub::DeviceReduce::Sum(nullptr, tmpb, c->d_seqlen.as<int32_t>() + q0, d_sum, (int)qn, st);
+        CUDA_TRY(c, c->d_tmp.ensure(tmpb));
+        cub::DeviceReduce::Sum(c->d_tmp.p, tmpb, c->d_seqlen.as<int32_t>() + q0, d_sum, (int)qn, st);
+        long long h = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&h, d_sum, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        sumL = (double)h;
+    }
+    double sumM = 0;
+    for (auto &h : c->prof) sumM += h.M;
+    ss.msv_cells = sumL * sumM;
+
+    const int fb_warps_per_lane = c->sm_count * 2 * (FB_THREADS / 32);
+    std::vector<int32_t> h_bounds((size_t)P + 1), h_envb((size_t)P + 1);
+    int32_t *d_nsel = (int32_t *)(c->d_counters.as<unsigned long long>() + 42);
+
+    for (int64_t s0 = q0; s0 < q0 + qn; s0 += chunk) {
+        const int ns = (int)std::min<int64_t>(chunk, q0 + qn - s0);
+        const size_t npair = (size_t)ns * P;
+        // ---- MSV ----
+        CUDA_TRY(c, cudaEventRecord(ev[1], st));
+        CUDA_TRY(c, c->d_msvres.ensure(npair));
+        CUDA_TRY(c, c->d_flag.ensure(npair + 16));
+        dim3 grid(nblk(ns, MSV_THREADS), ntile_p);
+        msv_kernel<<<grid, MSV_THREADS, msv_smem, st>>>(c->d_seqw.as<uint32_t>(), c->d_seqwoff.as<int64_t>(),
+                                                        c->d_seqlen.as<int32_t>(), s0, ns, c->d_msvtab.as<uint32_t>(),
+                                                        c->d_pscal.as<ProfScalars>(), P, c->d_tjb.as<uint8_t>(),
+                                                        c->d_nullsc.as<float>(), c->prm.F1,
+                                                        c->d_msvres.as<uint8_t>(), c->d_flag.as<uint8_t>());
+        c->launches++;
+        CUDA_TRY(c, cudaEventRecord(ev[2], st));
+        // ---- compact MSV survivors ----
+        CUDA_TRY(c, c->d_list.ensure(npair * 4 + 16));
+        size_t tmpb = 0;
+        cub::CountingInputIterator<int32_t> iota(0);
+        cub::DeviceSelect::Flagged(nullptr, tmpb, iota, c->d_flag.as<uint8_t>(), c->d_list.as<int32_t>(), d_nsel,
+                                   (int)npair, st);
+        CUDA_TRY(c, c->d_tmp.ensure(tmpb));
+        cub::DeviceSelect::Flagged(c->d_tmp.p, tmpb, iota, c->d_flag.as<uint8_t>(), c->d_list.as<int32_t>(), d_nsel,
+                                   (int)npair, st);
+        int32_t n1 = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&n1, d_nsel, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        ss.n_past_msv += n1;
+        if (n1 == 0) {
+            CUDA_TRY(c, cudaEventRecord(ev[3], st));
+            CUDA_TRY(c, cudaEventSynchronize(ev[3]));
+            float ms;
+            cudaEventElapsedTime(&ms, ev[1], ev[2]); acc_ms[0] += ms;
+            continue;
+        }
+        // ---- bias filter ----
+        CUDA_TRY(c, c->d_filtersc.ensure((size_t)n1 * 4));
+        CUDA_TRY(c, c->d_ndom.ensure((size_t)n1 + 16));   // reused as flag2 here
+        bias_kernel<<<nblk(n1, 128), 128, 0, st>>>(c->d_list.as<int32_t>(), d_nsel, s0, ns, c->d_seqw.as<uint32_t>(),
+                                                   c->d_seqwoff.as<int64_t>(), c->d_seqlen.as<int32_t>(),
+                                                   c->d_pscal.as<ProfScalars>(), c->d_msvres.as<uint8_t>(),
+                                                   c->d_tjb.as<uint8_t>(), c->prm.F1, c->d_filtersc.as<float>(),
+                                                   c->d_ndom.as<uint8_t>(), cnt);
+        CUDA_TRY(c, c->d_list2.ensure((size_t)n1 * 4 + 16));
+        CUDA_TRY(c, c->d_fsc2.ensure((size_t)n1 * 4 + 16));
+        int32_t *d_nsel2 = d_nsel + 1;
+        size_t tb1 = 0, tb2 = 0;
+        cub::DeviceSelect::Flagged(nullptr, tb1, c->d_list.as<int32_t>(), c->d_ndom.as<uint8_t>(),
+                                   c->d_list2.as<int32_t>(), d_nsel2, n1, st);
+        cub::DeviceSelect::Flagged(nullptr, tb2, c->d_filtersc.as<float>(), c->d_ndom.as<uint8_t>(),
+                                   c->d_fsc2.as<float>(), d_nsel2, n1, st);
+        CUDA_TRY(c, c->d_tmp.ensure(std::max(tb1, tb2)));
+        cub::DeviceSelect::Flagged(c->d_tmp.p, tb1, c->d_list.as<int32_t>(), c->d_ndom.as<uint8_t>(),
+                                   c->d_list2.as<int32_t>(), d_nsel2, n1, st);
+        cub::DeviceSelect::Flagged(c->d_tmp.p, tb2, c->d_filtersc.as<float>(), c->d_ndom.as<uint8_t>(),
+                                   c->d_fsc2.as<float>(), d_nsel2, n1, st);
+        CUDA_TRY(c, c->d_bounds.ensure((size_t)(P + 1) * 8));
+        bounds_kernel<<<nblk(P + 1, 128), 128, 0, st>>>(c->d_list2.as<int32_t>(), d_nsel2, ns, P,
+                                                        c->d_bounds.as<int32_t>());
+        c->launches += 2;
+        int32_t n2 = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&n2, d_nsel2, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(h_bounds.data(), c->d_bounds.p, (size_t)(P + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaEventRecord(ev[3], st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        ss.n_past_bias += n2;
+        {
+            float ms;
+            cudaEventElapsedTime(&ms, ev[1], ev[2]); acc_ms[0] += ms;
+            cudaEventElapsedTime(&ms, ev[2], ev[3]); acc_ms[1] += ms;
+        }
+        if (n2 == 0) continue;
+
+        // ---- Forward / Backward / regions: one launch per profile over side streams ----
+        CUDA_TRY(c, c->d_fwdsc.ensure((size_t)n2 * 4));
+        CUDA_TRY(c, c->d_pairout.ensure((size_t)n2 * 4));
+        CUDA_TRY(c, c->d_ndom.ensure((size_t)n2 + 16));
+        CUDA_TRY(c, c->d_env.ensure((size_t)n2 * ITSX_MAXDOM * 2 * 4));
+        const size_t slab = (size_t)(Lmax + 1) * SPEC_C * 32 * 4;
+        CUDA_TRY(c, c->d_spec.ensure(slab * fb_warps_per_lane * NLANE));
+        CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
+        for (int l = 0; l < NLANE; l++) CUDA_TRY(c, cudaStreamWaitEvent(c->lanes[l], c->ev_a, 0));
+        int lane_rr = 0;
+        for (int p = 0; p < P; p++) {
+            const int b0 = h_bounds[p], cntp = h_bounds[p + 1] - b0;
+            if (cntp <= 0) continue;
+            const int l = lane_rr++ % NLANE;
+            FbArgs fa;
+            fa.list = c->d_list2.as<int32_t>() + b0;
+            fa.filtersc = c->d_fsc2.as<float>() + b0;
+            fa.count = cntp; fa.s0 = s0; fa.ns = ns; fa.prof = p;
+            fa.seqw = c->d_seqw.as<uint32_t>(); fa.woff = c->d_seqwoff.as<int64_t>(); fa.seqlen = c->d_seqlen.as<int32_t>();
+            fa.etab = c->d_etab.as<float>() + (size_t)p * (MAXM + 1) * 16;
+            fa.spec = (float *)(c->d_spec.as<char>() + slab * fb_warps_per_lane * l);
+            fa.Lmax = Lmax;
+            fa.tau = c->prof[p].ev[EV_FTAU]; fa.lambda = c->prof[p].ev[EV_FLAMBDA];
+            fa.F3 = c->prm.F3;
+            fa.e_move = expf(-(float)kLn2);
+            fa.fwdsc = c->d_fwdsc.as<float>() + b0;
+            fa.bcksc = c->d_pairout.as<float>() + b0;
+            fa.ndom = c->d_ndom.as<uint8_t>() + b0;
+            fa.env = c->d_env.as<int32_t>() + (size_t)b0 * ITSX_MAXDOM * 2;
+            fa.counters = cnt;
+            const int tiles = (cntp + 31) / 32;
+            const int ctas = std::min((tiles + 3) / 4, c->sm_count * 2);
+            fb_kernel<<<ctas, FB_THREADS, 0, c->lanes[l]>>>(c->pconst[p], fa);
+            c->launches++;
+        }
+        for (int l = 0; l < NLANE; l++) {
+            CUDA_TRY(c, cudaEventRecord(c->lane_ev[l], c->lanes[l]));
+            CUDA_TRY(c, cudaStreamWaitEvent(st, c->lane_ev[l], 0));
+        }
+        CUDA_TRY(c, cudaEventRecord(ev[4], st));
+
+        // ---- envelope worklist ----
+        CUDA_TRY(c, c->d_scan.ensure((size_t)(n2 + 1) * 4));
+        CUDA_TRY(c, c->d_envoff.ensure((size_t)(n2 + 1) * 4));
+        ndom_widen_kernel<<<nblk(n2 + 1, 256), 256, 0, st>>>(c->d_ndom.as<uint8_t>(), n2, c->d_scan.as<int32_t>());
+        size_t tb3 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb3, c->d_scan.as<int32_t>(), c->d_envoff.as<int32_t>(), n2 + 1, st);
+        CUDA_TRY(c, c->d_tmp.ensure(tb3));
+        cub::DeviceScan::ExclusiveSum(c->d_tmp.p, tb3, c->d_scan.as<int32_t>(), c->d_envoff.as<int32_t>(), n2 + 1, st);
+        gather_bounds_kernel<<<nblk(P + 1, 128), 128, 0, st>>>(c->d_envoff.as<int32_t>(), c->d_bounds.as<int32_t>(), P,
+                                                               c->d_bounds.as<int32_t>() + (P + 1));
+        c->launches += 2;
+        CUDA_TRY(c, cudaMemcpyAsync(h_envb.data(), c->d_bounds.as<int32_t>() + (P + 1), (size_t)(P + 1) * 4,
+                                    cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        const int nenv = h_envb[P];
+        if (nenv > 0) {
+            CUDA_TRY(c, c->d_envwork.ensure((size_t)nenv * 4));
+            CUDA_TRY(c, c->d_envout.ensure((size_t)nenv * 20 * 4));
+            envwork_kernel<<<nblk(n2, 256), 256, 0, st>>>(c->d_ndom.as<uint8_t>(), c->d_envoff.as<int32_t>(), n2,
+                                                          c->d_envwork.as<int32_t>());
+            c->launches++;
+            // envelopes are at most Lmax long; scratch per resident warp
+            const int Ldmax = Lmax;
+            const size_t eslab = (size_t)(Ldmax + 1) * ENV_ROWF * 32 * 4;
+            CUDA_TRY(c, c->d_envscratch.ensure(eslab * fb_warps_per_lane * NLANE));
+            CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
+            for (int l = 0; l < NLANE; l++) CUDA_TRY(c, cudaStreamWaitEvent(c->lanes[l], c->ev_b, 0));
+            lane_rr = 0;
+            for (int p = 0; p < P; p++) {
+                const int e0 = h_envb[p], cnte = h_envb[p + 1] - e0;
+                if (cnte <= 0) continue;
+                const int l = lane_rr++ % NLANE;
+                EnvArgs ea;
+                ea.work = c->d_envwork.as<int32_t>() + e0;
+                ea.count = cnte;
+                ea.list = c->d_list2.as<int32_t>();
+                ea.env = c->d_env.as<int32_t>();
+                ea.s0 = s0; ea.ns = ns; ea.prof = p;
+                ea.seqw = c->d_seqw.as<uint32_t>(); ea.woff = c->d_seqwoff.as<int64_t>(); ea.seqlen = c->d_seqlen.as<int32_t>();
+                ea.etab = c->d_etab.as<float>() + (size_t)p * (MAXM + 1) * 16;
+                ea.scratch = (float *)(c->d_envscratch.as<char>() + eslab * fb_warps_per_lane * l);
+                ea.Ldmax = Ldmax;
+                ea.out = c->d_envout.as<float>();
+                ea.out_base = e0;
+                ea.counters = cnt;
+                const int tiles = (cnte + 31) / 32;
+                const int ctas = std::min((tiles + 3) / 4, c->sm_count * 2);
+                env_kernel<<<ctas, FB_THREADS, 0, c->lanes[l]>>>(c->pconst[p], ea);
+                c->launches++;
+            }
+            for (int l = 0; l < NLANE; l++) {
+                CUDA_TRY(c, cudaEventRecord(c->lane_ev[l], c->lanes[l]));
+                CUDA_TRY(c, cudaStreamWaitEvent(st, c->lane_ev[l], 0));
+            }
+        }
+        CUDA_TRY(c, cudaEventRecord(ev[5], st));
+        // ---- scores ----
+        if (nenv > 0) {
+            CUDA_TRY(c, c->d_doms.ensure((size_t)(c->ndom + nenv) * sizeof(DomRec), true, st));
+            FinalArgs fa;
+            fa.list = c->d_list2.as<int32_t>(); fa.n = n2; fa.s0 = s0; fa.ns = ns;
+            fa.seqw = c->d_seqw.as<uint32_t>(); fa.woff = c->d_seqwoff.as<int64_t>(); fa.seqlen = c->d_seqlen.as<int32_t>();
+            fa.pscal = c->d_pscal.as<ProfScalars>(); fa.nullsctab = c->d_nullsc.as<float>();
+            fa.logsum = c->d_logsum.as<float>(); fa.fwdsc = c->d_fwdsc.as<float>();
+            fa.ndom = c->d_ndom.as<uint8_t>(); fa.envoff = c->d_envoff.as<int32_t>(); fa.env = c->d_env.as<int32_t>();
+            fa.envout = c->d_envout.as<float>(); fa.T = c->prm.T;
+            fa.doms = c->d_doms.as<DomRec>() + c->ndom;
+            fa.nrep = c->d_nrep.as<int32_t>(); fa.counters = cnt;
+            final_kernel<<<nblk(n2, 128), 128, 0, st>>>(fa);
+            c->launches++;
+            c->ndom += nenv;
+        }
+        CUDA_TRY(c, cudaEventRecord(ev[6], st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        CUDA_TRY(c, cudaGetLastError());
+        {
+            float ms;
+            cudaEventElapsedTime(&ms, ev[3], ev[4]); acc_ms[2] += ms;
+            cudaEventElapsedTime(&ms, ev[4], ev[5]); acc_ms[3] += ms;
+            cudaEventElapsedTime(&ms, ev[5], ev[6]); acc_ms[4] += ms;
+        }
+    }
+    CUDA_TRY(c, cudaEventRecord(ev[7], st));
+    unsigned long long h_cnt[CNT_N];
+    CUDA_TRY(c, cudaMemcpyAsync(h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_nrep.data(), c->d_nrep.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    CUDA_TRY(c, cudaGetLastError());
+    ss.n_past_fwd = (int64_t)h_cnt[CNT_PAST_FWD];
+    ss.n_hits_reported = (int64_t)h_cnt[CNT_HITS_REPORTED];
+    ss.n_domains = c->ndom;
+    ss.n_multidomain_regions = (int64_t)h_cnt[CNT_MULTI];
+    ss.n_dom_overflow = (int64_t)h_cnt[CNT_DOM_OVERFLOW];
+    ss.bias_rows = (double)h_cnt[CNT_BIAS_ROWS];
+    ss.fwd_cells = (double)h_cnt[CNT_FWD_ROWS] * MAXM;
+    ss.bck_cells = (double)h_cnt[CNT_BCK_ROWS] * MAXM;
+    ss.env_cells = (double)h_cnt[CNT_ENV_ROWS] * MAXM * 2;
+    ss.ms_msv = acc_ms[0]; ss.ms_bias = acc_ms[1]; ss.ms_fwd = acc_ms[2]; ss.ms_env = acc_ms[3]; ss.ms_final = acc_ms[4];
+    ss.ms_bck = 0.f;
+    cudaEventElapsedTime(&ss.ms_total, ev[0], ev[7]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    c->stage1_done = true;
+    if (ss.n_dom_overflow > 0) {
+        c->err = "search: a hit had more than ITSX_MAXDOM envelopes";
+        return ITSX_ELIMIT;
+    }
+    return ITSX_OK;
+}
+
+int search_stage2(itsx_ctx *c)
+{
+    if (!c->stage1_done) { c->err = "search: stage2 before stage1"; return ITSX_EINVAL; }
+    cudaStream_t st = c->stream;
+    const int P = (int)c->prof.size();
+    const int64_t q0 = c->shard_first;
+    const int64_t qn = c->shard_n < 0 ? c->nseq - q0 : c->shard_n;
+    c->npos = qn;
+    CUDA_TRY(c, c->d_pos.ensure((size_t)std::max<int64_t>(qn, 1) * 9 * 4));
+    CUDA_TRY(c, c->d_best.ensure((size_t)std::max<int64_t>(qn, 1) * 2 * 8));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(c, cudaEventCreate(&e0));
+    CUDA_TRY(c, cudaEventCreate(&e1));
+    CUDA_TRY(c, cudaEventRecord(e0, st));
+    if (qn > 0) {
+        pos_init_kernel<<<nblk(qn, 256), 256, 0, st>>>(c->d_pos.as<int32_t>(), c->d_best.as<unsigned long long>(), qn);
+        c->launches++;
+    }
+    if (c->ndom > 0 && P > 0) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_nrep.p, c->h_nrep.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
+        unsigned long long *cnt = c->d_counters.as<unsigned long long>();
+        CUDA_TRY(c, cudaMemsetAsync(cnt + CNT_DOM_REPORTED, 0, 8, st));
+        select_kernel<<<nblk(c->ndom, 256), 256, 0, st>>>(c->d_doms.as<DomRec>(), c->ndom, c->d_nrep.as<int32_t>(),
+                                                          c->d_pscal.as<ProfScalars>(), c->prm.domE,
+                                                          c->d_best.as<unsigned long long>(), qn, q0, cnt);
+        best_kernel<<<nblk(c->ndom, 256), 256, 0, st>>>(c->d_doms.as<DomRec>(), c->ndom, c->d_pscal.as<ProfScalars>(),
+                                                        c->d_best.as<unsigned long long>(), qn, q0,
+                                                        c->d_pos.as<int32_t>());
+        c->launches += 2;
+        unsigned long long nr = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&nr, cnt + CNT_DOM_REPORTED, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        c->sstats.n_domains_reported = (int64_t)nr;
+    }
+    CUDA_TRY(c, cudaEventRecord(e1, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    CUDA_TRY(c, cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->sstats.ms_final += ms;
+    c->sstats.ms_total += ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->stage2_done = true;
+    c->pos_valid = true;
+    return ITSX_OK;
+}
