@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ITSxpress hot path on B200.
+
+One "step" = one pass of the whole hot path (exact derep -> profile-HMM cascade -> boundary selection
+-> trim bounds for every read) over one synthetic sample of BASELINE.json configs[1]
+(1 M single-end 250 bp ITS1 reads, 30 % unique).  F.hmm (Fungi) is missing from the reference mount,
+so the largest present analogue M.hmm (Metazoa, 98 ITS1 profiles) stands in -- stated in `config`.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--scale S] [--impl reference]
+
+value  reads/s with the reads resident in HBM when the timed region starts (itsx_run_resident)
+e2e    reads/s through the C-ABI call with pinned HOST buffers (itsx_run: H2D + kernels + D2H)
+N > 1  (torchrun, one rank per GPU): every rank processes its own sample (QIIME2 artifacts are
+       many independent samples) -> weak scaling, no data-path collective; time = max over ranks.
+--impl reference  times the CPU oracle (restatement of vsearch + hmmsearch + ItsPosition + trim, all host
+       threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import synth  # noqa: E402
+
+INT_OPS_PER_2CELLS = 3.0      # vmax, viaddmax, max-into-xE: the algorithmic minimum of one s16x2 MSV step
+FP_OPS_PER_CELL = 11.0        # Forward (and Backward): FMA-pipe instructions per M/I/D cell
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    d = {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            d.update(hbm_gbs=float(j["hbm_gbs"]), sm_max_mhz=float(j.get("sm_max_mhz", 1965.0)), source="measured")
+        except Exception:
+            pass
+    f = d["sm_max_mhz"] * 1e6
+    d["int_gcups"] = 148 * 4 * 16 * f * 2.0 / INT_OPS_PER_2CELLS / 1e9      # 16 int lanes/clk/SMSP
+    d["fp_gcups"] = 148 * 128 * f / FP_OPS_PER_CELL / 1e9
+    return d
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(seq, off, which, frac_mod=50, pick=7):
+    """Bounded sample that keeps the workload's unique fraction: all reads of every 50th unique."""
+    sel = np.flatnonzero((which % frac_mod) == pick)
+    lens = (off[1:] - off[:-1])[sel]
+    o = np.zeros(len(sel) + 1, np.int64)
+    o[1:] = np.cumsum(lens)
+    delta = np.repeat(off[sel] - o[:-1], lens)
+    s = seq[delta + np.arange(int(o[-1]), dtype=np.int64)]
+    return s, o, "all reads of every %dth unique (%d reads, %d uniques)" % (frac_mod, len(sel),
+                                                                             len(np.unique(which[sel])))
+
+
+def oracle_pipeline(O, db, side, seq, off, threads=0):
+    """derep -> search -> ItsPosition -> trim bounds on the CPU oracle; returns kept count."""
+    rep, strand, nu = O.derep(seq, off)
+    idx = np.flatnonzero(rep == np.arange(len(rep)))
+    lens = (off[1:] - off[:-1])[idx]
+    uoff = np.zeros(len(idx) + 1, np.int64)
+    uoff[1:] = np.cumsum(lens)
+    delta = np.repeat(off[idx] - uoff[:-1], lens)
+    useq = seq[delta + np.arange(int(uoff[-1]), dtype=np.int64)]
+    codes = O.digitize(useq.tobytes())
+    rows, nrep, st = db.search(codes, uoff, O.default_params(threads))
+    pos = O.itspos(rows, side, lens.astype(np.int32))
+    n = len(rep)
+    s_r = np.full(n, -1, np.int32); e_r = s_r.copy(); t_r = s_r.copy()
+    s_r[idx] = pos["start"]; e_r[idx] = pos["stop"]; t_r[idx] = pos["tlen"]
+    keep, lo, hi = O.trim_bounds(off, rep, s_r, e_r, t_r, mode=0)
+    return int(keep.sum()), st
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.lib()
+    seq, off, which, cfg = synth.make_config("c2", scale=args.scale)
+    s, o, desc = cpu_sample(seq, off, which)
+    paths = [os.path.join(synth.HMM_DIR, cfg["hmm_file"])]
+    db = O.ProfileDB(paths, [cfg["left_prefix"], cfg["right_prefix"]])
+    side = np.array([0 if n.startswith(cfg["left_prefix"]) else 1 for n in db.names], np.int8)
+    cores = os.cpu_count()
+    for _ in range(min(args.warmup, 1)):
+        oracle_pipeline(O, db, side, s, o)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_pipeline(O, db, side, s, o)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = (len(o) - 1) / dt
+    line = {"impl": "reference", "metric": "reads/s", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8+f32", "data": "synthetic",
+            "config": workload_config(cfg, args),
+            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(cfg, args):
+    return {"workload": "BASELINE configs[1]: %d single-end %d bp ITS1 reads, %d unique (Zipf s=1), --region ITS1, "
+                        "profiles = %s %s_/%s_ (F.hmm missing from the reference mount)" %
+                        (cfg["n_reads"], cfg["length"], cfg["n_unique"], cfg["hmm_file"], cfg["left_prefix"][0],
+                         cfg["right_prefix"][0]),
+            "taxa": cfg["taxa"], "region": cfg["region"], "scale": args.scale,
+            "l2_policy": "inputs (%.0f MB of read bytes per step) are larger than the 126 MB L2" %
+                         (cfg["n_reads"] * cfg["length"] / 1e6),
+            "parallelism": "1 sample per GPU (independent samples, no data-path collective)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (testing only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from itsxpress_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = _lib.Context(local)
+    # every rank gets its own sample (different seed)
+    seq, off, which, cfg = synth.make_config("c2", seed=2 * 1_000_003 + rank, scale=args.scale)
+    nreads = len(off) - 1
+    ctx.load_profiles([os.path.join(synth.HMM_DIR, cfg["hmm_file"])], [cfg["left_prefix"], cfg["right_prefix"]])
+    ctx.set_sides_by_prefix(cfg["left_prefix"], cfg["right_prefix"])
+    prm = _lib.default_params()
+
+    # pinned host staging for the e2e leg
+    pin_in = _lib.PinnedBuffer(seq.nbytes + off.nbytes + 64)
+    pseq = pin_in.array(np.uint8, seq.size)
+    poff = pin_in.array(np.int64, off.size, offset=(seq.nbytes + 63) // 64 * 64)
+    pseq[:] = seq
+    poff[:] = off
+    pin_out = _lib.PinnedBuffer(nreads * 13 + 256)
+    o_rep = pin_out.array(np.int32, nreads, 0)
+    o_lo = pin_out.array(np.int32, nreads, nreads * 4)
+    o_hi = pin_out.array(np.int32, nreads, nreads * 8)
+    o_keep = pin_out.array(np.uint8, nreads, nreads * 12)
+    outs = dict(rep=o_rep, keep=o_keep, lo=o_lo, hi=o_hi)
+
+    ext = torch.cuda.ExternalStream(ctx.stream, device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        with torch.cuda.stream(ext):
+            e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    # ---- resident leg (value) ----
+    ctx.reads_upload(pseq, poff)
+    stage = {k: 0.0 for k in ("ms_msv", "ms_bias", "ms_fwd", "ms_env", "ms_final", "ms_total")}
+    dstage = {k: 0.0 for k in ("ms_pack", "ms_hash", "ms_insert", "ms_verify", "ms_compact", "ms_total")}
+    last = {}
+
+    def step_resident():
+        st = ctx.run_resident(prm)
+        ss, ds = ctx.search_stats(), ctx.derep_stats()
+        for k in stage:
+            stage[k] += getattr(ss, k)
+        for k in dstage:
+            dstage[k] += getattr(ds, k)
+        last["run"], last["search"], last["derep"] = st, ss, ds
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    for k in stage:
+        stage[k] = 0.0
+    for k in dstage:
+        dstage[k] = 0.0
+    clk = ClockSampler(local)
+    clk.start()
+    l0 = ctx.launch_count()
+    ms_dev, ms_wall = timed(step_resident, args.steps)
+    launches = ctx.launch_count() - l0
+    # ---- e2e leg: host buffers in, host buffers out ----
+    for _ in range(2):
+        ctx.run(pseq, poff, prm, out=outs)
+    ms_e2e_dev, ms_e2e_wall = timed(lambda: ctx.run(pseq, poff, prm, out=outs), args.steps)
+    clocks = clk.stop()
+
+    total_reads = nreads * world
+    value = total_reads / (ms_dev / 1e3 / args.steps)
+    e2e_v = total_reads / (max(ms_e2e_dev, ms_e2e_wall) / 1e3 / args.steps)
+    ss, ds, rs = last["search"], last["derep"], last["run"]
+    pk = peaks()
+    K = args.steps
+    sec = {k: v / 1e3 / K for k, v in stage.items()}
+    dsec = {k: v / 1e3 / K for k, v in dstage.items()}
+    L = cfg["length"]
+    stages = {
+        "msv": {"ms": sec["ms_msv"] * 1e3, "gcups": ss.msv_cells / max(sec["ms_msv"], 1e-9) / 1e9,
+                "peak_gcups": pk["int_gcups"], "bound": "int-alu (s16x2 DPX)"},
+        "fwd_bwd_decode": {"ms": sec["ms_fwd"] * 1e3,
+                           "gcups": (ss.fwd_cells + ss.bck_cells) / max(sec["ms_fwd"], 1e-9) / 1e9,
+                           "peak_gcups": pk["fp_gcups"], "bound": "fp32 fma"},
+        "envelope": {"ms": sec["ms_env"] * 1e3, "gcups": ss.env_cells / max(sec["ms_env"], 1e-9) / 1e9,
+                     "peak_gcups": pk["fp_gcups"], "bound": "fp32 fma / hbm scratch"},
+        "bias": {"ms": sec["ms_bias"] * 1e3, "rows_per_s": ss.bias_rows / max(sec["ms_bias"], 1e-9)},
+        "derep_pack": {"ms": dsec["ms_pack"] * 1e3,
+                       "gbs": ds.bytes_ascii * (1 + 0.25 + 0.125) / max(dsec["ms_pack"], 1e-9) / 1e9,
+                       "peak_gbs": pk["hbm_gbs"], "bound": "hbm"},
+        "derep_hash": {"ms": dsec["ms_hash"] * 1e3,
+                       "gbs": (ds.bytes_ascii * 0.25 + 25.0 * nreads) / max(dsec["ms_hash"], 1e-9) / 1e9,
+                       "peak_gbs": pk["hbm_gbs"], "bound": "hbm"},
+        "derep_insert_verify": {"ms": (dsec["ms_insert"] + dsec["ms_verify"]) * 1e3,
+                                "gbs": nreads * (L / 2 + 28.0) / max(dsec["ms_insert"] + dsec["ms_verify"], 1e-9) / 1e9,
+                                "peak_gbs": pk["hbm_gbs"], "bound": "hbm + atomics"},
+        "search_total_ms": sec["ms_total"] * 1e3, "derep_total_ms": dsec["ms_total"] * 1e3,
+        "survival": {"pairs": ss.n_pairs, "past_msv": ss.n_past_msv, "past_bias": ss.n_past_bias,
+                     "past_fwd": ss.n_past_fwd, "hits": ss.n_hits_reported, "domains": ss.n_domains,
+                     "multidomain_regions": ss.n_multidomain_regions},
+    }
+    dom = max(("msv", "fwd_bwd_decode", "envelope"), key=lambda k: stages[k]["ms"])
+    roof = {"kernel": {"msv": "msv_kernel", "fwd_bwd_decode": "fb_kernel", "envelope": "env_kernel"}[dom],
+            "bound": "alu", "achieved": stages[dom]["gcups"], "peak": stages[dom]["peak_gcups"], "unit": "GCUPS",
+            "frac": stages[dom]["gcups"] / stages[dom]["peak_gcups"], "traffic": None,
+            "note": "DP recurrence: integer/fp32 ALU bound, not HBM or tensor; peak = computed issue-rate peak at "
+                    "clocks.max.sm (%s HBM peak %.0f GB/s used for the derep kernels in `stages`)" %
+                    (pk["source"], pk["hbm_gbs"])}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        s, o, desc = cpu_sample(seq, off, which)
+        db = O.ProfileDB([os.path.join(synth.HMM_DIR, cfg["hmm_file"])], [cfg["left_prefix"], cfg["right_prefix"]])
+        side = np.array([0 if n.startswith(cfg["left_prefix"]) else 1 for n in db.names], np.int8)
+        t0 = time.perf_counter()
+        kept, ost = oracle_pipeline(O, db, side, s, o)
+        dt = time.perf_counter() - t0
+        cpu = {"value": (len(o) - 1) / dt, "unit": "reads/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": desc, "seconds": dt}
+
+    if rank == 0:
+        line = {"metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/s16x2 (MSV) + f32 (Forward/Backward)",
+                "data": "synthetic", "config": workload_config(cfg, args), "clocks": clocks,
+                "e2e": {"value": e2e_v, "unit": "reads/s", "h2d_bytes_per_step": int(seq.nbytes + off.nbytes),
+                        "d2h_bytes_per_step": int(nreads * 13), "ms_per_step": max(ms_e2e_dev, ms_e2e_wall) / args.steps},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "stages": stages,
+                "hmm_gcups": {"msv": stages["msv"]["gcups"], "fwd_bwd": stages["fwd_bwd_decode"]["gcups"],
+                              "envelope": stages["envelope"]["gcups"]},
+                "result": {"n_unique": int(rs.n_unique), "n_kept": int(rs.n_kept)}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

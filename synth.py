@@ -1,0 +1,162 @@
+"""Seeded synthetic amplicon generator for bench.py and the size-independent GPU tests.
+
+Shapes follow SURVEY.md section 8(d): reads are built as
+    [5' flank][SSU/5.8S-end motif sampled from a LEFT-boundary profile][random ITS spacer]
+    [5.8S/LSU-start motif sampled from a RIGHT-boundary profile][3' flank]
+so that the filter cascade sees realistic boundary motifs (random reads would make the search look
+2-3x cheaper than it is).  Motifs are sampled position by position from the match-emission
+distributions of profiles of the bundled ITSx_db (a tiny HMMER3 text reader lives here so that the
+generator does not depend on the product or on the oracle).  Abundances follow a Zipf law with every
+unique seen at least once; read order is a seeded permutation.
+"""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+HMM_DIR = os.path.join(ROOT, "itsxpress_b200", "ITSx_db", "HMMs")
+SHARPEN = 1.0   # exponent on the match-emission distributions when sampling motifs (1 = as the profile says)
+
+
+def read_match_emissions(path, prefixes):
+    """[(name, probs[M,4])] for profiles whose NAME starts with one of `prefixes`, file order."""
+    out = []
+    name, M, rows = None, 0, None
+    with open(path) as f:
+        lines = f.read().split("\n")
+    i = 0
+    while i < len(lines):
+        ln = lines[i]
+        if ln.startswith("NAME "):
+            name = ln[5:].strip()
+        elif ln.startswith("LENG "):
+            M = int(ln[5:])
+        elif ln.startswith("HMM "):
+            i += 2
+            if "COMPO" in lines[i]:
+                i += 1
+            i += 2          # node-0 insert emissions + transitions
+            rows = np.zeros((M, 4))
+            for k in range(M):
+                tok = lines[i].split()
+                rows[k] = [0.0 if t == "*" else np.exp(-float(t)) for t in tok[1:5]]
+                i += 3
+            if any(name.startswith(p) for p in prefixes):
+                out.append((name, rows / rows.sum(1, keepdims=True)))
+            continue
+        i += 1
+    return out
+
+
+def _sample_motifs(rng, profs, n):
+    """n motifs, each sampled from a random profile of `profs` -> list of uint8 arrays (ASCII)."""
+    pick = rng.integers(len(profs), size=n)
+    out = [None] * n
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    for p in range(len(profs)):
+        idx = np.flatnonzero(pick == p)
+        if len(idx) == 0:
+            continue
+        pr = profs[p][1]
+        # sharpen towards the consensus so that most motifs score like real boundaries
+        pr = pr ** SHARPEN
+        pr = pr / pr.sum(1, keepdims=True)
+        cum = np.cumsum(pr, axis=1)
+        u = rng.random((len(idx), pr.shape[0], 1))
+        codes = (u > cum[None, :, :]).sum(2).clip(0, 3)
+        letters = acgt[codes]
+        for j, i in enumerate(idx):
+            out[i] = letters[j]
+    return out
+
+
+def make_uniques(rng, n_unique, length, left_profs, right_profs, spacer=(110, 150), flank5=(5, 25),
+                 n_frac=0.005):
+    """n_unique distinct amplicons.  length: int (fixed, truncated/padded) or (lo, hi) (natural length)."""
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    left = _sample_motifs(rng, left_profs, n_unique)
+    right = _sample_motifs(rng, right_profs, n_unique)
+    f5 = rng.integers(flank5[0], flank5[1] + 1, n_unique)
+    sp = rng.integers(spacer[0], spacer[1] + 1, n_unique)
+    seqs = []
+    seen = set()
+    for i in range(n_unique):
+        while True:
+            if isinstance(length, tuple):
+                tot = int(rng.integers(length[0], length[1] + 1))
+            else:
+                tot = int(length)
+            core = np.concatenate([acgt[rng.integers(4, size=f5[i])], left[i], acgt[rng.integers(4, size=sp[i])],
+                                   right[i]])
+            if len(core) < tot:
+                core = np.concatenate([core, acgt[rng.integers(4, size=tot - len(core))]])
+            s = core[:tot].copy()
+            if rng.random() < n_frac:
+                s[int(rng.integers(tot))] = ord("N")
+            b = s.tobytes()
+            if b not in seen:
+                seen.add(b)
+                seqs.append(s)
+                break
+            sp[i] = rng.integers(spacer[0], spacer[1] + 1)
+    return seqs
+
+
+def zipf_counts(rng, n_reads, n_unique, s=1.0):
+    w = 1.0 / np.arange(1, n_unique + 1) ** s
+    w /= w.sum()
+    extra = rng.multinomial(n_reads - n_unique, w) if n_reads > n_unique else np.zeros(n_unique, np.int64)
+    return 1 + extra
+
+
+def make_reads(seed, n_reads, n_unique, length, hmm_file, left_prefix, right_prefix, zipf_s=1.0,
+               spacer=(110, 150), with_qual=False):
+    """Returns (seq uint8[total], off int64[n_reads+1], qual or None, unique_of_read int32[n_reads])."""
+    rng = np.random.default_rng(seed)
+    path = os.path.join(HMM_DIR, hmm_file)
+    lp = read_match_emissions(path, [left_prefix])
+    rp = read_match_emissions(path, [right_prefix])
+    uniq = make_uniques(rng, n_unique, length, lp, rp, spacer=spacer)
+    counts = zipf_counts(rng, n_reads, n_unique, zipf_s)
+    which = np.repeat(np.arange(n_unique, dtype=np.int32), counts)
+    rng.shuffle(which)
+    ulen = np.array([len(u) for u in uniq], np.int64)
+    uoff = np.zeros(n_unique + 1, np.int64)
+    uoff[1:] = np.cumsum(ulen)
+    ucat = np.concatenate(uniq)
+    lens = ulen[which]
+    off = np.zeros(n_reads + 1, np.int64)
+    off[1:] = np.cumsum(lens)
+    total = int(off[-1])
+    # gather: per-read source start - destination start, repeated
+    delta = np.repeat(uoff[which] - off[:-1], lens)
+    seq = ucat[delta + np.arange(total, dtype=np.int64)]
+    qual = None
+    if with_qual:
+        # Illumina-like: Q in [2, 41] with 3' decay
+        pos = np.arange(total, dtype=np.int64) - np.repeat(off[:-1], lens)
+        q = 38.0 - 20.0 * (pos / np.repeat(lens, lens)) ** 2 + rng.normal(0, 3, total)
+        qual = (np.clip(q, 2, 41).astype(np.uint8) + 33)
+    return seq, off, qual, which
+
+
+CONFIGS = {
+    # BASELINE.json configs[1]: 1 M single-end 250 bp fungal ITS1 reads, 30 % unique.  F.hmm (Fungi) is
+    # missing from the reference mount, so the largest present analogue M.hmm (Metazoa) stands in.
+    "c2": dict(n_reads=1_000_000, n_unique=300_000, length=250, hmm_file="M.hmm", left_prefix="1_",
+               right_prefix="2_", zipf_s=1.0, region="ITS1", taxa="Metazoa (stand-in for Fungi: F.hmm missing)"),
+    # reduced copy of the same shape for smoke tests
+    "c2_small": dict(n_reads=20_000, n_unique=6_000, length=250, hmm_file="M.hmm", left_prefix="1_",
+                     right_prefix="2_", zipf_s=1.0, region="ITS1", taxa="Metazoa"),
+}
+
+
+def make_config(name, seed=None, scale=1.0):
+    cfg = dict(CONFIGS[name])
+    meta = {k: cfg.pop(k) for k in ("region", "taxa")}
+    if scale != 1.0:
+        cfg["n_reads"] = max(1000, int(cfg["n_reads"] * scale))
+        cfg["n_unique"] = max(300, int(cfg["n_unique"] * scale))
+    seed = 2 * 1_000_003 if seed is None else seed
+    seq, off, qual, which = make_reads(seed, **cfg)
+    return seq, off, which, dict(cfg, **meta)
