@@ -1,0 +1,113 @@
+"""HMMER-free known-answer test of the oracle's profile parsing, configuration, MSV byte arithmetic and
+Forward recurrence.
+
+Every profile in ITSx_db carries hmmbuild's own calibration of exactly the scoring systems the search
+uses: `STATS LOCAL MSV mu lambda`, `STATS LOCAL FORWARD tau lambda`.  hmmbuild derives them as
+  lambda = ln 2 + 1.44 / (M * H)        H = mean match-state relative entropy (bits) vs f = 0.25
+  MSV mu    = ML Gumbel location at fixed lambda over random sequences of L = 200
+  Forward tau: complete-Gumbel ML fit over random sequences of L = 100, tail mass 0.04
+Re-deriving them from the oracle must land on the file's values (lambda exactly, mu/tau within the
+sampling noise of hmmbuild's own N = 200 simulation, ~0.3-0.5 bit); an error in tbm/tjb, the -3 nat
+correction, the entry distribution or the length model would show up as a multi-bit offset.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import HMM_DIR
+
+LN2 = 0.69314718055994529
+
+
+@pytest.fixture(scope="module")
+def db(oracle):
+    return oracle.ProfileDB([os.path.join(HMM_DIR, "A.hmm"), os.path.join(HMM_DIR, "M.hmm")], None)
+
+
+def _entropy_bits(mat):
+    p = mat[1:].astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.where(p > 0, p * np.log2(p / 0.25), 0.0)
+    return t.sum(1).mean()
+
+
+@pytest.mark.parametrize("p", [0, 1, 2, 50, 150, 300])
+def test_lambda_exact(db, p):
+    if p >= db.n:
+        pytest.skip("profile index beyond the loaded set")
+    mat, t, compo = db.raw(p)
+    M = db.M[p]
+    lam = LN2 + 1.44 / (M * _entropy_bits(mat))
+    ev = db.evparam(p)
+    assert abs(lam - ev[1]) < 2e-5          # MSV lambda
+    assert abs(lam - ev[5]) < 2e-5          # Forward lambda
+
+
+def _random_codes(rng, n, L):
+    return rng.integers(0, 4, size=(n, L), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("p", [0, 2, 200])
+def test_msv_mu(db, oracle, p):
+    rng = np.random.default_rng(100 + p)
+    ev = db.evparam(p)
+    lam = float(ev[1])
+    L = 200
+    nullsc = oracle.lib().ora_nullsc(L)
+    xs = []
+    for dsq in _random_codes(rng, 3000, L):
+        sc, ovf = db.msv_score(p, np.ascontiguousarray(dsq))
+        assert not ovf
+        xs.append((sc - nullsc) / LN2)
+    xs = np.array(xs, np.float64)
+    mu = -np.log(np.mean(np.exp(-lam * xs))) / lam
+    assert abs(mu - ev[0]) < 0.5, (mu, ev[0])
+
+
+@pytest.mark.parametrize("p", [0, 2, 200])
+def test_forward_tau(db, oracle, p):
+    rng = np.random.default_rng(200 + p)
+    ev = db.evparam(p)
+    lam = float(ev[5])
+    L = 100
+    nullsc = oracle.lib().ora_nullsc(L)
+    xs = np.array([(db.forward_score(p, np.ascontiguousarray(d)) - nullsc) / LN2
+                   for d in _random_codes(rng, 3000, L)], np.float64)
+    # complete-data Gumbel ML fit (Newton on lambda), as esl_gumbel_FitComplete
+    lg = np.pi / np.sqrt(6 * xs.var())
+    for _ in range(100):
+        e = np.exp(-lg * xs)
+        fx = 1.0 / lg - xs.mean() + (xs * e).sum() / e.sum()
+        dfx = ((xs * e).sum() / e.sum()) ** 2 - (xs * xs * e).sum() / e.sum() - 1.0 / lg ** 2
+        step = fx / dfx
+        lg -= step
+        if abs(step) < 1e-9:
+            break
+    mug = -np.log(np.mean(np.exp(-lg * xs))) / lg
+    tailp = 0.04
+    tau = mug - np.log(-np.log(1 - tailp)) / lg + np.log(tailp) / lam
+    assert abs(tau - ev[4]) < 0.6, (tau, ev[4])
+
+
+def test_forward_equals_backward(db):
+    rng = np.random.default_rng(9)
+    for p in (0, 5, 120):
+        for L in (30, 180, 400):
+            dsq = np.ascontiguousarray(rng.integers(0, 4, size=L, dtype=np.uint8))
+            f, b = db.forward_score(p, dsq), db.backward_score(p, dsq)
+            assert abs(f - b) < 2e-3 * max(1.0, abs(f)), (p, L, f, b)
+
+
+def test_short_models_present(oracle):
+    """G.hmm holds the two profiles with M < 45 (25 and 11 match states)."""
+    g = oracle.ProfileDB([os.path.join(HMM_DIR, "G.hmm")], ["1_"])
+    assert sorted(set(g.M)) == [11, 25, 45]
+
+
+def test_msv_profile_bytes(db):
+    cost, sc = db.msv_profile(0)
+    assert sc["base"] == 190 and sc["tec"] == 3          # byteify(ln 0.5) = round(3) third-bits
+    assert cost.shape == (db.M[0] + 1, 16)
+    assert 0 < sc["bias"] < 60
+    assert sc["tbm"] == int(round(-(3.0 / LN2) * np.log(2.0 / (45 * 46))))
