@@ -155,6 +155,11 @@ int  itsx_positions_set(itsx_ctx *ctx, const int32_t *start, const int32_t *stop
                         int64_t n);
 
 /* ---- trim + re-expansion ---------------------------------------------------------------- */
+/* Install a read -> unique map computed elsewhere (Dedup built from a uc.txt on disk, SeqSample.py:542-562,
+ * or another rank's derep): uid[i] in [0, n_unique) or -1 (read absent from the map -> dropped,
+ * SeqSample.py:817).  Replaces the map left by the last itsx_derep; the position table installed with
+ * itsx_positions_set / itsx_search must then have n_unique rows. */
+int  itsx_trim_set_map(itsx_ctx *ctx, const int32_t *uid, int64_t nreads, int64_t n_unique);
 /* mode: 0 = single-end / merged record[start:stop]           (SeqSample.py:862)
  *       2 = paired R1  [start:stop] or [start:] if stop>tlen  (SeqSample.py:639-645)
  *       1 = paired R2  [tlen-stop : tlen-start]               (SeqSample.py:640,648-655)

@@ -1,0 +1,576 @@
+"""Per-sample pipeline objects with the reference's names, arguments and error behaviour
+(itsxpress/SeqSample.py: SeqSample :18, SeqSampleNotPaired :228, SeqSamplePairedNotInterleaved :244,
+ItsPosition :368, Dedup :501) -- but ``deduplicate`` and ``_search`` run on the B200 through
+libitsx_b200 instead of shelling out to vsearch / hmmsearch, ItsPosition's arg-max runs on the device,
+and the per-read filter / slice / re-expansion of ``create_*trimmed_seqs`` is ``itsx_trim_*``.
+
+Stage hand-off stays what it is upstream: paths to ``uc.txt``, ``rep.fa`` and ``domtbl.txt`` in the temp
+directory, so ``ItsPosition(path, region)`` and ``Dedup(uc, rep, seq, ...)`` also work on files written by
+the real tools (that is how the reference's tests build them, tests/test_main_pytest.py:32-35,49-53).
+Objects created from files that a live GPU session just wrote additionally see that session's arrays and
+skip the text round trip.  There is no CPU implementation of the kernels here: without libitsx_b200 and a
+B200 these classes raise.
+"""
+import logging
+import os
+import shutil
+import subprocess
+
+import numpy as np
+
+from . import _lib
+from . import fastq as fq
+from . import host
+from .definitions import ROOT_DIR, REGION_PREFIXES, maxmismatches, vsearch_fastq_qmax
+
+logger = logging.getLogger(__name__)
+
+CCS_FWD = b"GACAGGTACAAGAAGGA"      # synthetic primers of --trim-ccs (SeqSample.py:601-603)
+CCS_REV = b"TTAACCCAGTCTCCAGT"
+
+_CTX = None
+_GENERATION = 0           # bumped whenever the shared context's resident sample / search changes
+_SESSIONS = {}            # abspath of uc.txt / rep.fa / domtbl.txt  ->  _Session that wrote it
+
+
+def get_context():
+    """The process-wide GPU context (one per process; device = LOCAL_RANK under torchrun, else 0)."""
+    global _CTX
+    if _CTX is None:
+        _CTX = _lib.Context(int(os.environ.get("ITSX_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+    return _CTX
+
+
+class _Session:
+    """What one sample leaves behind on the host after deduplicate() / _search()."""
+
+    def __init__(self):
+        self.batch = None          # FastqBatch of seq_file
+        self.ids = None            # record ids (first token of the title)
+        self.rep = None            # int32[n]  index of the representative read
+        self.uid = None            # int32[n]  dense unique id, first-occurrence order
+        self.first = None          # int32[U]  read index of every unique
+        self.n_unique = 0
+        self.derep_gen = -1        # _GENERATION at which the context held this sample's reads
+        self.search_gen = -1       # ... and this sample's search results
+        self.names = None
+        self.nseq = 0
+        self.seq_path = None
+        self.seq_ids = None
+
+
+def _external(tool, argv, what):
+    """Run one of the reference's external steps that are outside the GPU path (merge, orient, cluster)."""
+    try:
+        p = subprocess.run(argv, stderr=subprocess.PIPE)
+        logging.info(p.stderr.decode("utf-8"))
+        p.check_returncode()
+    except subprocess.CalledProcessError as e:
+        logging.exception("Could not perform %s with %s. Error from %s was:\n %s" % (what, tool, tool,
+                                                                                     p.stderr.decode("utf-8")))
+        raise e
+    except FileNotFoundError as f:
+        logging.error("%s was not found, make sure %s is installed and executable" % (tool, tool))
+        raise f
+
+
+class SeqSample:
+    """Base class: one sample on its way from FASTQ to trimmed FASTQ (reference SeqSample.py:18-225)."""
+
+    def __init__(self, fastq, tempdir):
+        self.tempdir = tempdir
+        self.fastq = fastq
+        self.uc_file = None
+        self.rep_file = None
+        self.dom_file = None
+        self.seq_file = None
+        self.r1 = None
+        self.fastq2 = None
+        self._session = None
+
+    # -- steps outside the named hot path: still the external tool, exactly as upstream ------------------
+    def orient_reads(self, threads=1):
+        """vsearch --orient against the universal reference (SeqSample.py:48-91); needs vsearch."""
+        oriented = os.path.join(self.tempdir, "oriented.fq")
+        _external("Vsearch", ["vsearch", "--orient", self.fastq, "--db",
+                              os.path.join(ROOT_DIR, "universal_orient_ref_clean.fasta.gz"),
+                              "--fastqout", oriented, "--threads", str(threads)], "read orientation")
+        self.fastq = self.seq_file = self.r1 = oriented
+
+    def cluster(self, threads, cluster_id=0.995):
+        """vsearch --cluster_size (SeqSample.py:133-176); approximate clustering is not part of the GPU path."""
+        self.uc_file = os.path.join(self.tempdir, "uc.txt")
+        self.rep_file = os.path.join(self.tempdir, "rep.fa")
+        _external("Vsearch", ["vsearch", "--cluster_size", self.seq_file, "--centroids", self.rep_file, "--uc",
+                              self.uc_file, "--strand", "both", "--id", str(cluster_id), "--threads",
+                              str(threads)], "clustering")
+
+    # -- the hot path ---------------------------------------------------------------------------------------
+    def deduplicate(self, threads=1):
+        """Exact full-length dereplication over both strands on the GPU; writes ``uc.txt`` and ``rep.fa`` in
+        vsearch's formats (replaces `vsearch --fastx_uniques`, SeqSample.py:93-131).  ``threads`` is accepted
+        and unused, as upstream (it is never passed to vsearch, :106-116)."""
+        global _GENERATION
+        try:
+            self.uc_file = os.path.join(self.tempdir, "uc.txt")
+            self.rep_file = os.path.join(self.tempdir, "rep.fa")
+            batch = fq.read_fastq(self.seq_file)
+            seq, off = batch.seq_concat()
+            ctx = get_context()
+            rep, strand, nu = ctx.derep(seq, off)
+            _GENERATION += 1
+            first, _ = ctx.derep_clusters(nu)
+            s = _Session()
+            s.batch, s.ids, s.rep, s.first, s.n_unique = batch, batch.ids(), rep, first, nu
+            s.uid = np.searchsorted(first, rep).astype(np.int32) if nu else np.zeros(0, np.int32)
+            s.derep_gen = _GENERATION
+            s.seq_path = os.path.abspath(self.seq_file)
+            order = host.cluster_order(rep, s.ids)
+            with open(self.rep_file, "wb") as f:
+                f.write(host.write_rep_fasta(batch, order, s.ids))
+            with open(self.uc_file, "wb") as f:
+                f.write(host.write_uc(rep, strand, s.ids, batch.s_len, order))
+            st = ctx.derep_stats()
+            logging.info("GPU dereplication: %d reads, %d unique sequences, %.2f ms on device" %
+                         (batch.n, nu, st.ms_total))
+            self._session = s
+            _SESSIONS[os.path.abspath(self.uc_file)] = s
+            _SESSIONS[os.path.abspath(self.rep_file)] = s
+        except FileNotFoundError as f:
+            logging.error("The sequence file %s could not be found." % self.seq_file)
+            raise f
+        except Exception as e:
+            logging.exception("Could not perform dereplication on the GPU.")
+            raise e
+
+    def _search(self, hmmfile, threads):
+        """Profile-HMM search of every representative against every profile of ``hmmfile`` on the GPU with
+        hmmsearch's thresholds ``-T 10 --F1 1e-6 --F2 1e-6 --F3 1e-6``; writes ``domtbl.txt``
+        (replaces SeqSample.py:178-225)."""
+        global _GENERATION
+        try:
+            self.dom_file = os.path.join(self.tempdir, "domtbl.txt")
+            if not os.path.exists(hmmfile):
+                raise FileNotFoundError(hmmfile)
+            ctx = get_context()
+            ctx.load_profiles([hmmfile], None)
+            s = self._session
+            resident = (s is not None and s.derep_gen == _GENERATION and
+                        os.path.abspath(self.rep_file) in _SESSIONS and _SESSIONS[os.path.abspath(self.rep_file)] is s)
+            if resident:
+                # representatives are already on the device, in first-occurrence order
+                ctx.set_sides(np.full(len(ctx.names), -1, np.int8))
+                ctx.search()
+                seq_ids = [s.ids[i] for i in s.first.tolist()]
+                nseq = s.n_unique
+            else:
+                seq_ids, seq, off = _read_fasta(self.rep_file)
+                s = _Session()
+                ctx.search_seqs(seq, off)
+                nseq = len(seq_ids)
+                self._session = s
+            _GENERATION += 1
+            s.search_gen = _GENERATION
+            if resident:
+                s.derep_gen = _GENERATION
+            s.names, s.nseq, s.seq_ids = list(ctx.names), nseq, seq_ids
+            rows = ctx.hits()
+            M = [ctx.profile_M(p) for p in range(len(ctx.names))]
+            with open(self.dom_file, "wb") as f:
+                f.write(host.write_domtbl(rows, seq_ids, ctx.names, M, nseq, ctx.nreported()))
+            st = ctx.search_stats()
+            logging.info("GPU hmmsearch: %d sequences x %d profiles, %d domain rows, %.1f ms on device" %
+                         (nseq, len(ctx.names), len(rows), st.ms_total))
+            _SESSIONS[os.path.abspath(self.dom_file)] = s
+        except FileNotFoundError as f:
+            logging.error("A file needed by the profile search was not found: %s" % f)
+            raise f
+        except Exception as e:
+            logging.exception("Could not perform ITS identification on the GPU.")
+            raise e
+
+
+class SeqSampleNotPaired(SeqSample):
+    """Single-end (or already merged) reads (reference SeqSample.py:228-241)."""
+
+    def __init__(self, fastq, tempdir):
+        SeqSample.__init__(self, fastq, tempdir)
+        self.seq_file = self.fastq
+        self.r1 = self.fastq
+        self.fastq2 = None
+
+
+class SeqSamplePairedNotInterleaved(SeqSample):
+    """Paired reads in two files (reference SeqSample.py:244-365)."""
+
+    def __init__(self, fastq, tempdir, fastq2, reversed_primers=False):
+        SeqSample.__init__(self, fastq, tempdir)
+        if reversed_primers:
+            self.r1, self.fastq2 = fastq2, fastq
+        else:
+            self.r1, self.fastq2 = fastq, fastq2
+
+    def _merge_reads(self, threads, stagger):
+        """Paired-end merging is upstream of the GPU path and stays `vsearch --fastq_mergepairs` with the
+        reference's flags (SeqSample.py:266-365); raises FileNotFoundError when vsearch is not installed."""
+        seq_file = os.path.join(self.tempdir, "seq.fq")
+        if not os.path.exists(self.tempdir):
+            logging.info("Expected %s to exist, but it does not. Creating it now." % self.tempdir)
+            os.makedirs(self.tempdir)
+        if self.r1 is None or self.fastq2 is None:
+            raise ValueError("Both r1 and fastq2 paths must be defined to merge reads.")
+        if self.r1.endswith(".zst") and self.fastq2.endswith(".zst"):
+            from . import _zstd
+            for attr, name in (("r1", "r1_temp.fq"), ("fastq2", "r2_temp.fq")):
+                tmp = os.path.join(self.tempdir, name)
+                with open(getattr(self, attr), "rb") as fi, open(tmp, "wb") as fo:
+                    fo.write(_zstd.decompress(fi.read()))
+                setattr(self, attr, tmp)
+        argv = ["vsearch", "--fastq_mergepairs", self.r1, "--reverse", self.fastq2, "--fastqout", seq_file,
+                "--fastq_maxdiffs", str(maxmismatches), "--fastq_maxee", str(2), "--threads", str(threads)]
+        if stagger:
+            argv.append("--fastq_allowmergestagger")
+        argv += ["--fastq_qmax", str(vsearch_fastq_qmax)]
+        self.seq_file = seq_file
+        _external("vsearch", argv, "read merging")
+
+
+def _read_fasta(path):
+    """(labels, bases uint8, off int64) of a FASTA file (the `rep.fa` hmmsearch would be given)."""
+    labels, parts = [], []
+    cur = None
+    with open(path, "rb") as f:
+        for line in f:
+            line = line.rstrip()
+            if line.startswith(b">"):
+                sp = line[1:].split(None, 1)
+                labels.append(sp[0].decode("ascii", "replace") if sp else "")
+                cur = []
+                parts.append(cur)
+            elif cur is not None and line:
+                cur.append(line)
+    seqs = [b"".join(p) for p in parts]
+    off = np.zeros(len(seqs) + 1, np.int64)
+    off[1:] = np.cumsum([len(x) for x in seqs])
+    return labels, np.frombuffer(b"".join(seqs), np.uint8), off
+
+
+class ItsPosition:
+    """ITS boundary positions per representative sequence (reference SeqSample.py:368-498).
+
+    ``ddict`` has the reference's shape ``{seq: {"left": {score, from_pos, to_pos}, "right": {...}, "tlen": n}}``.
+    When ``domtable`` was written by a live GPU search the per-sequence winners are taken straight from the
+    device (``itsx_positions``: arg-max of the printed 0.1-bit score per side, first row wins ties) and
+    ``ddict`` is only materialised if somebody looks at it.
+    """
+
+    def __init__(self, domtable, region):
+        self.domtable = domtable
+        self._ddict = None
+        if region in REGION_PREFIXES:
+            self.leftprefix, self.rightprefix = REGION_PREFIXES[region]
+        self.region = region
+        self._dev = None              # dict of int32 arrays from itsx_positions, per searched sequence
+        self._session = None
+        s = _SESSIONS.get(os.path.abspath(domtable)) if isinstance(domtable, str) else None
+        if s is not None and s.search_gen == _GENERATION and hasattr(self, "leftprefix"):
+            ctx = get_context()
+            ctx.set_sides_by_prefix(self.leftprefix, self.rightprefix)
+            ctx.search_stage2()
+            self._dev = ctx.positions(s.nseq)
+            self._session = s
+        else:
+            self.parse()
+
+    @property
+    def ddict(self):
+        if self._ddict is None:
+            self._ddict = {}
+            self.parse()
+        return self._ddict
+
+    @ddict.setter
+    def ddict(self, value):
+        self._ddict = value
+
+    def _score(self, sequence, stype, score, from_pos, to_pos, tlen):
+        """Keep the highest score per side; strict '>' so the first row wins ties (SeqSample.py:400-429)."""
+        entry = self._ddict[sequence]
+        best = entry.get(stype)
+        if best is None:
+            entry[stype] = {"score": score, "to_pos": to_pos, "from_pos": from_pos}
+            entry["tlen"] = tlen
+        elif score > best["score"]:
+            best["score"], best["to_pos"], best["from_pos"] = score, to_pos, from_pos
+
+    def parse(self):
+        """Read the domain table: columns 0 (target), 2 (tlen), 3 (profile), 13 (domain score), 19/20
+        (env from/to) -- SeqSample.py:431-461."""
+        if self._ddict is None:
+            self._ddict = {}
+        try:
+            with open(self.domtable, "r") as f:
+                for line in f:
+                    if line.startswith("#"):
+                        continue
+                    ll = line.split()
+                    sequence, hmmprofile = ll[0], ll[3]
+                    score, from_pos, to_pos, tlen = float(ll[13]), int(ll[19]), int(ll[20]), int(ll[2])
+                    if sequence not in self._ddict:
+                        self._ddict[sequence] = {}
+                    if hmmprofile.startswith(self.leftprefix):
+                        self._score(sequence, "left", score, from_pos, to_pos, tlen)
+                    elif hmmprofile.startswith(self.rightprefix):
+                        self._score(sequence, "right", score, from_pos, to_pos, tlen)
+        except Exception as e:
+            logging.error("Exception occurred when parsing HMMSearch results")
+            raise e
+
+    def get_position(self, sequence):
+        """(start, stop, tlen): start = left.to_pos, stop = right.from_pos - 1, 0-based; None when a side is
+        missing; KeyError when the sequence has no row at all (SeqSample.py:463-498)."""
+        try:
+            entry = self.ddict[sequence]
+            start = int(entry["left"]["to_pos"]) if "left" in entry else None
+            stop = int(entry["right"]["from_pos"]) - 1 if "right" in entry else None
+            tlen = int(entry["tlen"]) if "tlen" in entry else None
+            return (start, stop, tlen)
+        except KeyError:
+            logging.debug("No ITS stop or start sites were identified for sequence {}, skipping.".format(sequence))
+            raise KeyError
+
+
+class Dedup:
+    """Read -> representative map plus the trim / re-expansion step (reference SeqSample.py:501-949)."""
+
+    def __init__(self, uc_file, rep_file, seq_file, fastq=None, fastq2=None):
+        self._matchdict = None
+        self._matchdict_set = False
+        self.uc_file = uc_file
+        self.rep_file = rep_file
+        self.seq_file = seq_file
+        self.fastq = fastq
+        self.fastq2 = fastq2
+        s = _SESSIONS.get(os.path.abspath(uc_file)) if isinstance(uc_file, str) else None
+        self._session = s if (s is not None and s.rep is not None) else None
+        if self._session is None:
+            self.parse()
+
+    @property
+    def matchdict(self):
+        if self._matchdict is None and not self._matchdict_set:
+            self.parse()
+        return self._matchdict
+
+    @matchdict.setter
+    def matchdict(self, value):
+        self._matchdict = value
+        self._matchdict_set = True
+        self._session = None          # a hand-made map overrides the session's arrays
+
+    def parse(self):
+        """uc.txt: 'S' rows map a read to itself, 'H' rows to column 10; 'C' rows and the strand column are
+        ignored (SeqSample.py:542-562)."""
+        try:
+            md = {}
+            with open(self.uc_file, "r") as f:
+                for line in f:
+                    ll = line.split()
+                    if ll[0] == "S":
+                        md[ll[8]] = ll[8]
+                    elif ll[0] == "H":
+                        md[ll[8]] = ll[9]
+            self._matchdict = md
+        except Exception as e:
+            logging.exception("Could not parse the Vsearch '.uc' file.")
+            raise e
+
+    # ---- record-at-a-time API (duck-typed itspos; what the reference's unit tests drive) ---------------------
+    def _position_of(self, rec_id, itspos):
+        """(start, stop, tlen) of a read's representative, or None when the read must be dropped."""
+        md = self.matchdict
+        if md is None or rec_id not in md:
+            return None
+        try:
+            start, stop, tlen = itspos.get_position(md[rec_id])
+        except KeyError:
+            return None
+        if start is None or stop is None or not start < stop:
+            return None
+        return start, stop, tlen
+
+    @staticmethod
+    def _stitch(record):
+        q = record.letter_annotations.get("phred_quality")
+        quals = [93] * len(CCS_FWD) + (list(q) if q is not None else [93] * len(record)) + [93] * len(CCS_REV)
+        return fq.Record(CCS_FWD.decode() + str(record.seq) + CCS_REV.decode(), id=record.id, name=record.name,
+                         description=record.description, quals=quals)
+
+    @staticmethod
+    def _report_empty(records, label=""):
+        empty = [r.id for r in records if str(r.seq) == ""]
+        if empty:
+            print("Total number of sequences that are empty%s: " % label, len(empty))
+            print("Sequence IDs: ")
+            print(empty)
+
+    def _get_trimmed_seq_generator(self, seqgen, itspos, wri_file, trim_ccs=False):
+        """Generator of trimmed records in input order; reads without both boundaries (or with
+        start >= stop) are skipped; start == 0 is a valid coordinate (SeqSample.py:792-884)."""
+        if self.matchdict is None:
+            raise ValueError("matchdict must be parsed before calling sequence generators.")
+
+        def trimmed():
+            for record in seqgen:
+                pos = self._position_of(record.id, itspos)
+                if pos is None:
+                    continue
+                out = record[pos[0]:pos[1]]
+                yield self._stitch(out) if trim_ccs else out
+
+        if wri_file:
+            return trimmed()
+        done = list(trimmed())
+        self._report_empty(done)
+        return iter(done)
+
+    def _get_paired_seq_generator(self, zipseqgen, itspos, wri_file, trim_ccs=False):
+        """Two generators (forward, reverse) of trimmed records; R1 -> [start:stop] (or [start:] when
+        stop > tlen), R2 -> [tlen-stop : tlen-start] (SeqSample.py:564-711)."""
+        if self.matchdict is None:
+            raise ValueError("matchdict must be parsed before calling sequence generators.")
+
+        def pairs():
+            for rec1, rec2 in zipseqgen:
+                pos = self._position_of(rec1.id, itspos)
+                if pos is None:
+                    continue
+                start, stop, tlen = pos
+                if tlen is None:
+                    raise ValueError("Could not retrieve valid positions for sequence %s" % rec1.id)
+                r2start, r2end = tlen - stop, tlen - start
+                a = rec1[start:] if stop > tlen else rec1[start:stop]
+                b = rec2[r2start:] if r2end > tlen else rec2[r2start:r2end]
+                if trim_ccs:
+                    a, b = self._stitch(a), self._stitch(b)
+                yield a, b
+
+        if wri_file:
+            from itertools import tee
+            g1, g2 = tee(pairs(), 2)
+            return (a for a, _ in g1), (b for _, b in g2)
+        done = list(pairs())
+        self._report_empty([a for a, _ in done], " Split A")
+        self._report_empty([b for _, b in done], " Split B")
+        return (a for a, _ in done), (b for _, b in done)
+
+    # ---- bulk API: whole files through the GPU ---------------------------------------------------------------------
+    def _unique_table(self, ids, itspos):
+        """uid[read] (dense unique index or -1) and the (start, stop, tlen) table per unique for the reads
+        ``ids``.  Fast path: arrays of the live session; general path: matchdict + itspos.get_position (any
+        duck-typed object), evaluated once per distinct representative."""
+        s = self._session
+        if (s is not None and isinstance(itspos, ItsPosition) and itspos._dev is not None and
+                itspos._session is s and s.ids is not None):
+            dev = itspos._dev
+            if ids is s.ids:
+                uid = s.uid
+            else:
+                where = {k: i for i, k in enumerate(s.ids)}
+                uid = np.fromiter((s.uid[where[k]] if k in where else -1 for k in ids), np.int32, len(ids))
+            return uid, dev["start"], dev["stop"], dev["tlen"], s.n_unique
+        md = self.matchdict or {}
+        index, start, stop, tlen = {}, [], [], []
+        uid = np.full(len(ids), -1, np.int32)
+        for i, rid in enumerate(ids):
+            repid = md.get(rid)
+            if repid is None:
+                continue
+            u = index.get(repid)
+            if u is None:
+                u = index[repid] = len(start)
+                try:
+                    a, b, c = itspos.get_position(repid)
+                except KeyError:
+                    a = b = c = None
+                start.append(-1 if a is None else a)
+                stop.append(-1 if b is None else b)
+                tlen.append(-1 if c is None else c)
+            uid[i] = u
+        return (uid, np.asarray(start, np.int32), np.asarray(stop, np.int32), np.asarray(tlen, np.int32),
+                len(start))
+
+    def _trim_file(self, batch, ids, itspos, mode, trim_ccs):
+        """FASTQ text of ``batch`` trimmed on the GPU (mode 0 single, 2 paired R1, 1 paired R2)."""
+        global _GENERATION
+        uid, start, stop, tlen, nu = self._unique_table(ids, itspos)
+        if mode != 0 and np.any((tlen < 0) & (start >= 0) & (stop >= 0) & (start < stop)):
+            raise ValueError("Could not retrieve valid positions for a kept sequence (tlen is missing)")
+        ctx = get_context()
+        seq, off = batch.seq_concat()
+        qual, _ = batch.qual_concat()
+        ctx.trim_set_map(uid, nu)
+        ctx.positions_set(start, stop, tlen)
+        _GENERATION += 1                      # the context no longer holds any session's derep map
+        ki, oo, os_, oq = ctx.trim_gather(batch.n, mode=mode, seq=seq, qual=qual, off=off)
+        pre = (CCS_FWD, b"~" * len(CCS_FWD)) if trim_ccs else None
+        suf = (CCS_REV, b"~" * len(CCS_REV)) if trim_ccs else None
+        n_empty = int(np.count_nonzero(np.diff(oo) == 0))
+        return fq.format_gathered(batch, ki, oo, os_, oq, prefix=pre, suffix=suf), ki, n_empty
+
+    def create_trimmed_seqs(self, outfile, gzipped, zstd_file, itspos, wri_file, tempdir, trim_ccs=False):
+        """Write the reads of ``seq_file`` trimmed to the selected region, input order, plain / gz / zst
+        (SeqSample.py:886-949)."""
+        if self._session is not None and self._session.batch is not None and \
+                os.path.abspath(self.seq_file) == self._session.seq_path:
+            batch, ids = self._session.batch, self._session.ids
+        else:
+            batch = fq.read_fastq(self.seq_file)
+            ids = batch.ids()
+        text, ki, n_empty = self._trim_file(batch, ids, itspos, 0, trim_ccs)
+        if not wri_file:
+            if n_empty and not trim_ccs:
+                print("Total number of sequences that are empty: ", n_empty)
+            return
+        fq.write_compressed(outfile, text, gzipped=gzipped, zstd_file=zstd_file)
+
+    def create_paired_trimmed_seqs(self, outfile1, outfile2, gzipped, zstd_file, itspos, wri_file, trim_ccs=False):
+        """Write R1 and R2 trimmed but unmerged (for DADA2), input order (SeqSample.py:713-790)."""
+        if self.fastq is None or self.fastq2 is None:
+            raise ValueError("Both fastq and fastq2 paths must be defined to create paired trimmed sequences.")
+        f1, f2 = self.fastq, self.fastq2
+        plain = (".fastq", ".fq")
+        if not ((f1.endswith(".gz") and f2.endswith(".gz")) or (f1.endswith(".zst") and f2.endswith(".zst")) or
+                (f1.endswith(plain) and f2.endswith(plain))):
+            raise ValueError("Fastq and Fastq2 files should both be gzipped (.gz), zstd compressed (.zst) or both "
+                             "be uncompressed. Mixed input is not accepted.")
+        b1, b2 = fq.read_fastq(f1), fq.read_fastq(f2)
+        n = min(b1.n, b2.n)                     # zip() semantics
+        if b1.n != n:
+            b1 = _head(b1, n)
+        if b2.n != n:
+            b2 = _head(b2, n)
+        ids1 = b1.ids()                         # the filter is keyed on R1's id (SeqSample.py:591)
+        t1, k1, e1 = self._trim_file(b1, ids1, itspos, 2, trim_ccs)
+        t2, k2, e2 = self._trim_file(b2, ids1, itspos, 1, trim_ccs)
+        if not wri_file:
+            if (e1 or e2) and not trim_ccs:
+                print("Total number of sequences that are empty Split A: ", e1)
+                print("Total number of sequences that are empty Split B: ", e2)
+            return
+        fq.write_compressed(outfile1, t1, gzipped=gzipped, zstd_file=zstd_file)
+        fq.write_compressed(outfile2, t2, gzipped=gzipped, zstd_file=zstd_file)
+
+
+def _head(batch, n):
+    return fq.FastqBatch(batch.buf, batch.t_off[:n], batch.t_len[:n], batch.s_off[:n], batch.s_len[:n],
+                         batch.q_off[:n])
+
+
+def reset_sessions():
+    """Forget every live session (tests; long-running drivers between samples)."""
+    _SESSIONS.clear()
+
+
+__all__ = ["SeqSample", "SeqSampleNotPaired", "SeqSamplePairedNotInterleaved", "ItsPosition", "Dedup",
+           "get_context", "reset_sessions", "shutil"]

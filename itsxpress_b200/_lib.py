@@ -69,7 +69,7 @@ SYMBOLS = [
     "itsx_search_default_params", "itsx_search", "itsx_search_seqs", "itsx_search_get_stats", "itsx_hits",
     "itsx_nreported", "itsx_positions", "itsx_search_stage1", "itsx_search_seqs_stage1", "itsx_search_shard",
     "itsx_nreported_set", "itsx_search_stage2", "itsx_positions_set",
-    "itsx_trim_bounds", "itsx_trim_gather", "itsx_run", "itsx_reads_upload", "itsx_run_resident",
+    "itsx_trim_set_map", "itsx_trim_bounds", "itsx_trim_gather", "itsx_run", "itsx_reads_upload", "itsx_run_resident",
     "itsx_launch_count",
 ]
 
@@ -123,6 +123,7 @@ def lib():
     L.itsx_nreported_set.argtypes = [vp, vp]
     L.itsx_search_stage2.argtypes = [vp]
     L.itsx_positions_set.argtypes = [vp, vp, vp, vp, i64]
+    L.itsx_trim_set_map.argtypes = [vp, vp, i64, i64]
     L.itsx_trim_bounds.argtypes = [vp, C.c_int, vp, i64, vp, vp, vp, vp]
     L.itsx_trim_gather.argtypes = [vp, C.c_int, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
     L.itsx_run.argtypes = [vp, vp, vp, i64, C.POINTER(SearchParams), vp, vp, vp, vp, C.POINTER(RunStats)]
@@ -335,6 +336,11 @@ class Context:
         self._chk(lib().itsx_positions_set(self._h, _p(start), _p(stop), _p(tlen), len(start)))
 
     # ---- trim -------------------------------------------------------------------------------
+    def trim_set_map(self, uid, n_unique):
+        """Install a read -> unique map (uid[i] = -1: read is not in the map and is dropped)."""
+        uid = np.ascontiguousarray(uid, dtype=np.int32)
+        self._chk(lib().itsx_trim_set_map(self._h, _p(uid), len(uid), int(n_unique)))
+
     def trim_bounds(self, nreads, mode=0, off_other=None):
         keep = np.empty(nreads, np.uint8)
         lo = np.empty(nreads, np.int32)

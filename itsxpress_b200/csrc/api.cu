@@ -177,6 +177,7 @@ int itsx_reads_upload(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64
     c->nreads = nreads;
     c->total_bases = total;
     c->n_unique = 0;
+    c->map_external = false;
     c->pos_valid = false;
     const size_t padded = ((size_t)total + 15) / 16 * 16 + 32;
     CUDA_TRY(c, c->d_ascii.ensure(padded));
@@ -401,6 +402,22 @@ int itsx_positions_set(itsx_ctx *c, const int32_t *start, const int32_t *stop, c
 }
 
 // ---- trim ------------------------------------------------------------------------------------------
+int itsx_trim_set_map(itsx_ctx *c, const int32_t *uid, int64_t nreads, int64_t n_unique)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (nreads < 0 || n_unique < 0 || (nreads && !uid)) { c->err = "trim_set_map: bad argument"; return ITSX_EINVAL; }
+    if (nreads >= 0x7fffffffLL) { c->err = "trim_set_map: more than 2^31-1 reads in one call"; return ITSX_ELIMIT; }
+    CUDA_TRY(c, c->d_uid.ensure((size_t)std::max<int64_t>(nreads, 1) * 4));
+    if (nreads) CUDA_TRY(c, cudaMemcpyAsync(c->d_uid.p, uid, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->nreads = nreads;
+    c->n_unique = n_unique;
+    c->total_bases = 0;       // no resident read bytes: itsx_trim_* must be given seq/qual/off
+    c->map_external = true;
+    return ITSX_OK;
+}
+
 static int check_trim(itsx_ctx *c, int mode, int64_t nreads)
 {
     if (mode < 0 || mode > 2) { c->err = "trim: mode must be 0, 1 or 2"; return ITSX_EINVAL; }
@@ -416,6 +433,7 @@ int itsx_trim_bounds(itsx_ctx *c, int mode, const int64_t *off_other, int64_t nr
     CUDA_TRY(c, cudaSetDevice(c->device));
     int rc = check_trim(c, mode, nreads);
     if (rc) return rc;
+    if (c->map_external && !off_other) { c->err = "trim: offsets are required after itsx_trim_set_map"; return ITSX_EINVAL; }
     static thread_local DevBuf t_off, t_keep, t_lo, t_hi;
     CUDA_TRY(c, t_keep.ensure((size_t)nreads + 16));
     CUDA_TRY(c, t_lo.ensure((size_t)nreads * 4 + 16));
@@ -446,6 +464,11 @@ int itsx_trim_gather(itsx_ctx *c, int mode, const uint8_t *seq, const uint8_t *q
     int rc = check_trim(c, mode, nreads);
     if (rc) return rc;
     if (!n_kept || !total) return ITSX_EINVAL;
+    if (c->map_external && !off) { c->err = "trim: offsets are required after itsx_trim_set_map"; return ITSX_EINVAL; }
+    if (c->map_external && !seq && (out_seq || out_off || kept_index)) {
+        c->err = "trim: sequence bytes are required after itsx_trim_set_map";
+        return ITSX_EINVAL;
+    }
     static thread_local DevBuf t_off, t_seq, t_qual, t_keep, t_lo, t_hi, t_ki, t_oo, t_os, t_oq;
     cudaStream_t st = c->stream;
     const bool query = !out_seq && !out_off && !kept_index;

@@ -99,6 +99,7 @@ struct itsx_ctx {
     DevBuf d_counters;                // uint64 [32] device counters (see CNT_* below)
     DevBuf d_lut;                     // uint8 [256] ASCII -> residue code
     int64_t n_unique = 0;
+    bool map_external = false;        // d_uid installed by itsx_trim_set_map (no resident read bytes)
     int key_bits = 64;
     itsx_derep_stats dstats{};
 

@@ -1415,6 +1415,11 @@ int search_stage2(itsx_ctx *c)
     if (!c->stage1_done) { c->err = "search: stage2 before stage1"; return ITSX_EINVAL; }
     cudaStream_t st = c->stream;
     const int P = (int)c->prof.size();
+    {
+        // itsx_profiles_set_sides after stage1 (ItsPosition learns the region only now): refresh the tables
+        int rc = search_upload_profiles(c);
+        if (rc) return rc;
+    }
     const int64_t q0 = c->shard_first;
     const int64_t qn = c->shard_n < 0 ? c->nseq - q0 : c->shard_n;
     c->npos = qn;

@@ -187,3 +187,126 @@ def _scatter(dst, dst_off, src, src_off, length):
     np.cumsum(length, out=cs[1:])
     within = ar - np.repeat(cs[:-1], length)
     dst[np.repeat(dst_off, length) + within] = src[np.repeat(src_off.astype(np.int64), length) + within]
+
+
+def format_gathered(batch, keep_idx, out_off, out_seq, out_qual, prefix=None, suffix=None):
+    """FASTQ text from slices already gathered back to back on the device (itsx_trim_gather):
+    record t = title of batch[keep_idx[t]], bases out_seq[out_off[t]:out_off[t+1]], same for qualities.
+    prefix / suffix: (bases, quals) byte strings stitched to every record (--trim-ccs, SeqSample.py:601-622)."""
+    keep_idx = np.asarray(keep_idx, dtype=np.int64)
+    n = len(keep_idx)
+    if n == 0:
+        return b""
+    out_off = np.asarray(out_off, dtype=np.int64)
+    pre_s, pre_q = prefix if prefix else (b"", b"")
+    suf_s, suf_q = suffix if suffix else (b"", b"")
+    lp, ls = len(pre_s), len(suf_s)
+    tl = batch.t_len[keep_idx].astype(np.int64)
+    sl = out_off[1:] - out_off[:-1]
+    full = sl + lp + ls
+    rec_len = 1 + tl + 1 + full + 1 + 2 + full + 1
+    rec_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(rec_len, out=rec_off[1:])
+    out = np.empty(int(rec_off[-1]), dtype=np.uint8)
+    base = rec_off[:-1]
+    out[base] = ord("@")
+    _scatter(out, base + 1, batch.buf, batch.t_off[keep_idx], tl)
+    p = base + 1 + tl
+    out[p] = 10
+    p = p + 1
+    for src, pre, suf in ((out_seq, pre_s, suf_s), (out_qual, pre_q, suf_q)):
+        if lp:
+            out[(p[:, None] + np.arange(lp)[None, :]).ravel()] = np.tile(np.frombuffer(pre, np.uint8), n)
+        _scatter(out, p + lp, src, out_off[:-1], sl)
+        if ls:
+            out[((p + lp + sl)[:, None] + np.arange(ls)[None, :]).ravel()] = np.tile(np.frombuffer(suf, np.uint8), n)
+        q = p + full
+        out[q] = 10
+        if src is out_seq:
+            out[q + 1] = ord("+")
+            out[q + 2] = 10
+            p = q + 3
+    return out.tobytes()
+
+
+class Record:
+    """The slice of Biopython's SeqRecord that the reference's generators touch (SeqSample.py:586-670,
+    814-864): ``id``, ``name``, ``description``, ``seq`` (a str), ``letter_annotations['phred_quality']``,
+    ``len()``, slicing, and ``format('fastq')``."""
+
+    __slots__ = ("id", "name", "description", "seq", "letter_annotations")
+
+    def __init__(self, seq, id="<unknown id>", name="<unknown name>", description="<unknown description>",
+                 quals=None):
+        self.seq = str(seq)
+        self.id, self.name, self.description = id, name, description
+        self.letter_annotations = {}
+        if quals is not None:
+            self.letter_annotations["phred_quality"] = list(quals)
+
+    def __len__(self):
+        return len(self.seq)
+
+    def __getitem__(self, idx):
+        if not isinstance(idx, slice):
+            return self.seq[idx]
+        r = Record(self.seq[idx], self.id, self.name, self.description)
+        if "phred_quality" in self.letter_annotations:
+            r.letter_annotations["phred_quality"] = self.letter_annotations["phred_quality"][idx]
+        return r
+
+    def format(self, fmt="fastq"):
+        if fmt != "fastq":
+            raise ValueError("only the fastq format is supported")
+        q = self.letter_annotations.get("phred_quality")
+        if q is None:
+            raise ValueError("No suitable quality scores found in letter_annotations of SeqRecord")
+        title = self.description if self.description and self.description.split(None, 1)[0] == self.id else \
+            (self.id if not self.description or self.description == "<unknown description>" else
+             "%s %s" % (self.id, self.description))
+        return "@%s\n%s\n+\n%s\n" % (title, self.seq, "".join(chr(min(int(v), 93) + 33) for v in q))
+
+
+def iter_records(source):
+    """Records of a FASTQ path (plain / .gz / .zst), text handle or bytes, like SeqIO.parse(.., 'fastq')."""
+    if isinstance(source, (bytes, bytearray)):
+        data = bytes(source)
+    elif isinstance(source, str):
+        data = _open_bytes(source)
+    else:
+        data = source.read()
+        if isinstance(data, str):
+            data = data.encode()
+    b = parse_bytes(data)
+    for i in range(b.n):
+        title = b.title(i)
+        rid = title.split(None, 1)[0] if title.split() else ""
+        yield Record(b.seq(i), id=rid, name=rid, description=title,
+                     quals=[c - 33 for c in b.buf[int(b.q_off[i]):int(b.q_off[i]) + int(b.s_len[i])].tolist()])
+
+
+def write_compressed(path, data, gzipped=False, zstd_file=False, threads=8):
+    """Write FASTQ bytes plain, as gzip (independent members compressed in parallel -- a valid gzip stream
+    whose DECOMPRESSED bytes are what parity is judged on; gzip headers carry mtime, so compressed bytes are not
+    reproducible even reference-vs-reference) or as one zstd frame."""
+    if gzipped:
+        import zlib
+        from concurrent.futures import ThreadPoolExecutor
+
+        def member(chunk):
+            co = zlib.compressobj(6, zlib.DEFLATED, 31)
+            return co.compress(chunk) + co.flush()
+        step = 8 << 20
+        chunks = [data[i:i + step] for i in range(0, len(data), step)] or [b""]
+        with ThreadPoolExecutor(max(1, threads)) as ex:
+            parts = list(ex.map(member, chunks))
+        with open(path, "wb") as f:
+            for p in parts:
+                f.write(p)
+    elif zstd_file:
+        from . import _zstd
+        with open(path, "wb") as f:
+            f.write(_zstd.compress(data))
+    else:
+        with open(path, "wb") as f:
+            f.write(data)

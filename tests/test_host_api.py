@@ -1,0 +1,320 @@
+"""CPU tests of the reference-facing host layer (itsxpress_b200/SeqSample.py, main.py, fastq.py) and of the
+C-ABI's shape.  They mirror the reference's own unit tests (tests/test_main_pytest.py, cited per test);
+nothing here launches a kernel."""
+import ctypes
+import gzip
+import os
+import re
+import shutil
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import HMM_DIR, ROOT, TD
+
+from itsxpress_b200 import fastq as fq
+from itsxpress_b200 import main as cli
+from itsxpress_b200.SeqSample import Dedup, ItsPosition
+
+
+UC = os.path.join(TD, "ex_tmpdir", "uc.txt")
+SEQ = os.path.join(TD, "ex_tmpdir", "seq.fq.gz")
+REP = os.path.join(TD, "ex_tmpdir", "rep.fa")
+
+
+# ---- C ABI -------------------------------------------------------------------------------------------
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "itsx_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(itsx_[A-Za-z0-9_]+)\s*\(", text)))
+
+
+def test_abi_exports_every_declared_symbol():
+    from itsxpress_b200 import _lib
+    L = _lib.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 38
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert set(_lib.SYMBOLS) == set(declared)
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the product refuses to run (ITSX_ENODEV) instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from itsxpress_b200 import _lib
+    with pytest.raises(_lib.ItsxError) as e:
+        _lib.Context(0)
+    assert e.value.code == -1
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "itsxpress_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py") or f.endswith(".cu") or f.endswith(".cpp") or f.endswith(".h"):
+                src = open(os.path.join(dp, f), errors="replace").read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+# ---- FASTQ reader / writer (Biopython semantics) --------------------------------------
+def test_fastq_roundtrip_bytes():
+    raw = gzip.open(SEQ, "rb").read()
+    b = fq.parse_bytes(raw)
+    assert b.n == 227
+    assert fq.format_records(b, np.arange(b.n), np.zeros(b.n, np.int64), b.s_len) == raw
+    assert "".join(r.format("fastq") for r in fq.iter_records(SEQ)).encode() == raw
+
+
+def test_broken_fastq_raises_valueerror():
+    # reference tests/test_main_pytest.py:20-29
+    with pytest.raises(ValueError):
+        fq.read_fastq(os.path.join(TD, "broken.fastq"))
+    with pytest.raises(ValueError):
+        cli._check_fastqs(os.path.join(TD, "broken.fastq"))
+
+
+def test_check_fastqs_empty(tmp_path):
+    # reference :403-409
+    p = tmp_path / "empty.fastq"
+    p.write_text("")
+    cli._check_fastqs(str(p))
+
+
+def test_zstd_and_gzip_writers(tmp_path):
+    raw = gzip.open(SEQ, "rb").read()
+    fq.write_compressed(str(tmp_path / "a.gz"), raw, gzipped=True)
+    fq.write_compressed(str(tmp_path / "a.zst"), raw, zstd_file=True)
+    fq.write_compressed(str(tmp_path / "a.fq"), raw)
+    assert gzip.open(str(tmp_path / "a.gz"), "rb").read() == raw
+    assert fq.read_fastq(str(tmp_path / "a.zst")).n == 227
+    assert open(str(tmp_path / "a.fq"), "rb").read() == raw
+
+
+# ---- Dedup / ItsPosition from files -------------------------------------------------------------------------
+def test_dedup_parse():
+    # reference test_dedup :49-65
+    d = Dedup(uc_file=UC, rep_file=REP, seq_file=SEQ)
+    assert len(d.matchdict) == 227
+    assert d.matchdict["M02696:28:000000000-ATWK5:1:1101:11740:1800"] == "M02696:28:000000000-ATWK5:1:1101:10899:1561"
+    assert d.matchdict["M02696:28:000000000-ATWK5:1:1101:10899:1561"] == "M02696:28:000000000-ATWK5:1:1101:10899:1561"
+
+
+def _golden_domtbl(path):
+    """A domtbl with the rows the reference's fixture must have contained for two sequences
+    (tests/test_main_pytest.py:36-46) plus a losing and a tying sibling row."""
+    from itsxpress_b200.host import DOMTBL_HEADER
+    row = "%-20s -          %5d %-20s -             45 %9.2g %6.1f   0.0   1   1 %9.2g %9.2g %6.1f   0.0     1    45 %5d %5d %5d %5d 0.90 -\n"
+    a, b = "M02696:28:000000000-ATWK5:1:1101:19331:3209", "M02696:28:000000000-ATWK5:1:1101:23011:4341"
+    rows = [
+        (a, 341, "3_End_5_8S_fungi_a", 51.0, 85, 128),
+        (a, 341, "3_End_5_8S_fungi_b", 52.2, 84, 128),
+        (a, 341, "3_End_5_8S_fungi_c", 52.2, 80, 120),        # tie: the first 52.2 row wins
+        (a, 341, "4_Start_LSU_fungi_a", 59.1, 282, 326),
+        (a, 341, "4_Start_LSU_fungi_b", 40.0, 283, 326),
+        (b, 385, "4_Start_LSU_fungi_a", 34.0, 327, 370),
+    ]
+    with open(path, "w") as f:
+        f.write(DOMTBL_HEADER)
+        for t, tlen, q, sc, i, j in rows:
+            f.write(row % (t, tlen, q, 1e-10, sc, 1e-10, 1e-10, sc, i, j, i, j))
+        f.write("#\n# [ok]\n")
+
+
+def test_its_position_parse(tmp_path):
+    # reference test_its_position_init :32-46
+    p = str(tmp_path / "domtbl.txt")
+    _golden_domtbl(p)
+    its = ItsPosition(p, "ITS2")
+    exp1 = {"tlen": 341, "right": {"score": 59.1, "to_pos": 326, "from_pos": 282},
+            "left": {"score": 52.2, "to_pos": 128, "from_pos": 84}}
+    exp2 = {"tlen": 385, "right": {"score": 34.0, "to_pos": 370, "from_pos": 327}}
+    assert its.ddict["M02696:28:000000000-ATWK5:1:1101:19331:3209"] == exp1
+    assert its.ddict["M02696:28:000000000-ATWK5:1:1101:23011:4341"] == exp2
+    assert its.get_position("M02696:28:000000000-ATWK5:1:1101:19331:3209") == (128, 281, 341)
+    assert its.get_position("M02696:28:000000000-ATWK5:1:1101:23011:4341") == (None, 326, 385)
+    with pytest.raises(KeyError):
+        its.get_position("never-seen")
+
+
+def test_domtbl_emitter_is_parsed_back():
+    """host.write_domtbl -> ItsPosition.parse returns the rows' own values (columns 0, 2, 3, 13, 19, 20)."""
+    from itsxpress_b200 import _lib, host
+    rows = np.zeros(3, _lib.ROW_DTYPE)
+    rows["seq"] = [0, 0, 1]
+    rows["prof"] = [0, 1, 1]
+    rows["ienv"] = [84, 282, 300]
+    rows["jenv"] = [128, 326, 344]
+    rows["tlen"] = [341, 341, 400]
+    rows["bitscore"] = [52.24, 59.06, 33.96]
+    rows["seq_score"] = [52.0, 59.0, 33.0]
+    rows["lnP"] = rows["seq_lnP"] = [-40.0, -44.0, -20.0]
+    text = host.write_domtbl(rows, ["s0", "s1"], ["3_left", "4_right"], [45, 45], 2, np.array([1, 2]))
+    with tempfile.NamedTemporaryFile("wb", suffix=".txt", delete=False) as f:
+        f.write(text)
+    try:
+        its = ItsPosition(f.name, "ITS2")
+        assert its.get_position("s0") == (128, 281, 341)
+        assert its.ddict["s0"]["left"]["score"] == 52.2 and its.ddict["s0"]["right"]["score"] == 59.1
+        assert its.get_position("s1") == (None, 299, 400)
+        for line in text.decode().splitlines():
+            if not line.startswith("#"):
+                assert len(line.split()) == 23
+    finally:
+        os.unlink(f.name)
+
+
+# ---- record generators with duck-typed itspos (reference :412-509) -------------------------------------------
+class _Mock:
+    def __init__(self, pos):
+        self.pos = pos
+
+    def get_position(self, seq_id):
+        return self.pos
+
+
+def _dedup_seq1():
+    d = Dedup(uc_file=UC, rep_file=REP, seq_file=SEQ)
+    d.matchdict = {"seq1": "seq1"}
+    return d
+
+
+def test_coordinate_zero_not_falsy():
+    d = _dedup_seq1()
+    recs = [fq.Record("ATCG" * 50, id="seq1", description="")]
+    out = list(d._get_trimmed_seq_generator(iter(recs), _Mock((0, 10, 100)), wri_file=True))
+    assert len(out) == 1 and str(out[0].seq) == "ATCGATCGAT"
+
+
+def test_generator_exhaustion_wri_file_false():
+    d = _dedup_seq1()
+    recs = [fq.Record("ATCG" * 50, id="seq1", description="")]
+    out = list(d._get_trimmed_seq_generator(iter(recs), _Mock((5, 15, 100)), wri_file=False))
+    assert len(out) == 1 and len(out[0].seq) == 10
+
+
+def test_trim_ccs_stitching():
+    d = _dedup_seq1()
+    rec = fq.Record("N" * 50, id="seq1", description="", quals=[40] * 50)
+    out = list(d._get_trimmed_seq_generator(iter([rec]), _Mock((5, 15, 100)), wri_file=True, trim_ccs=True))
+    assert len(out) == 1
+    assert str(out[0].seq) == "GACAGGTACAAGAAGGA" + "N" * 10 + "TTAACCCAGTCTCCAGT"
+    assert out[0].letter_annotations["phred_quality"] == [93] * 17 + [40] * 10 + [93] * 17
+
+
+def test_generators_drop_unmapped_and_inverted():
+    d = _dedup_seq1()
+    recs = [fq.Record("ACGT" * 10, id="other"), fq.Record("ACGT" * 10, id="seq1")]
+    assert list(d._get_trimmed_seq_generator(iter(recs), _Mock((10, 10, 40)), True)) == []
+    assert list(d._get_trimmed_seq_generator(iter(recs), _Mock((None, 10, 40)), True)) == []
+
+    class Raises:
+        def get_position(self, s):
+            raise KeyError
+
+    assert list(d._get_trimmed_seq_generator(iter(recs), Raises(), True)) == []
+
+
+class _GoldenPos:
+    """get_position from the recovered golden table (= what the missing domtbl.txt fixture implied)."""
+
+    def __init__(self):
+        self.tab = {}
+        with open(os.path.join(ROOT, "tests", "golden", "c1_positions.tsv")) as f:
+            for line in f:
+                if not line.startswith("#"):
+                    k, a, b, c = line.split("\t")
+                    self.tab[k] = (int(a), int(b), int(c))
+
+    def get_position(self, k):
+        if k not in self.tab:
+            raise KeyError
+        return self.tab[k]
+
+
+def test_single_generator_golden_counts():
+    # reference test_dedup_create_trimmed_seqs :68-98 -> 226 records, 42 637 bases
+    d = Dedup(uc_file=UC, rep_file=REP, seq_file=SEQ)
+    out = list(d._get_trimmed_seq_generator(fq.iter_records(SEQ), _GoldenPos(), wri_file=True))
+    assert len(out) == 226
+    assert sum(len(r) for r in out) == 42637
+
+
+def test_paired_generator_golden_bytes():
+    # reference test_get_paired_seq_generator :350-375 and test_create_paired_trimmed_seqs :378-397
+    r1, r2 = os.path.join(TD, "4774-1-MSITS3_R1.fastq"), os.path.join(TD, "4774-1-MSITS3_R2.fastq")
+    d = Dedup(uc_file=UC, rep_file=REP, seq_file=SEQ, fastq=r1, fastq2=r2)
+    g1, g2 = d._get_paired_seq_generator(zip(fq.iter_records(r1), fq.iter_records(r2)), _GoldenPos(), wri_file=True)
+    a, b = list(g1), list(g2)
+    assert len(a) == 226 and len(b) == 226
+    assert "".join(r.format("fastq") for r in a).encode() == open(os.path.join(TD, "t2_r1.fq"), "rb").read()
+    assert "".join(r.format("fastq") for r in b).encode() == open(os.path.join(TD, "t2_r2.fq"), "rb").read()
+
+
+def test_paired_mixed_compression_rejected():
+    d = Dedup(uc_file=UC, rep_file=REP, seq_file=SEQ, fastq=os.path.join(TD, "4774-1-MSITS3_R1.fastq.gz"),
+              fastq2=os.path.join(TD, "4774-1-MSITS3_R2.fastq"))
+    with pytest.raises(ValueError):
+        d.create_paired_trimmed_seqs("/tmp/x1", "/tmp/x2", False, False, _GoldenPos(), True)
+    d2 = Dedup(uc_file=UC, rep_file=REP, seq_file=SEQ)
+    with pytest.raises(ValueError):
+        d2.create_paired_trimmed_seqs("/tmp/x1", "/tmp/x2", False, False, _GoldenPos(), True)
+
+
+# ---- CLI plumbing --------------------------------------------------------------------------------------------
+def test_is_paired():
+    # reference :196-204
+    assert cli._is_paired("fastq1.fq", "fastq2.fq", False)
+    assert not cli._is_paired("fastq1.fq", None, True)
+    assert not cli._is_paired("fastq1.fq", None, False)
+    with pytest.raises(AssertionError):
+        cli._is_paired(None, None, False)
+
+
+def test_myparser():
+    # reference :207-223
+    p = cli.myparser()
+    a = p.parse_args(["--fastq", "test.fastq", "--outfile", "test.out", "--region", "ITS2", "--taxa", "Fungi"])
+    assert a.fastq == "test.fastq" and a.outfile == "test.out" and a.region == "ITS2" and a.taxa == "Fungi"
+    assert a.threads == 1 and a.cluster_id == 1.0 and a.log == "ITSxpress.log" and a.allow_staggered_reads is True
+    assert not a.keeptemp and not a.single_end and not a.reversed_primers and not a.trim_ccs
+    assert p.parse_args(["-f", "a", "-o", "b", "--region", "ALL", "--taxa", " Rhizaria"]).taxa == " Rhizaria"
+    with pytest.raises(SystemExit):
+        p.parse_args(["-f", "a", "-o", "b", "--region", "ITS2", "--cluster_id", "0.9"])
+    with pytest.raises(SystemExit):
+        p.parse_args(["-f", "a", "-o", "b", "--region", "ITS3"])
+
+
+def test_create_runtime_hmm():
+    # reference :512-569 (Metazoa stands in for Fungi: F.hmm is missing from the mount)
+    tmp = tempfile.mkdtemp()
+    try:
+        def names(path):
+            return [l[6:].strip() for l in open(path) if l.startswith("NAME  ")]
+        for region, ok, bad in (("ITS2", ("3_", "4_"), ("1_", "2_")), ("ITS1", ("1_", "2_"), ("3_", "4_")),
+                                ("ALL", ("1_", "4_"), ("2_", "3_"))):
+            n = names(cli.create_runtime_hmm("Metazoa", region, tmp))
+            assert n and all(x.startswith(ok) and not x.startswith(bad) for x in n)
+        assert len(names(cli.create_runtime_hmm("Metazoa", "ITS2", tmp))) == 256
+        n_all = names(cli.create_runtime_hmm("All", "ITS2", tmp))
+        assert len(n_all) == 814 and all(x.startswith(("3_", "4_")) for x in n_all)
+        # a taxon whose file is absent gives an empty profile file (reference main.py:214-215)
+        assert names(cli.create_runtime_hmm("Fungi", "ITS2", tmp)) == [] or os.path.exists(os.path.join(HMM_DIR, "F.hmm"))
+    finally:
+        shutil.rmtree(tmp)
+
+
+def test_suffix_dispatch():
+    assert cli._suffix_flags("a.fq.gz") == (True, False)
+    assert cli._suffix_flags("a.fq.zst", "b.zst") == (False, True)
+    assert cli._suffix_flags("a.fq.gz", "b.fq") == (False, False)
+    assert cli._suffix_flags("a.fastq") == (False, False)
+
+
+def test_names_look_paired():
+    assert cli._names_look_paired("r1 1:N:0:1", "r1 2:N:0:1")
+    assert cli._names_look_paired("r1/1", "r1/2")
+    assert not cli._names_look_paired("r1 1:N:0:1", "r2 1:N:0:1")
