@@ -120,6 +120,9 @@ int  itsx_derep(itsx_ctx *ctx, const uint8_t *seq, const int64_t *off, int64_t n
                 int32_t *rep_index, uint8_t *strand, int64_t *n_unique);
 /* clusters in first-occurrence order: first_read[u], abundance[u], u < n_unique */
 int  itsx_derep_clusters(itsx_ctx *ctx, int32_t *first_read, int32_t *abundance);
+/* 64-bit canonical key (strand-independent, case-insensitive) of every unique, same order as
+ * itsx_derep_clusters: the owner rank of a class in the hash-partitioned multi-GPU derep is key % G. */
+int  itsx_derep_unique_keys(itsx_ctx *ctx, uint64_t *keys);
 int  itsx_derep_get_stats(const itsx_ctx *ctx, itsx_derep_stats *st);
 /* test hook: keep only the low `bits` bits of the 64-bit key (forces collisions); 64 = normal */
 int  itsx_derep_set_key_bits(itsx_ctx *ctx, int bits);

@@ -65,7 +65,7 @@ SYMBOLS = [
     "itsx_pinned_alloc", "itsx_pinned_free",
     "itsx_profiles_clear", "itsx_profiles_append_file", "itsx_profiles_count", "itsx_profile_name", "itsx_profile_M",
     "itsx_profiles_set_sides", "itsx_profile_msv",
-    "itsx_derep", "itsx_derep_clusters", "itsx_derep_get_stats", "itsx_derep_set_key_bits",
+    "itsx_derep", "itsx_derep_clusters", "itsx_derep_unique_keys", "itsx_derep_get_stats", "itsx_derep_set_key_bits",
     "itsx_search_default_params", "itsx_search", "itsx_search_seqs", "itsx_search_get_stats", "itsx_hits",
     "itsx_nreported", "itsx_positions", "itsx_search_stage1", "itsx_search_seqs_stage1", "itsx_search_shard",
     "itsx_nreported_set", "itsx_search_stage2", "itsx_positions_set",
@@ -107,6 +107,7 @@ def lib():
     L.itsx_profile_msv.argtypes = [vp, C.c_int, vp, vp]
     L.itsx_derep.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     L.itsx_derep_clusters.argtypes = [vp, vp, vp]
+    L.itsx_derep_unique_keys.argtypes = [vp, vp]
     L.itsx_derep_get_stats.argtypes = [vp, C.POINTER(DerepStats)]
     L.itsx_derep_set_key_bits.argtypes = [vp, C.c_int]
     L.itsx_search_default_params.argtypes = [C.POINTER(SearchParams)]
@@ -274,6 +275,11 @@ class Context:
         self._chk(lib().itsx_derep_clusters(self._h, _p(first), _p(ab)))
         return first, ab
 
+    def derep_unique_keys(self, n_unique):
+        keys = np.empty(n_unique, np.uint64)
+        self._chk(lib().itsx_derep_unique_keys(self._h, _p(keys)))
+        return keys
+
     def derep_stats(self):
         st = DerepStats()
         self._chk(lib().itsx_derep_get_stats(self._h, C.byref(st)))
@@ -292,6 +298,12 @@ class Context:
         self._nseq = len(off) - 1
         self._chk(lib().itsx_search_seqs(self._h, _p(seq), _p(off), len(off) - 1,
                                          C.byref(params) if params is not None else None))
+
+    def search_seqs_stage1(self, seq, off, params=None):
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        self._chk(lib().itsx_search_seqs_stage1(self._h, _p(seq), _p(off), len(off) - 1,
+                                                C.byref(params) if params is not None else None))
 
     def search_stage1(self, params=None):
         self._chk(lib().itsx_search_stage1(self._h, C.byref(params) if params is not None else None))

@@ -234,6 +234,30 @@ int itsx_derep_clusters(itsx_ctx *c, int32_t *first_read, int32_t *abundance)
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ITSX_OK;
 }
+__global__ void key_gather_kernel(const int32_t *__restrict__ first, const unsigned long long *__restrict__ key,
+                                  int64_t nu, unsigned long long *__restrict__ out)
+{
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < nu) out[u] = key[first[u]];
+}
+
+int itsx_derep_unique_keys(itsx_ctx *c, uint64_t *keys)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int64_t nu = c->n_unique;
+    if (nu == 0 || !keys) return ITSX_OK;
+    if (c->map_external) { c->err = "derep_unique_keys: no dereplicated reads are resident"; return ITSX_EINVAL; }
+    CUDA_TRY(c, c->d_list.ensure((size_t)nu * 8));
+    key_gather_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, c->stream>>>(c->d_first.as<int32_t>(),
+                                                                            c->d_key.as<unsigned long long>(), nu,
+                                                                            c->d_list.as<unsigned long long>());
+    c->launches++;
+    CUDA_TRY(c, cudaMemcpyAsync(keys, c->d_list.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ITSX_OK;
+}
+
 int itsx_derep_get_stats(const itsx_ctx *c, itsx_derep_stats *st)
 {
     CHECK_CTX(c);

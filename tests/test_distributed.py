@@ -1,0 +1,63 @@
+"""world_size-2 gloo test (CPU) of the sharded driver: results must equal the single-process pipeline on the
+concatenated input -- global first-occurrence representatives, strands, keep / lo / hi for every read."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _single(O, eng, seq, off):
+    rep, strand, nu = O.derep(seq, off)
+    idx = np.flatnonzero(rep == np.arange(len(rep)))
+    parts = [seq[off[i]:off[i + 1]] for i in idx]
+    uoff = np.zeros(len(idx) + 1, np.int64)
+    uoff[1:] = np.cumsum([len(p) for p in parts])
+    rows, nrep, st = eng.db.search(O.digitize(np.concatenate(parts).tobytes()), uoff)
+    pos = O.itspos(rows, eng.side, np.diff(uoff).astype(np.int32))
+    n = len(rep)
+    s = np.full(n, -1, np.int32); e = s.copy(); t = s.copy()
+    s[idx] = pos["start"]; e[idx] = pos["stop"]; t[idx] = pos["tlen"]
+    keep, lo, hi = O.trim_bounds(off, rep, s, e, t, mode=0)
+    return rep, strand, keep, lo, hi, nu, nrep
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_run_sharded_equals_single(tmp_path, world):
+    import dist_worker as W
+    port = 29650 + world
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_worker.py"), str(tmp_path)],
+                                      env=env))
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    seq, off = W.dataset()
+    O, eng = W.engine()
+    rep, strand, keep, lo, hi, nu, nrep = _single(O, eng, seq, off)
+    assert keep.sum() > 50 and strand.sum() >= 2
+    got = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    assert int(got[0]["blo"]) == 0 and int(got[-1]["bhi"]) == len(off) - 1
+    for k, want in (("rep", rep), ("strand", strand), ("keep", keep), ("lo", lo), ("hi", hi)):
+        assert np.array_equal(np.concatenate([g[k] for g in got]), want), k
+    for g in got:
+        assert int(g["n_unique_global"]) == nu
+        assert np.array_equal(g["nreported"], nrep)
+    assert sum(int(g["n_owned"]) for g in got) == nu
+
+
+def test_block_range_partitions():
+    from itsxpress_b200.distributed import block_range
+    for n in (0, 1, 7, 100):
+        for w in (1, 2, 3, 8):
+            blocks = [block_range(n, r, w) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in blocks) - min(b - a for a, b in blocks) <= 1

@@ -249,3 +249,30 @@ def test_whole_path_fixture(gpu_ctx, oracle, fixture_reads):
     assert np.array_equal(out["rep"], orep)
     assert np.array_equal(out["keep"], okeep)
     assert np.array_equal(out["lo"], olo) and np.array_equal(out["hi"], ohi)
+
+
+def test_run_sharded_single_rank_equals_itsx_run(gpu_ctx, fixture_reads):
+    """distributed.run_sharded with the GPU engine on one rank == itsx_run on the same reads."""
+    from itsxpress_b200.distributed import Comm, GpuEngine, run_sharded
+    b, seq, off, _ = fixture_reads
+    paths = [os.path.join(HMM_DIR, "M.hmm")]
+    gpu_ctx.load_profiles(paths, ["3_", "4_"])
+    gpu_ctx.set_sides_by_prefix("3_", "4_")
+    want, st = gpu_ctx.run(seq, off)
+    want = {k: v.copy() for k, v in want.items()}
+    got = run_sharded(GpuEngine(gpu_ctx), Comm(), seq, off, 0)
+    assert got["n_unique_global"] == st.n_unique
+    assert np.array_equal(got["rep"], want["rep"])
+    assert np.array_equal(got["keep"], want["keep"]) and int(got["keep"].sum()) == st.n_kept
+    assert np.array_equal(got["lo"], want["lo"]) and np.array_equal(got["hi"], want["hi"])
+
+
+def test_trim_set_map_drops_unmapped_reads(gpu_ctx):
+    off = np.array([0, 10, 20, 30], np.int64)
+    gpu_ctx.trim_set_map(np.array([0, -1, 1], np.int32), 2)
+    gpu_ctx.positions_set(np.array([2, 0], np.int32), np.array([8, 4], np.int32), np.array([10, 10], np.int32))
+    keep, lo, hi, nk = gpu_ctx.trim_bounds(3, mode=0, off_other=off)
+    assert keep.tolist() == [1, 0, 1] and nk == 2
+    assert (lo[0], hi[0], lo[2], hi[2]) == (2, 8, 0, 4)
+    with pytest.raises(Exception):
+        gpu_ctx.trim_bounds(3, mode=0)           # offsets are mandatory once the map is external
