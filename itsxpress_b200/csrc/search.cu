@@ -36,7 +36,7 @@ constexpr int MSV_TP = 32;                 // profiles per MSV tile (32 * 23 * 1
 constexpr int MSV_THREADS = 128;
 constexpr int FB_THREADS = 128;
 constexpr int SPEC_C = 5;                  // parser specials kept per row
-constexpr int ENV_ROWF = 2 * (MAXM + 1) + 4;   // floats per envelope row: M[0..45], I[0..45], Eraw, N, J, C
+constexpr int ENV_ROWF = MAXM + 1;             // floats per envelope row: M[1..45] (cols 0..44), Eraw (col 45)
 constexpr double kLn2 = 0.69314718055994529;
 
 inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
@@ -352,21 +352,25 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
         for (int i = 1; i <= Lw; i++) {
             if (i <= L) {
                 const float *er = s_e + residue_at(w, i - 1);
-                float mprev = 0.f, iprev = 0.f, dprev = 0.f, mcur = 0.f, dcur = 0.f, xEm = 0.f, xEd = 0.f;
+                // pass 1, descending k, in place: M and I of row i from row i-1 (no serial dependence, so the
+                // scheduler needs no far-ahead coefficient loads); pass 2, ascending: the D chain and the E sums.
+                // Same operations and summation order as the oracle's single ascending loop.
+#pragma unroll
+                for (int k = MAXM; k >= 1; k--) {
+                    float sv = xB * pc.fw[k][F_BM];
+                    sv = fmaf(Mx[k - 1], pc.fw[k][F_MM], sv);
+                    sv = fmaf(Ix[k - 1], pc.fw[k][F_IM], sv);
+                    sv = fmaf(Dx[k - 1], pc.fw[k][F_DM], sv);
+                    sv = sv * er[k * 16];
+                    const float ic = fmaf(Ix[k], pc.fw[k][F_II], Mx[k] * pc.fw[k][F_MI]);
+                    Mx[k] = sv; Ix[k] = ic;
+                }
+                float xEm = 0.f, xEd = 0.f, dcur = 0.f;
 #pragma unroll
                 for (int k = 1; k <= MAXM; k++) {
-                    float sv = xB * pc.tp[k][T_BM];
-                    sv = fmaf(mprev, pc.tp[k - 1][T_MM], sv);
-                    sv = fmaf(iprev, pc.tp[k - 1][T_IM], sv);
-                    sv = fmaf(dprev, pc.tp[k - 1][T_DM], sv);
-                    sv = sv * er[k * 16];
-                    const float dc = fmaf(dcur, pc.tp[k - 1][T_DD], mcur * pc.tp[k - 1][T_MD]);
-                    const float mp = Mx[k], ip = Ix[k], dp = Dx[k];
-                    const float ic = fmaf(ip, pc.tp[k][T_II], mp * pc.tp[k][T_MI]);
-                    Mx[k] = sv; Ix[k] = ic; Dx[k] = dc;
-                    xEm += sv; xEd += dc;
-                    mprev = mp; iprev = ip; dprev = dp;
-                    mcur = sv; dcur = dc;
+                    const float dc = fmaf(dcur, pc.fw[k][F_DD], Mx[k - 1] * pc.fw[k][F_MD]);
+                    Dx[k] = dc; dcur = dc;
+                    xEm += Mx[k]; xEd += dc;
                 }
                 xE = xEm + xEd;
                 xN = xN * N_loop;
@@ -580,7 +584,7 @@ struct EnvArgs {
     const int64_t  *woff;
     const int32_t  *seqlen;
     const float    *etab;
-    float          *scratch;  // warps_total * (Ldmax+1) * ENV_ROWF * 32 floats
+    float          *scratch;  // warps_total * (Ldmax+1) * ENV_ROWF * 32 floats (match rows + raw E)
     int             Ldmax;
     float          *out;      // [envelope][20]: envsc, domcorrection, null2[16], pad
     int             out_base; // index of this slice's first envelope in the batch numbering
@@ -599,7 +603,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
     const int ntiles = (a.count + 31) >> 5;
     float *sc = a.scratch + (size_t)warp_in_grid * (size_t)(a.Ldmax + 1) * ENV_ROWF * 32 + lane;
 #define ROW(row, c) sc[((size_t)(row) * ENV_ROWF + (c)) * 32]
-    constexpr int C_I = MAXM + 1, C_E = 2 * (MAXM + 1), C_N = C_E + 1, C_J = C_E + 2, C_C = C_E + 3;
+    constexpr int C_E = MAXM;
 
     for (int tile = warp_in_grid; tile < ntiles; tile += nwarps) {
         const int t = tile * 32 + lane;
@@ -631,26 +635,30 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
 #pragma unroll
         for (int k = 0; k <= MAXM + 1; k++) Mx[k] = Ix[k] = Dx[k] = 0.f;
 
+        // ---- Forward over the envelope; match rows (+ raw E) go to the scratch slab ----
         float xN = 1.f, xJ = 0.f, xC = 0.f, xE = 0.f, xB = N_move, totscale = 0.f;
-        if (valid) { ROW(0, C_E) = 0.f; ROW(0, C_N) = 1.f; ROW(0, C_J) = 0.f; ROW(0, C_C) = 0.f; }
         for (int i = 1; i <= Lw; i++) {
             if (i <= Ld) {
                 const float *er = s_e + residue_at(w, ienv - 1 + i - 1);
-                float mprev = 0.f, iprev = 0.f, dprev = 0.f, mcur = 0.f, dcur = 0.f, xEm = 0.f, xEd = 0.f;
+                // pass 1, descending k, in place: M and I of row i from row i-1 (no serial dependence, so the
+                // scheduler needs no far-ahead coefficient loads); pass 2, ascending: the D chain and the E sums.
+                // Same operations and summation order as the oracle's single ascending loop.
+#pragma unroll
+                for (int k = MAXM; k >= 1; k--) {
+                    float sv = xB * pc.fw[k][F_BM];
+                    sv = fmaf(Mx[k - 1], pc.fw[k][F_MM], sv);
+                    sv = fmaf(Ix[k - 1], pc.fw[k][F_IM], sv);
+                    sv = fmaf(Dx[k - 1], pc.fw[k][F_DM], sv);
+                    sv = sv * er[k * 16];
+                    const float ic = fmaf(Ix[k], pc.fw[k][F_II], Mx[k] * pc.fw[k][F_MI]);
+                    Mx[k] = sv; Ix[k] = ic;
+                }
+                float xEm = 0.f, xEd = 0.f, dcur = 0.f;
 #pragma unroll
                 for (int k = 1; k <= MAXM; k++) {
-                    float sv = xB * pc.tp[k][T_BM];
-                    sv = fmaf(mprev, pc.tp[k - 1][T_MM], sv);
-                    sv = fmaf(iprev, pc.tp[k - 1][T_IM], sv);
-                    sv = fmaf(dprev, pc.tp[k - 1][T_DM], sv);
-                    sv = sv * er[k * 16];
-                    const float dc = fmaf(dcur, pc.tp[k - 1][T_DD], mcur * pc.tp[k - 1][T_MD]);
-                    const float mp = Mx[k], ip = Ix[k], dp = Dx[k];
-                    const float ic = fmaf(ip, pc.tp[k][T_II], mp * pc.tp[k][T_MI]);
-                    Mx[k] = sv; Ix[k] = ic; Dx[k] = dc;
-                    xEm += sv; xEd += dc;
-                    mprev = mp; iprev = ip; dprev = dp;
-                    mcur = sv; dcur = dc;
+                    const float dc = fmaf(dcur, pc.fw[k][F_DD], Mx[k - 1] * pc.fw[k][F_MD]);
+                    Dx[k] = dc; dcur = dc;
+                    xEm += Mx[k]; xEd += dc;
                 }
                 xE = xEm + xEd;
                 xN = xN * N_loop;
@@ -667,16 +675,16 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                     xE = 1.0f;
                 }
 #pragma unroll
-                for (int k = 1; k <= MAXM; k++) { ROW(i, k) = Mx[k]; ROW(i, C_I + k) = Ix[k]; }
-                ROW(i, C_E) = eraw; ROW(i, C_N) = xN; ROW(i, C_J) = xJ; ROW(i, C_C) = xC;
+                for (int k = 1; k <= MAXM; k++) ROW(i, k - 1) = Mx[k];
+                ROW(i, C_E) = eraw;
             }
         }
         const float envsc = totscale + logf_via_double(xC * N_move);
 
-        // Backward with posterior accumulation
-        float acc[8];
+        // ---- Backward; nk[k] accumulates the expected usage of match state k ----
+        float nk[MAXM + 1];
 #pragma unroll
-        for (int q = 0; q < 8; q++) acc[q] = 0.f;
+        for (int k = 0; k <= MAXM; k++) nk[k] = 0.f;
         float bJ = 0.f, bB = 0.f, bN = 0.f, bC = N_move, bE = bC * E_move;
         if (valid) {
             Dx[MAXM + 1] = 0.f;
@@ -699,26 +707,8 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
             if (i <= Ld) {
                 float fE, fS;
                 spec_decode(ROW(i, C_E), fE, fS);
-                {
-                    float rM0 = 0.f, rM1 = 0.f, rM2 = 0.f, rM3 = 0.f, rI = 0.f;
 #pragma unroll
-                    for (int k = 1; k <= MAXM; k++) {
-                        const float pm = ROW(i, k) * Mx[k];
-                        rM0 = fmaf(pm, s_e[k * 16 + 0], rM0);
-                        rM1 = fmaf(pm, s_e[k * 16 + 1], rM1);
-                        rM2 = fmaf(pm, s_e[k * 16 + 2], rM2);
-                        rM3 = fmaf(pm, s_e[k * 16 + 3], rM3);
-                        rI = fmaf(ROW(i, C_I + k), Ix[k], rI);
-                    }
-                    acc[0] = fmaf(rM0, fS, acc[0]);
-                    acc[1] = fmaf(rM1, fS, acc[1]);
-                    acc[2] = fmaf(rM2, fS, acc[2]);
-                    acc[3] = fmaf(rM3, fS, acc[3]);
-                    acc[4] = fmaf(rI, fS, acc[4]);
-                    acc[5] += ROW(i - 1, C_N) * bN * N_loop;
-                    acc[6] += ROW(i - 1, C_C) * bC * N_loop;
-                    acc[7] += ROW(i - 1, C_J) * bJ * N_loop;
-                }
+                for (int k = 1; k <= MAXM; k++) nk[k] = fmaf(ROW(i, k - 1) * Mx[k], fS, nk[k]);
                 if (i > 1) {
                     float fEp, fSp;
                     spec_decode(ROW(i - 1, C_E), fEp, fSp);
@@ -762,13 +752,17 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
             }
         }
         if (valid) {
+            // null2[x] = 1 + sum_k pbar(M_k) (odds_k[x] - 1): every non-match emitter has odds 1 (see oracle)
             const float scaleproduct = 1.0f / bN;
             const float norm = 1.0f / (float)Ld;
             float null2[16];
-            const float xfactor = (acc[5] + acc[6] + acc[7]) * scaleproduct * norm;
-            const float isum = acc[4] * scaleproduct * norm;
 #pragma unroll
-            for (int x = 0; x < 4; x++) null2[x] = acc[x] * scaleproduct * norm + isum + xfactor;
+            for (int x = 0; x < 4; x++) {
+                float ws = 0.f;
+#pragma unroll
+                for (int k = 1; k <= MAXM; k++) ws = fmaf(nk[k], s_e[k * 16 + x] - 1.0f, ws);
+                null2[x] = 1.0f + ws * scaleproduct * norm;
+            }
             const int degen[16] = {1, 2, 4, 8, 5, 10, 3, 12, 6, 9, 11, 14, 7, 13, 15, 0};
 #pragma unroll
             for (int x = 4; x < 15; x++) {
@@ -995,6 +989,13 @@ int search_upload_profiles(itsx_ctx *c)
         for (int k = 0; k <= h.M; k++) {
             for (int s = 0; s < 7; s++) pc.tp[k][s] = h.tp[k * 7 + s];
             pc.tp[k][T_BM] = h.bm[k];
+        }
+        for (int k = 1; k <= MAXM; k++) {
+            float *f = pc.fw[k];
+            f[F_BM] = pc.tp[k][T_BM];
+            f[F_MM] = pc.tp[k - 1][T_MM]; f[F_IM] = pc.tp[k - 1][T_IM]; f[F_DM] = pc.tp[k - 1][T_DM];
+            f[F_DD] = pc.tp[k - 1][T_DD]; f[F_MD] = pc.tp[k - 1][T_MD];
+            f[F_II] = pc.tp[k][T_II];     f[F_MI] = pc.tp[k][T_MI];
         }
         ProfScalars &q = ps[p];
         memset(&q, 0, sizeof(q));

@@ -558,11 +558,11 @@ static float forward_engine(const prof_t *pf, const xf_t *xf, const uint8_t *dsq
 }
 
 /* Backward.  Uses the Forward scale factors fsp->S.  Writes backward specials to bsp.
- * If fullM/fullI are given (Forward rows) it accumulates the unnormalised posterior sums
- * needed by null2-by-expectation: accM[x] (x<4), accI, accN, accC, accJ.            */
+ * If fullM is given (Forward match rows) it accumulates the unnormalised expected usage of
+ * every match state, acc[1..M], which is all null2-by-expectation needs (see rescore_envelope). */
 static float backward_engine(const prof_t *pf, const xf_t *xf, const uint8_t *dsq, int L,
                              const specials_t *fsp, specials_t *bsp,
-                             const float *fullM, const float *fullI, float *acc /*[8]*/)
+                             const float *fullM, const float *fullI, float *acc /*[M+1]*/)
 {
     const int    M   = pf->M;
     float       *Mx  = calloc((size_t)(M + 3) * 4, sizeof(float));
@@ -572,7 +572,7 @@ static float backward_engine(const prof_t *pf, const xf_t *xf, const uint8_t *ds
     float        xC = xf->N_move;
     float        xE = xC * xf->E_move;
     float        totscale;
-    if (acc) for (int a = 0; a < 8; a++) acc[a] = 0.f;
+    if (acc) for (int a = 0; a <= M; a++) acc[a] = 0.f;
 
     /* row L */
     Dx[M + 1] = 0.f;
@@ -596,24 +596,10 @@ static float backward_engine(const prof_t *pf, const xf_t *xf, const uint8_t *ds
 
     for (int i = L; i >= 1; i--) {
         if (acc) {
-            /* posterior contributions of row i (Forward row i x Backward row i) */
-            const float *fM = fullM + (size_t)i * (M + 1), *fI = fullI + (size_t)i * (M + 1);
-            const float *er = pf->e + dsq[i - 1]; (void)er;
-            float rM[4] = {0.f, 0.f, 0.f, 0.f}, rI = 0.f;
-            for (int k = 1; k <= M; k++) {
-                float pm = fM[k] * Mx[k];
-                rM[0]    = fmaf(pm, pf->e[k * 16 + 0], rM[0]);
-                rM[1]    = fmaf(pm, pf->e[k * 16 + 1], rM[1]);
-                rM[2]    = fmaf(pm, pf->e[k * 16 + 2], rM[2]);
-                rM[3]    = fmaf(pm, pf->e[k * 16 + 3], rM[3]);
-                rI       = fmaf(fI[k], Ix[k], rI);
-            }
-            float w = fsp->S[i];
-            for (int x = 0; x < 4; x++) acc[x] = fmaf(rM[x], w, acc[x]);
-            acc[4] = fmaf(rI, w, acc[4]);
-            acc[5] += fsp->N[i - 1] * xN * xf->N_loop;
-            acc[6] += fsp->C[i - 1] * xC * xf->N_loop;
-            acc[7] += fsp->J[i - 1] * xJ * xf->N_loop;
+            /* expected match-state usage: nk[k] += fM_k(i) * bM_k(i) * scale(i)   (acc = nk[M+1]) */
+            const float *fM = fullM + (size_t)i * (M + 1);
+            const float  w  = fsp->S[i];
+            for (int k = 1; k <= M; k++) acc[k] = fmaf(fM[k] * Mx[k], w, acc[k]);
         }
         if (i == 1) break;
         /* compute row i-1 from row i */
@@ -689,15 +675,23 @@ static void rescore_envelope(const prof_t *pf, const uint8_t *dsq, int L, int i,
     specials_t fs = specials_alloc(Ld), bs = specials_alloc(Ld);
     float     *fM = malloc((size_t)(Ld + 1) * (M + 1) * 2 * sizeof(float));
     float     *fI = fM + (size_t)(Ld + 1) * (M + 1);
-    float      acc[8];
+    float      acc[64];
     float envsc = forward_engine(pf, &xf, dsq + (i - 1), Ld, &fs, fM, fI);
     backward_engine(pf, &xf, dsq + (i - 1), Ld, &fs, &bs, fM, fI, acc);
+    /* null2 by expectation (p7_Null2_ByExpectation): null2[x] = sum_k pbar(M_k) odds_k[x] + sum_k pbar(I_k)
+     * + pbar(N) + pbar(C) + pbar(J), pbar = posterior usage averaged over the Ld envelope positions.  Every
+     * envelope residue is emitted by exactly one of these states and all non-match states emit with odds 1,
+     * so the non-match mass is 1 - sum_k pbar(M_k) and
+     *     null2[x] = 1 + sum_k pbar(M_k) * (odds_k[x] - 1),
+     * which needs only the Forward MATCH rows (half the scratch traffic of the direct form on the GPU). */
     float scaleproduct = 1.0f / bs.N[0];
     float norm         = 1.0f / (float)Ld;
     float null2[16];
-    float xfactor = (acc[5] + acc[6] + acc[7]) * scaleproduct * norm;
-    float isum    = acc[4] * scaleproduct * norm;
-    for (int x = 0; x < 4; x++) null2[x] = acc[x] * scaleproduct * norm + isum + xfactor;
+    for (int x = 0; x < 4; x++) {
+        float w = 0.f;
+        for (int k = 1; k <= M; k++) w = fmaf(acc[k], pf->e[k * 16 + x] - 1.0f, w);
+        null2[x] = 1.0f + w * scaleproduct * norm;
+    }
     for (int x = 4; x < 15; x++) {
         float s = 0.f;
         int   n = 0;
