@@ -34,7 +34,10 @@ constexpr int MAXM = ITSX_MAXM;
 constexpr int KP = ITSX_KP;
 constexpr int MSV_TP = 32;                 // profiles per MSV tile (32 * 23 * 16 * 4 B = 47 KB smem)
 constexpr int MSV_THREADS = 128;
-constexpr int FB_THREADS = 128;
+constexpr int FB_THREADS = 64;              // 2 warps / CTA: 6 CTAs (12 warps) per SM at 168 registers
+constexpr int FB_CTAS_PER_SM = 6;
+constexpr int ENV_THREADS = 128;
+constexpr int ENV_CTAS_PER_SM = 2;
 constexpr int SPEC_C = 5;                  // parser specials kept per row
 constexpr int ENV_ROWF = MAXM + 1;             // floats per envelope row: M[1..45] (cols 0..44), Eraw (col 45)
 constexpr double kLn2 = 0.69314718055994529;
@@ -306,7 +309,7 @@ __device__ __forceinline__ void spec_decode(float eraw, float &E, float &S)
     if (eraw > 1.0e4f) { E = 1.0f; S = eraw; } else { E = eraw; S = 1.0f; }
 }
 
-__global__ void __launch_bounds__(FB_THREADS, 2)
+__global__ void __launch_bounds__(FB_THREADS, FB_CTAS_PER_SM)
 fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
 {
     __shared__ float s_e[(MAXM + 1) * 16];
@@ -349,9 +352,17 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
         // ------------------------------ Forward ------------------------------
         float xN = 1.f, xJ = 0.f, xC = 0.f, xE = 0.f, xB = N_move, totscale = 0.f;
         if (valid) { SPEC(0, 0) = 0.f; SPEC(0, 1) = 1.f; SPEC(0, 2) = 0.f; SPEC(0, 3) = xB; SPEC(0, 4) = 0.f; }
+        // the residue word (8 nibbles) of rows i..i+7 is fetched one word ahead of its use
+        int widx = 0;
+        uint32_t wcur = L > 0 ? w[0] : 0u, wnxt = L > 8 ? w[1] : 0u;
         for (int i = 1; i <= Lw; i++) {
+            if (((i - 1) >> 3) != widx) {
+                widx = (i - 1) >> 3;
+                wcur = wnxt;
+                wnxt = ((widx + 1) * 8 < L) ? w[widx + 1] : 0u;
+            }
             if (i <= L) {
-                const float *er = s_e + residue_at(w, i - 1);
+                const float *er = s_e + ((wcur >> (((i - 1) & 7) * 4)) & 15u);
                 // pass 1, descending k, in place: M and I of row i from row i-1 (no serial dependence, so the
                 // scheduler needs no far-ahead coefficient loads); pass 2, ascending: the D chain and the E sums.
                 // Same operations and summation order as the oracle's single ascending loop.
@@ -439,19 +450,35 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
             }
             btotscale = logf_via_double(fS_i);
         }
+        // forward row i-1 (5 specials) is loaded during iteration i+1, the residue word one word ahead
+        float qE = 0.f, qN = 0.f, qJ = 0.f, qB = 0.f, qC = 0.f;
+        if (Lw >= 1 && Lw - 1 <= L) {
+            qE = SPEC(Lw - 1, 0); qN = SPEC(Lw - 1, 1); qJ = SPEC(Lw - 1, 2); qB = SPEC(Lw - 1, 3); qC = SPEC(Lw - 1, 4);
+        }
+        int bidx = Lw >= 1 ? (Lw - 1) >> 3 : 0;
+        uint32_t bcur = (bidx * 8 < L) ? w[bidx] : 0u, bnxt = (bidx >= 1 && (bidx - 1) * 8 < L) ? w[bidx - 1] : 0u;
         for (int i = Lw; i >= 1; i--) {
+            const float cE = qE, cN = qN, cJ = qJ, cB = qB, cC = qC;
+            if (i >= 2 && i - 2 <= L) {
+                qE = SPEC(i - 2, 0); qN = SPEC(i - 2, 1); qJ = SPEC(i - 2, 2); qB = SPEC(i - 2, 3); qC = SPEC(i - 2, 4);
+            }
+            if (((i - 1) >> 3) != bidx) {
+                bidx = (i - 1) >> 3;
+                bcur = bnxt;
+                bnxt = (bidx >= 1 && (bidx - 1) * 8 < L) ? w[bidx - 1] : 0u;
+            }
             if (i <= L) {
                 // forward row i-1
-                const float fN_p = SPEC(i - 1, 1), fJ_p = SPEC(i - 1, 2), fB_p = SPEC(i - 1, 3), fC_p = SPEC(i - 1, 4);
+                const float fN_p = cN, fJ_p = cJ, fB_p = cB, fC_p = cC;
                 float fE_p, fS_p;
-                spec_decode(SPEC(i - 1, 0), fE_p, fS_p);
+                spec_decode(cE, fE_p, fS_p);
                 // products that involve backward row i
                 SPEC(i, 1) = (fE_i * bE) * fS_i;
                 SPEC(i, 2) = (fN_p * bN) * N_loop;
                 SPEC(i, 3) = (fJ_p * bJ) * N_loop;
                 SPEC(i, 4) = (fC_p * bC) * N_loop;
                 if (i > 1) {
-                    const float *er = s_e + residue_at(w, i - 1);   // residue x_i
+                    const float *er = s_e + ((bcur >> (((i - 1) & 7) * 4)) & 15u);   // residue x_i
                     bB = 0.f;
 #pragma unroll
                     for (int k = 1; k <= MAXM; k++) {
@@ -484,7 +511,7 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
                     btotscale += logf_via_double(fS_p);
                 } else {
                     // row 0: only B and N are live
-                    const float *er = s_e + residue_at(w, 0);
+                    const float *er = s_e + (bcur & 15u);
                     bB = 0.f;
 #pragma unroll
                     for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * er[k * 16], pc.tp[k][T_BM], bB);
@@ -506,14 +533,17 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
             bool triggered = false;
             int nmulti = 0;
             SPEC(0, 0) = 0.f; SPEC(0, 1) = 0.f;   // btot[0], etot[0]
+            float r0 = SPEC(1, 0), r1 = SPEC(1, 1), r2 = SPEC(1, 2), r3 = SPEC(1, 3), r4 = SPEC(1, 4);
             for (int j = 1; j <= L; j++) {
-                const float db = SPEC(j, 0) * scaleproduct, de = SPEC(j, 1) * scaleproduct;
+                const float v0 = r0, v1 = r1, v2 = r2, v3 = r3, v4 = r4;
+                if (j < L) { r0 = SPEC(j + 1, 0); r1 = SPEC(j + 1, 1); r2 = SPEC(j + 1, 2); r3 = SPEC(j + 1, 3); r4 = SPEC(j + 1, 4); }
+                const float db = v0 * scaleproduct, de = v1 * scaleproduct;
                 const float btot_p = btot, etot_p = etot;
                 btot = btot + db;
                 etot = etot + de;
-                float njcp = SPEC(j, 2) * scaleproduct;
-                njcp += SPEC(j, 3) * scaleproduct;
-                njcp += SPEC(j, 4) * scaleproduct;
+                float njcp = v2 * scaleproduct;
+                njcp += v3 * scaleproduct;
+                njcp += v4 * scaleproduct;
                 const float mocc = 1.f - njcp;
                 SPEC(j, 0) = btot; SPEC(j, 1) = etot;
                 if (!triggered) {
@@ -591,15 +621,15 @@ struct EnvArgs {
     unsigned long long *counters;
 };
 
-__global__ void __launch_bounds__(FB_THREADS, 2)
+__global__ void __launch_bounds__(ENV_THREADS, ENV_CTAS_PER_SM)
 env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
 {
     __shared__ float s_e[(MAXM + 1) * 16];
-    for (int t = threadIdx.x; t < (MAXM + 1) * 16; t += FB_THREADS) s_e[t] = a.etab[t];
+    for (int t = threadIdx.x; t < (MAXM + 1) * 16; t += ENV_THREADS) s_e[t] = a.etab[t];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int warp_in_grid = (blockIdx.x * FB_THREADS + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * FB_THREADS) >> 5;
+    const int warp_in_grid = (blockIdx.x * ENV_THREADS + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * ENV_THREADS) >> 5;
     const int ntiles = (a.count + 31) >> 5;
     float *sc = a.scratch + (size_t)warp_in_grid * (size_t)(a.Ldmax + 1) * ENV_ROWF * 32 + lane;
 #define ROW(row, c) sc[((size_t)(row) * ENV_ROWF + (c)) * 32]
@@ -1184,7 +1214,8 @@ int search_stage1(itsx_ctx *c)
     for (auto &h : c->prof) sumM += h.M;
     ss.msv_cells = sumL * sumM;
 
-    const int fb_warps_per_lane = c->sm_count * 2 * (FB_THREADS / 32);
+    const int fb_warps_per_lane = c->sm_count * FB_CTAS_PER_SM * (FB_THREADS / 32);
+    const int env_warps_per_lane = c->sm_count * ENV_CTAS_PER_SM * (ENV_THREADS / 32);
     std::vector<int32_t> h_bounds((size_t)P + 1), h_envb((size_t)P + 1);
     int32_t *d_nsel = (int32_t *)(c->d_counters.as<unsigned long long>() + 42);
 
@@ -1292,7 +1323,8 @@ int search_stage1(itsx_ctx *c)
             fa.env = c->d_env.as<int32_t>() + (size_t)b0 * ITSX_MAXDOM * 2;
             fa.counters = cnt;
             const int tiles = (cntp + 31) / 32;
-            const int ctas = std::min((tiles + 3) / 4, c->sm_count * 2);
+            const int wpc = FB_THREADS / 32;
+            const int ctas = std::min((tiles + wpc - 1) / wpc, c->sm_count * FB_CTAS_PER_SM);
             fb_kernel<<<ctas, FB_THREADS, 0, c->lanes[l]>>>(c->pconst[p], fa);
             c->launches++;
         }
@@ -1326,7 +1358,7 @@ int search_stage1(itsx_ctx *c)
             // envelopes are at most Lmax long; scratch per resident warp
             const int Ldmax = Lmax;
             const size_t eslab = (size_t)(Ldmax + 1) * ENV_ROWF * 32 * 4;
-            CUDA_TRY(c, c->d_envscratch.ensure(eslab * fb_warps_per_lane * NLANE));
+            CUDA_TRY(c, c->d_envscratch.ensure(eslab * env_warps_per_lane * NLANE));
             CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
             for (int l = 0; l < NLANE; l++) CUDA_TRY(c, cudaStreamWaitEvent(c->lanes[l], c->ev_b, 0));
             lane_rr = 0;
@@ -1342,14 +1374,15 @@ int search_stage1(itsx_ctx *c)
                 ea.s0 = s0; ea.ns = ns; ea.prof = p;
                 ea.seqw = c->d_seqw.as<uint32_t>(); ea.woff = c->d_seqwoff.as<int64_t>(); ea.seqlen = c->d_seqlen.as<int32_t>();
                 ea.etab = c->d_etab.as<float>() + (size_t)p * (MAXM + 1) * 16;
-                ea.scratch = (float *)(c->d_envscratch.as<char>() + eslab * fb_warps_per_lane * l);
+                ea.scratch = (float *)(c->d_envscratch.as<char>() + eslab * env_warps_per_lane * l);
                 ea.Ldmax = Ldmax;
                 ea.out = c->d_envout.as<float>();
                 ea.out_base = e0;
                 ea.counters = cnt;
                 const int tiles = (cnte + 31) / 32;
-                const int ctas = std::min((tiles + 3) / 4, c->sm_count * 2);
-                env_kernel<<<ctas, FB_THREADS, 0, c->lanes[l]>>>(c->pconst[p], ea);
+                const int wpc = ENV_THREADS / 32;
+                const int ctas = std::min((tiles + wpc - 1) / wpc, c->sm_count * ENV_CTAS_PER_SM);
+                env_kernel<<<ctas, ENV_THREADS, 0, c->lanes[l]>>>(c->pconst[p], ea);
                 c->launches++;
             }
             for (int l = 0; l < NLANE; l++) {
