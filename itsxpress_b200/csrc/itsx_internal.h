@@ -40,14 +40,21 @@ uint8_t msv_unbiased_byteify(float scale_b, float sc);
 // transitions + entry, node-major: tp[k] = {MM, MI, MD, IM, II, DM, DD, BM_k}, k = 0..MAXM+1.
 // Passed BY VALUE as a __grid_constant__ kernel argument so that every FFMA reads its
 // coefficient straight from the constant bank (no load instruction in the DP inner loop).
-// fw[k] = the eight coefficients the Forward cell of node k consumes, contiguous, so that a cell is two
-// 128-bit uniform loads with no value shared between cells:
-//   {BM_k, MM_{k-1}, IM_{k-1}, DM_{k-1}, DD_{k-1}, MD_{k-1}, II_k, MI_k}
+// Coefficients are additionally laid out in the order the unrolled DP loops consume them, so that every
+// uniform load (LDCU.128 / .64) is fully used and no value is shared between distant cells:
+//   Forward  pass 1 (M, I of row i):  fa[k] = {BM_k, MM_{k-1}, IM_{k-1}, DM_{k-1}}   fi[k] = {II_k, MI_k}
+//            pass 2 (D chain):        fd[k] = {DD_{k-1}, MD_{k-1}}
+//   Backward pass 1 (B sum):          bm[k] = BM_k
+//            pass 2 (M, I, D):        ba[k] = {IM_k, II_k, MM_k, MI_k}               bd[k] = {DM_k, DD_k, MD_k, 0}
 struct ProfConst {
     float tp[ITSX_MAXM + 2][8];
-    float fw[ITSX_MAXM + 1][8];
+    float fa[ITSX_MAXM + 1][4];
+    float fi[ITSX_MAXM + 1][2];
+    float fd[ITSX_MAXM + 1][2];
+    float ba[ITSX_MAXM + 1][4];
+    float bd[ITSX_MAXM + 1][4];
+    float bm[ITSX_MAXM + 3];
 };
-enum { F_BM = 0, F_MM, F_IM, F_DM, F_DD, F_MD, F_II, F_MI };
 // per-profile scalars used by the filter kernels
 struct ProfScalars {
     int32_t M, bias, base, tbm, tec, side, pad0, pad1;

@@ -368,18 +368,18 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
                 // Same operations and summation order as the oracle's single ascending loop.
 #pragma unroll
                 for (int k = MAXM; k >= 1; k--) {
-                    float sv = xB * pc.fw[k][F_BM];
-                    sv = fmaf(Mx[k - 1], pc.fw[k][F_MM], sv);
-                    sv = fmaf(Ix[k - 1], pc.fw[k][F_IM], sv);
-                    sv = fmaf(Dx[k - 1], pc.fw[k][F_DM], sv);
+                    float sv = xB * pc.fa[k][0];
+                    sv = fmaf(Mx[k - 1], pc.fa[k][1], sv);
+                    sv = fmaf(Ix[k - 1], pc.fa[k][2], sv);
+                    sv = fmaf(Dx[k - 1], pc.fa[k][3], sv);
                     sv = sv * er[k * 16];
-                    const float ic = fmaf(Ix[k], pc.fw[k][F_II], Mx[k] * pc.fw[k][F_MI]);
+                    const float ic = fmaf(Ix[k], pc.fi[k][0], Mx[k] * pc.fi[k][1]);
                     Mx[k] = sv; Ix[k] = ic;
                 }
                 float xEm = 0.f, xEd = 0.f, dcur = 0.f;
 #pragma unroll
                 for (int k = 1; k <= MAXM; k++) {
-                    const float dc = fmaf(dcur, pc.fw[k][F_DD], Mx[k - 1] * pc.fw[k][F_MD]);
+                    const float dc = fmaf(dcur, pc.fd[k][0], Mx[k - 1] * pc.fd[k][1]);
                     Dx[k] = dc; dcur = dc;
                     xEm += Mx[k]; xEd += dc;
                 }
@@ -437,8 +437,8 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
             Dx[MAXM + 1] = 0.f;
 #pragma unroll
             for (int k = MAXM; k >= 1; k--) {
-                Dx[k] = fmaf(pc.tp[k][T_DD], Dx[k + 1], bE);
-                Mx[k] = fmaf(pc.tp[k][T_MD], Dx[k + 1], bE);
+                Dx[k] = fmaf(pc.bd[k][1], Dx[k + 1], bE);
+                Mx[k] = fmaf(pc.bd[k][2], Dx[k + 1], bE);
                 Ix[k] = 0.f;
             }
             spec_decode(SPEC(L, 0), fE_i, fS_i);
@@ -483,7 +483,7 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
 #pragma unroll
                     for (int k = 1; k <= MAXM; k++) {
                         Mx[k] = Mx[k] * er[k * 16];
-                        bB = fmaf(Mx[k], pc.tp[k][T_BM], bB);
+                        bB = fmaf(Mx[k], pc.bm[k], bB);
                     }
                     bC = bC * N_loop;
                     bJ = fmaf(bB, N_move, bJ * N_loop);
@@ -494,11 +494,11 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
 #pragma unroll
                     for (int k = MAXM; k >= 1; k--) {
                         const float mpe_k = Mx[k];
-                        const float ic = fmaf(mnext, pc.tp[k][T_IM], Ix[k] * pc.tp[k][T_II]);
-                        float mc = fmaf(mnext, pc.tp[k][T_MM], Ix[k] * pc.tp[k][T_MI]);
-                        float dc = mnext * pc.tp[k][T_DM];
-                        dc = fmaf(Dx[k + 1], pc.tp[k][T_DD], dc) + bE;
-                        mc = fmaf(Dx[k + 1], pc.tp[k][T_MD], mc) + bE;
+                        const float ic = fmaf(mnext, pc.ba[k][0], Ix[k] * pc.ba[k][1]);
+                        float mc = fmaf(mnext, pc.ba[k][2], Ix[k] * pc.ba[k][3]);
+                        float dc = mnext * pc.bd[k][0];
+                        dc = fmaf(Dx[k + 1], pc.bd[k][1], dc) + bE;
+                        mc = fmaf(Dx[k + 1], pc.bd[k][2], mc) + bE;
                         Mx[k] = mc; Ix[k] = ic; Dx[k] = dc;
                         mnext = mpe_k;
                     }
@@ -507,14 +507,14 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
                         const float inv = 1.0f / fS_p;
 #pragma unroll
                         for (int k = 1; k <= MAXM; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
+                        btotscale += logf_via_double(fS_p);     // log(1) == +0 exactly: rows without a rescale add nothing
                     }
-                    btotscale += logf_via_double(fS_p);
                 } else {
                     // row 0: only B and N are live
                     const float *er = s_e + (bcur & 15u);
                     bB = 0.f;
 #pragma unroll
-                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * er[k * 16], pc.tp[k][T_BM], bB);
+                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * er[k * 16], pc.bm[k], bB);
                     bN = fmaf(bB, N_move, bN * N_loop);
                 }
                 SPEC(i, 0) = (fB_p * bB) * fS_p;
@@ -675,18 +675,18 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                 // Same operations and summation order as the oracle's single ascending loop.
 #pragma unroll
                 for (int k = MAXM; k >= 1; k--) {
-                    float sv = xB * pc.fw[k][F_BM];
-                    sv = fmaf(Mx[k - 1], pc.fw[k][F_MM], sv);
-                    sv = fmaf(Ix[k - 1], pc.fw[k][F_IM], sv);
-                    sv = fmaf(Dx[k - 1], pc.fw[k][F_DM], sv);
+                    float sv = xB * pc.fa[k][0];
+                    sv = fmaf(Mx[k - 1], pc.fa[k][1], sv);
+                    sv = fmaf(Ix[k - 1], pc.fa[k][2], sv);
+                    sv = fmaf(Dx[k - 1], pc.fa[k][3], sv);
                     sv = sv * er[k * 16];
-                    const float ic = fmaf(Ix[k], pc.fw[k][F_II], Mx[k] * pc.fw[k][F_MI]);
+                    const float ic = fmaf(Ix[k], pc.fi[k][0], Mx[k] * pc.fi[k][1]);
                     Mx[k] = sv; Ix[k] = ic;
                 }
                 float xEm = 0.f, xEd = 0.f, dcur = 0.f;
 #pragma unroll
                 for (int k = 1; k <= MAXM; k++) {
-                    const float dc = fmaf(dcur, pc.fw[k][F_DD], Mx[k - 1] * pc.fw[k][F_MD]);
+                    const float dc = fmaf(dcur, pc.fd[k][0], Mx[k - 1] * pc.fd[k][1]);
                     Dx[k] = dc; dcur = dc;
                     xEm += Mx[k]; xEd += dc;
                 }
@@ -720,8 +720,8 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
             Dx[MAXM + 1] = 0.f;
 #pragma unroll
             for (int k = MAXM; k >= 1; k--) {
-                Dx[k] = fmaf(pc.tp[k][T_DD], Dx[k + 1], bE);
-                Mx[k] = fmaf(pc.tp[k][T_MD], Dx[k + 1], bE);
+                Dx[k] = fmaf(pc.bd[k][1], Dx[k + 1], bE);
+                Mx[k] = fmaf(pc.bd[k][2], Dx[k + 1], bE);
                 Ix[k] = 0.f;
             }
             float fE, fS;
@@ -747,7 +747,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
 #pragma unroll
                     for (int k = 1; k <= MAXM; k++) {
                         Mx[k] = Mx[k] * er[k * 16];
-                        bB = fmaf(Mx[k], pc.tp[k][T_BM], bB);
+                        bB = fmaf(Mx[k], pc.bm[k], bB);
                     }
                     bC = bC * N_loop;
                     bJ = fmaf(bB, N_move, bJ * N_loop);
@@ -758,11 +758,11 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
 #pragma unroll
                     for (int k = MAXM; k >= 1; k--) {
                         const float mpe_k = Mx[k];
-                        const float ic = fmaf(mnext, pc.tp[k][T_IM], Ix[k] * pc.tp[k][T_II]);
-                        float mc = fmaf(mnext, pc.tp[k][T_MM], Ix[k] * pc.tp[k][T_MI]);
-                        float dc = mnext * pc.tp[k][T_DM];
-                        dc = fmaf(Dx[k + 1], pc.tp[k][T_DD], dc) + bE;
-                        mc = fmaf(Dx[k + 1], pc.tp[k][T_MD], mc) + bE;
+                        const float ic = fmaf(mnext, pc.ba[k][0], Ix[k] * pc.ba[k][1]);
+                        float mc = fmaf(mnext, pc.ba[k][2], Ix[k] * pc.ba[k][3]);
+                        float dc = mnext * pc.bd[k][0];
+                        dc = fmaf(Dx[k + 1], pc.bd[k][1], dc) + bE;
+                        mc = fmaf(Dx[k + 1], pc.bd[k][2], mc) + bE;
                         Mx[k] = mc; Ix[k] = ic; Dx[k] = dc;
                         mnext = mpe_k;
                     }
@@ -776,7 +776,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                     const float *er = s_e + residue_at(w, ienv - 1);
                     bB = 0.f;
 #pragma unroll
-                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * er[k * 16], pc.tp[k][T_BM], bB);
+                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * er[k * 16], pc.bm[k], bB);
                     bN = fmaf(bB, N_move, bN * N_loop);
                 }
             }
@@ -1021,11 +1021,13 @@ int search_upload_profiles(itsx_ctx *c)
             pc.tp[k][T_BM] = h.bm[k];
         }
         for (int k = 1; k <= MAXM; k++) {
-            float *f = pc.fw[k];
-            f[F_BM] = pc.tp[k][T_BM];
-            f[F_MM] = pc.tp[k - 1][T_MM]; f[F_IM] = pc.tp[k - 1][T_IM]; f[F_DM] = pc.tp[k - 1][T_DM];
-            f[F_DD] = pc.tp[k - 1][T_DD]; f[F_MD] = pc.tp[k - 1][T_MD];
-            f[F_II] = pc.tp[k][T_II];     f[F_MI] = pc.tp[k][T_MI];
+            pc.fa[k][0] = pc.tp[k][T_BM];
+            pc.fa[k][1] = pc.tp[k - 1][T_MM]; pc.fa[k][2] = pc.tp[k - 1][T_IM]; pc.fa[k][3] = pc.tp[k - 1][T_DM];
+            pc.fi[k][0] = pc.tp[k][T_II];     pc.fi[k][1] = pc.tp[k][T_MI];
+            pc.fd[k][0] = pc.tp[k - 1][T_DD]; pc.fd[k][1] = pc.tp[k - 1][T_MD];
+            pc.ba[k][0] = pc.tp[k][T_IM]; pc.ba[k][1] = pc.tp[k][T_II]; pc.ba[k][2] = pc.tp[k][T_MM]; pc.ba[k][3] = pc.tp[k][T_MI];
+            pc.bd[k][0] = pc.tp[k][T_DM]; pc.bd[k][1] = pc.tp[k][T_DD]; pc.bd[k][2] = pc.tp[k][T_MD]; pc.bd[k][3] = 0.f;
+            pc.bm[k] = pc.tp[k][T_BM];
         }
         ProfScalars &q = ps[p];
         memset(&q, 0, sizeof(q));

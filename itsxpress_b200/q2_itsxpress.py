@@ -1,0 +1,171 @@
+"""QIIME 2 driver with the reference's action signatures (itsxpress/q2_itsxpress.py: trim_single :120,
+trim_pair :156, trim_pair_output_unmerged :194, main :232-364) on top of the GPU path.
+
+Per sample (derep clusters, Z and domZ are per sample upstream, :273-296): check the FASTQs, [merge pairs],
+dereplicate, build the runtime profile set, search, ItsPosition, Dedup, write gzipped output named after the
+input file into a Casava-1.8 single-lane-per-sample directory.
+
+``per_sample_sequences`` is duck-typed exactly as upstream uses it: ``.manifest.view(pd.DataFrame)`` must give
+a frame indexed by sample id with columns ``forward`` [, ``reverse``].  When q2_types is installed the real
+directory formats are used; otherwise `CasavaDir` / `PerSampleDir` below read and write the same on-disk
+layout (``MANIFEST``, ``metadata.yml``, ``<sample>_<n>_L001_R<d>_001.fastq.gz``).
+"""
+import math
+import os
+import pathlib
+import shutil
+import tempfile
+
+import pandas as pd
+
+from . import main as itsxpress
+
+try:  # pragma: no cover - only with QIIME 2 installed
+    from q2_types.per_sample_sequences import CasavaOneEightSingleLanePerSampleDirFmt
+except ModuleNotFoundError:
+    CasavaOneEightSingleLanePerSampleDirFmt = None
+
+default_cluster_id = 1.0
+
+
+class _Manifest:
+    def __init__(self, frame):
+        self._frame = frame
+
+    def view(self, kind):
+        return self._frame
+
+
+class PerSampleDir:
+    """A SingleLanePerSample{Single,Paired}EndFastqDirFmt directory on disk (data/MANIFEST layout)."""
+
+    def __init__(self, path):
+        self.path = str(path)
+        man = pd.read_csv(os.path.join(self.path, "MANIFEST"), comment="#")
+        rows = {}
+        for sid, fn, direction in zip(man["sample-id"], man["filename"], man["direction"]):
+            rows.setdefault(sid, {})[direction] = os.path.join(self.path, fn)
+        cols = ["forward", "reverse"] if any("reverse" in v for v in rows.values()) else ["forward"]
+        frame = pd.DataFrame([[v.get(c) for c in cols] for v in rows.values()], index=list(rows), columns=cols)
+        frame.index.name = "sample-id"
+        self.manifest = _Manifest(frame)
+
+    def __str__(self):
+        return self.path
+
+
+class CasavaDir:
+    """Stand-in for CasavaOneEightSingleLanePerSampleDirFmt(): str() is a fresh directory to write into."""
+
+    def __init__(self):
+        self.path = tempfile.mkdtemp(prefix="q2-CasavaOneEightSingleLanePerSampleDirFmt-")
+
+    def __str__(self):
+        return self.path
+
+    def write_manifest(self):
+        """MANIFEST + metadata.yml for the files present (what QIIME 2 derives when it imports the directory)."""
+        lines = ["sample-id,filename,direction"]
+        for fn in sorted(os.listdir(self.path)):
+            if fn.endswith(".fastq.gz"):
+                stem = fn.rsplit("_", 4)
+                direction = "reverse" if "_R2_" in fn else "forward"
+                lines.append("%s,%s,%s" % (stem[0], fn, direction))
+        with open(os.path.join(self.path, "MANIFEST"), "w") as f:
+            f.write("\n".join(lines) + "\n")
+        with open(os.path.join(self.path, "metadata.yml"), "w") as f:
+            f.write("{phred-offset: 33}\n")
+
+
+def _set_fastqs_and_check(fastq, fastq2, tempdir, sample_id, single_end, reversed_primers, allow_staggered_reads,
+                          threads):
+    try:
+        itsxpress._check_fastqs(fastq=fastq, fastq2=fastq2)
+        paired_end = itsxpress._is_paired(fastq=fastq, fastq2=fastq2, single_end=single_end)
+    except (NotADirectoryError, FileNotFoundError):
+        raise ValueError("There is a problem with the fastq file(s) you selected")
+    if paired_end:
+        sobj = itsxpress.SeqSamplePairedNotInterleaved(fastq=fastq, fastq2=fastq2, tempdir=tempdir,
+                                                       reversed_primers=reversed_primers)
+        sobj._merge_reads(threads=threads, stagger=allow_staggered_reads)
+        return sobj
+    return itsxpress.SeqSampleNotPaired(fastq=fastq, tempdir=tempdir)
+
+
+_TAXA_LETTERS = {"A": "Alveolata", "B": "Bryophyta", "C": "Bacillariophyta", "D": "Amoebozoa", "E": "Euglenozoa",
+                 "F": "Fungi", "G": "Chlorophyta", "H": "Rhodophyta", "I": "Phaeophyceae", "L": "Marchantiophyta",
+                 "M": "Metazoa", "O": "Oomycota", "P": "Haptophyceae", "Q": "Raphidophyceae", "R": "Rhizaria",
+                 "S": "Synurophyceae", "T": "Tracheophyta", "U": "Eustigmatophyceae", "Y": "Parabasalia",
+                 "ALL": "All"}
+
+
+def _taxa_prefix_to_taxa(taxa_prefix):
+    """Plugin letter -> taxon name (q2_itsxpress.py:86-117).  'R' gives 'Rhizaria' without the blank that
+    definitions.taxa_dict carries, so -- as upstream -- it resolves to no profile file."""
+    return _TAXA_LETTERS[taxa_prefix]
+
+
+def trim_single(per_sample_sequences, region, taxa="F", threads=1, cluster_id=default_cluster_id, trim_ccs=False):
+    return main(per_sample_sequences=per_sample_sequences, threads=threads, taxa=taxa, region=region,
+                paired_in=False, paired_out=False, reversed_primers=False, allow_staggered_reads=False,
+                cluster_id=cluster_id, trim_ccs=trim_ccs)
+
+
+def trim_pair(per_sample_sequences, region, taxa="F", threads=1, reversed_primers=False, allow_staggered_reads=True,
+              cluster_id=default_cluster_id):
+    return main(per_sample_sequences=per_sample_sequences, threads=threads, taxa=taxa, region=region, paired_in=True,
+                paired_out=False, reversed_primers=reversed_primers, allow_staggered_reads=allow_staggered_reads,
+                cluster_id=cluster_id, trim_ccs=False)
+
+
+def trim_pair_output_unmerged(per_sample_sequences, region, taxa="F", threads=1, reversed_primers=False,
+                              allow_staggered_reads=True, cluster_id=default_cluster_id):
+    return main(per_sample_sequences=per_sample_sequences, threads=threads, taxa=taxa, region=region, paired_in=True,
+                paired_out=True, reversed_primers=reversed_primers, allow_staggered_reads=allow_staggered_reads,
+                cluster_id=cluster_id, trim_ccs=False)
+
+
+def main(per_sample_sequences, threads, taxa, region, paired_in, paired_out, reversed_primers, allow_staggered_reads,
+         cluster_id, trim_ccs=False):
+    taxa = _taxa_prefix_to_taxa(taxa)
+    samples = per_sample_sequences.manifest.view(pd.DataFrame)
+    try:
+        tempdir = tempfile.mkdtemp(prefix="itsxpress_")
+    except Exception:
+        raise ValueError("Could not create temporary directory")
+    results = CasavaOneEightSingleLanePerSampleDirFmt() if CasavaOneEightSingleLanePerSampleDirFmt else CasavaDir()
+    for sample in samples.itertuples():
+        sobj = _set_fastqs_and_check(fastq=sample.forward, fastq2=sample.reverse if paired_in else None,
+                                     tempdir=tempdir, sample_id=sample.Index, single_end=not paired_in,
+                                     reversed_primers=reversed_primers, allow_staggered_reads=allow_staggered_reads,
+                                     threads=threads)
+        if trim_ccs:
+            sobj.orient_reads(threads=threads)
+        if math.isclose(cluster_id, 1, rel_tol=1e-05):
+            sobj.deduplicate(threads=threads)
+        else:
+            sobj.cluster(threads=threads, cluster_id=cluster_id)
+        try:
+            hmmfile = itsxpress.create_runtime_hmm(taxa, region, tempdir)
+            sobj._search(hmmfile=hmmfile, threads=threads)
+        except (ModuleNotFoundError, FileNotFoundError, NotADirectoryError):
+            raise ValueError("the profile search could not run: libitsx_b200 or a profile file is missing")
+        its_pos = itsxpress.ItsPosition(domtable=sobj.dom_file, region=region)
+        dedup_obj = itsxpress.Dedup(uc_file=sobj.uc_file, rep_file=sobj.rep_file, seq_file=sobj.seq_file,
+                                    fastq=sobj.r1, fastq2=sobj.fastq2)
+        out_fwd = os.path.join(str(results), pathlib.Path(sample.forward).name)
+        if paired_out:
+            out_rev = os.path.join(str(results), pathlib.Path(sample.reverse).name)
+            dedup_obj.create_paired_trimmed_seqs(out_fwd, out_rev, gzipped=True, zstd_file=False, itspos=its_pos,
+                                                 wri_file=True, trim_ccs=trim_ccs)
+        else:
+            dedup_obj.create_trimmed_seqs(out_fwd, gzipped=True, zstd_file=False, itspos=its_pos, wri_file=True,
+                                          tempdir=sobj.tempdir, trim_ccs=trim_ccs)
+    if trim_ccs:
+        print("\n" + "=" * 80 + "\nPacBio CCS trimming complete.\n\nCAUTION: data contain fake sequence at the ends "
+              "needed for DADA2\n\nqiime dada2 denoise-ccs --p-front GACAGGTACAAGAAGGA --p-adapter ACTGGAGACTGGGTTAA\n"
+              + "*" * 80 + "\n")
+    if isinstance(results, CasavaDir):
+        results.write_manifest()
+    shutil.rmtree(tempdir)
+    return results

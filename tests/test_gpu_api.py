@@ -167,3 +167,40 @@ def test_cli_failure_exit_code(tmp_path):
     with pytest.raises(SystemExit) as e:
         cli.main(args=args)
     assert e.value.code == 1
+
+
+def test_q2_trim_single(tmp_path):
+    """q2 action trim_single on a single-end per-sample directory (layout of the reference's
+    tests/test_data/singleIn artifact; the sample here is the MERGED fixture so that both ITS2 boundaries are inside
+    the reads) with the taxon present in the mount; output is a Casava-1.8 directory whose file carries the input's
+    name; bytes equal the CLI's output for the same sample."""
+    import shutil
+    from itsxpress_b200 import fastq as fq
+    from itsxpress_b200 import main as cli
+    from itsxpress_b200 import q2_itsxpress as q2
+    src = tmp_path / "in"
+    src.mkdir()
+    name = "4774-1-MSITS3_0_L001_R1_001.fastq.gz"
+    shutil.copy(SEQ, str(src / name))
+    (src / "MANIFEST").write_text("sample-id,filename,direction\n4774-1-MSITS3,%s,forward\n" % name)
+    (src / "metadata.yml").write_text("{phred-offset: 33}\n")
+    inp = q2.PerSampleDir(str(src))
+    frame = inp.manifest.view(None)
+    assert list(frame.columns) == ["forward"] and list(frame.index) == ["4774-1-MSITS3"]
+    res = q2.trim_single(inp, region="ITS2", taxa="M")
+    out = os.path.join(str(res), name)
+    assert os.path.exists(out)
+    b = fq.read_fastq(out)
+    assert 100 < b.n <= 227
+    man = open(os.path.join(str(res), "MANIFEST")).read().splitlines()
+    assert man == ["sample-id,filename,direction", "4774-1-MSITS3,%s,forward" % name]
+    ref = str(tmp_path / "cli.fastq")
+    cli.main(args=cli.myparser().parse_args(["--fastq", SEQ, "--single_end", "--outfile", ref, "--region", "ITS2",
+                                             "--taxa", "Metazoa", "--log", str(tmp_path / "l.txt")]))
+    assert fq._open_bytes(out) == open(ref, "rb").read()
+    # the reference's own single-end artifact holds raw R1 reads: no read spans both ITS2 boundaries
+    r1 = q2.trim_single(q2.PerSampleDir(os.path.join(TD, "singleIn", "cfd0e65b-05fb-4329-9618-15ecd0aec9b3", "data")),
+                        region="ITS2", taxa="M")
+    assert fq.read_fastq(os.path.join(str(r1), name)).n < 20
+    with pytest.raises(KeyError):
+        q2._taxa_prefix_to_taxa("Z")

@@ -318,3 +318,15 @@ def test_names_look_paired():
     assert cli._names_look_paired("r1 1:N:0:1", "r1 2:N:0:1")
     assert cli._names_look_paired("r1/1", "r1/2")
     assert not cli._names_look_paired("r1 1:N:0:1", "r2 1:N:0:1")
+
+
+def test_q2_directory_formats():
+    """MANIFEST reader of the per-sample directory format (the reference's fixtures under tests/test_data)."""
+    from itsxpress_b200 import q2_itsxpress as q2
+    p = q2.PerSampleDir(os.path.join(TD, "paired", "445cf54a-bf06-4852-8010-13a60fa1598c", "data"))
+    f = p.manifest.view(None)
+    assert list(f.columns) == ["forward", "reverse"] and list(f.index) == ["4774-1-MSITS3"]
+    assert f.loc["4774-1-MSITS3", "forward"].endswith("4774-1-MSITS3_0_L001_R1_001.fastq.gz")
+    assert f.loc["4774-1-MSITS3", "reverse"].endswith("4774-1-MSITS3_1_L001_R2_001.fastq.gz")
+    assert q2._taxa_prefix_to_taxa("F") == "Fungi" and q2._taxa_prefix_to_taxa("ALL") == "All"
+    assert q2._taxa_prefix_to_taxa("R") == "Rhizaria"          # upstream quirk: not the " Rhizaria" key
