@@ -40,6 +40,7 @@ constexpr int ENV_THREADS = 128;
 constexpr int ENV_CTAS_PER_SM = 2;
 constexpr int SPEC_C = 5;                  // parser specials kept per row
 constexpr int ENV_ROWF = MAXM + 1;             // floats per envelope row: M[1..45] (cols 0..44), Eraw (col 45)
+constexpr int ENV_ROWBYTES = ENV_ROWF * 32 * 4;    // one row of one warp: 5 888 B, contiguous
 constexpr double kLn2 = 0.69314718055994529;
 
 inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
@@ -307,6 +308,30 @@ struct FbArgs {
 __device__ __forceinline__ void spec_decode(float eraw, float &E, float &S)
 {
     if (eraw > 1.0e4f) { E = 1.0f; S = eraw; } else { E = eraw; S = 1.0f; }
+}
+
+// ---- TMA (bulk async copy) + mbarrier helpers: a warp streams its own scratch rows back into shared memory ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_row_load(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "MBAR_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra MBAR_DONE;\n"
+                 "bra MBAR_WAIT;\n"
+                 "MBAR_DONE:\n"
+                 "}" ::"r"(bar), "r"(parity) : "memory");
 }
 
 __global__ void __launch_bounds__(FB_THREADS, FB_CTAS_PER_SM)
@@ -587,13 +612,22 @@ __global__ void ndom_widen_kernel(const uint8_t *__restrict__ ndom, int n, int32
     if (e < n) out[e] = ndom[e];
     if (e == n) out[e] = 0;
 }
+// work item = entry * MAXDOM + d; sort key = (profile, envelope length) so that the 32 envelopes of a warp tile
+// have (nearly) the same number of rows -- lanes of a tile run to the longest envelope
 __global__ void envwork_kernel(const uint8_t *__restrict__ ndom, const int32_t *__restrict__ envoff, int n,
-                               int32_t *__restrict__ work)
+                               const int32_t *__restrict__ list, int ns, const int32_t *__restrict__ env,
+                               int32_t *__restrict__ work, uint32_t *__restrict__ key)
 {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const int nd = ndom[e], o = envoff[e];
-    for (int d = 0; d < nd; d++) work[o + d] = e * ITSX_MAXDOM + d;
+    const uint32_t p = (uint32_t)(list[e] / ns);
+    for (int d = 0; d < nd; d++) {
+        const int ienv = env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
+        const int jenv = env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1] & 0x3fffffff;
+        work[o + d] = e * ITSX_MAXDOM + d;
+        key[o + d] = (p << 12) | (uint32_t)min(jenv - ienv + 1, 4095);
+    }
 }
 __global__ void gather_bounds_kernel(const int32_t *__restrict__ envoff, const int32_t *__restrict__ bounds, int P,
                                      int32_t *__restrict__ out)
@@ -607,6 +641,7 @@ struct EnvArgs {
     const int32_t *work;      // this profile's slice of the envelope worklist: entry*MAXDOM + d
     int            count;
     const int32_t *list;      // whole pair list of the batch
+    const int32_t *envoff;    // first envelope number of every entry (output slot = envoff[entry] + d)
     const int32_t *env;
     int64_t        s0;
     int            ns, prof;
@@ -628,21 +663,34 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
     for (int t = threadIdx.x; t < (MAXM + 1) * 16; t += ENV_THREADS) s_e[t] = a.etab[t];
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    const int wid = threadIdx.x >> 5;
     const int warp_in_grid = (blockIdx.x * ENV_THREADS + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * ENV_THREADS) >> 5;
     const int ntiles = (a.count + 31) >> 5;
     float *sc = a.scratch + (size_t)warp_in_grid * (size_t)(a.Ldmax + 1) * ENV_ROWF * 32 + lane;
 #define ROW(row, c) sc[((size_t)(row) * ENV_ROWF + (c)) * 32]
+    // Backward reads the Forward rows back in reverse order: each warp streams its rows (ENV_ROWBYTES, contiguous)
+    // into a two-deep shared-memory ring with bulk async copies, one row ahead of use.
+    extern __shared__ __align__(128) unsigned char env_smem[];
+    float *ring = (float *)env_smem + (size_t)wid * 2 * ENV_ROWF * 32;
+    unsigned long long *bars = (unsigned long long *)(env_smem + (size_t)(ENV_THREADS / 32) * 2 * ENV_ROWBYTES) + wid * 2;
+    const uint32_t bar0 = smem_u32(bars), ring0 = smem_u32(ring);
+    if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t phase[2] = {0u, 0u};
+    const float *rowbase = a.scratch + (size_t)warp_in_grid * (size_t)(a.Ldmax + 1) * ENV_ROWF * 32;
     constexpr int C_E = MAXM;
 
     for (int tile = warp_in_grid; tile < ntiles; tile += nwarps) {
         const int t = tile * 32 + lane;
         const bool valid = t < a.count;
-        int L = 0, Ld = 0, ienv = 1;
+        int L = 0, Ld = 0, ienv = 1, oslot = 0;
         const uint32_t *w = a.seqw;
         if (valid) {
             const int wk = a.work[t];
             const int ent = wk / ITSX_MAXDOM, d = wk - ent * ITSX_MAXDOM;
+            oslot = a.envoff[ent] + d;
             const int idx = a.list[ent];
             const int sl = idx - a.prof * a.ns;
             const int64_t s = a.s0 + sl;
@@ -733,15 +781,35 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                 for (int k = 1; k <= MAXM; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
             }
         }
+        // the rows were written through the generic proxy; order them before the async-proxy reads
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            if (Lw >= 1) tma_row_load(ring0 + (Lw & 1) * ENV_ROWBYTES, rowbase + (size_t)Lw * ENV_ROWF * 32, ENV_ROWBYTES, bar0 + (Lw & 1) * 8);
+            if (Lw >= 2) tma_row_load(ring0 + ((Lw - 1) & 1) * ENV_ROWBYTES, rowbase + (size_t)(Lw - 1) * ENV_ROWF * 32, ENV_ROWBYTES, bar0 + ((Lw - 1) & 1) * 8);
+        }
+        // raw E of row i-1 (rescale of the new Backward row) comes through a register, one row ahead
+        float qE = (Lw >= 2 && Lw - 1 <= Ld) ? ROW(Lw - 1, C_E) : 0.f;
         for (int i = Lw; i >= 1; i--) {
+            const int b = i & 1;
+            mbar_wait(bar0 + b * 8, phase[b]);
+            phase[b] ^= 1u;
+            const float *rs = ring + (size_t)b * ENV_ROWF * 32 + lane;
+            const float cEp = qE;
+            if (i >= 3 && i - 2 <= Ld) qE = ROW(i - 2, C_E);
             if (i <= Ld) {
                 float fE, fS;
-                spec_decode(ROW(i, C_E), fE, fS);
+                spec_decode(rs[C_E * 32], fE, fS);
 #pragma unroll
-                for (int k = 1; k <= MAXM; k++) nk[k] = fmaf(ROW(i, k - 1) * Mx[k], fS, nk[k]);
+                for (int k = 1; k <= MAXM; k++) nk[k] = fmaf(rs[(k - 1) * 32] * Mx[k], fS, nk[k]);
+            }
+            __syncwarp();
+            if (lane == 0 && i >= 3)
+                tma_row_load(ring0 + b * ENV_ROWBYTES, rowbase + (size_t)(i - 2) * ENV_ROWF * 32, ENV_ROWBYTES, bar0 + b * 8);
+            if (i <= Ld) {
                 if (i > 1) {
                     float fEp, fSp;
-                    spec_decode(ROW(i - 1, C_E), fEp, fSp);
+                    spec_decode(cEp, fEp, fSp);
                     const float *er = s_e + residue_at(w, ienv - 1 + i - 1);
                     bB = 0.f;
 #pragma unroll
@@ -804,7 +872,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                 null2[x] = s / (float)n;
             }
             null2[15] = 1.0f;
-            float *o = a.out + (size_t)(a.out_base + t) * 20;
+            float *o = a.out + (size_t)oslot * 20;
             o[0] = envsc;
 #pragma unroll
             for (int x = 0; x < 16; x++) o[2 + x] = null2[x];
@@ -1352,14 +1420,28 @@ int search_stage1(itsx_ctx *c)
         CUDA_TRY(c, cudaStreamSynchronize(st));
         const int nenv = h_envb[P];
         if (nenv > 0) {
-            CUDA_TRY(c, c->d_envwork.ensure((size_t)nenv * 4));
             CUDA_TRY(c, c->d_envout.ensure((size_t)nenv * 20 * 4));
+            // worklist sorted by (profile, envelope length): two ping-pong buffers for the radix sort
+            CUDA_TRY(c, c->d_envwork.ensure((size_t)nenv * 4 * 4));
+            int32_t *wk_in = c->d_envwork.as<int32_t>(), *wk_out = wk_in + nenv;
+            uint32_t *key_in = (uint32_t *)(wk_in + 2 * (size_t)nenv), *key_out = key_in + nenv;
             envwork_kernel<<<nblk(n2, 256), 256, 0, st>>>(c->d_ndom.as<uint8_t>(), c->d_envoff.as<int32_t>(), n2,
-                                                          c->d_envwork.as<int32_t>());
-            c->launches++;
+                                                          c->d_list2.as<int32_t>(), ns, c->d_env.as<int32_t>(), wk_in,
+                                                          key_in);
+            {
+                int pbits = 1;
+                while ((1 << pbits) < P) pbits++;
+                size_t tbs = 0;
+                cub::DeviceRadixSort::SortPairs(nullptr, tbs, key_in, key_out, wk_in, wk_out, nenv, 0, 12 + pbits, st);
+                CUDA_TRY(c, c->d_tmp.ensure(tbs));
+                cub::DeviceRadixSort::SortPairs(c->d_tmp.p, tbs, key_in, key_out, wk_in, wk_out, nenv, 0, 12 + pbits, st);
+            }
+            c->launches += 2;
             // envelopes are at most Lmax long; scratch per resident warp
             const int Ldmax = Lmax;
             const size_t eslab = (size_t)(Ldmax + 1) * ENV_ROWF * 32 * 4;
+            const size_t env_smem = (size_t)(ENV_THREADS / 32) * (2 * ENV_ROWBYTES + 16);
+            CUDA_TRY(c, cudaFuncSetAttribute(env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env_smem));
             CUDA_TRY(c, c->d_envscratch.ensure(eslab * env_warps_per_lane * NLANE));
             CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
             for (int l = 0; l < NLANE; l++) CUDA_TRY(c, cudaStreamWaitEvent(c->lanes[l], c->ev_b, 0));
@@ -1369,7 +1451,8 @@ int search_stage1(itsx_ctx *c)
                 if (cnte <= 0) continue;
                 const int l = lane_rr++ % NLANE;
                 EnvArgs ea;
-                ea.work = c->d_envwork.as<int32_t>() + e0;
+                ea.work = wk_out + e0;
+                ea.envoff = c->d_envoff.as<int32_t>();
                 ea.count = cnte;
                 ea.list = c->d_list2.as<int32_t>();
                 ea.env = c->d_env.as<int32_t>();
@@ -1384,7 +1467,7 @@ int search_stage1(itsx_ctx *c)
                 const int tiles = (cnte + 31) / 32;
                 const int wpc = ENV_THREADS / 32;
                 const int ctas = std::min((tiles + wpc - 1) / wpc, c->sm_count * ENV_CTAS_PER_SM);
-                env_kernel<<<ctas, ENV_THREADS, 0, c->lanes[l]>>>(c->pconst[p], ea);
+                env_kernel<<<ctas, ENV_THREADS, env_smem, c->lanes[l]>>>(c->pconst[p], ea);
                 c->launches++;
             }
             for (int l = 0; l < NLANE; l++) {
