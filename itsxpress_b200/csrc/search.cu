@@ -32,8 +32,9 @@ namespace {
 
 constexpr int MAXM = ITSX_MAXM;
 constexpr int KP = ITSX_KP;
-constexpr int MSV_TP = 32;                 // profiles per MSV tile (32 * 23 * 16 * 4 B = 47 KB smem)
-constexpr int MSV_THREADS = 128;
+constexpr int MSV_TP = 32;                 // profiles per MSV tile (32 * 2 layouts * 23 * 16 * 4 B = 94 KB smem)
+constexpr int MSV_THREADS = 256;           // 2 CTAs / SM by shared memory -> 16 warps / SM
+constexpr int MSV_TABW = 2 * KP * 16;      // table words per profile: layout A then layout B
 constexpr int FB_THREADS = 64;              // 2 warps / CTA: 6 CTAs (12 warps) per SM at 168 registers
 constexpr int FB_CTAS_PER_SM = 6;
 constexpr int ENV_THREADS = 128;
@@ -118,19 +119,23 @@ __global__ void __launch_bounds__(256) seqcode_kernel(const uint8_t *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: MSV filter.  State st[j] holds nodes (2j+1, 2j+2) as two s16 lanes with HMMER's u8 values.
-// Before the overflow test fires no lane can reach 255 - bias, so the u8 upper clamp of the reference
-// arithmetic never binds and   sv = max(max(M_{k-1}(i-1), xB) + (bias - cost), 0)   is exact.
-__global__ void __launch_bounds__(MSV_THREADS)
+// K4: MSV filter.  u8-range scores in s16x2 lanes (HMMER's u8 values; before the overflow test fires no lane can
+// reach 255 - bias, so the u8 upper clamp never binds and  sv = max(max(M_{k-1}(i-1), xB) + (bias - cost), 0)
+// is exact).  The diagonal dependency M_k(i) <- M_{k-1}(i-1) is absorbed by alternating two word layouts instead
+// of shifting lanes every row:
+//   layout A: word j = nodes (2j+1, 2j+2)      layout B: word j = nodes (2j, 2j+1)     (node 0 / 46: neutral 0)
+//   A -> B:  new[j] = F(old[j-1], costB[j][x])        B -> A:  new[j] = F(old[j], costA[j][x])
+// so a cell pair costs VIMNMX (xB) + VIADDMNMX (score, floor 0) + half a VIMNMX3 (row maximum) + one LDS.
+__global__ void __launch_bounds__(MSV_THREADS, 2)
 msv_kernel(const uint32_t *__restrict__ seqw, const int64_t *__restrict__ woff, const int32_t *__restrict__ seqlen,
            int64_t s0, int ns, const uint32_t *__restrict__ msvtab, const ProfScalars *__restrict__ pscal, int P,
            const uint8_t *__restrict__ tjbtab, const float *__restrict__ nullsctab, double F1,
            uint8_t *__restrict__ res, uint8_t *__restrict__ flag)
 {
-    extern __shared__ uint32_t s_tab[];    // [tile profiles][KP][16]
+    extern __shared__ uint32_t s_tab[];    // [tile profiles][layout A | layout B][KP][16]
     const int p0 = blockIdx.y * MSV_TP;
     const int np = min(MSV_TP, P - p0);
-    for (int t = threadIdx.x; t < np * KP * 16; t += MSV_THREADS) s_tab[t] = msvtab[(size_t)p0 * KP * 16 + t];
+    for (int t = threadIdx.x; t < np * MSV_TABW; t += MSV_THREADS) s_tab[t] = msvtab[(size_t)p0 * MSV_TABW + t];
     __syncthreads();
 
     const int sl = blockIdx.x * MSV_THREADS + threadIdx.x;
@@ -149,28 +154,36 @@ msv_kernel(const uint32_t *__restrict__ seqw, const int64_t *__restrict__ woff, 
         const int bias = ps.bias, base = ps.base, tec = ps.tec;
         const int tjbm = (tjb + ps.tbm) & 255;
         const int limit = 255 - bias;
-        const uint32_t *tab = s_tab + pl * KP * 16;
+        // the floor operand of VIADDMNMX as a run-time register (pad0 is always 0): a literal 0 makes ptxas
+        // re-materialise zero registers (PRMT / IMAD.MOV) once per cell pair
+        const uint32_t zero = (uint32_t)ps.pad0;
+        const uint32_t *tabA = s_tab + pl * MSV_TABW, *tabB = tabA + KP * 16;
         uint32_t st[KP];
 #pragma unroll
         for (int j = 0; j < KP; j++) st[j] = 0u;
         int xJ = 0, xB = max(base - tjbm, 0), resJ = 0;
         bool ovf = false;
+        uint32_t wnext = L > 0 ? w[0] : 0u;
         for (int wi = 0; wi * 8 < Lw; wi++) {
-            uint32_t word = (wi * 8 < L) ? w[wi] : 0u;
+            uint32_t word = wnext;
+            wnext = ((wi + 1) * 8 < L) ? w[wi + 1] : 0u;       // next residue word, one block ahead
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 const int i = wi * 8 + r;
                 const uint32_t x = word & 15u;
                 word >>= 4;
-                const uint32_t *tx = tab + x;
                 const uint32_t xB2 = (uint32_t)xB * 0x00010001u;
-                uint32_t xE2 = 0u;
+                if ((r & 1) == 0) {                    // layout A -> B
+                    const uint32_t *tx = tabB + x;
 #pragma unroll
-                for (int j = KP - 1; j >= 1; j--) {
-                    uint32_t sh = __byte_perm(st[j - 1], st[j], 0x5432);
-                    st[j] = __viaddmax_s16x2(__vmaxs2(sh, xB2), tx[j * 16], 0u);
+                    for (int j = KP - 1; j >= 1; j--) st[j] = __viaddmax_s16x2(__vmaxs2(st[j - 1], xB2), tx[j * 16], zero);
+                    st[0] = __viaddmax_s16x2(xB2, tx[0], zero);          // nodes (0, 1): predecessors are empty
+                } else {                               // layout B -> A
+                    const uint32_t *tx = tabA + x;
+#pragma unroll
+                    for (int j = 0; j < KP; j++) st[j] = __viaddmax_s16x2(__vmaxs2(st[j], xB2), tx[j * 16], zero);
                 }
-                st[0] = __viaddmax_s16x2(__vmaxs2(st[0] << 16, xB2), tx[0], 0u);
+                uint32_t xE2 = 0u;
 #pragma unroll
                 for (int j = 0; j + 1 < KP; j += 2) xE2 = __vimax3_s16x2(xE2, st[j], st[j + 1]);
                 xE2 = __vmaxs2(xE2, st[KP - 1]);
@@ -1057,7 +1070,7 @@ int search_upload_profiles(itsx_ctx *c)
     if (!c->prof_dirty) return ITSX_OK;
     const int P = (int)c->prof.size();
     cudaStream_t st = c->stream;
-    std::vector<uint32_t> msvtab((size_t)std::max(P, 1) * KP * 16);
+    std::vector<uint32_t> msvtab((size_t)std::max(P, 1) * MSV_TABW);
     std::vector<float> etab((size_t)std::max(P, 1) * (MAXM + 1) * 16, 0.f);
     std::vector<ProfScalars> ps((size_t)std::max(P, 1));
     c->pconst.assign((size_t)P, ProfConst{});
@@ -1071,15 +1084,18 @@ int search_upload_profiles(itsx_ctx *c)
             c->err = "profile '" + h.name + "': MSV bias outside the range the s16x2 kernel is exact for";
             return ITSX_ELIMIT;
         }
-        for (int j = 0; j < KP; j++)
-            for (int x = 0; x < 16; x++) {
-                int v[2];
-                for (int q = 0; q < 2; q++) {
-                    const int k = 2 * j + 1 + q;
-                    v[q] = (k <= h.M) ? h.bias_b - (int)h.cost[k * 16 + x] : -20000;
+        // layout A: word j = nodes (2j+1, 2j+2); layout B: word j = nodes (2j, 2j+1); absent nodes get -20000
+        for (int lay = 0; lay < 2; lay++)
+            for (int j = 0; j < KP; j++)
+                for (int x = 0; x < 16; x++) {
+                    int v[2];
+                    for (int q = 0; q < 2; q++) {
+                        const int k = 2 * j + q + (lay == 0 ? 1 : 0);
+                        v[q] = (k >= 1 && k <= h.M) ? h.bias_b - (int)h.cost[k * 16 + x] : -20000;
+                    }
+                    msvtab[(size_t)p * MSV_TABW + ((size_t)lay * KP + j) * 16 + x] =
+                        ((uint32_t)(uint16_t)(int16_t)v[0]) | ((uint32_t)(uint16_t)(int16_t)v[1] << 16);
                 }
-                msvtab[((size_t)p * KP + j) * 16 + x] = ((uint32_t)(uint16_t)(int16_t)v[0]) | ((uint32_t)(uint16_t)(int16_t)v[1] << 16);
-            }
         for (int k = 1; k <= h.M; k++)
             for (int x = 0; x < 16; x++) etab[((size_t)p * (MAXM + 1) + k) * 16 + x] = h.e[k * 16 + x];
         ProfConst &pc = c->pconst[p];
@@ -1261,7 +1277,7 @@ int search_stage1(itsx_ctx *c)
     CUDA_TRY(c, cudaEventRecord(ev[0], st));
 
     const int ntile_p = (P + MSV_TP - 1) / MSV_TP;
-    const size_t msv_smem = (size_t)MSV_TP * KP * 16 * 4;
+    const size_t msv_smem = (size_t)MSV_TP * MSV_TABW * 4;
     CUDA_TRY(c, cudaFuncSetAttribute(msv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msv_smem));
 
     int64_t chunk = std::min<int64_t>(qn, std::max<int64_t>(1024, (1LL << 30) / P));
