@@ -119,6 +119,7 @@ struct itsx_ctx {
     int64_t nseq = 0;
     int     Lmax = 0;
     DevBuf d_seqw, d_seqwoff, d_seqlen;   // uint32 words (8 residues each), int64 word offset [nseq+1], int32 length
+    DevBuf d_order;                       // int32: sequences of the searched shard sorted by length (+ sort scratch)
     DevBuf d_nullsc, d_tjb;               // per-length tables: float nullsc[Lmax+1], uint8 tjb[Lmax+1]
     std::vector<int32_t> h_seqlen;
     int64_t shard_first = 0, shard_n = -1;

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) seqcode_kernel(const uint8_t *__restrict_
 // so a cell pair costs VIMNMX (xB) + VIADDMNMX (score, floor 0) + half a VIMNMX3 (row maximum) + one LDS.
 __global__ void __launch_bounds__(MSV_THREADS, 2)
 msv_kernel(const uint32_t *__restrict__ seqw, const int64_t *__restrict__ woff, const int32_t *__restrict__ seqlen,
-           int64_t s0, int ns, const uint32_t *__restrict__ msvtab, const ProfScalars *__restrict__ pscal, int P,
+           const int32_t *__restrict__ order, int64_t s0, int ns, const uint32_t *__restrict__ msvtab, const ProfScalars *__restrict__ pscal, int P,
            const uint8_t *__restrict__ tjbtab, const float *__restrict__ nullsctab, double F1,
            uint8_t *__restrict__ res, uint8_t *__restrict__ flag)
 {
@@ -140,7 +140,7 @@ msv_kernel(const uint32_t *__restrict__ seqw, const int64_t *__restrict__ woff, 
 
     const int sl = blockIdx.x * MSV_THREADS + threadIdx.x;
     const bool valid = sl < ns;
-    const int64_t s = s0 + (valid ? sl : 0);
+    const int64_t s = order[s0 + (valid ? sl : 0)];     // sequences are visited in order of length
     const int L = valid ? seqlen[s] : 0;
     const uint32_t *w = seqw + woff[s];
     int Lw = L;
@@ -213,6 +213,12 @@ msv_kernel(const uint32_t *__restrict__ seqw, const int64_t *__restrict__ woff, 
     }
 }
 
+__global__ void iota_kernel(int32_t *out, int32_t first, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = first + (int32_t)i;
+}
+
 // lower_bound of p*ns in the sorted pair list, p = 0..P
 __global__ void bounds_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ n_ptr, int ns, int P,
                               int32_t *__restrict__ bounds)
@@ -232,7 +238,8 @@ __global__ void bounds_kernel(const int32_t *__restrict__ list, const int32_t *_
 // ------------------------------------------------------------------------------------------------
 // K5: bias filter -- 2-state HMM Forward with per-row rescaling (Easel esl_hmm_Forward semantics)
 __global__ void __launch_bounds__(128)
-bias_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ n_ptr, int64_t s0, int ns,
+bias_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ n_ptr, const int32_t *__restrict__ order,
+            int64_t s0, int ns,
             const uint32_t *__restrict__ seqw, const int64_t *__restrict__ woff, const int32_t *__restrict__ seqlen,
             const ProfScalars *__restrict__ pscal, const uint8_t *__restrict__ res,
             const uint8_t *__restrict__ tjbtab, double F1, float *__restrict__ filtersc, uint8_t *__restrict__ flag2,
@@ -242,7 +249,7 @@ bias_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ n_ptr,
     if (e >= *n_ptr) return;
     const int idx = list[e];
     const int p = idx / ns, sl = idx - p * ns;
-    const int64_t s = s0 + sl;
+    const int64_t s = order[s0 + sl];
     const int L = seqlen[s];
     const uint32_t *w = seqw + woff[s];
     const ProfScalars &ps = pscal[p];
@@ -300,6 +307,7 @@ struct FbArgs {
     const int32_t *list;      // worklist (pair index = p*ns + sl), this profile's slice
     const float   *filtersc;
     int            count;
+    const int32_t *order;     // sequences of the shard sorted by length; s0 indexes into it
     int64_t        s0;
     int            ns, prof;
     const uint32_t *seqw;
@@ -369,7 +377,7 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
         if (valid) {
             const int idx = a.list[ent];
             const int sl = idx - a.prof * a.ns;
-            const int64_t s = a.s0 + sl;
+            const int64_t s = a.order[a.s0 + sl];
             L = a.seqlen[s];
             w = a.seqw + a.woff[s];
             filtersc = a.filtersc[ent];
@@ -656,6 +664,7 @@ struct EnvArgs {
     const int32_t *list;      // whole pair list of the batch
     const int32_t *envoff;    // first envelope number of every entry (output slot = envoff[entry] + d)
     const int32_t *env;
+    const int32_t *order;
     int64_t        s0;
     int            ns, prof;
     const uint32_t *seqw;
@@ -706,7 +715,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
             oslot = a.envoff[ent] + d;
             const int idx = a.list[ent];
             const int sl = idx - a.prof * a.ns;
-            const int64_t s = a.s0 + sl;
+            const int64_t s = a.order[a.s0 + sl];
             L = a.seqlen[s];
             w = a.seqw + a.woff[s];
             ienv = a.env[((size_t)ent * ITSX_MAXDOM + d) * 2 + 0];
@@ -901,6 +910,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
 struct FinalArgs {
     const int32_t *list;
     int            n;         // entries in the batch
+    const int32_t *order;
     int64_t        s0;
     int            ns;
     const uint32_t *seqw;
@@ -928,7 +938,7 @@ __global__ void __launch_bounds__(128) final_kernel(const FinalArgs a)
     if (nd == 0) return;
     const int idx = a.list[e];
     const int p = idx / a.ns, sl = idx - p * a.ns;
-    const int64_t s = a.s0 + sl;
+    const int64_t s = a.order[a.s0 + sl];
     const int L = a.seqlen[s];
     const uint32_t *w = a.seqw + a.woff[s];
     const ProfScalars &ps = a.pscal[p];
@@ -1299,14 +1309,29 @@ int search_stage1(itsx_ctx *c)
     double sumM = 0;
     for (auto &h : c->prof) sumM += h.M;
     ss.msv_cells = sumL * sumM;
+    // visit the shard's sequences in order of length: the 32 pairs of a warp then run the same number of rows
+    CUDA_TRY(c, c->d_order.ensure((size_t)qn * 4 * 4));
+    int32_t *d_order = c->d_order.as<int32_t>();
+    {
+        int32_t *idx_in = d_order + qn, *len_in = d_order + 2 * qn, *len_out = d_order + 3 * qn;
+        iota_kernel<<<nblk(qn, 256), 256, 0, st>>>(idx_in, (int32_t)q0, qn);
+        CUDA_TRY(c, cudaMemcpyAsync(len_in, c->d_seqlen.as<int32_t>() + q0, (size_t)qn * 4, cudaMemcpyDeviceToDevice, st));
+        int lbits = 1;
+        while ((1 << lbits) <= c->Lmax) lbits++;
+        size_t tbs = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tbs, len_in, len_out, idx_in, d_order, (int)qn, 0, lbits, st);
+        CUDA_TRY(c, c->d_tmp.ensure(tbs));
+        cub::DeviceRadixSort::SortPairs(c->d_tmp.p, tbs, len_in, len_out, idx_in, d_order, (int)qn, 0, lbits, st);
+        c->launches += 2;
+    }
 
     const int fb_warps_per_lane = c->sm_count * FB_CTAS_PER_SM * (FB_THREADS / 32);
     const int env_warps_per_lane = c->sm_count * ENV_CTAS_PER_SM * (ENV_THREADS / 32);
     std::vector<int32_t> h_bounds((size_t)P + 1), h_envb((size_t)P + 1);
     int32_t *d_nsel = (int32_t *)(c->d_counters.as<unsigned long long>() + 42);
 
-    for (int64_t s0 = q0; s0 < q0 + qn; s0 += chunk) {
-        const int ns = (int)std::min<int64_t>(chunk, q0 + qn - s0);
+    for (int64_t s0 = 0; s0 < qn; s0 += chunk) {          // s0: offset into d_order
+        const int ns = (int)std::min<int64_t>(chunk, qn - s0);
         const size_t npair = (size_t)ns * P;
         // ---- MSV ----
         CUDA_TRY(c, cudaEventRecord(ev[1], st));
@@ -1314,7 +1339,7 @@ int search_stage1(itsx_ctx *c)
         CUDA_TRY(c, c->d_flag.ensure(npair + 16));
         dim3 grid(nblk(ns, MSV_THREADS), ntile_p);
         msv_kernel<<<grid, MSV_THREADS, msv_smem, st>>>(c->d_seqw.as<uint32_t>(), c->d_seqwoff.as<int64_t>(),
-                                                        c->d_seqlen.as<int32_t>(), s0, ns, c->d_msvtab.as<uint32_t>(),
+                                                        c->d_seqlen.as<int32_t>(), d_order, s0, ns, c->d_msvtab.as<uint32_t>(),
                                                         c->d_pscal.as<ProfScalars>(), P, c->d_tjb.as<uint8_t>(),
                                                         c->d_nullsc.as<float>(), c->prm.F1,
                                                         c->d_msvres.as<uint8_t>(), c->d_flag.as<uint8_t>());
@@ -1343,7 +1368,7 @@ int search_stage1(itsx_ctx *c)
         // ---- bias filter ----
         CUDA_TRY(c, c->d_filtersc.ensure((size_t)n1 * 4));
         CUDA_TRY(c, c->d_ndom.ensure((size_t)n1 + 16));   // reused as flag2 here
-        bias_kernel<<<nblk(n1, 128), 128, 0, st>>>(c->d_list.as<int32_t>(), d_nsel, s0, ns, c->d_seqw.as<uint32_t>(),
+        bias_kernel<<<nblk(n1, 128), 128, 0, st>>>(c->d_list.as<int32_t>(), d_nsel, d_order, s0, ns, c->d_seqw.as<uint32_t>(),
                                                    c->d_seqwoff.as<int64_t>(), c->d_seqlen.as<int32_t>(),
                                                    c->d_pscal.as<ProfScalars>(), c->d_msvres.as<uint8_t>(),
                                                    c->d_tjb.as<uint8_t>(), c->prm.F1, c->d_filtersc.as<float>(),
@@ -1395,7 +1420,7 @@ int search_stage1(itsx_ctx *c)
             FbArgs fa;
             fa.list = c->d_list2.as<int32_t>() + b0;
             fa.filtersc = c->d_fsc2.as<float>() + b0;
-            fa.count = cntp; fa.s0 = s0; fa.ns = ns; fa.prof = p;
+            fa.count = cntp; fa.order = d_order; fa.s0 = s0; fa.ns = ns; fa.prof = p;
             fa.seqw = c->d_seqw.as<uint32_t>(); fa.woff = c->d_seqwoff.as<int64_t>(); fa.seqlen = c->d_seqlen.as<int32_t>();
             fa.etab = c->d_etab.as<float>() + (size_t)p * (MAXM + 1) * 16;
             fa.spec = (float *)(c->d_spec.as<char>() + slab * fb_warps_per_lane * l);
@@ -1472,7 +1497,7 @@ int search_stage1(itsx_ctx *c)
                 ea.count = cnte;
                 ea.list = c->d_list2.as<int32_t>();
                 ea.env = c->d_env.as<int32_t>();
-                ea.s0 = s0; ea.ns = ns; ea.prof = p;
+                ea.order = d_order; ea.s0 = s0; ea.ns = ns; ea.prof = p;
                 ea.seqw = c->d_seqw.as<uint32_t>(); ea.woff = c->d_seqwoff.as<int64_t>(); ea.seqlen = c->d_seqlen.as<int32_t>();
                 ea.etab = c->d_etab.as<float>() + (size_t)p * (MAXM + 1) * 16;
                 ea.scratch = (float *)(c->d_envscratch.as<char>() + eslab * env_warps_per_lane * l);
@@ -1496,7 +1521,7 @@ int search_stage1(itsx_ctx *c)
         if (nenv > 0) {
             CUDA_TRY(c, c->d_doms.ensure((size_t)(c->ndom + nenv) * sizeof(DomRec), true, st));
             FinalArgs fa;
-            fa.list = c->d_list2.as<int32_t>(); fa.n = n2; fa.s0 = s0; fa.ns = ns;
+            fa.list = c->d_list2.as<int32_t>(); fa.n = n2; fa.order = d_order; fa.s0 = s0; fa.ns = ns;
             fa.seqw = c->d_seqw.as<uint32_t>(); fa.woff = c->d_seqwoff.as<int64_t>(); fa.seqlen = c->d_seqlen.as<int32_t>();
             fa.pscal = c->d_pscal.as<ProfScalars>(); fa.nullsctab = c->d_nullsc.as<float>();
             fa.logsum = c->d_logsum.as<float>(); fa.fwdsc = c->d_fwdsc.as<float>();
