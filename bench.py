@@ -130,9 +130,9 @@ def run_reference(args, rank, world):
         return
     from oracle import oracle as O
     O.lib()
-    seq, off, which, cfg = synth.make_config("c2", scale=args.scale)
+    seq, off, which, cfg = synth.make_config(args.config, scale=args.scale)
     s, o, desc = cpu_sample(seq, off, which)
-    paths = [os.path.join(synth.HMM_DIR, cfg["hmm_file"])]
+    paths = [os.path.join(synth.HMM_DIR, f) for f in cfg["search_files"]]
     db = O.ProfileDB(paths, [cfg["left_prefix"], cfg["right_prefix"]])
     side = np.array([0 if n.startswith(cfg["left_prefix"]) else 1 for n in db.names], np.int8)
     cores = os.cpu_count()
@@ -153,13 +153,17 @@ def run_reference(args, rank, world):
 
 
 def workload_config(cfg, args):
-    return {"workload": "BASELINE configs[1]: %d single-end %d bp ITS1 reads, %d unique (Zipf s=1), --region ITS1, "
-                        "profiles = %s %s_/%s_ (F.hmm missing from the reference mount)" %
-                        (cfg["n_reads"], cfg["length"], cfg["n_unique"], cfg["hmm_file"], cfg["left_prefix"][0],
-                         cfg["right_prefix"][0]),
+    length = cfg["length"]
+    lmean = sum(length) / 2 if isinstance(length, tuple) else length
+    return {"workload": "%s: %d reads of %s bp, %d unique (Zipf s=1), --region %s, profiles = %s %s_/%s_ "
+                        "(F.hmm missing from the reference mount)" %
+                        ({"c2": "BASELINE configs[1]", "c2_small": "configs[1] reduced", "c4s": "configs[3] shape, scaled",
+                          "c3s": "configs[2] shape, scaled"}[args.config], cfg["n_reads"], length, cfg["n_unique"],
+                         cfg["region"], "+".join(cfg["search_files"]) if len(cfg["search_files"]) < 4 else
+                         "%d taxon files" % len(cfg["search_files"]), cfg["left_prefix"][0], cfg["right_prefix"][0]),
             "taxa": cfg["taxa"], "region": cfg["region"], "scale": args.scale,
             "l2_policy": "inputs (%.0f MB of read bytes per step) are larger than the 126 MB L2" %
-                         (cfg["n_reads"] * cfg["length"] / 1e6),
+                         (cfg["n_reads"] * lmean / 1e6),
             "parallelism": "1 sample per GPU (independent samples, no data-path collective)"}
 
 
@@ -170,9 +174,9 @@ def run_sharded_bench(args, ctx, rank, world, local):
     import torch.distributed as dist
     from itsxpress_b200 import _lib
     from itsxpress_b200.distributed import Comm, GpuEngine, block_range, run_sharded
-    seq, off, which, cfg = synth.make_config("c2", scale=args.scale)
+    seq, off, which, cfg = synth.make_config(args.config, scale=args.scale)
     n = len(off) - 1
-    ctx.load_profiles([os.path.join(synth.HMM_DIR, cfg["hmm_file"])], [cfg["left_prefix"], cfg["right_prefix"]])
+    ctx.load_profiles([os.path.join(synth.HMM_DIR, f) for f in cfg["search_files"]], [cfg["left_prefix"], cfg["right_prefix"]])
     ctx.set_sides_by_prefix(cfg["left_prefix"], cfg["right_prefix"])
     lo, hi = block_range(n, rank, world)
     bseq = np.ascontiguousarray(seq[off[lo]:off[hi]])
@@ -230,6 +234,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (testing only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4s", "c3s", "c2_small"],
+                    help="workload: c2 = BASELINE configs[1] (the headline); c4s / c3s = scaled shapes of configs[3] / [2]")
     ap.add_argument("--sharded", action="store_true",
                     help="ONE sample sharded over all ranks (hash-partitioned derep all-to-all, domZ all-reduce, "
                          "position all-gather; strong scaling) instead of one sample per rank")
@@ -257,9 +263,9 @@ def main():
             dist.destroy_process_group()
         return
     # every rank gets its own sample (different seed)
-    seq, off, which, cfg = synth.make_config("c2", seed=2 * 1_000_003 + rank, scale=args.scale)
+    seq, off, which, cfg = synth.make_config(args.config, seed=2 * 1_000_003 + rank, scale=args.scale)
     nreads = len(off) - 1
-    ctx.load_profiles([os.path.join(synth.HMM_DIR, cfg["hmm_file"])], [cfg["left_prefix"], cfg["right_prefix"]])
+    ctx.load_profiles([os.path.join(synth.HMM_DIR, f) for f in cfg["search_files"]], [cfg["left_prefix"], cfg["right_prefix"]])
     ctx.set_sides_by_prefix(cfg["left_prefix"], cfg["right_prefix"])
     prm = _lib.default_params()
 
@@ -342,7 +348,7 @@ def main():
     K = args.steps
     sec = {k: v / 1e3 / K for k, v in stage.items()}
     dsec = {k: v / 1e3 / K for k, v in dstage.items()}
-    L = cfg["length"]
+    L = sum(cfg["length"]) / 2 if isinstance(cfg["length"], tuple) else cfg["length"]
     stages = {
         "msv": {"ms": sec["ms_msv"] * 1e3, "gcups": ss.msv_cells / max(sec["ms_msv"], 1e-9) / 1e9,
                 "peak_gcups": pk["int_gcups"], "bound": "int-alu (s16x2 DPX)"},
@@ -378,7 +384,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import oracle as O
         s, o, desc = cpu_sample(seq, off, which)
-        db = O.ProfileDB([os.path.join(synth.HMM_DIR, cfg["hmm_file"])], [cfg["left_prefix"], cfg["right_prefix"]])
+        db = O.ProfileDB([os.path.join(synth.HMM_DIR, f) for f in cfg["search_files"]], [cfg["left_prefix"], cfg["right_prefix"]])
         side = np.array([0 if n.startswith(cfg["left_prefix"]) else 1 for n in db.names], np.int8)
         t0 = time.perf_counter()
         kept, ost = oracle_pipeline(O, db, side, s, o)

@@ -541,10 +541,9 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
                     for (int k = MAXM; k >= 1; k--) {
                         const float mpe_k = Mx[k];
                         const float ic = fmaf(mnext, pc.ba[k][0], Ix[k] * pc.ba[k][1]);
-                        float mc = fmaf(mnext, pc.ba[k][2], Ix[k] * pc.ba[k][3]);
-                        float dc = mnext * pc.bd[k][0];
-                        dc = fmaf(Dx[k + 1], pc.bd[k][1], dc) + bE;
-                        mc = fmaf(Dx[k + 1], pc.bd[k][2], mc) + bE;
+                        // every M and D state also exits to E: bE is the addend the FMA chains start from
+                        const float dc = fmaf(mnext, pc.bd[k][0], fmaf(Dx[k + 1], pc.bd[k][1], bE));
+                        const float mc = fmaf(mnext, pc.ba[k][2], fmaf(Ix[k], pc.ba[k][3], fmaf(Dx[k + 1], pc.bd[k][2], bE)));
                         Mx[k] = mc; Ix[k] = ic; Dx[k] = dc;
                         mnext = mpe_k;
                     }
@@ -849,10 +848,9 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                     for (int k = MAXM; k >= 1; k--) {
                         const float mpe_k = Mx[k];
                         const float ic = fmaf(mnext, pc.ba[k][0], Ix[k] * pc.ba[k][1]);
-                        float mc = fmaf(mnext, pc.ba[k][2], Ix[k] * pc.ba[k][3]);
-                        float dc = mnext * pc.bd[k][0];
-                        dc = fmaf(Dx[k + 1], pc.bd[k][1], dc) + bE;
-                        mc = fmaf(Dx[k + 1], pc.bd[k][2], mc) + bE;
+                        // every M and D state also exits to E: bE is the addend the FMA chains start from
+                        const float dc = fmaf(mnext, pc.bd[k][0], fmaf(Dx[k + 1], pc.bd[k][1], bE));
+                        const float mc = fmaf(mnext, pc.ba[k][2], fmaf(Ix[k], pc.ba[k][3], fmaf(Dx[k + 1], pc.bd[k][2], bE)));
                         Mx[k] = mc; Ix[k] = ic; Dx[k] = dc;
                         mnext = mpe_k;
                     }

@@ -621,10 +621,9 @@ static float backward_engine(const prof_t *pf, const xf_t *xf, const uint8_t *ds
             const float *tk    = tp + k * 7;
             float        mnext = mpe[k + 1];
             float        ic    = fmaf(mnext, tk[T_IM], Ix[k] * tk[T_II]);
-            float        mc    = fmaf(mnext, tk[T_MM], Ix[k] * tk[T_MI]);
-            float        dc    = mnext * tk[T_DM];
-            dc                 = fmaf(Dx[k + 1], tk[T_DD], dc) + xE;
-            mc                 = fmaf(Dx[k + 1], tk[T_MD], mc) + xE;
+            /* every M and D state also exits to E: xE is the addend the FMA chains start from */
+            float        dc    = fmaf(mnext, tk[T_DM], fmaf(Dx[k + 1], tk[T_DD], xE));
+            float        mc    = fmaf(mnext, tk[T_MM], fmaf(Ix[k], tk[T_MI], fmaf(Dx[k + 1], tk[T_MD], xE)));
             Mx[k] = mc; Ix[k] = ic; Dx[k] = dc;
         }
         float s = fsp->S[r];

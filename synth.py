@@ -145,6 +145,15 @@ CONFIGS = {
     # missing from the reference mount, so the largest present analogue M.hmm (Metazoa) stands in.
     "c2": dict(n_reads=1_000_000, n_unique=300_000, length=250, hmm_file="M.hmm", left_prefix="1_",
                right_prefix="2_", zipf_s=1.0, region="ITS1", taxa="Metazoa (stand-in for Fungi: F.hmm missing)"),
+    # scaled-down BASELINE configs[3] shape: merged reads of 330-441 bp, 90 % unique, ITS2 (hmmsearch-bound)
+    "c4s": dict(n_reads=400_000, n_unique=360_000, length=(330, 441), hmm_file="M.hmm", left_prefix="3_",
+                right_prefix="4_", zipf_s=1.0, spacer=(150, 230), region="ITS2",
+                taxa="Metazoa (stand-in for Fungi: F.hmm missing)"),
+    # scaled-down BASELINE configs[2] shape: merged reads ~450 bp, 40 % unique, --region ALL --taxa All
+    # (motifs sampled from M.hmm, searched against the 1_/4_ profiles of EVERY present taxon file)
+    "c3s": dict(n_reads=200_000, n_unique=80_000, length=(380, 520), hmm_file="M.hmm", left_prefix="1_",
+                right_prefix="4_", zipf_s=1.0, spacer=(250, 330), region="ALL", taxa="All",
+                search_files="ALL"),
     # reduced copy of the same shape for smoke tests
     "c2_small": dict(n_reads=20_000, n_unique=6_000, length=250, hmm_file="M.hmm", left_prefix="1_",
                      right_prefix="2_", zipf_s=1.0, region="ITS1", taxa="Metazoa"),
@@ -154,9 +163,14 @@ CONFIGS = {
 def make_config(name, seed=None, scale=1.0):
     cfg = dict(CONFIGS[name])
     meta = {k: cfg.pop(k) for k in ("region", "taxa")}
+    search_files = cfg.pop("search_files", None)
     if scale != 1.0:
         cfg["n_reads"] = max(1000, int(cfg["n_reads"] * scale))
         cfg["n_unique"] = max(300, int(cfg["n_unique"] * scale))
     seed = 2 * 1_000_003 if seed is None else seed
     seq, off, qual, which = make_reads(seed, **cfg)
-    return seq, off, which, dict(cfg, **meta)
+    if search_files == "ALL":
+        files = sorted(f for f in os.listdir(HMM_DIR) if f.endswith(".hmm") and os.path.getsize(os.path.join(HMM_DIR, f)))
+    else:
+        files = [cfg["hmm_file"]]
+    return seq, off, which, dict(cfg, search_files=files, **meta)
