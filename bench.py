@@ -30,8 +30,13 @@ sys.path.insert(0, ROOT)
 
 import synth  # noqa: E402
 
-INT_OPS_PER_2CELLS = 3.0      # vmax, viaddmax, max-into-xE: the algorithmic minimum of one s16x2 MSV step
-FP_OPS_PER_CELL = 11.0        # Forward (and Backward): FMA-pipe instructions per M/I/D cell
+INT_OPS_PER_2CELLS = 3.0      # VIMNMX (xB), VIADDMNMX (score, floor), half a VIMNMX3 x2 (row max): one s16x2 MSV cell pair
+FP_OPS_PER_CELL = 10.0        # Forward 11 + Backward 9 FMA-pipe instructions per M/I/D cell, averaged
+ENV_OPS_PER_CELL = 11.0       # envelope: Forward 11 + Backward 9 + decoding 2 per row cell, counted as 2 cells
+# issue rates measured on this pool's B200 with tools/ubench/ffma2.cu (profiles/r1_ubench_issue_rates.txt):
+# warp-instructions per clock per SM at 1965 MHz
+MEASURED_FFMA_PER_CLK_SM = 3.820
+MEASURED_S16X2_PER_CLK_SM = 1.959
 
 
 def peaks():
@@ -44,8 +49,10 @@ def peaks():
         except Exception:
             pass
     f = d["sm_max_mhz"] * 1e6
-    d["int_gcups"] = 148 * 4 * 16 * f * 2.0 / INT_OPS_PER_2CELLS / 1e9      # 16 int lanes/clk/SMSP
-    d["fp_gcups"] = 148 * 128 * f / FP_OPS_PER_CELL / 1e9
+    # cells/s = SMs x warp-instr/clk/SM x 32 lanes x f / instructions per cell
+    d["int_gcups"] = 148 * MEASURED_S16X2_PER_CLK_SM * 32 * f * 2.0 / INT_OPS_PER_2CELLS / 1e9
+    d["fp_gcups"] = 148 * MEASURED_FFMA_PER_CLK_SM * 32 * f / FP_OPS_PER_CELL / 1e9
+    d["env_gcups"] = 148 * MEASURED_FFMA_PER_CLK_SM * 32 * f / ENV_OPS_PER_CELL / 1e9
     return d
 
 
@@ -356,7 +363,7 @@ def main():
                            "gcups": (ss.fwd_cells + ss.bck_cells) / max(sec["ms_fwd"], 1e-9) / 1e9,
                            "peak_gcups": pk["fp_gcups"], "bound": "fp32 fma"},
         "envelope": {"ms": sec["ms_env"] * 1e3, "gcups": ss.env_cells / max(sec["ms_env"], 1e-9) / 1e9,
-                     "peak_gcups": pk["fp_gcups"], "bound": "fp32 fma / hbm scratch"},
+                     "peak_gcups": pk["env_gcups"], "bound": "fp32 fma (+ TMA-staged scratch rows)"},
         "bias": {"ms": sec["ms_bias"] * 1e3, "rows_per_s": ss.bias_rows / max(sec["ms_bias"], 1e-9)},
         "derep_pack": {"ms": dsec["ms_pack"] * 1e3,
                        "gbs": ds.bytes_ascii * (1 + 0.25 + 0.125) / max(dsec["ms_pack"], 1e-9) / 1e9,
@@ -373,12 +380,17 @@ def main():
                      "multidomain_regions": ss.n_multidomain_regions},
     }
     dom = max(("msv", "fwd_bwd_decode", "envelope"), key=lambda k: stages[k]["ms"])
-    roof = {"kernel": {"msv": "msv_kernel", "fwd_bwd_decode": "fb_kernel", "envelope": "env_kernel"}[dom],
-            "bound": "alu", "achieved": stages[dom]["gcups"], "peak": stages[dom]["peak_gcups"], "unit": "GCUPS",
-            "frac": stages[dom]["gcups"] / stages[dom]["peak_gcups"], "traffic": None,
-            "note": "DP recurrence: integer/fp32 ALU bound, not HBM or tensor; peak = computed issue-rate peak at "
-                    "clocks.max.sm (%s HBM peak %.0f GB/s used for the derep kernels in `stages`)" %
-                    (pk["source"], pk["hbm_gbs"])}
+    # dram traffic of the dominant kernel from the committed ncu --set full capture (one per-profile launch at
+    # --scale 0.2; profiles/*_fb_kernel_full.md): far below anything HBM-bound -- the DP kernels are issue-bound
+    traffic = {"fb_kernel": 260.4e6, "env_kernel": 709.2e6, "msv_kernel": 8.6e6}
+    kname = {"msv": "msv_kernel", "fwd_bwd_decode": "fb_kernel", "envelope": "env_kernel"}[dom]
+    roof = {"kernel": kname, "bound": "alu", "achieved": stages[dom]["gcups"], "peak": stages[dom]["peak_gcups"],
+            "unit": "GCUPS", "frac": stages[dom]["gcups"] / stages[dom]["peak_gcups"], "traffic": traffic[kname],
+            "traffic_note": "dram bytes of one launch in the ncu capture at --scale 0.2 (per-profile launch)",
+            "note": "DP recurrence: fp32 / s16x2 issue-bound, not HBM or tensor; peak = MEASURED issue rate "
+                    "(tools/ubench/ffma2.cu: %.3f FFMA, %.3f VIADDMNMX.S16x2 warp-instr/clk/SM) x 148 SMs x "
+                    "clocks.max.sm / instructions per cell; %s HBM peak %.0f GB/s is used for the derep kernels in "
+                    "`stages`" % (MEASURED_FFMA_PER_CLK_SM, MEASURED_S16X2_PER_CLK_SM, pk["source"], pk["hbm_gbs"])}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -38,6 +38,7 @@ extern "C" {
 #define ITSX_EIO      -4   /* cannot read a profile file */
 #define ITSX_ECOLLIDE -5   /* unresolvable 64-bit key collision in derep (two independent hashes) */
 #define ITSX_ELIMIT   -6   /* a fixed capacity was exceeded (domains per hit, model length) */
+#define ITSX_EFORMAT  -7   /* malformed FASTQ (host scanner); text in itsx_host_last_error */
 
 #define ITSX_MAXM      45  /* longest profile the DP kernels hold in registers (all ITSx_db profiles) */
 #define ITSX_MAXDOM     8  /* envelopes kept per (sequence, profile) hit */
@@ -194,6 +195,24 @@ int  itsx_reads_upload(itsx_ctx *ctx, const uint8_t *seq, const int64_t *off, in
 int  itsx_run_resident(itsx_ctx *ctx, const itsx_search_params *prm, itsx_run_stats *st);
 /* number of kernel launches issued by this ctx so far (bench.py's gpu_launches) */
 int64_t itsx_launch_count(const itsx_ctx *ctx);
+
+/* ---- host-side FASTQ scanner / packer / formatter (multi-threaded C++, no GPU involved) -------------
+ * Replace Biopython's SeqIO.parse / SeqIO.write on the path (SeqSample.py:746-757, 912-945): a decompressed
+ * 4-line FASTQ buffer -> offset arrays (title after '@' right-stripped, sequence, quality), packed byte
+ * streams for itsx_derep / itsx_trim_*, and FASTQ text from the slices itsx_trim_gather returns. */
+const char *itsx_host_last_error(void);
+/* cap == 0: count records only.  Returns the record count or ITSX_EFORMAT / ITSX_EINVAL. */
+int64_t itsx_fastq_index(const uint8_t *buf, int64_t nbytes, int64_t cap, int64_t *t_off, int32_t *t_len,
+                         int64_t *s_off, int32_t *s_len, int64_t *q_off);
+/* out_off[n+1] = prefix sums of len; out (may be NULL) = segments packed back to back.  Returns total bytes. */
+int64_t itsx_bytes_gather(const uint8_t *buf, const int64_t *off, const int32_t *len, int64_t n, uint8_t *out,
+                          int64_t *out_off);
+/* '@title\nseq\n+\nqual\n' for nkeep records (dst == NULL: size query); pre_ and suf_ (lp, ls bytes) are stitched to
+ * every record's bases and qualities (--trim-ccs, SeqSample.py:601-622).  Returns the number of bytes. */
+int64_t itsx_fastq_format(const uint8_t *buf, const int64_t *t_off, const int32_t *t_len, const int32_t *keep_idx,
+                          int64_t nkeep, const int64_t *out_off, const uint8_t *out_seq, const uint8_t *out_qual,
+                          const uint8_t *pre_s, const uint8_t *pre_q, int32_t lp, const uint8_t *suf_s,
+                          const uint8_t *suf_q, int32_t ls, uint8_t *dst);
 
 #ifdef __cplusplus
 }

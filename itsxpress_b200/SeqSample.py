@@ -28,6 +28,14 @@ logger = logging.getLogger(__name__)
 CCS_FWD = b"GACAGGTACAAGAAGGA"      # synthetic primers of --trim-ccs (SeqSample.py:601-603)
 CCS_REV = b"TTAACCCAGTCTCCAGT"
 
+# uc.txt / rep.fa / domtbl.txt are the reference's inter-stage interface and are always written for samples up to
+# this many reads (and whenever --keeptemp / ITSX_TEMP_FILES=always asks for them).  Above it, in "auto" mode, the
+# text files would dominate the run (a 1 M-read sample has ~16 M domtbl rows), so one-line placeholders are left in
+# their place and ItsPosition / Dedup take the arrays of the live GPU session.
+TEMP_FILE_POLICY = os.environ.get("ITSX_TEMP_FILES", "auto")      # auto | always | never
+TEMP_FILE_AUTO_MAX_READS = 200_000
+_PLACEHOLDER = "# itsxpress-b200: not materialised for a large sample; rerun with --keeptemp or ITSX_TEMP_FILES=always\n"
+
 _CTX = None
 _GENERATION = 0           # bumped whenever the shared context's resident sample / search changes
 _SESSIONS = {}            # abspath of uc.txt / rep.fa / domtbl.txt  ->  _Session that wrote it
@@ -46,7 +54,7 @@ class _Session:
 
     def __init__(self):
         self.batch = None          # FastqBatch of seq_file
-        self.ids = None            # record ids (first token of the title)
+        self.files = True          # uc.txt / rep.fa / domtbl.txt were written in full
         self.rep = None            # int32[n]  index of the representative read
         self.uid = None            # int32[n]  dense unique id, first-occurrence order
         self.first = None          # int32[U]  read index of every unique
@@ -57,6 +65,17 @@ class _Session:
         self.nseq = 0
         self.seq_path = None
         self.seq_ids = None
+
+    def ensure_seq_ids(self):
+        if self.seq_ids is None and self.batch is not None and self.first is not None:
+            ids = self.ids
+            self.seq_ids = [ids[i] for i in self.first.tolist()]
+        return self.seq_ids
+
+    @property
+    def ids(self):
+        """Record ids (first token of the title); materialised on first use."""
+        return self.batch.ids() if self.batch is not None else None
 
 
 def _external(tool, argv, what):
@@ -87,6 +106,16 @@ class SeqSample:
         self.r1 = None
         self.fastq2 = None
         self._session = None
+        self.materialize = None        # True / False overrides TEMP_FILE_POLICY (main.py sets it for --keeptemp)
+
+    def _want_files(self, n_reads):
+        if self.materialize is not None:
+            return bool(self.materialize)
+        if TEMP_FILE_POLICY == "always":
+            return True
+        if TEMP_FILE_POLICY == "never":
+            return False
+        return n_reads <= TEMP_FILE_AUTO_MAX_READS
 
     # -- steps outside the named hot path: still the external tool, exactly as upstream ------------------
     def orient_reads(self, threads=1):
@@ -121,15 +150,22 @@ class SeqSample:
             _GENERATION += 1
             first, _ = ctx.derep_clusters(nu)
             s = _Session()
-            s.batch, s.ids, s.rep, s.first, s.n_unique = batch, batch.ids(), rep, first, nu
+            s.batch, s.rep, s.first, s.n_unique = batch, rep, first, nu
             s.uid = np.searchsorted(first, rep).astype(np.int32) if nu else np.zeros(0, np.int32)
             s.derep_gen = _GENERATION
             s.seq_path = os.path.abspath(self.seq_file)
-            order = host.cluster_order(rep, s.ids)
-            with open(self.rep_file, "wb") as f:
-                f.write(host.write_rep_fasta(batch, order, s.ids))
-            with open(self.uc_file, "wb") as f:
-                f.write(host.write_uc(rep, strand, s.ids, batch.s_len, order))
+            s.files = self._want_files(batch.n)
+            if s.files:
+                ids = s.ids
+                order = host.cluster_order(rep, ids)
+                with open(self.rep_file, "wb") as f:
+                    f.write(host.write_rep_fasta(batch, order, ids))
+                with open(self.uc_file, "wb") as f:
+                    f.write(host.write_uc(rep, strand, ids, batch.s_len, order))
+            else:
+                for path in (self.rep_file, self.uc_file):
+                    with open(path, "w") as f:
+                        f.write(_PLACEHOLDER)
             st = ctx.derep_stats()
             logging.info("GPU dereplication: %d reads, %d unique sequences, %.2f ms on device" %
                          (batch.n, nu, st.ms_total))
@@ -161,7 +197,7 @@ class SeqSample:
                 # representatives are already on the device, in first-occurrence order
                 ctx.set_sides(np.full(len(ctx.names), -1, np.int8))
                 ctx.search()
-                seq_ids = [s.ids[i] for i in s.first.tolist()]
+                seq_ids = None
                 nseq = s.n_unique
             else:
                 seq_ids, seq, off = _read_fasta(self.rep_file)
@@ -173,14 +209,25 @@ class SeqSample:
             s.search_gen = _GENERATION
             if resident:
                 s.derep_gen = _GENERATION
-            s.names, s.nseq, s.seq_ids = list(ctx.names), nseq, seq_ids
-            rows = ctx.hits()
-            M = [ctx.profile_M(p) for p in range(len(ctx.names))]
-            with open(self.dom_file, "wb") as f:
-                f.write(host.write_domtbl(rows, seq_ids, ctx.names, M, nseq, ctx.nreported()))
+            s.names, s.nseq = list(ctx.names), nseq
+            if self._want_files(s.batch.n if s.batch is not None else nseq):
+                if seq_ids is None:
+                    ids = s.ids
+                    seq_ids = [ids[i] for i in s.first.tolist()]
+                s.seq_ids = seq_ids
+                rows = ctx.hits()
+                M = [ctx.profile_M(p) for p in range(len(ctx.names))]
+                with open(self.dom_file, "wb") as f:
+                    f.write(host.write_domtbl(rows, seq_ids, ctx.names, M, nseq, ctx.nreported()))
+                nrows = len(rows)
+            else:
+                s.files = False
+                with open(self.dom_file, "w") as f:
+                    f.write(_PLACEHOLDER)
+                nrows = ctx.search_stats().n_domains_reported
             st = ctx.search_stats()
             logging.info("GPU hmmsearch: %d sequences x %d profiles, %d domain rows, %.1f ms on device" %
-                         (nseq, len(ctx.names), len(rows), st.ms_total))
+                         (nseq, len(ctx.names), nrows, st.ms_total))
             _SESSIONS[os.path.abspath(self.dom_file)] = s
         except FileNotFoundError as f:
             logging.error("A file needed by the profile search was not found: %s" % f)
@@ -355,6 +402,8 @@ class Dedup:
         self._session = s if (s is not None and s.rep is not None) else None
         if self._session is None:
             self.parse()
+            if not self._matchdict and _is_placeholder(uc_file):
+                logging.warning("uc file %s is a placeholder (large sample, temp files not materialised)" % uc_file)
 
     @property
     def matchdict(self):
@@ -465,20 +514,27 @@ class Dedup:
         return (a for a, _ in done), (b for _, b in done)
 
     # ---- bulk API: whole files through the GPU ---------------------------------------------------------------------
-    def _unique_table(self, ids, itspos):
-        """uid[read] (dense unique index or -1) and the (start, stop, tlen) table per unique for the reads
-        ``ids``.  Fast path: arrays of the live session; general path: matchdict + itspos.get_position (any
+    def _unique_table(self, batch, ids, itspos):
+        """uid[read] (dense unique index or -1) and the (start, stop, tlen) table per unique for the reads of
+        ``batch``.  Fast path: arrays of the live session; general path: matchdict + itspos.get_position (any
         duck-typed object), evaluated once per distinct representative."""
         s = self._session
         if (s is not None and isinstance(itspos, ItsPosition) and itspos._dev is not None and
-                itspos._session is s and s.ids is not None):
+                itspos._session is s and s.batch is not None):
             dev = itspos._dev
-            if ids is s.ids:
+            if batch is s.batch:
                 uid = s.uid
             else:
+                if ids is None:
+                    ids = batch.ids()
                 where = {k: i for i, k in enumerate(s.ids)}
                 uid = np.fromiter((s.uid[where[k]] if k in where else -1 for k in ids), np.int32, len(ids))
             return uid, dev["start"], dev["stop"], dev["tlen"], s.n_unique
+        if s is not None and not s.files and not self._matchdict_set:
+            raise RuntimeError("the temp files of this sample were not materialised and the GPU session that holds "
+                               "its arrays is no longer live; rerun with --keeptemp or ITSX_TEMP_FILES=always")
+        if ids is None:
+            ids = batch.ids()
         md = self.matchdict or {}
         index, start, stop, tlen = {}, [], [], []
         uid = np.full(len(ids), -1, np.int32)
@@ -503,7 +559,7 @@ class Dedup:
     def _trim_file(self, batch, ids, itspos, mode, trim_ccs):
         """FASTQ text of ``batch`` trimmed on the GPU (mode 0 single, 2 paired R1, 1 paired R2)."""
         global _GENERATION
-        uid, start, stop, tlen, nu = self._unique_table(ids, itspos)
+        uid, start, stop, tlen, nu = self._unique_table(batch, ids, itspos)
         if mode != 0 and np.any((tlen < 0) & (start >= 0) & (stop >= 0) & (start < stop)):
             raise ValueError("Could not retrieve valid positions for a kept sequence (tlen is missing)")
         ctx = get_context()
@@ -523,10 +579,9 @@ class Dedup:
         (SeqSample.py:886-949)."""
         if self._session is not None and self._session.batch is not None and \
                 os.path.abspath(self.seq_file) == self._session.seq_path:
-            batch, ids = self._session.batch, self._session.ids
+            batch, ids = self._session.batch, None
         else:
-            batch = fq.read_fastq(self.seq_file)
-            ids = batch.ids()
+            batch, ids = fq.read_fastq(self.seq_file), None
         text, ki, n_empty = self._trim_file(batch, ids, itspos, 0, trim_ccs)
         if not wri_file:
             if n_empty and not trim_ccs:
@@ -552,7 +607,7 @@ class Dedup:
             b2 = _head(b2, n)
         ids1 = b1.ids()                         # the filter is keyed on R1's id (SeqSample.py:591)
         t1, k1, e1 = self._trim_file(b1, ids1, itspos, 2, trim_ccs)
-        t2, k2, e2 = self._trim_file(b2, ids1, itspos, 1, trim_ccs)
+        t2, k2, e2 = self._trim_file(b2, ids1, itspos, 1, trim_ccs)      # keyed on R1's ids
         if not wri_file:
             if (e1 or e2) and not trim_ccs:
                 print("Total number of sequences that are empty Split A: ", e1)
@@ -560,6 +615,14 @@ class Dedup:
             return
         fq.write_compressed(outfile1, t1, gzipped=gzipped, zstd_file=zstd_file)
         fq.write_compressed(outfile2, t2, gzipped=gzipped, zstd_file=zstd_file)
+
+
+def _is_placeholder(path):
+    try:
+        with open(path) as f:
+            return f.readline().startswith("# itsxpress-b200: not materialised")
+    except Exception:
+        return False
 
 
 def _head(batch, n):

@@ -71,6 +71,7 @@ SYMBOLS = [
     "itsx_nreported_set", "itsx_search_stage2", "itsx_positions_set",
     "itsx_trim_set_map", "itsx_trim_bounds", "itsx_trim_gather", "itsx_run", "itsx_reads_upload", "itsx_run_resident",
     "itsx_launch_count",
+    "itsx_host_last_error", "itsx_fastq_index", "itsx_bytes_gather", "itsx_fastq_format",
 ]
 
 
@@ -132,6 +133,14 @@ def lib():
     L.itsx_run_resident.argtypes = [vp, C.POINTER(SearchParams), C.POINTER(RunStats)]
     L.itsx_launch_count.argtypes = [vp]
     L.itsx_launch_count.restype = i64
+    L.itsx_host_last_error.restype = C.c_char_p
+    L.itsx_fastq_index.restype = i64
+    L.itsx_fastq_index.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp]
+    L.itsx_bytes_gather.restype = i64
+    L.itsx_bytes_gather.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.itsx_fastq_format.restype = i64
+    L.itsx_fastq_format.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, C.c_char_p, C.c_char_p, i32, C.c_char_p,
+                                    C.c_char_p, i32, vp]
     _LIB = L
     return L
 

@@ -118,14 +118,15 @@ def block_range(n, rank, world):
 
 
 def _gather_segments(seq, off, idx):
-    """Bases of reads ``idx`` packed back to back -> (bytes, lengths)."""
+    """Bases of reads ``idx`` packed back to back -> (bytes, lengths); multi-threaded memcpy in libitsx_b200
+    (itsx_bytes_gather), host side only."""
+    from .fastq import _gather
+    idx = np.asarray(idx, dtype=np.int64)
     lens = (off[1:] - off[:-1])[idx]
-    o = np.zeros(len(idx) + 1, np.int64)
-    np.cumsum(lens, out=o[1:])
-    if len(idx) == 0 or o[-1] == 0:
+    if len(idx) == 0:
         return np.zeros(0, np.uint8), lens
-    delta = np.repeat(off[idx] - o[:-1], lens)
-    return seq[delta + np.arange(int(o[-1]), dtype=np.int64)], lens
+    out, _ = _gather(seq, off[idx], lens)
+    return out, lens
 
 
 # ---- the sharded hot path --------------------------------------------------------------------------------------

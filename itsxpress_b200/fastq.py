@@ -22,12 +22,13 @@ class FastqBatch:
     s_off/s_len : sequence start / length (q_off: quality start; same length)
     """
 
-    __slots__ = ("buf", "t_off", "t_len", "s_off", "s_len", "q_off", "n")
+    __slots__ = ("buf", "t_off", "t_len", "s_off", "s_len", "q_off", "n", "_ids")
 
     def __init__(self, buf, t_off, t_len, s_off, s_len, q_off):
         self.buf, self.t_off, self.t_len = buf, t_off, t_len
         self.s_off, self.s_len, self.q_off = s_off, s_len, q_off
         self.n = len(t_off)
+        self._ids = None
 
     # -- flat views for the device path -------------------------------------------------------
     def seq_concat(self):
@@ -41,15 +42,28 @@ class FastqBatch:
         o = int(self.t_off[i])
         return self.buf[o:o + int(self.t_len[i])].tobytes().decode("ascii", "replace")
 
+    def id_lengths(self):
+        """Length of the first whitespace-delimited token of every title, vectorised (titles never start with
+        white space in practice; a leading blank gives an empty id, as str.split would not -- callers that care
+        use ids())."""
+        ws = np.flatnonzero((self.buf == 32) | (self.buf == 9))
+        if len(ws) == 0 or self.n == 0:
+            return self.t_len.astype(np.int64)
+        nxt = np.searchsorted(ws, self.t_off)
+        pos = np.where(nxt < len(ws), ws[np.minimum(nxt, len(ws) - 1)], np.iinfo(np.int64).max)
+        return np.minimum(pos - self.t_off, self.t_len).astype(np.int64)
+
     def ids(self):
-        """First whitespace-delimited token of every title (Biopython's record.id)."""
-        out = []
-        b = self.buf
-        for o, l in zip(self.t_off.tolist(), self.t_len.tolist()):
-            t = b[o:o + l].tobytes()
-            sp = t.split(None, 1)
-            out.append(sp[0].decode("ascii", "replace") if sp else "")
-        return out
+        """First whitespace-delimited token of every title (Biopython's record.id); cached."""
+        if self._ids is None:
+            out = []
+            b = self.buf
+            for o, l in zip(self.t_off.tolist(), self.t_len.tolist()):
+                t = b[o:o + l].tobytes()
+                sp = t.split(None, 1)
+                out.append(sp[0].decode("ascii", "replace") if sp else "")
+            self._ids = out
+        return self._ids
 
     def seq(self, i):
         o = int(self.s_off[i])
@@ -60,7 +74,33 @@ class FastqBatch:
         return self.buf[o:o + int(self.s_len[i])].tobytes().decode("ascii")
 
 
+def _native():
+    from . import _lib
+    return _lib.lib()
+
+
+def _vp(a):
+    import ctypes
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
 def _gather(buf, off, length):
+    """Segments buf[off[i] : off[i] + length[i]] packed back to back (native, multi-threaded memcpy)."""
+    n = len(off)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    length = np.ascontiguousarray(length, dtype=np.int32)
+    buf = np.ascontiguousarray(buf)
+    out_off = np.zeros(n + 1, dtype=np.int64)
+    if n == 0:
+        return np.zeros(0, np.uint8), out_off
+    L = _native()
+    total = L.itsx_bytes_gather(_vp(buf), _vp(off), _vp(length), n, None, _vp(out_off))
+    out = np.empty(total, np.uint8)
+    L.itsx_bytes_gather(_vp(buf), _vp(off), _vp(length), n, _vp(out), _vp(out_off))
+    return out, out_off
+
+
+def _gather_numpy(buf, off, length):
     n = len(off)
     out_off = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(length, out=out_off[1:])
@@ -86,7 +126,27 @@ def _open_bytes(path):
 
 
 def parse_bytes(data):
-    """Parse a whole (decompressed) 4-line FASTQ byte string into a FastqBatch."""
+    """Parse a whole (decompressed) 4-line FASTQ byte string into a FastqBatch (native scanner,
+    csrc/fastq_host.cpp); ValueError on malformed input with Biopython's wording."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    z = np.zeros(0, np.int64)
+    if buf.size == 0:
+        return FastqBatch(buf, z, z, z, z, z)
+    L = _native()
+    n = L.itsx_fastq_index(_vp(buf), buf.size, 0, None, None, None, None, None)
+    if n < 0:
+        raise ValueError(L.itsx_host_last_error().decode())
+    t_off, s_off, q_off = (np.empty(n, np.int64) for _ in range(3))
+    t_len, s_len = (np.empty(n, np.int32) for _ in range(2))
+    if n:
+        rc = L.itsx_fastq_index(_vp(buf), buf.size, n, _vp(t_off), _vp(t_len), _vp(s_off), _vp(s_len), _vp(q_off))
+        if rc < 0:
+            raise ValueError(L.itsx_host_last_error().decode())
+    return FastqBatch(buf, t_off, t_len.astype(np.int64), s_off, s_len.astype(np.int64), q_off)
+
+
+def _parse_bytes_numpy(data):
+    """The same scanner in numpy (kept as an independent cross-check of the native one in the tests)."""
     buf = np.frombuffer(data, dtype=np.uint8)
     if buf.size == 0:
         z = np.zeros(0, np.int64)
@@ -134,7 +194,7 @@ def parse_bytes(data):
     # quality range check (ASCII 33..126)
     batch = FastqBatch(buf, t0 + 1, tl, s0, slen, q0)
     if len(t0):
-        q, _ = batch.qual_concat()
+        q, _ = _gather_numpy(buf, q0, slen)
         if q.size and (q.min() < 33 or q.max() > 126):
             raise ValueError("Invalid character in quality string")
     return batch
@@ -192,7 +252,31 @@ def _scatter(dst, dst_off, src, src_off, length):
 def format_gathered(batch, keep_idx, out_off, out_seq, out_qual, prefix=None, suffix=None):
     """FASTQ text from slices already gathered back to back on the device (itsx_trim_gather):
     record t = title of batch[keep_idx[t]], bases out_seq[out_off[t]:out_off[t+1]], same for qualities.
-    prefix / suffix: (bases, quals) byte strings stitched to every record (--trim-ccs, SeqSample.py:601-622)."""
+    prefix / suffix: (bases, quals) byte strings stitched to every record (--trim-ccs, SeqSample.py:601-622).
+    Native, multi-threaded (csrc/fastq_host.cpp)."""
+    n = len(keep_idx)
+    if n == 0:
+        return b""
+    ki = np.ascontiguousarray(keep_idx, dtype=np.int32)
+    oo = np.ascontiguousarray(out_off, dtype=np.int64)
+    os_ = np.ascontiguousarray(out_seq, dtype=np.uint8)
+    oq = np.ascontiguousarray(out_qual, dtype=np.uint8)
+    t_off = np.ascontiguousarray(batch.t_off, dtype=np.int64)
+    t_len = np.ascontiguousarray(batch.t_len, dtype=np.int32)
+    buf = np.ascontiguousarray(batch.buf)
+    pre_s, pre_q = prefix if prefix else (b"", b"")
+    suf_s, suf_q = suffix if suffix else (b"", b"")
+    L = _native()
+    args = [_vp(buf), _vp(t_off), _vp(t_len), _vp(ki), n, _vp(oo), _vp(os_), _vp(oq), pre_s, pre_q, len(pre_s),
+            suf_s, suf_q, len(suf_s)]
+    total = L.itsx_fastq_format(*args, None)
+    dst = np.empty(total, np.uint8)
+    L.itsx_fastq_format(*args, _vp(dst))
+    return dst.tobytes()
+
+
+def _format_gathered_numpy(batch, keep_idx, out_off, out_seq, out_qual, prefix=None, suffix=None):
+    """numpy version of format_gathered (cross-check in the tests)."""
     keep_idx = np.asarray(keep_idx, dtype=np.int64)
     n = len(keep_idx)
     if n == 0:

@@ -197,12 +197,34 @@ def _check_fastqs(fastq, fastq2=None):
 
 
 def _check_total_reads(file, file2=None):
+    """Log the number of reads (= every fourth line, main.py:417-438), counted on raw newline bytes."""
     for path in (file, file2):
         if not path:
             continue
-        with read_file(path) as handle:
-            reads = sum(1 for i, _ in enumerate(handle) if i % 4 == 0)
-        logging.info("Total number of reads in file {} is {}.".format(path, reads))
+        try:
+            if path.endswith(".gz"):
+                fh = gzip.open(path, "rb")
+            elif path.endswith(".zst"):
+                import io
+                from . import _zstd
+                with open(path, "rb") as f:
+                    fh = io.BytesIO(_zstd.decompress(f.read()))
+            else:
+                fh = open(path, "rb")
+        except FileNotFoundError as f:
+            logging.error("The input file {} could not be found.".format(path))
+            raise f
+        lines, last = 0, b"\n"
+        with fh:
+            while True:
+                chunk = fh.read(1 << 24)
+                if not chunk:
+                    break
+                lines += chunk.count(b"\n")
+                last = chunk[-1:]
+        if last != b"\n":
+            lines += 1
+        logging.info("Total number of reads in file {} is {}.".format(path, (lines + 3) // 4))
 
 
 def create_temp_directory(tempdir_arg=None):
@@ -263,6 +285,8 @@ def main(args=None):
         else:
             logging.info("Sequences are assumed to be single-end.")
             sobj = SeqSampleNotPaired(fastq=args.fastq, tempdir=session_tempdir)
+        if args.keeptemp:
+            sobj.materialize = True        # --keeptemp: leave complete uc.txt / rep.fa / domtbl.txt behind
         if args.trim_ccs:
             logging.info("Orients PacBio reads using Vsearch --orient against the universal reference database.")
             sobj.orient_reads(threads=str(args.threads))

@@ -204,3 +204,25 @@ def test_q2_trim_single(tmp_path):
     assert fq.read_fastq(os.path.join(str(r1), name)).n < 20
     with pytest.raises(KeyError):
         q2._taxa_prefix_to_taxa("Z")
+
+
+def test_pipeline_without_materialised_temp_files(tmp_path):
+    """Large-sample mode: uc.txt / rep.fa / domtbl.txt are placeholders and ItsPosition / Dedup run from the live
+    session's device arrays; the output must equal the fully materialised run."""
+    from itsxpress_b200 import SeqSample as S
+    from itsxpress_b200.main import create_runtime_hmm
+    outs = []
+    for mat in (True, False):
+        d = tmp_path / ("m%d" % mat)
+        d.mkdir()
+        s = S.SeqSampleNotPaired(SEQ, str(d))
+        s.materialize = mat
+        s.deduplicate(threads=1)
+        s._search(hmmfile=create_runtime_hmm("Metazoa", "ITS2", str(d)), threads=1)
+        its = S.ItsPosition(s.dom_file, "ITS2")
+        dd = S.Dedup(s.uc_file, s.rep_file, s.seq_file)
+        out = str(d / "o.fastq")
+        dd.create_trimmed_seqs(out, False, False, its, True, str(d))
+        outs.append(open(out, "rb").read())
+        assert (os.path.getsize(s.dom_file) > 10000) == mat
+    assert outs[0] == outs[1] and len(outs[0]) > 10000

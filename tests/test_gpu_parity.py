@@ -276,3 +276,42 @@ def test_trim_set_map_drops_unmapped_reads(gpu_ctx):
     assert (lo[0], hi[0], lo[2], hi[2]) == (2, 8, 0, 4)
     with pytest.raises(Exception):
         gpu_ctx.trim_bounds(3, mode=0)           # offsets are mandatory once the map is external
+
+
+def test_full_size_properties(gpu_ctx):
+    """BASELINE configs[1] at FULL size (1 M reads x 250 bp, 300 k uniques) through itsx_run: properties that do
+    not need the oracle -- the planted class structure is recovered exactly, representatives are first
+    occurrences and idempotent, abundances add up, every kept slice is a non-empty in-range slice, and a second
+    run over the representatives alone returns the same boundaries."""
+    import synth
+    seq, off, which, cfg = synth.make_config("c2", scale=1.0)
+    n = len(off) - 1
+    gpu_ctx.load_profiles([os.path.join(HMM_DIR, cfg["hmm_file"])], [cfg["left_prefix"], cfg["right_prefix"]])
+    gpu_ctx.set_sides_by_prefix(cfg["left_prefix"], cfg["right_prefix"])
+    out, st = gpu_ctx.run(seq, off)
+    rep, keep, lo, hi = out["rep"].copy(), out["keep"].copy(), out["lo"].copy(), out["hi"].copy()
+    assert st.n_reads == n == 1_000_000 and st.n_unique == 300_000
+    # derep == the generator's planted classes (no planted read is the reverse complement of another)
+    first_of_class = np.full(which.max() + 1, n, np.int64)
+    np.minimum.at(first_of_class, which, np.arange(n))
+    assert np.array_equal(rep, first_of_class[which])
+    assert np.all(rep <= np.arange(n)) and np.array_equal(rep[rep], rep)
+    first, ab = gpu_ctx.derep_clusters(st.n_unique)
+    assert int(ab.sum()) == n and np.all(np.diff(first) > 0)
+    # trim: members of a class share the decision and the bounds; slices are in range and non-empty
+    assert np.array_equal(keep, keep[rep]) and np.array_equal(lo, lo[rep]) and np.array_equal(hi, hi[rep])
+    k = keep == 1
+    assert st.n_kept == int(k.sum()) > 0.5 * n
+    lens = np.diff(off)
+    assert np.all(lo[k] >= 0) and np.all(hi[k] <= lens[k]) and np.all(lo[k] < hi[k])
+    # idempotence: searching only the representatives gives every class the same boundaries
+    idx = first.astype(np.int64)
+    sub_lens = lens[idx]
+    sub_off = np.zeros(len(idx) + 1, np.int64)
+    np.cumsum(sub_lens, out=sub_off[1:])
+    delta = np.repeat(off[idx] - sub_off[:-1], sub_lens)
+    sub = seq[delta + np.arange(int(sub_off[-1]), dtype=np.int64)]
+    out2, st2 = gpu_ctx.run(sub, sub_off)
+    assert st2.n_unique == len(idx)
+    assert np.array_equal(out2["keep"], keep[idx]) and np.array_equal(out2["lo"], lo[idx])
+    assert np.array_equal(out2["hi"], hi[idx])

@@ -330,3 +330,34 @@ def test_q2_directory_formats():
     assert f.loc["4774-1-MSITS3", "reverse"].endswith("4774-1-MSITS3_1_L001_R2_001.fastq.gz")
     assert q2._taxa_prefix_to_taxa("F") == "Fungi" and q2._taxa_prefix_to_taxa("ALL") == "All"
     assert q2._taxa_prefix_to_taxa("R") == "Rhizaria"          # upstream quirk: not the " Rhizaria" key
+
+
+def test_native_fastq_matches_numpy_reference():
+    """csrc/fastq_host.cpp (scanner, packer, formatter) against the independent numpy implementation."""
+    raw = gzip.open(SEQ, "rb").read()
+    for data in (raw, raw.replace(b"\n", b"\r\n"), raw + b"\n\n", raw[:-1],
+                 raw.replace(b"\n+\n", b"\n+M02696:28:000000000-ATWK5:1:1101:21090:1000 1:N:0:108\n", 1)):
+        a, b = fq.parse_bytes(data), fq._parse_bytes_numpy(data)
+        assert a.n == b.n == 227
+        for f in ("t_off", "t_len", "s_off", "s_len", "q_off"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    a = fq.parse_bytes(raw)
+    s1, o1 = fq._gather(a.buf, a.s_off, a.s_len)
+    s2, o2 = fq._gather_numpy(a.buf, a.s_off, a.s_len)
+    assert np.array_equal(s1, s2) and np.array_equal(o1, o2)
+    q1, _ = a.qual_concat()
+    ki = np.arange(0, a.n, 3)
+    oo = np.zeros(len(ki) + 1, np.int64)
+    oo[1:] = np.cumsum(a.s_len[ki])
+    seq_k, _ = fq._gather(a.buf, a.s_off[ki], a.s_len[ki])
+    qual_k, _ = fq._gather(a.buf, a.q_off[ki], a.s_len[ki])
+    for pre, suf in ((None, None), ((b"GAC", b"~~~"), (b"TT", b"~~"))):
+        assert fq.format_gathered(a, ki, oo, seq_k, qual_k, pre, suf) == \
+            fq._format_gathered_numpy(a, ki, oo, seq_k, qual_k, pre, suf)
+    for bad in (raw[:200], raw.replace(b"\n+\n", b"\n-\n", 1), b"@x\nACGT\n+\nII\n", b"@x\nAC\n+\nI\x01\n",
+                raw.replace(b"\n+\n", b"\n+other\n", 1)):
+        with pytest.raises(ValueError):
+            fq.parse_bytes(bad)
+        with pytest.raises(ValueError):
+            fq._parse_bytes_numpy(bad)
+    assert fq.parse_bytes(b"").n == 0
