@@ -43,6 +43,9 @@ constexpr int SPEC_C = 5;                  // parser specials kept per row
 constexpr int ENV_ROWF = MAXM + 1;             // floats per envelope row: M[1..45] (cols 0..44), Eraw (col 45)
 constexpr int ENV_ROWBYTES = ENV_ROWF * 32 * 4;    // one row of one warp: 5 888 B, contiguous
 constexpr double kLn2 = 0.69314718055994529;
+constexpr int ESTRIDE = 52;                // floats per residue row of the shared emission table (48 used)
+// e_k of residue row `er` (float4 view): one 128-bit shared load serves nodes 4q .. 4q+3
+#define EMIS(er, k) (((k) & 3) == 0 ? (er)[(k) >> 2].x : ((k) & 3) == 1 ? (er)[(k) >> 2].y : ((k) & 3) == 2 ? (er)[(k) >> 2].z : (er)[(k) >> 2].w)
 
 inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
 
@@ -358,8 +361,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 __global__ void __launch_bounds__(FB_THREADS, FB_CTAS_PER_SM)
 fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
 {
-    __shared__ float s_e[(MAXM + 1) * 16];
-    for (int t = threadIdx.x; t < (MAXM + 1) * 16; t += FB_THREADS) s_e[t] = a.etab[t];
+    __shared__ __align__(16) float s_e[16 * ESTRIDE];     // [residue code][node]: odds of the launch's profile
+    for (int t = threadIdx.x; t < 16 * ESTRIDE; t += FB_THREADS) {
+        const int x = t / ESTRIDE, k = t - x * ESTRIDE;
+        s_e[t] = k <= MAXM ? a.etab[k * 16 + x] : 0.f;
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warp_in_grid = (blockIdx.x * FB_THREADS + threadIdx.x) >> 5;
@@ -408,7 +414,7 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
                 wnxt = ((widx + 1) * 8 < L) ? w[widx + 1] : 0u;
             }
             if (i <= L) {
-                const float *er = s_e + ((wcur >> (((i - 1) & 7) * 4)) & 15u);
+                const float4 *er = (const float4 *)(s_e + ((wcur >> (((i - 1) & 7) * 4)) & 15u) * ESTRIDE);
                 // pass 1, descending k, in place: M and I of row i from row i-1 (no serial dependence, so the
                 // scheduler needs no far-ahead coefficient loads); pass 2, ascending: the D chain and the E sums.
                 // Same operations and summation order as the oracle's single ascending loop.
@@ -418,7 +424,7 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
                     sv = fmaf(Mx[k - 1], pc.fa[k][1], sv);
                     sv = fmaf(Ix[k - 1], pc.fa[k][2], sv);
                     sv = fmaf(Dx[k - 1], pc.fa[k][3], sv);
-                    sv = sv * er[k * 16];
+                    sv = sv * EMIS(er, k);
                     const float ic = fmaf(Ix[k], pc.fi[k][0], Mx[k] * pc.fi[k][1]);
                     Mx[k] = sv; Ix[k] = ic;
                 }
@@ -524,11 +530,11 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
                 SPEC(i, 3) = (fJ_p * bJ) * N_loop;
                 SPEC(i, 4) = (fC_p * bC) * N_loop;
                 if (i > 1) {
-                    const float *er = s_e + ((bcur >> (((i - 1) & 7) * 4)) & 15u);   // residue x_i
+                    const float4 *er = (const float4 *)(s_e + ((bcur >> (((i - 1) & 7) * 4)) & 15u) * ESTRIDE);   // x_i
                     bB = 0.f;
 #pragma unroll
                     for (int k = 1; k <= MAXM; k++) {
-                        Mx[k] = Mx[k] * er[k * 16];
+                        Mx[k] = Mx[k] * EMIS(er, k);
                         bB = fmaf(Mx[k], pc.bm[k], bB);
                     }
                     bC = bC * N_loop;
@@ -556,10 +562,10 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
                     }
                 } else {
                     // row 0: only B and N are live
-                    const float *er = s_e + (bcur & 15u);
+                    const float4 *er = (const float4 *)(s_e + (bcur & 15u) * ESTRIDE);
                     bB = 0.f;
 #pragma unroll
-                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * er[k * 16], pc.bm[k], bB);
+                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * EMIS(er, k), pc.bm[k], bB);
                     bN = fmaf(bB, N_move, bN * N_loop);
                 }
                 SPEC(i, 0) = (fB_p * bB) * fS_p;
@@ -680,8 +686,11 @@ struct EnvArgs {
 __global__ void __launch_bounds__(ENV_THREADS, ENV_CTAS_PER_SM)
 env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
 {
-    __shared__ float s_e[(MAXM + 1) * 16];
-    for (int t = threadIdx.x; t < (MAXM + 1) * 16; t += ENV_THREADS) s_e[t] = a.etab[t];
+    __shared__ __align__(16) float s_e[16 * ESTRIDE];     // [residue code][node]: odds of the launch's profile
+    for (int t = threadIdx.x; t < 16 * ESTRIDE; t += ENV_THREADS) {
+        const int x = t / ESTRIDE, k = t - x * ESTRIDE;
+        s_e[t] = k <= MAXM ? a.etab[k * 16 + x] : 0.f;
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
@@ -738,7 +747,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
         float xN = 1.f, xJ = 0.f, xC = 0.f, xE = 0.f, xB = N_move, totscale = 0.f;
         for (int i = 1; i <= Lw; i++) {
             if (i <= Ld) {
-                const float *er = s_e + residue_at(w, ienv - 1 + i - 1);
+                const float4 *er = (const float4 *)(s_e + residue_at(w, ienv - 1 + i - 1) * ESTRIDE);
                 // pass 1, descending k, in place: M and I of row i from row i-1 (no serial dependence, so the
                 // scheduler needs no far-ahead coefficient loads); pass 2, ascending: the D chain and the E sums.
                 // Same operations and summation order as the oracle's single ascending loop.
@@ -748,7 +757,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                     sv = fmaf(Mx[k - 1], pc.fa[k][1], sv);
                     sv = fmaf(Ix[k - 1], pc.fa[k][2], sv);
                     sv = fmaf(Dx[k - 1], pc.fa[k][3], sv);
-                    sv = sv * er[k * 16];
+                    sv = sv * EMIS(er, k);
                     const float ic = fmaf(Ix[k], pc.fi[k][0], Mx[k] * pc.fi[k][1]);
                     Mx[k] = sv; Ix[k] = ic;
                 }
@@ -831,11 +840,11 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                 if (i > 1) {
                     float fEp, fSp;
                     spec_decode(cEp, fEp, fSp);
-                    const float *er = s_e + residue_at(w, ienv - 1 + i - 1);
+                    const float4 *er = (const float4 *)(s_e + residue_at(w, ienv - 1 + i - 1) * ESTRIDE);
                     bB = 0.f;
 #pragma unroll
                     for (int k = 1; k <= MAXM; k++) {
-                        Mx[k] = Mx[k] * er[k * 16];
+                        Mx[k] = Mx[k] * EMIS(er, k);
                         bB = fmaf(Mx[k], pc.bm[k], bB);
                     }
                     bC = bC * N_loop;
@@ -861,10 +870,10 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                         for (int k = 1; k <= MAXM; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
                     }
                 } else {
-                    const float *er = s_e + residue_at(w, ienv - 1);
+                    const float4 *er = (const float4 *)(s_e + residue_at(w, ienv - 1) * ESTRIDE);
                     bB = 0.f;
 #pragma unroll
-                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * er[k * 16], pc.bm[k], bB);
+                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * EMIS(er, k), pc.bm[k], bB);
                     bN = fmaf(bB, N_move, bN * N_loop);
                 }
             }
@@ -878,7 +887,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
             for (int x = 0; x < 4; x++) {
                 float ws = 0.f;
 #pragma unroll
-                for (int k = 1; k <= MAXM; k++) ws = fmaf(nk[k], s_e[k * 16 + x] - 1.0f, ws);
+                for (int k = 1; k <= MAXM; k++) ws = fmaf(nk[k], s_e[x * ESTRIDE + k] - 1.0f, ws);
                 null2[x] = 1.0f + ws * scaleproduct * norm;
             }
             const int degen[16] = {1, 2, 4, 8, 5, 10, 3, 12, 6, 9, 11, 14, 7, 13, 15, 0};
