@@ -209,6 +209,7 @@ msv_kernel(const uint32_t *__restrict__ seqw, const int64_t *__restrict__ woff, 
                 float seq_score = (float)((double)(sc - nullsc) / kLn2);
                 pass = gumbel_surv((double)seq_score, (double)ps.ev[EV_MMU], (double)ps.ev[EV_MLAMBDA]) <= F1;
             }
+            if (L == 0) pass = false;       // hmmsearch skips zero-length targets (p7_Pipeline)
             const size_t o = (size_t)(p0 + pl) * ns + sl;
             res[o]  = ovf ? 255 : (uint8_t)resJ;
             flag[o] = pass ? 1 : 0;

@@ -719,6 +719,8 @@ int ora_pair_run(const ora_db *db, int p, const uint8_t *dsq, int L,
 {
     const prof_t *pf = &db->p[p];
     memset(pr, 0, sizeof(*pr));
+    /* p7_Pipeline returns at once for a zero-length target ("silently skip length 0 seqs") */
+    if (L <= 0) return 0;
     pr->nullsc = ora_nullsc(L);
     int xJ;
     pr->usc          = msv_filter(pf, dsq, L, &pr->msv_overflow, &xJ);

@@ -315,3 +315,34 @@ def test_full_size_properties(gpu_ctx):
     assert st2.n_unique == len(idx)
     assert np.array_equal(out2["keep"], keep[idx]) and np.array_equal(out2["lo"], lo[idx])
     assert np.array_equal(out2["hi"], hi[idx])
+
+
+def test_search_short_and_empty_sequences(gpu_ctx, oracle, fixture_reads):
+    """Ragged input: empty, 1-base, shorter-than-the-model and ordinary sequences in one search; and a search
+    over zero sequences."""
+    b, seq, off, _ = fixture_reads
+    parts = [np.zeros(0, np.uint8), seq[off[3]:off[3] + 1], seq[off[4]:off[4] + 7], seq[off[5]:off[5] + 44],
+             seq[off[6]:off[7]], np.zeros(0, np.uint8), seq[off[8]:off[8] + 130], seq[off[9]:off[10]]]
+    s2 = np.concatenate(parts)
+    o2 = np.zeros(len(parts) + 1, np.int64)
+    o2[1:] = np.cumsum([len(p) for p in parts])
+    rows, st, orows, onrep, ost, side, db = _search_both(gpu_ctx, oracle, ["M.hmm"], ["3_", "4_"], s2, o2, "3_", "4_")
+    assert len(orows) > 50
+    _compare_search(gpu_ctx, oracle, rows, st, orows, onrep, ost, side, np.diff(o2).astype(np.int32))
+    gpu_ctx.search_seqs(np.zeros(0, np.uint8), np.zeros(1, np.int64))
+    assert len(gpu_ctx.hits()) == 0
+
+
+def test_derep_then_trim_ragged(gpu_ctx, oracle):
+    """Empty reads and single-base reads go through derep and the whole path without special cases."""
+    reads = [b"", b"A", b"", b"ACGT" * 70, b"T", b"ACGT" * 70, b"a"]
+    off = np.zeros(len(reads) + 1, np.int64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    seq = np.frombuffer(b"".join(reads), np.uint8).copy()
+    rep, strand, nu = gpu_ctx.derep(seq, off)
+    orep, ostrand, onu = oracle.derep(seq, off)
+    assert nu == onu and np.array_equal(rep, orep) and np.array_equal(strand, ostrand)
+    gpu_ctx.load_profiles([os.path.join(HMM_DIR, "A.hmm")], ["3_", "4_"])
+    gpu_ctx.set_sides_by_prefix("3_", "4_")
+    out, st = gpu_ctx.run(seq, off)
+    assert st.n_unique == onu and st.n_kept == 0
