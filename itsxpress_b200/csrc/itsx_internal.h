@@ -46,14 +46,14 @@ uint8_t msv_unbiased_byteify(float scale_b, float sc);
 //            pass 2 (D chain):        fd[k] = {DD_{k-1}, MD_{k-1}}
 //   Backward pass 1 (B sum):          bm[k] = BM_k
 //            pass 2 (M, I, D):        ba[k] = {IM_k, II_k, MM_k, MI_k}               bd[k] = {DM_k, DD_k, MD_k, 0}
-struct ProfConst {
-    float tp[ITSX_MAXM + 2][8];
+struct alignas(16) ProfConst {
     float fa[ITSX_MAXM + 1][4];
     float fi[ITSX_MAXM + 1][2];
     float fd[ITSX_MAXM + 1][2];
     float ba[ITSX_MAXM + 1][4];
-    float bd[ITSX_MAXM + 1][4];
-    float bm[ITSX_MAXM + 3];
+    // node k lives at index k - 1 so that four consecutive nodes are one aligned 128-bit uniform load (LDCU.128)
+    float bd0[ITSX_MAXM + 3], bd1[ITSX_MAXM + 3], bd2[ITSX_MAXM + 3];   // D->M, D->D, M->D out of node k
+    float bm[ITSX_MAXM + 3];                                            // B->M_k entry
 };
 // per-profile scalars used by the filter kernels
 struct ProfScalars {

@@ -490,8 +490,8 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
             Dx[MAXM + 1] = 0.f;
 #pragma unroll
             for (int k = MAXM; k >= 1; k--) {
-                Dx[k] = fmaf(pc.bd[k][1], Dx[k + 1], bE);
-                Mx[k] = fmaf(pc.bd[k][2], Dx[k + 1], bE);
+                Dx[k] = fmaf(pc.bd1[k - 1], Dx[k + 1], bE);
+                Mx[k] = fmaf(pc.bd2[k - 1], Dx[k + 1], bE);
                 Ix[k] = 0.f;
             }
             spec_decode(SPEC(L, 0), fE_i, fS_i);
@@ -536,7 +536,7 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
 #pragma unroll
                     for (int k = 1; k <= MAXM; k++) {
                         Mx[k] = Mx[k] * EMIS(er, k);
-                        bB = fmaf(Mx[k], pc.bm[k], bB);
+                        bB = fmaf(Mx[k], pc.bm[k - 1], bB);
                     }
                     bC = bC * N_loop;
                     bJ = fmaf(bB, N_move, bJ * N_loop);
@@ -549,8 +549,8 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
                         const float mpe_k = Mx[k];
                         const float ic = fmaf(mnext, pc.ba[k][0], Ix[k] * pc.ba[k][1]);
                         // every M and D state also exits to E: bE is the addend the FMA chains start from
-                        const float dc = fmaf(mnext, pc.bd[k][0], fmaf(Dx[k + 1], pc.bd[k][1], bE));
-                        const float mc = fmaf(mnext, pc.ba[k][2], fmaf(Ix[k], pc.ba[k][3], fmaf(Dx[k + 1], pc.bd[k][2], bE)));
+                        const float dc = fmaf(mnext, pc.bd0[k - 1], fmaf(Dx[k + 1], pc.bd1[k - 1], bE));
+                        const float mc = fmaf(mnext, pc.ba[k][2], fmaf(Ix[k], pc.ba[k][3], fmaf(Dx[k + 1], pc.bd2[k - 1], bE)));
                         Mx[k] = mc; Ix[k] = ic; Dx[k] = dc;
                         mnext = mpe_k;
                     }
@@ -566,7 +566,7 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
                     const float4 *er = (const float4 *)(s_e + (bcur & 15u) * ESTRIDE);
                     bB = 0.f;
 #pragma unroll
-                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * EMIS(er, k), pc.bm[k], bB);
+                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * EMIS(er, k), pc.bm[k - 1], bB);
                     bN = fmaf(bB, N_move, bN * N_loop);
                 }
                 SPEC(i, 0) = (fB_p * bB) * fS_p;
@@ -799,8 +799,8 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
             Dx[MAXM + 1] = 0.f;
 #pragma unroll
             for (int k = MAXM; k >= 1; k--) {
-                Dx[k] = fmaf(pc.bd[k][1], Dx[k + 1], bE);
-                Mx[k] = fmaf(pc.bd[k][2], Dx[k + 1], bE);
+                Dx[k] = fmaf(pc.bd1[k - 1], Dx[k + 1], bE);
+                Mx[k] = fmaf(pc.bd2[k - 1], Dx[k + 1], bE);
                 Ix[k] = 0.f;
             }
             float fE, fS;
@@ -846,7 +846,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
 #pragma unroll
                     for (int k = 1; k <= MAXM; k++) {
                         Mx[k] = Mx[k] * EMIS(er, k);
-                        bB = fmaf(Mx[k], pc.bm[k], bB);
+                        bB = fmaf(Mx[k], pc.bm[k - 1], bB);
                     }
                     bC = bC * N_loop;
                     bJ = fmaf(bB, N_move, bJ * N_loop);
@@ -859,8 +859,8 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                         const float mpe_k = Mx[k];
                         const float ic = fmaf(mnext, pc.ba[k][0], Ix[k] * pc.ba[k][1]);
                         // every M and D state also exits to E: bE is the addend the FMA chains start from
-                        const float dc = fmaf(mnext, pc.bd[k][0], fmaf(Dx[k + 1], pc.bd[k][1], bE));
-                        const float mc = fmaf(mnext, pc.ba[k][2], fmaf(Ix[k], pc.ba[k][3], fmaf(Dx[k + 1], pc.bd[k][2], bE)));
+                        const float dc = fmaf(mnext, pc.bd0[k - 1], fmaf(Dx[k + 1], pc.bd1[k - 1], bE));
+                        const float mc = fmaf(mnext, pc.ba[k][2], fmaf(Ix[k], pc.ba[k][3], fmaf(Dx[k + 1], pc.bd2[k - 1], bE)));
                         Mx[k] = mc; Ix[k] = ic; Dx[k] = dc;
                         mnext = mpe_k;
                     }
@@ -874,7 +874,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                     const float4 *er = (const float4 *)(s_e + residue_at(w, ienv - 1) * ESTRIDE);
                     bB = 0.f;
 #pragma unroll
-                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * EMIS(er, k), pc.bm[k], bB);
+                    for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * EMIS(er, k), pc.bm[k - 1], bB);
                     bN = fmaf(bB, N_move, bN * N_loop);
                 }
             }
@@ -1118,18 +1118,20 @@ int search_upload_profiles(itsx_ctx *c)
             for (int x = 0; x < 16; x++) etab[((size_t)p * (MAXM + 1) + k) * 16 + x] = h.e[k * 16 + x];
         ProfConst &pc = c->pconst[p];
         memset(&pc, 0, sizeof(pc));
+        float tp[MAXM + 2][8];      // transitions out of node k (zero beyond the model), B->M_k entry in slot T_BM
+        memset(tp, 0, sizeof(tp));
         for (int k = 0; k <= h.M; k++) {
-            for (int s = 0; s < 7; s++) pc.tp[k][s] = h.tp[k * 7 + s];
-            pc.tp[k][T_BM] = h.bm[k];
+            for (int s = 0; s < 7; s++) tp[k][s] = h.tp[k * 7 + s];
+            tp[k][T_BM] = h.bm[k];
         }
         for (int k = 1; k <= MAXM; k++) {
-            pc.fa[k][0] = pc.tp[k][T_BM];
-            pc.fa[k][1] = pc.tp[k - 1][T_MM]; pc.fa[k][2] = pc.tp[k - 1][T_IM]; pc.fa[k][3] = pc.tp[k - 1][T_DM];
-            pc.fi[k][0] = pc.tp[k][T_II];     pc.fi[k][1] = pc.tp[k][T_MI];
-            pc.fd[k][0] = pc.tp[k - 1][T_DD]; pc.fd[k][1] = pc.tp[k - 1][T_MD];
-            pc.ba[k][0] = pc.tp[k][T_IM]; pc.ba[k][1] = pc.tp[k][T_II]; pc.ba[k][2] = pc.tp[k][T_MM]; pc.ba[k][3] = pc.tp[k][T_MI];
-            pc.bd[k][0] = pc.tp[k][T_DM]; pc.bd[k][1] = pc.tp[k][T_DD]; pc.bd[k][2] = pc.tp[k][T_MD]; pc.bd[k][3] = 0.f;
-            pc.bm[k] = pc.tp[k][T_BM];
+            pc.fa[k][0] = tp[k][T_BM];
+            pc.fa[k][1] = tp[k - 1][T_MM]; pc.fa[k][2] = tp[k - 1][T_IM]; pc.fa[k][3] = tp[k - 1][T_DM];
+            pc.fi[k][0] = tp[k][T_II];     pc.fi[k][1] = tp[k][T_MI];
+            pc.fd[k][0] = tp[k - 1][T_DD]; pc.fd[k][1] = tp[k - 1][T_MD];
+            pc.ba[k][0] = tp[k][T_IM]; pc.ba[k][1] = tp[k][T_II]; pc.ba[k][2] = tp[k][T_MM]; pc.ba[k][3] = tp[k][T_MI];
+            pc.bd0[k - 1] = tp[k][T_DM]; pc.bd1[k - 1] = tp[k][T_DD]; pc.bd2[k - 1] = tp[k][T_MD];
+            pc.bm[k - 1] = tp[k][T_BM];
         }
         ProfScalars &q = ps[p];
         memset(&q, 0, sizeof(q));
