@@ -52,6 +52,10 @@ typedef struct {
     double F2;       /* --F2 1e-6    Viterbi filter (never runs when F1 == F2)      */
     double F3;       /* --F3 1e-6    Forward filter P-value                         */
     double domE;     /* 10.0         per-domain conditional E-value (hmmsearch default) */
+    int32_t resolve_multidomain; /* 1 (default): regions flagged multidomain are resolved like p7_domaindef does
+                                  * (200 stochastic tracebacks, RNG seed 42, single-linkage clustering);
+                                  * 0: such a region is rescored as one envelope */
+    int32_t reserved;
 } itsx_search_params;
 
 /* one domtbl-equivalent row (only the fields ItsPosition reads, plus diagnostics) */
@@ -67,7 +71,7 @@ typedef struct {
     float   seq_score;     /* per-sequence bit score of the hit */
     double  lnP;           /* ln P-value of the domain score */
     double  seq_lnP;       /* ln P-value of the hit (row order key within a profile) */
-    int32_t is_multidomain;/* region was flagged multidomain (kept as one envelope) */
+    int32_t is_multidomain;/* envelope comes from a region flagged multidomain */
     int32_t reported;      /* passes -T and domE (rows returned by itsx_hits always have 1) */
 } itsx_dom_row;
 
@@ -78,7 +82,7 @@ typedef struct {
     int64_t n_domains, n_domains_reported, n_multidomain_regions, n_dom_overflow;
     double  msv_cells, bias_rows, fwd_cells, bck_cells, env_cells;   /* DP cells actually computed */
     /* device time per stage, milliseconds, CUDA events on the library's stream */
-    float   ms_msv, ms_bias, ms_fwd, ms_bck, ms_env, ms_final, ms_total;
+    float   ms_msv, ms_bias, ms_fwd, ms_mdom, ms_env, ms_final, ms_total;   /* ms_mdom: multidomain regions */
 } itsx_search_stats;
 
 typedef struct {

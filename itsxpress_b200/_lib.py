@@ -23,7 +23,8 @@ class ItsxError(RuntimeError):
 
 
 class SearchParams(C.Structure):
-    _fields_ = [("T", C.c_float), ("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double), ("domE", C.c_double)]
+    _fields_ = [("T", C.c_float), ("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double), ("domE", C.c_double),
+                ("resolve_multidomain", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SearchStats(C.Structure):
@@ -31,7 +32,7 @@ class SearchStats(C.Structure):
                                           "n_hits_reported", "n_domains", "n_domains_reported",
                                           "n_multidomain_regions", "n_dom_overflow")] + \
                [(n, C.c_double) for n in ("msv_cells", "bias_rows", "fwd_cells", "bck_cells", "env_cells")] + \
-               [(n, C.c_float) for n in ("ms_msv", "ms_bias", "ms_fwd", "ms_bck", "ms_env", "ms_final", "ms_total")]
+               [(n, C.c_float) for n in ("ms_msv", "ms_bias", "ms_fwd", "ms_mdom", "ms_env", "ms_final", "ms_total")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

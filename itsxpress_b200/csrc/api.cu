@@ -278,6 +278,8 @@ void itsx_search_default_params(itsx_search_params *prm)
     prm->T = 10.0f;
     prm->F1 = prm->F2 = prm->F3 = 1e-6;
     prm->domE = 10.0;
+    prm->resolve_multidomain = 1;
+    prm->reserved = 0;
 }
 static int set_params(itsx_ctx *c, const itsx_search_params *prm)
 {

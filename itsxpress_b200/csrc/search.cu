@@ -632,6 +632,507 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// K9b: multidomain regions (p7_domaindef.c: region_trace_ensemble + p7_spensemble_Cluster), operation
+// for operation the same as oracle/ora_hmm.c:resolve_multidomain.  About 1 % of the regions: one THREAD per
+// worklist entry that has a flagged region, plain loops, all per-thread state in a global scratch block:
+//   multihit Forward over the region with the full M/I/D matrix -> 200 stochastic tracebacks with HMMER's "fast" RNG
+//   re-seeded per region (x0 = mix3(42), x <- 69069 x + 1) -> null2 by trace averaged per position -> single-linkage
+//   clustering of the sampled segments -> cluster envelopes (start order) replace the region in the entry's list.
+// The cluster envelopes carry bit 29 ("null2 done"): env_kernel still gives their unihit Forward score, final_kernel
+// takes their domcorrection from envdc[] and the region-wide sum of the trace n2sc from n2reg[].
+constexpr int MD_NSAMPLES = 200;
+constexpr int MD_MAXSEG = 1024;
+constexpr int MD_MAXCL = 16;
+constexpr int MD_W = MAXM + 1;
+struct MdArgs {
+    const int32_t *mdlist;    // entries with at least one flagged region
+    const int32_t *count_ptr;
+    const int32_t *list;
+    const int32_t *order;
+    int64_t        s0;
+    int            ns;
+    const uint32_t *seqw;
+    const int64_t  *woff;
+    const int32_t  *seqlen;
+    const float    *mdtab;    // [P][MAXM + 2][8]: transitions out of node k, B->M_k in slot 7
+    const float    *etab;     // [P][MAXM + 1][16]
+    const ProfScalars *pscal;
+    uint8_t        *ndom;
+    int32_t        *env;
+    float          *envdc;    // [entry][MAXDOM]
+    float          *n2reg;    // [entry]
+    char           *scratch;
+    size_t          per_thread;
+    int             rows;     // longest flagged region + 1
+    float           e_move;
+    uint32_t        rng0;
+    unsigned long long *counters;
+};
+struct MdSeg { uint16_t i, j; uint8_t k, m; uint16_t n; };     // distinct segment and how many traces sampled it
+struct MdRow { float pC0, pC1, pJ0, pJ1, pB0, pB1, nrmE, xB; };   // per row: normalised C / J / B choices, 1 / xE, xB
+__host__ __device__ inline size_t md_scratch_bytes(int rows)
+{
+    // cells (M, I, D, pad) + row records + acc + distinct segments + raw (segment id, trace) + assignment, stack,
+    // last trace and trace count per cluster
+    size_t b = (size_t)rows * MD_W * 16 + (size_t)rows * sizeof(MdRow) + (size_t)(rows + 1) * 4 +
+               (size_t)MD_MAXSEG * (8 + 4 + 2 + 2 + 2 + 2);
+    return (b + 255) / 256 * 256;
+}
+__device__ __forceinline__ double md_rng(uint32_t &x)
+{
+    x = x * 69069u + 1u;
+    return (double)x / 4294967296.0;
+}
+// esl_vec_FNorm
+__device__ __forceinline__ void md_norm(float *p, int n)
+{
+    float sum = 0.f;
+    for (int a = 0; a < n; a++) sum += p[a];
+    if (sum != 0.f) { const float inv = 1.0f / sum; for (int a = 0; a < n; a++) p[a] = p[a] * inv; }   // esl_vec_FScale(1/sum)
+    else { for (int a = 0; a < n; a++) p[a] = 1.0f / (float)n; }
+}
+// esl_rnd_FChoose on a normalised vector
+__device__ __forceinline__ int md_pick(uint32_t &rng, const float *p, int n)
+{
+    for (;;) {
+        const double roll = md_rng(rng);
+        float c = 0.f;
+        for (int a = 0; a < n; a++) { c += p[a]; if (roll < (double)c) return a; }
+    }
+}
+__device__ __forceinline__ int md_pick2(uint32_t &rng, float p0, float p1)
+{
+    for (;;) {
+        const double roll = md_rng(rng);
+        float c = 0.f;
+        c += p0; if (roll < (double)c) return 0;
+        c += p1; if (roll < (double)c) return 1;
+    }
+}
+__device__ __forceinline__ bool md_link(const MdSeg &a, const MdSeg &b)
+{
+    int nov = min((int)a.j, (int)b.j) - max((int)a.i, (int)b.i) + 1;
+    int n = min(a.j - a.i + 1, b.j - b.i + 1);
+    if ((float)nov / (float)n < 0.8f) return false;
+    nov = min((int)a.m, (int)b.m) - max((int)a.k, (int)b.k) + 1;
+    n = min(a.m - a.k + 1, b.m - b.k + 1);
+    if ((float)nov / (float)n < 0.8f) return false;
+    if (abs(((int)a.i - (int)a.k) - ((int)b.i - (int)b.k)) > 4) return false;
+    if (abs(((int)a.j - (int)a.m) - ((int)b.j - (int)b.m)) > 4) return false;
+    return true;
+}
+enum { MS_M = 0, MS_D, MS_I, MS_N, MS_C, MS_J, MS_E, MS_B, MS_S };
+
+// resolves region ireg..jreg of a target of length L; returns the number of cluster envelopes (ci/cj/cdc) and the
+// sum of the trace n2sc over the region
+// Warp-synchronous: all 32 lanes call it together (act = this lane has a region); every phase of the walk is a loop
+// whose condition is a warp vote, so the lanes stay converged phase by phase.
+__device__ int md_resolve(const MdArgs &a, char *scr, bool act, const uint32_t *w, int L, int M, const float *tp,
+                          const float *et, int ireg, int jreg, int *ci, int *cj, float *cdc, float &regsum)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int Ld = act ? jreg - ireg + 1 : 0;
+    const int R = a.rows;
+    float4 *cell = (float4 *)scr;                    // [row][MD_W]: (M, I, D, -)
+    MdRow *rowrec = (MdRow *)(cell + (size_t)R * MD_W);
+    float *acc = (float *)(rowrec + R);              // [rows + 1]
+    MdSeg *seg = (MdSeg *)(acc + (R + 1));            // distinct segments
+    uint16_t *rawid = (uint16_t *)(seg + MD_MAXSEG), *rawtr = rawid + MD_MAXSEG;
+    int16_t *asg = (int16_t *)(rawtr + MD_MAXSEG), *stack = asg + MD_MAXSEG, *lasttr = stack + MD_MAXSEG,
+            *ntrc = lasttr + MD_MAXSEG;
+#define CELL(i, k) cell[(size_t)(i) * MD_W + (k)]
+    // ---- multihit Forward, full matrix (oracle forward_engine), and the per-row choice tables ----
+    const float pmove = (2.0f + 1.0f) / ((float)L + 2.0f + 1.0f);
+    const float N_move = pmove, N_loop = 1.0f - pmove, E_move = a.e_move, E_loop = a.e_move;
+    for (int k = 0; k <= M; k++) CELL(0, k) = make_float4(0.f, 0.f, 0.f, 0.f);
+    float xN = 1.f, xJ = 0.f, xC = 0.f, xE = 0.f, xB = N_move;
+    {
+        MdRow r0;
+        float pb[2] = {xN * N_move, xJ * N_move};
+        md_norm(pb, 2);
+        r0.pC0 = r0.pC1 = r0.pJ0 = r0.pJ1 = 0.f; r0.pB0 = pb[0]; r0.pB1 = pb[1]; r0.nrmE = 0.f; r0.xB = xB;
+        rowrec[0] = r0;
+    }
+    int Ldw = Ld;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) Ldw = max(Ldw, __shfl_xor_sync(FULL, Ldw, o));
+    for (int i = 1; i <= Ldw; i++) {
+        if (i > Ld) continue;
+        const uint32_t x = residue_at(w, ireg - 1 + i - 1);
+        const float cprev = xC, jprev = xJ;          // stored (scaled) specials of row i-1
+        float mcur = 0.f, dcur = 0.f, xEm = 0.f, xEd = 0.f;
+        CELL(i, 0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pk1 = CELL(i - 1, 0);                 // row i-1, node k-1
+        for (int k = 1; k <= M; k++) {
+            const float4 pk = CELL(i - 1, k);
+            const float4 t1a = __ldg((const float4 *)(tp + (k - 1) * 8)), t1b = __ldg((const float4 *)(tp + (k - 1) * 8 + 4));
+            const float4 ta = __ldg((const float4 *)(tp + k * 8)), tb = __ldg((const float4 *)(tp + k * 8 + 4));
+            // slots: a = (MM, MI, MD, IM), b = (II, DM, DD, BM)
+            float sv = xB * tb.w;
+            sv = fmaf(pk1.x, t1a.x, sv);
+            sv = fmaf(pk1.y, t1a.w, sv);
+            sv = fmaf(pk1.z, t1b.y, sv);
+            sv = sv * __ldg(et + k * 16 + x);
+            const float dc = fmaf(dcur, t1b.z, mcur * t1a.z);
+            const float ic = fmaf(pk.y, tb.x, pk.x * ta.y);
+            CELL(i, k) = make_float4(sv, ic, dc, 0.f);
+            xEm += sv; xEd += dc;
+            mcur = sv; dcur = dc;
+            pk1 = pk;
+        }
+        xE = xEm + xEd;
+        xN = xN * N_loop;
+        xC = fmaf(xC, N_loop, xE * E_move);
+        xJ = fmaf(xJ, N_loop, xE * E_loop);
+        xB = fmaf(xJ, N_move, xN * N_move);
+        float sc = 1.0f;
+        if (xE > 1.0e4f) {
+            xN = xN / xE; xC = xC / xE; xJ = xJ / xE; xB = xB / xE;
+            const float inv = 1.0f / xE;
+            for (int k = 1; k <= M; k++) {
+                float4 v = CELL(i, k);
+                v.x *= inv; v.z *= inv; v.y *= inv;
+                CELL(i, k) = v;
+            }
+            sc = xE;
+            xE = 1.0f;
+        }
+        MdRow rr;
+        float pc[2] = {cprev * N_loop, xE * E_move * sc};
+        md_norm(pc, 2);
+        float pj[2] = {jprev * N_loop, xE * E_loop * sc};
+        md_norm(pj, 2);
+        float pb[2] = {xN * N_move, xJ * N_move};
+        md_norm(pb, 2);
+        rr.pC0 = pc[0]; rr.pC1 = pc[1]; rr.pJ0 = pj[0]; rr.pJ1 = pj[1]; rr.pB0 = pb[0]; rr.pB1 = pb[1];
+        rr.nrmE = (float)(1.0 / (double)xE);
+        rr.xB = xB;
+        rowrec[i] = rr;
+    }
+    const int Q = max(((M - 1) / 4) + 1, 2);
+    for (int pos = 0; pos <= Ld; pos++) acc[pos] = 0.f;
+    int nseg = 0, nraw = 0;
+    uint32_t rng = a.rng0;
+    const int degen[16] = {1, 2, 4, 8, 5, 10, 3, 12, 6, 9, 11, 14, 7, 13, 15, 0};
+
+    // A trace is  C..C E [domain] B ( N.. | J..J E [domain] B ... ).  The walk is written as nested loops (special-state
+    // walk, E choice, domain walk, B choice) so that the lanes of a warp -- each on its own region -- reconverge after
+    // every phase; the domain step is one predicated code path for M, D and I.  The N walk draws no random numbers and
+    // is skipped.
+    for (int t = 0; t < MD_NSAMPLES; t++) {
+        int dfrom[8], dto[8], dk[8], dm[8], nd = 0;
+        float dn[8][4];
+        int i = Ld, k = 0;
+        bool inJ = false, alive = act;
+        while (__any_sync(FULL, alive)) {
+            // ---- C (or J) walk: stay with p0 (i--), leave to E with p1 ----
+            bool walking = alive;
+            while (__any_sync(FULL, walking)) {
+                if (walking) {
+                    const MdRow &rr = rowrec[i];
+                    if (md_pick2(rng, inJ ? rr.pJ0 : rr.pC0, inJ ? rr.pJ1 : rr.pC1) != 0 || i <= 1) walking = false;
+                    else i--;       // (i <= 1 is unreachable: C(0) = J(0) = 0)
+                }
+            }
+            // ---- E at row i: M_k / D_k in striped order, scaled by 1 / xE(i) ----
+            int st = MS_B;
+            if (alive) {
+                const double roll = md_rng(rng);
+                const float nrm = rowrec[i].nrmE;
+                double sum = 0.0;
+                bool done = false;
+                st = MS_M;
+                while (!done) {
+                    for (int q = 0; q < Q && !done; q++) {
+                        float4 cc[4];
+                        for (int r = 0; r < 4; r++) {
+                            const int kk = r * Q + q + 1;
+                            cc[r] = kk <= M ? CELL(i, kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        for (int r = 0; r < 4 && !done; r++) {
+                            sum += (double)(cc[r].x * nrm);
+                            if (roll < sum) { k = r * Q + q + 1; st = MS_M; done = true; }
+                        }
+                        for (int r = 0; r < 4 && !done; r++) {
+                            sum += (double)(cc[r].z * nrm);
+                            if (roll < sum) { k = r * Q + q + 1; st = MS_D; done = true; }
+                        }
+                    }
+                    if (!done && sum < 0.99) { k = 1; st = MS_M; done = true; }
+                }
+            }
+            __syncwarp();
+            // ---- domain walk back to B; null2 odds are summed in walk order ----
+            int d_to = 0, d_m = 0, d_from = 0, d_k = 0, nI = 0;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            while (__any_sync(FULL, st != MS_B)) {
+                if (st == MS_B) continue;
+                if (st == MS_M) {
+                    if (d_to == 0) { d_to = i; d_m = k; }
+                    d_from = i; d_k = k;
+                    const float4 e4 = __ldg((const float4 *)(et + k * 16));
+                    s0 += e4.x; s1 += e4.y; s2 += e4.z; s3 += e4.w;
+                } else if (st == MS_I) {
+                    nI++;
+                }
+                // predecessor of state st at (i, k): one cell, the transitions out of its node
+                const int ri = st == MS_D ? i : i - 1, kc = st == MS_I ? k : k - 1;
+                const float4 c1 = CELL(ri, kc);
+                const float4 ta = __ldg((const float4 *)(tp + kc * 8)), tb = __ldg((const float4 *)(tp + kc * 8 + 4));
+                float path[4];
+                int n;
+                if (st == MS_M) {
+                    path[0] = rowrec[i - 1].xB * __ldg(tp + k * 8 + 7);
+                    path[1] = c1.x * ta.x; path[2] = c1.y * ta.w; path[3] = c1.z * tb.y;
+                    n = 4;
+                } else if (st == MS_D) {
+                    path[0] = c1.x * ta.z; path[1] = c1.z * tb.z; path[2] = 0.f; path[3] = 0.f;
+                    n = 2;
+                } else {
+                    path[0] = c1.x * ta.y; path[1] = c1.y * tb.x; path[2] = 0.f; path[3] = 0.f;
+                    n = 2;
+                }
+                // esl_vec_FNorm over the n live paths (the padded zeros leave the float sums unchanged)
+                float sum = 0.f;
+                sum += path[0]; sum += path[1]; sum += path[2]; sum += path[3];
+                if (sum != 0.f) {
+                    const float inv = 1.0f / sum;
+                    path[0] = path[0] * inv; path[1] = path[1] * inv; path[2] = path[2] * inv; path[3] = path[3] * inv;
+                } else {
+                    const float u = 1.0f / (float)n;
+                    path[0] = u; path[1] = u;
+                    if (n == 4) { path[2] = u; path[3] = u; }
+                }
+                int c;
+                for (;;) {
+                    const double roll = md_rng(rng);
+                    float cs = 0.f;
+                    cs += path[0]; if (roll < (double)cs) { c = 0; break; }
+                    cs += path[1]; if (roll < (double)cs) { c = 1; break; }
+                    if (n == 4) {
+                        cs += path[2]; if (roll < (double)cs) { c = 2; break; }
+                        cs += path[3]; if (roll < (double)cs) { c = 3; break; }
+                    }
+                }
+                if (st == MS_M) { st = c == 0 ? MS_B : c == 1 ? MS_M : c == 2 ? MS_I : MS_D; k--; i--; }
+                else if (st == MS_D) { st = c == 0 ? MS_M : MS_D; k--; }
+                else { st = c == 0 ? MS_M : MS_I; i--; }
+            }
+            if (alive) {
+                if (nd < 8) {
+                    const float norm = 1.0f / (float)(d_to - d_from + 1), fi = (float)nI;
+                    dfrom[nd] = d_from; dto[nd] = d_to; dk[nd] = d_k; dm[nd] = d_m;
+                    dn[nd][0] = (s0 + fi) * norm; dn[nd][1] = (s1 + fi) * norm;
+                    dn[nd][2] = (s2 + fi) * norm; dn[nd][3] = (s3 + fi) * norm;
+                    nd++;
+                }
+                // ---- B at row i: N ends the trace, J goes on ----
+                const MdRow &rr = rowrec[i];
+                if (md_pick2(rng, rr.pB0, rr.pB1) == 0) alive = false;
+                inJ = true;
+            }
+        }
+        int pos = 1;
+        for (int d = nd - 1; d >= 0; d--) {
+            if (nraw < MD_MAXSEG) {
+                const uint16_t si = (uint16_t)(dfrom[d] + ireg - 1), sj = (uint16_t)(dto[d] + ireg - 1);
+                int u = 0;
+                for (; u < nseg; u++) {
+                    const MdSeg g = seg[u];
+                    if (g.i == si && g.j == sj && g.k == dk[d] && g.m == dm[d]) break;
+                }
+                if (u == nseg) {
+                    MdSeg sg;
+                    sg.i = si; sg.j = sj; sg.k = (uint8_t)dk[d]; sg.m = (uint8_t)dm[d]; sg.n = 0;
+                    seg[nseg++] = sg;
+                }
+                seg[u].n++;
+                rawid[nraw] = (uint16_t)u; rawtr[nraw] = (uint16_t)t;
+                nraw++;
+            }
+            for (; pos <= dfrom[d]; pos++) acc[pos] += 1.0f;
+            for (; pos <= dto[d]; pos++) {
+                const uint32_t x = residue_at(w, ireg - 1 + pos - 1);
+                float v;
+                if (x < 4) v = x == 0 ? dn[d][0] : x == 1 ? dn[d][1] : x == 2 ? dn[d][2] : dn[d][3];
+                else if (x == 15) v = 1.0f;
+                else {
+                    float sa = 0.f;
+                    int na = 0;
+                    for (int y = 0; y < 4; y++)
+                        if (degen[x] & (1 << y)) { sa += dn[d][y]; na++; }
+                    v = sa / (float)na;
+                }
+                acc[pos] += v;
+            }
+        }
+        for (; pos <= Ld; pos++) acc[pos] += 1.0f;
+    }
+    // n2sc of the region (kept in acc[])
+    regsum = 0.f;
+    for (int pos = 1; pos <= Ld; pos++) {
+        const float v = logf_via_double(acc[pos] / (float)MD_NSAMPLES);
+        acc[pos] = v;
+        regsum += v;
+    }
+    // ---- single linkage clustering over the DISTINCT segments (same components as over all samples) ----
+    for (int s = 0; s < nseg; s++) asg[s] = -1;
+    int nc = 0;
+    for (int s = 0; s < nseg; s++) {
+        if (asg[s] >= 0) continue;
+        int top = 0;
+        stack[top++] = (int16_t)s; asg[s] = (int16_t)nc;
+        while (top) {
+            const MdSeg v = seg[stack[--top]];
+            for (int b = 0; b < nseg; b++)
+                if (asg[b] < 0 && md_link(v, seg[b])) { asg[b] = (int16_t)nc; stack[top++] = (int16_t)b; }
+        }
+        nc++;
+    }
+    // traces that contribute to each cluster (samples were appended in trace order)
+    for (int c = 0; c < nc; c++) { lasttr[c] = -1; ntrc[c] = 0; }
+    for (int r = 0; r < nraw; r++) {
+        const int c = asg[rawid[r]];
+        if (lasttr[c] != (int16_t)rawtr[r]) { ntrc[c]++; lasttr[c] = (int16_t)rawtr[r]; }
+    }
+    int nenv = 0;
+    for (int c = 0; c < nc; c++) {
+        if ((float)ntrc[c] / (float)MD_NSAMPLES < 0.25f) continue;
+        int ninc = 0;
+        int imin = 1 << 30, imax = 0, jmin = 1 << 30, jmax = 0;
+        for (int s = 0; s < nseg; s++) {
+            if (asg[s] != c) continue;
+            const MdSeg g = seg[s];
+            ninc += g.n;
+            imin = min(imin, (int)g.i); imax = max(imax, (int)g.i);
+            jmin = min(jmin, (int)g.j); jmax = max(jmax, (int)g.j);
+        }
+        const int thr = (int)ceilf((float)ninc * 0.02f);
+        int best_i, best_j;
+        for (best_i = imin; best_i <= imax; best_i++) {
+            int cnt = 0;
+            for (int s = 0; s < nseg; s++) cnt += (asg[s] == c && (int)seg[s].i == best_i) ? (int)seg[s].n : 0;
+            if (cnt >= thr) break;
+        }
+        for (best_j = jmax; best_j >= jmin; best_j--) {
+            int cnt = 0;
+            for (int s = 0; s < nseg; s++) cnt += (asg[s] == c && (int)seg[s].j == best_j) ? (int)seg[s].n : 0;
+            if (cnt >= thr) break;
+        }
+        if (nenv < MD_MAXCL) {
+            int at = nenv;
+            while (at > 0 && (ci[at - 1] > best_i || (ci[at - 1] == best_i && cj[at - 1] > best_j))) {
+                ci[at] = ci[at - 1]; cj[at] = cj[at - 1]; at--;
+            }
+            ci[at] = best_i; cj[at] = best_j;
+            nenv++;
+        }
+    }
+    for (int c = 0; c < nenv; c++) {
+        float dc = 0.f;
+        for (int pos = ci[c]; pos <= cj[c]; pos++) dc += acc[pos - ireg + 1];
+        cdc[c] = dc;
+    }
+#undef CELL
+    return nenv;
+}
+
+__global__ void __launch_bounds__(64) mdom_kernel(const MdArgs a)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    char *scr = a.scratch + (size_t)tid * a.per_thread;
+    const int count = *a.count_ptr;
+    for (int t0 = tid - (threadIdx.x & 31); t0 < count; t0 += nthreads) {      // warp-uniform trip count
+        const int t = t0 + (threadIdx.x & 31);
+        const bool valid = t < count;
+        int e = 0, L = 0, M = 1, nd = 0;
+        const uint32_t *w = a.seqw;
+        const float *tp = a.mdtab, *et = a.etab;
+        int oi[ITSX_MAXDOM], oj[ITSX_MAXDOM];
+        if (valid) {
+            e = a.mdlist[t];
+            const int idx = a.list[e];
+            const int p = idx / a.ns, sl = idx - p * a.ns;
+            const int64_t s = a.order[a.s0 + sl];
+            L = a.seqlen[s];
+            w = a.seqw + a.woff[s];
+            M = a.pscal[p].M;
+            tp = a.mdtab + (size_t)p * (MAXM + 2) * 8;
+            et = a.etab + (size_t)p * (MAXM + 1) * 16;
+            nd = a.ndom[e];
+            for (int d = 0; d < nd; d++) {
+                oi[d] = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
+                oj[d] = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1];
+            }
+        }
+        int nn = 0, d = 0;
+        float n2sum = 0.f;
+        for (;;) {
+            // copy simple envelopes up to this lane's next flagged region
+            while (d < nd && !((oj[d] >> 30) & 1)) {
+                if (nn < ITSX_MAXDOM) {
+                    a.env[((size_t)e * ITSX_MAXDOM + nn) * 2 + 0] = oi[d];
+                    a.env[((size_t)e * ITSX_MAXDOM + nn) * 2 + 1] = oj[d];
+                    a.envdc[(size_t)e * ITSX_MAXDOM + nn] = 0.f;
+                    nn++;
+                }
+                d++;
+            }
+            const bool act = d < nd;
+            if (!__any_sync(FULL, act)) break;
+            int ci[MD_MAXCL], cj[MD_MAXCL];
+            float cdc[MD_MAXCL], regsum = 0.f;
+            const int ncl = md_resolve(a, scr, act, w, L, M, tp, et, act ? oi[d] : 1, act ? (oj[d] & 0x1fffffff) : 0,
+                                       ci, cj, cdc, regsum);
+            if (act) {
+                n2sum += regsum;
+                for (int c = 0; c < ncl; c++) {
+                    if (nn < ITSX_MAXDOM) {
+                        a.env[((size_t)e * ITSX_MAXDOM + nn) * 2 + 0] = ci[c];
+                        a.env[((size_t)e * ITSX_MAXDOM + nn) * 2 + 1] = cj[c] | (1 << 30) | (1 << 29);
+                        a.envdc[(size_t)e * ITSX_MAXDOM + nn] = cdc[c];
+                        nn++;
+                    } else {
+                        atomicAdd(&a.counters[CNT_DOM_OVERFLOW], 1ull);
+                    }
+                }
+                d++;
+            }
+        }
+        if (valid) {
+            a.ndom[e] = (uint8_t)nn;
+            a.n2reg[e] = n2sum;
+        }
+    }
+}
+// entries that hold a flagged region -> mdlist, with the sort key (profile, total flagged length): lanes of a warp
+// then walk regions of similar size against the same tables.  count[1] = longest flagged region
+__global__ void mdlist_kernel(const uint8_t *__restrict__ ndom, const int32_t *__restrict__ env, int n,
+                              const int32_t *__restrict__ list, int ns,
+                              int32_t *__restrict__ mdlist, uint32_t *__restrict__ mdkey, int32_t *__restrict__ count)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int nd = ndom[e];
+    int longest = 0, total = 0;
+    for (int d = 0; d < nd; d++) {
+        const int jraw = env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1];
+        if ((jraw >> 30) & 1) {
+            const int len = (jraw & 0x1fffffff) - env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0] + 1;
+            longest = max(longest, len);
+            total += len;
+        }
+    }
+    if (longest) {
+        const int at = atomicAdd(count, 1);
+        mdlist[at] = e;
+        mdkey[at] = ((uint32_t)(list[e] / ns) << 12) | (uint32_t)min(total, 4095);
+        atomicMax(count + 1, longest);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // envelope worklist
 __global__ void ndom_widen_kernel(const uint8_t *__restrict__ ndom, int n, int32_t *__restrict__ out)
 {
@@ -651,7 +1152,7 @@ __global__ void envwork_kernel(const uint8_t *__restrict__ ndom, const int32_t *
     const uint32_t p = (uint32_t)(list[e] / ns);
     for (int d = 0; d < nd; d++) {
         const int ienv = env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
-        const int jenv = env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1] & 0x3fffffff;
+        const int jenv = env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1] & 0x1fffffff;
         work[o + d] = e * ITSX_MAXDOM + d;
         key[o + d] = (p << 12) | (uint32_t)min(jenv - ienv + 1, 4095);
     }
@@ -728,7 +1229,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
             L = a.seqlen[s];
             w = a.seqw + a.woff[s];
             ienv = a.env[((size_t)ent * ITSX_MAXDOM + d) * 2 + 0];
-            const int jenv = a.env[((size_t)ent * ITSX_MAXDOM + d) * 2 + 1] & 0x3fffffff;
+            const int jenv = a.env[((size_t)ent * ITSX_MAXDOM + d) * 2 + 1] & 0x1fffffff;
             Ld = jenv - ienv + 1;
         }
         int Lw = Ld;
@@ -931,6 +1432,8 @@ struct FinalArgs {
     const uint8_t  *ndom;
     const int32_t  *envoff;
     const int32_t  *env;
+    const float    *envdc;    // [entry][MAXDOM]: domcorrection of the envelopes whose null2 came from traces (bit 29)
+    const float    *n2reg;    // [entry]: trace n2sc summed over the entry's multidomain regions
     float          *envout;   // [envelope][20]; [1] receives domcorrection
     float           T;
     DomRec         *doms;     // output base for this batch
@@ -961,7 +1464,12 @@ __global__ void __launch_bounds__(128) final_kernel(const FinalArgs a)
     for (int d = 0; d < nd; d++) {
         float *o = a.envout + (size_t)(o0 + d) * 20;
         const int ienv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
-        const int jenv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1] & 0x3fffffff;
+        const int jraw = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1];
+        const int jenv = jraw & 0x1fffffff;
+        if ((jraw >> 29) & 1) {         // null2 by trace: the whole region counts once, below
+            o[1] = a.envdc[(size_t)e * ITSX_MAXDOM + d];
+            continue;
+        }
         float dc = 0.f;
         for (int pos = ienv; pos <= jenv; pos++) {
             const float v = logf(o[2 + residue_at(w, pos - 1)]);
@@ -970,6 +1478,7 @@ __global__ void __launch_bounds__(128) final_kernel(const FinalArgs a)
         }
         o[1] = dc;
     }
+    seqbias += a.n2reg[e];
     seqbias = flogsum(a.logsum, 0.0f, lnomega + seqbias);
     float pre_score = (float)((double)(fwdsc - nullsc) / kLn2);
     float sscore = (float)((double)(fwdsc - (nullsc + seqbias)) / kLn2);
@@ -979,7 +1488,7 @@ __global__ void __launch_bounds__(128) final_kernel(const FinalArgs a)
         const float *o = a.envout + (size_t)(o0 + d) * 20;
         if (o[0] - o[1] > 0.0f) {
             const int ienv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
-            const int jenv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1] & 0x3fffffff;
+            const int jenv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1] & 0x1fffffff;
             sum_score += o[0];
             Ldsum += jenv - ienv + 1;
             sbias += o[1];
@@ -1002,7 +1511,7 @@ __global__ void __launch_bounds__(128) final_kernel(const FinalArgs a)
         const float *o = a.envout + (size_t)(o0 + d) * 20;
         const int ienv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
         const int jraw = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1];
-        const int jenv = jraw & 0x3fffffff;
+        const int jenv = jraw & 0x1fffffff;
         const int ld = jenv - ienv + 1;
         const float bs = o[0] + (float)((L - ld) * lratio);
         const float dombias = flogsum(a.logsum, 0.0f, lnomega + o[1]);
@@ -1078,6 +1587,22 @@ __global__ void pos_init_kernel(int32_t *pos, unsigned long long *best, int64_t 
     best[q] = best[nseq + q] = 0ull;
 }
 
+// esl_randomness_Init for the "fast" generator: the state after seeding (Jenkins mix3 of the seed)
+uint32_t md_rng_state0(uint32_t seed)
+{
+    uint32_t a = seed, b = 87654321u, c = 12345678u;
+    a -= b; a -= c; a ^= (c >> 13);
+    b -= c; b -= a; b ^= (a << 8);
+    c -= a; c -= b; c ^= (b >> 13);
+    a -= b; a -= c; a ^= (c >> 12);
+    b -= c; b -= a; b ^= (a << 16);
+    c -= a; c -= b; c ^= (b >> 5);
+    a -= b; a -= c; a ^= (c >> 3);
+    b -= c; b -= a; b ^= (a << 10);
+    c -= a; c -= b; c ^= (b >> 15);
+    return c ? c : 42u;
+}
+
 }  // namespace
 
 // ==================================================================================================
@@ -1091,6 +1616,7 @@ int search_upload_profiles(itsx_ctx *c)
     std::vector<uint32_t> msvtab((size_t)std::max(P, 1) * MSV_TABW);
     std::vector<float> etab((size_t)std::max(P, 1) * (MAXM + 1) * 16, 0.f);
     std::vector<ProfScalars> ps((size_t)std::max(P, 1));
+    std::vector<float> mdtab((size_t)std::max(P, 1) * (MAXM + 2) * 8, 0.f);
     c->pconst.assign((size_t)P, ProfConst{});
     for (int p = 0; p < P; p++) {
         const HostProfile &h = c->prof[p];
@@ -1133,6 +1659,8 @@ int search_upload_profiles(itsx_ctx *c)
             pc.bd0[k - 1] = tp[k][T_DM]; pc.bd1[k - 1] = tp[k][T_DD]; pc.bd2[k - 1] = tp[k][T_MD];
             pc.bm[k - 1] = tp[k][T_BM];
         }
+        for (int k = 0; k <= MAXM + 1; k++)
+            for (int t8 = 0; t8 < 8; t8++) mdtab[((size_t)p * (MAXM + 2) + k) * 8 + t8] = tp[k][t8];
         ProfScalars &q = ps[p];
         memset(&q, 0, sizeof(q));
         q.M = h.M; q.bias = h.bias_b; q.base = h.base_b; q.tbm = h.tbm_b; q.tec = h.tec_b;
@@ -1141,6 +1669,8 @@ int search_upload_profiles(itsx_ctx *c)
         for (int i = 0; i < 6; i++) q.ev[i] = h.ev[i];
         for (int x = 0; x < 16; x++) { q.eo[x][0] = h.eo[x][0]; q.eo[x][1] = h.eo[x][1]; }
     }
+    CUDA_TRY(c, c->d_mdtab.ensure(mdtab.size() * 4));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_mdtab.p, mdtab.data(), mdtab.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(c, c->d_msvtab.ensure(msvtab.size() * 4));
     CUDA_TRY(c, c->d_etab.ensure(etab.size() * 4));
     CUDA_TRY(c, c->d_pscal.ensure(ps.size() * sizeof(ProfScalars)));
@@ -1291,7 +1821,7 @@ int search_stage1(itsx_ctx *c)
     if (rc) return rc;
     unsigned long long *cnt = c->d_counters.as<unsigned long long>();
 
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[9];
     for (auto &e : ev) CUDA_TRY(c, cudaEventCreate(&e));
     float acc_ms[6] = {0, 0, 0, 0, 0, 0};
     CUDA_TRY(c, cudaEventRecord(ev[0], st));
@@ -1455,6 +1985,57 @@ int search_stage1(itsx_ctx *c)
         }
         CUDA_TRY(c, cudaEventRecord(ev[4], st));
 
+        // ---- multidomain regions: stochastic-traceback clustering replaces the region by its cluster envelopes ----
+        CUDA_TRY(c, c->d_envdc.ensure((size_t)n2 * ITSX_MAXDOM * 4));
+        CUDA_TRY(c, c->d_n2reg.ensure((size_t)n2 * 4));
+        CUDA_TRY(c, cudaMemsetAsync(c->d_n2reg.p, 0, (size_t)n2 * 4, st));
+        if (c->prm.resolve_multidomain) {
+            // [0, n2) list, [n2, 2 n2) sorted list, [2 n2, 3 n2) keys, [3 n2, 4 n2) sorted keys, then the two counters
+            CUDA_TRY(c, c->d_mdlist.ensure(((size_t)n2 * 4 + 2) * 4));
+            int32_t *md_in = c->d_mdlist.as<int32_t>(), *md_out = md_in + n2;
+            uint32_t *mk_in = (uint32_t *)(md_in + 2 * (size_t)n2), *mk_out = mk_in + n2;
+            int32_t *d_mdcount = md_in + 4 * (size_t)n2;               // [0] entries, [1] longest flagged region
+            CUDA_TRY(c, cudaMemsetAsync(d_mdcount, 0, 8, st));
+            mdlist_kernel<<<nblk(n2, 256), 256, 0, st>>>(c->d_ndom.as<uint8_t>(), c->d_env.as<int32_t>(), n2,
+                                                        c->d_list2.as<int32_t>(), ns, md_in, mk_in, d_mdcount);
+            c->launches++;
+            int32_t h_md[2] = {0, 0};
+            CUDA_TRY(c, cudaMemcpyAsync(h_md, d_mdcount, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaStreamSynchronize(st));
+            if (h_md[0] > 0) {
+                int pbits = 1;
+                while ((1 << pbits) < P) pbits++;
+                size_t tbs = 0;
+                cub::DeviceRadixSort::SortPairs(nullptr, tbs, mk_in, mk_out, md_in, md_out, h_md[0], 0, 12 + pbits, st);
+                CUDA_TRY(c, c->d_tmp.ensure(tbs));
+                cub::DeviceRadixSort::SortPairs(c->d_tmp.p, tbs, mk_in, mk_out, md_in, md_out, h_md[0], 0, 12 + pbits, st);
+                c->launches++;
+            }
+            if (h_md[0] > 0) {
+                MdArgs ma;
+                ma.rows = h_md[1] + 1;
+                ma.per_thread = md_scratch_bytes(ma.rows);
+                // one thread per entry, as many resident as registers allow (24 warps / SM), scratch capped at 8 GB
+                int md_threads = std::min((h_md[0] + 63) / 64 * 64, c->sm_count * 768);
+                md_threads = (int)std::min<size_t>((size_t)md_threads, ((size_t)8 << 30) / ma.per_thread / 64 * 64);
+                md_threads = std::max(md_threads, 64);
+                CUDA_TRY(c, c->d_mdscratch.ensure(ma.per_thread * (size_t)md_threads));
+                ma.mdlist = md_out; ma.count_ptr = d_mdcount;
+                ma.list = c->d_list2.as<int32_t>(); ma.order = d_order; ma.s0 = s0; ma.ns = ns;
+                ma.seqw = c->d_seqw.as<uint32_t>(); ma.woff = c->d_seqwoff.as<int64_t>(); ma.seqlen = c->d_seqlen.as<int32_t>();
+                ma.mdtab = c->d_mdtab.as<float>(); ma.etab = c->d_etab.as<float>(); ma.pscal = c->d_pscal.as<ProfScalars>();
+                ma.ndom = c->d_ndom.as<uint8_t>(); ma.env = c->d_env.as<int32_t>();
+                ma.envdc = c->d_envdc.as<float>(); ma.n2reg = c->d_n2reg.as<float>();
+                ma.scratch = c->d_mdscratch.as<char>();
+                ma.e_move = expf(-(float)kLn2);
+                ma.rng0 = md_rng_state0(42u);
+                ma.counters = cnt;
+                mdom_kernel<<<md_threads / 64, 64, 0, st>>>(ma);
+                c->launches++;
+            }
+        }
+        CUDA_TRY(c, cudaEventRecord(ev[8], st));
+
         // ---- envelope worklist ----
         CUDA_TRY(c, c->d_scan.ensure((size_t)(n2 + 1) * 4));
         CUDA_TRY(c, c->d_envoff.ensure((size_t)(n2 + 1) * 4));
@@ -1536,6 +2117,7 @@ int search_stage1(itsx_ctx *c)
             fa.pscal = c->d_pscal.as<ProfScalars>(); fa.nullsctab = c->d_nullsc.as<float>();
             fa.logsum = c->d_logsum.as<float>(); fa.fwdsc = c->d_fwdsc.as<float>();
             fa.ndom = c->d_ndom.as<uint8_t>(); fa.envoff = c->d_envoff.as<int32_t>(); fa.env = c->d_env.as<int32_t>();
+            fa.envdc = c->d_envdc.as<float>(); fa.n2reg = c->d_n2reg.as<float>();
             fa.envout = c->d_envout.as<float>(); fa.T = c->prm.T;
             fa.doms = c->d_doms.as<DomRec>() + c->ndom;
             fa.nrep = c->d_nrep.as<int32_t>(); fa.counters = cnt;
@@ -1549,7 +2131,8 @@ int search_stage1(itsx_ctx *c)
         {
             float ms;
             cudaEventElapsedTime(&ms, ev[3], ev[4]); acc_ms[2] += ms;
-            cudaEventElapsedTime(&ms, ev[4], ev[5]); acc_ms[3] += ms;
+            cudaEventElapsedTime(&ms, ev[4], ev[8]); acc_ms[5] += ms;
+            cudaEventElapsedTime(&ms, ev[8], ev[5]); acc_ms[3] += ms;
             cudaEventElapsedTime(&ms, ev[5], ev[6]); acc_ms[4] += ms;
         }
     }
@@ -1569,7 +2152,7 @@ int search_stage1(itsx_ctx *c)
     ss.bck_cells = (double)h_cnt[CNT_BCK_ROWS] * MAXM;
     ss.env_cells = (double)h_cnt[CNT_ENV_ROWS] * MAXM * 2;
     ss.ms_msv = acc_ms[0]; ss.ms_bias = acc_ms[1]; ss.ms_fwd = acc_ms[2]; ss.ms_env = acc_ms[3]; ss.ms_final = acc_ms[4];
-    ss.ms_bck = 0.f;
+    ss.ms_mdom = acc_ms[5];
     cudaEventElapsedTime(&ss.ms_total, ev[0], ev[7]);
     for (auto &e : ev) cudaEventDestroy(e);
     c->stage1_done = true;

@@ -350,6 +350,7 @@ void ora_default_params(ora_params *prm)
     prm->F1 = prm->F2 = prm->F3 = 1e-6;
     prm->domE     = 10.0;
     prm->nthreads = 0;
+    prm->resolve_multidomain = 1;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -504,7 +505,7 @@ static void specials_free(specials_t *s) { free(s->E); }
 /* dsq points at the first residue of the (sub)sequence; rows are 1..L.
  * fullM/fullI (optional): (L+1)*(M+1) floats, row-major, for posterior decoding. */
 static float forward_engine(const prof_t *pf, const xf_t *xf, const uint8_t *dsq, int L,
-                            specials_t *sp, float *fullM, float *fullI)
+                            specials_t *sp, float *fullM, float *fullI, float *fullD)
 {
     const int    M  = pf->M;
     float       *Mx = calloc((size_t)(M + 2) * 3, sizeof(float));
@@ -551,6 +552,7 @@ static float forward_engine(const prof_t *pf, const xf_t *xf, const uint8_t *dsq
         if (fullM) {
             memcpy(fullM + (size_t)i * (M + 1), Mx, (size_t)(M + 1) * sizeof(float));
             memcpy(fullI + (size_t)i * (M + 1), Ix, (size_t)(M + 1) * sizeof(float));
+            if (fullD) memcpy(fullD + (size_t)i * (M + 1), Dx, (size_t)(M + 1) * sizeof(float));
         }
     }
     free(Mx);
@@ -675,7 +677,7 @@ static void rescore_envelope(const prof_t *pf, const uint8_t *dsq, int L, int i,
     float     *fM = malloc((size_t)(Ld + 1) * (M + 1) * 2 * sizeof(float));
     float     *fI = fM + (size_t)(Ld + 1) * (M + 1);
     float      acc[64];
-    float envsc = forward_engine(pf, &xf, dsq + (i - 1), Ld, &fs, fM, fI);
+    float envsc = forward_engine(pf, &xf, dsq + (i - 1), Ld, &fs, fM, fI, NULL);
     backward_engine(pf, &xf, dsq + (i - 1), Ld, &fs, &bs, fM, fI, acc);
     /* null2 by expectation (p7_Null2_ByExpectation): null2[x] = sum_k pbar(M_k) odds_k[x] + sum_k pbar(I_k)
      * + pbar(N) + pbar(C) + pbar(J), pbar = posterior usage averaged over the Ld envelope positions.  Every
@@ -714,6 +716,289 @@ static void rescore_envelope(const prof_t *pf, const uint8_t *dsq, int L, int i,
 }
 
 /* ------------------------------------------------------------------------ */
+/* Multidomain regions (p7_domaindef.c: is_multidomain_region -> region_trace_ensemble ->
+ * p7_spensemble_Cluster -> rescore_isolated_domain(null2_is_done = TRUE)), restated from HMMER 3.1b2+ sources
+ * (SURVEY Appendix A.5).  HMMER is absent from the reference mount, so this is "parity unpinned" like the rest
+ * of the HMM stage; the CUDA path (mdom_kernel) follows this restatement operation for operation.
+ *
+ *   1. multihit Forward (length model of the full target) over the region, full M/I/D matrix;
+ *   2. the domain definition's RNG is re-seeded for every region (esl_randomness_CreateFast(42), do_reseeding):
+ *      x0 = jenkins_mix3(42, 87654321, 12345678), then x <- 69069 x + 1, u = x / 2^32;
+ *   3. 200 stochastic tracebacks (p7_StochasticTrace, impl_sse/stotrace.c): one draw per state choice, paths
+ *      normalised (esl_vec_FNorm) and chosen by cumulative sum (esl_rnd_FChoose); the E state scans
+ *      M_k, D_k in the striped order of the SSE matrix (q = 0..Q-1, r = 0..3, k = r Q + q + 1);
+ *   4. every domain of every trace is one segment (i, j, k, m); null2 by trace (p7_Null2_ByTrace) is averaged
+ *      over the 200 traces into n2sc[] for every position of the region;
+ *   5. single-linkage clustering of the segments (min_overlap 0.8 of the smaller, max_diagdiff 4), clusters with
+ *      posterior >= 0.25, envelope = leftmost start / rightmost end whose endpoint count reaches
+ *      ceil(0.02 * cluster size); clusters ordered by start;
+ *   6. each cluster envelope is rescored by a unihit Forward; its domcorrection is the sum of the trace n2sc. */
+#define MD_NSAMPLES 200
+#define MD_MAXSEG   1024  /* segments kept per region (200 traces x domains per trace) */
+typedef struct { int idx, i, j, k, m; } spseg_t;
+
+static uint32_t jenkins_mix3(uint32_t a, uint32_t b, uint32_t c)
+{
+    a -= b; a -= c; a ^= (c >> 13);
+    b -= c; b -= a; b ^= (a << 8);
+    c -= a; c -= b; c ^= (b >> 13);
+    a -= b; a -= c; a ^= (c >> 12);
+    b -= c; b -= a; b ^= (a << 16);
+    c -= a; c -= b; c ^= (b >> 5);
+    a -= b; a -= c; a ^= (c >> 3);
+    b -= c; b -= a; b ^= (a << 10);
+    c -= a; c -= b; c ^= (b >> 15);
+    return c;
+}
+uint32_t ora_rng_state0(uint32_t seed)
+{
+    uint32_t x = jenkins_mix3(seed, 87654321u, 12345678u);
+    return x ? x : 42u;
+}
+static inline double rng_next(uint32_t *x)
+{
+    *x = *x * 69069u + 1u;
+    return (double)*x / 4294967296.0;
+}
+/* esl_vec_FNorm + esl_rnd_FChoose over n <= 4 paths */
+static int fchoose(uint32_t *rng, float *p, int n)
+{
+    float sum = 0.f;
+    for (int a = 0; a < n; a++) sum += p[a];
+    if (sum != 0.f) { const float inv = 1.0f / sum; for (int a = 0; a < n; a++) p[a] = p[a] * inv; } /* esl_vec_FScale(1/sum) */
+    else for (int a = 0; a < n; a++) p[a] = 1.0f / (float)n;
+    for (;;) {
+        double roll = rng_next(rng);
+        float  c    = 0.f;
+        for (int a = 0; a < n; a++) { c += p[a]; if (roll < (double)c) return a; }
+    }
+}
+enum { ST_M = 0, ST_D, ST_I, ST_N, ST_C, ST_J, ST_E, ST_B, ST_S };
+
+static int seg_link(const spseg_t *a, const spseg_t *b)
+{
+    int nov = (a->j < b->j ? a->j : b->j) - (a->i > b->i ? a->i : b->i) + 1;
+    int la = a->j - a->i + 1, lb = b->j - b->i + 1;
+    int n  = la < lb ? la : lb;
+    if ((float)nov / (float)n < 0.8f) return 0;
+    nov = (a->m < b->m ? a->m : b->m) - (a->k > b->k ? a->k : b->k) + 1;
+    la = a->m - a->k + 1; lb = b->m - b->k + 1;
+    n  = la < lb ? la : lb;
+    if ((float)nov / (float)n < 0.8f) return 0;
+    if (abs((a->i - a->k) - (b->i - b->k)) > 4) return 0;
+    if (abs((a->j - a->m) - (b->j - b->m)) > 4) return 0;
+    return 1;
+}
+
+/* Resolves region ireg..jreg (1-based, full-sequence coordinates).  Fills n2sc[ireg..jreg] and returns the number of
+ * cluster envelopes written to env_i/env_j (ascending start), at most cap. */
+static int resolve_multidomain(const prof_t *pf, const uint8_t *dsq, int L, int ireg, int jreg, float *n2sc,
+                               int *env_i, int *env_j, int cap)
+{
+    const int      M  = pf->M, Ld = jreg - ireg + 1, W = M + 1;
+    const uint8_t *x  = dsq + (ireg - 1); /* x[r-1] = residue of region row r */
+    xf_t           xf = xf_multihit(L);
+    specials_t     fs = specials_alloc(Ld);
+    float         *fM = calloc((size_t)(Ld + 1) * W * 3, sizeof(float));
+    float         *fI = fM + (size_t)(Ld + 1) * W, *fD = fI + (size_t)(Ld + 1) * W;
+    forward_engine(pf, &xf, x, Ld, &fs, fM, fI, fD);
+    const float *tp = pf->tp, *bm = pf->bm;
+    const int    Q  = (((M - 1) / 4) + 1) > 2 ? (((M - 1) / 4) + 1) : 2;
+
+    float   *acc = calloc((size_t)Ld + 2, sizeof(float)); /* sum over traces of the null2 odds of every region position */
+    spseg_t *seg = malloc(sizeof(spseg_t) * MD_MAXSEG);
+    int      nseg = 0;
+    uint32_t rng = ora_rng_state0(42u);
+
+    for (int t = 0; t < MD_NSAMPLES; t++) {
+        /* domains of this trace are discovered right to left */
+        int dfrom[8], dto[8], dk[8], dm[8], nd = 0;   /* a trace holds at most 8 domains (as the kernel) */
+        float dnull[8][16];
+        int   i = Ld, k = 0, sprv = ST_C, open = 0, nI = 0;
+        float sx[4] = {0.f, 0.f, 0.f, 0.f};
+        while (sprv != ST_S) {
+            int   scur = ST_S;
+            float path[4];
+            switch (sprv) {
+            case ST_M: {
+                path[0] = fs.B[i - 1] * bm[k];
+                path[1] = fM[(size_t)(i - 1) * W + k - 1] * tp[(k - 1) * 7 + T_MM];
+                path[2] = fI[(size_t)(i - 1) * W + k - 1] * tp[(k - 1) * 7 + T_IM];
+                path[3] = fD[(size_t)(i - 1) * W + k - 1] * tp[(k - 1) * 7 + T_DM];
+                static const int st[4] = {ST_B, ST_M, ST_I, ST_D};
+                scur = st[fchoose(&rng, path, 4)];
+                k--; i--;
+            } break;
+            case ST_D: {
+                path[0] = fM[(size_t)i * W + k - 1] * tp[(k - 1) * 7 + T_MD];
+                path[1] = fD[(size_t)i * W + k - 1] * tp[(k - 1) * 7 + T_DD];
+                scur = fchoose(&rng, path, 2) == 0 ? ST_M : ST_D;
+                k--;
+            } break;
+            case ST_I: {
+                path[0] = fM[(size_t)(i - 1) * W + k] * tp[k * 7 + T_MI];
+                path[1] = fI[(size_t)(i - 1) * W + k] * tp[k * 7 + T_II];
+                scur = fchoose(&rng, path, 2) == 0 ? ST_M : ST_I;
+                i--;
+            } break;
+            case ST_N: scur = (i == 0) ? ST_S : ST_N; break;
+            case ST_C: {
+                path[0] = fs.C[i - 1] * xf.N_loop;
+                path[1] = fs.E[i] * xf.E_move * fs.S[i];
+                scur = fchoose(&rng, path, 2) == 0 ? ST_C : ST_E;
+            } break;
+            case ST_J: {
+                path[0] = fs.J[i - 1] * xf.N_loop;
+                path[1] = fs.E[i] * xf.E_loop * fs.S[i];
+                scur = fchoose(&rng, path, 2) == 0 ? ST_J : ST_E;
+            } break;
+            case ST_E: {
+                /* M_k / D_k of row i in striped order, all scaled by 1 / xE(i) */
+                const double roll = rng_next(&rng);
+                const float  nrm  = (float)(1.0 / (double)fs.E[i]);
+                double       sum  = 0.0;
+                int          done = 0;
+                while (!done) {
+                    for (int q = 0; q < Q && !done; q++) {
+                        for (int r = 0; r < 4 && !done; r++) {
+                            int kk = r * Q + q + 1;
+                            sum += (double)((kk <= M ? fM[(size_t)i * W + kk] : 0.f) * nrm);
+                            if (roll < sum) { k = kk; scur = ST_M; done = 1; }
+                        }
+                        for (int r = 0; r < 4 && !done; r++) {
+                            int kk = r * Q + q + 1;
+                            sum += (double)((kk <= M ? fD[(size_t)i * W + kk] : 0.f) * nrm);
+                            if (roll < sum) { k = kk; scur = ST_D; done = 1; }
+                        }
+                    }
+                    if (!done && sum < 0.99) { k = 1; scur = ST_M; done = 1; } /* HMMER raises an exception here */
+                }
+            } break;
+            case ST_B: {
+                path[0] = fs.N[i] * xf.N_move;
+                path[1] = fs.J[i] * xf.N_move;
+                scur = fchoose(&rng, path, 2) == 0 ? ST_N : ST_J;
+            } break;
+            }
+            /* bookkeeping of the appended state (scur, k, i) */
+            if (scur == ST_E) {
+                if (nd < 8) { open = 1; dto[nd] = 0; dm[nd] = 0; dfrom[nd] = 0; dk[nd] = 0; nI = 0; sx[0] = sx[1] = sx[2] = sx[3] = 0.f; }
+            } else if (scur == ST_M && open) {
+                if (dto[nd] == 0) { dto[nd] = i; dm[nd] = k; }
+                dfrom[nd] = i; dk[nd] = k;
+                for (int a = 0; a < 4; a++) sx[a] += pf->e[k * 16 + a];
+            } else if (scur == ST_I && open) {
+                nI++;
+            } else if (scur == ST_B && open) {
+                /* p7_Null2_ByTrace over the domain's emitting states: null2[x] = (sum of the match odds of the M states
+                 * used + number of insert emissions) / Ld, summed in trace-walk order */
+                const int   ld   = dto[nd] - dfrom[nd] + 1;
+                const float norm = 1.0f / (float)ld;
+                float      *n2   = dnull[nd];
+                for (int a = 0; a < 4; a++) n2[a] = (sx[a] + (float)nI) * norm;
+                for (int a = 4; a < 15; a++) {
+                    float sa = 0.f;
+                    int   na = 0;
+                    for (int y = 0; y < 4; y++)
+                        if (degen_mask[a] & (1 << y)) { sa += n2[y]; na++; }
+                    n2[a] = sa / (float)na;
+                }
+                n2[15] = 1.0f;
+                open = 0;
+                nd++;
+            }
+            if ((scur == ST_N || scur == ST_J || scur == ST_C) && scur == sprv) i--;
+            sprv = scur;
+        }
+        /* left to right: segments for the ensemble, null2 odds per position */
+        int pos = 1;
+        for (int d = nd - 1; d >= 0; d--) {
+            if (nseg < MD_MAXSEG) {
+                seg[nseg].idx = t; seg[nseg].i = dfrom[d] + ireg - 1; seg[nseg].j = dto[d] + ireg - 1;
+                seg[nseg].k = dk[d]; seg[nseg].m = dm[d];
+                nseg++;
+            }
+            for (; pos <= dfrom[d]; pos++) acc[pos] += 1.0f;
+            for (; pos <= dto[d]; pos++) acc[pos] += dnull[d][x[pos - 1]];
+        }
+        for (; pos <= Ld; pos++) acc[pos] += 1.0f;
+    }
+    for (int pos = 1; pos <= Ld; pos++)
+        n2sc[ireg + pos - 1] = (float)log((double)(acc[pos] / (float)MD_NSAMPLES));
+
+    /* single linkage clustering (connected components of seg_link) */
+    int *asg = malloc(sizeof(int) * (size_t)(nseg + 1));
+    for (int a = 0; a < nseg; a++) asg[a] = -1;
+    int  nc = 0;
+    int *stack = malloc(sizeof(int) * (size_t)(nseg + 1));
+    for (int a = 0; a < nseg; a++) {
+        if (asg[a] >= 0) continue;
+        int top = 0;
+        stack[top++] = a; asg[a] = nc;
+        while (top) {
+            int v = stack[--top];
+            for (int b = 0; b < nseg; b++)
+                if (asg[b] < 0 && seg_link(&seg[v], &seg[b])) { asg[b] = nc; stack[top++] = b; }
+        }
+        nc++;
+    }
+    int nenv = 0;
+    for (int c = 0; c < nc; c++) {
+        int ninc = 0, ntr = 0, last = -1;
+        int imin = 1 << 30, imax = 0, jmin = 1 << 30, jmax = 0;
+        for (int a = 0; a < nseg; a++) {
+            if (asg[a] != c) continue;
+            ninc++;
+            if (seg[a].idx != last) { ntr++; last = seg[a].idx; }
+            if (seg[a].i < imin) imin = seg[a].i;
+            if (seg[a].i > imax) imax = seg[a].i;
+            if (seg[a].j < jmin) jmin = seg[a].j;
+            if (seg[a].j > jmax) jmax = seg[a].j;
+        }
+        if ((float)ntr / (float)MD_NSAMPLES < 0.25f) continue;
+        const int thr = (int)ceilf((float)ninc * 0.02f);
+        int best_i = imin, best_j = jmax;
+        for (best_i = imin; best_i <= imax; best_i++) {
+            int cnt = 0;
+            for (int a = 0; a < nseg; a++) cnt += (asg[a] == c && seg[a].i == best_i);
+            if (cnt >= thr) break;
+        }
+        for (best_j = jmax; best_j >= jmin; best_j--) {
+            int cnt = 0;
+            for (int a = 0; a < nseg; a++) cnt += (asg[a] == c && seg[a].j == best_j);
+            if (cnt >= thr) break;
+        }
+        /* insert by (start, end) ascending */
+        if (nenv < cap) {
+            int at = nenv;
+            while (at > 0 && (env_i[at - 1] > best_i || (env_i[at - 1] == best_i && env_j[at - 1] > best_j))) {
+                env_i[at] = env_i[at - 1]; env_j[at] = env_j[at - 1]; at--;
+            }
+            env_i[at] = best_i; env_j[at] = best_j;
+            nenv++;
+        }
+    }
+    free(asg); free(stack); free(seg); free(acc); free(fM);
+    specials_free(&fs);
+    return nenv;
+}
+
+/* rescore_isolated_domain with null2_is_done: unihit Forward score of the envelope, domcorrection from n2sc[] */
+static void rescore_envelope_n2done(const prof_t *pf, const uint8_t *dsq, int L, int i, int j, const float *n2sc,
+                                    ora_dom *dom)
+{
+    const int  Ld = j - i + 1;
+    xf_t       xf = xf_unihit(L);
+    specials_t fs = specials_alloc(Ld);
+    dom->envsc    = forward_engine(pf, &xf, dsq + (i - 1), Ld, &fs, NULL, NULL, NULL);
+    specials_free(&fs);
+    float dc = 0.f;
+    for (int pos = i; pos <= j; pos++) dc += n2sc[pos];
+    dom->ienv = i; dom->jenv = j;
+    dom->domcorrection = dc;
+}
+
+/* ------------------------------------------------------------------------ */
 int ora_pair_run(const ora_db *db, int p, const uint8_t *dsq, int L,
                  const ora_params *prm, ora_pair *pr, ora_dom *doms, int domcap)
 {
@@ -740,7 +1025,7 @@ int ora_pair_run(const ora_db *db, int p, const uint8_t *dsq, int L,
 
     xf_t       xf = xf_multihit(L);
     specials_t fs = specials_alloc(L), bs = specials_alloc(L);
-    pr->fwdsc     = forward_engine(pf, &xf, dsq, L, &fs, NULL, NULL);
+    pr->fwdsc     = forward_engine(pf, &xf, dsq, L, &fs, NULL, NULL, NULL);
     seq_score     = (float)((pr->fwdsc - pr->filtersc) / LOG2);
     pr->P_fwd     = exp_surv(seq_score, pf->ev[EV_FTAU], pf->ev[EV_FLAMBDA]);
     if (pr->P_fwd > prm->F3) { specials_free(&fs); specials_free(&bs); return 0; }
@@ -770,12 +1055,22 @@ int ora_pair_run(const ora_db *db, int p, const uint8_t *dsq, int L,
             }
             int multi = (max >= rt3);
             if (multi) pr->nmultidomain++;
-            if (ndom < domcap) {
+            if (multi && prm->resolve_multidomain) {
+                int ei[16], ej[16];
+                int nenv = resolve_multidomain(pf, dsq, L, i, j, n2sc, ei, ej, 16);
+                for (int c = 0; c < nenv && ndom < domcap; c++) {
+                    ora_dom *d = &doms[ndom];
+                    memset(d, 0, sizeof(*d));
+                    rescore_envelope_n2done(pf, dsq, L, ei[c], ej[c], n2sc, d);
+                    d->prof = p;
+                    d->is_multidomain = 1;
+                    d->dom_idx = ndom;
+                    ndom++;
+                }
+            } else if (ndom < domcap) {
                 ora_dom *d = &doms[ndom];
                 memset(d, 0, sizeof(*d));
-                /* NOTE: HMMER resolves multidomain regions by stochastic-traceback clustering
-                 * (200 samples, RNG seed 42).  That is not restated; the region is rescored as
-                 * one envelope and flagged (documented deviation). */
+                /* resolve_multidomain == 0: a multidomain region is rescored as one envelope and flagged */
                 rescore_envelope(pf, dsq, L, i, j, n2sc, d);
                 d->prof = p;
                 d->is_multidomain = multi;
@@ -844,7 +1139,7 @@ float ora_forward_score(const ora_db *db, int p, const uint8_t *dsq, int L)
 {
     xf_t       xf = xf_multihit(L);
     specials_t fs = specials_alloc(L);
-    float      sc = forward_engine(&db->p[p], &xf, dsq, L, &fs, NULL, NULL);
+    float      sc = forward_engine(&db->p[p], &xf, dsq, L, &fs, NULL, NULL, NULL);
     specials_free(&fs);
     return sc;
 }
@@ -852,7 +1147,7 @@ float ora_backward_score(const ora_db *db, int p, const uint8_t *dsq, int L)
 {
     xf_t       xf = xf_multihit(L);
     specials_t fs = specials_alloc(L), bs = specials_alloc(L);
-    forward_engine(&db->p[p], &xf, dsq, L, &fs, NULL, NULL);
+    forward_engine(&db->p[p], &xf, dsq, L, &fs, NULL, NULL, NULL);
     float sc = backward_engine(&db->p[p], &xf, dsq, L, &fs, &bs, NULL, NULL, NULL);
     specials_free(&fs);
     specials_free(&bs);
@@ -863,7 +1158,7 @@ int ora_forward_parser(const ora_db *db, int p, const uint8_t *dsq, int L,
 {
     xf_t       xf = xf_multihit(L);
     specials_t fs = specials_alloc(L);
-    float      sc = forward_engine(&db->p[p], &xf, dsq, L, &fs, NULL, NULL);
+    float      sc = forward_engine(&db->p[p], &xf, dsq, L, &fs, NULL, NULL, NULL);
     size_t     n  = (size_t)(L + 1) * sizeof(float);
     memcpy(xE, fs.E, n); memcpy(xN, fs.N, n); memcpy(xJ, fs.J, n);
     memcpy(xB, fs.B, n); memcpy(xC, fs.C, n); memcpy(scale, fs.S, n);
@@ -876,7 +1171,7 @@ int ora_domain_decoding(const ora_db *db, int p, const uint8_t *dsq, int L,
 {
     xf_t       xf = xf_multihit(L);
     specials_t fs = specials_alloc(L), bs = specials_alloc(L);
-    forward_engine(&db->p[p], &xf, dsq, L, &fs, NULL, NULL);
+    forward_engine(&db->p[p], &xf, dsq, L, &fs, NULL, NULL, NULL);
     backward_engine(&db->p[p], &xf, dsq, L, &fs, &bs, NULL, NULL, NULL);
     domain_decoding(&xf, L, &fs, &bs, btot, etot, mocc);
     specials_free(&fs);

@@ -67,7 +67,7 @@ typedef struct {
     int32_t pass_msv, pass_bias, pass_fwd;
     float   bcksc;        /* Backward parser score (nats); valid if pass_fwd */
     int32_t nregions;
-    int32_t nmultidomain; /* regions flagged multidomain (handled as one envelope; documented) */
+    int32_t nmultidomain; /* regions flagged multidomain */
     int32_t ndom;
     int32_t reported;     /* per-sequence score >= T */
     float   seq_score;    /* bits */
@@ -84,7 +84,7 @@ typedef struct {
     float   dombias;          /* nats */
     double  lnP;
     int32_t dom_idx;          /* 0-based index of the domain within its (seq,prof) hit */
-    int32_t is_multidomain;   /* region was flagged multidomain */
+    int32_t is_multidomain;   /* envelope comes from a region flagged multidomain */
     int32_t is_reported;      /* filled by ora_search (needs domZ) */
     int32_t pad;
 } ora_dom;
@@ -94,6 +94,7 @@ typedef struct {
     double F1, F2, F3; /* 1e-6 each    */
     double domE;       /* 10.0         */
     int    nthreads;   /* OpenMP threads (<=0: all) */
+    int    resolve_multidomain; /* 1 (default): multidomain regions go through the stochastic-traceback clustering */
 } ora_params;
 
 void ora_default_params(ora_params *prm);

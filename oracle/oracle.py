@@ -43,7 +43,7 @@ class OraDom(C.Structure):
 
 class OraParams(C.Structure):
     _fields_ = [("T", C.c_float), ("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double),
-                ("domE", C.c_double), ("nthreads", C.c_int)]
+                ("domE", C.c_double), ("nthreads", C.c_int), ("resolve_multidomain", C.c_int)]
 
 
 class OraStats(C.Structure):
@@ -226,10 +226,11 @@ class ProfileDB:
         return rows, nrep[: self.n], st
 
 
-def default_params(nthreads=0):
+def default_params(nthreads=0, resolve_multidomain=1):
     prm = OraParams()
     lib().ora_default_params(C.byref(prm))
     prm.nthreads = nthreads
+    prm.resolve_multidomain = resolve_multidomain
     return prm
 
 
