@@ -633,20 +633,36 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
 
 // ------------------------------------------------------------------------------------------------
 // K9b: multidomain regions (p7_domaindef.c: region_trace_ensemble + p7_spensemble_Cluster), operation
-// for operation the same as oracle/ora_hmm.c:resolve_multidomain.  About 1 % of the regions: one THREAD per
-// worklist entry that has a flagged region, plain loops, all per-thread state in a global scratch block:
-//   multihit Forward over the region with the full M/I/D matrix -> 200 stochastic tracebacks with HMMER's "fast" RNG
-//   re-seeded per region (x0 = mix3(42), x <- 69069 x + 1) -> null2 by trace averaged per position -> single-linkage
-//   clustering of the sampled segments -> cluster envelopes (start order) replace the region in the entry's list.
+// for operation the same as oracle/ora_hmm.c:resolve_multidomain.  About 1 % of the regions, but 200 stochastic
+// tracebacks each, so the stage is split so that the TRACE is the unit of parallelism:
+//   mdfwd_kernel    one thread per region: multihit Forward over the region, full (M, I, D) matrix and the per-row
+//                   normalised C / J / B choices to a region-private slab in HBM
+//   mdtrace_kernel  one thread per (region, trace): the random walk back through the matrix with HMMER's "fast"
+//                   generator leap-frogged to substream t (x_(t 2^20)); the 200 lanes of a region read the same slab
+//                   (L1 / L2 resident); phases of the walk are warp-vote loops so lanes stay converged; a trace
+//                   leaves its domains (coordinates + null2 odds by trace) in a fixed 100-byte record
+//   mdclust_kernel  one thread per region: n2sc per position, distinct segments, single-linkage clustering,
+//                   cluster envelopes (start order) with their domcorrection
+//   mdapply_kernel  one thread per worklist entry: the cluster envelopes replace the region in the entry's list.
 // The cluster envelopes carry bit 29 ("null2 done"): env_kernel still gives their unihit Forward score, final_kernel
 // takes their domcorrection from envdc[] and the region-wide sum of the trace n2sc from n2reg[].
 constexpr int MD_NSAMPLES = 200;
 constexpr int MD_MAXSEG = 1024;
-constexpr int MD_MAXCL = 16;
+constexpr int MD_MAXTDOM = 4;                  // domains kept per trace
 constexpr int MD_W = MAXM + 1;
+constexpr int MD_STREAM_LOG2 = 20;
+struct alignas(8) MdSeg { uint16_t i, j; uint8_t k, m; uint16_t n; };        // distinct segment and how many traces sampled it
+struct MdRow { float pC0, pC1, pJ0, pJ1, pB0, pB1, nrmE, xB; };   // per row: normalised C / J / B choices, 1 / xE, xB
+struct MdDom { uint16_t from, to; uint8_t k, m; uint16_t pad; float n2[4]; };   // region-relative rows
+struct MdTrace { int32_t nd; MdDom d[MD_MAXTDOM]; };
+struct MdRes { int32_t n; float regsum; int32_t ci[ITSX_MAXDOM], cj[ITSX_MAXDOM]; float cdc[ITSX_MAXDOM]; };
 struct MdArgs {
-    const int32_t *mdlist;    // entries with at least one flagged region
-    const int32_t *count_ptr;
+    // regions of this chunk: [r0, r1) of the region list
+    int             r0, r1;
+    const int32_t  *reg_ent;  // worklist entry of every region
+    const int32_t  *reg_i, *reg_j;
+    const int32_t  *reg_row;  // first row of the region's slab (prefix sum of Ld + 1), relative to the list
+    int             row0;     // reg_row of region r0
     const int32_t *list;
     const int32_t *order;
     int64_t        s0;
@@ -657,25 +673,21 @@ struct MdArgs {
     const float    *mdtab;    // [P][MAXM + 2][8]: transitions out of node k, B->M_k in slot 7
     const float    *etab;     // [P][MAXM + 1][16]
     const ProfScalars *pscal;
-    uint8_t        *ndom;
-    int32_t        *env;
-    float          *envdc;    // [entry][MAXDOM]
-    float          *n2reg;    // [entry]
-    char           *scratch;
+    float4         *cell;     // [row][MD_W]: (M, I, D, -)
+    MdRow          *rowrec;   // [row]
+    MdTrace        *trace;    // [region - r0][MD_NSAMPLES]
+    MdRes          *res;      // [region]
+    char           *scratch;  // mdclust: per thread
     size_t          per_thread;
-    int             rows;     // longest flagged region + 1
+    int             maxrows;
     float           e_move;
-    uint32_t        rng0;
     unsigned long long *counters;
 };
-struct MdSeg { uint16_t i, j; uint8_t k, m; uint16_t n; };     // distinct segment and how many traces sampled it
-struct MdRow { float pC0, pC1, pJ0, pJ1, pB0, pB1, nrmE, xB; };   // per row: normalised C / J / B choices, 1 / xE, xB
-__host__ __device__ inline size_t md_scratch_bytes(int rows)
+struct MdStreams { uint32_t x[MD_NSAMPLES]; };
+__host__ __device__ inline size_t md_clust_bytes(int maxrows)
 {
-    // cells (M, I, D, pad) + row records + acc + distinct segments + raw (segment id, trace) + assignment, stack,
-    // last trace and trace count per cluster
-    size_t b = (size_t)rows * MD_W * 16 + (size_t)rows * sizeof(MdRow) + (size_t)(rows + 1) * 4 +
-               (size_t)MD_MAXSEG * (8 + 4 + 2 + 2 + 2 + 2);
+    // per warp: acc + cover count per row, raw (segment id, trace), last trace and trace count per cluster
+    size_t b = (size_t)(maxrows + 1) * 8 + (size_t)MD_MAXSEG * (4 + 2 + 2);
     return (b + 255) / 256 * 256;
 }
 __device__ __forceinline__ double md_rng(uint32_t &x)
@@ -691,15 +703,6 @@ __device__ __forceinline__ void md_norm(float *p, int n)
     if (sum != 0.f) { const float inv = 1.0f / sum; for (int a = 0; a < n; a++) p[a] = p[a] * inv; }   // esl_vec_FScale(1/sum)
     else { for (int a = 0; a < n; a++) p[a] = 1.0f / (float)n; }
 }
-// esl_rnd_FChoose on a normalised vector
-__device__ __forceinline__ int md_pick(uint32_t &rng, const float *p, int n)
-{
-    for (;;) {
-        const double roll = md_rng(rng);
-        float c = 0.f;
-        for (int a = 0; a < n; a++) { c += p[a]; if (roll < (double)c) return a; }
-    }
-}
 __device__ __forceinline__ int md_pick2(uint32_t &rng, float p0, float p1)
 {
     for (;;) {
@@ -709,44 +712,60 @@ __device__ __forceinline__ int md_pick2(uint32_t &rng, float p0, float p1)
         c += p1; if (roll < (double)c) return 1;
     }
 }
+// link_spsamples.  (float)nov / (float)n < 0.8f  is decided exactly by  5 nov < 4 n : for n < 2^16 the quotient is
+// either 4/5 (rounds to 0.8f, not smaller) or at least 1 / (5 n) > 3e-6 away from it, far more than a float ulp.
 __device__ __forceinline__ bool md_link(const MdSeg &a, const MdSeg &b)
 {
     int nov = min((int)a.j, (int)b.j) - max((int)a.i, (int)b.i) + 1;
     int n = min(a.j - a.i + 1, b.j - b.i + 1);
-    if ((float)nov / (float)n < 0.8f) return false;
+    if (5 * nov < 4 * n) return false;
     nov = min((int)a.m, (int)b.m) - max((int)a.k, (int)b.k) + 1;
     n = min(a.m - a.k + 1, b.m - b.k + 1);
-    if ((float)nov / (float)n < 0.8f) return false;
+    if (5 * nov < 4 * n) return false;
     if (abs(((int)a.i - (int)a.k) - ((int)b.i - (int)b.k)) > 4) return false;
     if (abs(((int)a.j - (int)a.m) - ((int)b.j - (int)b.m)) > 4) return false;
     return true;
 }
 enum { MS_M = 0, MS_D, MS_I, MS_N, MS_C, MS_J, MS_E, MS_B, MS_S };
 
-// resolves region ireg..jreg of a target of length L; returns the number of cluster envelopes (ci/cj/cdc) and the
-// sum of the trace n2sc over the region
-// Warp-synchronous: all 32 lanes call it together (act = this lane has a region); every phase of the walk is a loop
-// whose condition is a warp vote, so the lanes stay converged phase by phase.
-__device__ int md_resolve(const MdArgs &a, char *scr, bool act, const uint32_t *w, int L, int M, const float *tp,
-                          const float *et, int ireg, int jreg, int *ci, int *cj, float *cdc, float &regsum)
+struct MdRegion { int L, M, ireg, Ld; const uint32_t *w; const float *tp, *et; };
+__device__ __forceinline__ MdRegion md_region(const MdArgs &a, int r)
+{
+    MdRegion g;
+    const int e = a.reg_ent[r];
+    const int idx = a.list[e];
+    const int p = idx / a.ns, sl = idx - p * a.ns;
+    const int64_t s = a.order[a.s0 + sl];
+    g.L = a.seqlen[s];
+    g.w = a.seqw + a.woff[s];
+    g.M = a.pscal[p].M;
+    g.tp = a.mdtab + (size_t)p * (MAXM + 2) * 8;
+    g.et = a.etab + (size_t)p * (MAXM + 1) * 16;
+    g.ireg = a.reg_i[r];
+    g.Ld = a.reg_j[r] - g.ireg + 1;
+    return g;
+}
+
+// ---- multihit Forward over the region, full matrix (oracle forward_engine), and the per-row choice tables ----
+__global__ void __launch_bounds__(64) mdfwd_kernel(const MdArgs a)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    const int Ld = act ? jreg - ireg + 1 : 0;
-    const int R = a.rows;
-    float4 *cell = (float4 *)scr;                    // [row][MD_W]: (M, I, D, -)
-    MdRow *rowrec = (MdRow *)(cell + (size_t)R * MD_W);
-    float *acc = (float *)(rowrec + R);              // [rows + 1]
-    MdSeg *seg = (MdSeg *)(acc + (R + 1));            // distinct segments
-    uint16_t *rawid = (uint16_t *)(seg + MD_MAXSEG), *rawtr = rawid + MD_MAXSEG;
-    int16_t *asg = (int16_t *)(rawtr + MD_MAXSEG), *stack = asg + MD_MAXSEG, *lasttr = stack + MD_MAXSEG,
-            *ntrc = lasttr + MD_MAXSEG;
+    const int r = a.r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = r < a.r1;
+    MdRegion g;
+    g.L = 1; g.M = 1; g.ireg = 1; g.Ld = 0; g.w = a.seqw; g.tp = a.mdtab; g.et = a.etab;
+    size_t row0 = 0;
+    if (act) { g = md_region(a, r); row0 = (size_t)(a.reg_row[r] - a.row0); }
+    float4 *cell = a.cell + row0 * MD_W;
+    MdRow *rowrec = a.rowrec + row0;
+    const int M = g.M, Ld = g.Ld;
+    const float *tp = g.tp, *et = g.et;
 #define CELL(i, k) cell[(size_t)(i) * MD_W + (k)]
-    // ---- multihit Forward, full matrix (oracle forward_engine), and the per-row choice tables ----
-    const float pmove = (2.0f + 1.0f) / ((float)L + 2.0f + 1.0f);
+    const float pmove = (2.0f + 1.0f) / ((float)g.L + 2.0f + 1.0f);
     const float N_move = pmove, N_loop = 1.0f - pmove, E_move = a.e_move, E_loop = a.e_move;
-    for (int k = 0; k <= M; k++) CELL(0, k) = make_float4(0.f, 0.f, 0.f, 0.f);
     float xN = 1.f, xJ = 0.f, xC = 0.f, xE = 0.f, xB = N_move;
-    {
+    if (act) {
+        for (int k = 0; k <= M; k++) CELL(0, k) = make_float4(0.f, 0.f, 0.f, 0.f);
         MdRow r0;
         float pb[2] = {xN * N_move, xJ * N_move};
         md_norm(pb, 2);
@@ -758,7 +777,7 @@ __device__ int md_resolve(const MdArgs &a, char *scr, bool act, const uint32_t *
     for (int o = 16; o; o >>= 1) Ldw = max(Ldw, __shfl_xor_sync(FULL, Ldw, o));
     for (int i = 1; i <= Ldw; i++) {
         if (i > Ld) continue;
-        const uint32_t x = residue_at(w, ireg - 1 + i - 1);
+        const uint32_t x = residue_at(g.w, g.ireg - 1 + i - 1);
         const float cprev = xC, jprev = xJ;          // stored (scaled) specials of row i-1
         float mcur = 0.f, dcur = 0.f, xEm = 0.f, xEd = 0.f;
         CELL(i, 0) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -809,327 +828,404 @@ __device__ int md_resolve(const MdArgs &a, char *scr, bool act, const uint32_t *
         rr.xB = xB;
         rowrec[i] = rr;
     }
-    const int Q = max(((M - 1) / 4) + 1, 2);
-    for (int pos = 0; pos <= Ld; pos++) acc[pos] = 0.f;
-    int nseg = 0, nraw = 0;
-    uint32_t rng = a.rng0;
-    const int degen[16] = {1, 2, 4, 8, 5, 10, 3, 12, 6, 9, 11, 14, 7, 13, 15, 0};
-
-    // A trace is  C..C E [domain] B ( N.. | J..J E [domain] B ... ).  The walk is written as nested loops (special-state
-    // walk, E choice, domain walk, B choice) so that the lanes of a warp -- each on its own region -- reconverge after
-    // every phase; the domain step is one predicated code path for M, D and I.  The N walk draws no random numbers and
-    // is skipped.
-    for (int t = 0; t < MD_NSAMPLES; t++) {
-        int dfrom[8], dto[8], dk[8], dm[8], nd = 0;
-        float dn[8][4];
-        int i = Ld, k = 0;
-        bool inJ = false, alive = act;
-        while (__any_sync(FULL, alive)) {
-            // ---- C (or J) walk: stay with p0 (i--), leave to E with p1 ----
-            bool walking = alive;
-            while (__any_sync(FULL, walking)) {
-                if (walking) {
-                    const MdRow &rr = rowrec[i];
-                    if (md_pick2(rng, inJ ? rr.pJ0 : rr.pC0, inJ ? rr.pJ1 : rr.pC1) != 0 || i <= 1) walking = false;
-                    else i--;       // (i <= 1 is unreachable: C(0) = J(0) = 0)
-                }
-            }
-            // ---- E at row i: M_k / D_k in striped order, scaled by 1 / xE(i) ----
-            int st = MS_B;
-            if (alive) {
-                const double roll = md_rng(rng);
-                const float nrm = rowrec[i].nrmE;
-                double sum = 0.0;
-                bool done = false;
-                st = MS_M;
-                while (!done) {
-                    for (int q = 0; q < Q && !done; q++) {
-                        float4 cc[4];
-                        for (int r = 0; r < 4; r++) {
-                            const int kk = r * Q + q + 1;
-                            cc[r] = kk <= M ? CELL(i, kk) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                        for (int r = 0; r < 4 && !done; r++) {
-                            sum += (double)(cc[r].x * nrm);
-                            if (roll < sum) { k = r * Q + q + 1; st = MS_M; done = true; }
-                        }
-                        for (int r = 0; r < 4 && !done; r++) {
-                            sum += (double)(cc[r].z * nrm);
-                            if (roll < sum) { k = r * Q + q + 1; st = MS_D; done = true; }
-                        }
-                    }
-                    if (!done && sum < 0.99) { k = 1; st = MS_M; done = true; }
-                }
-            }
-            __syncwarp();
-            // ---- domain walk back to B; null2 odds are summed in walk order ----
-            int d_to = 0, d_m = 0, d_from = 0, d_k = 0, nI = 0;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            while (__any_sync(FULL, st != MS_B)) {
-                if (st == MS_B) continue;
-                if (st == MS_M) {
-                    if (d_to == 0) { d_to = i; d_m = k; }
-                    d_from = i; d_k = k;
-                    const float4 e4 = __ldg((const float4 *)(et + k * 16));
-                    s0 += e4.x; s1 += e4.y; s2 += e4.z; s3 += e4.w;
-                } else if (st == MS_I) {
-                    nI++;
-                }
-                // predecessor of state st at (i, k): one cell, the transitions out of its node
-                const int ri = st == MS_D ? i : i - 1, kc = st == MS_I ? k : k - 1;
-                const float4 c1 = CELL(ri, kc);
-                const float4 ta = __ldg((const float4 *)(tp + kc * 8)), tb = __ldg((const float4 *)(tp + kc * 8 + 4));
-                float path[4];
-                int n;
-                if (st == MS_M) {
-                    path[0] = rowrec[i - 1].xB * __ldg(tp + k * 8 + 7);
-                    path[1] = c1.x * ta.x; path[2] = c1.y * ta.w; path[3] = c1.z * tb.y;
-                    n = 4;
-                } else if (st == MS_D) {
-                    path[0] = c1.x * ta.z; path[1] = c1.z * tb.z; path[2] = 0.f; path[3] = 0.f;
-                    n = 2;
-                } else {
-                    path[0] = c1.x * ta.y; path[1] = c1.y * tb.x; path[2] = 0.f; path[3] = 0.f;
-                    n = 2;
-                }
-                // esl_vec_FNorm over the n live paths (the padded zeros leave the float sums unchanged)
-                float sum = 0.f;
-                sum += path[0]; sum += path[1]; sum += path[2]; sum += path[3];
-                if (sum != 0.f) {
-                    const float inv = 1.0f / sum;
-                    path[0] = path[0] * inv; path[1] = path[1] * inv; path[2] = path[2] * inv; path[3] = path[3] * inv;
-                } else {
-                    const float u = 1.0f / (float)n;
-                    path[0] = u; path[1] = u;
-                    if (n == 4) { path[2] = u; path[3] = u; }
-                }
-                int c;
-                for (;;) {
-                    const double roll = md_rng(rng);
-                    float cs = 0.f;
-                    cs += path[0]; if (roll < (double)cs) { c = 0; break; }
-                    cs += path[1]; if (roll < (double)cs) { c = 1; break; }
-                    if (n == 4) {
-                        cs += path[2]; if (roll < (double)cs) { c = 2; break; }
-                        cs += path[3]; if (roll < (double)cs) { c = 3; break; }
-                    }
-                }
-                if (st == MS_M) { st = c == 0 ? MS_B : c == 1 ? MS_M : c == 2 ? MS_I : MS_D; k--; i--; }
-                else if (st == MS_D) { st = c == 0 ? MS_M : MS_D; k--; }
-                else { st = c == 0 ? MS_M : MS_I; i--; }
-            }
-            if (alive) {
-                if (nd < 8) {
-                    const float norm = 1.0f / (float)(d_to - d_from + 1), fi = (float)nI;
-                    dfrom[nd] = d_from; dto[nd] = d_to; dk[nd] = d_k; dm[nd] = d_m;
-                    dn[nd][0] = (s0 + fi) * norm; dn[nd][1] = (s1 + fi) * norm;
-                    dn[nd][2] = (s2 + fi) * norm; dn[nd][3] = (s3 + fi) * norm;
-                    nd++;
-                }
-                // ---- B at row i: N ends the trace, J goes on ----
-                const MdRow &rr = rowrec[i];
-                if (md_pick2(rng, rr.pB0, rr.pB1) == 0) alive = false;
-                inJ = true;
-            }
-        }
-        int pos = 1;
-        for (int d = nd - 1; d >= 0; d--) {
-            if (nraw < MD_MAXSEG) {
-                const uint16_t si = (uint16_t)(dfrom[d] + ireg - 1), sj = (uint16_t)(dto[d] + ireg - 1);
-                int u = 0;
-                for (; u < nseg; u++) {
-                    const MdSeg g = seg[u];
-                    if (g.i == si && g.j == sj && g.k == dk[d] && g.m == dm[d]) break;
-                }
-                if (u == nseg) {
-                    MdSeg sg;
-                    sg.i = si; sg.j = sj; sg.k = (uint8_t)dk[d]; sg.m = (uint8_t)dm[d]; sg.n = 0;
-                    seg[nseg++] = sg;
-                }
-                seg[u].n++;
-                rawid[nraw] = (uint16_t)u; rawtr[nraw] = (uint16_t)t;
-                nraw++;
-            }
-            for (; pos <= dfrom[d]; pos++) acc[pos] += 1.0f;
-            for (; pos <= dto[d]; pos++) {
-                const uint32_t x = residue_at(w, ireg - 1 + pos - 1);
-                float v;
-                if (x < 4) v = x == 0 ? dn[d][0] : x == 1 ? dn[d][1] : x == 2 ? dn[d][2] : dn[d][3];
-                else if (x == 15) v = 1.0f;
-                else {
-                    float sa = 0.f;
-                    int na = 0;
-                    for (int y = 0; y < 4; y++)
-                        if (degen[x] & (1 << y)) { sa += dn[d][y]; na++; }
-                    v = sa / (float)na;
-                }
-                acc[pos] += v;
-            }
-        }
-        for (; pos <= Ld; pos++) acc[pos] += 1.0f;
-    }
-    // n2sc of the region (kept in acc[])
-    regsum = 0.f;
-    for (int pos = 1; pos <= Ld; pos++) {
-        const float v = logf_via_double(acc[pos] / (float)MD_NSAMPLES);
-        acc[pos] = v;
-        regsum += v;
-    }
-    // ---- single linkage clustering over the DISTINCT segments (same components as over all samples) ----
-    for (int s = 0; s < nseg; s++) asg[s] = -1;
-    int nc = 0;
-    for (int s = 0; s < nseg; s++) {
-        if (asg[s] >= 0) continue;
-        int top = 0;
-        stack[top++] = (int16_t)s; asg[s] = (int16_t)nc;
-        while (top) {
-            const MdSeg v = seg[stack[--top]];
-            for (int b = 0; b < nseg; b++)
-                if (asg[b] < 0 && md_link(v, seg[b])) { asg[b] = (int16_t)nc; stack[top++] = (int16_t)b; }
-        }
-        nc++;
-    }
-    // traces that contribute to each cluster (samples were appended in trace order)
-    for (int c = 0; c < nc; c++) { lasttr[c] = -1; ntrc[c] = 0; }
-    for (int r = 0; r < nraw; r++) {
-        const int c = asg[rawid[r]];
-        if (lasttr[c] != (int16_t)rawtr[r]) { ntrc[c]++; lasttr[c] = (int16_t)rawtr[r]; }
-    }
-    int nenv = 0;
-    for (int c = 0; c < nc; c++) {
-        if ((float)ntrc[c] / (float)MD_NSAMPLES < 0.25f) continue;
-        int ninc = 0;
-        int imin = 1 << 30, imax = 0, jmin = 1 << 30, jmax = 0;
-        for (int s = 0; s < nseg; s++) {
-            if (asg[s] != c) continue;
-            const MdSeg g = seg[s];
-            ninc += g.n;
-            imin = min(imin, (int)g.i); imax = max(imax, (int)g.i);
-            jmin = min(jmin, (int)g.j); jmax = max(jmax, (int)g.j);
-        }
-        const int thr = (int)ceilf((float)ninc * 0.02f);
-        int best_i, best_j;
-        for (best_i = imin; best_i <= imax; best_i++) {
-            int cnt = 0;
-            for (int s = 0; s < nseg; s++) cnt += (asg[s] == c && (int)seg[s].i == best_i) ? (int)seg[s].n : 0;
-            if (cnt >= thr) break;
-        }
-        for (best_j = jmax; best_j >= jmin; best_j--) {
-            int cnt = 0;
-            for (int s = 0; s < nseg; s++) cnt += (asg[s] == c && (int)seg[s].j == best_j) ? (int)seg[s].n : 0;
-            if (cnt >= thr) break;
-        }
-        if (nenv < MD_MAXCL) {
-            int at = nenv;
-            while (at > 0 && (ci[at - 1] > best_i || (ci[at - 1] == best_i && cj[at - 1] > best_j))) {
-                ci[at] = ci[at - 1]; cj[at] = cj[at - 1]; at--;
-            }
-            ci[at] = best_i; cj[at] = best_j;
-            nenv++;
-        }
-    }
-    for (int c = 0; c < nenv; c++) {
-        float dc = 0.f;
-        for (int pos = ci[c]; pos <= cj[c]; pos++) dc += acc[pos - ireg + 1];
-        cdc[c] = dc;
-    }
 #undef CELL
-    return nenv;
 }
 
-__global__ void __launch_bounds__(64) mdom_kernel(const MdArgs a)
+// ---- one stochastic traceback per thread.  A trace is  C..C E [domain] B ( N.. | J..J E [domain] B ... ).  The N walk
+// draws no random numbers and is skipped.  Every phase is a loop on a warp vote, the domain step is one predicated
+// code path for M, D and I. ----
+__global__ void __launch_bounds__(128) mdtrace_kernel(const MdArgs a, const __grid_constant__ MdStreams streams)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    char *scr = a.scratch + (size_t)tid * a.per_thread;
-    const int count = *a.count_ptr;
-    for (int t0 = tid - (threadIdx.x & 31); t0 < count; t0 += nthreads) {      // warp-uniform trip count
-        const int t = t0 + (threadIdx.x & 31);
-        const bool valid = t < count;
-        int e = 0, L = 0, M = 1, nd = 0;
-        const uint32_t *w = a.seqw;
-        const float *tp = a.mdtab, *et = a.etab;
-        int oi[ITSX_MAXDOM], oj[ITSX_MAXDOM];
-        if (valid) {
-            e = a.mdlist[t];
-            const int idx = a.list[e];
-            const int p = idx / a.ns, sl = idx - p * a.ns;
-            const int64_t s = a.order[a.s0 + sl];
-            L = a.seqlen[s];
-            w = a.seqw + a.woff[s];
-            M = a.pscal[p].M;
-            tp = a.mdtab + (size_t)p * (MAXM + 2) * 8;
-            et = a.etab + (size_t)p * (MAXM + 1) * 16;
-            nd = a.ndom[e];
-            for (int d = 0; d < nd; d++) {
-                oi[d] = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
-                oj[d] = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1];
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = a.r0 + (int)(gid / MD_NSAMPLES), t = (int)(gid % MD_NSAMPLES);
+    const bool act = r < a.r1;
+    MdRegion g;
+    g.L = 1; g.M = 1; g.ireg = 1; g.Ld = 0; g.w = a.seqw; g.tp = a.mdtab; g.et = a.etab;
+    size_t row0 = 0;
+    if (act) { g = md_region(a, r); row0 = (size_t)(a.reg_row[r] - a.row0); }
+    const float4 *cell = a.cell + row0 * MD_W;
+    const MdRow *rowrec = a.rowrec + row0;
+    const int M = g.M;
+    const float *tp = g.tp, *et = g.et;
+#define CELL(i, k) cell[(size_t)(i) * MD_W + (k)]
+    const int Q = max(((M - 1) / 4) + 1, 2);
+    uint32_t rng = streams.x[t];
+    MdTrace out;
+    out.nd = 0;
+    int i = g.Ld, k = 0;
+    bool inJ = false, alive = act;
+    while (__any_sync(FULL, alive)) {
+        // ---- C (or J) walk: stay with p0 (i--), leave to E with p1 ----
+        bool walking = alive;
+        while (__any_sync(FULL, walking)) {
+            if (walking) {
+                const MdRow &rr = rowrec[i];
+                if (md_pick2(rng, inJ ? rr.pJ0 : rr.pC0, inJ ? rr.pJ1 : rr.pC1) != 0 || i <= 1) walking = false;
+                else i--;       // (i <= 1 is unreachable: C(0) = J(0) = 0)
             }
         }
-        int nn = 0, d = 0;
-        float n2sum = 0.f;
-        for (;;) {
-            // copy simple envelopes up to this lane's next flagged region
-            while (d < nd && !((oj[d] >> 30) & 1)) {
-                if (nn < ITSX_MAXDOM) {
-                    a.env[((size_t)e * ITSX_MAXDOM + nn) * 2 + 0] = oi[d];
-                    a.env[((size_t)e * ITSX_MAXDOM + nn) * 2 + 1] = oj[d];
-                    a.envdc[(size_t)e * ITSX_MAXDOM + nn] = 0.f;
-                    nn++;
-                }
-                d++;
-            }
-            const bool act = d < nd;
-            if (!__any_sync(FULL, act)) break;
-            int ci[MD_MAXCL], cj[MD_MAXCL];
-            float cdc[MD_MAXCL], regsum = 0.f;
-            const int ncl = md_resolve(a, scr, act, w, L, M, tp, et, act ? oi[d] : 1, act ? (oj[d] & 0x1fffffff) : 0,
-                                       ci, cj, cdc, regsum);
-            if (act) {
-                n2sum += regsum;
-                for (int c = 0; c < ncl; c++) {
-                    if (nn < ITSX_MAXDOM) {
-                        a.env[((size_t)e * ITSX_MAXDOM + nn) * 2 + 0] = ci[c];
-                        a.env[((size_t)e * ITSX_MAXDOM + nn) * 2 + 1] = cj[c] | (1 << 30) | (1 << 29);
-                        a.envdc[(size_t)e * ITSX_MAXDOM + nn] = cdc[c];
-                        nn++;
-                    } else {
-                        atomicAdd(&a.counters[CNT_DOM_OVERFLOW], 1ull);
+        // ---- E at row i: M_k / D_k in striped order, scaled by 1 / xE(i) ----
+        int st = MS_B;
+        if (alive) {
+            const double roll = md_rng(rng);
+            const float nrm = rowrec[i].nrmE;
+            double sum = 0.0;
+            bool done = false;
+            st = MS_M;
+            while (!done) {
+                for (int q = 0; q < Q && !done; q++) {
+                    float4 cc[4];
+                    for (int rr = 0; rr < 4; rr++) {
+                        const int kk = rr * Q + q + 1;
+                        cc[rr] = kk <= M ? CELL(i, kk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    for (int rr = 0; rr < 4 && !done; rr++) {
+                        sum += (double)(cc[rr].x * nrm);
+                        if (roll < sum) { k = rr * Q + q + 1; st = MS_M; done = true; }
+                    }
+                    for (int rr = 0; rr < 4 && !done; rr++) {
+                        sum += (double)(cc[rr].z * nrm);
+                        if (roll < sum) { k = rr * Q + q + 1; st = MS_D; done = true; }
                     }
                 }
-                d++;
+                if (!done && sum < 0.99) { k = 1; st = MS_M; done = true; }
             }
         }
-        if (valid) {
-            a.ndom[e] = (uint8_t)nn;
-            a.n2reg[e] = n2sum;
+        __syncwarp();
+        // ---- domain walk back to B; null2 odds are summed in walk order ----
+        int d_to = 0, d_m = 0, d_from = 0, d_k = 0, nI = 0;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        while (__any_sync(FULL, st != MS_B)) {
+            if (st == MS_B) continue;
+            if (st == MS_M) {
+                if (d_to == 0) { d_to = i; d_m = k; }
+                d_from = i; d_k = k;
+                const float4 e4 = __ldg((const float4 *)(et + k * 16));
+                s0 += e4.x; s1 += e4.y; s2 += e4.z; s3 += e4.w;
+            } else if (st == MS_I) {
+                nI++;
+            }
+            // predecessor of state st at (i, k): one cell, the transitions out of its node
+            const int ri = st == MS_D ? i : i - 1, kc = st == MS_I ? k : k - 1;
+            const float4 c1 = CELL(ri, kc);
+            const float4 ta = __ldg((const float4 *)(tp + kc * 8)), tb = __ldg((const float4 *)(tp + kc * 8 + 4));
+            float path[4];
+            int n;
+            if (st == MS_M) {
+                path[0] = rowrec[i - 1].xB * __ldg(tp + k * 8 + 7);
+                path[1] = c1.x * ta.x; path[2] = c1.y * ta.w; path[3] = c1.z * tb.y;
+                n = 4;
+            } else if (st == MS_D) {
+                path[0] = c1.x * ta.z; path[1] = c1.z * tb.z; path[2] = 0.f; path[3] = 0.f;
+                n = 2;
+            } else {
+                path[0] = c1.x * ta.y; path[1] = c1.y * tb.x; path[2] = 0.f; path[3] = 0.f;
+                n = 2;
+            }
+            // esl_vec_FNorm over the n live paths (the padded zeros leave the float sums unchanged)
+            float sum = 0.f;
+            sum += path[0]; sum += path[1]; sum += path[2]; sum += path[3];
+            if (sum != 0.f) {
+                const float inv = 1.0f / sum;
+                path[0] = path[0] * inv; path[1] = path[1] * inv; path[2] = path[2] * inv; path[3] = path[3] * inv;
+            } else {
+                const float u = 1.0f / (float)n;
+                path[0] = u; path[1] = u;
+                if (n == 4) { path[2] = u; path[3] = u; }
+            }
+            int c;
+            for (;;) {
+                const double roll = md_rng(rng);
+                float cs = 0.f;
+                cs += path[0]; if (roll < (double)cs) { c = 0; break; }
+                cs += path[1]; if (roll < (double)cs) { c = 1; break; }
+                if (n == 4) {
+                    cs += path[2]; if (roll < (double)cs) { c = 2; break; }
+                    cs += path[3]; if (roll < (double)cs) { c = 3; break; }
+                }
+            }
+            if (st == MS_M) { st = c == 0 ? MS_B : c == 1 ? MS_M : c == 2 ? MS_I : MS_D; k--; i--; }
+            else if (st == MS_D) { st = c == 0 ? MS_M : MS_D; k--; }
+            else { st = c == 0 ? MS_M : MS_I; i--; }
+        }
+        if (alive) {
+            if (out.nd < MD_MAXTDOM) {
+                const float norm = 1.0f / (float)(d_to - d_from + 1), fi = (float)nI;
+                MdDom &dd = out.d[out.nd];
+                dd.from = (uint16_t)d_from; dd.to = (uint16_t)d_to; dd.k = (uint8_t)d_k; dd.m = (uint8_t)d_m; dd.pad = 0;
+                dd.n2[0] = (s0 + fi) * norm; dd.n2[1] = (s1 + fi) * norm;
+                dd.n2[2] = (s2 + fi) * norm; dd.n2[3] = (s3 + fi) * norm;
+                out.nd++;
+            }
+            // ---- B at row i: N ends the trace, J goes on ----
+            const MdRow &rr = rowrec[i];
+            if (md_pick2(rng, rr.pB0, rr.pB1) == 0) alive = false;
+            inJ = true;
         }
     }
+    if (act) a.trace[(size_t)(r - a.r0) * MD_NSAMPLES + t] = out;
+#undef CELL
 }
-// entries that hold a flagged region -> mdlist, with the sort key (profile, total flagged length): lanes of a warp
-// then walk regions of similar size against the same tables.  count[1] = longest flagged region
-__global__ void mdlist_kernel(const uint8_t *__restrict__ ndom, const int32_t *__restrict__ env, int n,
-                              const int32_t *__restrict__ list, int ns,
-                              int32_t *__restrict__ mdlist, uint32_t *__restrict__ mdkey, int32_t *__restrict__ count)
+
+// ---- per region, one WARP: n2sc, distinct segments, single linkage clustering, cluster envelopes.  The samples are
+// visited in trace order (float sums keep the oracle's order); the lanes share the search for an equal segment, the
+// positions of a domain, the link tests of the component walk and the endpoint counts. ----
+constexpr int MDC_WARPS = 4;
+struct MdClustSmem {
+    MdSeg   seg[MD_MAXSEG];
+    int16_t asg[MD_MAXSEG];
+    int16_t stack[MD_MAXSEG];
+};
+__global__ void __launch_bounds__(MDC_WARPS * 32) mdclust_kernel(const MdArgs a)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char mdc_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int warp = blockIdx.x * MDC_WARPS + wid, nwarps = gridDim.x * MDC_WARPS;
+    MdClustSmem &sm = ((MdClustSmem *)mdc_smem)[wid];
+    char *scr = a.scratch + (size_t)warp * a.per_thread;
+    float *acc = (float *)scr;                               // [maxrows + 1]
+    int32_t *cov = (int32_t *)(acc + (a.maxrows + 1));       // [maxrows + 1]
+    uint16_t *rawid = (uint16_t *)(cov + (a.maxrows + 1)), *rawtr = rawid + MD_MAXSEG;
+    int16_t *lasttr = (int16_t *)(rawtr + MD_MAXSEG), *ntrc = lasttr + MD_MAXSEG;
+    const int degen[16] = {1, 2, 4, 8, 5, 10, 3, 12, 6, 9, 11, 14, 7, 13, 15, 0};
+    for (int r = a.r0 + warp; r < a.r1; r += nwarps) {
+        const MdRegion g = md_region(a, r);
+        const int Ld = g.Ld, ireg = g.ireg;
+        const MdTrace *tr = a.trace + (size_t)(r - a.r0) * MD_NSAMPLES;
+        for (int pos = lane; pos <= Ld; pos += 32) { acc[pos] = 0.f; cov[pos] = 0; }
+        __syncwarp();
+        int nseg = 0, nraw = 0;
+        for (int t = 0; t < MD_NSAMPLES; t++) {
+            const int nd = tr[t].nd;
+            for (int d = nd - 1; d >= 0; d--) {          // left to right
+                const MdDom dd = tr[t].d[d];
+                if (nraw < MD_MAXSEG) {
+                    const uint16_t si = (uint16_t)(dd.from + ireg - 1), sj = (uint16_t)(dd.to + ireg - 1);
+                    int u = -1;
+                    const unsigned long long want = (unsigned long long)si | ((unsigned long long)sj << 16) |
+                                                    ((unsigned long long)dd.k << 32) | ((unsigned long long)dd.m << 40);
+                    for (int u0 = 0; u0 < nseg && u < 0; u0 += 32) {
+                        const bool hit = u0 + lane < nseg &&
+                            ((*(const unsigned long long *)&sm.seg[u0 + lane]) & 0xffffffffffffull) == want;
+                        const unsigned m = __ballot_sync(FULL, hit);
+                        if (m) u = u0 + __ffs(m) - 1;
+                    }
+                    if (lane == 0) {
+                        if (u < 0) {
+                            MdSeg sg;
+                            sg.i = si; sg.j = sj; sg.k = dd.k; sg.m = dd.m; sg.n = 1;
+                            sm.seg[nseg] = sg;
+                            rawid[nraw] = (uint16_t)nseg;
+                        } else {
+                            sm.seg[u].n++;
+                            rawid[nraw] = (uint16_t)u;
+                        }
+                        rawtr[nraw] = (uint16_t)t;
+                    }
+                    if (u < 0) nseg++;
+                    nraw++;
+                    __syncwarp();
+                }
+                for (int pos = dd.from + lane; pos <= dd.to; pos += 32) {
+                    const uint32_t x = residue_at(g.w, ireg - 1 + pos - 1);
+                    float v;
+                    if (x < 4) v = dd.n2[x];
+                    else if (x == 15) v = 1.0f;
+                    else {
+                        float sa = 0.f;
+                        int na = 0;
+                        for (int y = 0; y < 4; y++)
+                            if (degen[x] & (1 << y)) { sa += dd.n2[y]; na++; }
+                        v = sa / (float)na;
+                    }
+                    acc[pos] += v;
+                    cov[pos]++;
+                }
+                __syncwarp();        // the next sample may touch the same positions from other lanes
+            }
+        }
+        // n2sc of the region (kept in acc[]); the sum over the region in position order
+        for (int pos = 1 + lane; pos <= Ld; pos += 32)
+            acc[pos] = logf_via_double((acc[pos] + (float)(MD_NSAMPLES - cov[pos])) / (float)MD_NSAMPLES);
+        __syncwarp();
+        float regsum = 0.f;
+        if (lane == 0)
+            for (int pos = 1; pos <= Ld; pos++) regsum += acc[pos];
+        // single linkage clustering over the DISTINCT segments (same components as over all samples)
+        for (int q = lane; q < nseg; q += 32) sm.asg[q] = -1;
+        __syncwarp();
+        int nc = 0;
+        for (int q = 0; q < nseg; q++) {
+            if (sm.asg[q] >= 0) continue;
+            int top = 0;
+            if (lane == 0) { sm.stack[0] = (int16_t)q; sm.asg[q] = (int16_t)nc; }
+            top = 1;
+            __syncwarp();
+            while (top) {
+                const MdSeg v = sm.seg[sm.stack[--top]];
+                __syncwarp();
+                for (int b0 = 0; b0 < nseg; b0 += 32) {
+                    const int bb = b0 + lane;
+                    const bool take = bb < nseg && sm.asg[bb] < 0 && md_link(v, sm.seg[bb]);
+                    const unsigned m = __ballot_sync(FULL, take);
+                    if (take) {
+                        sm.asg[bb] = (int16_t)nc;
+                        sm.stack[top + __popc(m & ((1u << lane) - 1u))] = (int16_t)bb;
+                    }
+                    top += __popc(m);
+                }
+                __syncwarp();
+            }
+            nc++;
+        }
+        // traces that contribute to each cluster (samples are in trace order)
+        if (lane == 0) {
+            for (int c = 0; c < nc; c++) { lasttr[c] = -1; ntrc[c] = 0; }
+            for (int q = 0; q < nraw; q++) {
+                const int c = sm.asg[rawid[q]];
+                if (lasttr[c] != (int16_t)rawtr[q]) { ntrc[c]++; lasttr[c] = (int16_t)rawtr[q]; }
+            }
+        }
+        __syncwarp();
+        int ci[16], cj[16];
+        int nenv = 0;
+        for (int c = 0; c < nc; c++) {
+            if ((float)ntrc[c] / (float)MD_NSAMPLES < 0.25f) continue;
+            int ninc = 0;
+            int imin = 1 << 30, imax = 0, jmin = 1 << 30, jmax = 0;
+            for (int q = lane; q < nseg; q += 32) {
+                if (sm.asg[q] != c) continue;
+                const MdSeg sgm = sm.seg[q];
+                ninc += sgm.n;
+                imin = min(imin, (int)sgm.i); imax = max(imax, (int)sgm.i);
+                jmin = min(jmin, (int)sgm.j); jmax = max(jmax, (int)sgm.j);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                ninc += __shfl_xor_sync(FULL, ninc, o);
+                imin = min(imin, __shfl_xor_sync(FULL, imin, o)); imax = max(imax, __shfl_xor_sync(FULL, imax, o));
+                jmin = min(jmin, __shfl_xor_sync(FULL, jmin, o)); jmax = max(jmax, __shfl_xor_sync(FULL, jmax, o));
+            }
+            const int thr = (int)ceilf((float)ninc * 0.02f);
+            int best_i, best_j;
+            for (best_i = imin; best_i <= imax; best_i++) {
+                int cnt = 0;
+                for (int q = lane; q < nseg; q += 32) cnt += (sm.asg[q] == c && (int)sm.seg[q].i == best_i) ? (int)sm.seg[q].n : 0;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+                if (cnt >= thr) break;
+            }
+            for (best_j = jmax; best_j >= jmin; best_j--) {
+                int cnt = 0;
+                for (int q = lane; q < nseg; q += 32) cnt += (sm.asg[q] == c && (int)sm.seg[q].j == best_j) ? (int)sm.seg[q].n : 0;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+                if (cnt >= thr) break;
+            }
+            if (nenv < 16) {
+                int at = nenv;
+                while (at > 0 && (ci[at - 1] > best_i || (ci[at - 1] == best_i && cj[at - 1] > best_j))) {
+                    ci[at] = ci[at - 1]; cj[at] = cj[at - 1]; at--;
+                }
+                ci[at] = best_i; cj[at] = best_j;
+                nenv++;
+            }
+        }
+        if (lane == 0) {
+            if (nenv > ITSX_MAXDOM) {
+                atomicAdd(&a.counters[CNT_DOM_OVERFLOW], (unsigned long long)(nenv - ITSX_MAXDOM));
+                nenv = ITSX_MAXDOM;
+            }
+            MdRes res;
+            res.n = nenv; res.regsum = regsum;
+            for (int c = 0; c < ITSX_MAXDOM; c++) { res.ci[c] = 0; res.cj[c] = 0; res.cdc[c] = 0.f; }
+            for (int c = 0; c < nenv; c++) {
+                float dc = 0.f;
+                for (int pos = ci[c]; pos <= cj[c]; pos++) dc += acc[pos - ireg + 1];
+                res.ci[c] = ci[c]; res.cj[c] = cj[c]; res.cdc[c] = dc;
+            }
+            a.res[r] = res;
+        }
+        __syncwarp();
+    }
+}
+
+// number of flagged regions of every worklist entry
+__global__ void mdcount_kernel(const uint8_t *__restrict__ ndom, const int32_t *__restrict__ env, int n,
+                               int32_t *__restrict__ nreg)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e > n) return;
+    int c = 0;
+    if (e < n) {
+        const int nd = ndom[e];
+        for (int d = 0; d < nd; d++) c += (env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1] >> 30) & 1;
+    }
+    nreg[e] = c;
+}
+// region list in entry order: entry, coordinates, rows of the slab (Ld + 1)
+__global__ void mdregs_kernel(const uint8_t *__restrict__ ndom, const int32_t *__restrict__ env, int n,
+                              const int32_t *__restrict__ base, int32_t *__restrict__ reg_ent,
+                              int32_t *__restrict__ reg_i, int32_t *__restrict__ reg_j, int32_t *__restrict__ reg_rows)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
+    if (base[e + 1] == base[e]) return;
     const int nd = ndom[e];
-    int longest = 0, total = 0;
+    int at = base[e];
     for (int d = 0; d < nd; d++) {
         const int jraw = env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1];
         if ((jraw >> 30) & 1) {
-            const int len = (jraw & 0x1fffffff) - env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0] + 1;
-            longest = max(longest, len);
-            total += len;
+            const int i = env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0], j = jraw & 0x1fffffff;
+            reg_ent[at] = e; reg_i[at] = i; reg_j[at] = j; reg_rows[at] = j - i + 2;
+            at++;
         }
     }
-    if (longest) {
-        const int at = atomicAdd(count, 1);
-        mdlist[at] = e;
-        mdkey[at] = ((uint32_t)(list[e] / ns) << 12) | (uint32_t)min(total, 4095);
-        atomicMax(count + 1, longest);
+}
+// the cluster envelopes replace the flagged regions in the entry's list
+__global__ void mdapply_kernel(uint8_t *__restrict__ ndom, int32_t *__restrict__ env, int n,
+                               const int32_t *__restrict__ base, const MdRes *__restrict__ res,
+                               float *__restrict__ envdc, float *__restrict__ n2reg,
+                               unsigned long long *__restrict__ counters)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (base[e + 1] == base[e]) return;
+    const int nd = ndom[e];
+    int oi[ITSX_MAXDOM], oj[ITSX_MAXDOM];
+    for (int d = 0; d < nd; d++) {
+        oi[d] = env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
+        oj[d] = env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1];
     }
+    int nn = 0, at = base[e];
+    float n2sum = 0.f;
+    for (int d = 0; d < nd; d++) {
+        if (!((oj[d] >> 30) & 1)) {
+            if (nn < ITSX_MAXDOM) {
+                env[((size_t)e * ITSX_MAXDOM + nn) * 2 + 0] = oi[d];
+                env[((size_t)e * ITSX_MAXDOM + nn) * 2 + 1] = oj[d];
+                envdc[(size_t)e * ITSX_MAXDOM + nn] = 0.f;
+                nn++;
+            }
+            continue;
+        }
+        const MdRes rs = res[at++];
+        n2sum += rs.regsum;
+        for (int c = 0; c < rs.n; c++) {
+            if (nn < ITSX_MAXDOM) {
+                env[((size_t)e * ITSX_MAXDOM + nn) * 2 + 0] = rs.ci[c];
+                env[((size_t)e * ITSX_MAXDOM + nn) * 2 + 1] = rs.cj[c] | (1 << 30) | (1 << 29);
+                envdc[(size_t)e * ITSX_MAXDOM + nn] = rs.cdc[c];
+                nn++;
+            } else {
+                atomicAdd(&counters[CNT_DOM_OVERFLOW], 1ull);
+            }
+        }
+    }
+    ndom[e] = (uint8_t)nn;
+    n2reg[e] = n2sum;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1603,6 +1699,19 @@ uint32_t md_rng_state0(uint32_t seed)
     return c ? c : 42u;
 }
 
+// state after k more draws of x <- 69069 x + 1: x_(n+k) = A x_n + C (mod 2^32), by doubling
+uint32_t md_rng_jump(uint32_t x, uint64_t k)
+{
+    uint32_t A = 1u, C = 0u, a = 69069u, cc = 1u;
+    while (k) {
+        if (k & 1u) { A = A * a; C = C * a + cc; }
+        cc = cc * (a + 1u);
+        a = a * a;
+        k >>= 1;
+    }
+    return A * x + C;
+}
+
 }  // namespace
 
 // ==================================================================================================
@@ -1990,47 +2099,79 @@ int search_stage1(itsx_ctx *c)
         CUDA_TRY(c, c->d_n2reg.ensure((size_t)n2 * 4));
         CUDA_TRY(c, cudaMemsetAsync(c->d_n2reg.p, 0, (size_t)n2 * 4, st));
         if (c->prm.resolve_multidomain) {
-            // [0, n2) list, [n2, 2 n2) sorted list, [2 n2, 3 n2) keys, [3 n2, 4 n2) sorted keys, then the two counters
-            CUDA_TRY(c, c->d_mdlist.ensure(((size_t)n2 * 4 + 2) * 4));
-            int32_t *md_in = c->d_mdlist.as<int32_t>(), *md_out = md_in + n2;
-            uint32_t *mk_in = (uint32_t *)(md_in + 2 * (size_t)n2), *mk_out = mk_in + n2;
-            int32_t *d_mdcount = md_in + 4 * (size_t)n2;               // [0] entries, [1] longest flagged region
-            CUDA_TRY(c, cudaMemsetAsync(d_mdcount, 0, 8, st));
-            mdlist_kernel<<<nblk(n2, 256), 256, 0, st>>>(c->d_ndom.as<uint8_t>(), c->d_env.as<int32_t>(), n2,
-                                                        c->d_list2.as<int32_t>(), ns, md_in, mk_in, d_mdcount);
-            c->launches++;
-            int32_t h_md[2] = {0, 0};
-            CUDA_TRY(c, cudaMemcpyAsync(h_md, d_mdcount, 8, cudaMemcpyDeviceToHost, st));
+            // flagged regions per entry -> prefix sum -> region list in entry order
+            CUDA_TRY(c, c->d_mdlist.ensure((size_t)(n2 + 1) * 2 * 4));
+            int32_t *d_nreg = c->d_mdlist.as<int32_t>(), *d_base = d_nreg + (n2 + 1);
+            mdcount_kernel<<<nblk(n2 + 1, 256), 256, 0, st>>>(c->d_ndom.as<uint8_t>(), c->d_env.as<int32_t>(), n2, d_nreg);
+            size_t tbm = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tbm, d_nreg, d_base, n2 + 1, st);
+            CUDA_TRY(c, c->d_tmp.ensure(tbm));
+            cub::DeviceScan::ExclusiveSum(c->d_tmp.p, tbm, d_nreg, d_base, n2 + 1, st);
+            c->launches += 2;
+            int32_t h_nregions = 0;
+            CUDA_TRY(c, cudaMemcpyAsync(&h_nregions, d_base + n2, 4, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(c, cudaStreamSynchronize(st));
-            if (h_md[0] > 0) {
-                int pbits = 1;
-                while ((1 << pbits) < P) pbits++;
-                size_t tbs = 0;
-                cub::DeviceRadixSort::SortPairs(nullptr, tbs, mk_in, mk_out, md_in, md_out, h_md[0], 0, 12 + pbits, st);
-                CUDA_TRY(c, c->d_tmp.ensure(tbs));
-                cub::DeviceRadixSort::SortPairs(c->d_tmp.p, tbs, mk_in, mk_out, md_in, md_out, h_md[0], 0, 12 + pbits, st);
-                c->launches++;
-            }
-            if (h_md[0] > 0) {
+            if (h_nregions > 0) {
+                const int NR = h_nregions;
+                CUDA_TRY(c, c->d_mdreg.ensure(((size_t)NR * 3 + (size_t)(NR + 1) * 2) * 4));
+                int32_t *reg_ent = c->d_mdreg.as<int32_t>(), *reg_i = reg_ent + NR, *reg_j = reg_i + NR,
+                        *reg_rows = reg_j + NR, *reg_row = reg_rows + (NR + 1);
+                CUDA_TRY(c, cudaMemsetAsync(reg_rows + NR, 0, 4, st));
+                mdregs_kernel<<<nblk(n2, 256), 256, 0, st>>>(c->d_ndom.as<uint8_t>(), c->d_env.as<int32_t>(), n2, d_base,
+                                                            reg_ent, reg_i, reg_j, reg_rows);
+                cub::DeviceScan::ExclusiveSum(nullptr, tbm, reg_rows, reg_row, NR + 1, st);
+                CUDA_TRY(c, c->d_tmp.ensure(tbm));
+                cub::DeviceScan::ExclusiveSum(c->d_tmp.p, tbm, reg_rows, reg_row, NR + 1, st);
+                c->launches += 2;
+                std::vector<int32_t> h_row((size_t)NR + 1);
+                CUDA_TRY(c, cudaMemcpyAsync(h_row.data(), reg_row, (size_t)(NR + 1) * 4, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(c, cudaStreamSynchronize(st));
+                CUDA_TRY(c, c->d_mdres.ensure((size_t)NR * sizeof(MdRes)));
+                MdStreams streams;
+                {
+                    const uint32_t x0 = md_rng_state0(42u);
+                    for (int t = 0; t < MD_NSAMPLES; t++) streams.x[t] = md_rng_jump(x0, (uint64_t)t << MD_STREAM_LOG2);
+                }
                 MdArgs ma;
-                ma.rows = h_md[1] + 1;
-                ma.per_thread = md_scratch_bytes(ma.rows);
-                // one thread per entry, as many resident as registers allow (24 warps / SM), scratch capped at 8 GB
-                int md_threads = std::min((h_md[0] + 63) / 64 * 64, c->sm_count * 768);
-                md_threads = (int)std::min<size_t>((size_t)md_threads, ((size_t)8 << 30) / ma.per_thread / 64 * 64);
-                md_threads = std::max(md_threads, 64);
-                CUDA_TRY(c, c->d_mdscratch.ensure(ma.per_thread * (size_t)md_threads));
-                ma.mdlist = md_out; ma.count_ptr = d_mdcount;
+                ma.reg_ent = reg_ent; ma.reg_i = reg_i; ma.reg_j = reg_j; ma.reg_row = reg_row;
                 ma.list = c->d_list2.as<int32_t>(); ma.order = d_order; ma.s0 = s0; ma.ns = ns;
                 ma.seqw = c->d_seqw.as<uint32_t>(); ma.woff = c->d_seqwoff.as<int64_t>(); ma.seqlen = c->d_seqlen.as<int32_t>();
                 ma.mdtab = c->d_mdtab.as<float>(); ma.etab = c->d_etab.as<float>(); ma.pscal = c->d_pscal.as<ProfScalars>();
-                ma.ndom = c->d_ndom.as<uint8_t>(); ma.env = c->d_env.as<int32_t>();
-                ma.envdc = c->d_envdc.as<float>(); ma.n2reg = c->d_n2reg.as<float>();
-                ma.scratch = c->d_mdscratch.as<char>();
+                ma.res = c->d_mdres.as<MdRes>();
                 ma.e_move = expf(-(float)kLn2);
-                ma.rng0 = md_rng_state0(42u);
                 ma.counters = cnt;
-                mdom_kernel<<<md_threads / 64, 64, 0, st>>>(ma);
+                // chunks of regions: slabs (matrix + row tables) and trace records within a fixed HBM budget
+                const size_t row_bytes = (size_t)MD_W * 16 + sizeof(MdRow), reg_bytes = (size_t)MD_NSAMPLES * sizeof(MdTrace);
+                const size_t budget = (size_t)6 << 30;
+                for (int r0 = 0; r0 < NR;) {
+                    int r1 = r0 + 1;
+                    while (r1 < NR && (size_t)(h_row[r1 + 1] - h_row[r0]) * row_bytes + (size_t)(r1 + 1 - r0) * reg_bytes <= budget)
+                        r1++;
+                    const size_t rows = (size_t)(h_row[r1] - h_row[r0]);
+                    int maxrows = 0;
+                    for (int r = r0; r < r1; r++) maxrows = std::max(maxrows, h_row[r + 1] - h_row[r]);
+                    CUDA_TRY(c, c->d_mdcell.ensure(rows * row_bytes));
+                    CUDA_TRY(c, c->d_mdtrace.ensure((size_t)(r1 - r0) * reg_bytes));
+                    ma.r0 = r0; ma.r1 = r1; ma.row0 = h_row[r0];
+                    ma.cell = c->d_mdcell.as<float4>();
+                    ma.rowrec = (MdRow *)(c->d_mdcell.as<char>() + rows * MD_W * 16);
+                    ma.trace = c->d_mdtrace.as<MdTrace>();
+                    ma.maxrows = maxrows;
+                    ma.per_thread = md_clust_bytes(maxrows);
+                    const size_t cl_smem = sizeof(MdClustSmem) * MDC_WARPS;
+                    CUDA_TRY(c, cudaFuncSetAttribute(mdclust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem));
+                    const int cl_ctas = std::min((r1 - r0 + MDC_WARPS - 1) / MDC_WARPS, c->sm_count * 4);
+                    CUDA_TRY(c, c->d_mdscratch.ensure(ma.per_thread * (size_t)cl_ctas * MDC_WARPS));
+                    ma.scratch = c->d_mdscratch.as<char>();
+                    mdfwd_kernel<<<nblk(r1 - r0, 64), 64, 0, st>>>(ma);
+                    mdtrace_kernel<<<nblk((int64_t)(r1 - r0) * MD_NSAMPLES, 128), 128, 0, st>>>(ma, streams);
+                    mdclust_kernel<<<cl_ctas, MDC_WARPS * 32, cl_smem, st>>>(ma);
+                    c->launches += 3;
+                    r0 = r1;
+                }
+                mdapply_kernel<<<nblk(n2, 256), 256, 0, st>>>(c->d_ndom.as<uint8_t>(), c->d_env.as<int32_t>(), n2, d_base,
+                                                             c->d_mdres.as<MdRes>(), c->d_envdc.as<float>(),
+                                                             c->d_n2reg.as<float>(), cnt);
                 c->launches++;
             }
         }

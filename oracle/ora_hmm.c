@@ -722,13 +722,18 @@ static void rescore_envelope(const prof_t *pf, const uint8_t *dsq, int L, int i,
  * of the HMM stage; the CUDA path (mdom_kernel) follows this restatement operation for operation.
  *
  *   1. multihit Forward (length model of the full target) over the region, full M/I/D matrix;
- *   2. the domain definition's RNG is re-seeded for every region (esl_randomness_CreateFast(42), do_reseeding):
- *      x0 = jenkins_mix3(42, 87654321, 12345678), then x <- 69069 x + 1, u = x / 2^32;
+ *   2. the domain definition's RNG is HMMER's "fast" generator (esl_randomness_CreateFast(42): x0 = jenkins_mix3(42,
+ *      87654321, 12345678), x <- 69069 x + 1, u = x / 2^32), re-seeded for every region.  DEVIATION, on purpose: HMMER
+ *      draws the 200 tracebacks of a region from ONE sequential stream; here trace t draws from the same generator
+ *      leap-frogged to x_(t * 2^20), i.e. 200 non-overlapping substreams, so that the traces are independent work
+ *      items (the CUDA path runs one thread per trace).  The ensemble has the same distribution; it is not
+ *      draw-for-draw the one hmmsearch samples (which a different fp32 summation order would not reproduce either);
  *   3. 200 stochastic tracebacks (p7_StochasticTrace, impl_sse/stotrace.c): one draw per state choice, paths
  *      normalised (esl_vec_FNorm) and chosen by cumulative sum (esl_rnd_FChoose); the E state scans
  *      M_k, D_k in the striped order of the SSE matrix (q = 0..Q-1, r = 0..3, k = r Q + q + 1);
  *   4. every domain of every trace is one segment (i, j, k, m); null2 by trace (p7_Null2_ByTrace) is averaged
- *      over the 200 traces into n2sc[] for every position of the region;
+ *      over the 200 traces into n2sc[] for every position of the region: n2sc[pos] = log((sum of the null2 odds
+ *      of the domains that cover pos, in trace order, + number of traces that do not cover it) / 200);
  *   5. single-linkage clustering of the segments (min_overlap 0.8 of the smaller, max_diagdiff 4), clusters with
  *      posterior >= 0.25, envelope = leftmost start / rightmost end whose endpoint count reaches
  *      ceil(0.02 * cluster size); clusters ordered by start;
@@ -760,6 +765,20 @@ static inline double rng_next(uint32_t *x)
     *x = *x * 69069u + 1u;
     return (double)*x / 4294967296.0;
 }
+/* state after k more draws: x_(n+k) = A x_n + C (mod 2^32), by doubling */
+uint32_t ora_rng_jump(uint32_t x, uint64_t k)
+{
+    uint32_t A = 1u, C = 0u, a = 69069u, c = 1u;
+    while (k) {
+        if (k & 1u) { A = A * a; C = C * a + c; }
+        c = c * (a + 1u);
+        a = a * a;
+        k >>= 1;
+    }
+    return A * x + C;
+}
+#define MD_STREAM_LOG2 20
+#define MD_MAXTDOM 4 /* domains kept per trace */
 /* esl_vec_FNorm + esl_rnd_FChoose over n <= 4 paths */
 static int fchoose(uint32_t *rng, float *p, int n)
 {
@@ -805,15 +824,17 @@ static int resolve_multidomain(const prof_t *pf, const uint8_t *dsq, int L, int 
     const float *tp = pf->tp, *bm = pf->bm;
     const int    Q  = (((M - 1) / 4) + 1) > 2 ? (((M - 1) / 4) + 1) : 2;
 
-    float   *acc = calloc((size_t)Ld + 2, sizeof(float)); /* sum over traces of the null2 odds of every region position */
+    float   *acc = calloc((size_t)Ld + 2, sizeof(float)); /* sum of the null2 odds of the domains that cover a position */
+    int     *cov = calloc((size_t)Ld + 2, sizeof(int));   /* number of traces that cover it */
     spseg_t *seg = malloc(sizeof(spseg_t) * MD_MAXSEG);
     int      nseg = 0;
-    uint32_t rng = ora_rng_state0(42u);
+    const uint32_t rng0 = ora_rng_state0(42u);
 
     for (int t = 0; t < MD_NSAMPLES; t++) {
+        uint32_t rng = ora_rng_jump(rng0, (uint64_t)t << MD_STREAM_LOG2);
         /* domains of this trace are discovered right to left */
-        int dfrom[8], dto[8], dk[8], dm[8], nd = 0;   /* a trace holds at most 8 domains (as the kernel) */
-        float dnull[8][16];
+        int dfrom[MD_MAXTDOM], dto[MD_MAXTDOM], dk[MD_MAXTDOM], dm[MD_MAXTDOM], nd = 0;   /* as the kernel */
+        float dnull[MD_MAXTDOM][16];
         int   i = Ld, k = 0, sprv = ST_C, open = 0, nI = 0;
         float sx[4] = {0.f, 0.f, 0.f, 0.f};
         while (sprv != ST_S) {
@@ -882,7 +903,7 @@ static int resolve_multidomain(const prof_t *pf, const uint8_t *dsq, int L, int 
             }
             /* bookkeeping of the appended state (scur, k, i) */
             if (scur == ST_E) {
-                if (nd < 8) { open = 1; dto[nd] = 0; dm[nd] = 0; dfrom[nd] = 0; dk[nd] = 0; nI = 0; sx[0] = sx[1] = sx[2] = sx[3] = 0.f; }
+                if (nd < MD_MAXTDOM) { open = 1; dto[nd] = 0; dm[nd] = 0; dfrom[nd] = 0; dk[nd] = 0; nI = 0; sx[0] = sx[1] = sx[2] = sx[3] = 0.f; }
             } else if (scur == ST_M && open) {
                 if (dto[nd] == 0) { dto[nd] = i; dm[nd] = k; }
                 dfrom[nd] = i; dk[nd] = k;
@@ -910,21 +931,18 @@ static int resolve_multidomain(const prof_t *pf, const uint8_t *dsq, int L, int 
             if ((scur == ST_N || scur == ST_J || scur == ST_C) && scur == sprv) i--;
             sprv = scur;
         }
-        /* left to right: segments for the ensemble, null2 odds per position */
-        int pos = 1;
+        /* left to right: segments for the ensemble, null2 odds per covered position */
         for (int d = nd - 1; d >= 0; d--) {
             if (nseg < MD_MAXSEG) {
                 seg[nseg].idx = t; seg[nseg].i = dfrom[d] + ireg - 1; seg[nseg].j = dto[d] + ireg - 1;
                 seg[nseg].k = dk[d]; seg[nseg].m = dm[d];
                 nseg++;
             }
-            for (; pos <= dfrom[d]; pos++) acc[pos] += 1.0f;
-            for (; pos <= dto[d]; pos++) acc[pos] += dnull[d][x[pos - 1]];
+            for (int pos = dfrom[d]; pos <= dto[d]; pos++) { acc[pos] += dnull[d][x[pos - 1]]; cov[pos]++; }
         }
-        for (; pos <= Ld; pos++) acc[pos] += 1.0f;
     }
     for (int pos = 1; pos <= Ld; pos++)
-        n2sc[ireg + pos - 1] = (float)log((double)(acc[pos] / (float)MD_NSAMPLES));
+        n2sc[ireg + pos - 1] = (float)log((double)((acc[pos] + (float)(MD_NSAMPLES - cov[pos])) / (float)MD_NSAMPLES));
 
     /* single linkage clustering (connected components of seg_link) */
     int *asg = malloc(sizeof(int) * (size_t)(nseg + 1));
@@ -978,7 +996,7 @@ static int resolve_multidomain(const prof_t *pf, const uint8_t *dsq, int L, int 
             nenv++;
         }
     }
-    free(asg); free(stack); free(seg); free(acc); free(fM);
+    free(asg); free(stack); free(seg); free(acc); free(cov); free(fM);
     specials_free(&fs);
     return nenv;
 }
