@@ -317,7 +317,7 @@ def main():
 
     # ---- resident leg (value) ----
     ctx.reads_upload(pseq, poff)
-    stage = {k: 0.0 for k in ("ms_msv", "ms_bias", "ms_fwd", "ms_env", "ms_final", "ms_total")}
+    stage = {k: 0.0 for k in ("ms_msv", "ms_bias", "ms_fwd", "ms_mdom", "ms_env", "ms_final", "ms_total")}
     dstage = {k: 0.0 for k in ("ms_pack", "ms_hash", "ms_insert", "ms_verify", "ms_compact", "ms_total")}
     last = {}
 
@@ -365,6 +365,9 @@ def main():
         "envelope": {"ms": sec["ms_env"] * 1e3, "gcups": ss.env_cells / max(sec["ms_env"], 1e-9) / 1e9,
                      "peak_gcups": pk["env_gcups"], "bound": "fp32 fma (+ TMA-staged scratch rows)"},
         "bias": {"ms": sec["ms_bias"] * 1e3, "rows_per_s": ss.bias_rows / max(sec["ms_bias"], 1e-9)},
+        "multidomain": {"ms": sec["ms_mdom"] * 1e3, "regions": ss.n_multidomain_regions,
+                        "traces_per_s": ss.n_multidomain_regions * 200 / max(sec["ms_mdom"], 1e-9),
+                        "bound": "latency / issue (200 stochastic tracebacks per flagged region, p7_domaindef)"},
         "derep_pack": {"ms": dsec["ms_pack"] * 1e3,
                        "gbs": ds.bytes_ascii * (1 + 0.25 + 0.125) / max(dsec["ms_pack"], 1e-9) / 1e9,
                        "peak_gbs": pk["hbm_gbs"], "bound": "hbm"},

@@ -98,6 +98,9 @@ typedef struct {
 } ora_params;
 
 void ora_default_params(ora_params *prm);
+/* HMMER's "fast" generator as the multidomain resolver uses it: state after seeding, state after k more draws */
+uint32_t ora_rng_state0(uint32_t seed);
+uint32_t ora_rng_jump(uint32_t x, uint64_t k);
 
 /* run the cascade for one (sequence, profile).  doms: caller buffer of capacity domcap.
  * Returns number of domains written (also in pr->ndom). */

@@ -234,6 +234,20 @@ def default_params(nthreads=0, resolve_multidomain=1):
     return prm
 
 
+def rng_state0(seed=42):
+    L = lib()
+    L.ora_rng_state0.restype = C.c_uint32
+    L.ora_rng_state0.argtypes = [C.c_uint32]
+    return int(L.ora_rng_state0(seed))
+
+
+def rng_jump(x, k):
+    L = lib()
+    L.ora_rng_jump.restype = C.c_uint32
+    L.ora_rng_jump.argtypes = [C.c_uint32, C.c_uint64]
+    return int(L.ora_rng_jump(x, k))
+
+
 def score10(bits):
     return lib().ora_score10(float(np.float32(bits)))
 

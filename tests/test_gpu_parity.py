@@ -85,17 +85,20 @@ def _uniques(seq, off, rep):
     return np.concatenate(parts), uoff, idx
 
 
-def _search_both(gpu_ctx, oracle, files, prefixes, seq, off, left, right):
+def _search_both(gpu_ctx, oracle, files, prefixes, seq, off, left, right, resolve_multidomain=1):
+    from itsxpress_b200 import _lib
     paths = [os.path.join(HMM_DIR, f) for f in files]
     n = gpu_ctx.load_profiles(paths, prefixes)
     side = gpu_ctx.set_sides_by_prefix(left, right)
     db = oracle.ProfileDB(paths, prefixes)
     assert db.n == n and db.names == gpu_ctx.names
-    gpu_ctx.search_seqs(seq, off)
+    prm = _lib.default_params()
+    prm.resolve_multidomain = resolve_multidomain
+    gpu_ctx.search_seqs(seq, off, prm)
     rows = gpu_ctx.hits()
     st = gpu_ctx.search_stats()
     codes = oracle.digitize(seq.tobytes())
-    orows, onrep, ost = db.search(codes, off)
+    orows, onrep, ost = db.search(codes, off, oracle.default_params(0, resolve_multidomain))
     return rows, st, orows, onrep, ost, side, db
 
 
@@ -158,6 +161,27 @@ def test_search_fixture_all_taxa_with_iupac(gpu_ctx, oracle, fixture_reads):
                                                         "3_", "4_")
     assert min(db.M) < 45 and len(orows) > 500
     _compare_search(gpu_ctx, oracle, rows, st, orows, onrep, ost, side, np.diff(o2).astype(np.int32))
+
+
+@pytest.mark.parametrize("resolve", [1, 0])
+def test_search_multidomain_regions(gpu_ctx, oracle, resolve):
+    """Synthetic ITS1 amplicons: a few hundred regions are flagged multidomain.  resolve=1: stochastic-traceback
+    ensemble + clustering (p7_domaindef) on both sides, identical cluster envelopes; resolve=0: one envelope."""
+    import synth
+    seq, off, which, cfg = synth.make_config("c2_small", scale=0.1)
+    rep, _, _ = oracle.derep(seq, off)
+    useq, uoff, _ = _uniques(seq, off, rep)
+    rows, st, orows, onrep, ost, side, db = _search_both(gpu_ctx, oracle, [cfg["hmm_file"]],
+                                                        [cfg["left_prefix"], cfg["right_prefix"]], useq, uoff,
+                                                        cfg["left_prefix"], cfg["right_prefix"], resolve)
+    assert ost.n_multidomain_regions > 100 and st.n_multidomain_regions == ost.n_multidomain_regions
+    md = orows["is_multidomain"] != 0
+    assert md.sum() > 50
+    assert np.array_equal(rows["is_multidomain"] != 0, md)
+    _compare_search(gpu_ctx, oracle, rows, st, orows, onrep, ost, side, np.diff(uoff).astype(np.int32))
+    # the envelopes that came out of flagged regions, explicitly
+    assert np.array_equal(rows["ienv"][md], orows["ienv"][md]) and np.array_equal(rows["jenv"][md], orows["jenv"][md])
+    assert np.max(np.abs(rows["domcorrection"][md] - orows["domcorrection"][md])) <= 2e-3
 
 
 def test_search_random_sequences_no_hits(gpu_ctx, oracle):

@@ -111,3 +111,51 @@ def test_msv_profile_bytes(db):
     assert cost.shape == (db.M[0] + 1, 16)
     assert 0 < sc["bias"] < 60
     assert sc["tbm"] == int(round(-(3.0 / LN2) * np.log(2.0 / (45 * 46))))
+
+
+# ---- multidomain resolver (stochastic-traceback ensemble + clustering) ---------------------------------------
+def test_rng_leapfrog(oracle):
+    """x <- 69069 x + 1 (mod 2^32); the closed-form jump the trace substreams use equals stepping."""
+    x0 = oracle.rng_state0(42)
+    assert 0 < x0 < 2 ** 32
+    x = x0
+    for k in range(1, 2000):
+        x = (x * 69069 + 1) & 0xFFFFFFFF
+        if k in (1, 2, 3, 17, 255, 256, 1023, 1999):
+            assert oracle.rng_jump(x0, k) == x
+    a = oracle.rng_jump(x0, 1 << 20)
+    assert oracle.rng_jump(a, 1 << 20) == oracle.rng_jump(x0, 2 << 20)
+    assert oracle.rng_jump(x0, 0) == x0
+
+
+def test_multidomain_resolution(oracle):
+    """A flagged region is replaced by its cluster envelopes: they lie inside the region, are ordered by start,
+    carry the flag, and the run is deterministic; with the switch off the region stays one envelope."""
+    import synth
+    seq, off, which, cfg = synth.make_config("c2_small", scale=0.05)
+    paths = [os.path.join(synth.HMM_DIR, cfg["hmm_file"])]
+    db = oracle.ProfileDB(paths, [cfg["left_prefix"], cfg["right_prefix"]])
+    found = 0
+    for r in range(len(off) - 1):
+        dsq = oracle.digitize(seq[off[r]:off[r + 1]].tobytes())
+        for p in range(db.n):
+            pr0, d0 = db.pair_run(p, dsq, oracle.default_params(1, 0))
+            if not pr0.nmultidomain:
+                continue
+            pr1, d1 = db.pair_run(p, dsq, oracle.default_params(1, 1))
+            pr2, d2 = db.pair_run(p, dsq, oracle.default_params(1, 1))
+            assert [tuple(x) for x in d1[["ienv", "jenv"]].tolist()] == [tuple(x) for x in d2[["ienv", "jenv"]].tolist()]
+            assert pr1.fwdsc == pr0.fwdsc and pr1.nmultidomain == pr0.nmultidomain
+            regions = [(int(d["ienv"]), int(d["jenv"])) for d in d0 if d["is_multidomain"]]
+            simple0 = [(int(d["ienv"]), int(d["jenv"])) for d in d0 if not d["is_multidomain"]]
+            simple1 = [(int(d["ienv"]), int(d["jenv"])) for d in d1 if not d["is_multidomain"]]
+            assert simple0 == simple1
+            for d in d1:
+                if d["is_multidomain"]:
+                    assert any(a <= d["ienv"] <= d["jenv"] <= b for a, b in regions)
+            starts = [int(d["ienv"]) for d in d1]
+            assert starts == sorted(starts)
+            found += 1
+        if found >= 12:
+            break
+    assert found >= 12
