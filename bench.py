@@ -142,12 +142,12 @@ def run_reference(args, rank, world):
     paths = [os.path.join(synth.HMM_DIR, f) for f in cfg["search_files"]]
     db = O.ProfileDB(paths, [cfg["left_prefix"], cfg["right_prefix"]])
     side = np.array([0 if n.startswith(cfg["left_prefix"]) else 1 for n in db.names], np.int8)
-    cores = os.cpu_count()
+    cores = os.cpu_count()       # explicit: torchrun exports OMP_NUM_THREADS=1
     for _ in range(min(args.warmup, 1)):
-        oracle_pipeline(O, db, side, s, o)
+        oracle_pipeline(O, db, side, s, o, threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle_pipeline(O, db, side, s, o)
+        oracle_pipeline(O, db, side, s, o, threads=cores)
     dt = (time.perf_counter() - t0) / args.steps
     v = (len(o) - 1) / dt
     line = {"impl": "reference", "metric": "reads/s", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
@@ -156,7 +156,7 @@ def run_reference(args, rank, world):
             "config": workload_config(cfg, args),
             "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(cfg, args):
@@ -230,10 +230,23 @@ def run_sharded_bench(args, ctx, rank, world, local):
                 "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None,
                 "result": {"n_unique": int(out["n_unique_global"]), "n_kept": int(k.item())},
                 "note": "host-orchestrated sharded mode: value == e2e (wall clock, host buffers on every rank)"}
-        print(json.dumps(line))
+        emit(line)
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else that libraries print (NCCL's version
+    banner, torch warnings) was moved to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -402,7 +415,7 @@ def main():
         db = O.ProfileDB([os.path.join(synth.HMM_DIR, f) for f in cfg["search_files"]], [cfg["left_prefix"], cfg["right_prefix"]])
         side = np.array([0 if n.startswith(cfg["left_prefix"]) else 1 for n in db.names], np.int8)
         t0 = time.perf_counter()
-        kept, ost = oracle_pipeline(O, db, side, s, o)
+        kept, ost = oracle_pipeline(O, db, side, s, o, threads=os.cpu_count())
         dt = time.perf_counter() - t0
         cpu = {"value": (len(o) - 1) / dt, "unit": "reads/s", "cores": os.cpu_count(), "kind": "port",
                "sample": desc, "seconds": dt}
@@ -418,7 +431,7 @@ def main():
                 "hmm_gcups": {"msv": stages["msv"]["gcups"], "fwd_bwd": stages["fwd_bwd_decode"]["gcups"],
                               "envelope": stages["envelope"]["gcups"]},
                 "result": {"n_unique": int(rs.n_unique), "n_kept": int(rs.n_kept)}}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
