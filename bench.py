@@ -398,7 +398,7 @@ def main():
     dom = max(("msv", "fwd_bwd_decode", "envelope"), key=lambda k: stages[k]["ms"])
     # dram traffic of the dominant kernel from the committed ncu --set full capture (one per-profile launch at
     # --scale 0.2; profiles/*_fb_kernel_full.md): far below anything HBM-bound -- the DP kernels are issue-bound
-    traffic = {"fb_kernel": 260.4e6, "env_kernel": 709.2e6, "msv_kernel": 8.6e6}
+    traffic = {"fb_kernel": 262.9e6, "env_kernel": 376.1e6, "msv_kernel": 9.0e6}       # profiles/r1e_*_full.md
     kname = {"msv": "msv_kernel", "fwd_bwd_decode": "fb_kernel", "envelope": "env_kernel"}[dom]
     roof = {"kernel": kname, "bound": "alu", "achieved": stages[dom]["gcups"], "peak": stages[dom]["peak_gcups"],
             "unit": "GCUPS", "frac": stages[dom]["gcups"] / stages[dom]["peak_gcups"], "traffic": traffic[kname],
