@@ -172,8 +172,8 @@ int itsx_reads_upload(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64
     CHECK_CTX(c);
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (nreads < 0 || (nreads > 0 && (!seq || !off))) { c->err = "reads_upload: null buffer"; return ITSX_EINVAL; }
-    const int64_t total = nreads ? off[nreads] : 0;
-    if (nreads && off[0] != 0) { c->err = "reads_upload: off[0] must be 0"; return ITSX_EINVAL; }
+    const int64_t total = nreads ? itsx_peek_i64(off + nreads) : 0;
+    if (nreads && itsx_peek_i64(off) != 0) { c->err = "reads_upload: off[0] must be 0"; return ITSX_EINVAL; }
     c->nreads = nreads;
     c->total_bases = total;
     c->n_unique = 0;
@@ -183,8 +183,8 @@ int itsx_reads_upload(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64
     CUDA_TRY(c, c->d_ascii.ensure(padded));
     CUDA_TRY(c, c->d_off.ensure((size_t)(nreads + 1) * 8));
     CUDA_TRY(c, cudaMemsetAsync(c->d_ascii.as<uint8_t>() + (size_t)total / 16 * 16, 'A', padded - (size_t)total / 16 * 16, c->stream));
-    if (total) CUDA_TRY(c, cudaMemcpyAsync(c->d_ascii.p, seq, (size_t)total, cudaMemcpyHostToDevice, c->stream));
-    if (nreads) CUDA_TRY(c, cudaMemcpyAsync(c->d_off.p, off, (size_t)(nreads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (total) CUDA_TRY(c, cudaMemcpyAsync(c->d_ascii.p, seq, (size_t)total, cudaMemcpyDefault, c->stream));
+    if (nreads) CUDA_TRY(c, cudaMemcpyAsync(c->d_off.p, off, (size_t)(nreads + 1) * 8, cudaMemcpyDefault, c->stream));
     else CUDA_TRY(c, cudaMemsetAsync(c->d_off.p, 0, 8, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ITSX_OK;
@@ -199,8 +199,8 @@ int itsx_derep(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64_t nrea
     rc = derep_run(c);
     if (rc) return rc;
     if (nreads) {
-        if (rep_index) CUDA_TRY(c, cudaMemcpyAsync(rep_index, c->d_rep.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, c->stream));
-        if (strand) CUDA_TRY(c, cudaMemcpyAsync(strand, c->d_strand.p, (size_t)nreads, cudaMemcpyDeviceToHost, c->stream));
+        if (rep_index) CUDA_TRY(c, cudaMemcpyAsync(rep_index, c->d_rep.p, (size_t)nreads * 4, cudaMemcpyDefault, c->stream));
+        if (strand) CUDA_TRY(c, cudaMemcpyAsync(strand, c->d_strand.p, (size_t)nreads, cudaMemcpyDefault, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     }
     if (n_unique) *n_unique = c->n_unique;
@@ -223,13 +223,13 @@ int itsx_derep_clusters(itsx_ctx *c, int32_t *first_read, int32_t *abundance)
     CUDA_TRY(c, cudaSetDevice(c->device));
     const int64_t nu = c->n_unique;
     if (nu == 0) return ITSX_OK;
-    if (first_read) CUDA_TRY(c, cudaMemcpyAsync(first_read, c->d_first.p, (size_t)nu * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (first_read) CUDA_TRY(c, cudaMemcpyAsync(first_read, c->d_first.p, (size_t)nu * 4, cudaMemcpyDefault, c->stream));
     if (abundance) {
         CUDA_TRY(c, c->d_list.ensure((size_t)nu * 4));
         abund_gather_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, c->stream>>>(c->d_first.as<int32_t>(), c->d_abund.as<int32_t>(), nu,
                                                                                   c->d_list.as<int32_t>());
         c->launches++;
-        CUDA_TRY(c, cudaMemcpyAsync(abundance, c->d_list.p, (size_t)nu * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(abundance, c->d_list.p, (size_t)nu * 4, cudaMemcpyDefault, c->stream));
     }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ITSX_OK;
@@ -253,7 +253,7 @@ int itsx_derep_unique_keys(itsx_ctx *c, uint64_t *keys)
                                                                             c->d_key.as<unsigned long long>(), nu,
                                                                             c->d_list.as<unsigned long long>());
     c->launches++;
-    CUDA_TRY(c, cudaMemcpyAsync(keys, c->d_list.p, (size_t)nu * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(keys, c->d_list.p, (size_t)nu * 8, cudaMemcpyDefault, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ITSX_OK;
 }
@@ -364,7 +364,7 @@ int itsx_hits(itsx_ctx *c, itsx_dom_row *rows, int64_t cap, int64_t *n)
     if (!c->stage2_done) { c->err = "hits before search"; return ITSX_EINVAL; }
     std::vector<DomRec> h((size_t)c->ndom);
     if (c->ndom) {
-        CUDA_TRY(c, cudaMemcpyAsync(h.data(), c->d_doms.p, (size_t)c->ndom * sizeof(DomRec), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(h.data(), c->d_doms.p, (size_t)c->ndom * sizeof(DomRec), cudaMemcpyDefault, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     }
     std::vector<int64_t> idx;
@@ -404,7 +404,7 @@ int itsx_positions(itsx_ctx *c, int32_t *start, int32_t *stop, int32_t *tlen,
     if (n == 0) return ITSX_OK;
     for (int k = 0; k < 9; k++)
         if (outs[k])
-            CUDA_TRY(c, cudaMemcpyAsync(outs[k], c->d_pos.as<int32_t>() + (size_t)k * n, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaMemcpyAsync(outs[k], c->d_pos.as<int32_t>() + (size_t)k * n, (size_t)n * 4, cudaMemcpyDefault, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ITSX_OK;
 }
@@ -418,9 +418,9 @@ int itsx_positions_set(itsx_ctx *c, const int32_t *start, const int32_t *stop, c
     CUDA_TRY(c, c->d_pos.ensure((size_t)std::max<int64_t>(n, 1) * 9 * 4));
     if (n) {
         CUDA_TRY(c, cudaMemsetAsync(c->d_pos.p, 0xff, (size_t)n * 9 * 4, c->stream));
-        CUDA_TRY(c, cudaMemcpyAsync(c->d_pos.as<int32_t>(), start, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(c, cudaMemcpyAsync(c->d_pos.as<int32_t>() + n, stop, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(c, cudaMemcpyAsync(c->d_pos.as<int32_t>() + 2 * n, tlen, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_pos.as<int32_t>(), start, (size_t)n * 4, cudaMemcpyDefault, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_pos.as<int32_t>() + n, stop, (size_t)n * 4, cudaMemcpyDefault, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_pos.as<int32_t>() + 2 * n, tlen, (size_t)n * 4, cudaMemcpyDefault, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     }
     c->pos_valid = true;
@@ -435,7 +435,7 @@ int itsx_trim_set_map(itsx_ctx *c, const int32_t *uid, int64_t nreads, int64_t n
     if (nreads < 0 || n_unique < 0 || (nreads && !uid)) { c->err = "trim_set_map: bad argument"; return ITSX_EINVAL; }
     if (nreads >= 0x7fffffffLL) { c->err = "trim_set_map: more than 2^31-1 reads in one call"; return ITSX_ELIMIT; }
     CUDA_TRY(c, c->d_uid.ensure((size_t)std::max<int64_t>(nreads, 1) * 4));
-    if (nreads) CUDA_TRY(c, cudaMemcpyAsync(c->d_uid.p, uid, (size_t)nreads * 4, cudaMemcpyHostToDevice, c->stream));
+    if (nreads) CUDA_TRY(c, cudaMemcpyAsync(c->d_uid.p, uid, (size_t)nreads * 4, cudaMemcpyDefault, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->nreads = nreads;
     c->n_unique = n_unique;
@@ -467,15 +467,15 @@ int itsx_trim_bounds(itsx_ctx *c, int mode, const int64_t *off_other, int64_t nr
     const int64_t *d_off = nullptr;
     if (off_other) {
         CUDA_TRY(c, t_off.ensure((size_t)(nreads + 1) * 8));
-        CUDA_TRY(c, cudaMemcpyAsync(t_off.p, off_other, (size_t)(nreads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(t_off.p, off_other, (size_t)(nreads + 1) * 8, cudaMemcpyDefault, c->stream));
         d_off = t_off.as<int64_t>();
     }
     rc = trim_bounds_dev(c, mode, d_off, nreads, t_keep.as<uint8_t>(), t_lo.as<int32_t>(), t_hi.as<int32_t>(), n_kept);
     if (rc) return rc;
     if (nreads) {
-        if (keep) CUDA_TRY(c, cudaMemcpyAsync(keep, t_keep.p, (size_t)nreads, cudaMemcpyDeviceToHost, c->stream));
-        if (lo) CUDA_TRY(c, cudaMemcpyAsync(lo, t_lo.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, c->stream));
-        if (hi) CUDA_TRY(c, cudaMemcpyAsync(hi, t_hi.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (keep) CUDA_TRY(c, cudaMemcpyAsync(keep, t_keep.p, (size_t)nreads, cudaMemcpyDefault, c->stream));
+        if (lo) CUDA_TRY(c, cudaMemcpyAsync(lo, t_lo.p, (size_t)nreads * 4, cudaMemcpyDefault, c->stream));
+        if (hi) CUDA_TRY(c, cudaMemcpyAsync(hi, t_hi.p, (size_t)nreads * 4, cudaMemcpyDefault, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     }
     return ITSX_OK;
@@ -502,10 +502,10 @@ int itsx_trim_gather(itsx_ctx *c, int mode, const uint8_t *seq, const uint8_t *q
     CUDA_TRY(c, t_lo.ensure((size_t)nreads * 4 + 16));
     CUDA_TRY(c, t_hi.ensure((size_t)nreads * 4 + 16));
     const int64_t *d_off = nullptr;
-    const int64_t tot_in = (off && nreads) ? off[nreads] : 0;
+    const int64_t tot_in = (off && nreads) ? itsx_peek_i64(off + nreads) : 0;
     if (off) {
         CUDA_TRY(c, t_off.ensure((size_t)(nreads + 1) * 8));
-        CUDA_TRY(c, cudaMemcpyAsync(t_off.p, off, (size_t)(nreads + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaMemcpyAsync(t_off.p, off, (size_t)(nreads + 1) * 8, cudaMemcpyDefault, st));
         d_off = t_off.as<int64_t>();
     }
     int64_t nk = 0;
@@ -514,7 +514,7 @@ int itsx_trim_gather(itsx_ctx *c, int mode, const uint8_t *seq, const uint8_t *q
     if (query) {
         int64_t tot = 0;
         if (nreads) {
-            CUDA_TRY(c, cudaMemcpyAsync(&tot, c->d_list2.as<int64_t>() + nreads, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaMemcpyAsync(&tot, c->d_list2.as<int64_t>() + nreads, 8, cudaMemcpyDefault, st));
             CUDA_TRY(c, cudaStreamSynchronize(st));
         }
         *n_kept = nk;
@@ -525,22 +525,22 @@ int itsx_trim_gather(itsx_ctx *c, int mode, const uint8_t *seq, const uint8_t *q
     const uint8_t *d_qual = nullptr;
     if (seq) {
         CUDA_TRY(c, t_seq.ensure((size_t)tot_in + 16));
-        if (tot_in) CUDA_TRY(c, cudaMemcpyAsync(t_seq.p, seq, (size_t)tot_in, cudaMemcpyHostToDevice, st));
+        if (tot_in) CUDA_TRY(c, cudaMemcpyAsync(t_seq.p, seq, (size_t)tot_in, cudaMemcpyDefault, st));
         d_seq = t_seq.as<uint8_t>();
     }
     if (qual) {
         const int64_t tq = off ? tot_in : c->total_bases;
         CUDA_TRY(c, t_qual.ensure((size_t)tq + 16));
-        if (tq) CUDA_TRY(c, cudaMemcpyAsync(t_qual.p, qual, (size_t)tq, cudaMemcpyHostToDevice, st));
+        if (tq) CUDA_TRY(c, cudaMemcpyAsync(t_qual.p, qual, (size_t)tq, cudaMemcpyDefault, st));
         d_qual = t_qual.as<uint8_t>();
     }
     rc = trim_gather_dev(c, d_seq, d_qual, d_off ? d_off : c->d_off.as<int64_t>(), nreads, t_keep.as<uint8_t>(),
                          t_lo.as<int32_t>(), t_hi.as<int32_t>(), n_kept, total, t_ki, t_oo, t_os, t_oq);
     if (rc) return rc;
-    if (kept_index && *n_kept) CUDA_TRY(c, cudaMemcpyAsync(kept_index, t_ki.p, (size_t)*n_kept * 4, cudaMemcpyDeviceToHost, st));
-    if (out_off) CUDA_TRY(c, cudaMemcpyAsync(out_off, t_oo.p, (size_t)(*n_kept + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (out_seq && *total) CUDA_TRY(c, cudaMemcpyAsync(out_seq, t_os.p, (size_t)*total, cudaMemcpyDeviceToHost, st));
-    if (out_qual && d_qual && *total) CUDA_TRY(c, cudaMemcpyAsync(out_qual, t_oq.p, (size_t)*total, cudaMemcpyDeviceToHost, st));
+    if (kept_index && *n_kept) CUDA_TRY(c, cudaMemcpyAsync(kept_index, t_ki.p, (size_t)*n_kept * 4, cudaMemcpyDefault, st));
+    if (out_off) CUDA_TRY(c, cudaMemcpyAsync(out_off, t_oo.p, (size_t)(*n_kept + 1) * 8, cudaMemcpyDefault, st));
+    if (out_seq && *total) CUDA_TRY(c, cudaMemcpyAsync(out_seq, t_os.p, (size_t)*total, cudaMemcpyDefault, st));
+    if (out_qual && d_qual && *total) CUDA_TRY(c, cudaMemcpyAsync(out_qual, t_oq.p, (size_t)*total, cudaMemcpyDefault, st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     return ITSX_OK;
 }
@@ -578,7 +578,7 @@ static int run_device_part(itsx_ctx *c, const itsx_search_params *prm, itsx_run_
     rs->n_kept = nk;
     if (n) {
         int64_t tot = 0;
-        CUDA_TRY(c, cudaMemcpyAsync(&tot, c->d_list2.as<int64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(&tot, c->d_list2.as<int64_t>() + n, 8, cudaMemcpyDefault, st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
         rs->out_bytes = tot;
     }
@@ -599,10 +599,10 @@ int itsx_run(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64_t nreads
     int rc = itsx_reads_upload(c, seq, off, nreads);
     if (!rc) rc = run_device_part(c, prm, &rs, t_keep, t_lo, t_hi, ev);
     if (!rc && nreads) {
-        if (rep_index) CUDA_TRY(c, cudaMemcpyAsync(rep_index, c->d_rep.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, st));
-        if (keep) CUDA_TRY(c, cudaMemcpyAsync(keep, t_keep.p, (size_t)nreads, cudaMemcpyDeviceToHost, st));
-        if (lo) CUDA_TRY(c, cudaMemcpyAsync(lo, t_lo.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, st));
-        if (hi) CUDA_TRY(c, cudaMemcpyAsync(hi, t_hi.p, (size_t)nreads * 4, cudaMemcpyDeviceToHost, st));
+        if (rep_index) CUDA_TRY(c, cudaMemcpyAsync(rep_index, c->d_rep.p, (size_t)nreads * 4, cudaMemcpyDefault, st));
+        if (keep) CUDA_TRY(c, cudaMemcpyAsync(keep, t_keep.p, (size_t)nreads, cudaMemcpyDefault, st));
+        if (lo) CUDA_TRY(c, cudaMemcpyAsync(lo, t_lo.p, (size_t)nreads * 4, cudaMemcpyDefault, st));
+        if (hi) CUDA_TRY(c, cudaMemcpyAsync(hi, t_hi.p, (size_t)nreads * 4, cudaMemcpyDefault, st));
     }
     if (!rc) {
         CUDA_TRY(c, cudaEventRecord(ev[5], st));

@@ -72,6 +72,20 @@ struct DomRec {
     int32_t is_multidomain, pair_reported;
 };
 
+// one int64 of a caller buffer that may live on the host or on the device (every caller buffer of the C ABI may be
+// device memory: copies use cudaMemcpyDefault)
+inline int64_t itsx_peek_i64(const int64_t *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) {
+        int64_t v = 0;
+        cudaMemcpy(&v, p, 8, cudaMemcpyDefault);
+        return v;
+    }
+    cudaGetLastError();
+    return *p;
+}
+
 // growable device buffer (library-owned; grows geometrically, never shrinks)
 struct DevBuf {
     void  *p = nullptr;

@@ -1877,11 +1877,11 @@ int search_build_seqs_from_host(itsx_ctx *c, const uint8_t *seq, const int64_t *
 {
     // staged through separate buffers so that the reads of a previous itsx_derep stay resident
     static thread_local DevBuf t_ascii, t_off;
-    const int64_t total = nseq ? off[nseq] : 0;
+    const int64_t total = nseq ? itsx_peek_i64(off + nseq) : 0;
     CUDA_TRY(c, t_ascii.ensure((size_t)total + 64));
     CUDA_TRY(c, t_off.ensure((size_t)(nseq + 1) * 8));
-    if (total) CUDA_TRY(c, cudaMemcpyAsync(t_ascii.p, seq, (size_t)total, cudaMemcpyHostToDevice, c->stream));
-    if (nseq) CUDA_TRY(c, cudaMemcpyAsync(t_off.p, off, (size_t)(nseq + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (total) CUDA_TRY(c, cudaMemcpyAsync(t_ascii.p, seq, (size_t)total, cudaMemcpyDefault, c->stream));
+    if (nseq) CUDA_TRY(c, cudaMemcpyAsync(t_off.p, off, (size_t)(nseq + 1) * 8, cudaMemcpyDefault, c->stream));
     c->shard_first = 0;
     c->shard_n = -1;
     return build_seqs(c, t_ascii.as<uint8_t>(), t_off.as<int64_t>(), nullptr, nseq);

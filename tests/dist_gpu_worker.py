@@ -15,7 +15,7 @@ def main():
     import torch.distributed as dist
     import synth
     from itsxpress_b200 import _lib
-    from itsxpress_b200.distributed import Comm, GpuEngine, block_range, run_sharded
+    from itsxpress_b200.distributed import Comm, GpuEngine, block_range, run_sharded, run_sharded_device
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -26,10 +26,14 @@ def main():
     n = len(off) - 1
     lo, hi = block_range(n, rank, world)
     got = run_sharded(GpuEngine(ctx), Comm(), seq[off[lo]:off[hi]], off[lo:hi + 1] - off[lo], lo)
+    dev = run_sharded_device(ctx, seq[off[lo]:off[hi]], off[lo:hi + 1] - off[lo], lo)   # device-resident exchange
     want, st = ctx.run(seq, off)             # every rank also runs the whole sample alone
-    ok = (np.array_equal(got["rep"], want["rep"][lo:hi]) and np.array_equal(got["keep"], want["keep"][lo:hi]) and
-          np.array_equal(got["lo"], want["lo"][lo:hi]) and np.array_equal(got["hi"], want["hi"][lo:hi]) and
-          got["n_unique_global"] == st.n_unique)
+    ok = True
+    for res in (got, dev):
+        ok = ok and (np.array_equal(res["rep"], want["rep"][lo:hi]) and np.array_equal(res["keep"], want["keep"][lo:hi]) and
+                     np.array_equal(res["lo"], want["lo"][lo:hi]) and np.array_equal(res["hi"], want["hi"][lo:hi]) and
+                     res["n_unique_global"] == st.n_unique)
+    ok = ok and np.array_equal(got["strand"], dev["strand"]) and np.array_equal(got["nreported"], dev["nreported"])
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -291,6 +291,36 @@ def test_run_sharded_single_rank_equals_itsx_run(gpu_ctx, fixture_reads):
     assert np.array_equal(got["lo"], want["lo"]) and np.array_equal(got["hi"], want["hi"])
 
 
+def test_run_sharded_device_single_rank_equals_itsx_run(gpu_ctx, fixture_reads):
+    """the device-resident sharded driver (C ABI called with device pointers, torch index arithmetic on the GPU) on one
+    rank == itsx_run == the host-orchestrated driver, including strands and the per-profile reported-hit counts."""
+    from itsxpress_b200.distributed import Comm, GpuEngine, run_sharded, run_sharded_device
+    b, seq, off, _ = fixture_reads
+    # make some reads reverse complements of others so that strand '-' occurs
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+    parts = [seq[off[i]:off[i + 1]].tobytes() for i in range(len(off) - 1)]
+    parts += [p.translate(comp)[::-1] for p in parts[:20]]
+    seq2 = np.frombuffer(b"".join(parts), np.uint8).copy()
+    off2 = np.zeros(len(parts) + 1, np.int64)
+    off2[1:] = np.cumsum([len(p) for p in parts])
+    paths = [os.path.join(HMM_DIR, "M.hmm")]
+    gpu_ctx.load_profiles(paths, ["3_", "4_"])
+    gpu_ctx.set_sides_by_prefix("3_", "4_")
+    want, st = gpu_ctx.run(seq2, off2)
+    want = {k: v.copy() for k, v in want.items()}
+    host = run_sharded(GpuEngine(gpu_ctx), Comm(), seq2, off2, 0)
+    got = run_sharded_device(gpu_ctx, seq2, off2, 0)
+    assert got["n_unique_global"] == st.n_unique
+    assert np.array_equal(got["rep"], want["rep"])
+    assert np.array_equal(got["keep"], want["keep"]) and int(got["keep"].sum()) == st.n_kept
+    assert np.array_equal(got["lo"], want["lo"]) and np.array_equal(got["hi"], want["hi"])
+    assert np.array_equal(got["strand"], host["strand"]) and got["strand"].sum() >= 20
+    assert np.array_equal(got["nreported"], host["nreported"])
+    # an empty block is legal (more ranks than reads)
+    empty = run_sharded_device(gpu_ctx, np.zeros(0, np.uint8), np.zeros(1, np.int64), 0)
+    assert len(empty["keep"]) == 0 and empty["n_unique_global"] == 0
+
+
 def test_trim_set_map_drops_unmapped_reads(gpu_ctx):
     off = np.array([0, 10, 20, 30], np.int64)
     gpu_ctx.trim_set_map(np.array([0, -1, 1], np.int32), 2)
