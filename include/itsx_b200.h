@@ -18,8 +18,10 @@
  *
  * Conventions: plain C, no callbacks, no exceptions across the boundary.  Functions return
  * 0 on success and a negative ITSX_E* code on failure; itsx_last_error() gives the text.
- * Host buffers are caller-owned; device memory is library-owned behind itsx_ctx (one ctx per
- * host thread / per GPU).  There is NO CPU fallback: without a usable CUDA device
+ * Caller buffers are caller-owned and may live in host memory (pageable or pinned) OR in device
+ * memory of the context's GPU (copies use cudaMemcpyDefault; the multi-GPU driver passes torch tensors);
+ * the library's own device memory sits behind itsx_ctx (one ctx per host thread / per GPU).  Calls run on the
+ * library's stream and return after it drained: make a device buffer's producer finish first.  There is NO CPU fallback: without a usable CUDA device
  * itsx_create() fails with ITSX_ENODEV.
  */
 #ifndef ITSX_B200_H
