@@ -15,6 +15,8 @@
  *   itsx_positions       ItsPosition._score / get_position          SeqSample.py:400-429, 463-498
  *   itsx_trim_*          Dedup._get_trimmed_seq_generator /         SeqSample.py:792-884
  *                        Dedup._get_paired_seq_generator            SeqSample.py:564-711
+ *   itsx_merge_*         `vsearch --fastq_mergepairs` (paired input, the step in front of derep)
+ *                                                                  SeqSample.py:266-365 (argv :314-349)
  *
  * Conventions: plain C, no callbacks, no exceptions across the boundary.  Functions return
  * 0 on success and a negative ITSX_E* code on failure; itsx_last_error() gives the text.
@@ -185,6 +187,41 @@ int  itsx_trim_bounds(itsx_ctx *ctx, int mode, const int64_t *off_other, int64_t
 int  itsx_trim_gather(itsx_ctx *ctx, int mode, const uint8_t *seq, const uint8_t *qual, const int64_t *off,
                       int64_t nreads, int64_t *n_kept, int64_t *total,
                       int32_t *kept_index, int64_t *out_off, uint8_t *out_seq, uint8_t *out_qual);
+
+/* ---- paired-end merge ------------------------------------------------------------------
+ * Replaces the `vsearch --fastq_mergepairs R1 --reverse R2 --fastqout seq.fq --fastq_maxdiffs 40 --fastq_maxee 2
+ * [--fastq_allowmergestagger] --fastq_qmax 93` process of SeqSamplePairedNotInterleaved._merge_reads
+ * (SeqSample.py:266-365; constants definitions.py:79,82). */
+enum { ITSX_MERGE_OK = 0, ITSX_MERGE_REPEAT, ITSX_MERGE_STAGGERED, ITSX_MERGE_MAXDIFFS, ITSX_MERGE_MAXDIFFPCT,
+       ITSX_MERGE_NOKMERS, ITSX_MERGE_MINSCORE, ITSX_MERGE_MINOVLEN, ITSX_MERGE_MAXEE, ITSX_MERGE_BADQUAL };
+typedef struct {
+    int32_t maxdiffs;        /* --fastq_maxdiffs 40           definitions.py:79, SeqSample.py:322 */
+    int32_t allow_stagger;   /* --fastq_allowmergestagger     SeqSample.py:328 */
+    int32_t qmax;            /* --fastq_qmax 93               definitions.py:82, SeqSample.py:330 */
+    int32_t minovlen, qmaxout, qminout, ascii;   /* vsearch defaults the reference leaves alone: 10, 41, 0, 33 */
+    int32_t reserved;
+    double  maxee;           /* --fastq_maxee 2               SeqSample.py:324 */
+    double  maxdiffpct;      /* vsearch default 100 */
+} itsx_merge_params;
+typedef struct {
+    int64_t n_pairs, n_merged;
+    int64_t by_reason[16];   /* pairs per ITSX_MERGE_* outcome (what vsearch prints as its merge statistics) */
+    int64_t bytes_in, bytes_out;   /* bases + qualities read / written by the merge kernel */
+    float   ms_kernel;       /* merge_kernel alone, CUDA events on the library's stream */
+} itsx_merge_stats;
+void itsx_merge_default_params(itsx_merge_params *prm);
+/* fseq/fqual with foff[npairs+1]: R1 records; rseq/rqual with roff[npairs+1]: R2 records as they stand in the file
+ * (the library reverse-complements).  merged_len[i] = length of pair i's merged read or 0, reason[i] = ITSX_MERGE_*
+ * (either may be NULL).  *n_merged pairs with *total bases stay resident for itsx_merge_fetch.  A quality value
+ * outside [0, qmax] -- where vsearch stops with a fatal error -- returns ITSX_EFORMAT. */
+int  itsx_merge_pairs(itsx_ctx *ctx, const uint8_t *fseq, const uint8_t *fqual, const int64_t *foff,
+                      const uint8_t *rseq, const uint8_t *rqual, const int64_t *roff, int64_t npairs,
+                      const itsx_merge_params *prm, int32_t *merged_len, uint8_t *reason, int64_t *n_merged,
+                      int64_t *total);
+/* merged reads of the last itsx_merge_pairs in input order, packed back to back: merged_index[n_merged] = pair
+ * index (the title vsearch writes is R1's), out_off[n_merged+1], out_seq / out_qual [total].  Any may be NULL. */
+int  itsx_merge_fetch(itsx_ctx *ctx, int32_t *merged_index, int64_t *out_off, uint8_t *out_seq, uint8_t *out_qual);
+int  itsx_merge_get_stats(const itsx_ctx *ctx, itsx_merge_stats *st);
 
 /* ---- whole path, host buffers in / host buffers out (the call bench.py's e2e leg times) -- */
 typedef struct {

@@ -258,28 +258,61 @@ class SeqSamplePairedNotInterleaved(SeqSample):
             self.r1, self.fastq2 = fastq, fastq2
 
     def _merge_reads(self, threads, stagger):
-        """Paired-end merging is upstream of the GPU path and stays `vsearch --fastq_mergepairs` with the
-        reference's flags (SeqSample.py:266-365); raises FileNotFoundError when vsearch is not installed."""
+        """Merge the read pairs on the GPU and write ``<tempdir>/seq.fq`` (replaces the
+        `vsearch --fastq_mergepairs R1 --reverse R2 --fastqout seq.fq --fastq_maxdiffs 40 --fastq_maxee 2
+        [--fastq_allowmergestagger] --fastq_qmax 93` process of SeqSample.py:266-365; ``itsx_merge_pairs``,
+        csrc/merge.cu).  Records keep R1's title and follow input order, as vsearch writes them.  ``threads`` is
+        accepted for the reference's signature.  Inputs may be plain, .gz or .zst (vsearch reads .gz itself; the
+        reference unpacks .zst first, :287-306).
+
+        Raises ``subprocess.CalledProcessError`` where the vsearch process would have exited non-zero (files with
+        different record counts, a quality value above --fastq_qmax, malformed FASTQ) and ``FileNotFoundError``
+        for a missing input, after logging, like the reference (:351-365)."""
         seq_file = os.path.join(self.tempdir, "seq.fq")
         if not os.path.exists(self.tempdir):
             logging.info("Expected %s to exist, but it does not. Creating it now." % self.tempdir)
             os.makedirs(self.tempdir)
         if self.r1 is None or self.fastq2 is None:
             raise ValueError("Both r1 and fastq2 paths must be defined to merge reads.")
-        if self.r1.endswith(".zst") and self.fastq2.endswith(".zst"):
-            from . import _zstd
-            for attr, name in (("r1", "r1_temp.fq"), ("fastq2", "r2_temp.fq")):
-                tmp = os.path.join(self.tempdir, name)
-                with open(getattr(self, attr), "rb") as fi, open(tmp, "wb") as fo:
-                    fo.write(_zstd.decompress(fi.read()))
-                setattr(self, attr, tmp)
-        argv = ["vsearch", "--fastq_mergepairs", self.r1, "--reverse", self.fastq2, "--fastqout", seq_file,
-                "--fastq_maxdiffs", str(maxmismatches), "--fastq_maxee", str(2), "--threads", str(threads)]
+        argv = ["itsx_merge_pairs", self.r1, "--reverse", self.fastq2, "--fastqout", seq_file, "--fastq_maxdiffs",
+                str(maxmismatches), "--fastq_maxee", str(2), "--threads", str(threads)]
         if stagger:
             argv.append("--fastq_allowmergestagger")
         argv += ["--fastq_qmax", str(vsearch_fastq_qmax)]
         self.seq_file = seq_file
-        _external("vsearch", argv, "read merging")
+        try:
+            try:
+                b1 = fq.read_fastq(self.r1)
+                b2 = fq.read_fastq(self.fastq2)
+                if b1.n != b2.n:
+                    raise ValueError("More %s reads than %s reads" % (("forward", "reverse") if b1.n > b2.n
+                                                                      else ("reverse", "forward")))
+                fseq, foff = b1.seq_concat()
+                fqual, _ = b1.qual_concat()
+                rseq, roff = b2.seq_concat()
+                rqual, _ = b2.qual_concat()
+                prm = _lib.merge_params(allow_stagger=stagger, maxdiffs=maxmismatches, maxee=2.0,
+                                        qmax=vsearch_fastq_qmax)
+                ctx = get_context()
+                mlen, reason, idx, out_off, out_seq, out_qual = ctx.merge_pairs(fseq, fqual, foff, rseq, rqual, roff,
+                                                                               prm)
+            except FileNotFoundError:
+                raise
+            except (ValueError, _lib.ItsxError) as e:
+                raise subprocess.CalledProcessError(1, argv, stderr=str(e).encode("utf-8")) from e
+            with open(seq_file, "wb") as f:
+                f.write(fq.format_gathered(b1, idx, out_off, out_seq, out_qual))
+            st = ctx.merge_stats()
+            why = ", ".join("%s %d" % (_lib.MERGE_REASONS[r], st.by_reason[r])
+                            for r in range(1, len(_lib.MERGE_REASONS)) if st.by_reason[r])
+            logging.info("Merged %d of %d pairs on the GPU (%.2f ms)%s" % (st.n_merged, st.n_pairs, st.ms_kernel,
+                                                                         "; not merged: " + why if why else ""))
+        except subprocess.CalledProcessError as e:
+            logging.exception("Could not perform read merging. Error was: \n  {}".format(e.stderr.decode("utf-8")))
+            raise e
+        except FileNotFoundError as f:
+            logging.error("Could not perform read merging: %s" % f)
+            raise f
 
 
 def _read_fasta(path):

@@ -46,6 +46,21 @@ class DerepStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class MergeParams(C.Structure):
+    _fields_ = [("maxdiffs", C.c_int32), ("allow_stagger", C.c_int32), ("qmax", C.c_int32), ("minovlen", C.c_int32),
+                ("qmaxout", C.c_int32), ("qminout", C.c_int32), ("ascii", C.c_int32), ("reserved", C.c_int32),
+                ("maxee", C.c_double), ("maxdiffpct", C.c_double)]
+
+
+class MergeStats(C.Structure):
+    _fields_ = [("n_pairs", C.c_int64), ("n_merged", C.c_int64), ("by_reason", C.c_int64 * 16),
+                ("bytes_in", C.c_int64), ("bytes_out", C.c_int64), ("ms_kernel", C.c_float)]
+
+
+MERGE_REASONS = ("ok", "repeat", "staggered", "maxdiffs", "maxdiffpct", "nokmers", "minscore", "minovlen", "maxee",
+                 "badqual")
+
+
 class RunStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_reads", "n_unique", "n_kept", "out_bytes")] + \
                [(n, C.c_float) for n in ("ms_h2d", "ms_derep", "ms_search", "ms_trim", "ms_d2h", "ms_total")]
@@ -72,6 +87,7 @@ SYMBOLS = [
     "itsx_nreported_set", "itsx_search_stage2", "itsx_positions_set",
     "itsx_trim_set_map", "itsx_trim_bounds", "itsx_trim_gather", "itsx_run", "itsx_reads_upload", "itsx_run_resident",
     "itsx_launch_count",
+    "itsx_merge_default_params", "itsx_merge_pairs", "itsx_merge_fetch", "itsx_merge_get_stats",
     "itsx_host_last_error", "itsx_fastq_index", "itsx_bytes_gather", "itsx_fastq_format",
 ]
 
@@ -134,6 +150,11 @@ def lib():
     L.itsx_run_resident.argtypes = [vp, C.POINTER(SearchParams), C.POINTER(RunStats)]
     L.itsx_launch_count.argtypes = [vp]
     L.itsx_launch_count.restype = i64
+    L.itsx_merge_default_params.argtypes = [C.POINTER(MergeParams)]
+    L.itsx_merge_default_params.restype = None
+    L.itsx_merge_pairs.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(MergeParams), vp, vp, vp, vp]
+    L.itsx_merge_fetch.argtypes = [vp, vp, vp, vp, vp]
+    L.itsx_merge_get_stats.argtypes = [vp, C.POINTER(MergeStats)]
     L.itsx_host_last_error.restype = C.c_char_p
     L.itsx_fastq_index.restype = i64
     L.itsx_fastq_index.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp]
@@ -148,6 +169,16 @@ def lib():
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def merge_params(allow_stagger=False, **kw):
+    """vsearch --fastq_mergepairs options as the reference passes them (SeqSample.py:314-349)."""
+    prm = MergeParams()
+    lib().itsx_merge_default_params(C.byref(prm))
+    prm.allow_stagger = int(bool(allow_stagger))
+    for k, v in kw.items():
+        setattr(prm, k, v)
+    return prm
 
 
 def default_params():
@@ -388,6 +419,37 @@ class Context:
         self._chk(L.itsx_trim_gather(self._h, mode, _p(seq), _p(qual), _p(off), nreads, C.byref(nk), C.byref(tot),
                                      _p(ki), _p(oo), _p(os_), _p(oq)))
         return ki, oo, os_, oq
+
+    # ---- paired-end merge -----------------------------------------------------------------------
+    def merge_pairs(self, fseq, fqual, foff, rseq, rqual, roff, params=None, fetch=True):
+        """Merge R1/R2 records on the GPU.  Returns (merged_len[n], reason[n], merged_index, out_off, out_seq,
+        out_qual): the merged reads in input order, packed back to back (the last four are None with fetch=False)."""
+        a = [np.ascontiguousarray(x, dtype=np.uint8) for x in (fseq, fqual, rseq, rqual)]
+        foff = np.ascontiguousarray(foff, dtype=np.int64)
+        roff = np.ascontiguousarray(roff, dtype=np.int64)
+        n = len(foff) - 1
+        if len(roff) - 1 != n:
+            raise ValueError("R1 and R2 hold different numbers of records")
+        mlen = np.zeros(n, np.int32)
+        reason = np.zeros(n, np.uint8)
+        nm, tot = C.c_int64(), C.c_int64()
+        L = lib()
+        self._chk(L.itsx_merge_pairs(self._h, _p(a[0]), _p(a[1]), _p(foff), _p(a[2]), _p(a[3]), _p(roff), n,
+                                     C.byref(params) if params is not None else None, _p(mlen), _p(reason),
+                                     C.byref(nm), C.byref(tot)))
+        if not fetch:
+            return mlen, reason, None, None, None, None
+        idx = np.empty(nm.value, np.int32)
+        oo = np.zeros(nm.value + 1, np.int64)
+        os_ = np.empty(tot.value, np.uint8)
+        oq = np.empty(tot.value, np.uint8)
+        self._chk(L.itsx_merge_fetch(self._h, _p(idx), _p(oo), _p(os_), _p(oq)))
+        return mlen, reason, idx, oo, os_, oq
+
+    def merge_stats(self):
+        st = MergeStats()
+        self._chk(lib().itsx_merge_get_stats(self._h, C.byref(st)))
+        return st
 
     # ---- whole path ---------------------------------------------------------------------------
     def run(self, seq, off, params=None, out=None):

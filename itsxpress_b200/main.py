@@ -3,9 +3,9 @@
 reference's itsxpress/main.py (parser :74-170, workflow :486-654), driving the B200 path in SeqSample.py.
 
 Stage order is the reference's: [merge pairs] -> dereplicate -> build the runtime profile set -> search ->
-ItsPosition -> Dedup -> write trimmed reads -> count reads.  Merging, --trim-ccs orientation and
---cluster_id < 1 still need vsearch (they are outside the GPU path) and fail the way the reference fails
-when vsearch is absent.
+ItsPosition -> Dedup -> write trimmed reads -> count reads.  Pair merging runs on the GPU as well
+(SeqSample._merge_reads -> itsx_merge_pairs).  --trim-ccs orientation and --cluster_id < 1 still need vsearch
+(they are outside the GPU path) and fail the way the reference fails when vsearch is absent.
 """
 import argparse
 import contextlib
@@ -278,7 +278,7 @@ def main(args=None):
         if session_tempdir is None:
             raise ValueError("Failed to create temporary directory")
         if paired_end:
-            logging.info("Sequences are paired-end in two files. They will be merged using Vsearch.")
+            logging.info("Sequences are paired-end in two files. They will be merged on the GPU (vsearch --fastq_mergepairs semantics).")
             sobj = SeqSamplePairedNotInterleaved(fastq=args.fastq, fastq2=args.fastq2, tempdir=session_tempdir,
                                                  reversed_primers=args.reversed_primers)
             sobj._merge_reads(threads=str(args.threads), stagger=args.allow_staggered_reads)

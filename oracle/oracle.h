@@ -163,6 +163,25 @@ int64_t ora_trim_bounds(const int64_t *off, int64_t nreads, const int32_t *rep_i
                         const int64_t *off_r2,
                         uint8_t *keep, int32_t *out_lo, int32_t *out_hi);
 
+/* ---- paired-end merge: `vsearch --fastq_mergepairs` as SeqSample.py:314-349 calls it (ora_merge.c) ---- */
+enum { ORA_MERGE_OK = 0, ORA_MERGE_REPEAT, ORA_MERGE_STAGGERED, ORA_MERGE_MAXDIFFS, ORA_MERGE_MAXDIFFPCT,
+       ORA_MERGE_NOKMERS, ORA_MERGE_MINSCORE, ORA_MERGE_MINOVLEN, ORA_MERGE_MAXEE, ORA_MERGE_BADQUAL };
+typedef struct {
+    int32_t maxdiffs;        /* --fastq_maxdiffs 40  (definitions.py:79) */
+    int32_t allow_stagger;   /* --fastq_allowmergestagger */
+    int32_t qmax;            /* --fastq_qmax 93      (definitions.py:82) */
+    int32_t minovlen, qmaxout, qminout, ascii;   /* vsearch defaults 10, 41, 0, 33 */
+    int32_t pad;
+    double  maxee;           /* --fastq_maxee 2 */
+    double  maxdiffpct;      /* vsearch default 100 */
+} ora_merge_params;
+void    ora_merge_default_params(ora_merge_params *p);
+int64_t ora_merge_pairs(const uint8_t *fseq, const uint8_t *fqual, const int64_t *foff, const uint8_t *rseq,
+                        const uint8_t *rqual, const int64_t *roff, int64_t npairs, const ora_merge_params *prm,
+                        int32_t *merged_len, uint8_t *reason, uint8_t *out_seq, uint8_t *out_qual, int nthreads);
+void    ora_merge_tables(const ora_merge_params *prm, double *match, double *mism, uint8_t *same, uint8_t *diff,
+                         double *q2p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,9 +54,19 @@ class OraStats(C.Structure):
                 ("bck_cells", C.c_double), ("env_cells", C.c_double)]
 
 
+class OraMergeParams(C.Structure):
+    _fields_ = [("maxdiffs", C.c_int32), ("allow_stagger", C.c_int32), ("qmax", C.c_int32), ("minovlen", C.c_int32),
+                ("qmaxout", C.c_int32), ("qminout", C.c_int32), ("ascii", C.c_int32), ("pad", C.c_int32),
+                ("maxee", C.c_double), ("maxdiffpct", C.c_double)]
+
+
+MERGE_REASONS = ("ok", "repeat", "staggered", "maxdiffs", "maxdiffpct", "nokmers", "minscore", "minovlen", "maxee",
+                 "badqual")
+
+
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("ora_hmm.c", "ora_derep.c", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("ora_hmm.c", "ora_derep.c", "ora_merge.c", "oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "clean", "all"])
     return so
@@ -105,6 +115,10 @@ def lib():
     L.ora_derep.argtypes = [vp, vp, i64, vp, vp]
     L.ora_trim_bounds.restype = i64
     L.ora_trim_bounds.argtypes = [vp, i64, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]
+    L.ora_merge_default_params.argtypes = [C.POINTER(OraMergeParams)]
+    L.ora_merge_pairs.restype = i64
+    L.ora_merge_pairs.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.POINTER(OraMergeParams), vp, vp, vp, vp, C.c_int]
+    L.ora_merge_tables.argtypes = [C.POINTER(OraMergeParams), vp, vp, vp, vp, vp]
     _LIB = L
     return L
 
@@ -289,3 +303,41 @@ def trim_bounds(off, rep_index, start, stop, tlen, mode=0, off_r2=None):
     lib().ora_trim_bounds(_ptr(off), n, _ptr(rep_index), _ptr(start), _ptr(stop), _ptr(tlen), mode, _ptr(o2),
                           _ptr(keep), _ptr(lo), _ptr(hi))
     return keep, lo, hi
+
+
+def merge_params(allow_stagger=False, **kw):
+    p = OraMergeParams()
+    lib().ora_merge_default_params(C.byref(p))
+    p.allow_stagger = int(bool(allow_stagger))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def merge_pairs(fseq, fqual, foff, rseq, rqual, roff, params=None, nthreads=0):
+    """`vsearch --fastq_mergepairs` restatement (ora_merge.c).  Returns (merged_len int32[n], reason uint8[n],
+    slot_seq, slot_qual): pair i's merged read is slot_*[foff[i] + roff[i] :][: merged_len[i]].  Raises ValueError
+    where vsearch stops with a fatal error (quality value outside [0, qmax])."""
+    a = [np.ascontiguousarray(x, dtype=np.uint8) for x in (fseq, fqual, rseq, rqual)]
+    foff = np.ascontiguousarray(foff, dtype=np.int64)
+    roff = np.ascontiguousarray(roff, dtype=np.int64)
+    n = len(foff) - 1
+    params = params or merge_params()
+    mlen = np.zeros(n, np.int32)
+    reason = np.zeros(n, np.uint8)
+    cap = int(foff[-1] + roff[-1]) + 1
+    oseq = np.zeros(cap, np.uint8)
+    oqual = np.zeros(cap, np.uint8)
+    r = lib().ora_merge_pairs(_ptr(a[0]), _ptr(a[1]), _ptr(foff), _ptr(a[2]), _ptr(a[3]), _ptr(roff), n,
+                              C.byref(params), _ptr(mlen), _ptr(reason), _ptr(oseq), _ptr(oqual), nthreads)
+    if r < 0:
+        raise ValueError("FASTQ quality value outside [0, qmax]")
+    return mlen, reason, oseq, oqual
+
+
+def merge_tables(params=None):
+    params = params or merge_params()
+    match = np.zeros((94, 94)); mism = np.zeros((94, 94)); q2p = np.zeros(94)
+    same = np.zeros((94, 94), np.uint8); diff = np.zeros((94, 94), np.uint8)
+    lib().ora_merge_tables(C.byref(params), _ptr(match), _ptr(mism), _ptr(same), _ptr(diff), _ptr(q2p))
+    return match, mism, same, diff, q2p

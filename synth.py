@@ -174,3 +174,65 @@ def make_config(name, seed=None, scale=1.0):
     else:
         files = [cfg["hmm_file"]]
     return seq, off, which, dict(cfg, search_files=files, **meta)
+
+
+def make_pairs(seed, frag_seq, frag_off, read_len=250, trim=(0, 0), err_scale=1.0, n_rate=0.002, lower_rate=0.0,
+               empty_rate=0.0):
+    """Illumina-like read pairs off the given fragments (one pair per fragment, BASELINE configs[0]/[4] shape):
+    R1 = the first read_len bases, R2 = reverse complement of the last read_len bases (a fragment shorter than the
+    read gives a staggered pair with random read-through).  Qualities decay towards the 3' end; substitution errors
+    are drawn at each base's own error probability (x err_scale); n_rate of the bases become N with Q2; `trim` =
+    (lo, hi) random 3' shortening; lower_rate of the reads are lower-cased; empty_rate of the reads are empty.
+    Returns (fseq, fqual, foff, rseq, rqual, roff), uint8 / int64 arrays."""
+    rng = np.random.default_rng(seed)
+    n = len(frag_off) - 1
+    comp = np.zeros(256, np.uint8)
+    comp[:] = ord("N")
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    out = []
+    for side in (0, 1):
+        flen = (frag_off[1:] - frag_off[:-1]).astype(np.int64)
+        rl = np.full(n, read_len, np.int64)
+        if trim[1] > 0:
+            rl -= rng.integers(trim[0], trim[1] + 1, n)
+        if empty_rate > 0:
+            rl[rng.random(n) < empty_rate] = 0
+        off = np.zeros(n + 1, np.int64)
+        off[1:] = np.cumsum(rl)
+        total = int(off[-1])
+        pos = np.arange(total, dtype=np.int64) - np.repeat(off[:-1], rl)        # position within the read
+        fl = np.repeat(flen, rl)
+        inside = pos < fl
+        start = np.repeat(frag_off[:-1], rl)
+        if side == 0:
+            src = start + np.minimum(pos, fl - 1)
+            seq = frag_seq[np.maximum(src, 0)]
+        else:
+            src = start + np.maximum(fl - 1 - pos, 0)
+            seq = comp[frag_seq[np.maximum(src, 0)]]
+        seq = np.where(inside, seq, acgt[rng.integers(0, 4, total)])              # read-through past the fragment
+        q = 38.0 - 22.0 * (pos / max(read_len, 1)) ** 2 + rng.normal(0, 3, total)
+        q = np.clip(q, 2, 41).astype(np.int64)
+        perr = np.where(q < 2, 0.75, 10.0 ** (-q / 10.0)) * err_scale
+        hit = rng.random(total) < perr
+        seq = np.where(hit, acgt[(np.searchsorted(acgt, np.minimum(seq, ord("T"))) + rng.integers(1, 4, total)) % 4], seq)
+        isn = rng.random(total) < n_rate
+        seq = np.where(isn, ord("N"), seq).astype(np.uint8)
+        q = np.where(isn, 2, q)
+        if lower_rate > 0:
+            low = np.repeat(rng.random(n) < lower_rate, rl)
+            seq = np.where(low, seq | 0x20, seq).astype(np.uint8)
+        out += [seq, (q + 33).astype(np.uint8), off]
+    return tuple(out)
+
+
+def make_pair_config(seed, n_pairs, frag_len=(260, 480), read_len=250, **kw):
+    """Random-sequence fragments of the given length range and their read pairs (merge-stage workloads)."""
+    rng = np.random.default_rng(seed)
+    flen = rng.integers(frag_len[0], frag_len[1] + 1, n_pairs).astype(np.int64)
+    foff = np.zeros(n_pairs + 1, np.int64)
+    foff[1:] = np.cumsum(flen)
+    fseq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(foff[-1]))]
+    return (fseq, foff) + make_pairs(seed + 1, fseq, foff, read_len=read_len, **kw)

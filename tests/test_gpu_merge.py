@@ -1,0 +1,204 @@
+"""GPU parity of the paired-end merge (csrc/merge.cu, itsx_merge_pairs / itsx_merge_fetch through the C ABI) against
+the CPU oracle (oracle/ora_merge.c) and the committed golden vectors: decisions, merged bases and merged qualities are
+byte-identical.  Reference call site: SeqSamplePairedNotInterleaved._merge_reads, itsxpress/SeqSample.py:266-365."""
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import TD
+from itsxpress_b200 import _lib
+from itsxpress_b200.fastq import read_fastq
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_merge.tsv")
+
+
+def _load(r1, r2):
+    b1, b2 = read_fastq(os.path.join(TD, r1)), read_fastq(os.path.join(TD, r2))
+    fs, fo = b1.seq_concat()
+    rs, ro = b2.seq_concat()
+    return b1, b2, fs, b1.qual_concat()[0], fo, rs, b2.qual_concat()[0], ro
+
+
+def _compare(oracle, ctx, fs, fq, fo, rs, rq, ro, stagger, **kw):
+    oml, owhy, oseq, oqual = oracle.merge_pairs(fs, fq, fo, rs, rq, ro, oracle.merge_params(allow_stagger=stagger, **kw))
+    ml, why, idx, ooff, gseq, gqual = ctx.merge_pairs(fs, fq, fo, rs, rq, ro, _lib.merge_params(allow_stagger=stagger, **kw))
+    assert np.array_equal(why, owhy)
+    assert np.array_equal(ml, oml)
+    assert np.array_equal(idx, np.flatnonzero(oml > 0))
+    assert np.array_equal(np.diff(ooff), oml[idx])
+    # slot layout of the oracle -> packed layout of the library
+    slot = (np.asarray(fo[:-1]) + np.asarray(ro[:-1]))[idx]
+    src = np.repeat(slot - ooff[:-1], oml[idx]) + np.arange(int(ooff[-1]), dtype=np.int64)
+    assert np.array_equal(gseq, oseq[src])
+    assert np.array_equal(gqual, oqual[src])
+    st = ctx.merge_stats()
+    assert st.n_pairs == len(ml) and st.n_merged == len(idx)
+    assert [st.by_reason[r] for r in range(10)] == np.bincount(owhy, minlength=10).tolist()
+    return ml, why, idx, ooff, gseq, gqual
+
+
+@pytest.mark.parametrize("r1,r2", [("4774-1-MSITS3_R1.fastq", "4774-1-MSITS3_R2.fastq"),
+                                   ("high_qual_scores_R1.fastq.gz", "high_qual_scores_R2.fastq.gz")])
+@pytest.mark.parametrize("stagger", [0, 1])
+def test_fixture_pairs_match_oracle_and_golden(oracle, gpu_ctx, r1, r2, stagger):
+    b1, b2, fs, fq, fo, rs, rq, ro = _load(r1, r2)
+    ml, why, idx, ooff, gseq, gqual = _compare(oracle, gpu_ctx, fs, fq, fo, rs, rq, ro, stagger)
+    name = r1.split("_R1")[0]
+    k = 0
+    for line in open(GOLD):
+        f = line.rstrip("\n").split("\t")
+        if line.startswith("#") or f[0] != name or int(f[1]) != stagger:
+            continue
+        i = int(f[2])
+        assert _lib.MERGE_REASONS[why[i]] == f[3] and ml[i] == int(f[4])
+        if ml[i]:
+            assert idx[k] == i
+            assert zlib.crc32(gseq[ooff[k]:ooff[k + 1]].tobytes()) == int(f[5])
+            assert zlib.crc32(gqual[ooff[k]:ooff[k + 1]].tobytes()) == int(f[6])
+            k += 1
+    assert k == len(idx)
+
+
+@pytest.mark.parametrize("stagger", [0, 1])
+def test_synthetic_pairs_match_oracle(oracle, gpu_ctx, stagger):
+    """Ragged input: fragments shorter and longer than the reads (staggered / no overlap), 3'-trimmed reads, sequencing
+    errors, N, lower case, empty reads."""
+    import synth
+    _, _, fs, fq, fo, rs, rq, ro = synth.make_pair_config(5, 30000, frag_len=(150, 480), trim=(0, 40), lower_rate=0.05,
+                                                          empty_rate=0.002)
+    ml, why, *_ = _compare(oracle, gpu_ctx, fs, fq, fo, rs, rq, ro, stagger)
+    hist = np.bincount(why, minlength=10)
+    assert hist[0] > 10000 and hist[5] > 0 and hist[6] > 0 and hist[8] > 0      # ok, nokmers, minscore, maxee all occur
+    assert (hist[2] > 0) == (not stagger)
+
+
+def test_other_read_lengths_and_options(oracle, gpu_ctx):
+    import synth
+    # 2 x 301 (MiSeq v3) with a tight mismatch budget and a long minimum overlap
+    _, _, fs, fq, fo, rs, rq, ro = synth.make_pair_config(9, 4000, frag_len=(300, 590), read_len=301, err_scale=3.0)
+    _compare(oracle, gpu_ctx, fs, fq, fo, rs, rq, ro, 0, maxdiffs=5, minovlen=30)
+    # short reads, unequal lengths, very noisy, lax expected-error filter
+    _, _, fs, fq, fo, rs, rq, ro = synth.make_pair_config(10, 4000, frag_len=(40, 200), read_len=75, trim=(0, 30),
+                                                          err_scale=5.0, n_rate=0.02)
+    _compare(oracle, gpu_ctx, fs, fq, fo, rs, rq, ro, 1, maxee=8.0)
+    # long reads (2 x 1000) exercise the multi-word planes and the shared-memory layout
+    _, _, fs, fq, fo, rs, rq, ro = synth.make_pair_config(12, 300, frag_len=(900, 1900), read_len=1000, err_scale=0.2)
+    _compare(oracle, gpu_ctx, fs, fq, fo, rs, rq, ro, 0, maxee=50.0)
+    # low-complexity fragments: tandem repeats make several diagonals score -> "repeat"
+    rng = np.random.default_rng(4)
+    frags = [bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), int(rng.integers(4, 30)))) * 40 for _ in range(500)]
+    flen = np.array([min(len(f), 400) for f in frags], np.int64)
+    foff = np.zeros(len(frags) + 1, np.int64)
+    foff[1:] = np.cumsum(flen)
+    fcat = np.frombuffer(b"".join(f[:400] for f in frags), np.uint8)
+    fs, fq, fo, rs, rq, ro = synth.make_pairs(21, fcat, foff, read_len=250)
+    ml, why, *_ = _compare(oracle, gpu_ctx, fs, fq, fo, rs, rq, ro, 0)
+    assert np.bincount(why, minlength=10)[1] > 100
+
+
+def test_empty_and_degenerate_input(oracle, gpu_ctx):
+    z8, z64 = np.zeros(0, np.uint8), np.zeros(1, np.int64)
+    ml, why, idx, ooff, gseq, gqual = gpu_ctx.merge_pairs(z8, z8, z64, z8, z8, z64)
+    assert len(ml) == 0 and len(idx) == 0 and ooff.tolist() == [0] and len(gseq) == 0
+    # only empty reads; one empty mate
+    fs = np.frombuffer(b"ACGTACGTACGT", np.uint8)
+    fq = np.frombuffer(b"IIIIIIIIIIII", np.uint8)
+    fo = np.array([0, 0, 12, 12], np.int64)
+    ro = np.array([0, 12, 12, 12], np.int64)
+    _compare(oracle, gpu_ctx, fs, fq, fo, fs, fq, ro, 1)
+    with pytest.raises(ValueError):
+        gpu_ctx.merge_pairs(fs, fq, fo, fs, fq, ro[:-1])
+
+
+def test_quality_above_qmax_is_an_error(gpu_ctx):
+    import synth
+    _, _, fs, fq, fo, rs, rq, ro = synth.make_pair_config(3, 100, frag_len=(300, 400))
+    fq = fq.copy()
+    fq[1234] = 33 + 94
+    with pytest.raises(_lib.ItsxError) as e:
+        gpu_ctx.merge_pairs(fs, fq, fo, rs, rq, ro)
+    assert e.value.code == -7 and "qmax" in str(e.value)
+    rq = rq.copy()
+    rq[77] = 32
+    fq[1234] = 70
+    with pytest.raises(_lib.ItsxError):
+        gpu_ctx.merge_pairs(fs, fq, fo, rs, rq, ro)
+    # the context stays usable
+    ml, *_ = gpu_ctx.merge_pairs(fs, fq, fo, rs, np.maximum(rq, 33), ro)
+    assert (ml > 0).sum() > 50
+
+
+def test_merge_reads_api_writes_seq_fq(oracle, tmp_path):
+    """SeqSamplePairedNotInterleaved._merge_reads (reference tests/test_main_pytest.py:182-194): seq.fq holds the merged
+    records in input order under R1's title, plain / .gz inputs alike, reversed_primers swaps the mates."""
+    from itsxpress_b200.SeqSample import SeqSamplePairedNotInterleaved
+    b1, b2, fs, fq, fo, rs, rq, ro = _load("4774-1-MSITS3_R1.fastq", "4774-1-MSITS3_R2.fastq")
+    oml, owhy, oseq, oqual = oracle.merge_pairs(fs, fq, fo, rs, rq, ro, oracle.merge_params(allow_stagger=True))
+    want = []
+    for i in np.flatnonzero(oml > 0):
+        s = int(fo[i] + ro[i])
+        want.append("@%s\n%s\n+\n%s\n" % (b1.title(i), oseq[s:s + oml[i]].tobytes().decode(),
+                                          oqual[s:s + oml[i]].tobytes().decode()))
+    for ext in ("", ".gz"):
+        td = str(tmp_path / ("t" + ext.strip(".")))
+        sobj = SeqSamplePairedNotInterleaved(fastq=os.path.join(TD, "4774-1-MSITS3_R1.fastq" + ext), tempdir=td,
+                                             fastq2=os.path.join(TD, "4774-1-MSITS3_R2.fastq" + ext))
+        sobj._merge_reads(stagger=True, threads=1)
+        assert sobj.seq_file == os.path.join(td, "seq.fq")
+        assert open(sobj.seq_file).read() == "".join(want)
+        sobj.deduplicate(threads=1)                      # the merged file feeds the next stage as upstream
+        assert os.path.getsize(sobj.rep_file) > 0
+    # reversed primers: R2 is the forward read
+    td = str(tmp_path / "rev")
+    sobj = SeqSamplePairedNotInterleaved(fastq=os.path.join(TD, "4774-1-MSITS3_R1.fastq"), tempdir=td,
+                                         fastq2=os.path.join(TD, "4774-1-MSITS3_R2.fastq"), reversed_primers=True)
+    sobj._merge_reads(stagger=False, threads="4")
+    rml, _, _, _ = oracle.merge_pairs(rs, rq, ro, fs, fq, fo)
+    got = read_fastq(sobj.seq_file)
+    assert got.n == int((rml > 0).sum()) and got.title(0) == b2.title(int(np.flatnonzero(rml > 0)[0]))
+
+
+def test_merge_reads_errors(tmp_path):
+    from itsxpress_b200.SeqSample import SeqSamplePairedNotInterleaved
+    r1 = os.path.join(TD, "4774-1-MSITS3_R1.fastq")
+    # a file that is not FASTQ: vsearch exits non-zero -> CalledProcessError after logging (SeqSample.py:351-358)
+    with pytest.raises(subprocess.CalledProcessError):
+        SeqSamplePairedNotInterleaved(fastq=r1, tempdir=str(tmp_path / "a"),
+                                      fastq2=os.path.join(TD, "broken.fastq"))._merge_reads(1, False)
+    # different record counts
+    short = tmp_path / "short.fastq"
+    short.write_text("".join(open(os.path.join(TD, "4774-1-MSITS3_R2.fastq")).readlines()[:400]))
+    with pytest.raises(subprocess.CalledProcessError) as e:
+        SeqSamplePairedNotInterleaved(fastq=r1, tempdir=str(tmp_path / "b"), fastq2=str(short))._merge_reads(1, False)
+    assert b"More forward reads" in e.value.stderr
+    with pytest.raises(FileNotFoundError):
+        SeqSamplePairedNotInterleaved(fastq=r1, tempdir=str(tmp_path / "c"),
+                                      fastq2=str(tmp_path / "nope.fastq"))._merge_reads(1, False)
+    with pytest.raises(ValueError):
+        SeqSamplePairedNotInterleaved(fastq=r1, tempdir=str(tmp_path / "d"), fastq2=None)._merge_reads(1, False)
+
+
+def test_full_scale_property(gpu_ctx):
+    """1 M pairs (BASELINE configs[4] sample scale is 781 250 pairs): size-independent properties instead of the oracle --
+    every merged read of an error-free pair IS its fragment, merged lengths and the packed layout are consistent, and a
+    second run gives the same bytes."""
+    import synth
+    n = 1_000_000
+    frag, foff_, fs, fq, fo, rs, rq, ro = synth.make_pair_config(77, n, frag_len=(260, 480), err_scale=0.0, n_rate=0.0)
+    ml, why, idx, ooff, gseq, gqual = gpu_ctx.merge_pairs(fs, fq, fo, rs, rq, ro)
+    flen = np.diff(foff_)
+    assert np.all(ml[idx] == flen[idx]) and np.array_equal(np.diff(ooff), ml[idx])
+    assert len(idx) > 0.9 * n
+    # nothing but the expected-error filter and the rare random second hit ("repeat", ~2e-5 of random fragments) fails
+    assert set(np.unique(why).tolist()) <= {0, 1, 8} and int((why == 1).sum()) < n // 1000
+    src = np.repeat(foff_[:-1][idx] - ooff[:-1], ml[idx]) + np.arange(int(ooff[-1]), dtype=np.int64)
+    assert np.array_equal(gseq, frag[src])
+    ml2, why2, idx2, ooff2, gseq2, gqual2 = gpu_ctx.merge_pairs(fs, fq, fo, rs, rq, ro)
+    assert np.array_equal(ml, ml2) and zlib.crc32(gqual.tobytes()) == zlib.crc32(gqual2.tobytes())
+    st = gpu_ctx.merge_stats()
+    print("merge_kernel: %.2f ms for %d pairs (%.1f M pairs/s, %.1f GB/s in+out)" % (
+        st.ms_kernel, n, n / st.ms_kernel / 1e3, (st.bytes_in + st.bytes_out) / st.ms_kernel / 1e6))
