@@ -10,12 +10,16 @@
 //     one bit per base, built with warp ballots); for a diagonal the forward planes are ANDed with the funnel-shifted
 //     planes of the reverse complement, and the 5-mer hits are  m & m>>1 & m>>2 & m>>3 & m>>4  counted with popc:
 //     32 bases per instruction instead of a byte compare per cell.  Lanes stride over the F + R - 1 diagonals.
-//   * a candidate diagonal is scored by the lane that found it, sequentially from the 3' end in double precision
-//     (the running maximum / drop test and the summation order are part of the result);
-//   * the winner is reduced over the warp (score, then smaller offset), the merged read is written by all lanes,
-//     the expected-error sum is accumulated in read order by one lane (again: summation order is part of the result).
-// HBM traffic is the reads in and the merged reads out (about 3 (F + R) bytes per pair); the kernel is bound by the
-// integer pipe (plane work) and by the latency of the sequential double-precision chains.
+//     Lanes take 32 consecutive diagonals at a time.
+//   * the candidates of a group are scored one after the other by the whole warp: lanes fetch bases, qualities and
+//     the log-odds of 32 overlap positions in parallel, then the running sum / running maximum / drop test are
+//     replayed in sequence from shared memory (double precision, from the 3' end: the summation order and the drop
+//     test are part of the result).  Candidates come up in ascending offset, which is the order the
+//     "first strictly greater score wins" rule needs;
+//   * the merged read is written by all lanes; the expected-error sum is taken from strided partial sums unless it
+//     falls within rounding distance of maxee, in which case it is replayed in read order (see there).
+// HBM traffic is the reads in and the merged reads out (about 3 (F + R) bytes per pair); the kernel is bound by
+// instruction issue (plane work on the integer pipe, the sequential double-precision replay).
 #include <cmath>
 #include <cub/cub.cuh>
 #include "itsx_internal.h"
@@ -24,7 +28,7 @@ namespace {
 
 constexpr int MG_WARPS = 4;        // pairs in flight per CTA
 constexpr int MG_NQ = 94;          // quality values 0..93
-constexpr int MG_KMER = 5, MG_MINDIAG = 4;
+constexpr int MG_MINDIAG = 4;     // a diagonal needs this many matching 5-mers to be scored
 
 struct MergeTabs {
     double  match[MG_NQ * MG_NQ], mism[MG_NQ * MG_NQ], q2p[MG_NQ];
@@ -64,10 +68,15 @@ __global__ void __launch_bounds__(MG_WARPS * 32) merge_kernel(const MergeArgs a)
     for (int t = threadIdx.x; t < MG_NQ; t += blockDim.x) s_q2p[t] = a.tabs->q2p[t];
     __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const size_t per_warp = (size_t)16 * (a.WF + a.WR) + (size_t)3 * (a.LF + a.LR);
+    const size_t per_warp = (size_t)16 * (a.WF + a.WR + 2) + (size_t)3 * (a.LF + a.LR);
     unsigned char *base = smem + per_warp * wib;
+    // rc planes carry one zero word in front and one behind the data (the shifted reads of a diagonal reach word
+    // -1 and word nwR, never further), so the diagonal loop needs no bounds checks
+    const int SR = a.WR + 2;
     uint32_t *PF = (uint32_t *)base, *PR = PF + 4 * a.WF;
-    uint8_t *fs = (uint8_t *)(PR + 4 * a.WR), *fq = fs + a.LF, *rc = fq + a.LF, *rcq = rc + a.LR, *mq = rcq + a.LR;
+    uint8_t *fs = (uint8_t *)(PR + 4 * SR), *fq = fs + a.LF, *rc = fq + a.LF, *rcq = rc + a.LR, *mq = rcq + a.LR;
+    __shared__ double s_delta[MG_WARPS][32];
+    double *sd = s_delta[wib];
     const double *tmatch = a.tabs->match, *tmism = a.tabs->mism;
     const int a0 = a.ascii;
 
@@ -113,64 +122,100 @@ __global__ void __launch_bounds__(MG_WARPS * 32) merge_kernel(const MergeArgs a)
             const uint8_t c = p < R ? rc[p] : 0;
             const uint32_t bA = __ballot_sync(0xffffffffu, c == 'A'), bC = __ballot_sync(0xffffffffu, c == 'C'),
                            bG = __ballot_sync(0xffffffffu, c == 'G'), bT = __ballot_sync(0xffffffffu, c == 'T');
-            if (lane == 0) { PR[j] = bA; PR[a.WR + j] = bC; PR[2 * a.WR + j] = bG; PR[3 * a.WR + j] = bT; }
+            if (lane == 0) { PR[1 + j] = bA; PR[SR + 1 + j] = bC; PR[2 * SR + 1 + j] = bG; PR[3 * SR + 1 + j] = bT; }
         }
+        if (lane < 4) { PR[lane * SR] = 0u; PR[lane * SR + 1 + nwR] = 0u; }
         __syncwarp();
 
+        // Diagonals in ascending order, 32 at a time: every lane counts the 5-mer hits of its own diagonal; the
+        // candidates of the group are then scored one after the other BY THE WHOLE WARP (lanes fetch the bases,
+        // qualities and table entries of 32 overlap positions in parallel; the running sum / maximum / drop logic
+        // is replayed in sequence from shared memory, warp-uniformly).  Scoring order = ascending offset, so the
+        // "first strictly greater score" rule needs no reduction.
         double best_score = 0.0;
         int best_i = 0, best_diffs = 0, hits = 0, kmers = 0;
-        for (int i = 1 + lane; i <= F + R - 1; i += 32) {
-            const int sh = F - i;                            // forward position p pairs with rc position p - sh
-            const int p0 = sh > 0 ? sh : 0, p1 = F < sh + R ? F : sh + R;
-            const int j0 = p0 >> 5, j1 = (p1 - 1) >> 5;
-            auto mword = [&](int j) -> uint32_t {
-                if (j > j1) return 0u;
-                const int t = 32 * j - sh, q = t >> 5, r = t & 31;
-                const bool lo_ok = q >= 0 && q < nwR, hi_ok = q + 1 >= 0 && q + 1 < nwR;
-                uint32_t m = 0;
-#pragma unroll
-                for (int x = 0; x < 4; x++) {
-                    const uint32_t lo = lo_ok ? PR[x * a.WR + q] : 0u, hi = hi_ok ? PR[x * a.WR + q + 1] : 0u;
-                    m |= PF[x * a.WF + j] & __funnelshift_r(lo, hi, r);
-                }
-                return m;
-            };
+        const int ndiag = F + R - 1;
+        for (int gi = 1; gi <= ndiag; gi += 32) {
+            const int i = gi + lane;
             int cnt = 0;
-            uint32_t cur = mword(j0);
-            for (int j = j0; j <= j1; j++) {
-                const uint32_t nxt = mword(j + 1);
-                const uint32_t m5 = cur & __funnelshift_r(cur, nxt, 1) & __funnelshift_r(cur, nxt, 2) &
-                                    __funnelshift_r(cur, nxt, 3) & __funnelshift_r(cur, nxt, 4);
-                cnt += __popc(m5);
-                cur = nxt;
-            }
-            if (cnt < MG_MINDIAG) continue;
-            kmers = 1;
-            double score = 0.0, high = 0.0, dropmax = 0.0;
-            int diffs = 0;
-            for (int p = p1 - 1; p >= p0; p--) {
-                const int qa = fq[p] - a0, qb = rcq[p - sh] - a0;
-                if (fs[p] == rc[p - sh]) {
-                    score += __ldg(&tmatch[qa * MG_NQ + qb]);
-                    if (score > high) high = score;
-                } else {
-                    score += __ldg(&tmism[qa * MG_NQ + qb]);
-                    diffs++;
-                    if (score < high - dropmax) dropmax = high - score;
+            if (i <= ndiag) {
+                const int sh = F - i;                        // forward position p pairs with rc position p - sh
+                const int p0 = sh > 0 ? sh : 0, p1 = F < sh + R ? F : sh + R;
+                const int j0 = p0 >> 5, j1 = (p1 - 1) >> 5;
+                // match word j = OR over the planes of  PF[j] & (PR >> (32 j - sh)):  the shift within a word (r) is the
+                // same for every j, the rc word index q advances with j, so each rc word is loaded once and carried
+                const int t0 = 32 * j0 - sh, r = t0 & 31;
+                int q = t0 >> 5;
+                auto rword = [&](int x, int qq) -> uint32_t { return PR[x * SR + 1 + qq]; };     // qq in [-1, nwR]
+                uint32_t lo0 = rword(0, q), lo1 = rword(1, q), lo2 = rword(2, q), lo3 = rword(3, q);
+                uint32_t prev = 0;
+                for (int j = j0; j <= j1 + 1; j++) {
+                    uint32_t m = 0;
+                    if (j <= j1) {
+                        const uint32_t hi0 = rword(0, q + 1), hi1 = rword(1, q + 1), hi2 = rword(2, q + 1),
+                                       hi3 = rword(3, q + 1);
+                        m = (PF[j] & __funnelshift_r(lo0, hi0, r)) | (PF[a.WF + j] & __funnelshift_r(lo1, hi1, r)) |
+                            (PF[2 * a.WF + j] & __funnelshift_r(lo2, hi2, r)) |
+                            (PF[3 * a.WF + j] & __funnelshift_r(lo3, hi3, r));
+                        lo0 = hi0; lo1 = hi1; lo2 = hi2; lo3 = hi3;
+                        q++;
+                    }
+                    if (j > j0) {           // 5-mer hits that START in word j - 1 (bits 32.. come from word j)
+                        const uint32_t m5 = prev & __funnelshift_r(prev, m, 1) & __funnelshift_r(prev, m, 2) &
+                                            __funnelshift_r(prev, m, 3) & __funnelshift_r(prev, m, 4);
+                        cnt += __popc(m5);
+                    }
+                    prev = m;
                 }
             }
-            if (dropmax >= 16.0) score = 0.0;
-            if (score >= 16.0) hits++;
-            if (score > best_score) { best_score = score; best_i = i; best_diffs = diffs; }
-        }
-        // a lane's diagonals ascend, so its best is its first maximum; across lanes: larger score, then smaller offset
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            const double os = __shfl_xor_sync(0xffffffffu, best_score, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, best_i, o), od = __shfl_xor_sync(0xffffffffu, best_diffs, o);
-            if (os > best_score || (os == best_score && oi < best_i)) { best_score = os; best_i = oi; best_diffs = od; }
-            hits += __shfl_xor_sync(0xffffffffu, hits, o);
-            kmers |= __shfl_xor_sync(0xffffffffu, kmers, o);
+            unsigned cand = __ballot_sync(0xffffffffu, cnt >= MG_MINDIAG);
+            while (cand) {
+                const int ci = gi + __ffs(cand) - 1;
+                cand &= cand - 1;
+                kmers = 1;
+                const int sh = F - ci;
+                const int p0 = sh > 0 ? sh : 0, p1 = F < sh + R ? F : sh + R;
+                const int len = p1 - p0;
+                double score = 0.0, high = 0.0, dropmax = 0.0;
+                int diffs = 0;
+                bool pend = false;
+                for (int e0 = 0; e0 < len; e0 += 32) {
+                    const int e = e0 + lane, p = p1 - 1 - e;      // scoring runs from the 3' end of the forward read
+                    bool eq = true;
+                    double d = 0.0;
+                    if (e < len) {
+                        const int qa = fq[p] - a0, qb = rcq[p - sh] - a0;
+                        eq = fs[p] == rc[p - sh];
+                        d = __ldg(eq ? &tmatch[qa * MG_NQ + qb] : &tmism[qa * MG_NQ + qb]);
+                    }
+                    const unsigned eqm = __ballot_sync(0xffffffffu, eq);
+                    // "fast" element: a match whose log-odds are >= 0 (all but the Q < 2 corner, where rounding can
+                    // leave -1e-16).  It cannot lower the score, so within a run of fast elements the running
+                    // maximum only has to be taken when the run ends (pend).  Everything else is replayed literally.
+                    const unsigned fastm = __ballot_sync(0xffffffffu, eq && d >= 0.0);
+                    __syncwarp();
+                    sd[lane] = d;
+                    __syncwarp();
+                    const int ne = min(32, len - e0);
+                    diffs += __popc(~eqm);
+                    for (int t = 0; t < ne; t++) {
+                        if ((fastm >> t) & 1u) {
+                            score += sd[t];
+                            pend = true;
+                        } else {
+                            if (pend) { if (score > high) high = score; pend = false; }
+                            score += sd[t];
+                            if ((eqm >> t) & 1u) { if (score > high) high = score; }
+                            else if (score < high - dropmax) dropmax = high - score;
+                        }
+                    }
+                    // once the drop below the maximum has reached 16 bits the diagonal scores 0 whatever follows
+                    if (dropmax >= 16.0) break;
+                }
+                if (dropmax >= 16.0) score = 0.0;
+                if (score >= 16.0) hits++;
+                if (score > best_score) { best_score = score; best_i = ci; best_diffs = diffs; }
+            }
         }
         int why = ITSX_MERGE_OK;
         if (hits > 1) why = ITSX_MERGE_REPEAT;
@@ -188,6 +233,7 @@ __global__ void __launch_bounds__(MG_WARPS * 32) merge_kernel(const MergeArgs a)
             n = nA + ov + (R - r0 - ov);
             const uint8_t *tsame = a.tabs->same, *tdiff = a.tabs->diff;
             const int64_t slot = fo + ro;
+            double part = 0.0;
             for (int m = lane; m < n; m += 32) {
                 uint8_t s, q;
                 if (m < nA) { s = fs[m]; q = fq[m]; }
@@ -203,15 +249,28 @@ __global__ void __launch_bounds__(MG_WARPS * 32) merge_kernel(const MergeArgs a)
                 a.oseq[slot + m] = s;
                 a.oqual[slot + m] = q;
                 mq[m] = q;
+                part += s_q2p[q - a0];
             }
+            // Expected errors: the reference sums them in read order and the comparison with maxee is part of the
+            // result.  A sum in any other order differs from it by less than 2 n u sum|x| (u = 2^-53; n < 2^14 here),
+            // i.e. by far less than 1e-9 relative, so the strided partial sums decide unless the total lies inside
+            // that band around maxee -- only then is the sum replayed in read order by one lane.
+#pragma unroll
+            for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             __syncwarp();
-            int ok = 1;
-            if (lane == 0) {
-                double ee = 0.0;
-                for (int m = 0; m < n; m++) ee += s_q2p[mq[m] - a0];
-                ok = ee <= a.maxee;
+            int ok;
+            const double band = 1e-9 * (1.0 + fabs(part));
+            if (part > a.maxee + band) ok = 0;
+            else if (part < a.maxee - band) ok = 1;
+            else {
+                ok = 1;
+                if (lane == 0) {
+                    double ee = 0.0;
+                    for (int m = 0; m < n; m++) ee += s_q2p[mq[m] - a0];
+                    ok = ee <= a.maxee;
+                }
+                ok = __shfl_sync(0xffffffffu, ok, 0);
             }
-            ok = __shfl_sync(0xffffffffu, ok, 0);
             if (!ok) { why = ITSX_MERGE_MAXEE; n = 0; }
         }
         if (lane == 0) {
@@ -367,7 +426,7 @@ int itsx_merge_pairs(itsx_ctx *c, const uint8_t *fseq, const uint8_t *fqual, con
     a.WR = std::max(1, (maxR + 31) / 32);
     a.LF = (maxF + 3) & ~3;
     a.LR = (maxR + 3) & ~3;
-    const size_t per_warp = (size_t)16 * (a.WF + a.WR) + (size_t)3 * (a.LF + a.LR);
+    const size_t per_warp = (size_t)16 * (a.WF + a.WR + 2) + (size_t)3 * (a.LF + a.LR);
     const size_t smem = per_warp * MG_WARPS;
     if (smem > 200 * 1024) {
         c->err = "merge: reads longer than the shared-memory staging allows (" + std::to_string(maxF) + " + " +

@@ -16,6 +16,10 @@
  *             tests/test_data/ex_tmpdir/{seq.fq.gz,uc.txt,rep.fa}.
  *   trim    : pinned byte-for-byte against tests/test_data/t2_r1.fq, t2_r2.fq and
  *             singleOut/.../4774-1-MSITS3_0_L001_R1_001.fastq.gz.
+ *   merge   : (ora_merge.c, `vsearch --fastq_mergepairs` as SeqSample.py:314-349 calls it) "parity unpinned"
+ *             against a real vsearch run: the reference holds no vsearch-made merge output.  Checked against an
+ *             independent definition-level Python statement (tests/golden/make_merge_golden.py), the merged bases
+ *             of the reference's older merged fixture, and constructed known answers.
  *   hmm     : "parity unpinned" against real hmmsearch output (no HMMER binary, the
  *             domtbl.txt fixture and F.hmm are missing from the mount).  What IS
  *             pinned: the STATS LOCAL calibration lines of every profile (lambda exactly,

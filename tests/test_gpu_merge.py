@@ -85,6 +85,15 @@ def test_other_read_lengths_and_options(oracle, gpu_ctx):
     _, _, fs, fq, fo, rs, rq, ro = synth.make_pair_config(10, 4000, frag_len=(40, 200), read_len=75, trim=(0, 30),
                                                           err_scale=5.0, n_rate=0.02)
     _compare(oracle, gpu_ctx, fs, fq, fo, rs, rq, ro, 1, maxee=8.0)
+    # qualities 0 and 1 (error probability pinned at 0.75; log-odds round to +-1e-16 there)
+    _, _, fs, fq, fo, rs, rq, ro = synth.make_pair_config(13, 4000, frag_len=(260, 480), err_scale=2.0)
+    rng = np.random.default_rng(13)
+    fq, rq = fq.copy(), rq.copy()
+    fq[rng.random(len(fq)) < 0.15] = 33
+    rq[rng.random(len(rq)) < 0.15] = 34
+    fq[rng.random(len(fq)) < 0.05] = 34
+    ml, why, *_ = _compare(oracle, gpu_ctx, fs, fq, fo, rs, rq, ro, 0, maxee=200.0)
+    assert (ml > 0).sum() > 1000
     # long reads (2 x 1000) exercise the multi-word planes and the shared-memory layout
     _, _, fs, fq, fo, rs, rq, ro = synth.make_pair_config(12, 300, frag_len=(900, 1900), read_len=1000, err_scale=0.2)
     _compare(oracle, gpu_ctx, fs, fq, fo, rs, rq, ro, 0, maxee=50.0)
@@ -202,3 +211,95 @@ def test_full_scale_property(gpu_ctx):
     st = gpu_ctx.merge_stats()
     print("merge_kernel: %.2f ms for %d pairs (%.1f M pairs/s, %.1f GB/s in+out)" % (
         st.ms_kernel, n, n / st.ms_kernel / 1e3, (st.bytes_in + st.bytes_out) / st.ms_kernel / 1e6))
+
+
+def _oracle_pipeline(oracle, r1, r2, stagger=False):
+    """merge -> derep -> search (M.hmm 3_/4_) -> ItsPosition with the CPU oracle; returns what the trim needs."""
+    from conftest import HMM_DIR
+    b1, b2, fs, fq, fo, rs, rq, ro = _load(r1, r2)
+    oml, _, oseq, oqual = oracle.merge_pairs(fs, fq, fo, rs, rq, ro, oracle.merge_params(allow_stagger=stagger))
+    midx = np.flatnonzero(oml > 0)
+    moff = np.zeros(len(midx) + 1, np.int64)
+    moff[1:] = np.cumsum(oml[midx])
+    slot = (fo[:-1] + ro[:-1])[midx]
+    src = np.repeat(slot - moff[:-1], oml[midx]) + np.arange(int(moff[-1]), dtype=np.int64)
+    mseq, mqual = oseq[src], oqual[src]
+    rep, _, _ = oracle.derep(mseq, moff)
+    uidx = np.flatnonzero(rep == np.arange(len(midx)))
+    parts = [mseq[moff[i]:moff[i + 1]] for i in uidx]
+    uoff = np.zeros(len(uidx) + 1, np.int64)
+    uoff[1:] = np.cumsum([len(p) for p in parts])
+    db = oracle.ProfileDB([os.path.join(HMM_DIR, "M.hmm")], ["3_", "4_"])
+    rows, _, _ = db.search(oracle.digitize(np.concatenate(parts).tobytes()), uoff)
+    side = np.array([0 if n.startswith("3_") else 1 for n in db.names], np.int8)
+    pos = oracle.itspos(rows, side, np.diff(uoff).astype(np.int32))
+    n = len(midx)
+    s_r = np.full(n, -1, np.int32); e_r = s_r.copy(); t_r = s_r.copy()
+    s_r[uidx] = pos["start"]; e_r[uidx] = pos["stop"]; t_r[uidx] = pos["tlen"]
+    return b1, b2, fo, ro, midx, moff, mseq, mqual, rep, s_r, e_r, t_r
+
+
+def test_cli_paired_end_to_end(tmp_path, oracle):
+    """BASELINE configs[0]: `itsxpress --fastq R1 --fastq2 R2 --region ITS2` on the bundled pair sample (reference
+    test_main_paired, tests/test_main_pytest.py:228-254; Metazoa profiles, F.hmm is missing from the mount), every
+    stage on the GPU -- merged output and unmerged (--outfile2) output byte-identical to the oracle pipeline."""
+    from itsxpress_b200 import fastq as fq
+    from itsxpress_b200 import main as cli
+    r1n, r2n = "4774-1-MSITS3_R1.fastq", "4774-1-MSITS3_R2.fastq"
+    b1, b2, fo, ro, midx, moff, mseq, mqual, rep, s_r, e_r, t_r = _oracle_pipeline(oracle, r1n, r2n, stagger=True)      # the CLI's default, main.py:120-123
+    # merged output: records carry R1's title
+    out = str(tmp_path / "merged.fastq")
+    cli.main(args=cli.myparser().parse_args(["--fastq", os.path.join(TD, r1n), "--fastq2", os.path.join(TD, r2n),
+                                             "--outfile", out, "--region", "ITS2", "--taxa", "Metazoa",
+                                             "--log", str(tmp_path / "l1.txt")]))
+    keep, lo, hi = oracle.trim_bounds(moff, rep, s_r, e_r, t_r, mode=0)
+    ki = np.flatnonzero(keep)
+    assert len(ki) > 150
+    want = []
+    for k in ki:
+        a, b = int(moff[k] + lo[k]), int(moff[k] + hi[k])
+        want.append("@%s\n%s\n+\n%s\n" % (b1.title(int(midx[k])), mseq[a:b].tobytes().decode(), mqual[a:b].tobytes().decode()))
+    assert open(out).read() == "".join(want)
+    # unmerged output: R1[start:stop], R2[tlen-stop:tlen-start] of the pairs whose merged read was kept
+    o1, o2 = str(tmp_path / "r1.fastq.gz"), str(tmp_path / "r2.fastq.gz")
+    cli.main(args=cli.myparser().parse_args(["--fastq", os.path.join(TD, r1n), "--fastq2", os.path.join(TD, r2n),
+                                             "--outfile", o1, "--outfile2", o2, "--region", "ITS2", "--taxa", "Metazoa",
+                                             "--log", str(tmp_path / "l2.txt")]))
+    for path, batch, off_all, mode in ((o1, b1, fo, 2), (o2, b2, ro, 1)):
+        ln = np.diff(off_all)[midx]
+        off_m = np.zeros(len(midx) + 1, np.int64)
+        off_m[1:] = np.cumsum(ln)
+        keep, lo, hi = oracle.trim_bounds(off_m, rep, s_r, e_r, t_r, mode=mode, off_r2=off_m)
+        ki = np.flatnonzero(keep)
+        assert fq._open_bytes(path) == fq.format_records(batch, midx[ki], lo[ki], hi[ki])
+
+
+def test_q2_trim_pair_actions(tmp_path):
+    """BASELINE configs[4] at fixture scale: the QIIME 2 actions trim-pair and trim-pair-output-unmerged on the
+    reference's own paired per-sample directory (tests/test_data/paired/.../data; reference q2_itsxpress.py:156-230,
+    tests/test_q2_itsxpress.py), merge included on the GPU.  Plugin and CLI both allow staggered merges by default
+    (q2_itsxpress.py:161,199; main.py:120-123); output bytes equal the CLI's."""
+    from itsxpress_b200 import fastq as fq
+    from itsxpress_b200 import main as cli
+    from itsxpress_b200 import q2_itsxpress as q2
+    src = os.path.join(TD, "paired", "445cf54a-bf06-4852-8010-13a60fa1598c", "data")
+    n1, n2 = "4774-1-MSITS3_0_L001_R1_001.fastq.gz", "4774-1-MSITS3_1_L001_R2_001.fastq.gz"
+    res = q2.trim_pair_output_unmerged(q2.PerSampleDir(src), region="ITS2", taxa="M")
+    o1, o2 = os.path.join(str(res), n1), os.path.join(str(res), n2)
+    b1, b2 = fq.read_fastq(o1), fq.read_fastq(o2)
+    assert b1.n == b2.n and b1.n > 150
+    assert [b1.title(i).split()[0] for i in range(b1.n)] == [b2.title(i).split()[0] for i in range(b2.n)]
+    c1, c2 = str(tmp_path / "c1.fastq"), str(tmp_path / "c2.fastq")
+    cli.main(args=cli.myparser().parse_args(["--fastq", os.path.join(src, n1), "--fastq2", os.path.join(src, n2),
+                                             "--outfile", c1, "--outfile2", c2, "--region", "ITS2", "--taxa", "Metazoa",
+                                             "--log", str(tmp_path / "l.txt")]))
+    assert fq._open_bytes(o1) == open(c1, "rb").read() and fq._open_bytes(o2) == open(c2, "rb").read()
+    man = open(os.path.join(str(res), "MANIFEST")).read().splitlines()
+    assert man == ["sample-id,filename,direction", "4774-1-MSITS3,%s,forward" % n1, "4774-1-MSITS3,%s,reverse" % n2]
+    # merged output
+    res = q2.trim_pair(q2.PerSampleDir(src), region="ITS2", taxa="M")
+    m = fq.read_fastq(os.path.join(str(res), n1))
+    assert m.n == b1.n and not os.path.exists(os.path.join(str(res), n2))
+    # reversed primers: the mates swap roles before the merge
+    res = q2.trim_pair(q2.PerSampleDir(src), region="ITS2", taxa="M", reversed_primers=True)
+    assert fq.read_fastq(os.path.join(str(res), n1)).n > 0
