@@ -57,8 +57,8 @@ class PerSampleDir:
 class CasavaDir:
     """Stand-in for CasavaOneEightSingleLanePerSampleDirFmt(): str() is a fresh directory to write into."""
 
-    def __init__(self):
-        self.path = tempfile.mkdtemp(prefix="q2-CasavaOneEightSingleLanePerSampleDirFmt-")
+    def __init__(self, path=None):
+        self.path = path if path is not None else tempfile.mkdtemp(prefix="q2-CasavaOneEightSingleLanePerSampleDirFmt-")
 
     def __str__(self):
         return self.path
@@ -125,6 +125,37 @@ def trim_pair_output_unmerged(per_sample_sequences, region, taxa="F", threads=1,
                 cluster_id=cluster_id, trim_ccs=False)
 
 
+def _process_sample(sample, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
+                    allow_staggered_reads, cluster_id, trim_ccs):
+    """One sample of the artifact, start to finish (the body of the reference's loop, q2_itsxpress.py:273-333)."""
+    sobj = _set_fastqs_and_check(fastq=sample.forward, fastq2=sample.reverse if paired_in else None,
+                                 tempdir=tempdir, sample_id=sample.Index, single_end=not paired_in,
+                                 reversed_primers=reversed_primers, allow_staggered_reads=allow_staggered_reads,
+                                 threads=threads)
+    if trim_ccs:
+        sobj.orient_reads(threads=threads)
+    if math.isclose(cluster_id, 1, rel_tol=1e-05):
+        sobj.deduplicate(threads=threads)
+    else:
+        sobj.cluster(threads=threads, cluster_id=cluster_id)
+    try:
+        hmmfile = itsxpress.create_runtime_hmm(taxa, region, tempdir)
+        sobj._search(hmmfile=hmmfile, threads=threads)
+    except (ModuleNotFoundError, FileNotFoundError, NotADirectoryError):
+        raise ValueError("the profile search could not run: libitsx_b200 or a profile file is missing")
+    its_pos = itsxpress.ItsPosition(domtable=sobj.dom_file, region=region)
+    dedup_obj = itsxpress.Dedup(uc_file=sobj.uc_file, rep_file=sobj.rep_file, seq_file=sobj.seq_file,
+                                fastq=sobj.r1, fastq2=sobj.fastq2)
+    out_fwd = os.path.join(str(results), pathlib.Path(sample.forward).name)
+    if paired_out:
+        out_rev = os.path.join(str(results), pathlib.Path(sample.reverse).name)
+        dedup_obj.create_paired_trimmed_seqs(out_fwd, out_rev, gzipped=True, zstd_file=False, itspos=its_pos,
+                                             wri_file=True, trim_ccs=trim_ccs)
+    else:
+        dedup_obj.create_trimmed_seqs(out_fwd, gzipped=True, zstd_file=False, itspos=its_pos, wri_file=True,
+                                      tempdir=sobj.tempdir, trim_ccs=trim_ccs)
+
+
 def main(per_sample_sequences, threads, taxa, region, paired_in, paired_out, reversed_primers, allow_staggered_reads,
          cluster_id, trim_ccs=False):
     taxa = _taxa_prefix_to_taxa(taxa)
@@ -135,32 +166,8 @@ def main(per_sample_sequences, threads, taxa, region, paired_in, paired_out, rev
         raise ValueError("Could not create temporary directory")
     results = CasavaOneEightSingleLanePerSampleDirFmt() if CasavaOneEightSingleLanePerSampleDirFmt else CasavaDir()
     for sample in samples.itertuples():
-        sobj = _set_fastqs_and_check(fastq=sample.forward, fastq2=sample.reverse if paired_in else None,
-                                     tempdir=tempdir, sample_id=sample.Index, single_end=not paired_in,
-                                     reversed_primers=reversed_primers, allow_staggered_reads=allow_staggered_reads,
-                                     threads=threads)
-        if trim_ccs:
-            sobj.orient_reads(threads=threads)
-        if math.isclose(cluster_id, 1, rel_tol=1e-05):
-            sobj.deduplicate(threads=threads)
-        else:
-            sobj.cluster(threads=threads, cluster_id=cluster_id)
-        try:
-            hmmfile = itsxpress.create_runtime_hmm(taxa, region, tempdir)
-            sobj._search(hmmfile=hmmfile, threads=threads)
-        except (ModuleNotFoundError, FileNotFoundError, NotADirectoryError):
-            raise ValueError("the profile search could not run: libitsx_b200 or a profile file is missing")
-        its_pos = itsxpress.ItsPosition(domtable=sobj.dom_file, region=region)
-        dedup_obj = itsxpress.Dedup(uc_file=sobj.uc_file, rep_file=sobj.rep_file, seq_file=sobj.seq_file,
-                                    fastq=sobj.r1, fastq2=sobj.fastq2)
-        out_fwd = os.path.join(str(results), pathlib.Path(sample.forward).name)
-        if paired_out:
-            out_rev = os.path.join(str(results), pathlib.Path(sample.reverse).name)
-            dedup_obj.create_paired_trimmed_seqs(out_fwd, out_rev, gzipped=True, zstd_file=False, itspos=its_pos,
-                                                 wri_file=True, trim_ccs=trim_ccs)
-        else:
-            dedup_obj.create_trimmed_seqs(out_fwd, gzipped=True, zstd_file=False, itspos=its_pos, wri_file=True,
-                                          tempdir=sobj.tempdir, trim_ccs=trim_ccs)
+        _process_sample(sample, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
+                        allow_staggered_reads, cluster_id, trim_ccs)
     if trim_ccs:
         print("\n" + "=" * 80 + "\nPacBio CCS trimming complete.\n\nCAUTION: data contain fake sequence at the ends "
               "needed for DADA2\n\nqiime dada2 denoise-ccs --p-front GACAGGTACAAGAAGGA --p-adapter ACTGGAGACTGGGTTAA\n"
@@ -169,3 +176,58 @@ def main(per_sample_sequences, threads, taxa, region, paired_in, paired_out, rev
         results.write_manifest()
     shutil.rmtree(tempdir)
     return results
+
+
+def deal_samples(sizes, world):
+    """Whole samples dealt to `world` ranks, largest first onto the least-loaded rank (derep, Z and domZ are per
+    sample upstream, q2_itsxpress.py:273-296, so samples are independent units: SURVEY 8e).  Returns the owner rank of
+    every sample; deterministic, so every rank computes the same deal without talking to the others."""
+    load = [0] * world
+    owner = [0] * len(sizes)
+    for i in sorted(range(len(sizes)), key=lambda k: (-int(sizes[k]), k)):
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += int(sizes[i])
+    return owner
+
+
+def main_sharded(per_sample_sequences, outdir, region, taxa="F", threads=1, paired_in=True, paired_out=True,
+                 reversed_primers=False, allow_staggered_reads=True, cluster_id=default_cluster_id, trim_ccs=False,
+                 rank=None, world=None, barrier=None, process=None):
+    """The samples of one artifact over the GPUs of a box: one process per GPU (``torchrun``; RANK / WORLD_SIZE /
+    LOCAL_RANK from the environment), every rank runs the per-sample pipeline of ``main`` on the samples dealt to it
+    and writes their files into the shared directory ``outdir``; there is no data-path collective.  ``barrier`` (default:
+    ``torch.distributed.barrier`` when a process group is up) separates the work from rank 0 writing MANIFEST and
+    metadata.yml.  Returns (CasavaDir over outdir, sample ids this rank processed)."""
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    taxa = _taxa_prefix_to_taxa(taxa)
+    samples = per_sample_sequences.manifest.view(pd.DataFrame)
+    rows = list(samples.itertuples())
+    sizes = [os.path.getsize(s.forward) + (os.path.getsize(s.reverse) if paired_in else 0) for s in rows]
+    owner = deal_samples(sizes, world)
+    os.makedirs(outdir, exist_ok=True)
+    results = CasavaDir(outdir)
+    tempdir = tempfile.mkdtemp(prefix="itsxpress_r%d_" % rank)
+    process = process or _process_sample
+    mine = []
+    try:
+        for sample, o in zip(rows, owner):
+            if o != rank:
+                continue
+            process(sample, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
+                    allow_staggered_reads, cluster_id, trim_ccs)
+            mine.append(sample.Index)
+    finally:
+        shutil.rmtree(tempdir, ignore_errors=True)
+    if barrier is None and world > 1:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            barrier = dist.barrier
+    if barrier is not None:
+        barrier()
+    if rank == 0:
+        results.write_manifest()
+    if barrier is not None:
+        barrier()
+    return results, mine

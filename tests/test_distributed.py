@@ -85,3 +85,44 @@ def test_device_driver_index_helpers_on_cpu_tensors():
     out, off = _gather_segments_dev(torch, torch.from_numpy(src), torch.zeros(0, dtype=torch.int64),
                                     torch.zeros(0, dtype=torch.int64))
     assert out.numel() == 0 and off.tolist() == [0]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_q2_samples_dealt_to_ranks(tmp_path, world):
+    """q2_itsxpress.main_sharded over gloo: every sample of a 7-sample paired artifact is processed by exactly one
+    rank, the loads are balanced by input size, all outputs land in the shared directory and rank 0's MANIFEST lists
+    them all (whole samples shard across GPUs with no data-path collective)."""
+    import gzip
+    from itsxpress_b200 import q2_itsxpress as q2
+    src = tmp_path / "in"
+    src.mkdir()
+    lines = ["sample-id,filename,direction"]
+    sizes = {}
+    rng = np.random.default_rng(5)
+    for k, n in enumerate([900, 50, 400, 420, 30, 880, 10]):
+        sid = "S%d" % k
+        for d, tag in (("forward", "R1"), ("reverse", "R2")):
+            fn = "%s_%d_L001_%s_001.fastq.gz" % (sid, k, tag)
+            with gzip.open(str(src / fn), "wb", compresslevel=1) as f:
+                f.write(bytes(rng.integers(65, 90, n * 50, dtype=np.uint8)))
+            lines.append("%s,%s,%s" % (sid, fn, d))
+            sizes[sid] = sizes.get(sid, 0) + os.path.getsize(str(src / fn))
+    (src / "MANIFEST").write_text("\n".join(lines) + "\n")
+    out = tmp_path / "out"
+    port = 29750 + world
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_q2_worker.py"), str(src),
+                                       str(out)], env=env))
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    mine = [open(str(out / ("rank%d.txt" % r))).read().split() for r in range(world)]
+    assert sorted(sum(mine, [])) == sorted(sizes)                       # each sample exactly once
+    loads = [sum(sizes[s] for s in m) for m in mine]
+    assert max(loads) <= sum(loads) / world + max(sizes.values())       # greedy bound: within one sample of the mean
+    man = open(str(out / "MANIFEST")).read().splitlines()
+    assert man[0] == "sample-id,filename,direction" and len(man) == 1 + 14
+    assert sorted(l.split(",")[1] for l in man[1:]) == sorted(l.split(",")[1] for l in lines[1:])
+    assert q2.deal_samples([5, 5, 5, 5], 2) == [0, 1, 0, 1] and q2.deal_samples([], 4) == []
