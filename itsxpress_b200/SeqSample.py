@@ -65,6 +65,11 @@ class _Session:
         self.nseq = 0
         self.seq_path = None
         self.seq_ids = None
+        # paired input merged by _merge_reads in this process: record k of seq_file is pair pair_index[k] of the
+        # R1 / R2 files (their paths and parsed batches are kept for create_paired_trimmed_seqs)
+        self.pair_index = None
+        self.pair_files = None     # (abspath R1, abspath R2)
+        self.pair_batches = None   # (FastqBatch R1, FastqBatch R2)
 
     def ensure_seq_ids(self):
         if self.seq_ids is None and self.batch is not None and self.first is not None:
@@ -106,6 +111,7 @@ class SeqSample:
         self.r1 = None
         self.fastq2 = None
         self._session = None
+        self._merged = None            # (seq.fq path, FastqBatch, bases, offsets) left by _merge_reads for deduplicate
         self.materialize = None        # True / False overrides TEMP_FILE_POLICY (main.py sets it for --keeptemp)
 
     def _want_files(self, n_reads):
@@ -143,8 +149,13 @@ class SeqSample:
         try:
             self.uc_file = os.path.join(self.tempdir, "uc.txt")
             self.rep_file = os.path.join(self.tempdir, "rep.fa")
-            batch = fq.read_fastq(self.seq_file)
-            seq, off = batch.seq_concat()
+            merged = getattr(self, "_merged", None)
+            self._merged = None
+            if merged is not None and merged[0] == os.path.abspath(self.seq_file):
+                batch, seq, off = merged[1:4]          # records _merge_reads just wrote to seq_file
+            else:
+                batch = fq.read_fastq(self.seq_file)
+                seq, off = batch.seq_concat()
             ctx = get_context()
             rep, strand, nu = ctx.derep(seq, off)
             _GENERATION += 1
@@ -154,6 +165,8 @@ class SeqSample:
             s.uid = np.searchsorted(first, rep).astype(np.int32) if nu else np.zeros(0, np.int32)
             s.derep_gen = _GENERATION
             s.seq_path = os.path.abspath(self.seq_file)
+            if merged is not None and merged[0] == s.seq_path:
+                s.pair_index, s.pair_files, s.pair_batches = merged[4], merged[5], merged[6]
             s.files = self._want_files(batch.n)
             if s.files:
                 ids = s.ids
@@ -300,8 +313,12 @@ class SeqSamplePairedNotInterleaved(SeqSample):
                 raise
             except (ValueError, _lib.ItsxError) as e:
                 raise subprocess.CalledProcessError(1, argv, stderr=str(e).encode("utf-8")) from e
+            data = fq.format_gathered(b1, idx, out_off, out_seq, out_qual)
             with open(seq_file, "wb") as f:
-                f.write(fq.format_gathered(b1, idx, out_off, out_seq, out_qual))
+                f.write(data)
+            # deduplicate() takes the merged records from here instead of reading seq.fq back and scanning it again
+            self._merged = (os.path.abspath(seq_file), fq.batch_of_gathered(data, b1, idx, out_off), out_seq, out_off,
+                            idx, (os.path.abspath(self.r1), os.path.abspath(self.fastq2)), (b1, b2))
             st = ctx.merge_stats()
             why = ", ".join("%s %d" % (_lib.MERGE_REASONS[r], st.by_reason[r])
                             for r in range(1, len(_lib.MERGE_REASONS)) if st.by_reason[r])
@@ -557,6 +574,11 @@ class Dedup:
             dev = itspos._dev
             if batch is s.batch:
                 uid = s.uid
+            elif s.pair_batches is not None and batch is s.pair_batches[0]:
+                # R1 of the pairs this sample was merged from: merged record k came from pair pair_index[k] (same id,
+                # vsearch keeps R1's title), pairs that did not merge are absent from the map (SeqSample.py:591-598)
+                uid = np.full(batch.n, -1, np.int32)
+                uid[s.pair_index] = s.uid
             else:
                 if ids is None:
                     ids = batch.ids()
@@ -589,10 +611,10 @@ class Dedup:
         return (uid, np.asarray(start, np.int32), np.asarray(stop, np.int32), np.asarray(tlen, np.int32),
                 len(start))
 
-    def _trim_file(self, batch, ids, itspos, mode, trim_ccs):
+    def _trim_file(self, batch, ids, itspos, mode, trim_ccs, table=None):
         """FASTQ text of ``batch`` trimmed on the GPU (mode 0 single, 2 paired R1, 1 paired R2)."""
         global _GENERATION
-        uid, start, stop, tlen, nu = self._unique_table(batch, ids, itspos)
+        uid, start, stop, tlen, nu = table if table is not None else self._unique_table(batch, ids, itspos)
         if mode != 0 and np.any((tlen < 0) & (start >= 0) & (stop >= 0) & (start < stop)):
             raise ValueError("Could not retrieve valid positions for a kept sequence (tlen is missing)")
         ctx = get_context()
@@ -620,7 +642,7 @@ class Dedup:
             if n_empty and not trim_ccs:
                 print("Total number of sequences that are empty: ", n_empty)
             return
-        fq.write_compressed(outfile, text, gzipped=gzipped, zstd_file=zstd_file)
+        fq.write_compressed(outfile, text, gzipped=gzipped, zstd_file=zstd_file, n_records=len(ki))
 
     def create_paired_trimmed_seqs(self, outfile1, outfile2, gzipped, zstd_file, itspos, wri_file, trim_ccs=False):
         """Write R1 and R2 trimmed but unmerged (for DADA2), input order (SeqSample.py:713-790)."""
@@ -632,22 +654,28 @@ class Dedup:
                 (f1.endswith(plain) and f2.endswith(plain))):
             raise ValueError("Fastq and Fastq2 files should both be gzipped (.gz), zstd compressed (.zst) or both "
                              "be uncompressed. Mixed input is not accepted.")
-        b1, b2 = fq.read_fastq(f1), fq.read_fastq(f2)
-        n = min(b1.n, b2.n)                     # zip() semantics
-        if b1.n != n:
-            b1 = _head(b1, n)
-        if b2.n != n:
-            b2 = _head(b2, n)
-        ids1 = b1.ids()                         # the filter is keyed on R1's id (SeqSample.py:591)
-        t1, k1, e1 = self._trim_file(b1, ids1, itspos, 2, trim_ccs)
-        t2, k2, e2 = self._trim_file(b2, ids1, itspos, 1, trim_ccs)      # keyed on R1's ids
+        ps = self._session
+        if ps is not None and ps.pair_batches is not None and ps.pair_files == (os.path.abspath(f1), os.path.abspath(f2)):
+            b1, b2 = ps.pair_batches            # parsed by _merge_reads a moment ago; equal record counts
+            ids1 = None                         # ... and the read -> unique map follows from the merge itself
+        else:
+            b1, b2 = fq.read_fastq(f1), fq.read_fastq(f2)
+            n = min(b1.n, b2.n)                 # zip() semantics
+            if b1.n != n:
+                b1 = _head(b1, n)
+            if b2.n != n:
+                b2 = _head(b2, n)
+            ids1 = b1.ids()                     # the filter is keyed on R1's id (SeqSample.py:591)
+        table = self._unique_table(b1, ids1, itspos)                    # both files are keyed on R1's ids
+        t1, k1, e1 = self._trim_file(b1, ids1, itspos, 2, trim_ccs, table)
+        t2, k2, e2 = self._trim_file(b2, ids1, itspos, 1, trim_ccs, table)
         if not wri_file:
             if (e1 or e2) and not trim_ccs:
                 print("Total number of sequences that are empty Split A: ", e1)
                 print("Total number of sequences that are empty Split B: ", e2)
             return
-        fq.write_compressed(outfile1, t1, gzipped=gzipped, zstd_file=zstd_file)
-        fq.write_compressed(outfile2, t2, gzipped=gzipped, zstd_file=zstd_file)
+        fq.write_compressed(outfile1, t1, gzipped=gzipped, zstd_file=zstd_file, n_records=len(k1))
+        fq.write_compressed(outfile2, t2, gzipped=gzipped, zstd_file=zstd_file, n_records=len(k2))
 
 
 def _is_placeholder(path):

@@ -200,8 +200,36 @@ def _parse_bytes_numpy(data):
     return batch
 
 
+# record counts of files this process has just scanned or written, keyed by path and validated against size + mtime:
+# lets the closing "Total number of reads in file ..." lines (main.py:417-438 upstream) skip a second pass over
+# gigabytes it has already counted
+_COUNTS = {}
+
+
+def note_count(path, n):
+    try:
+        st = os.stat(path)
+        _COUNTS[os.path.abspath(path)] = (st.st_size, st.st_mtime_ns, int(n))
+    except OSError:
+        pass
+
+
+def cached_count(path):
+    """Record count of ``path`` if this process scanned / wrote exactly this file (same size and mtime), else None."""
+    hit = _COUNTS.get(os.path.abspath(path))
+    if hit is None:
+        return None
+    try:
+        st = os.stat(path)
+    except OSError:
+        return None
+    return hit[2] if (st.st_size, st.st_mtime_ns) == hit[:2] else None
+
+
 def read_fastq(path):
-    return parse_bytes(_open_bytes(path))
+    batch = parse_bytes(_open_bytes(path))
+    note_count(path, batch.n)
+    return batch
 
 
 def write_records(fh, batch, keep_idx, lo, hi):
@@ -273,6 +301,19 @@ def format_gathered(batch, keep_idx, out_off, out_seq, out_qual, prefix=None, su
     dst = np.empty(total, np.uint8)
     L.itsx_fastq_format(*args, _vp(dst))
     return dst.tobytes()
+
+
+def batch_of_gathered(data, batch, keep_idx, out_off):
+    """The FastqBatch ``parse_bytes`` would build from ``data = format_gathered(batch, keep_idx, out_off, ...)``
+    (no prefix / suffix), computed from the record lengths instead of scanning the text again."""
+    keep_idx = np.asarray(keep_idx, dtype=np.int64)
+    tl = np.asarray(batch.t_len, dtype=np.int64)[keep_idx]
+    sl = np.diff(np.asarray(out_off, dtype=np.int64))
+    base = np.zeros(len(keep_idx), np.int64)
+    if len(keep_idx) > 1:
+        np.cumsum((tl + 2 * sl + 6)[:-1], out=base[1:])            # '@' title '\n' seq '\n+\n' qual '\n'
+    s_off = base + 2 + tl
+    return FastqBatch(np.frombuffer(data, dtype=np.uint8), base + 1, tl, s_off, sl, s_off + sl + 3)
 
 
 def _format_gathered_numpy(batch, keep_idx, out_off, out_seq, out_qual, prefix=None, suffix=None):
@@ -369,7 +410,7 @@ def iter_records(source):
                      quals=[c - 33 for c in b.buf[int(b.q_off[i]):int(b.q_off[i]) + int(b.s_len[i])].tolist()])
 
 
-def write_compressed(path, data, gzipped=False, zstd_file=False, threads=8):
+def write_compressed(path, data, gzipped=False, zstd_file=False, threads=8, n_records=None):
     """Write FASTQ bytes plain, as gzip (independent members compressed in parallel -- a valid gzip stream
     whose DECOMPRESSED bytes are what parity is judged on; gzip headers carry mtime, so compressed bytes are not
     reproducible even reference-vs-reference) or as one zstd frame."""
@@ -394,3 +435,5 @@ def write_compressed(path, data, gzipped=False, zstd_file=False, threads=8):
     else:
         with open(path, "wb") as f:
             f.write(data)
+    if n_records is not None:
+        note_count(path, n_records)

@@ -201,6 +201,10 @@ def _check_total_reads(file, file2=None):
     for path in (file, file2):
         if not path:
             continue
+        known = fq.cached_count(path)      # a file this run has just scanned or written (size + mtime unchanged)
+        if known is not None:
+            logging.info("Total number of reads in file {} is {}.".format(path, known))
+            continue
         try:
             if path.endswith(".gz"):
                 fh = gzip.open(path, "rb")

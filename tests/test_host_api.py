@@ -361,3 +361,22 @@ def test_native_fastq_matches_numpy_reference():
         with pytest.raises(ValueError):
             fq._parse_bytes_numpy(bad)
     assert fq.parse_bytes(b"").n == 0
+
+
+def test_batch_of_gathered_equals_reparse():
+    """The batch _merge_reads hands to deduplicate() is what scanning the written seq.fq would give."""
+    from itsxpress_b200 import fastq as fq
+    b1 = fq.read_fastq(os.path.join(TD, "4774-1-MSITS3_R1.fastq"))
+    rng = np.random.default_rng(1)
+    idx = np.sort(rng.choice(b1.n, 180, replace=False)).astype(np.int32)
+    lens = rng.integers(1, 400, len(idx))
+    off = np.zeros(len(idx) + 1, np.int64)
+    off[1:] = np.cumsum(lens)
+    seq = rng.choice(np.frombuffer(b"ACGT", np.uint8), int(off[-1]))
+    qual = rng.integers(33, 74, int(off[-1])).astype(np.uint8)
+    data = fq.format_gathered(b1, idx, off, seq, qual)
+    a, b = fq.parse_bytes(data), fq.batch_of_gathered(data, b1, idx, off)
+    for k in ("t_off", "t_len", "s_off", "s_len", "q_off"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert a.n == b.n and np.array_equal(b.seq_concat()[0], seq) and np.array_equal(b.qual_concat()[0], qual)
+    assert fq.batch_of_gathered(b"", b1, np.zeros(0, np.int32), np.zeros(1, np.int64)).n == 0

@@ -15,10 +15,10 @@ sys.path.insert(0, ROOT)
 import synth  # noqa: E402
 
 
-def write_fastq(path, seq, off, qual):
+def write_fastq(path, seq, off, qual, mate=1):
     n = len(off) - 1
     lens = np.diff(off)
-    titles = [b"@SYN:2:%d 1:N:0:1\n" % i for i in range(n)]
+    titles = [b"@SYN:2:%d %d:N:0:1\n" % (i, mate) for i in range(n)]
     tl = np.array([len(t) for t in titles], np.int64)
     rec = tl + lens + 1 + 2 + lens + 1
     ro = np.zeros(n + 1, np.int64)
@@ -46,12 +46,44 @@ def write_fastq(path, seq, off, qual):
         f.write(out.tobytes())
 
 
+def paired(a):
+    n = int(781_250 * a.scale)
+    frag, foff, _, _ = synth.make_reads(5 * 1_000_003, n, max(300, n // 20), (330, 441), "M.hmm", "3_", "4_", zipf_s=1.2,
+                                        spacer=(150, 230))
+    fs, fq_, fo, rs, rq, ro = synth.make_pairs(5 * 1_000_003 + 1, frag, foff, read_len=250, err_scale=0.0, n_rate=0.0)
+    tmp = tempfile.mkdtemp(prefix="itsx_e2e_")
+    r1, r2 = os.path.join(tmp, "in_R1.fastq"), os.path.join(tmp, "in_R2.fastq")
+    write_fastq(r1, fs, fo, fq_, 1)
+    write_fastq(r2, rs, ro, rq, 2)
+    from itsxpress_b200 import main as cli
+    ext = ".gz" if a.gz else ""
+    o1, o2 = os.path.join(tmp, "out_R1.fastq" + ext), os.path.join(tmp, "out_R2.fastq" + ext)
+    argv = ["--fastq", r1, "--fastq2", r2, "--outfile", o1, "--region", "ITS2", "--taxa", "Metazoa",
+            "--log", os.path.join(tmp, "log.txt"), "--tempdir", tmp]
+    if a.paired == "unmerged":
+        argv += ["--outfile2", o2]
+    for rep in range(2):
+        t0 = time.perf_counter()
+        cli.main(args=cli.myparser().parse_args(argv))
+        dt = time.perf_counter() - t0
+    print(json.dumps({"cli_e2e_pairs_per_s": n / dt, "seconds": dt, "pairs": n, "mode": a.paired,
+                      "input_bytes": os.path.getsize(r1) + os.path.getsize(r2),
+                      "output_bytes": os.path.getsize(o1) + (os.path.getsize(o2) if a.paired == "unmerged" else 0),
+                      "gz": a.gz}))
+    print(open(os.path.join(tmp, "log.txt")).read()[-1800:])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--gz", action="store_true", help="gzipped output")
     ap.add_argument("--keeptemp", action="store_true")
+    ap.add_argument("--paired", choices=["merged", "unmerged"], default=None,
+                    help="one BASELINE configs[4] sample: 781 250 read pairs (2 x 250 bp off 330-441 bp ITS2 amplicons, 5 %% "
+                         "unique), R1 + R2 files in, merged reads or trimmed R1 + R2 files out")
     a = ap.parse_args()
+    if a.paired:
+        return paired(a)
     cfg = dict(synth.CONFIGS["c2"])
     for k in ("region", "taxa"):
         cfg.pop(k)
