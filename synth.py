@@ -215,7 +215,8 @@ def make_pairs(seed, frag_seq, frag_off, read_len=250, trim=(0, 0), err_scale=1.
         seq = np.where(inside, seq, acgt[rng.integers(0, 4, total)])              # read-through past the fragment
         q = 38.0 - 22.0 * (pos / max(read_len, 1)) ** 2 + rng.normal(0, 3, total)
         q = np.clip(q, 2, 41).astype(np.int64)
-        perr = np.where(q < 2, 0.75, 10.0 ** (-q / 10.0)) * err_scale
+        qv = np.arange(64, dtype=np.int64)
+        perr = (np.where(qv < 2, 0.75, 10.0 ** (-qv / 10.0)) * err_scale)[q]       # per-quality table, then gather
         hit = rng.random(total) < perr
         seq = np.where(hit, acgt[(np.searchsorted(acgt, np.minimum(seq, ord("T"))) + rng.integers(1, 4, total)) % 4], seq)
         isn = rng.random(total) < n_rate
