@@ -194,3 +194,32 @@ def test_bad_quality_is_fatal(oracle):
     q[7] = 32                                                            # below ASCII 33
     with pytest.raises(ValueError):
         merge(oracle, [(frag[:250], bytes(q))], [(revcomp(frag[-250:]), b"I" * 250)])
+
+
+def test_oracle_equals_definition_on_random_pairs(oracle):
+    """The C oracle against the definition-level Python statement (tests/golden/make_merge_golden.py) on ragged random
+    pairs -- staggered and non-overlapping fragments, trimmed reads, errors, N, qualities 0..41 -- under several option
+    sets (the options the reference passes, SeqSample.py:314-349, and tighter ones)."""
+    import importlib.util
+    import synth
+    spec = importlib.util.spec_from_file_location(
+        "make_merge_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_merge_golden.py"))
+    G = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(G)
+    _, _, fs, fq, fo, rs, rq, ro = synth.make_pair_config(31, 240, frag_len=(60, 300), read_len=150, trim=(0, 60),
+                                                          err_scale=2.0, n_rate=0.01, empty_rate=0.01)
+    rng = np.random.default_rng(31)
+    fq, rq = fq.copy(), rq.copy()
+    fq[rng.random(len(fq)) < 0.03] = 33          # quality 0
+    rq[rng.random(len(rq)) < 0.03] = 34          # quality 1
+    for kw in (dict(), dict(allow_stagger=True), dict(maxdiffs=3, minovlen=40), dict(allow_stagger=True, maxee=0.5)):
+        ml, why, os_, oq = oracle.merge_pairs(fs, fq, fo, rs, rq, ro, oracle.merge_params(**kw))
+        for i in range(len(fo) - 1):
+            res, reason = G.merge_pair(fs[fo[i]:fo[i + 1]].tobytes(), fq[fo[i]:fo[i + 1]].tobytes(),
+                                       rs[ro[i]:ro[i + 1]].tobytes(), rq[ro[i]:ro[i + 1]].tobytes(),
+                                       stagger=bool(kw.get("allow_stagger", False)), maxdiffs=kw.get("maxdiffs", 40),
+                                       maxee=kw.get("maxee", 2.0), minovlen=kw.get("minovlen", 10))
+            s = int(fo[i] + ro[i])
+            got = (bytes(os_[s:s + ml[i]]), bytes(oq[s:s + ml[i]])) if ml[i] else None
+            assert oracle.MERGE_REASONS[why[i]] == reason and got == res, (kw, i, reason)
+        assert len(set(why.tolist())) >= 3
