@@ -295,8 +295,7 @@ class SeqSamplePairedNotInterleaved(SeqSample):
         self.seq_file = seq_file
         try:
             try:
-                b1 = fq.read_fastq(self.r1)
-                b2 = fq.read_fastq(self.fastq2)
+                b1, b2 = fq.read_fastq_many([self.r1, self.fastq2])
                 if b1.n != b2.n:
                     raise ValueError("More %s reads than %s reads" % (("forward", "reverse") if b1.n > b2.n
                                                                       else ("reverse", "forward")))
@@ -659,7 +658,7 @@ class Dedup:
             b1, b2 = ps.pair_batches            # parsed by _merge_reads a moment ago; equal record counts
             ids1 = None                         # ... and the read -> unique map follows from the merge itself
         else:
-            b1, b2 = fq.read_fastq(f1), fq.read_fastq(f2)
+            b1, b2 = fq.read_fastq_many([f1, f2])
             n = min(b1.n, b2.n)                 # zip() semantics
             if b1.n != n:
                 b1 = _head(b1, n)
