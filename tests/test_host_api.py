@@ -380,3 +380,43 @@ def test_batch_of_gathered_equals_reparse():
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
     assert a.n == b.n and np.array_equal(b.seq_concat()[0], seq) and np.array_equal(b.qual_concat()[0], qual)
     assert fq.batch_of_gathered(b"", b1, np.zeros(0, np.int32), np.zeros(1, np.int64)).n == 0
+
+
+def test_cached_read_counts_and_parallel_gzip(tmp_path):
+    """Counts of files this process scanned / wrote are reused only while size and mtime are unchanged; the parallel
+    gzip writer's multi-member stream inflates to the input bytes with any reader."""
+    import subprocess
+    import time
+    from itsxpress_b200 import main as cli
+    src = os.path.join(TD, "4774-1-MSITS3_R1.fastq")
+    b = fq.read_fastq(src)
+    assert fq.cached_count(src) == b.n == 250
+    text = open(src, "rb").read() * 40                       # 4 MB members -> several of them
+    out = str(tmp_path / "o.fastq.gz")
+    fq.write_compressed(out, text, gzipped=True, n_records=250 * 40)
+    assert fq.cached_count(out) == 10000
+    assert gzip.open(out, "rb").read() == text
+    assert subprocess.run(["gzip", "-dc", out], stdout=subprocess.PIPE).stdout == text
+    plain = str(tmp_path / "p.fastq")
+    fq.write_compressed(plain, text[:len(text) // 40], n_records=250)
+    assert fq.cached_count(plain) == 250
+    time.sleep(0.01)
+    with open(plain, "ab") as f:                             # modified behind our back: the cache must not answer
+        f.write(open(src, "rb").read())
+    assert fq.cached_count(plain) is None
+    assert fq.cached_count(str(tmp_path / "missing.fastq")) is None
+    import logging
+    records = []
+    h = logging.Handler()
+    h.emit = lambda r: records.append(r.getMessage())
+    logging.getLogger().addHandler(h)
+    old = logging.getLogger().level
+    logging.getLogger().setLevel(logging.INFO)
+    try:
+        cli._check_total_reads(plain, out)
+    finally:
+        logging.getLogger().removeHandler(h)
+        logging.getLogger().setLevel(old)
+    assert any(m.endswith("p.fastq is 500.") for m in records) and any(m.endswith("o.fastq.gz is 10000.") for m in records)
+    a, c = fq.read_fastq_many([src, os.path.join(TD, "4774-1-MSITS3_R2.fastq.gz")])
+    assert a.n == c.n == 250 and a.title(0).split()[0] == c.title(0).split()[0]
