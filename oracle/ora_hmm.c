@@ -54,6 +54,8 @@ struct ora_db {
     prof_t *p;
 };
 
+static float viterbi_filter(const prof_t *pf, const uint8_t *dsq, int L, int *overflow);
+
 static const int degen_mask[ORA_NCODE] = {1, 2, 4, 8, 5, 10, 3, 12, 6, 9, 11, 14, 7, 13, 15, 0};
 
 /* ------------------------------------------------------------------------ */
@@ -1038,8 +1040,16 @@ int ora_pair_run(const ora_db *db, int p, const uint8_t *dsq, int L,
     pr->P_bias   = gumbel_surv(seq_score, pf->ev[EV_MMU], pf->ev[EV_MLAMBDA]);
     if (pr->P_bias > prm->F1) return 0;
     pr->pass_bias = 1;
-    /* Viterbi filter runs only if P > F2; with F1 == F2 it is never executed (A.4 step 3). */
-    if (pr->P_bias > prm->F2) return 0;
+    /* Viterbi filter runs only if P > F2; with F1 == F2 -- what the reference passes -- it is never executed
+     * (A.4 step 3).  An overflowing filter counts as a pass. */
+    if (pr->P_bias > prm->F2) {
+        int   ovf = 0;
+        float vsc = viterbi_filter(pf, dsq, L, &ovf);
+        if (!ovf) {
+            seq_score = (float)((vsc - pr->filtersc) / LOG2);
+            if (gumbel_surv(seq_score, pf->ev[EV_VMU], pf->ev[EV_VLAMBDA]) > prm->F2) return 0;
+        }
+    }
 
     xf_t       xf = xf_multihit(L);
     specials_t fs = specials_alloc(L), bs = specials_alloc(L);
@@ -1153,6 +1163,97 @@ float ora_bias_filtersc(const ora_db *db, int p, const uint8_t *dsq, int L)
 {
     return bias_filtersc(&db->p[p], dsq, L);
 }
+/* ---- Viterbi filter, 16-bit (HMMER p7_ViterbiFilter semantics) ----
+ * NOT on the reference's path: hmmsearch runs it only `if (P > F2)` for a pair that already has P <= F1, and ITSxpress
+ * passes F1 == F2 (SeqSample.py:191-209).  It is restated here so that the `STATS LOCAL VITERBI` line of every
+ * profile -- hmmbuild's own calibration of exactly this routine -- can serve as a known-answer test of the word
+ * profile (tests/test_oracle_calibration.py), and as the checker for a future kernel when a caller asks for F2 < F1.
+ * Scores are int16 in 1/500 bit units around base 12000 with saturating adds (-32768 acts as -infinity), insert
+ * emissions are 0, the N/C/J self loops cost 0 and a flat 3 nats is charged at the end, E is reached from M only.  The
+ * D path of a row is resolved in full (what the lazy-F loop of the striped code converges to). */
+static int wordify(float sc)
+{
+    const float scale_w = 500.0f / (float)LOG2;
+    if (!(sc > -INFINITY)) return -32768;
+    sc = roundf(scale_w * sc);
+    if (sc >= 32767.0f) return 32767;
+    if (sc <= -32768.0f) return -32768;
+    return (int)sc;
+}
+static inline int adds16(int a, int b)
+{
+    const int v = a + b;
+    return v > 32767 ? 32767 : v < -32768 ? -32768 : v;
+}
+static inline int max2(int a, int b) { return a > b ? a : b; }
+
+/* Returns the filter score in nats (the -3 nat correction included); *overflow = 1 (and +inf returned) when a row's
+ * best match cell saturates, which the pipeline treats as a pass. */
+static float viterbi_filter(const prof_t *pf, const uint8_t *dsq, int L, int *overflow)
+{
+    const int     M       = pf->M, W = M + 2;
+    const float   scale_w = 500.0f / (float)LOG2;
+    const int     base_w  = 12000;
+    int          *buf     = malloc((size_t)W * 14 * sizeof(int));
+    int *tBM = buf, *tMM = tBM + W, *tIM = tMM + W, *tDM = tIM + W, *tMD = tDM + W, *tDD = tMD + W, *tMI = tDD + W,
+        *tII = tMI + W;
+    int *Mp = tII + W, *Ip = Mp + W, *Dp = Ip + W, *Mn = Dp + W, *In = Mn + W, *Dn = In + W;
+    for (int k = 0; k < W; k++) {
+        const float *t = pf->tp + (size_t)(k <= M ? k : 0) * 7;     /* transitions out of node k (0 for k = 0, k = M) */
+        const int    ok = k >= 1 && k <= M;
+        tBM[k] = ok ? wordify(logf(pf->bm[k])) : -32768;
+        tMM[k] = ok ? wordify(logf(t[T_MM])) : -32768;
+        tIM[k] = ok ? wordify(logf(t[T_IM])) : -32768;
+        tDM[k] = ok ? wordify(logf(t[T_DM])) : -32768;
+        tMD[k] = ok ? wordify(logf(t[T_MD])) : -32768;
+        tDD[k] = ok ? wordify(logf(t[T_DD])) : -32768;
+        tMI[k] = ok ? wordify(logf(t[T_MI])) : -32768;
+        tII[k] = ok ? wordify(logf(t[T_II])) : -32768;
+        if (tII[k] == 0) tII[k] = -1;                               /* an II cost of 0 is not allowed in the filter */
+        Mp[k] = Ip[k] = Dp[k] = -32768;
+    }
+    const int xw_move = wordify(logf(3.0f / ((float)L + 3.0f)));     /* N, C, J -> move; multihit length model */
+    const int xw_E    = wordify(-(float)LOG2);                       /* E -> C and E -> J */
+    int       xN = base_w, xB = xN + xw_move, xJ = -32768, xC = -32768;
+    float     sc = -INFINITY;
+    if (overflow) *overflow = 0;
+    for (int i = 1; i <= L; i++) {
+        const float *rs = pf->msc + dsq[i - 1];
+        int          xE = -32768;
+        Mn[0] = In[0] = Dn[0] = -32768;
+        for (int k = 1; k <= M; k++) {
+            int sv = adds16(xB, tBM[k]);
+            sv     = max2(sv, adds16(Mp[k - 1], tMM[k - 1]));
+            sv     = max2(sv, adds16(Ip[k - 1], tIM[k - 1]));
+            sv     = max2(sv, adds16(Dp[k - 1], tDM[k - 1]));
+            sv     = adds16(sv, wordify(rs[k * 16]));
+            Mn[k]  = sv;
+            xE     = max2(xE, sv);
+            Dn[k]  = max2(adds16(Mn[k - 1], tMD[k - 1]), adds16(Dn[k - 1], tDD[k - 1]));
+            In[k]  = max2(adds16(Mp[k], tMI[k]), adds16(Ip[k], tII[k]));
+        }
+        if (xE >= 32767) {
+            if (overflow) *overflow = 1;
+            free(buf);
+            return INFINITY;
+        }
+        xC = max2(xC, xE + xw_E);                                    /* C, J, N loops cost 0 */
+        xJ = max2(xJ, xE + xw_E);
+        xB = max2(xJ + xw_move, xN + xw_move);
+        int *sw;
+        sw = Mp; Mp = Mn; Mn = sw;
+        sw = Ip; Ip = In; In = sw;
+        sw = Dp; Dp = Dn; Dn = sw;
+    }
+    if (xC > -32768) sc = ((float)xC + (float)xw_move - (float)base_w) / scale_w - 3.0f;
+    free(buf);
+    return sc;
+}
+float ora_viterbi_filter(const ora_db *db, int p, const uint8_t *dsq, int L, int *overflow)
+{
+    return viterbi_filter(&db->p[p], dsq, L, overflow);
+}
+
 float ora_forward_score(const ora_db *db, int p, const uint8_t *dsq, int L)
 {
     xf_t       xf = xf_multihit(L);

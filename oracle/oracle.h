@@ -119,6 +119,8 @@ int ora_domain_decoding(const ora_db *db, int p, const uint8_t *dsq, int L,
 /* raw filter scores for calibration tests */
 float ora_msv_score(const ora_db *db, int p, const uint8_t *dsq, int L, int *overflow);
 float ora_forward_score(const ora_db *db, int p, const uint8_t *dsq, int L);
+/* 16-bit Viterbi filter score in nats (p7_ViterbiFilter; never run on the reference's path, F1 == F2: see ora_hmm.c) */
+float ora_viterbi_filter(const ora_db *db, int p, const uint8_t *dsq, int L, int *overflow);
 float ora_backward_score(const ora_db *db, int p, const uint8_t *dsq, int L);
 float ora_nullsc(int L);
 float ora_bias_filtersc(const ora_db *db, int p, const uint8_t *dsq, int L);

@@ -95,7 +95,7 @@ def lib():
     L.ora_pair_run.argtypes = [vp, C.c_int, vp, C.c_int, C.POINTER(OraParams), C.POINTER(OraPair), vp, C.c_int]
     L.ora_forward_parser.argtypes = [vp, C.c_int, vp, C.c_int] + [vp] * 7
     L.ora_domain_decoding.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, vp]
-    for fn in ("ora_msv_score",):
+    for fn in ("ora_msv_score", "ora_viterbi_filter"):
         getattr(L, fn).restype = f32
         getattr(L, fn).argtypes = [vp, C.c_int, vp, C.c_int, vp]
     for fn in ("ora_forward_score", "ora_backward_score", "ora_bias_filtersc"):
@@ -189,6 +189,12 @@ class ProfileDB:
         ov = C.c_int(0)
         sc = lib().ora_msv_score(self._h, p, _ptr(dsq), len(dsq), C.byref(ov))
         return sc, bool(ov.value)
+
+    def viterbi_filter(self, p, dsq):
+        """16-bit Viterbi filter score in nats and its overflow flag (not on the reference's path: F1 == F2)."""
+        ov = C.c_int()
+        sc = lib().ora_viterbi_filter(self._h, p, _ptr(dsq), len(dsq), C.byref(ov))
+        return float(sc), bool(ov.value)
 
     def forward_score(self, p, dsq):
         return lib().ora_forward_score(self._h, p, _ptr(dsq), len(dsq))

@@ -90,6 +90,52 @@ def test_forward_tau(db, oracle, p):
     assert abs(tau - ev[4]) < 0.6, (tau, ev[4])
 
 
+@pytest.mark.parametrize("p", [0, 2, 200])
+def test_viterbi_filter_mu(db, oracle, p):
+    """`STATS LOCAL VITERBI mu lambda` is hmmbuild's calibration of the 16-bit Viterbi filter itself (ML Gumbel
+    location at fixed lambda, random sequences of L = 200): the oracle's restatement of that filter must land on it.
+    (The stage never runs on the reference's path, F1 == F2; this pins the word profile for the day it does.)"""
+    rng = np.random.default_rng(300 + p)
+    ev = db.evparam(p)
+    lam = float(ev[3])
+    assert abs(lam - float(ev[1])) < 1e-6                       # Viterbi and MSV share lambda
+    L = 200
+    nullsc = oracle.lib().ora_nullsc(L)
+    xs = []
+    for dsq in _random_codes(rng, 3000, L):
+        sc, ovf = db.viterbi_filter(p, np.ascontiguousarray(dsq))
+        assert not ovf
+        xs.append((sc - nullsc) / LN2)
+    xs = np.array(xs, np.float64)
+    mu = -np.log(np.mean(np.exp(-lam * xs))) / lam
+    assert abs(mu - ev[2]) < 0.5, (mu, ev[2])
+
+
+def test_viterbi_filter_below_forward(db):
+    """The best path scores no more than the sum over paths (up to the filter's 1/500-bit quantisation and its flat
+    3-nat length correction), and approaches it on a sequence that carries a strong match."""
+    import synth
+    rng = np.random.default_rng(12)
+    for p in (0, 5, 120):
+        for L in (60, 200, 420):
+            dsq = np.ascontiguousarray(rng.integers(0, 4, size=L, dtype=np.uint8))
+            v, ovf = db.viterbi_filter(p, dsq)
+            assert not ovf and v <= db.forward_score(p, dsq) + 0.15, (p, L)
+    seq, off, which, cfg = synth.make_config("c2_small", scale=0.05)
+    m = os.path.join(synth.HMM_DIR, cfg["hmm_file"])
+    from oracle import oracle as O
+    d2 = O.ProfileDB([m], [cfg["left_prefix"]])
+    close = 0
+    for r in range(40):
+        dsq = O.digitize(seq[off[r]:off[r + 1]].tobytes())
+        best = max(range(d2.n), key=lambda q: d2.forward_score(q, dsq))
+        f = d2.forward_score(best, dsq)
+        v, ovf = d2.viterbi_filter(best, dsq)
+        assert ovf or v <= f + 0.15
+        close += (not ovf) and f - v < 6.0 and f > 10.0
+    assert close >= 20
+
+
 def test_forward_equals_backward(db):
     rng = np.random.default_rng(9)
     for p in (0, 5, 120):
