@@ -231,3 +231,45 @@ def main_sharded(per_sample_sequences, outdir, region, taxa="F", threads=1, pair
     if barrier is not None:
         barrier()
     return results, mine
+
+
+def cli(argv=None):
+    """Shell entry for a whole per-sample directory (the `data/` of a QIIME 2 artifact), one process per GPU:
+
+        torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 -m itsxpress_b200.q2_itsxpress \\
+            --in ARTIFACT/data --out OUTDIR --region ITS2 --taxa F --mode pair-unmerged
+
+    --mode single | pair | pair-unmerged = the plugin actions trim-single / trim-pair / trim-pair-output-unmerged
+    (q2_itsxpress.py:119-230).  With one process it is the plain action writing into OUTDIR."""
+    import argparse
+    ap = argparse.ArgumentParser(prog="python -m itsxpress_b200.q2_itsxpress", description=cli.__doc__,
+                                 formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--in", dest="src", required=True, help="per-sample directory with MANIFEST")
+    ap.add_argument("--out", required=True, help="output directory (shared by all ranks)")
+    ap.add_argument("--region", required=True, choices=["ITS1", "ITS2", "ALL"])
+    ap.add_argument("--taxa", default="F", choices=sorted(_TAXA_LETTERS))
+    ap.add_argument("--mode", default="pair-unmerged", choices=["single", "pair", "pair-unmerged"])
+    ap.add_argument("--threads", type=int, default=1)
+    ap.add_argument("--reversed-primers", action="store_true")
+    ap.add_argument("--no-staggered", action="store_true", help="do not merge staggered pairs")
+    a = ap.parse_args(argv)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("gloo")      # barriers only; every rank computes on the GPU LOCAL_RANK names
+    try:
+        res, mine = main_sharded(PerSampleDir(a.src), a.out, region=a.region, taxa=a.taxa, threads=a.threads,
+                                 paired_in=a.mode != "single", paired_out=a.mode == "pair-unmerged",
+                                 reversed_primers=a.reversed_primers, allow_staggered_reads=not a.no_staggered)
+    finally:
+        if dist is not None and dist.is_initialized():
+            dist.destroy_process_group()
+    print("rank %s: %d sample(s) -> %s" % (os.environ.get("RANK", "0"), len(mine), str(res)))
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(cli())

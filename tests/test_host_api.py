@@ -420,3 +420,25 @@ def test_cached_read_counts_and_parallel_gzip(tmp_path):
     assert any(m.endswith("p.fastq is 500.") for m in records) and any(m.endswith("o.fastq.gz is 10000.") for m in records)
     a, c = fq.read_fastq_many([src, os.path.join(TD, "4774-1-MSITS3_R2.fastq.gz")])
     assert a.n == c.n == 250 and a.title(0).split()[0] == c.title(0).split()[0]
+
+
+def test_q2_shell_entry_single_process(tmp_path, monkeypatch):
+    """`python -m itsxpress_b200.q2_itsxpress --in DIR --out DIR ...` with one process: every sample goes through the
+    per-sample pipeline (stubbed here: the real one needs a B200) with the options of the chosen plugin action."""
+    from itsxpress_b200 import q2_itsxpress as q2
+    src = os.path.join(TD, "paired", "445cf54a-bf06-4852-8010-13a60fa1598c", "data")
+    seen = []
+
+    def stub(sample, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers, stagger, *rest):
+        seen.append((sample.Index, taxa, region, paired_in, paired_out, reversed_primers, stagger))
+        shutil.copy(sample.forward, os.path.join(str(results), os.path.basename(sample.forward)))
+
+    monkeypatch.setattr(q2, "_process_sample", stub)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.delenv("RANK", raising=False)
+    out = str(tmp_path / "o")
+    assert q2.cli(["--in", src, "--out", out, "--region", "ITS2", "--taxa", "M", "--mode", "pair", "--no-staggered"]) == 0
+    assert seen == [("4774-1-MSITS3", "Metazoa", "ITS2", True, False, False, False)]
+    assert open(os.path.join(out, "MANIFEST")).read().splitlines()[1].endswith(",forward")
+    with pytest.raises(SystemExit):
+        q2.cli(["--in", src, "--out", out, "--region", "ITS9"])
