@@ -226,10 +226,57 @@ def cached_count(path):
     return hit[2] if (st.st_size, st.st_mtime_ns) == hit[:2] else None
 
 
-def read_fastq(path):
+def _read_fastq_now(path):
     batch = parse_bytes(_open_bytes(path))
     note_count(path, batch.n)
     return batch
+
+
+# files being read ahead on background threads: abspath -> (Future[FastqBatch], size, mtime_ns)
+_PREFETCH = {}
+_PREFETCH_POOL = None
+
+
+def prefetch(paths):
+    """Start reading / inflating / scanning these files in the background (zlib and the native scanner release the
+    GIL).  A multi-sample driver calls it with the NEXT sample's files while the current sample is on the GPU;
+    ``read_fastq`` then picks the result up.  Errors are not raised here: a failed read-ahead is dropped and the
+    ordinary read raises in the caller's context."""
+    global _PREFETCH_POOL
+    from concurrent.futures import ThreadPoolExecutor
+    if _PREFETCH_POOL is None:
+        _PREFETCH_POOL = ThreadPoolExecutor(2, thread_name_prefix="itsx-readahead")
+    for p in paths:
+        if not p:
+            continue
+        key = os.path.abspath(p)
+        if key in _PREFETCH:
+            continue
+        try:
+            st = os.stat(p)
+        except OSError:
+            continue
+        _PREFETCH[key] = (_PREFETCH_POOL.submit(_read_fastq_now, p), st.st_size, st.st_mtime_ns)
+
+
+def drop_prefetched():
+    """Forget read-ahead results nobody collected (a driver calls it when it is done or gives up)."""
+    for fut, _, _ in list(_PREFETCH.values()):
+        fut.cancel()
+    _PREFETCH.clear()
+
+
+def read_fastq(path):
+    hit = _PREFETCH.pop(os.path.abspath(path), None)
+    if hit is not None:
+        fut, size, mtime = hit
+        try:
+            st = os.stat(path)
+            if (st.st_size, st.st_mtime_ns) == (size, mtime):
+                return fut.result()
+        except Exception:
+            pass                        # fall through: the ordinary read reports the problem where it is expected
+    return _read_fastq_now(path)
 
 
 def read_fastq_many(paths):

@@ -18,6 +18,7 @@ import tempfile
 
 import pandas as pd
 
+from . import fastq as fq
 from . import main as itsxpress
 
 try:  # pragma: no cover - only with QIIME 2 installed
@@ -165,9 +166,16 @@ def main(per_sample_sequences, threads, taxa, region, paired_in, paired_out, rev
     except Exception:
         raise ValueError("Could not create temporary directory")
     results = CasavaOneEightSingleLanePerSampleDirFmt() if CasavaOneEightSingleLanePerSampleDirFmt else CasavaDir()
-    for sample in samples.itertuples():
-        _process_sample(sample, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
-                        allow_staggered_reads, cluster_id, trim_ccs)
+    rows = list(samples.itertuples())
+    try:
+        for k, sample in enumerate(rows):
+            if k + 1 < len(rows):       # read the next sample's files while this one is on the GPU
+                nxt = rows[k + 1]
+                fq.prefetch([nxt.forward, nxt.reverse if paired_in else None])
+            _process_sample(sample, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
+                            allow_staggered_reads, cluster_id, trim_ccs)
+    finally:
+        fq.drop_prefetched()
     if trim_ccs:
         print("\n" + "=" * 80 + "\nPacBio CCS trimming complete.\n\nCAUTION: data contain fake sequence at the ends "
               "needed for DADA2\n\nqiime dada2 denoise-ccs --p-front GACAGGTACAAGAAGGA --p-adapter ACTGGAGACTGGGTTAA\n"
@@ -211,14 +219,16 @@ def main_sharded(per_sample_sequences, outdir, region, taxa="F", threads=1, pair
     tempdir = tempfile.mkdtemp(prefix="itsxpress_r%d_" % rank)
     process = process or _process_sample
     mine = []
+    todo = [sample for sample, o in zip(rows, owner) if o == rank]
     try:
-        for sample, o in zip(rows, owner):
-            if o != rank:
-                continue
+        for k, sample in enumerate(todo):
+            if k + 1 < len(todo):       # read the next sample's files while this one is on the GPU
+                fq.prefetch([todo[k + 1].forward, todo[k + 1].reverse if paired_in else None])
             process(sample, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
                     allow_staggered_reads, cluster_id, trim_ccs)
             mine.append(sample.Index)
     finally:
+        fq.drop_prefetched()
         shutil.rmtree(tempdir, ignore_errors=True)
     if barrier is None and world > 1:
         import torch.distributed as dist

@@ -442,3 +442,61 @@ def test_q2_shell_entry_single_process(tmp_path, monkeypatch):
     assert open(os.path.join(out, "MANIFEST")).read().splitlines()[1].endswith(",forward")
     with pytest.raises(SystemExit):
         q2.cli(["--in", src, "--out", out, "--region", "ITS9"])
+
+
+def test_fastq_read_ahead(tmp_path):
+    """fq.prefetch reads files in the background; read_fastq collects the result once, falls back to an ordinary read
+    when the file changed in between, and raises errors at the point of use (not in prefetch)."""
+    import time
+    r1, r2 = os.path.join(TD, "4774-1-MSITS3_R1.fastq.gz"), os.path.join(TD, "4774-1-MSITS3_R2.fastq")
+    want1, want2 = fq._read_fastq_now(r1), fq._read_fastq_now(r2)
+    fq.prefetch([r1, r2, None])
+    assert len(fq._PREFETCH) == 2
+    a, b = fq.read_fastq_many([r1, r2])
+    assert not fq._PREFETCH
+    assert np.array_equal(a.buf, want1.buf) and np.array_equal(b.s_off, want2.s_off) and a.n == b.n == 250
+    assert fq.read_fastq(r1).n == 250                       # nothing pending: ordinary read
+    # a file that changes between read-ahead and use is read again
+    p = str(tmp_path / "x.fastq")
+    shutil.copy(r2, p)
+    fq.prefetch([p])
+    time.sleep(0.05)
+    with open(p, "ab") as f:
+        f.write(open(r2, "rb").read())
+    assert fq.read_fastq(p).n == 500
+    # errors surface where the reference raises them
+    fq.prefetch([os.path.join(TD, "broken.fastq"), str(tmp_path / "missing.fastq")])
+    with pytest.raises(ValueError):
+        fq.read_fastq(os.path.join(TD, "broken.fastq"))
+    with pytest.raises(FileNotFoundError):
+        fq.read_fastq(str(tmp_path / "missing.fastq"))
+    fq.prefetch([r1])
+    fq.drop_prefetched()
+    assert not fq._PREFETCH
+
+
+def test_q2_loop_reads_next_sample_ahead(tmp_path, monkeypatch):
+    """The per-sample loops of the QIIME 2 driver start the next sample's read while the current one is processed."""
+    from itsxpress_b200 import q2_itsxpress as q2
+    src = tmp_path / "in"
+    src.mkdir()
+    lines = ["sample-id,filename,direction"]
+    for k in range(3):
+        for m, tag, d in ((1, "R1", "forward"), (2, "R2", "reverse")):
+            fn = "S%d_%d_L001_%s_001.fastq.gz" % (k, k, tag)
+            shutil.copy(os.path.join(TD, "4774-1-MSITS3_R%d.fastq.gz" % m), str(src / fn))
+            lines.append("S%d,%s,%s" % (k, fn, d))
+    (src / "MANIFEST").write_text("\n".join(lines) + "\n")
+    pending = []
+
+    def stub(sample, results, *rest):
+        pending.append(sorted(os.path.basename(p) for p in fq._PREFETCH))
+        b1, b2 = fq.read_fastq_many([sample.forward, sample.reverse])       # what _merge_reads does
+        assert b1.n == b2.n == 250
+        shutil.copy(sample.forward, os.path.join(str(results), os.path.basename(sample.forward)))
+
+    monkeypatch.setattr(q2, "_process_sample", stub)
+    q2.main_sharded(q2.PerSampleDir(str(src)), str(tmp_path / "o"), region="ITS2", taxa="M", rank=0, world=1)
+    # at the start of a sample its own files (read ahead during the previous one) and the next sample's are pending
+    assert [len(p) for p in pending] == [2, 4, 2] and not fq._PREFETCH
+    assert pending[0] == ["S1_1_L001_R1_001.fastq.gz", "S1_1_L001_R2_001.fastq.gz"]
