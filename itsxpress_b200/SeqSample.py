@@ -176,6 +176,9 @@ class SeqSample:
                 with open(self.uc_file, "wb") as f:
                     f.write(host.write_uc(rep, strand, ids, batch.s_len, order))
             else:
+                logging.info("uc.txt and rep.fa are one-line placeholders for this sample (%d reads > %d); Dedup takes "
+                             "the read -> representative map from the GPU session. Use --keeptemp or "
+                             "ITSX_TEMP_FILES=always for the full files." % (batch.n, TEMP_FILE_AUTO_MAX_READS))
                 for path in (self.rep_file, self.uc_file):
                     with open(path, "w") as f:
                         f.write(_PLACEHOLDER)
@@ -202,7 +205,16 @@ class SeqSample:
             if not os.path.exists(hmmfile):
                 raise FileNotFoundError(hmmfile)
             ctx = get_context()
-            ctx.load_profiles([hmmfile], None)
+            nprof = ctx.load_profiles([hmmfile], None)
+            if nprof == 0:
+                # upstream: hmmsearch stops with a non-zero status on an HMM file without profiles (a taxon whose
+                # file is not shipped, or the QIIME 2 letter that misses its taxa_dict key, main.py:197,214-215),
+                # check_returncode() raises and the CLI exits 1 (SeqSample.py:211-225) -- never an empty output
+                raise subprocess.CalledProcessError(
+                    1, ["itsx_search", "--domtblout", self.dom_file, "-T", "10", "--F1", "1e-6", "--F2", "1e-6",
+                        "--F3", "1e-6", hmmfile, str(self.rep_file)],
+                    stderr=("Error: no profile in HMM file %s (no profile matches the requested --taxa / --region, "
+                            "or the taxon's file is missing from ITSx_db/HMMs)" % hmmfile).encode("utf-8"))
             s = self._session
             resident = (s is not None and s.derep_gen == _GENERATION and
                         os.path.abspath(self.rep_file) in _SESSIONS and _SESSIONS[os.path.abspath(self.rep_file)] is s)
@@ -223,7 +235,9 @@ class SeqSample:
             if resident:
                 s.derep_gen = _GENERATION
             s.names, s.nseq = list(ctx.names), nseq
-            if self._want_files(s.batch.n if s.batch is not None else nseq):
+            # a search that was not fed from a resident derep session (rep.fa written by vsearch --cluster_size, or
+            # by another process) has no device-side hand-off to ItsPosition / Dedup: its table is always written
+            if not resident or self._want_files(s.batch.n if s.batch is not None else nseq):
                 if seq_ids is None:
                     ids = s.ids
                     seq_ids = [ids[i] for i in s.first.tolist()]
@@ -235,6 +249,9 @@ class SeqSample:
                 nrows = len(rows)
             else:
                 s.files = False
+                logging.info("domtbl.txt is a one-line placeholder for this sample (%d sequences > %d); ItsPosition "
+                             "takes the positions from the GPU session. Use --keeptemp or ITSX_TEMP_FILES=always for "
+                             "the full table." % (nseq, TEMP_FILE_AUTO_MAX_READS))
                 with open(self.dom_file, "w") as f:
                     f.write(_PLACEHOLDER)
                 nrows = ctx.search_stats().n_domains_reported

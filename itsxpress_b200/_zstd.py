@@ -59,14 +59,18 @@ def decompress(data):
         osz = max(L.ZSTD_DStreamOutSize(), 1 << 20)
         dst = C.create_string_buffer(osz)
         parts = []
-        while ib.pos < ib.size:
+        rc, full = 0, False
+        # keep calling while input remains OR the last call filled the output buffer: the decoder can hold a decoded
+        # block back after it has consumed all of the input (multi-frame / pzstd / `zstd -T` files)
+        while ib.pos < ib.size or full:
             ob = _Buf(C.cast(dst, C.c_void_p), osz, 0)
             rc = L.ZSTD_decompressStream(ds, C.byref(ob), C.byref(ib))
             if L.ZSTD_isError(rc):
                 raise ValueError("zstd: " + L.ZSTD_getErrorName(rc).decode())
             parts.append(dst.raw[:ob.pos])
-            if ob.pos == 0 and rc != 0 and ib.pos >= ib.size:
-                raise ValueError("zstd: truncated input")
+            full = ob.pos == osz
+        if rc != 0:         # the last frame was not finished: pyzstd raises here too
+            raise ValueError("zstd: truncated input")
         return b"".join(parts)
     finally:
         L.ZSTD_freeDStream(ds)

@@ -15,6 +15,34 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run on the GPU box with -m gpu)")
 
 
+_HAVE_GPU = None
+
+
+def _have_gpu():
+    """True iff libitsx_b200 can open device 0 (a B200); decided once per session."""
+    global _HAVE_GPU
+    if _HAVE_GPU is None:
+        try:
+            from itsxpress_b200 import _lib
+            _lib.Context(0).close()
+            _HAVE_GPU = True
+        except Exception:
+            _HAVE_GPU = False
+    return _HAVE_GPU
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest` on a CPU box skips the gpu-marked tests instead of erroring in every one of them.  With
+    `-m gpu` (the GPU box) nothing is skipped: a missing device must fail loudly there."""
+    if "gpu" in (config.getoption("-m") or ""):
+        return
+    gpu_items = [it for it in items if "gpu" in it.keywords]
+    if gpu_items and not _have_gpu():
+        skip = pytest.mark.skip(reason="no B200 in this box (gpu-marked tests run with -m gpu on the GPU box)")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import oracle as O

@@ -169,6 +169,28 @@ def test_cli_failure_exit_code(tmp_path):
     assert e.value.code == 1
 
 
+def test_search_without_profiles_fails_like_hmmsearch(tmp_path):
+    """`--taxa Fungi` with F.hmm absent (or the QIIME 2 letter R -> 'Rhizaria', which misses the
+    ' Rhizaria' key) yields a runtime HMM file without profiles; upstream hmmsearch exits non-zero on it
+    (SeqSample.py:211-225 -> CalledProcessError -> CLI exit 1).  Never an empty output with status 0."""
+    import subprocess
+    from itsxpress_b200 import main as cli
+    from itsxpress_b200.SeqSample import SeqSampleNotPaired
+    empty = tmp_path / "runtime_selected.hmm"
+    empty.write_text("")
+    s = SeqSampleNotPaired(os.path.join(TD, "ex_tmpdir", "seq.fq.gz"), str(tmp_path))
+    s.deduplicate(threads=1)
+    with pytest.raises(subprocess.CalledProcessError):
+        s._search(str(empty), threads=1)
+    if not os.path.exists(os.path.join(HMM_DIR, "F.hmm")):
+        args = cli.myparser().parse_args(["--fastq", os.path.join(TD, "4774-1-MSITS3_merged.fastq"), "--single_end",
+                                          "--outfile", str(tmp_path / "o.fq"), "--region", "ITS2", "--taxa", "Fungi",
+                                          "--log", str(tmp_path / "log.txt")])
+        with pytest.raises(SystemExit) as e:
+            cli.main(args=args)
+        assert e.value.code == 1
+
+
 def test_q2_trim_single(tmp_path):
     """q2 action trim_single on a single-end per-sample directory (layout of the reference's
     tests/test_data/singleIn artifact; the sample here is the MERGED fixture so that both ITS2 boundaries are inside

@@ -94,6 +94,19 @@ def test_zstd_and_gzip_writers(tmp_path):
     assert open(str(tmp_path / "a.fq"), "rb").read() == raw
 
 
+def test_zstd_decoder_flushes_held_back_blocks_and_rejects_truncation():
+    """the streaming decoder may consume all input while a decoded block still waits for output space
+    (multi-frame files, blocks that do not align to the 1 MiB output buffer); a cut-off frame raises like pyzstd."""
+    from itsxpress_b200 import _zstd
+    rng = np.random.default_rng(5)
+    a = rng.integers(65, 70, (1 << 20) + 12345, dtype=np.uint8).tobytes()          # > 1 MiB, compressible
+    b = rng.integers(65, 70, 700_001, dtype=np.uint8).tobytes()
+    blob = _zstd.compress(a, level=1) + _zstd.compress(b, level=19)                  # two frames back to back
+    assert _zstd.decompress(blob) == a + b
+    with pytest.raises(ValueError):
+        _zstd.decompress(blob[:-7])
+
+
 # ---- Dedup / ItsPosition from files -------------------------------------------------------------------------
 def test_dedup_parse():
     # reference test_dedup :49-65
