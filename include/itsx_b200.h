@@ -87,6 +87,10 @@ typedef struct {
     double  msv_cells, bias_rows, fwd_cells, bck_cells, env_cells;   /* DP cells actually computed */
     /* device time per stage, milliseconds, CUDA events on the library's stream */
     float   ms_msv, ms_bias, ms_fwd, ms_mdom, ms_env, ms_final, ms_total;   /* ms_mdom: multidomain regions */
+    float   reserved;
+    /* selected left / right boundaries (ItsPosition winners) whose envelope came out of a region flagged
+     * multidomain -- the only rows whose coordinates depend on the stochastic-traceback ensemble */
+    int64_t n_selected_multidomain;
 } itsx_search_stats;
 
 typedef struct {
@@ -223,21 +227,66 @@ int  itsx_merge_pairs(itsx_ctx *ctx, const uint8_t *fseq, const uint8_t *fqual, 
 int  itsx_merge_fetch(itsx_ctx *ctx, int32_t *merged_index, int64_t *out_off, uint8_t *out_seq, uint8_t *out_qual);
 int  itsx_merge_get_stats(const itsx_ctx *ctx, itsx_merge_stats *st);
 
-/* ---- whole path, host buffers in / host buffers out (the call bench.py's e2e leg times) -- */
+/* ---- whole path, host buffers in / host buffers out (the calls bench.py's e2e leg times) --
+ * Together they replace main.py:534-624 for one sample: deduplicate -> _search -> ItsPosition -> Dedup ->
+ * create_trimmed_seqs (SeqSample.py:93-131, 178-225, 380-498, 517-562, 792-949). */
 typedef struct {
     int64_t n_reads, n_unique, n_kept, out_bytes;
     float   ms_h2d, ms_derep, ms_search, ms_trim, ms_d2h, ms_total;
+    float   ms_gather, reserved;     /* re-expansion of the kept slices (itsx_run_trim, resident runs with qualities) */
 } itsx_run_stats;
-/* derep + search + positions + single-end trim.  Outputs: rep_index[nreads], keep[nreads],
+/* derep + search + positions + single-end trim bounds.  Outputs: rep_index[nreads], keep[nreads],
  * lo[nreads], hi[nreads] (any may be NULL). */
 int  itsx_run(itsx_ctx *ctx, const uint8_t *seq, const int64_t *off, int64_t nreads,
               const itsx_search_params *prm, int32_t *rep_index, uint8_t *keep, int32_t *lo, int32_t *hi,
               itsx_run_stats *st);
-/* the same with the reads already resident (uploaded by itsx_reads_upload): kernels only */
+/* the same followed by the re-expansion: bases AND qualities go in, the kept reads' trimmed bases and qualities come
+ * back packed in input order -- what Dedup.create_trimmed_seqs writes (SeqSample.py:792-949) minus the titles, which
+ * never leave the host.  Output buffers must hold the worst case: kept_index[nreads], out_off[nreads + 1],
+ * out_seq / out_qual [off[nreads]] (every read kept whole); st->n_kept / st->out_bytes say how much was written.
+ * rep_index may be NULL. */
+int  itsx_run_trim(itsx_ctx *ctx, const uint8_t *seq, const uint8_t *qual, const int64_t *off, int64_t nreads,
+                   const itsx_search_params *prm, int32_t *rep_index, int32_t *kept_index, int64_t *out_off,
+                   uint8_t *out_seq, uint8_t *out_qual, itsx_run_stats *st);
+/* the same with the reads already resident (itsx_reads_upload [+ itsx_quals_upload]): kernels only.  With the
+ * qualities resident the run ends with the re-expansion and itsx_run_fetch copies its result out. */
 int  itsx_reads_upload(itsx_ctx *ctx, const uint8_t *seq, const int64_t *off, int64_t nreads);
+int  itsx_quals_upload(itsx_ctx *ctx, const uint8_t *qual);      /* qual[off[nreads]] of the resident reads */
+/* exact dereplication of the resident reads (what itsx_derep does after its upload); build_search_set = 0 skips the
+ * re-coding of the representatives for a context that will not search them (the block side of a sharded run) */
+int  itsx_derep_resident(itsx_ctx *ctx, int build_search_set, int64_t *n_unique);
 int  itsx_run_resident(itsx_ctx *ctx, const itsx_search_params *prm, itsx_run_stats *st);
+int  itsx_run_fetch(itsx_ctx *ctx, int64_t *n_kept, int64_t *total, int32_t *kept_index, int64_t *out_off,
+                    uint8_t *out_seq, uint8_t *out_qual);
 /* number of kernel launches issued by this ctx so far (bench.py's gpu_launches) */
 int64_t itsx_launch_count(const itsx_ctx *ctx);
+
+/* ---- one sample sharded over the G GPUs of a box ---------------------------------------------------
+ * vsearch --fastx_uniques and hmmsearch are global over a sample (SeqSample.py:106-116, 191-209): first occurrence
+ * of a class, per-profile domZ.  A rank holds a contiguous block of the reads in a LOCAL context and the classes
+ * whose key64 % G equals its rank in an OWNER context; the host driver (itsxpress_b200/distributed.py) moves the
+ * buffers below with two NCCL all-to-alls and one all-reduce.  Every buffer may be device memory.
+ *   local:  itsx_reads_upload, itsx_derep_resident(0), itsx_shard_plan, itsx_shard_pack
+ *   owner:  itsx_shard_owner_derep, itsx_search_stage1, [all-reduce nreported], itsx_nreported_set,
+ *           itsx_search_stage2, itsx_shard_answers
+ *   local:  itsx_shard_apply, itsx_trim_bounds / itsx_trim_gather */
+/* per destination rank g: records (local uniques owned by g) and their bases; one D2H of 2 G counters */
+int  itsx_shard_plan(itsx_ctx *local, int G, int64_t *rec_counts, int64_t *byte_counts);
+/* rec[n_unique_local]: (global read index of the unique's first read) | (length << 32), grouped by owner, ascending
+ * index inside a group; bases[sum byte_counts]: their bases back to back in the same order */
+int  itsx_shard_pack(itsx_ctx *local, int64_t first_global_index, uint64_t *rec, uint8_t *bases);
+/* the records / bases received from all ranks in source-rank order (= ascending global read index) become the owner
+ * context's read set: exact derep (first arrival = first occurrence), the classes become its search set */
+int  itsx_shard_owner_derep(itsx_ctx *owner, const uint64_t *rec, int64_t nrec, const uint8_t *bases, int64_t nbytes,
+                            int64_t *n_own);
+/* after itsx_search_stage2: ans[nrec][4] = {global index of the class representative | strand << 31, start, stop,
+ * tlen} (-1 = None) per received record, arrival order */
+int  itsx_shard_answers(itsx_ctx *owner, int64_t nrec, int32_t *ans);
+/* the answers that came back (same order as itsx_shard_pack's records) become the local context's position table
+ * (one row per local unique); rep_global[nreads] / strand[nreads] (may be NULL): the global class representative
+ * and strand of every read of the block */
+int  itsx_shard_apply(itsx_ctx *local, const int32_t *ans, int64_t n_unique_local, int64_t *rep_global,
+                      uint8_t *strand);
 
 /* ---- host-side FASTQ scanner / packer / formatter (multi-threaded C++, no GPU involved) -------------
  * Replace Biopython's SeqIO.parse / SeqIO.write on the path (SeqSample.py:746-757, 912-945): a decompressed

@@ -32,7 +32,9 @@ class SearchStats(C.Structure):
                                           "n_hits_reported", "n_domains", "n_domains_reported",
                                           "n_multidomain_regions", "n_dom_overflow")] + \
                [(n, C.c_double) for n in ("msv_cells", "bias_rows", "fwd_cells", "bck_cells", "env_cells")] + \
-               [(n, C.c_float) for n in ("ms_msv", "ms_bias", "ms_fwd", "ms_mdom", "ms_env", "ms_final", "ms_total")]
+               [(n, C.c_float) for n in ("ms_msv", "ms_bias", "ms_fwd", "ms_mdom", "ms_env", "ms_final", "ms_total",
+                                          "reserved")] + \
+               [("n_selected_multidomain", C.c_int64)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -63,7 +65,8 @@ MERGE_REASONS = ("ok", "repeat", "staggered", "maxdiffs", "maxdiffpct", "nokmers
 
 class RunStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_reads", "n_unique", "n_kept", "out_bytes")] + \
-               [(n, C.c_float) for n in ("ms_h2d", "ms_derep", "ms_search", "ms_trim", "ms_d2h", "ms_total")]
+               [(n, C.c_float) for n in ("ms_h2d", "ms_derep", "ms_search", "ms_trim", "ms_d2h", "ms_total",
+                                          "ms_gather", "reserved")]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -86,7 +89,8 @@ SYMBOLS = [
     "itsx_nreported", "itsx_positions", "itsx_search_stage1", "itsx_search_seqs_stage1", "itsx_search_shard",
     "itsx_nreported_set", "itsx_search_stage2", "itsx_positions_set",
     "itsx_trim_set_map", "itsx_trim_bounds", "itsx_trim_gather", "itsx_run", "itsx_reads_upload", "itsx_run_resident",
-    "itsx_launch_count",
+    "itsx_launch_count", "itsx_run_trim", "itsx_quals_upload", "itsx_derep_resident", "itsx_run_fetch",
+    "itsx_shard_plan", "itsx_shard_pack", "itsx_shard_owner_derep", "itsx_shard_answers", "itsx_shard_apply",
     "itsx_merge_default_params", "itsx_merge_pairs", "itsx_merge_fetch", "itsx_merge_get_stats",
     "itsx_host_last_error", "itsx_fastq_index", "itsx_bytes_gather", "itsx_fastq_format",
 ]
@@ -150,6 +154,15 @@ def lib():
     L.itsx_run_resident.argtypes = [vp, C.POINTER(SearchParams), C.POINTER(RunStats)]
     L.itsx_launch_count.argtypes = [vp]
     L.itsx_launch_count.restype = i64
+    L.itsx_run_trim.argtypes = [vp, vp, vp, vp, i64, C.POINTER(SearchParams), vp, vp, vp, vp, vp, C.POINTER(RunStats)]
+    L.itsx_quals_upload.argtypes = [vp, vp]
+    L.itsx_derep_resident.argtypes = [vp, C.c_int, vp]
+    L.itsx_run_fetch.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.itsx_shard_plan.argtypes = [vp, C.c_int, vp, vp]
+    L.itsx_shard_pack.argtypes = [vp, i64, vp, vp]
+    L.itsx_shard_owner_derep.argtypes = [vp, vp, i64, vp, i64, vp]
+    L.itsx_shard_answers.argtypes = [vp, i64, vp]
+    L.itsx_shard_apply.argtypes = [vp, vp, i64, vp, vp]
     L.itsx_merge_default_params.argtypes = [C.POINTER(MergeParams)]
     L.itsx_merge_default_params.restype = None
     L.itsx_merge_pairs.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(MergeParams), vp, vp, vp, vp]
@@ -403,8 +416,9 @@ class Context:
         self._chk(lib().itsx_trim_bounds(self._h, mode, _p(o), nreads, _p(keep), _p(lo), _p(hi), C.byref(nk)))
         return keep, lo, hi, int(nk.value)
 
-    def trim_gather(self, nreads, mode=0, seq=None, qual=None, off=None):
-        """Returns (kept_index, out_off, out_seq, out_qual) with the slices packed back to back."""
+    def trim_gather(self, nreads, mode=0, seq=None, qual=None, off=None, resident_qual=False):
+        """Returns (kept_index, out_off, out_seq, out_qual) with the slices packed back to back.  resident_qual: the
+        qualities of the resident reads were uploaded with quals_upload()."""
         nk, tot = C.c_int64(), C.c_int64()
         seq = None if seq is None else np.ascontiguousarray(seq, dtype=np.uint8)
         qual = None if qual is None else np.ascontiguousarray(qual, dtype=np.uint8)
@@ -415,7 +429,7 @@ class Context:
         ki = np.empty(nk.value, np.int32)
         oo = np.empty(nk.value + 1, np.int64)
         os_ = np.empty(tot.value, np.uint8)
-        oq = np.empty(tot.value, np.uint8) if qual is not None else None
+        oq = np.empty(tot.value, np.uint8) if (qual is not None or resident_qual) else None
         self._chk(L.itsx_trim_gather(self._h, mode, _p(seq), _p(qual), _p(off), nreads, C.byref(nk), C.byref(tot),
                                      _p(ki), _p(oo), _p(os_), _p(oq)))
         return ki, oo, os_, oq
@@ -469,6 +483,49 @@ class Context:
         off = np.ascontiguousarray(off, dtype=np.int64)
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
         self._chk(lib().itsx_reads_upload(self._h, _p(seq), _p(off), len(off) - 1))
+
+    def quals_upload(self, qual):
+        qual = np.ascontiguousarray(qual, dtype=np.uint8)
+        self._chk(lib().itsx_quals_upload(self._h, _p(qual)))
+
+    def derep_resident(self, build_search_set=True):
+        nu = C.c_int64()
+        self._chk(lib().itsx_derep_resident(self._h, int(bool(build_search_set)), C.byref(nu)))
+        return int(nu.value)
+
+    def run_trim(self, seq, qual, off, params=None, out=None):
+        """The whole path for one single-end sample, host buffers in and out: derep + search + positions + trim with
+        re-expansion.  Returns (dict(kept_index, out_off, out_seq, out_qual[, rep]) trimmed to size, RunStats)."""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        qual = np.ascontiguousarray(qual, dtype=np.uint8)
+        n = len(off) - 1
+        if out is None:
+            out = dict(rep=np.empty(n, np.int32), kept_index=np.empty(n, np.int32), out_off=np.empty(n + 1, np.int64),
+                       out_seq=np.empty(len(seq), np.uint8), out_qual=np.empty(len(seq), np.uint8))
+        st = RunStats()
+        self._chk(lib().itsx_run_trim(self._h, _p(seq), _p(qual), _p(off), n,
+                                      C.byref(params) if params is not None else None, _p(out.get("rep")),
+                                      _p(out["kept_index"]), _p(out["out_off"]), _p(out["out_seq"]), _p(out["out_qual"]),
+                                      C.byref(st)))
+        nk, tot = int(st.n_kept), int(st.out_bytes)
+        view = dict(kept_index=out["kept_index"][:nk], out_off=out["out_off"][:nk + 1], out_seq=out["out_seq"][:tot],
+                    out_qual=out["out_qual"][:tot])
+        if out.get("rep") is not None:
+            view["rep"] = out["rep"]
+        return view, st
+
+    def run_fetch(self):
+        """Gathered slices left on the device by run_resident() with the qualities resident."""
+        nk, tot = C.c_int64(), C.c_int64()
+        L = lib()
+        self._chk(L.itsx_run_fetch(self._h, C.byref(nk), C.byref(tot), None, None, None, None))
+        ki = np.empty(nk.value, np.int32)
+        oo = np.empty(nk.value + 1, np.int64)
+        os_ = np.empty(tot.value, np.uint8)
+        oq = np.empty(tot.value, np.uint8)
+        self._chk(L.itsx_run_fetch(self._h, None, None, _p(ki), _p(oo), _p(os_), _p(oq)))
+        return ki, oo, os_, oq
 
     def run_resident(self, params=None):
         st = RunStats()

@@ -179,6 +179,8 @@ int itsx_reads_upload(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64
     c->n_unique = 0;
     c->map_external = false;
     c->pos_valid = false;
+    c->qual_resident = false;
+    c->r_gathered = false;
     const size_t padded = ((size_t)total + 15) / 16 * 16 + 32;
     CUDA_TRY(c, c->d_ascii.ensure(padded));
     CUDA_TRY(c, c->d_off.ensure((size_t)(nreads + 1) * 8));
@@ -533,6 +535,8 @@ int itsx_trim_gather(itsx_ctx *c, int mode, const uint8_t *seq, const uint8_t *q
         CUDA_TRY(c, t_qual.ensure((size_t)tq + 16));
         if (tq) CUDA_TRY(c, cudaMemcpyAsync(t_qual.p, qual, (size_t)tq, cudaMemcpyDefault, st));
         d_qual = t_qual.as<uint8_t>();
+    } else if (!seq && !off && c->qual_resident) {
+        d_qual = c->d_qual.as<uint8_t>();       // qualities of the resident reads (itsx_quals_upload)
     }
     rc = trim_gather_dev(c, d_seq, d_qual, d_off ? d_off : c->d_off.as<int64_t>(), nreads, t_keep.as<uint8_t>(),
                          t_lo.as<int32_t>(), t_hi.as<int32_t>(), n_kept, total, t_ki, t_oo, t_os, t_oq);
@@ -546,8 +550,8 @@ int itsx_trim_gather(itsx_ctx *c, int mode, const uint8_t *seq, const uint8_t *q
 }
 
 // ---- whole path ------------------------------------------------------------------------------------------
-static int run_device_part(itsx_ctx *c, const itsx_search_params *prm, itsx_run_stats *rs, DevBuf &keep, DevBuf &lo,
-                           DevBuf &hi, cudaEvent_t *ev)
+// derep -> search -> positions -> trim bounds [-> re-expansion of the kept slices when the qualities are resident]
+static int run_device_part(itsx_ctx *c, const itsx_search_params *prm, itsx_run_stats *rs, cudaEvent_t *ev)
 {
     cudaStream_t st = c->stream;
     CUDA_TRY(c, cudaEventRecord(ev[1], st));
@@ -566,22 +570,59 @@ static int run_device_part(itsx_ctx *c, const itsx_search_params *prm, itsx_run_
     if (rc) return rc;
     CUDA_TRY(c, cudaEventRecord(ev[3], st));
     const int64_t n = c->nreads;
-    CUDA_TRY(c, keep.ensure((size_t)n + 16));
-    CUDA_TRY(c, lo.ensure((size_t)n * 4 + 16));
-    CUDA_TRY(c, hi.ensure((size_t)n * 4 + 16));
+    CUDA_TRY(c, c->r_keep.ensure((size_t)n + 16));
+    CUDA_TRY(c, c->r_lo.ensure((size_t)n * 4 + 16));
+    CUDA_TRY(c, c->r_hi.ensure((size_t)n * 4 + 16));
     int64_t nk = 0;
-    rc = trim_bounds_dev(c, 0, nullptr, n, keep.as<uint8_t>(), lo.as<int32_t>(), hi.as<int32_t>(), &nk);
+    rc = trim_bounds_dev(c, 0, nullptr, n, c->r_keep.as<uint8_t>(), c->r_lo.as<int32_t>(), c->r_hi.as<int32_t>(), &nk);
     if (rc) return rc;
     CUDA_TRY(c, cudaEventRecord(ev[4], st));
     rs->n_reads = n;
     rs->n_unique = c->n_unique;
     rs->n_kept = nk;
+    c->r_nkept = nk;
+    c->r_total = 0;
+    c->r_gathered = false;
     if (n) {
         int64_t tot = 0;
         CUDA_TRY(c, cudaMemcpyAsync(&tot, c->d_list2.as<int64_t>() + n, 8, cudaMemcpyDefault, st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
         rs->out_bytes = tot;
+        c->r_total = tot;
     }
+    if (c->qual_resident) {
+        int64_t nk2 = 0, tot2 = 0;
+        rc = trim_gather_dev(c, c->d_ascii.as<uint8_t>(), c->d_qual.as<uint8_t>(), c->d_off.as<int64_t>(), n,
+                             c->r_keep.as<uint8_t>(), c->r_lo.as<int32_t>(), c->r_hi.as<int32_t>(), &nk2, &tot2,
+                             c->r_ki, c->r_oo, c->r_os, c->r_oq);
+        if (rc) return rc;
+        c->r_gathered = true;
+    }
+    CUDA_TRY(c, cudaEventRecord(ev[6], st));
+    return ITSX_OK;
+}
+
+static void run_times(itsx_run_stats &rs, cudaEvent_t *ev, bool with_copies)
+{
+    if (with_copies) cudaEventElapsedTime(&rs.ms_h2d, ev[0], ev[1]);
+    cudaEventElapsedTime(&rs.ms_derep, ev[1], ev[2]);
+    cudaEventElapsedTime(&rs.ms_search, ev[2], ev[3]);
+    cudaEventElapsedTime(&rs.ms_trim, ev[3], ev[4]);
+    cudaEventElapsedTime(&rs.ms_gather, ev[4], ev[6]);
+    if (with_copies) cudaEventElapsedTime(&rs.ms_d2h, ev[6], ev[5]);
+    cudaEventElapsedTime(&rs.ms_total, ev[0], ev[5]);
+}
+
+int itsx_quals_upload(itsx_ctx *c, const uint8_t *qual)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->map_external) { c->err = "quals_upload: no reads are resident (itsx_reads_upload first)"; return ITSX_EINVAL; }
+    if (c->total_bases && !qual) { c->err = "quals_upload: null buffer"; return ITSX_EINVAL; }
+    CUDA_TRY(c, c->d_qual.ensure((size_t)c->total_bases + 64));
+    if (c->total_bases) CUDA_TRY(c, cudaMemcpyAsync(c->d_qual.p, qual, (size_t)c->total_bases, cudaMemcpyDefault, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->qual_resident = true;
     return ITSX_OK;
 }
 
@@ -590,29 +631,23 @@ int itsx_run(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64_t nreads
 {
     CHECK_CTX(c);
     CUDA_TRY(c, cudaSetDevice(c->device));
-    static thread_local DevBuf t_keep, t_lo, t_hi;
     itsx_run_stats rs{};
-    cudaEvent_t ev[6];
+    cudaEvent_t ev[7];
     for (auto &e : ev) CUDA_TRY(c, cudaEventCreate(&e));
     cudaStream_t st = c->stream;
     CUDA_TRY(c, cudaEventRecord(ev[0], st));
     int rc = itsx_reads_upload(c, seq, off, nreads);
-    if (!rc) rc = run_device_part(c, prm, &rs, t_keep, t_lo, t_hi, ev);
+    if (!rc) rc = run_device_part(c, prm, &rs, ev);
     if (!rc && nreads) {
         if (rep_index) CUDA_TRY(c, cudaMemcpyAsync(rep_index, c->d_rep.p, (size_t)nreads * 4, cudaMemcpyDefault, st));
-        if (keep) CUDA_TRY(c, cudaMemcpyAsync(keep, t_keep.p, (size_t)nreads, cudaMemcpyDefault, st));
-        if (lo) CUDA_TRY(c, cudaMemcpyAsync(lo, t_lo.p, (size_t)nreads * 4, cudaMemcpyDefault, st));
-        if (hi) CUDA_TRY(c, cudaMemcpyAsync(hi, t_hi.p, (size_t)nreads * 4, cudaMemcpyDefault, st));
+        if (keep) CUDA_TRY(c, cudaMemcpyAsync(keep, c->r_keep.p, (size_t)nreads, cudaMemcpyDefault, st));
+        if (lo) CUDA_TRY(c, cudaMemcpyAsync(lo, c->r_lo.p, (size_t)nreads * 4, cudaMemcpyDefault, st));
+        if (hi) CUDA_TRY(c, cudaMemcpyAsync(hi, c->r_hi.p, (size_t)nreads * 4, cudaMemcpyDefault, st));
     }
     if (!rc) {
         CUDA_TRY(c, cudaEventRecord(ev[5], st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
-        cudaEventElapsedTime(&rs.ms_h2d, ev[0], ev[1]);
-        cudaEventElapsedTime(&rs.ms_derep, ev[1], ev[2]);
-        cudaEventElapsedTime(&rs.ms_search, ev[2], ev[3]);
-        cudaEventElapsedTime(&rs.ms_trim, ev[3], ev[4]);
-        cudaEventElapsedTime(&rs.ms_d2h, ev[4], ev[5]);
-        cudaEventElapsedTime(&rs.ms_total, ev[0], ev[5]);
+        run_times(rs, ev, true);
         if (out) *out = rs;
     }
     for (auto &e : ev) cudaEventDestroy(e);
@@ -623,20 +658,65 @@ int itsx_run_resident(itsx_ctx *c, const itsx_search_params *prm, itsx_run_stats
 {
     CHECK_CTX(c);
     CUDA_TRY(c, cudaSetDevice(c->device));
-    static thread_local DevBuf t_keep, t_lo, t_hi;
     itsx_run_stats rs{};
-    cudaEvent_t ev[6];
+    cudaEvent_t ev[7];
     for (auto &e : ev) CUDA_TRY(c, cudaEventCreate(&e));
     cudaStream_t st = c->stream;
     CUDA_TRY(c, cudaEventRecord(ev[0], st));
-    int rc = run_device_part(c, prm, &rs, t_keep, t_lo, t_hi, ev);
+    int rc = run_device_part(c, prm, &rs, ev);
     if (!rc) {
         CUDA_TRY(c, cudaEventRecord(ev[5], st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
-        cudaEventElapsedTime(&rs.ms_derep, ev[1], ev[2]);
-        cudaEventElapsedTime(&rs.ms_search, ev[2], ev[3]);
-        cudaEventElapsedTime(&rs.ms_trim, ev[3], ev[4]);
-        cudaEventElapsedTime(&rs.ms_total, ev[0], ev[5]);
+        run_times(rs, ev, false);
+        if (out) *out = rs;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+int itsx_run_fetch(itsx_ctx *c, int64_t *n_kept, int64_t *total, int32_t *kept_index, int64_t *out_off,
+                   uint8_t *out_seq, uint8_t *out_qual)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->r_gathered) { c->err = "run_fetch: no gathered output is resident (qualities were not uploaded)"; return ITSX_EINVAL; }
+    cudaStream_t st = c->stream;
+    const int64_t nk = c->r_nkept, tot = c->r_total;
+    if (n_kept) *n_kept = nk;
+    if (total) *total = tot;
+    if (kept_index && nk) CUDA_TRY(c, cudaMemcpyAsync(kept_index, c->r_ki.p, (size_t)nk * 4, cudaMemcpyDefault, st));
+    if (out_off) CUDA_TRY(c, cudaMemcpyAsync(out_off, c->r_oo.p, (size_t)(nk + 1) * 8, cudaMemcpyDefault, st));
+    if (out_seq && tot) CUDA_TRY(c, cudaMemcpyAsync(out_seq, c->r_os.p, (size_t)tot, cudaMemcpyDefault, st));
+    if (out_qual && tot) CUDA_TRY(c, cudaMemcpyAsync(out_qual, c->r_oq.p, (size_t)tot, cudaMemcpyDefault, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return ITSX_OK;
+}
+
+int itsx_run_trim(itsx_ctx *c, const uint8_t *seq, const uint8_t *qual, const int64_t *off, int64_t nreads,
+                  const itsx_search_params *prm, int32_t *rep_index, int32_t *kept_index, int64_t *out_off,
+                  uint8_t *out_seq, uint8_t *out_qual, itsx_run_stats *out)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (nreads > 0 && !qual) { c->err = "run_trim: qualities are required"; return ITSX_EINVAL; }
+    itsx_run_stats rs{};
+    cudaEvent_t ev[7];
+    for (auto &e : ev) CUDA_TRY(c, cudaEventCreate(&e));
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, cudaEventRecord(ev[0], st));
+    int rc = itsx_reads_upload(c, seq, off, nreads);
+    if (!rc) rc = itsx_quals_upload(c, qual);
+    if (!rc) rc = run_device_part(c, prm, &rs, ev);
+    if (!rc) {
+        const int64_t nk = c->r_nkept, tot = c->r_total;
+        if (rep_index && nreads) CUDA_TRY(c, cudaMemcpyAsync(rep_index, c->d_rep.p, (size_t)nreads * 4, cudaMemcpyDefault, st));
+        if (kept_index && nk) CUDA_TRY(c, cudaMemcpyAsync(kept_index, c->r_ki.p, (size_t)nk * 4, cudaMemcpyDefault, st));
+        if (out_off) CUDA_TRY(c, cudaMemcpyAsync(out_off, c->r_oo.p, (size_t)(nk + 1) * 8, cudaMemcpyDefault, st));
+        if (out_seq && tot) CUDA_TRY(c, cudaMemcpyAsync(out_seq, c->r_os.p, (size_t)tot, cudaMemcpyDefault, st));
+        if (out_qual && tot) CUDA_TRY(c, cudaMemcpyAsync(out_qual, c->r_oq.p, (size_t)tot, cudaMemcpyDefault, st));
+        CUDA_TRY(c, cudaEventRecord(ev[5], st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        run_times(rs, ev, true);
         if (out) *out = rs;
     }
     for (auto &e : ev) cudaEventDestroy(e);

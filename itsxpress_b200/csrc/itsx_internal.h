@@ -165,13 +165,24 @@ struct itsx_ctx {
     itsx_merge_params mg_tabs_prm{};
     itsx_merge_stats mgstats{};
 
+    // whole-path calls (itsx_run*): qualities of the resident reads, bounds and gathered slices of the last run
+    DevBuf d_qual;
+    bool qual_resident = false, r_gathered = false;
+    DevBuf r_keep, r_lo, r_hi, r_ki, r_oo, r_os, r_oq;
+    int64_t r_nkept = 0, r_total = 0;
+
+    // one sample sharded over G GPUs (shard.cu): bucket order of the block's uniques, scratch, send / receive staging
+    int sh_G = 0;
+    int64_t sh_bytes = 0;
+    DevBuf d_sh_order, d_sh_tmp, d_sh_bases, d_sh_rec;
+
     std::vector<cudaStream_t> lanes;      // side streams for the per-profile launches
     std::vector<cudaEvent_t> lane_ev;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 };
 
 enum { CNT_COLLIDE = 0, CNT_PAST_FWD, CNT_FWD_ROWS, CNT_BCK_ROWS, CNT_ENV_ROWS, CNT_DOM_OVERFLOW, CNT_MULTI,
-       CNT_HITS_REPORTED, CNT_DOM_REPORTED, CNT_MAX_ENVLEN, CNT_BIAS_ROWS, CNT_NDOM, CNT_N };
+       CNT_HITS_REPORTED, CNT_DOM_REPORTED, CNT_MAX_ENVLEN, CNT_BIAS_ROWS, CNT_NDOM, CNT_SEL_MULTI, CNT_N };
 
 #define CUDA_TRY(ctx, call)                                                                   \
     do {                                                                                      \
@@ -181,6 +192,38 @@ enum { CNT_COLLIDE = 0, CNT_PAST_FWD, CNT_FWD_ROWS, CNT_BCK_ROWS, CNT_ENV_ROWS, 
             return ITSX_ECUDA;                                                                \
         }                                                                                     \
     } while (0)
+
+#ifdef __CUDACC__
+// byte mover of the trim / re-expansion and shard-exchange kernels: segment j = src[soff[j] .. + len) -> dst[doff[j] ..), one warp per segment,
+// 16-byte stores on the aligned middle of the destination, bytes at its head and tail.  Source words are read as
+// aligned 32-bit words and funnel-shifted into place, so neither side needs any alignment.
+__device__ __forceinline__ void warp_copy(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int n, int lane)
+{
+    const int head = min(n, (int)((16 - ((uintptr_t)dst & 15)) & 15));
+    for (int b = lane; b < head; b += 32) dst[b] = src[b];
+    const int nvec = (n - head) >> 4;
+    const uint8_t *s = src + head;
+    uint4 *d4 = (uint4 *)(dst + head);
+    const int sh = (int)((uintptr_t)s & 3) * 8;
+    const uint32_t *sw = (const uint32_t *)((uintptr_t)s & ~(uintptr_t)3);
+    for (int v = lane; v < nvec; v += 32) {
+        const uint32_t *p = sw + v * 4;
+        const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
+        uint4 o;
+        if (sh == 0) {
+            o = make_uint4(w0, w1, w2, w3);
+        } else {
+            const uint32_t w4 = p[4];
+            o.x = __funnelshift_r(w0, w1, sh); o.y = __funnelshift_r(w1, w2, sh);
+            o.z = __funnelshift_r(w2, w3, sh); o.w = __funnelshift_r(w3, w4, sh);
+        }
+        d4[v] = o;
+    }
+    const int done = head + (nvec << 4);
+    for (int b = done + lane; b < n; b += 32) dst[b] = src[b];
+}
+
+#endif
 
 // stage entry points (implemented in derep.cu / search.cu / trim.cu)
 int derep_run(itsx_ctx *c);                                   // reads already in d_ascii/d_off

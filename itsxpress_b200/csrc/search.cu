@@ -585,42 +585,78 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
             bool triggered = false;
             int nmulti = 0;
             SPEC(0, 0) = 0.f; SPEC(0, 1) = 0.f;   // btot[0], etot[0]
-            float r0 = SPEC(1, 0), r1 = SPEC(1, 1), r2 = SPEC(1, 2), r3 = SPEC(1, 3), r4 = SPEC(1, 4);
-            for (int j = 1; j <= L; j++) {
-                const float v0 = r0, v1 = r1, v2 = r2, v3 = r3, v4 = r4;
-                if (j < L) { r0 = SPEC(j + 1, 0); r1 = SPEC(j + 1, 1); r2 = SPEC(j + 1, 2); r3 = SPEC(j + 1, 3); r4 = SPEC(j + 1, 4); }
-                const float db = v0 * scaleproduct, de = v1 * scaleproduct;
-                const float btot_p = btot, etot_p = etot;
-                btot = btot + db;
-                etot = etot + de;
-                float njcp = v2 * scaleproduct;
-                njcp += v3 * scaleproduct;
-                njcp += v4 * scaleproduct;
-                const float mocc = 1.f - njcp;
-                SPEC(j, 0) = btot; SPEC(j, 1) = etot;
-                if (!triggered) {
-                    if (mocc - (btot - btot_p) < rt2) ri = j;
-                    else if (ri == -1) ri = j;
-                    if (mocc >= rt1) triggered = true;
-                } else if (mocc - (etot - etot_p) < rt2) {
-                    float mx = -1.0f;
-                    const float e0 = SPEC(ri - 1, 1);
-                    for (int z = ri; z <= j; z++) {
-                        const float x1 = SPEC(z, 1) - e0, x2 = btot - SPEC(z - 1, 0);
-                        const float en = x1 < x2 ? x1 : x2;
-                        if (en > mx) mx = en;
+            // The posterior rows are read back in blocks of DEC_B rows with the NEXT block's loads already in flight:
+            // the DP state registers are dead here, and one row ahead is far too little to cover an HBM round trip
+            // for a 40-instruction body (ncu r2a: 16 % of the kernel's warp time sat on this loop's first load).
+            constexpr int DEC_B = 8;
+            float nx[DEC_B][SPEC_C];
+#pragma unroll
+            for (int q = 0; q < DEC_B; q++)
+#pragma unroll
+                for (int cc = 0; cc < SPEC_C; cc++) nx[q][cc] = (1 + q <= L) ? SPEC(1 + q, cc) : 0.f;
+            for (int j0 = 1; j0 <= L; j0 += DEC_B) {
+                float cur[DEC_B][SPEC_C];
+#pragma unroll
+                for (int q = 0; q < DEC_B; q++)
+#pragma unroll
+                    for (int cc = 0; cc < SPEC_C; cc++) cur[q][cc] = nx[q][cc];
+#pragma unroll
+                for (int q = 0; q < DEC_B; q++)
+#pragma unroll
+                    for (int cc = 0; cc < SPEC_C; cc++) nx[q][cc] = (j0 + DEC_B + q <= L) ? SPEC(j0 + DEC_B + q, cc) : 0.f;
+#pragma unroll
+                for (int q = 0; q < DEC_B; q++) {
+                    const int j = j0 + q;
+                    if (j > L) break;
+                    const float v0 = cur[q][0], v1 = cur[q][1], v2 = cur[q][2], v3 = cur[q][3], v4 = cur[q][4];
+                    const float db = v0 * scaleproduct, de = v1 * scaleproduct;
+                    const float btot_p = btot, etot_p = etot;
+                    btot = btot + db;
+                    etot = etot + de;
+                    float njcp = v2 * scaleproduct;
+                    njcp += v3 * scaleproduct;
+                    njcp += v4 * scaleproduct;
+                    const float mocc = 1.f - njcp;
+                    SPEC(j, 0) = btot; SPEC(j, 1) = etot;
+                    if (!triggered) {
+                        if (mocc - (btot - btot_p) < rt2) ri = j;
+                        else if (ri == -1) ri = j;
+                        if (mocc >= rt1) triggered = true;
+                    } else if (mocc - (etot - etot_p) < rt2) {
+                        // region ri..j: multidomain iff  max_z min(etot[z] - etot[ri-1], btot[j] - btot[z-1]) >= rt3.
+                        // etot[], btot[] of the region come back from the slab four z at a time (independent loads)
+                        float mx = -1.0f;
+                        const float e0 = SPEC(ri - 1, 1);
+                        int z = ri;
+                        for (; z + 3 <= j; z += 4) {
+                            const float ea = SPEC(z, 1), eb = SPEC(z + 1, 1), ec = SPEC(z + 2, 1), ed = SPEC(z + 3, 1);
+                            const float ba = SPEC(z - 1, 0), bb = SPEC(z, 0), bc = SPEC(z + 1, 0), bd = SPEC(z + 2, 0);
+                            float x1 = ea - e0, x2 = btot - ba, en = x1 < x2 ? x1 : x2;
+                            if (en > mx) mx = en;
+                            x1 = eb - e0; x2 = btot - bb; en = x1 < x2 ? x1 : x2;
+                            if (en > mx) mx = en;
+                            x1 = ec - e0; x2 = btot - bc; en = x1 < x2 ? x1 : x2;
+                            if (en > mx) mx = en;
+                            x1 = ed - e0; x2 = btot - bd; en = x1 < x2 ? x1 : x2;
+                            if (en > mx) mx = en;
+                        }
+                        for (; z <= j; z++) {
+                            const float x1 = SPEC(z, 1) - e0, x2 = btot - SPEC(z - 1, 0);
+                            const float en = x1 < x2 ? x1 : x2;
+                            if (en > mx) mx = en;
+                        }
+                        const int multi = mx >= rt3;
+                        nmulti += multi;
+                        if (nd < ITSX_MAXDOM) {
+                            a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 0] = ri;
+                            a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 1] = j | (multi << 30);
+                            nd++;
+                        } else {
+                            atomicAdd(&a.counters[CNT_DOM_OVERFLOW], 1ull);
+                        }
+                        ri = -1;
+                        triggered = false;
                     }
-                    const int multi = mx >= rt3;
-                    nmulti += multi;
-                    if (nd < ITSX_MAXDOM) {
-                        a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 0] = ri;
-                        a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 1] = j | (multi << 30);
-                        nd++;
-                    } else {
-                        atomicAdd(&a.counters[CNT_DOM_OVERFLOW], 1ull);
-                    }
-                    ri = -1;
-                    triggered = false;
                 }
             }
             if (nmulti) atomicAdd(&a.counters[CNT_MULTI], (unsigned long long)nmulti);
@@ -1343,9 +1379,20 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
 
         // ---- Forward over the envelope; match rows (+ raw E) go to the scratch slab ----
         float xN = 1.f, xJ = 0.f, xC = 0.f, xE = 0.f, xB = N_move, totscale = 0.f;
+        // residue words (8 nibbles) are fetched one word ahead of their use, in both sweeps: a dependent global load
+        // per row was this kernel's largest stall (ncu r2a: 20 % of its warp time on the shift after the load)
+        const int p0 = ienv - 1;                     // 0-based position of envelope row 1
+        int fw = p0 >> 3;
+        uint32_t wcur = (fw * 8 < L) ? w[fw] : 0u, wnxt = ((fw + 1) * 8 < L) ? w[fw + 1] : 0u;
         for (int i = 1; i <= Lw; i++) {
+            const int fpos = p0 + i - 1;
+            if ((fpos >> 3) != fw) {
+                fw = fpos >> 3;
+                wcur = wnxt;
+                wnxt = ((fw + 1) * 8 < L) ? w[fw + 1] : 0u;
+            }
             if (i <= Ld) {
-                const float4 *er = (const float4 *)(s_e + residue_at(w, ienv - 1 + i - 1) * ESTRIDE);
+                const float4 *er = (const float4 *)(s_e + ((wcur >> ((fpos & 7) * 4)) & 15u) * ESTRIDE);
                 // pass 1, descending k, in place: M and I of row i from row i-1 (no serial dependence, so the
                 // scheduler needs no far-ahead coefficient loads); pass 2, ascending: the D chain and the E sums.
                 // Same operations and summation order as the oracle's single ascending loop.
@@ -1418,8 +1465,17 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
         }
         // raw E of row i-1 (rescale of the new Backward row) comes through a register, one row ahead
         float qE = (Lw >= 2 && Lw - 1 <= Ld) ? ROW(Lw - 1, C_E) : 0.f;
+        int bw = (p0 + max(Lw, 1) - 1) >> 3;
+        uint32_t bcur = (bw * 8 < L) ? w[bw] : 0u, bnxt = (bw >= 1 && (bw - 1) * 8 < L) ? w[bw - 1] : 0u;
         for (int i = Lw; i >= 1; i--) {
             const int b = i & 1;
+            const int bpos = p0 + i - 1;
+            if ((bpos >> 3) != bw) {
+                bw = bpos >> 3;
+                bcur = bnxt;
+                bnxt = (bw >= 1 && (bw - 1) * 8 < L) ? w[bw - 1] : 0u;
+            }
+            const uint32_t xres = (bcur >> ((bpos & 7) * 4)) & 15u;
             mbar_wait(bar0 + b * 8, phase[b]);
             phase[b] ^= 1u;
             const float *rs = ring + (size_t)b * ENV_ROWF * 32 + lane;
@@ -1438,7 +1494,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                 if (i > 1) {
                     float fEp, fSp;
                     spec_decode(cEp, fEp, fSp);
-                    const float4 *er = (const float4 *)(s_e + residue_at(w, ienv - 1 + i - 1) * ESTRIDE);
+                    const float4 *er = (const float4 *)(s_e + xres * ESTRIDE);
                     bB = 0.f;
 #pragma unroll
                     for (int k = 1; k <= MAXM; k++) {
@@ -1468,7 +1524,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                         for (int k = 1; k <= MAXM; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
                     }
                 } else {
-                    const float4 *er = (const float4 *)(s_e + residue_at(w, ienv - 1) * ESTRIDE);
+                    const float4 *er = (const float4 *)(s_e + xres * ESTRIDE);
                     bB = 0.f;
 #pragma unroll
                     for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * EMIS(er, k), pc.bm[k - 1], bB);
@@ -1651,7 +1707,7 @@ __global__ void select_kernel(DomRec *__restrict__ doms, int64_t n, const int32_
 
 __global__ void best_kernel(const DomRec *__restrict__ doms, int64_t n, const ProfScalars *__restrict__ pscal,
                             const unsigned long long *__restrict__ best, int64_t nseq, int64_t seq_first,
-                            int32_t *__restrict__ pos)
+                            int32_t *__restrict__ pos, unsigned long long *__restrict__ counters)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -1664,6 +1720,7 @@ __global__ void best_kernel(const DomRec *__restrict__ doms, int64_t n, const Pr
     const unsigned long long key = (sc << 40) | (0xFFFFFFFFFFull - rank);
     const int64_t q = r.seq - seq_first;
     if (best[(size_t)side * nseq + q] != key) return;
+    if (r.is_multidomain) atomicAdd(&counters[CNT_SEL_MULTI], 1ull);
     int32_t *b = pos + (size_t)(3 + 3 * side) * nseq;
     b[q] = score10_of(r.bitscore);
     b[nseq + q] = r.ienv;
@@ -2331,17 +2388,20 @@ int search_stage2(itsx_ctx *c)
         CUDA_TRY(c, cudaMemcpyAsync(c->d_nrep.p, c->h_nrep.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
         unsigned long long *cnt = c->d_counters.as<unsigned long long>();
         CUDA_TRY(c, cudaMemsetAsync(cnt + CNT_DOM_REPORTED, 0, 8, st));
+        CUDA_TRY(c, cudaMemsetAsync(cnt + CNT_SEL_MULTI, 0, 8, st));
         select_kernel<<<nblk(c->ndom, 256), 256, 0, st>>>(c->d_doms.as<DomRec>(), c->ndom, c->d_nrep.as<int32_t>(),
                                                           c->d_pscal.as<ProfScalars>(), c->prm.domE,
                                                           c->d_best.as<unsigned long long>(), qn, q0, cnt);
         best_kernel<<<nblk(c->ndom, 256), 256, 0, st>>>(c->d_doms.as<DomRec>(), c->ndom, c->d_pscal.as<ProfScalars>(),
                                                         c->d_best.as<unsigned long long>(), qn, q0,
-                                                        c->d_pos.as<int32_t>());
+                                                        c->d_pos.as<int32_t>(), cnt);
         c->launches += 2;
-        unsigned long long nr = 0;
+        unsigned long long nr = 0, nsm = 0;
         CUDA_TRY(c, cudaMemcpyAsync(&nr, cnt + CNT_DOM_REPORTED, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(&nsm, cnt + CNT_SEL_MULTI, 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
         c->sstats.n_domains_reported = (int64_t)nr;
+        c->sstats.n_selected_multidomain = (int64_t)nsm;
     }
     CUDA_TRY(c, cudaEventRecord(e1, st));
     CUDA_TRY(c, cudaStreamSynchronize(st));

@@ -72,7 +72,8 @@ __global__ void kept_index_kernel(const int32_t *__restrict__ keepflag, const in
     }
 }
 
-// one warp per kept read: byte copy of the seq and qual slices into the packed outputs
+// one warp per kept read: the seq and qual slices go to the packed outputs with 16-byte stores on the aligned middle
+// of the destination (itsx_internal.h: warp_copy)
 __global__ void __launch_bounds__(256)
 gather_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual, const int64_t *__restrict__ off,
               const int32_t *__restrict__ kept_index, const int64_t *__restrict__ out_off,
@@ -85,10 +86,8 @@ gather_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
     const int32_t i = kept_index[t];
     const int64_t src = off[i] + lo[i], dst = out_off[t];
     const int n = hi[i] - lo[i];
-    for (int b = lane; b < n; b += 32) {
-        out_seq[dst + b] = seq[src + b];
-        if (qual) out_qual[dst + b] = qual[src + b];
-    }
+    warp_copy(seq + src, out_seq + dst, n, lane);
+    if (qual) warp_copy(qual + src, out_qual + dst, n, lane);
 }
 
 }  // namespace

@@ -4,25 +4,35 @@ The reference runs one vsearch and one hmmsearch process per sample (itsxpress/S
 191-209); both are global operations (first occurrence of a class; hmmsearch's per-profile domZ), so a
 sharded run needs exactly three exchanges:
 
-  1. dereplication, hash-partitioned:  every rank dereplicates its block of reads exactly (itsx_derep);
-     each LOCAL unique goes to the owner rank  key64 % G  with its global read index and its bases through
-     one all-to-all; the owner dereplicates what it received in global-index order (itsx_derep again, so
-     every class is verified base by base) and returns the class representative's global index.
-  2. profile search: the owner searches the classes it owns (profiles replicated); the per-profile count of
-     reported hits -- hmmsearch's domZ -- is all-reduced between stage 1 (scores, -T) and stage 2 (domE,
-     ItsPosition arg-max).
-  3. the per-class (representative index, start, stop, tlen) table is all-gathered; every rank then trims
-     its own block (itsx_trim_set_map + itsx_positions_set + itsx_trim_bounds).  Rank order = input order.
+  1. dereplication, hash-partitioned.  Reads are block-partitioned in input order.  Every rank dereplicates
+     its block exactly; each LOCAL unique goes to the owner rank  key64 % G  as one 8-byte record
+     (global read index | length << 32) plus its bases: two all-to-alls (records, bases) after one exchange of
+     the 2 G split sizes.  all_to_all delivers in source-rank order and blocks are contiguous, so the arrival
+     order IS ascending global read index: the owner's exact derep of what it received (every class verified
+     base by base again) picks the global first occurrence without any sort.
+  2. profile search.  The owner searches the classes it owns with the profiles replicated; the per-profile
+     count of reported hits -- hmmsearch's domZ -- is all-reduced between stage 1 (scores, -T) and stage 2
+     (domE, ItsPosition arg-max).  The same all-reduce carries the number of classes per owner.
+  3. answers.  One 16-byte record {representative's global index | strand << 31, start, stop, tlen} per received
+     record returns through the inverse all-to-all; the block's position table (one row per local unique) is
+     filled from it and the block is trimmed where it lies.  Rank order = input order.  No global table exists.
 
-The compute engine is duck-typed: `GpuEngine` (libitsx_b200, the product) below; the CPU tests drive the same
-orchestration over gloo with an oracle-backed engine that lives in tests/.
+`run_sharded` is the one orchestration; the compute engine is duck-typed: `GpuEngine` (libitsx_b200 through device
+pointers, csrc/shard.cu -- the product; buffers are torch CUDA tensors, collectives are NCCL over NVLink) and, in
+the CPU tests, an oracle-backed engine on numpy buffers over gloo (tests/dist_worker.py).
 """
+import time
+
 import numpy as np
+
+PHASES = ("local_derep", "plan_pack", "exchange", "owner_derep", "search_stage1", "domz_allreduce", "search_stage2",
+          "answers", "answers_exchange", "apply_trim")
 
 
 # ---- communication ---------------------------------------------------------------------------------------
 class Comm:
-    """Variable-size exchanges over torch.distributed (nccl: tensors staged on the rank's GPU; gloo: CPU)."""
+    """Variable-size exchanges over torch.distributed.  Buffers are torch tensors on `device` (nccl: the rank's GPU)
+    or numpy arrays (staged through `device`; gloo: CPU) -- what comes back has the kind that went in."""
 
     def __init__(self, group=None, device=None):
         import torch
@@ -34,79 +44,141 @@ class Comm:
         backend = dist.get_backend(group) if self.on else "none"
         self.device = device if device is not None else (
             torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
+        self.cuda = self.device.type == "cuda"
+        self.bytes_sent = {}           # collective name -> bytes this rank put on the wire (excluding its own share)
 
     def _t(self, a):
-        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        if isinstance(a, np.ndarray):
+            return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        return a.contiguous()
 
-    def all_to_all(self, arr, send_counts):
-        """arr: 1-D numpy array laid out by destination rank; send_counts[G].  Returns (recv, recv_counts)."""
-        send_counts = np.asarray(send_counts, np.int64)
+    def _back(self, t, like):
+        return t.cpu().numpy() if isinstance(like, np.ndarray) else t
+
+    def sync(self):
+        if self.cuda:
+            self.torch.cuda.current_stream(self.device).synchronize()
+
+    def exchange_counts(self, counts):
+        """counts: int64 [G, k] (row g goes to rank g) -> int64 [G, k] (row g came from rank g), numpy."""
+        counts = np.ascontiguousarray(counts, np.int64)
         if self.world == 1:
-            return arr.copy(), send_counts.copy()
-        rc = self.torch.empty(self.world, dtype=self.torch.int64, device=self.device)
-        self.dist.all_to_all_single(rc, self._t(send_counts), group=self.group)
-        recv_counts = rc.cpu().numpy()
-        view = np.ascontiguousarray(arr)
-        k = view.dtype.itemsize                                   # exchanged as raw bytes
-        t_in = self._t(view.view(np.uint8).reshape(-1))
-        out = self.torch.empty(int(recv_counts.sum()) * k, dtype=self.torch.uint8, device=self.device)
-        self.dist.all_to_all_single(out, t_in, [int(c) * k for c in recv_counts], [int(c) * k for c in send_counts],
-                                    group=self.group)
-        return out.cpu().numpy().view(view.dtype), recv_counts
+            return counts.copy()
+        t = self._t(counts.reshape(-1))
+        out = self.torch.empty_like(t)
+        self.dist.all_to_all_single(out, t, group=self.group)
+        return out.cpu().numpy().reshape(counts.shape)
+
+    def all_to_all(self, x, send, recv, name=None):
+        """x: 1-D or [n, k] buffer laid out by destination rank; send / recv: rows per rank."""
+        send, recv = [int(v) for v in send], [int(v) for v in recv]
+        if name is not None:
+            row = (x.dtype.itemsize if isinstance(x, np.ndarray) else x.element_size()) * \
+                (int(np.prod(x.shape[1:])) if x.ndim > 1 else 1)
+            self.bytes_sent[name] = self.bytes_sent.get(name, 0) + row * (sum(send) - send[self.rank])
+        if self.world == 1:
+            return x.copy() if isinstance(x, np.ndarray) else x.clone()
+        t = self._t(x)
+        out = self.torch.empty((sum(recv),) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+        self.dist.all_to_all_single(out, t, recv, send, group=self.group)
+        return self._back(out, x)
 
     def all_reduce_sum(self, arr):
+        arr = np.ascontiguousarray(arr, np.int64)
         if self.world == 1:
             return arr.copy()
         t = self._t(arr)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t.cpu().numpy()
 
-    def all_gather_v(self, arr):
-        """Concatenation of every rank's 1-D array (rank order) and the per-rank counts."""
-        if self.world == 1:
-            return arr.copy(), np.array([len(arr)], np.int64)
-        n = self.torch.tensor([len(arr)], dtype=self.torch.int64, device=self.device)
-        ns = [self.torch.empty_like(n) for _ in range(self.world)]
-        self.dist.all_gather(ns, n, group=self.group)
-        counts = np.array([int(x.item()) for x in ns], np.int64)
-        m = int(counts.max()) if len(counts) else 0
-        pad = np.zeros(m, arr.dtype)
-        pad[:len(arr)] = arr
-        t = self._t(pad)
-        outs = [self.torch.empty_like(t) for _ in range(self.world)]
-        self.dist.all_gather(outs, t, group=self.group)
-        parts = [o.cpu().numpy()[:c] for o, c in zip(outs, counts)]
-        return np.concatenate(parts) if parts else arr.copy(), counts
-
 
 # ---- the product engine --------------------------------------------------------------------------------------
 class GpuEngine:
-    """The five operations the sharded driver needs, on libitsx_b200 (no CPU path)."""
+    """The block side (`local`) and the owner side (`owner`) of a sharded run on libitsx_b200: two contexts on the
+    rank's GPU, every exchange buffer a torch CUDA tensor handed to the C ABI by device pointer (no CPU path)."""
 
-    def __init__(self, ctx, params=None):
-        self.ctx, self.params = ctx, params
+    def __init__(self, local, owner, params=None):
+        import ctypes as C
+        import torch
+        from ._lib import lib
+        self.C, self.torch, self.L = C, torch, lib()
+        self.local, self.owner, self.params = local, owner, params
+        self.dev = torch.device("cuda", int(local.device))
+        self.n = self.nu = self.m = 0
+        self.resident = self.resident_qual = False
 
-    def derep(self, seq, off):
-        rep, strand, nu = self.ctx.derep(seq, off)
-        first, _ = self.ctx.derep_clusters(nu) if nu else (np.zeros(0, np.int32), None)
-        keys = self.ctx.derep_unique_keys(nu)
-        return rep, strand, first, keys
+    def _p(self, t):
+        if t is None:
+            return None
+        if isinstance(t, np.ndarray):
+            return t.ctypes.data_as(self.C.c_void_p)
+        return self.C.c_void_p(t.data_ptr()) if t.numel() else None
 
-    def search_stage1(self, seq, off):
-        self.ctx.search_seqs_stage1(seq, off, self.params)
-        return self.ctx.nreported().astype(np.int64)
+    # -- block side --
+    def upload(self, seq, off, qual=None):
+        """Make the block resident ahead of the timed region (bench `value`); run_sharded then skips the upload."""
+        self.local.reads_upload(seq, off)
+        if qual is not None:
+            self.local.quals_upload(qual)
+        self.n = len(off) - 1
+        self.resident = True
+        self.resident_qual = qual is not None
 
-    def search_stage2(self, nreported_global, nseq):
-        self.ctx.nreported_set(nreported_global.astype(np.int32))
-        self.ctx.search_stage2()
-        p = self.ctx.positions(nseq)
-        return p["start"], p["stop"], p["tlen"]
+    def local_derep(self, seq, off):
+        if not self.resident:
+            self.local.reads_upload(seq, off)
+            self.n = len(off) - 1
+        self.nu = self.local.derep_resident(build_search_set=False)
+        return self.nu
 
-    def trim_bounds(self, uid, n_unique, start, stop, tlen, off, mode=0):
-        self.ctx.trim_set_map(uid, n_unique)
-        self.ctx.positions_set(start, stop, tlen)
-        keep, lo, hi, nk = self.ctx.trim_bounds(len(uid), mode=mode, off_other=off)
+    def plan(self, G):
+        rc, bc = np.zeros(G, np.int64), np.zeros(G, np.int64)
+        self.local._chk(self.L.itsx_shard_plan(self.local._h, G, self._p(rc), self._p(bc)))
+        return rc, bc
+
+    def pack(self, gidx0, nbytes):
+        t = self.torch
+        rec = t.empty(self.nu, dtype=t.int64, device=self.dev)
+        bases = t.empty(int(nbytes), dtype=t.uint8, device=self.dev)
+        self.local._chk(self.L.itsx_shard_pack(self.local._h, int(gidx0), self._p(rec), self._p(bases)))
+        return rec, bases
+
+    # -- owner side --
+    def owner_derep(self, rec, bases):
+        n_own = self.C.c_int64()
+        self.m = int(rec.shape[0])
+        self.owner._chk(self.L.itsx_shard_owner_derep(self.owner._h, self._p(rec), self.m, self._p(bases),
+                                                      int(bases.shape[0]), self.C.byref(n_own)))
+        return int(n_own.value)
+
+    def search_stage1(self):
+        self.owner.search_stage1(self.params)
+        return self.owner.nreported().astype(np.int64)
+
+    def search_stage2(self, nrep_global):
+        self.owner.nreported_set(nrep_global.astype(np.int32))
+        self.owner.search_stage2()
+
+    def answers(self):
+        t = self.torch
+        ans = t.empty((self.m, 4), dtype=t.int32, device=self.dev)
+        self.owner._chk(self.L.itsx_shard_answers(self.owner._h, self.m, self._p(ans)))
+        return ans
+
+    # -- block side again --
+    def apply(self, ans, want_rep=True):
+        rep = np.empty(self.n, np.int64) if want_rep else None
+        strand = np.empty(self.n, np.uint8) if want_rep else None
+        self.local._chk(self.L.itsx_shard_apply(self.local._h, self._p(ans), self.nu, self._p(rep), self._p(strand)))
+        return rep, strand
+
+    def trim_bounds(self, mode=0):
+        keep, lo, hi, nk = self.local.trim_bounds(self.n, mode=mode)
         return keep, lo, hi
+
+    def trim_gather(self, qual=None, mode=0):
+        """kept_index, out_off, out_seq, out_qual of the block (qualities resident or given)."""
+        return self.local.trim_gather(self.n, mode=mode, qual=qual, resident_qual=self.resident_qual and qual is None)
 
 
 # ---- helpers ---------------------------------------------------------------------------------------------------
@@ -117,283 +189,62 @@ def block_range(n, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def _gather_segments(seq, off, idx):
-    """Bases of reads ``idx`` packed back to back -> (bytes, lengths); multi-threaded memcpy in libitsx_b200
-    (itsx_bytes_gather), host side only."""
-    from .fastq import _gather
-    idx = np.asarray(idx, dtype=np.int64)
-    lens = (off[1:] - off[:-1])[idx]
-    if len(idx) == 0:
-        return np.zeros(0, np.uint8), lens
-    out, _ = _gather(seq, off[idx], lens)
-    return out, lens
-
-
 # ---- the sharded hot path --------------------------------------------------------------------------------------
-def run_sharded(engine, comm, seq, off, first_global_index):
+def run_sharded(engine, comm, seq, off, first_global_index, phases=None, want_rep=True, gather=False, qual=None):
     """Hot path for this rank's block of one sample.
 
-    seq/off: this rank's reads (ASCII back to back, int64 offsets); first_global_index: global index of its
-    first read.  Returns dict(rep=global representative index per local read (int64), strand, keep, lo, hi,
-    n_unique_global, n_owned).  Results are identical to the single-GPU path on the concatenated input.
+    seq/off: this rank's reads (ASCII back to back, int64 offsets; ignored by an engine whose block is already
+    resident); first_global_index: global index of its first read.  Returns dict(rep=global representative index per
+    local read (int64), strand, keep, lo, hi, n_unique_global, n_owned, nreported[, kept_index, out_off, out_seq,
+    out_qual with gather=True]).  Results are identical to the single-GPU path on the concatenated input.
+    phases: dict that receives the seconds spent per phase (PHASES), accumulated.
     """
-    G, me = comm.world, comm.rank
-    off = np.ascontiguousarray(off, np.int64)
-    seq = np.ascontiguousarray(seq, np.uint8)
-    n = len(off) - 1
-
-    # 1a. local exact derep
-    rep_l, strand_l, first_l, keys = engine.derep(seq, off)
-    nu_l = len(first_l)
-    uid_l = np.searchsorted(first_l, rep_l).astype(np.int64) if nu_l else np.zeros(0, np.int64)
-    # 1b. local uniques -> owner = key % G, grouped by destination, ascending global index inside a group
-    owner = (keys % np.uint64(G)).astype(np.int64) if nu_l else np.zeros(0, np.int64)
-    order = np.argsort(owner, kind="stable")                     # first_l ascending => gidx ascending per group
-    send_counts = np.bincount(owner, minlength=G).astype(np.int64)
-    gidx_send = (first_l[order].astype(np.int64) + first_global_index)
-    bases, lens = _gather_segments(seq, off, first_l[order])
-    byte_counts = np.zeros(G, np.int64)
-    np.add.at(byte_counts, owner[order], lens)
-    gidx_recv, recv_counts = comm.all_to_all(gidx_send, send_counts)
-    lens_recv, _ = comm.all_to_all(lens.astype(np.int64), send_counts)
-    bases_recv, _ = comm.all_to_all(bases, byte_counts)
-    # 1c. owner: exact derep of the received uniques in global-index order (first occurrence = smallest index)
-    m = len(gidx_recv)
-    o_in = np.zeros(m + 1, np.int64)
-    np.cumsum(lens_recv, out=o_in[1:])
-    by_g = np.argsort(gidx_recv, kind="stable")
-    bases_sorted, _ = _gather_segments(bases_recv, o_in, by_g)
-    o_sorted = np.zeros(m + 1, np.int64)
-    np.cumsum(lens_recv[by_g], out=o_sorted[1:])
-    rep_o, strand_o, first_o, _ = engine.derep(bases_sorted, o_sorted)
-    g_sorted = gidx_recv[by_g]
-    rep_g_sorted = g_sorted[rep_o] if m else np.zeros(0, np.int64)
-    # back to arrival order, then home through the inverse all-to-all
-    rep_g_arrival = np.empty(m, np.int64)
-    rep_g_arrival[by_g] = rep_g_sorted
-    strand_arrival = np.empty(m, np.int64)
-    strand_arrival[by_g] = strand_o.astype(np.int64) if m else np.zeros(0, np.int64)
-    rep_back, _ = comm.all_to_all(rep_g_arrival, recv_counts)
-    strand_back, _ = comm.all_to_all(strand_arrival, recv_counts)
-    rep_of_unique = np.empty(nu_l, np.int64)
-    rep_of_unique[order] = rep_back
-    strand_of_unique = np.empty(nu_l, np.int64)
-    strand_of_unique[order] = strand_back
-    rep_global = rep_of_unique[uid_l] if n else np.zeros(0, np.int64)
-    strand = (strand_l.astype(np.int64) ^ strand_of_unique[uid_l]).astype(np.uint8) if n else np.zeros(0, np.uint8)
-
-    # 2. the owner searches the classes it owns; domZ is global
-    own_bases, own_lens = _gather_segments(bases_sorted, o_sorted, first_o)
-    own_off = np.zeros(len(first_o) + 1, np.int64)
-    np.cumsum(own_lens, out=own_off[1:])
-    own_gidx = g_sorted[first_o] if len(first_o) else np.zeros(0, np.int64)
-    nrep_local = engine.search_stage1(own_bases, own_off)
-    nrep_global = comm.all_reduce_sum(nrep_local)
-    start_o, stop_o, tlen_o = engine.search_stage2(nrep_global, len(first_o))
-
-    # 3. all-gather the class table, trim the local block
-    table = np.stack([own_gidx, start_o.astype(np.int64), stop_o.astype(np.int64), tlen_o.astype(np.int64)],
-                     axis=1).reshape(-1) if len(first_o) else np.zeros(0, np.int64)
-    flat, _ = comm.all_gather_v(table)
-    tab = flat.reshape(-1, 4)
-    tab = tab[np.argsort(tab[:, 0], kind="stable")]
-    uid_g = np.searchsorted(tab[:, 0], rep_global).astype(np.int32) if n else np.zeros(0, np.int32)
-    keep, lo, hi = engine.trim_bounds(uid_g, len(tab), tab[:, 1].astype(np.int32), tab[:, 2].astype(np.int32),
-                                      tab[:, 3].astype(np.int32), off)
-    return dict(rep=rep_global, strand=strand, keep=keep, lo=lo, hi=hi, n_unique_global=len(tab),
-                n_owned=len(first_o), nreported=nrep_global)
-
-
-# ---- the sharded hot path, device resident -----------------------------------------------------------------------
-def _umod(keys_i64, G):
-    """(uint64 key) % G on an int64 tensor that holds the key's bit pattern (torch has no uint64 arithmetic)."""
-    hi = (keys_i64 >> 32) & 0xFFFFFFFF
-    lo = keys_i64 & 0xFFFFFFFF
-    return ((hi % G) * ((1 << 32) % G) + lo % G) % G
-
-
-def _gather_segments_dev(torch, src, starts, lens):
-    """src[starts[i] : starts[i] + lens[i]] packed back to back, on the device."""
-    total = int(lens.sum().item()) if lens.numel() else 0
-    out_off = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=src.device)
-    if lens.numel():
-        torch.cumsum(lens, 0, out=out_off[1:])
-    if total == 0:
-        return torch.zeros(0, dtype=src.dtype, device=src.device), out_off
-    delta = torch.repeat_interleave(starts - out_off[:-1], lens)
-    idx = delta + torch.arange(total, dtype=torch.int64, device=src.device)
-    return src[idx], out_off
-
-
-class DeviceComm:
-    """Variable-size exchanges on device tensors (NCCL over NVLink); only the split sizes visit the host."""
-
-    def __init__(self, torch, dist, group, device):
-        self.torch, self.dist, self.group, self.device = torch, dist, group, device
-        self.on = dist.is_available() and dist.is_initialized()
-        self.world = dist.get_world_size(group) if self.on else 1
-        self.rank = dist.get_rank(group) if self.on else 0
-
-    def counts(self, send_counts):
-        """send_counts: int64 device tensor [G] -> recv_counts (python lists of both)."""
-        s = [int(x) for x in send_counts.tolist()]
-        if self.world == 1:
-            return s, list(s)
-        rc = self.torch.empty_like(send_counts)
-        self.dist.all_to_all_single(rc, send_counts.contiguous(), group=self.group)
-        return s, [int(x) for x in rc.tolist()]
-
-    def all_to_all(self, t, send, recv):
-        if self.world == 1:
-            return t.clone()
-        out = self.torch.empty(sum(recv), dtype=t.dtype, device=self.device)
-        self.dist.all_to_all_single(out, t.contiguous(), recv, send, group=self.group)
-        return out
-
-    def all_reduce_sum(self, t):
-        if self.world > 1:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
-        return t
-
-    def all_gather_rows(self, t):
-        """t: [n, k] int64 -> concatenation over ranks (rank order)."""
-        if self.world == 1:
-            return t
-        torch = self.torch
-        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=self.device)
-        ns = torch.empty(self.world, dtype=torch.int64, device=self.device)
-        self.dist.all_gather_into_tensor(ns, n, group=self.group)
-        counts = [int(x) for x in ns.tolist()]
-        m = max(counts) if counts else 0
-        pad = torch.zeros((m, t.shape[1]), dtype=t.dtype, device=self.device)
-        pad[:t.shape[0]] = t
-        out = torch.empty((self.world * m, t.shape[1]), dtype=t.dtype, device=self.device)
-        self.dist.all_gather_into_tensor(out, pad, group=self.group)
-        return torch.cat([out[r * m:r * m + c] for r, c in enumerate(counts)])
-
-
-def run_sharded_device(ctx, seq, off, first_global_index, params=None, group=None):
-    """Same contract and results as run_sharded(GpuEngine(ctx), ...), but every intermediate stays in HBM: the C ABI is
-    called with device pointers (torch tensors), the regrouping is torch index arithmetic on the GPU, and the three
-    exchanges are NCCL collectives on device buffers.  Host traffic: the rank's block of reads in, keep/lo/hi/rep
-    out, and the split sizes of the collectives."""
-    import ctypes as C
-    import torch
-    import torch.distributed as dist
-    from ._lib import lib, SearchParams  # noqa: F401
-    L, h = lib(), ctx._h
-    dev = torch.device("cuda", int(ctx.device))
-    comm = DeviceComm(torch, dist, group, dev)
     G = comm.world
-    i64, i32, u8 = torch.int64, torch.int32, torch.uint8
-    off = np.ascontiguousarray(off, np.int64)
-    seq = np.ascontiguousarray(seq, np.uint8)
-    n = len(off) - 1
-    prm = C.byref(params) if params is not None else None
+    t_last = [time.perf_counter()]
 
-    def P(t):
-        return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else None
+    def lap(name):
+        comm.sync()
+        now = time.perf_counter()
+        if phases is not None:
+            phases[name] = phases.get(name, 0.0) + (now - t_last[0])
+        t_last[0] = now
 
-    def fence():
-        """torch's stream -> the library's stream: the library copies from these tensors on its own stream (and
-        synchronises it before it returns, which orders the other direction)."""
-        torch.cuda.current_stream(dev).synchronize()
-
-    def derep(seq_d, off_d, cnt):
-        rep = torch.empty(cnt, dtype=i32, device=dev)
-        strand = torch.empty(cnt, dtype=u8, device=dev)
-        nu = C.c_int64()
-        if cnt == 0:
-            off_d = torch.zeros(1, dtype=i64, device=dev)
-        fence()
-        ctx._chk(L.itsx_derep(h, P(seq_d), C.c_void_p(off_d.data_ptr()), cnt, P(rep), P(strand), C.byref(nu)))
-        first = torch.empty(int(nu.value), dtype=i32, device=dev)
-        if nu.value:
-            ctx._chk(L.itsx_derep_clusters(h, P(first), None))
-        return rep, strand, first
-
-    # 1a. local exact derep
-    seq_d = torch.from_numpy(seq).to(dev)
-    off_d = torch.from_numpy(off).to(dev)
-    rep_l, strand_l, first_l = derep(seq_d, off_d, n)
-    nu_l = first_l.numel()
-    keys = torch.empty(nu_l, dtype=i64, device=dev)
-    if nu_l:
-        ctx._chk(L.itsx_derep_unique_keys(h, P(keys)))
-    first_l64 = first_l.to(i64)
-    uid_l = torch.searchsorted(first_l64, rep_l.to(i64)) if nu_l else torch.zeros(0, dtype=i64, device=dev)
-    # 1b. local uniques -> owner = key % G, grouped by destination, ascending global index inside a group
-    owner = _umod(keys, G) if nu_l else torch.zeros(0, dtype=i64, device=dev)
-    order = torch.argsort(owner, stable=True)
-    send_counts = torch.bincount(owner, minlength=G).to(i64)
-    first_o = first_l64[order]
-    gidx_send = first_o + int(first_global_index)
-    lens_all = off_d[1:] - off_d[:-1]
-    lens = lens_all[first_o]
-    bases, _ = _gather_segments_dev(torch, seq_d, off_d[first_o], lens)
-    byte_counts = torch.zeros(G, dtype=i64, device=dev)
-    if nu_l:
-        byte_counts.index_add_(0, owner[order], lens)
-    sc, rc = comm.counts(send_counts)
-    bsc, brc = comm.counts(byte_counts)
-    gidx_recv = comm.all_to_all(gidx_send, sc, rc)
-    lens_recv = comm.all_to_all(lens, sc, rc)
-    bases_recv = comm.all_to_all(bases, bsc, brc)
-    # 1c. owner: exact derep of the received uniques in global-index order (first occurrence = smallest index)
-    m = gidx_recv.numel()
-    o_in = torch.zeros(m + 1, dtype=i64, device=dev)
-    if m:
-        torch.cumsum(lens_recv, 0, out=o_in[1:])
-    by_g = torch.argsort(gidx_recv, stable=True)
-    bases_sorted, o_sorted = _gather_segments_dev(torch, bases_recv, o_in[:-1][by_g], lens_recv[by_g])
-    rep_o, strand_o, first_own = derep(bases_sorted, o_sorted, m)     # the owned classes are now ctx's search set
-    g_sorted = gidx_recv[by_g]
-    rep_g_arrival = torch.empty(m, dtype=i64, device=dev)
-    strand_arrival = torch.empty(m, dtype=i64, device=dev)
-    if m:
-        rep_g_arrival[by_g] = g_sorted[rep_o.to(i64)]
-        strand_arrival[by_g] = strand_o.to(i64)
-    rep_back = comm.all_to_all(rep_g_arrival, rc, sc)
-    strand_back = comm.all_to_all(strand_arrival, rc, sc)
-    rep_of_unique = torch.empty(nu_l, dtype=i64, device=dev)
-    strand_of_unique = torch.empty(nu_l, dtype=i64, device=dev)
-    if nu_l:
-        rep_of_unique[order] = rep_back
-        strand_of_unique[order] = strand_back
-    rep_global = rep_of_unique[uid_l] if n else torch.zeros(0, dtype=i64, device=dev)
-    strand = (strand_l.to(i64) ^ strand_of_unique[uid_l]).to(u8) if n else torch.zeros(0, dtype=u8, device=dev)
-
-    # 2. the owner searches the classes it owns (resident since the second derep); domZ is global
-    n_own = first_own.numel()
-    ctx._chk(L.itsx_search_stage1(h, prm))
-    nrep = torch.from_numpy(ctx.nreported().astype(np.int64)).to(dev)
-    nrep = comm.all_reduce_sum(nrep)
-    nrep_h = nrep.cpu().numpy()
-    ctx.nreported_set(nrep_h.astype(np.int32))
-    ctx._chk(L.itsx_search_stage2(h))
-    start = torch.full((n_own,), -1, dtype=i32, device=dev)
-    stop = torch.full((n_own,), -1, dtype=i32, device=dev)
-    tlen = torch.full((n_own,), -1, dtype=i32, device=dev)
-    if n_own:
-        ctx._chk(L.itsx_positions(h, P(start), P(stop), P(tlen), None, None, None, None, None, None))
-    own_gidx = g_sorted[first_own.to(i64)] if n_own else torch.zeros(0, dtype=i64, device=dev)
-
-    # 3. all-gather the class table, trim the local block
-    table = torch.stack([own_gidx, start.to(i64), stop.to(i64), tlen.to(i64)], dim=1) if n_own else \
-        torch.zeros((0, 4), dtype=i64, device=dev)
-    tab = comm.all_gather_rows(table)
-    tab = tab[torch.argsort(tab[:, 0], stable=True)]
-    nt = tab.shape[0]
-    uid_g = torch.searchsorted(tab[:, 0].contiguous(), rep_global).to(i32) if n else torch.zeros(0, dtype=i32, device=dev)
-    keep = torch.empty(n, dtype=u8, device=dev)
-    lo = torch.empty(n, dtype=i32, device=dev)
-    hi = torch.empty(n, dtype=i32, device=dev)
-    if n:
-        t1, t2, t3 = (tab[:, k].to(i32).contiguous() for k in (1, 2, 3))
-        fence()
-        ctx._chk(L.itsx_trim_set_map(h, P(uid_g), n, nt))
-        ctx._chk(L.itsx_positions_set(h, P(t1), P(t2), P(t3), nt))
-        nk = C.c_int64()
-        ctx._chk(L.itsx_trim_bounds(h, 0, C.c_void_p(off_d.data_ptr()), n, P(keep), P(lo), P(hi), C.byref(nk)))
-    return dict(rep=rep_global.cpu().numpy(), strand=strand.cpu().numpy(), keep=keep.cpu().numpy(), lo=lo.cpu().numpy(),
-                hi=hi.cpu().numpy(), n_unique_global=int(nt), n_owned=int(n_own), nreported=nrep_h)
+    # 1a. exact derep of the block
+    nu_l = engine.local_derep(seq, off)
+    lap("local_derep")
+    # 1b. local uniques -> owner = key % G: bucket, record stream + bases in bucket order
+    rec_counts, byte_counts = engine.plan(G)
+    rec, bases = engine.pack(first_global_index, int(byte_counts.sum()))
+    lap("plan_pack")
+    got = comm.exchange_counts(np.stack([rec_counts, byte_counts], axis=1))
+    rrc, rbc = got[:, 0], got[:, 1]
+    rec_in = comm.all_to_all(rec, rec_counts, rrc, name="records")
+    bases_in = comm.all_to_all(bases, byte_counts, rbc, name="bases")
+    lap("exchange")
+    # 1c. owner: exact derep of the received uniques; arrival order = ascending global read index
+    n_own = engine.owner_derep(rec_in, bases_in)
+    lap("owner_derep")
+    # 2. the owner searches the classes it owns; domZ is global (and so is the class count)
+    nrep_local = engine.search_stage1()
+    lap("search_stage1")
+    red = comm.all_reduce_sum(np.concatenate([nrep_local, [n_own]]).astype(np.int64))
+    nrep_global, n_unique_global = red[:-1], int(red[-1])
+    lap("domz_allreduce")
+    engine.search_stage2(nrep_global)
+    lap("search_stage2")
+    # 3. answers home through the inverse all-to-all; trim the block where it lies
+    ans = engine.answers()
+    lap("answers")
+    ans_back = comm.all_to_all(ans, rrc, rec_counts, name="answers")
+    lap("answers_exchange")
+    rep_global, strand = engine.apply(ans_back, want_rep=want_rep)
+    out = dict(rep=rep_global, strand=strand, n_unique_global=n_unique_global, n_owned=int(n_own),
+               nreported=nrep_global, n_local_unique=int(nu_l))
+    if gather:
+        ki, oo, os_, oq = engine.trim_gather(qual=qual)
+        out.update(kept_index=ki, out_off=oo, out_seq=os_, out_qual=oq)
+    else:
+        keep, lo, hi = engine.trim_bounds()
+        out.update(keep=keep, lo=lo, hi=hi)
+    lap("apply_trim")
+    return out

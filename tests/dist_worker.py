@@ -1,5 +1,6 @@
 """Worker for the world_size-2 gloo test of itsxpress_b200.distributed.run_sharded (CPU, no GPU):
-the orchestration (hash-partitioned derep exchange, domZ all-reduce, position all-gather) is the product's;
+the orchestration (hash-partitioned derep exchange, domZ all-reduce, answers through the inverse exchange) is the
+product's;
 the per-rank compute engine here is the CPU ORACLE -- test infrastructure standing in for libitsx_b200."""
 import hashlib
 import os
@@ -20,33 +21,93 @@ def canon_key(s):
 
 
 class OracleEngine:
+    """numpy stand-in for itsxpress_b200.distributed.GpuEngine (same methods, same buffer contents)."""
+
     def __init__(self, O, db, side):
         self.O, self.db, self.side = O, db, side
 
-    def derep(self, seq, off):
-        rep, strand, nu = self.O.derep(seq, off)
-        first = np.flatnonzero(rep == np.arange(len(rep))).astype(np.int32)
-        keys = np.array([canon_key(seq[off[i]:off[i + 1]].tobytes()) for i in first], np.uint64)
-        return rep, strand, first, keys
+    # -- block side --
+    def local_derep(self, seq, off):
+        self.seq, self.off = np.ascontiguousarray(seq, np.uint8), np.ascontiguousarray(off, np.int64)
+        self.rep_l, self.strand_l, nu = self.O.derep(self.seq, self.off)
+        self.first = np.flatnonzero(self.rep_l == np.arange(len(self.rep_l))).astype(np.int64)
+        self.uid = np.searchsorted(self.first, self.rep_l).astype(np.int64)
+        self.keys = np.array([canon_key(self.seq[self.off[i]:self.off[i + 1]].tobytes()) for i in self.first], np.uint64)
+        return len(self.first)
 
-    def search_stage1(self, seq, off):
+    def plan(self, G):
+        owner = (self.keys % np.uint64(G)).astype(np.int64) if len(self.keys) else np.zeros(0, np.int64)
+        self.order = np.argsort(owner, kind="stable")
+        lens = (self.off[1:] - self.off[:-1])[self.first]
+        bc = np.zeros(G, np.int64)
+        np.add.at(bc, owner, lens)
+        return np.bincount(owner, minlength=G).astype(np.int64), bc
+
+    def pack(self, gidx0, nbytes):
+        r = self.first[self.order]
+        lens = (self.off[1:] - self.off[:-1])[r]
+        rec = ((r + gidx0).astype(np.uint64) | (lens.astype(np.uint64) << np.uint64(32))).view(np.int64)
+        bases = np.concatenate([self.seq[self.off[i]:self.off[i + 1]] for i in r]) if len(r) else np.zeros(0, np.uint8)
+        assert len(bases) == nbytes
+        return rec, bases
+
+    # -- owner side --
+    def owner_derep(self, rec, bases):
+        rec = rec.view(np.uint64)
+        self.gidx = (rec & np.uint64(0xffffffff)).astype(np.int64)
+        assert np.all(np.diff(self.gidx) > 0)        # arrival order = ascending global read index
+        lens = (rec >> np.uint64(32)).astype(np.int64)
+        self.o_off = np.zeros(len(rec) + 1, np.int64)
+        np.cumsum(lens, out=self.o_off[1:])
+        self.o_seq = np.ascontiguousarray(bases, np.uint8)
+        self.o_rep, self.o_strand, nu = self.O.derep(self.o_seq, self.o_off)
+        self.o_first = np.flatnonzero(self.o_rep == np.arange(len(self.o_rep))).astype(np.int64)
+        self.o_uid = np.searchsorted(self.o_first, self.o_rep)
+        return len(self.o_first)
+
+    def search_stage1(self):
         prm = self.O.default_params()
         prm.domE = 1e300                       # keep every domain of a reported hit; domE is applied in stage 2
-        self.seqlen = np.diff(off).astype(np.int32)
-        if len(off) > 1:
-            self.rows, nrep, _ = self.db.search(self.O.digitize(seq.tobytes()), off, prm)
+        parts = [self.o_seq[self.o_off[i]:self.o_off[i + 1]] for i in self.o_first]
+        uoff = np.zeros(len(parts) + 1, np.int64)
+        uoff[1:] = np.cumsum([len(p) for p in parts])
+        self.seqlen = np.diff(uoff).astype(np.int32)
+        if len(parts):
+            self.rows, nrep, _ = self.db.search(self.O.digitize(np.concatenate(parts).tobytes()), uoff, prm)
         else:
             self.rows, nrep = np.zeros(0, self.O.DOM_DTYPE), np.zeros(self.db.n, np.int32)
         return nrep.astype(np.int64)
 
-    def search_stage2(self, nrep_global, nseq):
+    def search_stage2(self, nrep_global):
         r = self.rows
         ok = np.exp(r["lnP"]) * nrep_global[r["prof"]] <= 10.0
-        pos = self.O.itspos(r[ok], self.side, self.seqlen)
-        return pos["start"], pos["stop"], pos["tlen"]
+        self.pos = self.O.itspos(r[ok], self.side, self.seqlen)
 
-    def trim_bounds(self, uid, n_unique, start, stop, tlen, off, mode=0):
-        return self.O.trim_bounds(off, uid, start, stop, tlen, mode=mode)
+    def answers(self):
+        m = len(self.o_rep)
+        ans = np.full((m, 4), -1, np.int32)
+        if m:
+            g = self.gidx[self.o_rep].astype(np.uint32) | (self.o_strand.astype(np.uint32) << np.uint32(31))
+            ans[:, 0] = g.view(np.int32)
+            for k, name in ((1, "start"), (2, "stop"), (3, "tlen")):
+                ans[:, k] = self.pos[name][self.o_uid]
+        return ans
+
+    # -- block side again --
+    def apply(self, ans, want_rep=True):
+        nu = len(self.first)
+        tab = np.full((nu, 4), -1, np.int32)
+        tab[self.order] = ans
+        self.tab = tab
+        g = tab[:, 0].view(np.uint32)[self.uid] if len(self.uid) else np.zeros(0, np.uint32)
+        rep = (g & np.uint32(0x7fffffff)).astype(np.int64)
+        strand = ((g >> np.uint32(31)).astype(np.uint8) ^ self.strand_l.astype(np.uint8)) & 1
+        return rep, strand
+
+    def trim_bounds(self, mode=0):
+        t = self.tab
+        return self.O.trim_bounds(self.off, self.uid.astype(np.int32), t[:, 1].copy(), t[:, 2].copy(), t[:, 3].copy(),
+                                  mode=mode)
 
 
 def dataset():

@@ -63,30 +63,6 @@ def test_block_range_partitions():
             assert max(b - a for a, b in blocks) - min(b - a for a, b in blocks) <= 1
 
 
-def test_device_driver_index_helpers_on_cpu_tensors():
-    """The index arithmetic of run_sharded_device is plain torch: checked here on CPU tensors against numpy."""
-    import numpy as np
-    import torch
-    from itsxpress_b200.distributed import _gather_segments_dev, _umod
-    rng = np.random.default_rng(3)
-    keys = rng.integers(0, 2 ** 64, 5000, dtype=np.uint64)
-    keys[:4] = [0, 2 ** 64 - 1, 2 ** 63, 2 ** 32]
-    for G in (1, 2, 3, 7, 8):
-        got = _umod(torch.from_numpy(keys.view(np.int64)), G).numpy()
-        assert np.array_equal(got, (keys % np.uint64(G)).astype(np.int64))
-    src = rng.integers(0, 256, 10000, dtype=np.uint8)
-    starts = rng.integers(0, 9000, 300)
-    lens = rng.integers(0, 1000, 300)
-    lens[::17] = 0
-    out, off = _gather_segments_dev(torch, torch.from_numpy(src), torch.from_numpy(starts), torch.from_numpy(lens))
-    want = np.concatenate([src[s:s + l] for s, l in zip(starts, lens)])
-    assert np.array_equal(out.numpy(), want)
-    assert np.array_equal(off.numpy(), np.concatenate([[0], np.cumsum(lens)]))
-    out, off = _gather_segments_dev(torch, torch.from_numpy(src), torch.zeros(0, dtype=torch.int64),
-                                    torch.zeros(0, dtype=torch.int64))
-    assert out.numel() == 0 and off.tolist() == [0]
-
-
 @pytest.mark.parametrize("world", [1, 2, 3])
 def test_q2_samples_dealt_to_ranks(tmp_path, world):
     """q2_itsxpress.main_sharded over gloo: every sample of a 7-sample paired artifact is processed by exactly one

@@ -275,50 +275,161 @@ def test_whole_path_fixture(gpu_ctx, oracle, fixture_reads):
     assert np.array_equal(out["lo"], olo) and np.array_equal(out["hi"], ohi)
 
 
-def test_run_sharded_single_rank_equals_itsx_run(gpu_ctx, fixture_reads):
-    """distributed.run_sharded with the GPU engine on one rank == itsx_run on the same reads."""
+@pytest.fixture(scope="module")
+def owner_ctx():
+    """second context on the same GPU: the owner side of a sharded run"""
+    from itsxpress_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def test_run_sharded_single_rank_equals_itsx_run(gpu_ctx, owner_ctx, fixture_reads):
+    """distributed.run_sharded with the GPU engine (csrc/shard.cu through device pointers) on one rank == itsx_run on
+    the same reads: representatives, strands, bounds, and the re-expanded slices == itsx_run_trim."""
     from itsxpress_b200.distributed import Comm, GpuEngine, run_sharded
-    b, seq, off, _ = fixture_reads
-    paths = [os.path.join(HMM_DIR, "M.hmm")]
-    gpu_ctx.load_profiles(paths, ["3_", "4_"])
-    gpu_ctx.set_sides_by_prefix("3_", "4_")
-    want, st = gpu_ctx.run(seq, off)
-    want = {k: v.copy() for k, v in want.items()}
-    got = run_sharded(GpuEngine(gpu_ctx), Comm(), seq, off, 0)
-    assert got["n_unique_global"] == st.n_unique
-    assert np.array_equal(got["rep"], want["rep"])
-    assert np.array_equal(got["keep"], want["keep"]) and int(got["keep"].sum()) == st.n_kept
-    assert np.array_equal(got["lo"], want["lo"]) and np.array_equal(got["hi"], want["hi"])
-
-
-def test_run_sharded_device_single_rank_equals_itsx_run(gpu_ctx, fixture_reads):
-    """the device-resident sharded driver (C ABI called with device pointers, torch index arithmetic on the GPU) on one
-    rank == itsx_run == the host-orchestrated driver, including strands and the per-profile reported-hit counts."""
-    from itsxpress_b200.distributed import Comm, GpuEngine, run_sharded, run_sharded_device
-    b, seq, off, _ = fixture_reads
+    b, seq, off, qual = fixture_reads
     # make some reads reverse complements of others so that strand '-' occurs
     comp = bytes.maketrans(b"ACGTN", b"TGCAN")
     parts = [seq[off[i]:off[i + 1]].tobytes() for i in range(len(off) - 1)]
+    quals = [qual[off[i]:off[i + 1]].tobytes() for i in range(len(off) - 1)]
     parts += [p.translate(comp)[::-1] for p in parts[:20]]
+    quals += [q[::-1] for q in quals[:20]]
     seq2 = np.frombuffer(b"".join(parts), np.uint8).copy()
+    qual2 = np.frombuffer(b"".join(quals), np.uint8).copy()
     off2 = np.zeros(len(parts) + 1, np.int64)
     off2[1:] = np.cumsum([len(p) for p in parts])
     paths = [os.path.join(HMM_DIR, "M.hmm")]
-    gpu_ctx.load_profiles(paths, ["3_", "4_"])
-    gpu_ctx.set_sides_by_prefix("3_", "4_")
+    for c in (gpu_ctx, owner_ctx):
+        c.load_profiles(paths, ["3_", "4_"])
+        c.set_sides_by_prefix("3_", "4_")
     want, st = gpu_ctx.run(seq2, off2)
     want = {k: v.copy() for k, v in want.items()}
-    host = run_sharded(GpuEngine(gpu_ctx), Comm(), seq2, off2, 0)
-    got = run_sharded_device(gpu_ctx, seq2, off2, 0)
-    assert got["n_unique_global"] == st.n_unique
+    _, wstrand, _ = gpu_ctx.derep(seq2, off2)
+    wt, st2 = gpu_ctx.run_trim(seq2, qual2, off2)
+    wt = {k: v.copy() for k, v in wt.items()}
+    eng = GpuEngine(gpu_ctx, owner_ctx)
+    phases = {}
+    got = run_sharded(eng, Comm(), seq2, off2, 0, phases=phases)
+    assert got["n_unique_global"] == st.n_unique == got["n_owned"] == got["n_local_unique"]
     assert np.array_equal(got["rep"], want["rep"])
+    assert np.array_equal(got["strand"], wstrand) and got["strand"].sum() >= 20
     assert np.array_equal(got["keep"], want["keep"]) and int(got["keep"].sum()) == st.n_kept
     assert np.array_equal(got["lo"], want["lo"]) and np.array_equal(got["hi"], want["hi"])
-    assert np.array_equal(got["strand"], host["strand"]) and got["strand"].sum() >= 20
-    assert np.array_equal(got["nreported"], host["nreported"])
+    assert set(phases) == set(__import__("itsxpress_b200.distributed", fromlist=["PHASES"]).PHASES)
+    # block resident ahead of the call, re-expansion at the end
+    eng.upload(seq2, off2, qual2)
+    g2 = run_sharded(eng, Comm(), None, None, 0, want_rep=False, gather=True)
+    for k in ("kept_index", "out_off", "out_seq", "out_qual"):
+        assert np.array_equal(g2[k], wt[k]), k
+    assert len(wt["kept_index"]) == st2.n_kept == st.n_kept and st2.out_bytes == len(wt["out_seq"]) > 10000
     # an empty block is legal (more ranks than reads)
-    empty = run_sharded_device(gpu_ctx, np.zeros(0, np.uint8), np.zeros(1, np.int64), 0)
+    eng2 = GpuEngine(gpu_ctx, owner_ctx)
+    empty = run_sharded(eng2, Comm(), np.zeros(0, np.uint8), np.zeros(1, np.int64), 0)
     assert len(empty["keep"]) == 0 and empty["n_unique_global"] == 0
+
+
+def test_run_trim_equals_bounds_plus_slices(gpu_ctx, fixture_reads):
+    """itsx_run_trim (the e2e call: qualities in, trimmed records out) == itsx_run's bounds applied on the host, and
+    the resident path (reads_upload + quals_upload + run_resident + run_fetch) gives the same bytes."""
+    b, seq, off, qual = fixture_reads
+    gpu_ctx.load_profiles([os.path.join(HMM_DIR, "M.hmm")], ["3_", "4_"])
+    gpu_ctx.set_sides_by_prefix("3_", "4_")
+    want, st = gpu_ctx.run(seq, off)
+    keep, lo, hi = want["keep"].copy(), want["lo"].copy(), want["hi"].copy()
+    got, st2 = gpu_ctx.run_trim(seq, qual, off)
+    got = {k: v.copy() for k, v in got.items()}
+    ki = np.flatnonzero(keep)
+    assert np.array_equal(got["kept_index"], ki) and st2.n_kept == len(ki) == st.n_kept
+    exp_seq = np.concatenate([seq[off[i] + lo[i]:off[i] + hi[i]] for i in ki])
+    exp_qual = np.concatenate([qual[off[i] + lo[i]:off[i] + hi[i]] for i in ki])
+    assert np.array_equal(got["out_seq"], exp_seq) and np.array_equal(got["out_qual"], exp_qual)
+    assert np.array_equal(np.diff(got["out_off"]), (hi - lo)[ki]) and st2.out_bytes == len(exp_seq)
+    gpu_ctx.reads_upload(seq, off)
+    gpu_ctx.quals_upload(qual)
+    st3 = gpu_ctx.run_resident()
+    ki3, oo3, os3, oq3 = gpu_ctx.run_fetch()
+    assert st3.n_kept == len(ki) and np.array_equal(ki3, ki) and np.array_equal(os3, exp_seq) and np.array_equal(oq3, exp_qual)
+    assert np.array_equal(oo3, got["out_off"])
+
+
+def test_vector_gather_all_alignments(gpu_ctx):
+    """the 16-byte-store copy of trim / shard kernels (warp_copy) against numpy for every source and destination
+    alignment and for slice lengths around the 16- and 32-byte edges"""
+    rng = np.random.default_rng(11)
+    lens = np.concatenate([np.arange(0, 70), rng.integers(0, 400, 600)]).astype(np.int64)
+    n = len(lens)
+    rl = lens + rng.integers(0, 40, n)                 # read lengths; the slice starts at a random offset inside
+    off = np.zeros(n + 1, np.int64)
+    off[1:] = np.cumsum(rl)
+    seq = rng.integers(33, 127, int(off[-1]), dtype=np.uint8)
+    qual = rng.integers(33, 127, int(off[-1]), dtype=np.uint8)
+    start = rng.integers(0, (rl - lens) + 1)
+    stop = start + lens
+    gpu_ctx.trim_set_map(np.arange(n, dtype=np.int32), n)
+    gpu_ctx.positions_set(start.astype(np.int32), stop.astype(np.int32), rl.astype(np.int32))
+    ki, oo, os_, oq = gpu_ctx.trim_gather(n, mode=0, seq=seq, qual=qual, off=off)
+    want_k = np.flatnonzero(lens > 0)
+    assert np.array_equal(ki, want_k)
+    exp_s = np.concatenate([seq[off[i] + start[i]:off[i] + stop[i]] for i in want_k])
+    exp_q = np.concatenate([qual[off[i] + start[i]:off[i] + stop[i]] for i in want_k])
+    assert np.array_equal(os_, exp_s) and np.array_equal(oq, exp_q)
+    assert np.array_equal(np.diff(oo), lens[want_k])
+
+
+def _winners_from_multidomain(rows, side):
+    """ItsPosition restated on the oracle's rows (table order, strict > on the printed 0.1-bit score: first row wins,
+    SeqSample.py:400-429): how many selected left / right boundaries came out of a multidomain region."""
+    sd = side[rows["prof"]]
+    ok = sd >= 0
+    r = rows[ok]
+    sd = sd[ok]
+    s10 = np.rint(r["bitscore"].astype(np.float64) * 10.0).astype(np.int64)
+    order = np.lexsort((np.arange(len(r)), -s10, sd, r["seq"]))        # per (seq, side): best score, earliest row
+    key = r["seq"][order].astype(np.int64) * 2 + sd[order]
+    firsts = np.concatenate([[True], key[1:] != key[:-1]]) if len(order) else np.zeros(0, bool)
+    return int((r["is_multidomain"][order][firsts] != 0).sum())
+
+
+@pytest.mark.parametrize("config,scale,frac_mod", [("c2", 1.0, 12), ("c3s", 0.05, 1), ("c4s", 0.02, 1)])
+def test_bench_workloads_against_oracle(gpu_ctx, oracle, config, scale, frac_mod):
+    """the bench's own workloads against the oracle, whole path.  c2 = bench.cpu_sample of the FULL
+    BASELINE configs[1] sample (all reads of every 12th unique: 75 k reads, 25 k uniques, 98 profiles -- the sample the
+    cpu_baseline leg times); c3s = configs[2] shape (--region ALL --taxa All: 340 profiles of every taxon file, 380-520
+    bp); c4s = configs[3] shape (ITS2, 90 % unique, 330-441 bp, 256 profiles).  Compared: derep classes, the MSV pass
+    count, per-profile reported hits, every unique's ItsPosition fields, keep / lo / hi of every read, and how many
+    selected boundaries came out of multidomain regions."""
+    import synth
+    import bench
+    seq, off, which, cfg = synth.make_config(config, scale=scale)
+    if frac_mod > 1:
+        seq, off, _ = bench.cpu_sample(seq, off, which, frac_mod=frac_mod)
+    paths = [os.path.join(HMM_DIR, f) for f in cfg["search_files"]]
+    pre = [cfg["left_prefix"], cfg["right_prefix"]]
+    nprof = gpu_ctx.load_profiles(paths, pre)
+    side = gpu_ctx.set_sides_by_prefix(*pre)
+    got, st = gpu_ctx.run(seq, off)
+    got = {k: v.copy() for k, v in got.items()}
+    ss = gpu_ctx.search_stats()
+    pos = gpu_ctx.positions(st.n_unique)
+    nrep = gpu_ctx.nreported().copy()
+    db = oracle.ProfileDB(paths, pre)
+    assert db.n == nprof and (config != "c3s" or nprof == 340)
+    o, ost = bench.oracle_pipeline(oracle, db, side, seq, off, threads=os.cpu_count(), want_pos=True)
+    assert st.n_unique == len(o["first"]) and np.array_equal(got["rep"], o["rep"])
+    assert ss.n_past_msv == ost.n_past_msv and ss.n_pairs == ost.npairs_total
+    assert ss.n_past_bias == ost.n_past_bias and ss.n_past_fwd == ost.n_past_fwd
+    assert ss.n_multidomain_regions == ost.n_multidomain_regions
+    assert np.array_equal(nrep, o["nrep"]) and ss.n_domains_reported == len(o["rows"])
+    for k in ("start", "stop", "tlen", "left_from", "left_to", "right_from", "right_to"):
+        assert np.array_equal(pos[k], o["pos"][k]), k
+    for k in ("left_score10", "right_score10"):
+        assert np.max(np.abs(pos[k].astype(np.int64) - o["pos"][k].astype(np.int64))) <= 1, k
+    assert np.array_equal(got["keep"], o["keep"]) and int(o["keep"].sum()) == st.n_kept > 0.5 * len(o["keep"])
+    assert np.array_equal(got["lo"], o["lo"]) and np.array_equal(got["hi"], o["hi"])
+    assert ss.n_selected_multidomain == _winners_from_multidomain(o["rows"], side)
+    if config == "c2":
+        assert ss.n_multidomain_regions > 1000       # the resolver is exercised at scale
 
 
 def test_trim_set_map_drops_unmapped_reads(gpu_ctx):
