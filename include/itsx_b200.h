@@ -59,7 +59,17 @@ typedef struct {
     int32_t resolve_multidomain; /* 1 (default): regions flagged multidomain are resolved like p7_domaindef does
                                   * (200 stochastic tracebacks, RNG seed 42, single-linkage clustering);
                                   * 0: such a region is rescored as one envelope */
-    int32_t reserved;
+    int32_t keep_rows;  /* what stays on the device until domZ is known (hmmsearch prints a domain iff
+                         * P x domZ <= domE, domZ = reported hits of the profile over the WHOLE run):
+                         *   1  every domain row (itsx_hits gives the full domtbl-equivalent table),
+                         *   2  compact: a row whose P x domz_upper <= domE is printed whatever domZ turns out to
+                         *      be, so ItsPosition's arg-max over those rows is taken at once; only rows that are
+                         *      still undecided AND would beat that winner are kept.  Positions are identical;
+                         *      itsx_hits then returns only the kept rows.  Memory per searched sequence drops
+                         *      from ~3.5 KB (54 rows of 64 B) to < 100 B,
+                         *   0  (default) 1 up to 200 000 searched sequences, 2 above. */
+    int64_t domz_upper; /* upper bound of any profile's domZ for mode 2; 0 = the number of sequences this context
+                         * searches (a sharded run passes the sample's read count) */
 } itsx_search_params;
 
 /* one domtbl-equivalent row (only the fields ItsPosition reads, plus diagnostics) */

@@ -24,7 +24,7 @@ class ItsxError(RuntimeError):
 
 class SearchParams(C.Structure):
     _fields_ = [("T", C.c_float), ("F1", C.c_double), ("F2", C.c_double), ("F3", C.c_double), ("domE", C.c_double),
-                ("resolve_multidomain", C.c_int32), ("reserved", C.c_int32)]
+                ("resolve_multidomain", C.c_int32), ("keep_rows", C.c_int32), ("domz_upper", C.c_int64)]
 
 
 class SearchStats(C.Structure):

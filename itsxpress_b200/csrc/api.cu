@@ -281,7 +281,8 @@ void itsx_search_default_params(itsx_search_params *prm)
     prm->F1 = prm->F2 = prm->F3 = 1e-6;
     prm->domE = 10.0;
     prm->resolve_multidomain = 1;
-    prm->reserved = 0;
+    prm->keep_rows = 0;
+    prm->domz_upper = 0;
 }
 static int set_params(itsx_ctx *c, const itsx_search_params *prm)
 {
@@ -364,6 +365,7 @@ int itsx_hits(itsx_ctx *c, itsx_dom_row *rows, int64_t cap, int64_t *n)
     CHECK_CTX(c);
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (!c->stage2_done) { c->err = "hits before search"; return ITSX_EINVAL; }
+    // (compact mode, itsx_search_params.keep_rows: only the rows that were still undecided after stage 1 are here)
     std::vector<DomRec> h((size_t)c->ndom);
     if (c->ndom) {
         CUDA_TRY(c, cudaMemcpyAsync(h.data(), c->d_doms.p, (size_t)c->ndom * sizeof(DomRec), cudaMemcpyDefault, c->stream));

@@ -148,6 +148,10 @@ struct itsx_ctx {
     DevBuf d_nrep;                        // int32 [P] reported hits per profile (domZ)
     std::vector<int32_t> h_nrep;
     bool stage1_done = false, stage2_done = false;
+    bool compact = false;                 // keep_rows mode 2 of the last stage 1 (see include/itsx_b200.h)
+    bool stage2_applied = false;
+    int64_t n_certain_rows = 0;
+    DevBuf d_selmulti;                    // uint8 [2][nseq]: the selected left / right row came out of a multidomain region
     DevBuf d_pos;                         // int32 [9][nseq] start, stop, tlen, lsc, lfrom, lto, rsc, rfrom, rto
     DevBuf d_best;                        // uint64 [2][nseq]
     int64_t npos = 0;
@@ -182,7 +186,7 @@ struct itsx_ctx {
 };
 
 enum { CNT_COLLIDE = 0, CNT_PAST_FWD, CNT_FWD_ROWS, CNT_BCK_ROWS, CNT_ENV_ROWS, CNT_DOM_OVERFLOW, CNT_MULTI,
-       CNT_HITS_REPORTED, CNT_DOM_REPORTED, CNT_MAX_ENVLEN, CNT_BIAS_ROWS, CNT_NDOM, CNT_SEL_MULTI, CNT_N };
+       CNT_HITS_REPORTED, CNT_DOM_REPORTED, CNT_MAX_ENVLEN, CNT_BIAS_ROWS, CNT_NDOM, CNT_SEL_MULTI, CNT_CERTAIN, CNT_N };
 
 #define CUDA_TRY(ctx, call)                                                                   \
     do {                                                                                      \

@@ -25,6 +25,7 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "itsx_internal.h"
 
@@ -585,78 +586,42 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
             bool triggered = false;
             int nmulti = 0;
             SPEC(0, 0) = 0.f; SPEC(0, 1) = 0.f;   // btot[0], etot[0]
-            // The posterior rows are read back in blocks of DEC_B rows with the NEXT block's loads already in flight:
-            // the DP state registers are dead here, and one row ahead is far too little to cover an HBM round trip
-            // for a 40-instruction body (ncu r2a: 16 % of the kernel's warp time sat on this loop's first load).
-            constexpr int DEC_B = 8;
-            float nx[DEC_B][SPEC_C];
-#pragma unroll
-            for (int q = 0; q < DEC_B; q++)
-#pragma unroll
-                for (int cc = 0; cc < SPEC_C; cc++) nx[q][cc] = (1 + q <= L) ? SPEC(1 + q, cc) : 0.f;
-            for (int j0 = 1; j0 <= L; j0 += DEC_B) {
-                float cur[DEC_B][SPEC_C];
-#pragma unroll
-                for (int q = 0; q < DEC_B; q++)
-#pragma unroll
-                    for (int cc = 0; cc < SPEC_C; cc++) cur[q][cc] = nx[q][cc];
-#pragma unroll
-                for (int q = 0; q < DEC_B; q++)
-#pragma unroll
-                    for (int cc = 0; cc < SPEC_C; cc++) nx[q][cc] = (j0 + DEC_B + q <= L) ? SPEC(j0 + DEC_B + q, cc) : 0.f;
-#pragma unroll
-                for (int q = 0; q < DEC_B; q++) {
-                    const int j = j0 + q;
-                    if (j > L) break;
-                    const float v0 = cur[q][0], v1 = cur[q][1], v2 = cur[q][2], v3 = cur[q][3], v4 = cur[q][4];
-                    const float db = v0 * scaleproduct, de = v1 * scaleproduct;
-                    const float btot_p = btot, etot_p = etot;
-                    btot = btot + db;
-                    etot = etot + de;
-                    float njcp = v2 * scaleproduct;
-                    njcp += v3 * scaleproduct;
-                    njcp += v4 * scaleproduct;
-                    const float mocc = 1.f - njcp;
-                    SPEC(j, 0) = btot; SPEC(j, 1) = etot;
-                    if (!triggered) {
-                        if (mocc - (btot - btot_p) < rt2) ri = j;
-                        else if (ri == -1) ri = j;
-                        if (mocc >= rt1) triggered = true;
-                    } else if (mocc - (etot - etot_p) < rt2) {
-                        // region ri..j: multidomain iff  max_z min(etot[z] - etot[ri-1], btot[j] - btot[z-1]) >= rt3.
-                        // etot[], btot[] of the region come back from the slab four z at a time (independent loads)
-                        float mx = -1.0f;
-                        const float e0 = SPEC(ri - 1, 1);
-                        int z = ri;
-                        for (; z + 3 <= j; z += 4) {
-                            const float ea = SPEC(z, 1), eb = SPEC(z + 1, 1), ec = SPEC(z + 2, 1), ed = SPEC(z + 3, 1);
-                            const float ba = SPEC(z - 1, 0), bb = SPEC(z, 0), bc = SPEC(z + 1, 0), bd = SPEC(z + 2, 0);
-                            float x1 = ea - e0, x2 = btot - ba, en = x1 < x2 ? x1 : x2;
-                            if (en > mx) mx = en;
-                            x1 = eb - e0; x2 = btot - bb; en = x1 < x2 ? x1 : x2;
-                            if (en > mx) mx = en;
-                            x1 = ec - e0; x2 = btot - bc; en = x1 < x2 ? x1 : x2;
-                            if (en > mx) mx = en;
-                            x1 = ed - e0; x2 = btot - bd; en = x1 < x2 ? x1 : x2;
-                            if (en > mx) mx = en;
-                        }
-                        for (; z <= j; z++) {
-                            const float x1 = SPEC(z, 1) - e0, x2 = btot - SPEC(z - 1, 0);
-                            const float en = x1 < x2 ? x1 : x2;
-                            if (en > mx) mx = en;
-                        }
-                        const int multi = mx >= rt3;
-                        nmulti += multi;
-                        if (nd < ITSX_MAXDOM) {
-                            a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 0] = ri;
-                            a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 1] = j | (multi << 30);
-                            nd++;
-                        } else {
-                            atomicAdd(&a.counters[CNT_DOM_OVERFLOW], 1ull);
-                        }
-                        ri = -1;
-                        triggered = false;
+            float r0 = SPEC(1, 0), r1 = SPEC(1, 1), r2 = SPEC(1, 2), r3 = SPEC(1, 3), r4 = SPEC(1, 4);
+            for (int j = 1; j <= L; j++) {
+                const float v0 = r0, v1 = r1, v2 = r2, v3 = r3, v4 = r4;
+                if (j < L) { r0 = SPEC(j + 1, 0); r1 = SPEC(j + 1, 1); r2 = SPEC(j + 1, 2); r3 = SPEC(j + 1, 3); r4 = SPEC(j + 1, 4); }
+                const float db = v0 * scaleproduct, de = v1 * scaleproduct;
+                const float btot_p = btot, etot_p = etot;
+                btot = btot + db;
+                etot = etot + de;
+                float njcp = v2 * scaleproduct;
+                njcp += v3 * scaleproduct;
+                njcp += v4 * scaleproduct;
+                const float mocc = 1.f - njcp;
+                SPEC(j, 0) = btot; SPEC(j, 1) = etot;
+                if (!triggered) {
+                    if (mocc - (btot - btot_p) < rt2) ri = j;
+                    else if (ri == -1) ri = j;
+                    if (mocc >= rt1) triggered = true;
+                } else if (mocc - (etot - etot_p) < rt2) {
+                    float mx = -1.0f;
+                    const float e0 = SPEC(ri - 1, 1);
+                    for (int z = ri; z <= j; z++) {
+                        const float x1 = SPEC(z, 1) - e0, x2 = btot - SPEC(z - 1, 0);
+                        const float en = x1 < x2 ? x1 : x2;
+                        if (en > mx) mx = en;
                     }
+                    const int multi = mx >= rt3;
+                    nmulti += multi;
+                    if (nd < ITSX_MAXDOM) {
+                        a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 0] = ri;
+                        a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 1] = j | (multi << 30);
+                        nd++;
+                    } else {
+                        atomicAdd(&a.counters[CNT_DOM_OVERFLOW], 1ull);
+                    }
+                    ri = -1;
+                    triggered = false;
                 }
             }
             if (nmulti) atomicAdd(&a.counters[CNT_MULTI], (unsigned long long)nmulti);
@@ -1379,20 +1344,9 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
 
         // ---- Forward over the envelope; match rows (+ raw E) go to the scratch slab ----
         float xN = 1.f, xJ = 0.f, xC = 0.f, xE = 0.f, xB = N_move, totscale = 0.f;
-        // residue words (8 nibbles) are fetched one word ahead of their use, in both sweeps: a dependent global load
-        // per row was this kernel's largest stall (ncu r2a: 20 % of its warp time on the shift after the load)
-        const int p0 = ienv - 1;                     // 0-based position of envelope row 1
-        int fw = p0 >> 3;
-        uint32_t wcur = (fw * 8 < L) ? w[fw] : 0u, wnxt = ((fw + 1) * 8 < L) ? w[fw + 1] : 0u;
         for (int i = 1; i <= Lw; i++) {
-            const int fpos = p0 + i - 1;
-            if ((fpos >> 3) != fw) {
-                fw = fpos >> 3;
-                wcur = wnxt;
-                wnxt = ((fw + 1) * 8 < L) ? w[fw + 1] : 0u;
-            }
             if (i <= Ld) {
-                const float4 *er = (const float4 *)(s_e + ((wcur >> ((fpos & 7) * 4)) & 15u) * ESTRIDE);
+                const float4 *er = (const float4 *)(s_e + residue_at(w, ienv - 1 + i - 1) * ESTRIDE);
                 // pass 1, descending k, in place: M and I of row i from row i-1 (no serial dependence, so the
                 // scheduler needs no far-ahead coefficient loads); pass 2, ascending: the D chain and the E sums.
                 // Same operations and summation order as the oracle's single ascending loop.
@@ -1465,17 +1419,8 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
         }
         // raw E of row i-1 (rescale of the new Backward row) comes through a register, one row ahead
         float qE = (Lw >= 2 && Lw - 1 <= Ld) ? ROW(Lw - 1, C_E) : 0.f;
-        int bw = (p0 + max(Lw, 1) - 1) >> 3;
-        uint32_t bcur = (bw * 8 < L) ? w[bw] : 0u, bnxt = (bw >= 1 && (bw - 1) * 8 < L) ? w[bw - 1] : 0u;
         for (int i = Lw; i >= 1; i--) {
             const int b = i & 1;
-            const int bpos = p0 + i - 1;
-            if ((bpos >> 3) != bw) {
-                bw = bpos >> 3;
-                bcur = bnxt;
-                bnxt = (bw >= 1 && (bw - 1) * 8 < L) ? w[bw - 1] : 0u;
-            }
-            const uint32_t xres = (bcur >> ((bpos & 7) * 4)) & 15u;
             mbar_wait(bar0 + b * 8, phase[b]);
             phase[b] ^= 1u;
             const float *rs = ring + (size_t)b * ENV_ROWF * 32 + lane;
@@ -1494,7 +1439,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                 if (i > 1) {
                     float fEp, fSp;
                     spec_decode(cEp, fEp, fSp);
-                    const float4 *er = (const float4 *)(s_e + xres * ESTRIDE);
+                    const float4 *er = (const float4 *)(s_e + residue_at(w, ienv - 1 + i - 1) * ESTRIDE);
                     bB = 0.f;
 #pragma unroll
                     for (int k = 1; k <= MAXM; k++) {
@@ -1524,7 +1469,7 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                         for (int k = 1; k <= MAXM; k++) { Mx[k] *= inv; Dx[k] *= inv; Ix[k] *= inv; }
                     }
                 } else {
-                    const float4 *er = (const float4 *)(s_e + xres * ESTRIDE);
+                    const float4 *er = (const float4 *)(s_e + residue_at(w, ienv - 1) * ESTRIDE);
                     bB = 0.f;
 #pragma unroll
                     for (int k = 1; k <= MAXM; k++) bB = fmaf(Mx[k] * EMIS(er, k), pc.bm[k - 1], bB);
@@ -1567,6 +1512,16 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// the "%6.1f"-printed score in integer tenths, and ItsPosition's ordering key under max: (score10, NOT row rank) --
+// row order of the reference table restricted to one target = (profile, domain index), first row wins ties
+__device__ __forceinline__ int score10_of(float bits) { return (int)rint((double)bits * 10.0); }
+__device__ __forceinline__ unsigned long long row_key(float bits, int prof, int dom_idx)
+{
+    const unsigned long long sc = (unsigned long long)(score10_of(bits) + (1 << 20));
+    const unsigned long long rank = (unsigned long long)prof * ITSX_MAXDOM + (unsigned long long)dom_idx;
+    return (sc << 40) | (0xFFFFFFFFFFull - rank);
+}
+
 // K11a: per-hit and per-domain scores, -T threshold, reported-hit counts
 struct FinalArgs {
     const int32_t *list;
@@ -1588,9 +1543,14 @@ struct FinalArgs {
     const float    *n2reg;    // [entry]: trace n2sc summed over the entry's multidomain regions
     float          *envout;   // [envelope][20]; [1] receives domcorrection
     float           T;
-    DomRec         *doms;     // output base for this batch
+    DomRec         *doms;     // output base for this batch (keep_rows mode 1)
     int32_t        *nrep;     // per profile
     unsigned long long *counters;
+    // compact mode (keep_rows 2): rows that are printed whatever domZ turns out to be enter the arg-max at once
+    int             compact;
+    unsigned long long *best; // [2][nseq]
+    int64_t         nseq, seq_first;
+    double          lnP_certain;   // ln(domE / domz_upper): lnP <= this  =>  P x domZ <= domE for every possible domZ
 };
 
 __global__ void __launch_bounds__(128) final_kernel(const FinalArgs a)
@@ -1660,18 +1620,33 @@ __global__ void __launch_bounds__(128) final_kernel(const FinalArgs a)
         atomicAdd(&a.counters[CNT_HITS_REPORTED], 1ull);
     }
     for (int d = 0; d < nd; d++) {
-        const float *o = a.envout + (size_t)(o0 + d) * 20;
+        float *o = a.envout + (size_t)(o0 + d) * 20;
         const int ienv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
         const int jraw = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1];
         const int jenv = jraw & 0x1fffffff;
         const int ld = jenv - ienv + 1;
         const float bs = o[0] + (float)((L - ld) * lratio);
         const float dombias = flogsum(a.logsum, 0.0f, lnomega + o[1]);
+        const float bitscore = (float)((double)(bs - (nullsc + dombias)) / kLn2);
+        const double lnP = exp_logsurv((double)bitscore, (double)ps.ev[EV_FTAU], (double)ps.ev[EV_FLAMBDA]);
+        if (a.compact) {
+            // bit 0: the hit is reported (-T); bit 1: the row is printed for every possible domZ
+            const int certain = reported && lnP <= a.lnP_certain;
+            o[18] = bitscore;
+            o[19] = __int_as_float(reported | (certain << 1));
+            o[17] = sscore;
+            if (certain) {
+                atomicAdd(&a.counters[CNT_CERTAIN], 1ull);
+                if (ps.side >= 0)
+                    atomicMax(&a.best[(size_t)ps.side * a.nseq + (s - a.seq_first)], row_key(bitscore, p, d));
+            }
+            continue;
+        }
         DomRec r;
         r.seq = (int32_t)s; r.prof = p; r.ienv = ienv; r.jenv = jenv; r.tlen = L; r.dom_idx = d;
-        r.bitscore = (float)((double)(bs - (nullsc + dombias)) / kLn2);
+        r.bitscore = bitscore;
         r.envsc = o[0]; r.domcorrection = o[1]; r.seq_score = sscore;
-        r.lnP = exp_logsurv((double)r.bitscore, (double)ps.ev[EV_FTAU], (double)ps.ev[EV_FLAMBDA]);
+        r.lnP = lnP;
         r.seq_lnP = seq_lnP;
         r.is_multidomain = (jraw >> 30) & 1;
         r.pair_reported = reported;
@@ -1679,12 +1654,62 @@ __global__ void __launch_bounds__(128) final_kernel(const FinalArgs a)
     }
 }
 
+// compact mode, second pass over the batch once every certain row has entered the arg-max: the certain winners leave
+// their coordinates in the position table; an undecided row is kept (appended to doms) only if it would beat the
+// certain winner of its (sequence, side) -- nothing else can change the outcome once domZ is known.
+__global__ void __launch_bounds__(128) compact_select_kernel(const FinalArgs a, unsigned long long *__restrict__ ndom_at,
+                                                            int32_t *__restrict__ pos, uint8_t *__restrict__ selmulti)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.n) return;
+    const int nd = a.ndom[e];
+    if (nd == 0) return;
+    const int idx = a.list[e];
+    const int p = idx / a.ns, sl = idx - p * a.ns;
+    const int64_t s = a.order[a.s0 + sl];
+    const ProfScalars &ps = a.pscal[p];
+    const int side = ps.side;
+    const int o0 = a.envoff[e];
+    const int64_t q = s - a.seq_first;
+    for (int d = 0; d < nd; d++) {
+        const float *o = a.envout + (size_t)(o0 + d) * 20;
+        const int fl = __float_as_int(o[19]);
+        if (!(fl & 1)) continue;                       // hit below -T: never printed
+        const float bitscore = o[18];
+        const int ienv = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 0];
+        const int jraw = a.env[((size_t)e * ITSX_MAXDOM + d) * 2 + 1];
+        const int jenv = jraw & 0x1fffffff;
+        const int multi = (jraw >> 30) & 1;
+        if (side < 0) continue;                        // printed or not, ItsPosition ignores the row
+        const unsigned long long key = row_key(bitscore, p, d);
+        const unsigned long long cur = a.best[(size_t)side * a.nseq + q];
+        if (fl & 2) {
+            if (cur != key) continue;
+            int32_t *b = pos + (size_t)(3 + 3 * side) * a.nseq;
+            b[q] = score10_of(bitscore);
+            b[a.nseq + q] = ienv;
+            b[2 * a.nseq + q] = jenv;
+            pos[2 * a.nseq + q] = a.seqlen[s];
+            if (side == 0) pos[q] = jenv;
+            else pos[a.nseq + q] = ienv - 1;
+            selmulti[(size_t)side * a.nseq + q] = (uint8_t)multi;
+        } else if (key > cur) {
+            DomRec r;
+            r.seq = (int32_t)s; r.prof = p; r.ienv = ienv; r.jenv = jenv; r.tlen = a.seqlen[s]; r.dom_idx = d;
+            r.bitscore = bitscore; r.envsc = o[0]; r.domcorrection = o[1]; r.seq_score = o[17];
+            r.lnP = exp_logsurv((double)bitscore, (double)ps.ev[EV_FTAU], (double)ps.ev[EV_FLAMBDA]);
+            r.seq_lnP = exp_logsurv((double)o[17], (double)ps.ev[EV_FTAU], (double)ps.ev[EV_FLAMBDA]);
+            r.is_multidomain = multi;
+            r.pair_reported = 1;
+            a.doms[atomicAdd(ndom_at, 1ull)] = r;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K11b + K12: domE threshold with the global domZ, then ItsPosition's arg-max.
 // Row order of the reference table restricted to one target = (profile, domain index); the first row
 // wins ties on the printed score, so the key is (score10, NOT rank) under max.
-__device__ __forceinline__ int score10_of(float bits) { return (int)rint((double)bits * 10.0); }
-
 __global__ void select_kernel(DomRec *__restrict__ doms, int64_t n, const int32_t *__restrict__ nrep,
                               const ProfScalars *__restrict__ pscal, double domE,
                               unsigned long long *__restrict__ best, int64_t nseq, int64_t seq_first,
@@ -1699,15 +1724,12 @@ __global__ void select_kernel(DomRec *__restrict__ doms, int64_t n, const int32_
     atomicAdd(&counters[CNT_DOM_REPORTED], 1ull);
     const int side = pscal[r.prof].side;
     if (side < 0) return;
-    const unsigned long long sc = (unsigned long long)(score10_of(r.bitscore) + (1 << 20));
-    const unsigned long long rank = (unsigned long long)r.prof * ITSX_MAXDOM + (unsigned long long)r.dom_idx;
-    const unsigned long long key = (sc << 40) | (0xFFFFFFFFFFull - rank);
-    atomicMax(&best[(size_t)side * nseq + (r.seq - seq_first)], key);
+    atomicMax(&best[(size_t)side * nseq + (r.seq - seq_first)], row_key(r.bitscore, r.prof, r.dom_idx));
 }
 
 __global__ void best_kernel(const DomRec *__restrict__ doms, int64_t n, const ProfScalars *__restrict__ pscal,
                             const unsigned long long *__restrict__ best, int64_t nseq, int64_t seq_first,
-                            int32_t *__restrict__ pos, unsigned long long *__restrict__ counters)
+                            int32_t *__restrict__ pos, uint8_t *__restrict__ selmulti)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -1715,12 +1737,10 @@ __global__ void best_kernel(const DomRec *__restrict__ doms, int64_t n, const Pr
     if (!(r.pair_reported & 2)) return;
     const int side = pscal[r.prof].side;
     if (side < 0) return;
-    const unsigned long long sc = (unsigned long long)(score10_of(r.bitscore) + (1 << 20));
-    const unsigned long long rank = (unsigned long long)r.prof * ITSX_MAXDOM + (unsigned long long)r.dom_idx;
-    const unsigned long long key = (sc << 40) | (0xFFFFFFFFFFull - rank);
+    const unsigned long long key = row_key(r.bitscore, r.prof, r.dom_idx);
     const int64_t q = r.seq - seq_first;
     if (best[(size_t)side * nseq + q] != key) return;
-    if (r.is_multidomain) atomicAdd(&counters[CNT_SEL_MULTI], 1ull);
+    selmulti[(size_t)side * nseq + q] = (uint8_t)(r.is_multidomain != 0);
     int32_t *b = pos + (size_t)(3 + 3 * side) * nseq;
     b[q] = score10_of(r.bitscore);
     b[nseq + q] = r.ienv;
@@ -1730,10 +1750,19 @@ __global__ void best_kernel(const DomRec *__restrict__ doms, int64_t n, const Pr
     else pos[nseq + q] = r.ienv - 1;            // stop  = right.from_pos - 1      (SeqSample.py:484)
 }
 
-__global__ void pos_init_kernel(int32_t *pos, unsigned long long *best, int64_t nseq)
+__global__ void selmulti_count_kernel(const uint8_t *__restrict__ selmulti, int64_t n, unsigned long long *__restrict__ counters)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = t < n ? selmulti[t] : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, v != 0);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[CNT_SEL_MULTI], (unsigned long long)__popc(m));
+}
+
+__global__ void pos_init_kernel(int32_t *pos, unsigned long long *best, uint8_t *selmulti, int64_t nseq)
 {
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nseq) return;
+    selmulti[q] = selmulti[nseq + q] = 0;
     pos[q] = pos[nseq + q] = pos[2 * nseq + q] = -1;
     pos[3 * nseq + q] = pos[6 * nseq + q] = INT32_MIN;
     pos[4 * nseq + q] = pos[5 * nseq + q] = pos[7 * nseq + q] = pos[8 * nseq + q] = -1;
@@ -1981,7 +2010,23 @@ int search_stage1(itsx_ctx *c)
     CUDA_TRY(c, c->d_nrep.ensure((size_t)std::max(P, 1) * 4));
     CUDA_TRY(c, cudaMemsetAsync(c->d_nrep.p, 0, (size_t)std::max(P, 1) * 4, st));
     c->h_nrep.assign((size_t)P, 0);
+    c->compact = false;
+    c->stage2_applied = false;
+    c->n_certain_rows = 0;
     if (P == 0 || qn == 0) { c->stage1_done = true; return ITSX_OK; }
+    c->compact = c->prm.keep_rows == 2 || (c->prm.keep_rows == 0 && qn > 200000);
+    // position table, arg-max keys and the winners' multidomain flags live from stage 1 on (compact mode fills them as
+    // it goes; mode 1 re-initialises them in stage 2, which may then be repeated with another domZ)
+    c->npos = qn;
+    CUDA_TRY(c, c->d_pos.ensure((size_t)qn * 9 * 4));
+    CUDA_TRY(c, c->d_best.ensure((size_t)qn * 2 * 8));
+    CUDA_TRY(c, c->d_selmulti.ensure((size_t)qn * 2 + 16));
+    pos_init_kernel<<<nblk(qn, 256), 256, 0, st>>>(c->d_pos.as<int32_t>(), c->d_best.as<unsigned long long>(),
+                                                   c->d_selmulti.as<uint8_t>(), qn);
+    c->launches++;
+    const double domz_upper = c->prm.domz_upper > 0 ? (double)c->prm.domz_upper : (double)qn;
+    const double lnP_certain = log(c->prm.domE / std::max(domz_upper, 1.0));
+    int64_t total_env = 0;
     const int NLANE = 8;
     rc = ensure_lanes(c, NLANE);
     if (rc) return rc;
@@ -1996,7 +2041,9 @@ int search_stage1(itsx_ctx *c)
     const size_t msv_smem = (size_t)MSV_TP * MSV_TABW * 4;
     CUDA_TRY(c, cudaFuncSetAttribute(msv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msv_smem));
 
-    int64_t chunk = std::min<int64_t>(qn, std::max<int64_t>(1024, (1LL << 30) / P));
+    // a chunk's scratch grows with its survivors (up to ~half of the pairs on amplicons: 64 B of envelope list + ~110 B
+    // of rescoring output each), so chunks are capped at 2^27 pairs (~12 GB of scratch at 45 % survival)
+    int64_t chunk = std::min<int64_t>(qn, std::max<int64_t>(1024, (1LL << 27) / P));
     chunk = std::min<int64_t>(chunk, 1LL << 22);
     const int Lmax = c->Lmax;
     // total residues of the shard, for cell accounting
@@ -2317,11 +2364,25 @@ int search_stage1(itsx_ctx *c)
             fa.ndom = c->d_ndom.as<uint8_t>(); fa.envoff = c->d_envoff.as<int32_t>(); fa.env = c->d_env.as<int32_t>();
             fa.envdc = c->d_envdc.as<float>(); fa.n2reg = c->d_n2reg.as<float>();
             fa.envout = c->d_envout.as<float>(); fa.T = c->prm.T;
-            fa.doms = c->d_doms.as<DomRec>() + c->ndom;
+            fa.doms = c->d_doms.as<DomRec>() + (c->compact ? 0 : c->ndom);
             fa.nrep = c->d_nrep.as<int32_t>(); fa.counters = cnt;
+            fa.compact = c->compact ? 1 : 0;
+            fa.best = c->d_best.as<unsigned long long>(); fa.nseq = qn; fa.seq_first = q0;
+            fa.lnP_certain = lnP_certain;
             final_kernel<<<nblk(n2, 128), 128, 0, st>>>(fa);
             c->launches++;
-            c->ndom += nenv;
+            total_env += nenv;
+            if (c->compact) {
+                compact_select_kernel<<<nblk(n2, 128), 128, 0, st>>>(fa, cnt + CNT_NDOM, c->d_pos.as<int32_t>(),
+                                                                    c->d_selmulti.as<uint8_t>());
+                c->launches++;
+                unsigned long long cur = 0;
+                CUDA_TRY(c, cudaMemcpyAsync(&cur, cnt + CNT_NDOM, 8, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(c, cudaStreamSynchronize(st));
+                c->ndom = (int64_t)cur;
+            } else {
+                c->ndom += nenv;
+            }
         }
         CUDA_TRY(c, cudaEventRecord(ev[6], st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
@@ -2342,7 +2403,8 @@ int search_stage1(itsx_ctx *c)
     CUDA_TRY(c, cudaGetLastError());
     ss.n_past_fwd = (int64_t)h_cnt[CNT_PAST_FWD];
     ss.n_hits_reported = (int64_t)h_cnt[CNT_HITS_REPORTED];
-    ss.n_domains = c->ndom;
+    ss.n_domains = total_env;
+    c->n_certain_rows = (int64_t)h_cnt[CNT_CERTAIN];
     ss.n_multidomain_regions = (int64_t)h_cnt[CNT_MULTI];
     ss.n_dom_overflow = (int64_t)h_cnt[CNT_DOM_OVERFLOW];
     ss.bias_rows = (double)h_cnt[CNT_BIAS_ROWS];
@@ -2373,36 +2435,49 @@ int search_stage2(itsx_ctx *c)
     }
     const int64_t q0 = c->shard_first;
     const int64_t qn = c->shard_n < 0 ? c->nseq - q0 : c->shard_n;
+    if (c->compact && c->stage2_applied) {
+        c->err = "search: stage 2 was already applied to this compact search (keep_rows 2); run stage 1 again";
+        return ITSX_EINVAL;
+    }
     c->npos = qn;
     CUDA_TRY(c, c->d_pos.ensure((size_t)std::max<int64_t>(qn, 1) * 9 * 4));
     CUDA_TRY(c, c->d_best.ensure((size_t)std::max<int64_t>(qn, 1) * 2 * 8));
+    CUDA_TRY(c, c->d_selmulti.ensure((size_t)std::max<int64_t>(qn, 1) * 2 + 16));
     cudaEvent_t e0, e1;
     CUDA_TRY(c, cudaEventCreate(&e0));
     CUDA_TRY(c, cudaEventCreate(&e1));
     CUDA_TRY(c, cudaEventRecord(e0, st));
-    if (qn > 0) {
-        pos_init_kernel<<<nblk(qn, 256), 256, 0, st>>>(c->d_pos.as<int32_t>(), c->d_best.as<unsigned long long>(), qn);
+    if (qn > 0 && !c->compact) {
+        pos_init_kernel<<<nblk(qn, 256), 256, 0, st>>>(c->d_pos.as<int32_t>(), c->d_best.as<unsigned long long>(),
+                                                       c->d_selmulti.as<uint8_t>(), qn);
         c->launches++;
     }
-    if (c->ndom > 0 && P > 0) {
-        CUDA_TRY(c, cudaMemcpyAsync(c->d_nrep.p, c->h_nrep.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
-        unsigned long long *cnt = c->d_counters.as<unsigned long long>();
+    unsigned long long *cnt = c->d_counters.as<unsigned long long>();
+    c->sstats.n_domains_reported = c->compact ? c->n_certain_rows : 0;
+    c->sstats.n_selected_multidomain = 0;
+    if (qn > 0 && P > 0) {
         CUDA_TRY(c, cudaMemsetAsync(cnt + CNT_DOM_REPORTED, 0, 8, st));
         CUDA_TRY(c, cudaMemsetAsync(cnt + CNT_SEL_MULTI, 0, 8, st));
-        select_kernel<<<nblk(c->ndom, 256), 256, 0, st>>>(c->d_doms.as<DomRec>(), c->ndom, c->d_nrep.as<int32_t>(),
-                                                          c->d_pscal.as<ProfScalars>(), c->prm.domE,
-                                                          c->d_best.as<unsigned long long>(), qn, q0, cnt);
-        best_kernel<<<nblk(c->ndom, 256), 256, 0, st>>>(c->d_doms.as<DomRec>(), c->ndom, c->d_pscal.as<ProfScalars>(),
-                                                        c->d_best.as<unsigned long long>(), qn, q0,
-                                                        c->d_pos.as<int32_t>(), cnt);
-        c->launches += 2;
+        if (c->ndom > 0) {
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_nrep.p, c->h_nrep.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
+            select_kernel<<<nblk(c->ndom, 256), 256, 0, st>>>(c->d_doms.as<DomRec>(), c->ndom, c->d_nrep.as<int32_t>(),
+                                                              c->d_pscal.as<ProfScalars>(), c->prm.domE,
+                                                              c->d_best.as<unsigned long long>(), qn, q0, cnt);
+            best_kernel<<<nblk(c->ndom, 256), 256, 0, st>>>(c->d_doms.as<DomRec>(), c->ndom, c->d_pscal.as<ProfScalars>(),
+                                                            c->d_best.as<unsigned long long>(), qn, q0,
+                                                            c->d_pos.as<int32_t>(), c->d_selmulti.as<uint8_t>());
+            c->launches += 2;
+        }
+        selmulti_count_kernel<<<nblk(2 * qn, 256), 256, 0, st>>>(c->d_selmulti.as<uint8_t>(), 2 * qn, cnt);
+        c->launches++;
         unsigned long long nr = 0, nsm = 0;
         CUDA_TRY(c, cudaMemcpyAsync(&nr, cnt + CNT_DOM_REPORTED, 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaMemcpyAsync(&nsm, cnt + CNT_SEL_MULTI, 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
-        c->sstats.n_domains_reported = (int64_t)nr;
+        c->sstats.n_domains_reported += (int64_t)nr;
         c->sstats.n_selected_multidomain = (int64_t)nsm;
     }
+    c->stage2_applied = true;
     CUDA_TRY(c, cudaEventRecord(e1, st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     CUDA_TRY(c, cudaGetLastError());

@@ -432,6 +432,40 @@ def test_bench_workloads_against_oracle(gpu_ctx, oracle, config, scale, frac_mod
         assert ss.n_multidomain_regions > 1000       # the resolver is exercised at scale
 
 
+@pytest.mark.parametrize("config,scale", [("c2_small", 0.3), ("c4s", 0.01)])
+def test_compact_rows_mode_gives_the_same_positions(gpu_ctx, config, scale):
+    """keep_rows = 2 (rows that are printed for every possible domZ enter ItsPosition's arg-max at once; only undecided
+    rows that would beat that winner are stored) == keep_rows = 1 (every row kept until domZ is known): positions,
+    printed scores, reported-hit counts and the multidomain-winner count, for the sequence count and for a loose
+    domz_upper; the stored rows are a small fraction; stage 2 cannot be applied twice to a compact search."""
+    import synth
+    from itsxpress_b200 import _lib
+    seq, off, which, cfg = synth.make_config(config, scale=scale)
+    gpu_ctx.load_profiles([os.path.join(HMM_DIR, f) for f in cfg["search_files"]], [cfg["left_prefix"], cfg["right_prefix"]])
+    gpu_ctx.set_sides_by_prefix(cfg["left_prefix"], cfg["right_prefix"])
+    res = {}
+    for mode, zup in ((1, 0), (2, 0), (2, 100_000_000)):
+        prm = _lib.default_params()
+        prm.keep_rows, prm.domz_upper = mode, zup
+        out, st = gpu_ctx.run(seq, off, prm)
+        ss = gpu_ctx.search_stats()
+        res[(mode, zup)] = (dict((k, v.copy()) for k, v in out.items()), gpu_ctx.positions(st.n_unique),
+                            gpu_ctx.nreported().copy(), ss.n_selected_multidomain, ss.n_domains, len(gpu_ctx.hits()),
+                            st.n_kept)
+    ref = res[(1, 0)]
+    assert ref[6] > 0.5 * (len(off) - 1) and ref[4] == res[(2, 0)][4] > 0
+    for key in ((2, 0), (2, 100_000_000)):
+        got = res[key]
+        for k in ("rep", "keep", "lo", "hi"):
+            assert np.array_equal(got[0][k], ref[0][k]), (key, k)
+        for k in ref[1]:
+            assert np.array_equal(got[1][k], ref[1][k]), (key, k)
+        assert np.array_equal(got[2], ref[2]) and got[3] == ref[3] and got[6] == ref[6]
+        assert got[5] < 0.1 * ref[5]                    # rows kept on the device: a small fraction of the table
+    with pytest.raises(_lib.ItsxError):
+        gpu_ctx.search_stage2()
+
+
 def test_trim_set_map_drops_unmapped_reads(gpu_ctx):
     off = np.array([0, 10, 20, 30], np.int64)
     gpu_ctx.trim_set_map(np.array([0, -1, 1], np.int32), 2)
