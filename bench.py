@@ -165,8 +165,17 @@ def run_reference(args, rank, world):
         return
     from oracle import oracle as O
     O.lib()
-    seq, off, which, cfg = synth.make_config(args.config, scale=args.scale)
-    s, o, desc = cpu_sample(seq, off, which)
+    import synth_big
+    if args.config in synth_big.BIG_CONFIGS:
+        sc = args.scale * min(1.0, 12_000 / synth_big.config(args.config, args.scale)["n_reads"])
+        S1 = synth_big.BigSample(args.config, scale=sc, device="cpu")
+        a, _, c = S1.block(0, S1.N, want_qual=False)
+        s, o, cfg = a.numpy(), c.numpy(), synth_big.config(args.config, args.scale)
+        desc = ("the same generator at %d reads / %d uniques (scale %.3g of the workload); reads/s of the whole workload is "
+                "taken to be this sample's" % (S1.N, S1.U, sc))
+    else:
+        seq, off, which, cfg = synth.make_config(args.config, scale=args.scale)
+        s, o, desc = cpu_sample(seq, off, which)
     db = O.ProfileDB(profile_paths(cfg), [cfg["left_prefix"], cfg["right_prefix"]])
     side = np.array([0 if n.startswith(cfg["left_prefix"]) else 1 for n in db.names], np.int8)
     cores = os.cpu_count()       # explicit: torchrun exports OMP_NUM_THREADS=1
@@ -200,9 +209,10 @@ def workload_config(cfg, args, world):
         par = "replicas: one independent sample per GPU, no data-path collective"
     else:
         par = "one sample on one GPU"
-    return {"workload": "%s: %d reads of %s bp, %d unique (Zipf s=1), --region %s, profiles = %s %s_/%s_ "
+    law = {"exact_twice": "singletons + uniques seen exactly twice", "zipf": "Zipf s=1"}.get(cfg.get("law"), "Zipf s=1")
+    return {"workload": "%s: %d reads of %s bp, %d unique (%s), --region %s, profiles = %s %s_/%s_ "
                         "(F.hmm missing from the reference mount)" %
-                        (WORKLOAD_NAMES.get(args.config, args.config), cfg["n_reads"], length, cfg["n_unique"],
+                        (WORKLOAD_NAMES.get(args.config, args.config), cfg["n_reads"], length, cfg["n_unique"], law,
                          cfg["region"], "+".join(cfg["search_files"]) if len(cfg["search_files"]) < 4 else
                          "%d taxon files" % len(cfg["search_files"]), cfg["left_prefix"][0], cfg["right_prefix"][0]),
             "taxa": cfg["taxa"], "region": cfg["region"], "scale": args.scale,
@@ -280,9 +290,9 @@ def trim_stage(ms_bounds, ms_gather, nreads, in_bytes, out_bytes, pk):
                           "the kept slices in and out plus the per-read index arrays"}
 
 
-def cpu_baseline_leg(seq, off, which, cfg):
+def cpu_baseline_leg(cfg, small_sample):
     from oracle import oracle as O
-    s, o, desc = cpu_sample(seq, off, which)
+    s, o, desc = small_sample()
     db = O.ProfileDB(profile_paths(cfg), [cfg["left_prefix"], cfg["right_prefix"]])
     side = np.array([0 if n.startswith(cfg["left_prefix"]) else 1 for n in db.names], np.int8)
     t0 = time.perf_counter()
@@ -299,8 +309,17 @@ def run_single(args, rank, world, local):
     import torch.distributed as dist
     from itsxpress_b200 import _lib
     ctx = _lib.Context(local)
-    seq, off, which, cfg = synth.make_config(args.config, seed=2 * 1_000_003 + rank, scale=args.scale)
-    qual = synth.make_quals(77 + rank, off)
+    import synth_big
+    if args.config in synth_big.BIG_CONFIGS:
+        S = synth_big.BigSample(args.config, scale=args.scale, device="cuda:%d" % local)
+        cfg = S.cfg
+        a, b, c_ = S.block(0, S.N)
+        seq, qual, off, which = a.cpu().numpy(), b.cpu().numpy(), c_.cpu().numpy(), None
+        del a, b, c_, S
+        torch.cuda.empty_cache()
+    else:
+        seq, off, which, cfg = synth.make_config(args.config, seed=2 * 1_000_003 + rank, scale=args.scale)
+        qual = synth.make_quals(77 + rank, off)
     nreads = len(off) - 1
     ctx.load_profiles(profile_paths(cfg), [cfg["left_prefix"], cfg["right_prefix"]])
     ctx.set_sides_by_prefix(cfg["left_prefix"], cfg["right_prefix"])
@@ -405,7 +424,13 @@ def run_single(args, rank, world, local):
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_leg(seq, off, which, cfg)
+        if which is not None:
+            cpu = cpu_baseline_leg(cfg, lambda: cpu_sample(seq, off, which))
+        else:
+            k = min(nreads, 12_000)
+            cpu = cpu_baseline_leg(cfg, lambda: (seq[:off[k]].copy(), off[:k + 1].copy(),
+                                                 "the first %d reads of the workload; reads/s of the whole workload is taken "
+                                                 "to be this sample's" % k))
 
     if rank == 0:
         h2d = int(2 * tot + off.nbytes)
@@ -426,6 +451,81 @@ def run_single(args, rank, world, local):
         emit(line)
 
 
+def pinned_or_pageable(_lib, nbytes):
+    try:
+        return _lib.PinnedBuffer(nbytes)
+    except MemoryError:
+        class _Pageable:
+            def __init__(self, n):
+                self.buf = np.empty(n, np.uint8)
+
+            def array(self, dtype=np.uint8, count=None, offset=0):
+                dtype = np.dtype(dtype)
+                return self.buf[offset:offset + count * dtype.itemsize].view(dtype)
+        return _Pageable(nbytes)
+
+
+def load_block(args, rank, world, local, _lib, block_range):
+    """This rank's block of the workload in pinned host memory: (bseq, bqual, boff, lo, hi, n, total_bytes, cfg, full)
+    where full() returns the whole sample (seq, qual, off, which) when it is small enough to check against one GPU."""
+    a64 = lambda x: (x + 63) // 64 * 64
+    import synth_big
+    if args.config in synth_big.BIG_CONFIGS:
+        import torch
+        S = synth_big.BigSample(args.config, scale=args.scale, device="cuda:%d" % local)
+        cfg, n = S.cfg, S.N
+        lo, hi = block_range(n, rank, world)
+        seq_d, qual_d, off_d = S.block(lo, hi)
+        tb, nb = int(off_d[-1].item()), hi - lo
+        pin = pinned_or_pageable(_lib, 2 * a64(tb) + (nb + 1) * 8 + 64)
+        bseq, bqual = pin.array(np.uint8, tb), pin.array(np.uint8, tb, offset=a64(tb))
+        boff = pin.array(np.int64, nb + 1, offset=2 * a64(tb))
+        torch.from_numpy(bseq).copy_(seq_d)
+        torch.from_numpy(bqual).copy_(qual_d)
+        torch.from_numpy(boff).copy_(off_d)
+        tot = torch.tensor([float(tb)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            torch.distributed.all_reduce(tot)
+        del seq_d, qual_d, off_d
+        torch.cuda.empty_cache()
+
+        def full():
+            if n > 4_000_000:
+                return None
+            S0 = synth_big.BigSample(args.config, scale=args.scale, device="cuda:%d" % local)
+            a, b, c = S0.block(0, n)
+            r = (a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy(), None)
+            del a, b, c, S0
+            torch.cuda.empty_cache()
+            return r
+
+        def small():
+            """the same generator at a size the CPU oracle finishes in ~10-20 s"""
+            sc = args.scale * min(1.0, 12_000 / n)
+            S1 = synth_big.BigSample(args.config, scale=sc, device="cpu")
+            a, _, c = S1.block(0, S1.N, want_qual=False)
+            return a.numpy(), c.numpy(), ("the same generator at %d reads / %d uniques (scale %.3g of the workload); reads/s "
+                                          "of the whole workload is taken to be this sample's" % (S1.N, S1.U, sc))
+        return bseq, bqual, boff, lo, hi, n, int(tot.item()), cfg, full, small
+    seq, off, which, cfg = synth.make_config(args.config, scale=args.scale)
+    qual = synth.make_quals(77, off)
+    n = len(off) - 1
+    lo, hi = block_range(n, rank, world)
+    b0, b1 = int(off[lo]), int(off[hi])
+    nb, tb = hi - lo, b1 - b0
+    pin = pinned_or_pageable(_lib, 2 * a64(tb) + (nb + 1) * 8 + 64)
+    bseq, bqual = pin.array(np.uint8, tb), pin.array(np.uint8, tb, offset=a64(tb))
+    boff = pin.array(np.int64, nb + 1, offset=2 * a64(tb))
+    bseq[:] = seq[b0:b1]
+    bqual[:] = qual[b0:b1]
+    boff[:] = off[lo:hi + 1] - b0
+
+    def small():
+        s_, o_, desc = cpu_sample(seq, off, which)
+        return s_, o_, desc
+    return bseq, bqual, boff, lo, hi, n, int(off[-1]), cfg, (lambda: (seq, qual, off, which)), small
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def run_sharded_bench(args, rank, world, local):
     """ONE sample, block-partitioned over the ranks (itsxpress_b200.distributed.run_sharded on libitsx_b200).
@@ -435,25 +535,15 @@ def run_sharded_bench(args, rank, world, local):
     import torch.distributed as dist
     from itsxpress_b200 import _lib
     from itsxpress_b200.distributed import PHASES, Comm, GpuEngine, block_range, run_sharded
-    seq, off, which, cfg = synth.make_config(args.config, scale=args.scale)
-    qual = synth.make_quals(77, off)
-    n = len(off) - 1
+    bseq, bqual, boff, lo, hi, n, total_bytes, cfg, full_sample, small_sample = load_block(args, rank, world, local, _lib,
+                                                                                         block_range)
+    nb, tb = hi - lo, int(boff[-1])
     paths, pre = profile_paths(cfg), [cfg["left_prefix"], cfg["right_prefix"]]
     local_ctx, owner_ctx = _lib.Context(local), _lib.Context(local)
     owner_ctx.load_profiles(paths, pre)
     owner_ctx.set_sides_by_prefix(*pre)
     prm = _lib.default_params()
-    lo, hi = block_range(n, rank, world)
-    b0, b1 = int(off[lo]), int(off[hi])
-    nb, tb = hi - lo, b1 - b0
-    a64 = lambda x: (x + 63) // 64 * 64
-    pin = _lib.PinnedBuffer(2 * a64(tb) + (nb + 1) * 8 + 64)
-    bseq = pin.array(np.uint8, tb)
-    bqual = pin.array(np.uint8, tb, offset=a64(tb))
-    boff = pin.array(np.int64, nb + 1, offset=2 * a64(tb))
-    bseq[:] = seq[b0:b1]
-    bqual[:] = qual[b0:b1]
-    boff[:] = off[lo:hi + 1] - b0
+    prm.domz_upper = n               # any profile's domZ <= the sample's read count (compact row mode, see itsx_b200.h)
     comm = Comm()
     eng = GpuEngine(local_ctx, owner_ctx, prm)
 
@@ -486,9 +576,15 @@ def run_sharded_bench(args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1])
 
-    # ---- value: block resident ----
+    # pinned worst-case outputs of the e2e leg (every read kept whole)
+    a64 = lambda x: (x + 63) // 64 * 64
+    pout = pinned_or_pageable(_lib, 2 * a64(tb) + a64(nb * 4) + (nb + 1) * 8 + 64)
+    gout = dict(out_seq=pout.array(np.uint8, tb), out_qual=pout.array(np.uint8, tb, offset=a64(tb)),
+                kept_index=pout.array(np.int32, nb, offset=2 * a64(tb)),
+                out_off=pout.array(np.int64, nb + 1, offset=2 * a64(tb) + a64(nb * 4)))
+    # ---- value: block resident, results left in HBM ----
     eng.upload(bseq, boff, bqual)
-    step_res = lambda ph: run_sharded(eng, comm, None, None, lo, phases=ph, want_rep=False, gather=True)
+    step_res = lambda ph: run_sharded(eng, comm, None, None, lo, phases=ph, want_rep=False, gather="device")
     for _ in range(max(args.warmup, 3)):
         step_res(None)
     clk = ClockSampler(local)
@@ -502,7 +598,8 @@ def run_sharded_bench(args, rank, world, local):
     out_res = last["out"]
     # ---- e2e: host buffers in (H2D inside), trimmed records out (D2H inside) ----
     eng.resident = eng.resident_qual = False
-    step_e2e = lambda ph: run_sharded(eng, comm, bseq, boff, lo, phases=ph, want_rep=False, gather=True, qual=bqual)
+    step_e2e = lambda ph: run_sharded(eng, comm, bseq, boff, lo, phases=ph, want_rep=False, gather=True, qual=bqual,
+                                      gather_out=gout)
     for _ in range(2):
         step_e2e(None)
     ph_e2e = {}
@@ -549,30 +646,38 @@ def run_sharded_bench(args, rank, world, local):
         stages = search_stages(ss_sum, sec, None, None, n, L, pk, world)
         roof = roofline_of(stages)
         # ---- the same sample on ONE GPU (untimed): identical kept reads, identical trimmed bytes ----
-        single, st1 = owner_ctx.run_trim(seq, qual, off, prm)
-        ki1, oo1 = single["kept_index"], single["out_off"]
-        ok = int(st1.n_kept) == int(n_kept) and int(st1.out_bytes) == int(out_bytes) and \
-            int(st1.n_unique) == int(out["n_unique_global"]) and \
-            int(ki1.astype(np.int64).sum()) == int(kept_cksum)
-        for r in range(world):
-            rlo, rhi = block_range(n, r, world)
-            a, b = np.searchsorted(ki1, rlo), np.searchsorted(ki1, rhi)
-            want = (zlib.crc32(single["out_seq"][oo1[a]:oo1[b]].tobytes()), zlib.crc32(single["out_qual"][oo1[a]:oo1[b]].tobytes()))
-            ok = ok and tuple(int(x) for x in crcs[r].tolist()) == want
-        if not ok:
-            raise SystemExit("bench.py: the sharded result differs from the one-GPU result on the same sample "
-                             "(n_kept %d vs %d, n_unique %d vs %d)" % (n_kept, st1.n_kept, out["n_unique_global"], st1.n_unique))
+        whole = full_sample()
+        equal, check = None, "skipped: the sample is too large for one untimed one-GPU pass inside the bench"
+        if whole is not None:
+            seq, qual, off, _ = whole
+            single, st1 = owner_ctx.run_trim(seq, qual, off, prm)
+            ki1, oo1 = single["kept_index"], single["out_off"]
+            ok = int(st1.n_kept) == int(n_kept) and int(st1.out_bytes) == int(out_bytes) and \
+                int(st1.n_unique) == int(out["n_unique_global"]) and int(ki1.astype(np.int64).sum()) == int(kept_cksum)
+            for r in range(world):
+                rlo, rhi = block_range(n, r, world)
+                a, b = np.searchsorted(ki1, rlo), np.searchsorted(ki1, rhi)
+                want = (zlib.crc32(single["out_seq"][oo1[a]:oo1[b]].tobytes()),
+                        zlib.crc32(single["out_qual"][oo1[a]:oo1[b]].tobytes()))
+                ok = ok and tuple(int(x) for x in crcs[r].tolist()) == want
+            if not ok:
+                raise SystemExit("bench.py: the sharded result differs from the one-GPU result on the same sample "
+                                 "(n_kept %d vs %d, n_unique %d vs %d)" % (n_kept, st1.n_kept, out["n_unique_global"],
+                                                                          st1.n_unique))
+            equal = True
+            check = ("n_unique, n_kept, trimmed byte count, kept-index checksum and per-block CRC32 of the trimmed bases and "
+                     "qualities equal itsx_run_trim on one GPU (rank 0, untimed)")
         ex_s = max(ph["exchange"], 1e-6) / 1e3
         an_s = max(ph["answers_exchange"], 1e-6) / 1e3
         value = n / (max(ms_dev, ms_wall) / 1e3 / K)
         e2e_v = n / (max(ms_e2e_dev, ms_e2e_wall) / 1e3 / K)
-        cpu = None if args.no_cpu_baseline else cpu_baseline_leg(seq, off, which, cfg)
+        cpu = None if args.no_cpu_baseline else cpu_baseline_leg(cfg, small_sample)
         search_ms = ph["search_stage1"] + ph["search_stage2"]
         line = {"metric": "reads/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": K,
                 "warmup": max(args.warmup, 3), "ms_per_step": max(ms_dev, ms_wall) / K, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u8/s16x2 (MSV) + f32 (Forward/Backward)",
                 "data": "synthetic", "config": workload_config(cfg, args, world), "clocks": clocks,
-                "e2e": {"value": e2e_v, "unit": "reads/s", "h2d_bytes_per_step": int(2 * int(off[-1]) + off.nbytes),
+                "e2e": {"value": e2e_v, "unit": "reads/s", "h2d_bytes_per_step": int(2 * total_bytes + (n + world) * 8),
                         "d2h_bytes_per_step": int(2 * out_bytes + n_kept * 4 + (n_kept + world) * 8),
                         "ms_per_step": max(ms_e2e_dev, ms_e2e_wall) / K,
                         "call": "run_sharded(GpuEngine): every rank's block goes up from pinned host memory, its "
@@ -601,9 +706,7 @@ def run_sharded_bench(args, rank, world, local):
                               "envelope": stages["envelope"]["gcups"]},
                 "search_share": search_ms / max(sum(ph[p] for p in PHASES), 1e-9),
                 "result": {"n_unique": int(out["n_unique_global"]), "n_kept": int(n_kept), "out_bytes": int(out_bytes),
-                           "equals_single_gpu": True,
-                           "check": "n_unique, n_kept, trimmed byte count, kept-index checksum and per-block CRC32 of the "
-                                    "trimmed bases and qualities equal itsx_run_trim on one GPU (rank 0, untimed)"}}
+                           "equals_single_gpu": equal, "check": check}}
         emit(line)
     barrier()
 
@@ -620,7 +723,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (testing only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c2", choices=sorted(synth.CONFIGS),
+    import synth_big
+    ap.add_argument("--config", default="c2", choices=sorted(set(synth.CONFIGS) | set(synth_big.BIG_CONFIGS)),
                     help="workload: c2 = BASELINE configs[1] (the headline); c3 / c4 = configs[2] / [3]; c4s / c3s = "
                          "scaled shapes of them")
     ap.add_argument("--replicas", action="store_true",

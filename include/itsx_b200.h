@@ -202,6 +202,10 @@ int  itsx_trim_gather(itsx_ctx *ctx, int mode, const uint8_t *seq, const uint8_t
                       int64_t nreads, int64_t *n_kept, int64_t *total,
                       int32_t *kept_index, int64_t *out_off, uint8_t *out_seq, uint8_t *out_qual);
 
+/* the same for the RESIDENT reads (itsx_reads_upload / itsx_quals_upload, after itsx_search or itsx_shard_apply): the
+ * gathered slices stay on the device; itsx_run_fetch copies them out */
+int  itsx_trim_gather_resident(itsx_ctx *ctx, int mode, int64_t *n_kept, int64_t *total);
+
 /* ---- paired-end merge ------------------------------------------------------------------
  * Replaces the `vsearch --fastq_mergepairs R1 --reverse R2 --fastqout seq.fq --fastq_maxdiffs 40 --fastq_maxee 2
  * [--fastq_allowmergestagger] --fastq_qmax 93` process of SeqSamplePairedNotInterleaved._merge_reads

@@ -89,7 +89,7 @@ SYMBOLS = [
     "itsx_nreported", "itsx_positions", "itsx_search_stage1", "itsx_search_seqs_stage1", "itsx_search_shard",
     "itsx_nreported_set", "itsx_search_stage2", "itsx_positions_set",
     "itsx_trim_set_map", "itsx_trim_bounds", "itsx_trim_gather", "itsx_run", "itsx_reads_upload", "itsx_run_resident",
-    "itsx_launch_count", "itsx_run_trim", "itsx_quals_upload", "itsx_derep_resident", "itsx_run_fetch",
+    "itsx_launch_count", "itsx_trim_gather_resident", "itsx_run_trim", "itsx_quals_upload", "itsx_derep_resident", "itsx_run_fetch",
     "itsx_shard_plan", "itsx_shard_pack", "itsx_shard_owner_derep", "itsx_shard_answers", "itsx_shard_apply",
     "itsx_merge_default_params", "itsx_merge_pairs", "itsx_merge_fetch", "itsx_merge_get_stats",
     "itsx_host_last_error", "itsx_fastq_index", "itsx_bytes_gather", "itsx_fastq_format",
@@ -154,6 +154,7 @@ def lib():
     L.itsx_run_resident.argtypes = [vp, C.POINTER(SearchParams), C.POINTER(RunStats)]
     L.itsx_launch_count.argtypes = [vp]
     L.itsx_launch_count.restype = i64
+    L.itsx_trim_gather_resident.argtypes = [vp, C.c_int, vp, vp]
     L.itsx_run_trim.argtypes = [vp, vp, vp, vp, i64, C.POINTER(SearchParams), vp, vp, vp, vp, vp, C.POINTER(RunStats)]
     L.itsx_quals_upload.argtypes = [vp, vp]
     L.itsx_derep_resident.argtypes = [vp, C.c_int, vp]
@@ -515,17 +516,25 @@ class Context:
             view["rep"] = out["rep"]
         return view, st
 
-    def run_fetch(self):
-        """Gathered slices left on the device by run_resident() with the qualities resident."""
+    def trim_gather_resident(self, mode=0):
+        """Bounds + re-expansion of the resident reads (and qualities), results left on the device -> (n_kept, total)."""
+        nk, tot = C.c_int64(), C.c_int64()
+        self._chk(lib().itsx_trim_gather_resident(self._h, mode, C.byref(nk), C.byref(tot)))
+        return int(nk.value), int(tot.value)
+
+    def run_fetch(self, out=None):
+        """Gathered slices left on the device by run_resident() / trim_gather_resident().  out: preallocated (pinned)
+        arrays kept_index / out_off / out_seq / out_qual of worst-case size; the returned views are cut to size."""
         nk, tot = C.c_int64(), C.c_int64()
         L = lib()
         self._chk(L.itsx_run_fetch(self._h, C.byref(nk), C.byref(tot), None, None, None, None))
-        ki = np.empty(nk.value, np.int32)
-        oo = np.empty(nk.value + 1, np.int64)
-        os_ = np.empty(tot.value, np.uint8)
-        oq = np.empty(tot.value, np.uint8)
-        self._chk(L.itsx_run_fetch(self._h, None, None, _p(ki), _p(oo), _p(os_), _p(oq)))
-        return ki, oo, os_, oq
+        if out is None:
+            out = dict(kept_index=np.empty(nk.value, np.int32), out_off=np.empty(nk.value + 1, np.int64),
+                       out_seq=np.empty(tot.value, np.uint8), out_qual=np.empty(tot.value, np.uint8))
+        self._chk(L.itsx_run_fetch(self._h, None, None, _p(out["kept_index"]), _p(out["out_off"]), _p(out["out_seq"]),
+                                   _p(out["out_qual"])))
+        return (out["kept_index"][:nk.value], out["out_off"][:nk.value + 1], out["out_seq"][:tot.value],
+                out["out_qual"][:tot.value])
 
     def run_resident(self, params=None):
         st = RunStats()

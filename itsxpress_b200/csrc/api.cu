@@ -551,6 +551,33 @@ int itsx_trim_gather(itsx_ctx *c, int mode, const uint8_t *seq, const uint8_t *q
     return ITSX_OK;
 }
 
+int itsx_trim_gather_resident(itsx_ctx *c, int mode, int64_t *n_kept, int64_t *total)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int64_t n = c->nreads;
+    int rc = check_trim(c, mode, n);
+    if (rc) return rc;
+    if (c->map_external) { c->err = "trim_gather_resident: no reads are resident"; return ITSX_EINVAL; }
+    CUDA_TRY(c, c->r_keep.ensure((size_t)n + 16));
+    CUDA_TRY(c, c->r_lo.ensure((size_t)n * 4 + 16));
+    CUDA_TRY(c, c->r_hi.ensure((size_t)n * 4 + 16));
+    int64_t nk = 0, nk2 = 0, tot = 0;
+    rc = trim_bounds_dev(c, mode, nullptr, n, c->r_keep.as<uint8_t>(), c->r_lo.as<int32_t>(), c->r_hi.as<int32_t>(), &nk);
+    if (rc) return rc;
+    rc = trim_gather_dev(c, c->d_ascii.as<uint8_t>(), c->qual_resident ? c->d_qual.as<uint8_t>() : nullptr,
+                         c->d_off.as<int64_t>(), n, c->r_keep.as<uint8_t>(), c->r_lo.as<int32_t>(), c->r_hi.as<int32_t>(),
+                         &nk2, &tot, c->r_ki, c->r_oo, c->r_os, c->r_oq);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->r_nkept = nk2;
+    c->r_total = tot;
+    c->r_gathered = true;
+    if (n_kept) *n_kept = nk2;
+    if (total) *total = tot;
+    return ITSX_OK;
+}
+
 // ---- whole path ------------------------------------------------------------------------------------------
 // derep -> search -> positions -> trim bounds [-> re-expansion of the kept slices when the qualities are resident]
 static int run_device_part(itsx_ctx *c, const itsx_search_params *prm, itsx_run_stats *rs, cudaEvent_t *ev)
@@ -689,7 +716,7 @@ int itsx_run_fetch(itsx_ctx *c, int64_t *n_kept, int64_t *total, int32_t *kept_i
     if (kept_index && nk) CUDA_TRY(c, cudaMemcpyAsync(kept_index, c->r_ki.p, (size_t)nk * 4, cudaMemcpyDefault, st));
     if (out_off) CUDA_TRY(c, cudaMemcpyAsync(out_off, c->r_oo.p, (size_t)(nk + 1) * 8, cudaMemcpyDefault, st));
     if (out_seq && tot) CUDA_TRY(c, cudaMemcpyAsync(out_seq, c->r_os.p, (size_t)tot, cudaMemcpyDefault, st));
-    if (out_qual && tot) CUDA_TRY(c, cudaMemcpyAsync(out_qual, c->r_oq.p, (size_t)tot, cudaMemcpyDefault, st));
+    if (out_qual && tot && c->qual_resident) CUDA_TRY(c, cudaMemcpyAsync(out_qual, c->r_oq.p, (size_t)tot, cudaMemcpyDefault, st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     return ITSX_OK;
 }

@@ -176,9 +176,16 @@ class GpuEngine:
         keep, lo, hi, nk = self.local.trim_bounds(self.n, mode=mode)
         return keep, lo, hi
 
-    def trim_gather(self, qual=None, mode=0):
-        """kept_index, out_off, out_seq, out_qual of the block (qualities resident or given)."""
-        return self.local.trim_gather(self.n, mode=mode, qual=qual, resident_qual=self.resident_qual and qual is None)
+    def trim_gather(self, qual=None, mode=0, out=None, fetch=True):
+        """Re-expansion of the block: kept_index, out_off, out_seq, out_qual.  qual: host qualities of the block when they
+        are not resident (uploaded here).  out: preallocated (pinned) worst-case arrays for the copy back.  fetch=False:
+        the slices stay in HBM (-> (n_kept, total))."""
+        if qual is not None:
+            self.local.quals_upload(qual)
+        nk, tot = self.local.trim_gather_resident(mode)
+        if not fetch:
+            return nk, tot
+        return self.local.run_fetch(out)
 
 
 # ---- helpers ---------------------------------------------------------------------------------------------------
@@ -190,13 +197,14 @@ def block_range(n, rank, world):
 
 
 # ---- the sharded hot path --------------------------------------------------------------------------------------
-def run_sharded(engine, comm, seq, off, first_global_index, phases=None, want_rep=True, gather=False, qual=None):
+def run_sharded(engine, comm, seq, off, first_global_index, phases=None, want_rep=True, gather=False, qual=None,
+                gather_out=None):
     """Hot path for this rank's block of one sample.
 
     seq/off: this rank's reads (ASCII back to back, int64 offsets; ignored by an engine whose block is already
     resident); first_global_index: global index of its first read.  Returns dict(rep=global representative index per
     local read (int64), strand, keep, lo, hi, n_unique_global, n_owned, nreported[, kept_index, out_off, out_seq,
-    out_qual with gather=True]).  Results are identical to the single-GPU path on the concatenated input.
+    out_qual with gather=True; gather="device" leaves the slices in HBM and returns only n_kept / out_bytes]).  Results are identical to the single-GPU path on the concatenated input.
     phases: dict that receives the seconds spent per phase (PHASES), accumulated.
     """
     G = comm.world
@@ -240,9 +248,12 @@ def run_sharded(engine, comm, seq, off, first_global_index, phases=None, want_re
     rep_global, strand = engine.apply(ans_back, want_rep=want_rep)
     out = dict(rep=rep_global, strand=strand, n_unique_global=n_unique_global, n_owned=int(n_own),
                nreported=nrep_global, n_local_unique=int(nu_l))
-    if gather:
-        ki, oo, os_, oq = engine.trim_gather(qual=qual)
-        out.update(kept_index=ki, out_off=oo, out_seq=os_, out_qual=oq)
+    if gather == "device":
+        nk, tot = engine.trim_gather(qual=qual, fetch=False)
+        out.update(n_kept=nk, out_bytes=tot)
+    elif gather:
+        ki, oo, os_, oq = engine.trim_gather(qual=qual, out=gather_out)
+        out.update(kept_index=ki, out_off=oo, out_seq=os_, out_qual=oq, n_kept=len(ki), out_bytes=len(os_))
     else:
         keep, lo, hi = engine.trim_bounds()
         out.update(keep=keep, lo=lo, hi=hi)
