@@ -451,9 +451,13 @@ def run_single(args, rank, world, local):
         emit(line)
 
 
+_KEEP = []      # pinned allocations stay alive for the life of the process (numpy views do not own them)
+
+
 def pinned_or_pageable(_lib, nbytes):
     try:
-        return _lib.PinnedBuffer(nbytes)
+        _KEEP.append(_lib.PinnedBuffer(nbytes))
+        return _KEEP[-1]
     except MemoryError:
         class _Pageable:
             def __init__(self, n):
@@ -713,6 +717,8 @@ def run_sharded_bench(args, rank, world, local):
 
 def main():
     global _REAL_STDOUT
+    import faulthandler
+    faulthandler.enable()
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)

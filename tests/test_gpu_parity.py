@@ -323,6 +323,15 @@ def test_run_sharded_single_rank_equals_itsx_run(gpu_ctx, owner_ctx, fixture_rea
     for k in ("kept_index", "out_off", "out_seq", "out_qual"):
         assert np.array_equal(g2[k], wt[k]), k
     assert len(wt["kept_index"]) == st2.n_kept == st.n_kept and st2.out_bytes == len(wt["out_seq"]) > 10000
+    # the bench's legs: slices left in HBM (value), then fetched into preallocated worst-case buffers (e2e)
+    g3 = run_sharded(eng, Comm(), None, None, 0, want_rep=False, gather="device")
+    assert g3["n_kept"] == st2.n_kept and g3["out_bytes"] == st2.out_bytes
+    big = dict(kept_index=np.empty(len(off2) - 1, np.int32), out_off=np.empty(len(off2), np.int64),
+               out_seq=np.empty(len(seq2), np.uint8), out_qual=np.empty(len(seq2), np.uint8))
+    eng.resident = eng.resident_qual = False
+    g4 = run_sharded(eng, Comm(), seq2, off2, 0, want_rep=False, gather=True, qual=qual2, gather_out=big)
+    for k in ("kept_index", "out_off", "out_seq", "out_qual"):
+        assert np.array_equal(g4[k], wt[k]), k
     # an empty block is legal (more ranks than reads)
     eng2 = GpuEngine(gpu_ctx, owner_ctx)
     empty = run_sharded(eng2, Comm(), np.zeros(0, np.uint8), np.zeros(1, np.int64), 0)
