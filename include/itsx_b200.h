@@ -146,6 +146,10 @@ int  itsx_derep_clusters(itsx_ctx *ctx, int32_t *first_read, int32_t *abundance)
 /* 64-bit canonical key (strand-independent, case-insensitive) of every unique, same order as
  * itsx_derep_clusters: the owner rank of a class in the hash-partitioned multi-GPU derep is key % G. */
 int  itsx_derep_unique_keys(itsx_ctx *ctx, uint64_t *keys);
+/* the read -> representative map of the last derep (what Dedup.parse rebuilds from uc.txt, SeqSample.py:542-562):
+ * rep_index[i] = first read of i's class, strand[i], uid[i] = dense class index in first-occurrence order (= row of
+ * itsx_positions / itsx_derep_clusters).  Any may be NULL. */
+int  itsx_derep_map(itsx_ctx *ctx, int32_t *rep_index, uint8_t *strand, int32_t *uid);
 int  itsx_derep_get_stats(const itsx_ctx *ctx, itsx_derep_stats *st);
 /* test hook: keep only the low `bits` bits of the 64-bit key (forces collisions); 64 = normal */
 int  itsx_derep_set_key_bits(itsx_ctx *ctx, int bits);
@@ -266,6 +270,12 @@ int  itsx_run_trim(itsx_ctx *ctx, const uint8_t *seq, const uint8_t *qual, const
  * qualities resident the run ends with the re-expansion and itsx_run_fetch copies its result out. */
 int  itsx_reads_upload(itsx_ctx *ctx, const uint8_t *seq, const int64_t *off, int64_t nreads);
 int  itsx_quals_upload(itsx_ctx *ctx, const uint8_t *qual);      /* qual[off[nreads]] of the resident reads */
+/* Several samples in one pass (the loop over samples of q2_itsxpress.py:273-333 runs one vsearch and one hmmsearch PER
+ * SAMPLE: classes never span samples and domZ is per sample): sample_of_read[nreads] in [0, n_samples) for the resident
+ * reads, set before itsx_derep_resident.  The search then counts reported hits per (sample, profile) -- itsx_nreported /
+ * itsx_nreported_set carry n_samples x n_profiles values, sample-major -- and every later call works on the concatenated
+ * reads in input order.  Reset by the next itsx_reads_upload. */
+int  itsx_reads_set_samples(itsx_ctx *ctx, const int32_t *sample_of_read, int32_t n_samples);
 /* exact dereplication of the resident reads (what itsx_derep does after its upload); build_search_set = 0 skips the
  * re-coding of the representatives for a context that will not search them (the block side of a sharded run) */
 int  itsx_derep_resident(itsx_ctx *ctx, int build_search_set, int64_t *n_unique);

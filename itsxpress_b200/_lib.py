@@ -89,7 +89,7 @@ SYMBOLS = [
     "itsx_nreported", "itsx_positions", "itsx_search_stage1", "itsx_search_seqs_stage1", "itsx_search_shard",
     "itsx_nreported_set", "itsx_search_stage2", "itsx_positions_set",
     "itsx_trim_set_map", "itsx_trim_bounds", "itsx_trim_gather", "itsx_run", "itsx_reads_upload", "itsx_run_resident",
-    "itsx_launch_count", "itsx_trim_gather_resident", "itsx_run_trim", "itsx_quals_upload", "itsx_derep_resident", "itsx_run_fetch",
+    "itsx_launch_count", "itsx_derep_map", "itsx_reads_set_samples", "itsx_trim_gather_resident", "itsx_run_trim", "itsx_quals_upload", "itsx_derep_resident", "itsx_run_fetch",
     "itsx_shard_plan", "itsx_shard_pack", "itsx_shard_owner_derep", "itsx_shard_answers", "itsx_shard_apply",
     "itsx_merge_default_params", "itsx_merge_pairs", "itsx_merge_fetch", "itsx_merge_get_stats",
     "itsx_host_last_error", "itsx_fastq_index", "itsx_bytes_gather", "itsx_fastq_format",
@@ -154,6 +154,8 @@ def lib():
     L.itsx_run_resident.argtypes = [vp, C.POINTER(SearchParams), C.POINTER(RunStats)]
     L.itsx_launch_count.argtypes = [vp]
     L.itsx_launch_count.restype = i64
+    L.itsx_reads_set_samples.argtypes = [vp, vp, i32]
+    L.itsx_derep_map.argtypes = [vp, vp, vp, vp]
     L.itsx_trim_gather_resident.argtypes = [vp, C.c_int, vp, vp]
     L.itsx_run_trim.argtypes = [vp, vp, vp, vp, i64, C.POINTER(SearchParams), vp, vp, vp, vp, vp, C.POINTER(RunStats)]
     L.itsx_quals_upload.argtypes = [vp, vp]
@@ -335,6 +337,12 @@ class Context:
         self._chk(lib().itsx_derep_unique_keys(self._h, _p(keys)))
         return keys
 
+    def derep_map(self, n):
+        """(rep_index, strand, uid) of the n resident reads after a derep."""
+        rep, strand, uid = np.empty(n, np.int32), np.empty(n, np.uint8), np.empty(n, np.int32)
+        self._chk(lib().itsx_derep_map(self._h, _p(rep), _p(strand), _p(uid)))
+        return rep, strand, uid
+
     def derep_stats(self):
         st = DerepStats()
         self._chk(lib().itsx_derep_get_stats(self._h, C.byref(st)))
@@ -366,10 +374,17 @@ class Context:
     def search_shard(self, first, n):
         self._chk(lib().itsx_search_shard(self._h, int(first), int(n)))
 
-    def nreported(self):
-        out = np.zeros(max(1, len(self.names)), np.int32)
+    def nreported(self, n_samples=1):
+        """Reported hits per profile (hmmsearch's domZ); with n_samples > 1 (set_samples) an [n_samples, P] array."""
+        out = np.zeros(max(1, len(self.names) * n_samples), np.int32)
         self._chk(lib().itsx_nreported(self._h, _p(out)))
-        return out[:len(self.names)]
+        out = out[:len(self.names) * n_samples]
+        return out if n_samples == 1 else out.reshape(n_samples, len(self.names))
+
+    def set_samples(self, sample_of_read, n_samples):
+        """Sample id of every resident read (several samples in one pass; classes and domZ stay per sample)."""
+        a = np.ascontiguousarray(sample_of_read, dtype=np.int32)
+        self._chk(lib().itsx_reads_set_samples(self._h, _p(a), int(n_samples)))
 
     def nreported_set(self, arr):
         arr = np.ascontiguousarray(arr, dtype=np.int32)

@@ -181,6 +181,8 @@ int itsx_reads_upload(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64
     c->pos_valid = false;
     c->qual_resident = false;
     c->r_gathered = false;
+    c->have_samples = false;
+    c->n_samples = 1;
     const size_t padded = ((size_t)total + 15) / 16 * 16 + 32;
     CUDA_TRY(c, c->d_ascii.ensure(padded));
     CUDA_TRY(c, c->d_off.ensure((size_t)(nreads + 1) * 8));
@@ -189,6 +191,20 @@ int itsx_reads_upload(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64
     if (nreads) CUDA_TRY(c, cudaMemcpyAsync(c->d_off.p, off, (size_t)(nreads + 1) * 8, cudaMemcpyDefault, c->stream));
     else CUDA_TRY(c, cudaMemsetAsync(c->d_off.p, 0, 8, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ITSX_OK;
+}
+
+int itsx_reads_set_samples(itsx_ctx *c, const int32_t *sample_of_read, int32_t n_samples)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->map_external) { c->err = "reads_set_samples: no reads are resident (itsx_reads_upload first)"; return ITSX_EINVAL; }
+    if (n_samples < 1 || (c->nreads && !sample_of_read)) { c->err = "reads_set_samples: bad argument"; return ITSX_EINVAL; }
+    CUDA_TRY(c, c->d_sample.ensure((size_t)std::max<int64_t>(c->nreads, 1) * 4));
+    if (c->nreads) CUDA_TRY(c, cudaMemcpyAsync(c->d_sample.p, sample_of_read, (size_t)c->nreads * 4, cudaMemcpyDefault, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->n_samples = n_samples;
+    c->have_samples = true;
     return ITSX_OK;
 }
 
@@ -260,6 +276,20 @@ int itsx_derep_unique_keys(itsx_ctx *c, uint64_t *keys)
     return ITSX_OK;
 }
 
+int itsx_derep_map(itsx_ctx *c, int32_t *rep_index, uint8_t *strand, int32_t *uid)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->map_external || c->dstats.n_reads != c->nreads) { c->err = "derep_map: no dereplicated reads are resident"; return ITSX_EINVAL; }
+    const int64_t n = c->nreads;
+    if (n == 0) return ITSX_OK;
+    if (rep_index) CUDA_TRY(c, cudaMemcpyAsync(rep_index, c->d_rep.p, (size_t)n * 4, cudaMemcpyDefault, c->stream));
+    if (strand) CUDA_TRY(c, cudaMemcpyAsync(strand, c->d_strand.p, (size_t)n, cudaMemcpyDefault, c->stream));
+    if (uid) CUDA_TRY(c, cudaMemcpyAsync(uid, c->d_uid.p, (size_t)n * 4, cudaMemcpyDefault, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ITSX_OK;
+}
+
 int itsx_derep_get_stats(const itsx_ctx *c, itsx_derep_stats *st)
 {
     CHECK_CTX(c);
@@ -325,14 +355,14 @@ int itsx_nreported(itsx_ctx *c, int32_t *per_profile)
 {
     CHECK_CTX(c);
     if (!c->stage1_done) { c->err = "nreported before search"; return ITSX_EINVAL; }
-    if (per_profile) memcpy(per_profile, c->h_nrep.data(), c->h_nrep.size() * 4);
+    if (per_profile) memcpy(per_profile, c->h_nrep.data(), c->h_nrep.size() * 4);     // [n_samples][P]
     return ITSX_OK;
 }
 int itsx_nreported_set(itsx_ctx *c, const int32_t *g)
 {
     CHECK_CTX(c);
     if (!c->stage1_done) { c->err = "nreported_set before search stage1"; return ITSX_EINVAL; }
-    c->h_nrep.assign(g, g + c->prof.size());
+    c->h_nrep.assign(g, g + c->h_nrep.size());       // [n_samples][P] of the last stage 1
     return ITSX_OK;
 }
 int itsx_search_stage2(itsx_ctx *c)

@@ -133,6 +133,7 @@ __device__ bool range_has_exc(const uint16_t *__restrict__ exc, int64_t base, in
 __global__ void __launch_bounds__(128) hash_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off,
                                                    const uint32_t *__restrict__ P, const uint16_t *__restrict__ exc,
                                                    int64_t nreads, unsigned long long keymask,
+                                                   const int32_t *__restrict__ sample,
                                                    unsigned long long *__restrict__ key, uint8_t *__restrict__ flags)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(128) hash_kernel(const uint8_t *__restrict__ a
             h ^= k; h = rotl64(h, 27) * 5ull + 0x52dce729ull;
         }
     }
+    if (sample) h ^= mix64((unsigned long long)(uint32_t)sample[i] * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull);
     h = mix64(h) & keymask;
     if (h == kEmpty) h = 0x7fffffffffffffffull;
     key[i]   = h;
@@ -202,8 +204,10 @@ __global__ void __launch_bounds__(256) insert_kernel(const unsigned long long *_
 }
 
 __device__ bool same_class(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off,
-                           const uint32_t *__restrict__ P, const uint8_t *__restrict__ flags, int64_t a, int64_t b)
+                           const uint32_t *__restrict__ P, const uint8_t *__restrict__ flags,
+                           const int32_t *__restrict__ sample, int64_t a, int64_t b)
 {
+    if (sample && sample[a] != sample[b]) return false;      // classes never span samples
     const int64_t ba = off[a], bb = off[b];
     const int L = (int)(off[a + 1] - ba);
     if ((int)(off[b + 1] - bb) != L) return false;
@@ -225,7 +229,8 @@ __device__ bool same_class(const uint8_t *__restrict__ ascii, const int64_t *__r
 __global__ void __launch_bounds__(128) verify_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off,
                                                      const uint32_t *__restrict__ P,
                                                      const unsigned long long *__restrict__ key,
-                                                     const uint8_t *__restrict__ flags, int64_t nreads,
+                                                     const uint8_t *__restrict__ flags, const int32_t *__restrict__ sample,
+                                                     int64_t nreads,
                                                      const Slot *__restrict__ table, unsigned long long mask,
                                                      int32_t *__restrict__ rep, uint8_t *__restrict__ strand,
                                                      int32_t *__restrict__ abund, int32_t *__restrict__ collide,
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(128) verify_kernel(const uint8_t *__restrict__
     unsigned long long s = mix64(k ^ 0xD6E8FEB86659FD93ull) & mask;
     while (table[s].key != k) s = (s + 1) & mask;
     const int r = table[s].first;
-    if (r == (int)i || same_class(ascii, off, P, flags, i, r)) {
+    if (r == (int)i || same_class(ascii, off, P, flags, sample, i, r)) {
         rep[i]    = r;
         strand[i] = ((flags[i] ^ flags[r]) & FLAG_RC) ? 1 : 0;
         atomicAdd(&abund[r], 1);
@@ -251,6 +256,7 @@ __global__ void __launch_bounds__(128) verify_kernel(const uint8_t *__restrict__
 // ---- rare path: exact all-pairs resolution among collided reads -------------------------------------
 __global__ void collide_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off,
                                const uint32_t *__restrict__ P, const uint8_t *__restrict__ flags,
+                               const int32_t *__restrict__ sample,
                                const int32_t *__restrict__ collide, int64_t nc, int32_t *__restrict__ rep,
                                uint8_t *__restrict__ strand, int32_t *__restrict__ abund)
 {
@@ -260,7 +266,7 @@ __global__ void collide_kernel(const uint8_t *__restrict__ ascii, const int64_t 
     int best = a;
     for (int64_t u = 0; u < nc; u++) {
         const int b = collide[u];
-        if (b < best && same_class(ascii, off, P, flags, a, b)) best = b;
+        if (b < best && same_class(ascii, off, P, flags, sample, a, b)) best = b;
     }
     rep[a]    = best;
     strand[a] = ((flags[a] ^ flags[best]) & FLAG_RC) ? 1 : 0;
@@ -339,7 +345,8 @@ int derep_run(itsx_ctx *c)
     CUDA_TRY(c, cudaMemsetAsync(X + nchunk, 0, 4, st));
     pack2_kernel<<<nblk(nchunk, 256), 256, 0, st>>>((const uint4 *)ascii, nchunk, P, X);
     CUDA_TRY(c, cudaEventRecord(ev[1], st));
-    hash_kernel<<<nblk(n, 128), 128, 0, st>>>(ascii, off, P, X, n, keymask, c->d_key.as<unsigned long long>(),
+    const int32_t *d_samp = c->have_samples ? c->d_sample.as<int32_t>() : nullptr;
+    hash_kernel<<<nblk(n, 128), 128, 0, st>>>(ascii, off, P, X, n, keymask, d_samp, c->d_key.as<unsigned long long>(),
                                               c->d_flags.as<uint8_t>());
     CUDA_TRY(c, cudaEventRecord(ev[2], st));
     table_init_kernel<<<nblk(cap, 256), 256, 0, st>>>(c->d_table.as<Slot>(), cap);
@@ -348,7 +355,7 @@ int derep_run(itsx_ctx *c)
     CUDA_TRY(c, cudaMemsetAsync(c->d_abund.p, 0, (size_t)n * 4, st));
     CUDA_TRY(c, cudaMemsetAsync(d_ncol, 0, 8, st));
     verify_kernel<<<nblk(n, 128), 128, 0, st>>>(ascii, off, P, c->d_key.as<unsigned long long>(),
-                                                c->d_flags.as<uint8_t>(), n, c->d_table.as<Slot>(), mask,
+                                                c->d_flags.as<uint8_t>(), d_samp, n, c->d_table.as<Slot>(), mask,
                                                 c->d_rep.as<int32_t>(), c->d_strand.as<uint8_t>(),
                                                 c->d_abund.as<int32_t>(), c->d_collide.as<int32_t>(), d_ncol);
     c->launches += 5;
@@ -360,7 +367,7 @@ int derep_run(itsx_ctx *c)
             c->err = "derep: too many 64-bit key collisions to resolve exactly";
             return ITSX_ECOLLIDE;
         }
-        collide_kernel<<<nblk((int64_t)ncol, 64), 64, 0, st>>>(ascii, off, P, c->d_flags.as<uint8_t>(),
+        collide_kernel<<<nblk((int64_t)ncol, 64), 64, 0, st>>>(ascii, off, P, c->d_flags.as<uint8_t>(), d_samp,
                                                                c->d_collide.as<int32_t>(), (int64_t)ncol,
                                                                c->d_rep.as<int32_t>(), c->d_strand.as<uint8_t>(),
                                                                c->d_abund.as<int32_t>());

@@ -127,6 +127,11 @@ struct itsx_ctx {
     DevBuf d_counters;                // uint64 [32] device counters (see CNT_* below)
     DevBuf d_lut;                     // uint8 [256] ASCII -> residue code
     int64_t n_unique = 0;
+    // several samples in one pass (QIIME 2 artifacts, q2_itsxpress.py:273-333: derep, Z and domZ are per sample):
+    // sample id per read; classes never span samples, reported-hit counts are per (sample, profile)
+    DevBuf d_sample, d_seq_sample;     // int32 per read / per searched sequence
+    int32_t n_samples = 1;
+    bool have_samples = false;
     bool map_external = false;        // d_uid installed by itsx_trim_set_map (no resident read bytes)
     int key_bits = 64;
     itsx_derep_stats dstats{};

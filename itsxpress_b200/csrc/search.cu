@@ -122,6 +122,13 @@ __global__ void __launch_bounds__(256) seqcode_kernel(const uint8_t *__restrict_
     }
 }
 
+__global__ void seqsample_kernel(const int32_t *__restrict__ sample, const int32_t *__restrict__ first, int64_t nseq,
+                                 int32_t *__restrict__ out)
+{
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < nseq) out[u] = sample[first[u]];
+}
+
 // ------------------------------------------------------------------------------------------------
 // K4: MSV filter.  u8-range scores in s16x2 lanes (HMMER's u8 values; before the overflow test fires no lane can
 // reach 255 - bias, so the u8 upper clamp never binds and  sv = max(max(M_{k-1}(i-1), xB) + (bias - cost), 0)
@@ -1544,7 +1551,9 @@ struct FinalArgs {
     float          *envout;   // [envelope][20]; [1] receives domcorrection
     float           T;
     DomRec         *doms;     // output base for this batch (keep_rows mode 1)
-    int32_t        *nrep;     // per profile
+    int32_t        *nrep;     // per (sample, profile)
+    const int32_t  *seq_sample;   // sample of every searched sequence (NULL: one sample)
+    int             P;
     unsigned long long *counters;
     // compact mode (keep_rows 2): rows that are printed whatever domZ turns out to be enter the arg-max at once
     int             compact;
@@ -1616,7 +1625,7 @@ __global__ void __launch_bounds__(128) final_kernel(const FinalArgs a)
     const double seq_lnP = exp_logsurv((double)sscore, (double)ps.ev[EV_FTAU], (double)ps.ev[EV_FLAMBDA]);
     const int reported = sscore >= a.T;
     if (reported) {
-        atomicAdd(&a.nrep[p], 1);
+        atomicAdd(&a.nrep[(a.seq_sample ? (size_t)a.seq_sample[s] * a.P : 0) + p], 1);
         atomicAdd(&a.counters[CNT_HITS_REPORTED], 1ull);
     }
     for (int d = 0; d < nd; d++) {
@@ -1711,6 +1720,7 @@ __global__ void __launch_bounds__(128) compact_select_kernel(const FinalArgs a, 
 // Row order of the reference table restricted to one target = (profile, domain index); the first row
 // wins ties on the printed score, so the key is (score10, NOT rank) under max.
 __global__ void select_kernel(DomRec *__restrict__ doms, int64_t n, const int32_t *__restrict__ nrep,
+                              const int32_t *__restrict__ seq_sample, int P,
                               const ProfScalars *__restrict__ pscal, double domE,
                               unsigned long long *__restrict__ best, int64_t nseq, int64_t seq_first,
                               unsigned long long *__restrict__ counters)
@@ -1718,7 +1728,8 @@ __global__ void select_kernel(DomRec *__restrict__ doms, int64_t n, const int32_
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     DomRec &r = doms[t];
-    const int rep = r.pair_reported && (exp(r.lnP) * (double)nrep[r.prof] <= domE);
+    const int domZ = nrep[(seq_sample ? (size_t)seq_sample[r.seq] * P : 0) + r.prof];
+    const int rep = r.pair_reported && (exp(r.lnP) * (double)domZ <= domE);
     r.pair_reported = rep ? 3 : (r.pair_reported & 1);   // bit1: row is printed
     if (!rep) return;
     atomicAdd(&counters[CNT_DOM_REPORTED], 1ull);
@@ -1956,7 +1967,16 @@ static int build_seqs(itsx_ctx *c, const uint8_t *d_ascii, const int64_t *d_off,
 
 int search_build_seqs_from_derep(itsx_ctx *c)
 {
-    return build_seqs(c, c->d_ascii.as<uint8_t>(), c->d_off.as<int64_t>(), c->d_first.as<int32_t>(), c->n_unique);
+    int rc = build_seqs(c, c->d_ascii.as<uint8_t>(), c->d_off.as<int64_t>(), c->d_first.as<int32_t>(), c->n_unique);
+    if (rc) return rc;
+    if (c->have_samples && c->n_unique > 0) {
+        CUDA_TRY(c, c->d_seq_sample.ensure((size_t)c->n_unique * 4));
+        seqsample_kernel<<<nblk(c->n_unique, 256), 256, 0, c->stream>>>(c->d_sample.as<int32_t>(), c->d_first.as<int32_t>(),
+                                                                       c->n_unique, c->d_seq_sample.as<int32_t>());
+        c->launches++;
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    return ITSX_OK;
 }
 
 int search_build_seqs_from_host(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64_t nseq)
@@ -1970,6 +1990,8 @@ int search_build_seqs_from_host(itsx_ctx *c, const uint8_t *seq, const int64_t *
     if (nseq) CUDA_TRY(c, cudaMemcpyAsync(t_off.p, off, (size_t)(nseq + 1) * 8, cudaMemcpyDefault, c->stream));
     c->shard_first = 0;
     c->shard_n = -1;
+    c->have_samples = false;       // caller-supplied sequences are one sample
+    c->n_samples = 1;
     return build_seqs(c, t_ascii.as<uint8_t>(), t_off.as<int64_t>(), nullptr, nseq);
 }
 
@@ -2007,9 +2029,11 @@ int search_stage1(itsx_ctx *c)
     ss.n_seq = qn; ss.n_prof = P; ss.n_pairs = qn * P;
     CUDA_TRY(c, c->d_counters.ensure(64 * 8));
     CUDA_TRY(c, cudaMemsetAsync(c->d_counters.p, 0, 32 * 8, st));
-    CUDA_TRY(c, c->d_nrep.ensure((size_t)std::max(P, 1) * 4));
-    CUDA_TRY(c, cudaMemsetAsync(c->d_nrep.p, 0, (size_t)std::max(P, 1) * 4, st));
-    c->h_nrep.assign((size_t)P, 0);
+    const bool multi_sample = c->have_samples && c->n_samples > 1 && c->d_seq_sample.p != nullptr;
+    const size_t nrep_n = (size_t)P * (multi_sample ? c->n_samples : 1);
+    CUDA_TRY(c, c->d_nrep.ensure(std::max<size_t>(nrep_n, 1) * 4));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_nrep.p, 0, std::max<size_t>(nrep_n, 1) * 4, st));
+    c->h_nrep.assign(nrep_n, 0);
     c->compact = false;
     c->stage2_applied = false;
     c->n_certain_rows = 0;
@@ -2366,6 +2390,7 @@ int search_stage1(itsx_ctx *c)
             fa.envout = c->d_envout.as<float>(); fa.T = c->prm.T;
             fa.doms = c->d_doms.as<DomRec>() + (c->compact ? 0 : c->ndom);
             fa.nrep = c->d_nrep.as<int32_t>(); fa.counters = cnt;
+            fa.seq_sample = multi_sample ? c->d_seq_sample.as<int32_t>() : nullptr; fa.P = P;
             fa.compact = c->compact ? 1 : 0;
             fa.best = c->d_best.as<unsigned long long>(); fa.nseq = qn; fa.seq_first = q0;
             fa.lnP_certain = lnP_certain;
@@ -2398,7 +2423,7 @@ int search_stage1(itsx_ctx *c)
     CUDA_TRY(c, cudaEventRecord(ev[7], st));
     unsigned long long h_cnt[CNT_N];
     CUDA_TRY(c, cudaMemcpyAsync(h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_nrep.data(), c->d_nrep.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_nrep.data(), c->d_nrep.p, nrep_n * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     CUDA_TRY(c, cudaGetLastError());
     ss.n_past_fwd = (int64_t)h_cnt[CNT_PAST_FWD];
@@ -2459,8 +2484,10 @@ int search_stage2(itsx_ctx *c)
         CUDA_TRY(c, cudaMemsetAsync(cnt + CNT_DOM_REPORTED, 0, 8, st));
         CUDA_TRY(c, cudaMemsetAsync(cnt + CNT_SEL_MULTI, 0, 8, st));
         if (c->ndom > 0) {
-            CUDA_TRY(c, cudaMemcpyAsync(c->d_nrep.p, c->h_nrep.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
+            const bool multi_sample = c->have_samples && c->n_samples > 1 && c->h_nrep.size() == (size_t)P * c->n_samples;
+            CUDA_TRY(c, cudaMemcpyAsync(c->d_nrep.p, c->h_nrep.data(), c->h_nrep.size() * 4, cudaMemcpyHostToDevice, st));
             select_kernel<<<nblk(c->ndom, 256), 256, 0, st>>>(c->d_doms.as<DomRec>(), c->ndom, c->d_nrep.as<int32_t>(),
+                                                              multi_sample ? c->d_seq_sample.as<int32_t>() : nullptr, P,
                                                               c->d_pscal.as<ProfScalars>(), c->prm.domE,
                                                               c->d_best.as<unsigned long long>(), qn, q0, cnt);
             best_kernel<<<nblk(c->ndom, 256), 256, 0, st>>>(c->d_doms.as<DomRec>(), c->ndom, c->d_pscal.as<ProfScalars>(),

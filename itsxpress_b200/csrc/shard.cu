@@ -236,6 +236,10 @@ int itsx_shard_owner_derep(itsx_ctx *c, const uint64_t *rec, int64_t nrec, const
     c->map_external = false;
     c->pos_valid = false;
     c->sh_G = 0;
+    c->have_samples = false;
+    c->n_samples = 1;
+    c->qual_resident = false;
+    c->r_gathered = false;
     const size_t padded = ((size_t)nbytes + 15) / 16 * 16 + 32;
     CUDA_TRY(c, c->d_ascii.ensure(padded));
     CUDA_TRY(c, c->d_off.ensure((size_t)(nrec + 1) * 8));

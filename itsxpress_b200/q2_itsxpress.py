@@ -157,6 +157,156 @@ def _process_sample(sample, results, tempdir, threads, taxa, region, paired_in, 
                                       tempdir=sobj.tempdir, trim_ccs=trim_ccs)
 
 
+# ---- several samples in one device pass ---------------------------------------------------------
+# The reference runs vsearch and hmmsearch once PER SAMPLE (q2_itsxpress.py:273-296), so classes never span samples and
+# domZ is per sample.  libitsx_b200 keeps exactly that while batching: the sample id is part of the derep key and of the
+# class test, reported hits are counted per (sample, profile) (itsx_reads_set_samples).  One pass then carries the
+# merged reads of as many samples as fit BATCH_READS; an artifact of many small samples costs one chain of launches
+# instead of one per sample.  Outputs are byte-identical to the per-sample loop (tests/test_gpu_merge.py).
+BATCH_READS = int(os.environ.get("ITSX_Q2_BATCH_READS", "4000000"))      # 0 = the per-sample loop
+
+
+def _batches(rows, paired_in, budget):
+    """Consecutive samples grouped so that a group's reads (estimated from the input size) fit `budget`.  A sample that
+    alone takes more than an eighth of the budget is a group of its own: it fills the device without company and goes
+    through the per-sample path, which overlaps reading the next sample's files with the GPU work."""
+    groups, cur, est = [], [], 0
+    for s in rows:
+        try:
+            size = os.path.getsize(s.forward)
+        except OSError:
+            size = 0
+        # ~250-byte records per read; gzip shrinks amplicon FASTQ ~4-5x
+        reads = size // (60 if str(s.forward).endswith((".gz", ".zst")) else 250) + 1
+        if reads > budget // 8:
+            if cur:
+                groups.append(cur)
+            groups.append([s])
+            cur, est = [], 0
+            continue
+        if cur and est + reads > budget:
+            groups.append(cur)
+            cur, est = [], 0
+        cur.append(s)
+        est += reads
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+def _process_batch(rows, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
+                   allow_staggered_reads):
+    """The samples `rows` through ONE derep + search pass; per sample the files the sequential loop writes."""
+    import numpy as np
+    from . import _lib
+    from .SeqSample import CCS_FWD, get_context  # noqa: F401
+    from .definitions import REGION_PREFIXES, maxmismatches, vsearch_fastq_qmax
+    ctx = get_context()
+    items = []
+    for sample in rows:
+        sobj_check = (sample.forward, sample.reverse if paired_in else None)
+        try:
+            itsxpress._check_fastqs(fastq=sobj_check[0], fastq2=sobj_check[1])
+        except (NotADirectoryError, FileNotFoundError):
+            raise ValueError("There is a problem with the fastq file(s) you selected")
+        if paired_in:
+            r1, r2 = (sample.reverse, sample.forward) if reversed_primers else (sample.forward, sample.reverse)
+            b1, b2 = fq.read_fastq_many([r1, r2])
+            if b1.n != b2.n:
+                raise ValueError("More %s reads than %s reads" % (("forward", "reverse") if b1.n > b2.n else
+                                                                  ("reverse", "forward")))
+            fseq, foff = b1.seq_concat()
+            fqual, _ = b1.qual_concat()
+            rseq, roff = b2.seq_concat()
+            rqual, _ = b2.qual_concat()
+            prm = _lib.merge_params(allow_stagger=allow_staggered_reads, maxdiffs=maxmismatches, maxee=2.0,
+                                    qmax=vsearch_fastq_qmax)
+            _, _, idx, off, seq, qual = ctx.merge_pairs(fseq, fqual, foff, rseq, rqual, roff, prm)
+            items.append(dict(sample=sample, b1=b1, b2=b2, idx=idx, off=off, seq=seq, qual=qual,
+                              raw1=(fseq, fqual, foff), raw2=(rseq, rqual, roff)))
+        else:
+            b = fq.read_fastq(sample.forward)
+            seq, off = b.seq_concat()
+            qual, _ = b.qual_concat()
+            items.append(dict(sample=sample, b1=b, idx=np.arange(b.n, dtype=np.int32), off=off, seq=seq, qual=qual))
+    counts = np.array([len(it["off"]) - 1 for it in items], np.int64)
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    seq_all = np.concatenate([it["seq"] for it in items]) if len(items) else np.zeros(0, np.uint8)
+    base = np.concatenate([[0], np.cumsum([int(it["off"][-1]) for it in items])])
+    off_all = np.concatenate([[0]] + [it["off"][1:] + base[k] for k, it in enumerate(items)]).astype(np.int64)
+    sample_of_read = np.repeat(np.arange(len(items), dtype=np.int32), counts)
+    try:
+        hmmfile = itsxpress.create_runtime_hmm(taxa, region, tempdir)
+        if ctx.load_profiles([hmmfile], None) == 0:
+            raise FileNotFoundError(hmmfile)
+    except (ModuleNotFoundError, FileNotFoundError, NotADirectoryError):
+        raise ValueError("the profile search could not run: libitsx_b200 or a profile file is missing")
+    ctx.set_sides_by_prefix(*REGION_PREFIXES[region])
+    n_all = len(off_all) - 1
+    ctx.reads_upload(seq_all, off_all)
+    ctx.set_samples(sample_of_read, max(len(items), 1))
+    nu = ctx.derep_resident()
+    ctx.search()
+    if not paired_out:
+        # merged / single-end output: the re-expansion of the whole batch in one go, split by sample afterwards
+        ctx.quals_upload(np.concatenate([it["qual"] for it in items]) if len(items) else np.zeros(0, np.uint8))
+        ctx.trim_gather_resident(0)
+        ki, oo, os_, oq = ctx.run_fetch()
+        for k, it in enumerate(items):
+            a, b = np.searchsorted(ki, starts[k]), np.searchsorted(ki, starts[k + 1])
+            kept_local = ki[a:b] - starts[k]
+            text = fq.format_gathered(it["b1"], it["idx"][kept_local], oo[a:b + 1] - oo[a], os_[oo[a]:oo[b]],
+                                      oq[oo[a]:oo[b]])
+            out_fwd = os.path.join(str(results), pathlib.Path(it["sample"].forward).name)
+            fq.write_compressed(out_fwd, text, gzipped=True, zstd_file=False, n_records=len(kept_local))
+        return
+    # unmerged output: R1 [start:stop], R2 [tlen-stop : tlen-start] of every pair whose merged read was kept
+    _, _, uid = ctx.derep_map(n_all)
+    pos = ctx.positions(nu)
+    start, stop, tlen = pos["start"].copy(), pos["stop"].copy(), pos["tlen"].copy()
+    for k, it in enumerate(items):
+        b1, b2 = it["b1"], it["b2"]
+        uid_pair = np.full(b1.n, -1, np.int32)
+        uid_pair[it["idx"]] = uid[starts[k]:starts[k + 1]]
+        outs = []
+        for mode, b, raw in ((2, b1, it["raw1"]), (1, b2, it["raw2"])):
+            ctx.trim_set_map(uid_pair, nu)
+            ctx.positions_set(start, stop, tlen)
+            kk, oo, os_, oq = ctx.trim_gather(b.n, mode=mode, seq=raw[0], qual=raw[1], off=raw[2])
+            outs.append((fq.format_gathered(b, kk, oo, os_, oq), len(kk)))
+        # as upstream (q2_itsxpress.py:311-323): the trimmed r1 goes under the forward file's name, r2 under the reverse's
+        fq.write_compressed(os.path.join(str(results), pathlib.Path(it["sample"].forward).name), outs[0][0],
+                            gzipped=True, zstd_file=False, n_records=outs[0][1])
+        fq.write_compressed(os.path.join(str(results), pathlib.Path(it["sample"].reverse).name), outs[1][0],
+                            gzipped=True, zstd_file=False, n_records=outs[1][1])
+
+
+def _can_batch(cluster_id, trim_ccs):
+    return BATCH_READS > 0 and math.isclose(cluster_id, 1, rel_tol=1e-05) and not trim_ccs
+
+
+def _run_rows(rows, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
+              allow_staggered_reads, cluster_id, trim_ccs, process):
+    """The samples `rows` in order: small ones batched into shared device passes, large ones one at a time with the next
+    sample's files read ahead.  Returns the sample ids done."""
+    done = []
+    batch = _can_batch(cluster_id, trim_ccs) and process is _process_sample      # (a caller-supplied per-sample hook is kept)
+    groups = _batches(rows, paired_in, BATCH_READS) if batch else [[r] for r in rows]
+    flat = [g for g in groups]
+    for gi, group in enumerate(flat):
+        if len(group) > 1:
+            _process_batch(group, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
+                           allow_staggered_reads)
+        else:
+            if gi + 1 < len(flat) and len(flat[gi + 1]) == 1:       # read the next sample's files while this one is on the GPU
+                nxt = flat[gi + 1][0]
+                fq.prefetch([nxt.forward, nxt.reverse if paired_in else None])
+            process(group[0], results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
+                    allow_staggered_reads, cluster_id, trim_ccs)
+        done += [smp.Index for smp in group]
+    return done
+
+
 def main(per_sample_sequences, threads, taxa, region, paired_in, paired_out, reversed_primers, allow_staggered_reads,
          cluster_id, trim_ccs=False):
     taxa = _taxa_prefix_to_taxa(taxa)
@@ -168,12 +318,8 @@ def main(per_sample_sequences, threads, taxa, region, paired_in, paired_out, rev
     results = CasavaOneEightSingleLanePerSampleDirFmt() if CasavaOneEightSingleLanePerSampleDirFmt else CasavaDir()
     rows = list(samples.itertuples())
     try:
-        for k, sample in enumerate(rows):
-            if k + 1 < len(rows):       # read the next sample's files while this one is on the GPU
-                nxt = rows[k + 1]
-                fq.prefetch([nxt.forward, nxt.reverse if paired_in else None])
-            _process_sample(sample, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
-                            allow_staggered_reads, cluster_id, trim_ccs)
+        _run_rows(rows, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
+                  allow_staggered_reads, cluster_id, trim_ccs, _process_sample)
     finally:
         fq.drop_prefetched()
     if trim_ccs:
@@ -221,12 +367,8 @@ def main_sharded(per_sample_sequences, outdir, region, taxa="F", threads=1, pair
     mine = []
     todo = [sample for sample, o in zip(rows, owner) if o == rank]
     try:
-        for k, sample in enumerate(todo):
-            if k + 1 < len(todo):       # read the next sample's files while this one is on the GPU
-                fq.prefetch([todo[k + 1].forward, todo[k + 1].reverse if paired_in else None])
-            process(sample, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
-                    allow_staggered_reads, cluster_id, trim_ccs)
-            mine.append(sample.Index)
+        mine += _run_rows(todo, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
+                          allow_staggered_reads, cluster_id, trim_ccs, process)
     finally:
         fq.drop_prefetched()
         shutil.rmtree(tempdir, ignore_errors=True)

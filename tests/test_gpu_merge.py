@@ -318,3 +318,55 @@ def test_q2_main_sharded_single_rank_equals_action(tmp_path):
     for n in (n1, n2):
         assert fq._open_bytes(os.path.join(str(res), n)) == fq._open_bytes(os.path.join(str(ref), n))
     assert open(os.path.join(str(res), "MANIFEST")).read() == open(os.path.join(str(ref), "MANIFEST")).read()
+
+
+def _make_artifact(root, sizes, seed=3):
+    """A paired per-sample directory of len(sizes) samples drawn from the reference's 250 fixture pairs (overlapping
+    subsets, so the same sequences occur in several samples), plus one sample with zero reads."""
+    import gzip
+    from itsxpress_b200 import fastq as fq
+    src = os.path.join(TD, "paired", "445cf54a-bf06-4852-8010-13a60fa1598c", "data")
+    b1 = fq.read_fastq(os.path.join(src, "4774-1-MSITS3_0_L001_R1_001.fastq.gz"))
+    b2 = fq.read_fastq(os.path.join(src, "4774-1-MSITS3_1_L001_R2_001.fastq.gz"))
+    rng = np.random.default_rng(seed)
+    os.makedirs(root)
+    lines = ["sample-id,filename,direction"]
+    for k, n in enumerate(sizes):
+        pick = np.sort(rng.choice(b1.n, size=n, replace=False)) if n else np.zeros(0, np.int64)
+        for b, tag, d in ((b1, "R1", "forward"), (b2, "R2", "reverse")):
+            fn = "S%d_%d_L001_%s_001.fastq.gz" % (k, k, tag)
+            z = np.zeros(len(pick), np.int32)
+            with gzip.open(os.path.join(root, fn), "wb", compresslevel=1) as f:
+                f.write(fq.format_records(b, pick, z, b.s_len[pick].astype(np.int32)))
+            lines.append("S%d,%s,%s" % (k, fn, d))
+    with open(os.path.join(root, "MANIFEST"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return root
+
+
+@pytest.mark.parametrize("action", ["pair-unmerged", "pair"])
+def test_q2_batched_samples_equal_the_per_sample_loop(tmp_path, action, monkeypatch):
+    """all samples of an artifact in ONE device pass (segmented derep: the sample id is part of the key and
+    of the class test; reported hits per (sample, profile)) write the same bytes as the reference's sequential loop over
+    samples (q2_itsxpress.py:273-333) -- five samples of 17..230 pairs sharing sequences, one of them empty."""
+    from itsxpress_b200 import fastq as fq
+    from itsxpress_b200 import q2_itsxpress as q2
+    art = _make_artifact(str(tmp_path / "in"), [230, 17, 120, 0, 64])
+    fn = q2.trim_pair_output_unmerged if action == "pair-unmerged" else q2.trim_pair
+    monkeypatch.setattr(q2, "BATCH_READS", 0)
+    ref = fn(q2.PerSampleDir(art), region="ITS2", taxa="M")
+    monkeypatch.setattr(q2, "BATCH_READS", 4_000_000)
+    one = fn(q2.PerSampleDir(art), region="ITS2", taxa="M")
+    monkeypatch.setattr(q2, "BATCH_READS", 300)             # several batches
+    few = fn(q2.PerSampleDir(art), region="ITS2", taxa="M")
+    names = sorted(f for f in os.listdir(str(ref)) if f.endswith(".gz"))
+    assert len(names) == (10 if action == "pair-unmerged" else 5)
+    total = 0
+    for got in (one, few):
+        assert sorted(f for f in os.listdir(str(got)) if f.endswith(".gz")) == names
+        for n in names:
+            want = fq._open_bytes(os.path.join(str(ref), n))
+            assert fq._open_bytes(os.path.join(str(got), n)) == want, n
+            total += len(want)
+        assert open(os.path.join(str(got), "MANIFEST")).read() == open(os.path.join(str(ref), "MANIFEST")).read()
+    assert total > 100_000

@@ -475,6 +475,50 @@ def test_compact_rows_mode_gives_the_same_positions(gpu_ctx, config, scale):
         gpu_ctx.search_stage2()
 
 
+@pytest.mark.parametrize("keep_rows", [1, 2])
+def test_several_samples_in_one_pass(gpu_ctx, keep_rows):
+    """the samples of an artifact batched into ONE device pass (itsx_reads_set_samples: sample id folded into
+    the derep key and the class test, reported hits counted per (sample, profile)) == the reference's sequential loop
+    over samples (q2_itsxpress.py:273-333): per sample the same classes, domZ, positions, keep / lo / hi and bytes.
+    The samples share sequences (which must NOT merge across samples) and differ in size (so their domZ differ)."""
+    import synth
+    from itsxpress_b200 import _lib
+    seq, off, which, cfg = synth.make_config("c2_small", scale=0.5)
+    qual = synth.make_quals(3, off)
+    n = len(off) - 1
+    cuts = [0, n // 8, n // 2, n]                      # three samples of very different sizes over the same unique pool
+    paths = [os.path.join(HMM_DIR, cfg["hmm_file"])]
+    gpu_ctx.load_profiles(paths, [cfg["left_prefix"], cfg["right_prefix"]])
+    gpu_ctx.set_sides_by_prefix(cfg["left_prefix"], cfg["right_prefix"])
+    prm = _lib.default_params()
+    prm.keep_rows = keep_rows
+    prm.domE = 1e-3            # a tighter domE than the reference's 10: domZ then really decides rows (10-20 bit domains)
+    alone = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        s_, q_, o_ = seq[off[a]:off[b]], qual[off[a]:off[b]], off[a:b + 1] - off[a]
+        out, st = gpu_ctx.run(s_, o_, prm)
+        out = {k: v.copy() for k, v in out.items()}
+        nrep = gpu_ctx.nreported().copy()
+        tr, _ = gpu_ctx.run_trim(s_, q_, o_, prm)
+        alone.append((out, nrep, {k: v.copy() for k, v in tr.items()}, st.n_unique))
+    assert len({tuple(x[1]) for x in alone}) == 3          # the three samples have different domZ vectors
+    sample = np.repeat(np.arange(3, dtype=np.int32), np.diff(cuts))
+    gpu_ctx.reads_upload(seq, off)
+    gpu_ctx.quals_upload(qual)
+    gpu_ctx.set_samples(sample, 3)
+    st = gpu_ctx.run_resident(prm)
+    ki, oo, os_, oq = gpu_ctx.run_fetch()
+    nrep_b = gpu_ctx.nreported(3).copy()
+    assert st.n_unique == sum(x[3] for x in alone)
+    for k, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        out, nrep, tr, nu = alone[k]
+        assert np.array_equal(nrep_b[k], nrep), k
+        lo_k, hi_k = np.searchsorted(ki, a), np.searchsorted(ki, b)
+        assert np.array_equal(ki[lo_k:hi_k] - a, tr["kept_index"]), k
+        assert np.array_equal(os_[oo[lo_k]:oo[hi_k]], tr["out_seq"]) and np.array_equal(oq[oo[lo_k]:oo[hi_k]], tr["out_qual"]), k
+        assert np.array_equal(oo[lo_k:hi_k + 1] - oo[lo_k], tr["out_off"]), k
+
+
 def test_trim_set_map_drops_unmapped_reads(gpu_ctx):
     off = np.array([0, 10, 20, 30], np.int64)
     gpu_ctx.trim_set_map(np.array([0, -1, 1], np.int32), 2)
