@@ -697,14 +697,15 @@ def run_sharded_bench(args, rank, world, local):
                                            "itsxpress_b200.distributed.run_sharded, block resident in HBM"),
                 "limiting_phase": max(ph, key=ph.get),
                 "collectives": {
-                    "forward_all_to_all": {"bytes_per_rank_max": int(sent_t[0] + sent_t[1]), "records_bytes": int(sent_t[0]),
-                                           "bases_bytes": int(sent_t[1]), "ms": ph["exchange"],
+                    "forward_all_to_all": {"bytes_per_rank_max": int((sent_t[0] + sent_t[1]) / K),
+                                           "records_bytes": int(sent_t[0] / K), "bases_bytes": int(sent_t[1] / K),
+                                           "ms": ph["exchange"],
                                            "gbs_per_rank": (sent_t[0].item() + sent_t[1].item()) / K / ex_s / 1e9,
                                            "nvlink_peak_gbs": NVLINK_GBS,
                                            "note": "2 G split sizes, then records (8 B / local unique) and bases; "
                                                    "latency-bound at this size"},
                     "domz_all_reduce": {"bytes": 8 * (int(ss["n_prof"]) + 1), "ms": ph["domz_allreduce"]},
-                    "answers_all_to_all": {"bytes_per_rank_max": int(sent_t[2]), "ms": ph["answers_exchange"],
+                    "answers_all_to_all": {"bytes_per_rank_max": int(sent_t[2] / K), "ms": ph["answers_exchange"],
                                            "gbs_per_rank": sent_t[2].item() / K / an_s / 1e9, "nvlink_peak_gbs": NVLINK_GBS}},
                 "balance": {"classes_per_owner_max": int(own_max), "classes_per_owner_min": int(own_min),
                             "block_bytes_max": int(tb_max), "block_bytes_min": int(tb_min),
