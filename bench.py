@@ -302,6 +302,40 @@ def cpu_baseline_leg(cfg, small_sample):
             "sample": desc, "seconds": dt}
 
 
+def cli_file_to_file(seq, qual, off, cfg):
+    """The real end to end a user sees: `itsxpress --fastq in.fastq --single_end --outfile out.fastq[.gz]` on this
+    sample written to disk (FASTQ text in -> parse -> GPU path -> format -> [gzip] -> file out), second of two runs (page
+    cache and context warm).  Host-bound; reported beside the buffer-to-buffer e2e, not instead of it."""
+    import shutil
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from cli_e2e import write_fastq
+    from itsxpress_b200 import main as cli
+    tmp = tempfile.mkdtemp(prefix="itsx_bench_cli_")
+    out = {}
+    try:
+        fq_in = os.path.join(tmp, "in.fastq")
+        write_fastq(fq_in, seq, off, qual)
+        n = len(off) - 1
+        taxa = "All" if cfg["taxa"] == "All" else "Metazoa"
+        for tag, name in (("plain", "out.fastq"), ("gz", "out.fastq.gz")):
+            argv = ["--fastq", fq_in, "--single_end", "--outfile", os.path.join(tmp, name), "--region", cfg["region"],
+                    "--taxa", taxa, "--log", os.path.join(tmp, "log.txt"), "--tempdir", tmp]
+            dt = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                cli.main(args=cli.myparser().parse_args(argv))
+                dt = time.perf_counter() - t0
+            out[tag] = {"reads_per_s": n / dt, "seconds": dt, "input_bytes": os.path.getsize(fq_in),
+                        "output_bytes": os.path.getsize(os.path.join(tmp, name))}
+        out["note"] = "wall clock of itsxpress_b200.main.main(); bound by FASTQ parsing / formatting and gzip on the host"
+    except BaseException as e:          # the CLI ends in SystemExit on failure; the bench line must still come out
+        out["error"] = "%s: %s" % (type(e).__name__, e)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def run_single(args, rank, world, local):
     """One sample per GPU (N = 1, or --replicas)."""
@@ -422,6 +456,9 @@ def run_single(args, rank, world, local):
     stages["trim_gather"] = trim_stage(tstage["ms_trim"] / K, tstage["ms_gather"] / K, nreads, tot, int(rs.out_bytes), pk)
     roof = roofline_of(stages)
 
+    cli_extra = None
+    if rank == 0 and world == 1 and not args.no_cli and nreads <= 2_000_000:
+        cli_extra = cli_file_to_file(seq, qual, off, cfg)
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         if which is not None:
@@ -447,7 +484,8 @@ def run_single(args, rank, world, local):
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "stages": stages,
                 "hmm_gcups": {"msv": stages["msv"]["gcups"], "fwd_bwd": stages["fwd_bwd_decode"]["gcups"],
                               "envelope": stages["envelope"]["gcups"]},
-                "result": {"n_unique": int(rs.n_unique), "n_kept": int(rs.n_kept), "out_bytes": int(rs.out_bytes)}}
+                "result": {"n_unique": int(rs.n_unique), "n_kept": int(rs.n_kept), "out_bytes": int(rs.out_bytes)},
+                "extra": {"cli_file_to_file": cli_extra}}
         emit(line)
 
 
@@ -735,6 +773,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (testing only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the file-to-file command-line timing (extra.cli_file_to_file)")
     import synth_big
     ap.add_argument("--config", default="c2", choices=sorted(set(synth.CONFIGS) | set(synth_big.BIG_CONFIGS)),
                     help="workload: c2 = BASELINE configs[1] (the headline); c3 / c4 = configs[2] / [3]; c4s / c3s = "

@@ -177,7 +177,7 @@ struct itsx_ctx {
     // whole-path calls (itsx_run*): qualities of the resident reads, bounds and gathered slices of the last run
     DevBuf d_qual;
     bool qual_resident = false, r_gathered = false;
-    DevBuf r_keep, r_lo, r_hi, r_ki, r_oo, r_os, r_oq;
+    DevBuf r_keep, r_lo, r_hi, r_ki, r_oo, r_os, r_oq, d_gather;
     int64_t r_nkept = 0, r_total = 0;
 
     // one sample sharded over G GPUs (shard.cu): bucket order of the block's uniques, scratch, send / receive staging
@@ -203,19 +203,21 @@ enum { CNT_COLLIDE = 0, CNT_PAST_FWD, CNT_FWD_ROWS, CNT_BCK_ROWS, CNT_ENV_ROWS, 
     } while (0)
 
 #ifdef __CUDACC__
-// byte mover of the trim / re-expansion and shard-exchange kernels: segment j = src[soff[j] .. + len) -> dst[doff[j] ..), one warp per segment,
+// byte mover of the trim / re-expansion and shard-exchange kernels: segment j = src[soff[j] .. + len) -> dst[doff[j] ..), one group of
+// `width` lanes (a warp, or 8 lanes for slices of ~130 bytes) per segment,
 // 16-byte stores on the aligned middle of the destination, bytes at its head and tail.  Source words are read as
 // aligned 32-bit words and funnel-shifted into place, so neither side needs any alignment.
-__device__ __forceinline__ void warp_copy(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int n, int lane)
+__device__ __forceinline__ void group_copy(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int n, int lane,
+                                           int width)
 {
     const int head = min(n, (int)((16 - ((uintptr_t)dst & 15)) & 15));
-    for (int b = lane; b < head; b += 32) dst[b] = src[b];
+    for (int b = lane; b < head; b += width) dst[b] = src[b];
     const int nvec = (n - head) >> 4;
     const uint8_t *s = src + head;
     uint4 *d4 = (uint4 *)(dst + head);
     const int sh = (int)((uintptr_t)s & 3) * 8;
     const uint32_t *sw = (const uint32_t *)((uintptr_t)s & ~(uintptr_t)3);
-    for (int v = lane; v < nvec; v += 32) {
+    for (int v = lane; v < nvec; v += width) {
         const uint32_t *p = sw + v * 4;
         const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3];
         uint4 o;
@@ -229,9 +231,12 @@ __device__ __forceinline__ void warp_copy(const uint8_t *__restrict__ src, uint8
         d4[v] = o;
     }
     const int done = head + (nvec << 4);
-    for (int b = done + lane; b < n; b += 32) dst[b] = src[b];
+    for (int b = done + lane; b < n; b += width) dst[b] = src[b];
 }
-
+__device__ __forceinline__ void warp_copy(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int n, int lane)
+{
+    group_copy(src, dst, n, lane, 32);
+}
 #endif
 
 // stage entry points (implemented in derep.cu / search.cu / trim.cu)

@@ -59,35 +59,41 @@ bounds_kernel(const int32_t *__restrict__ uid, const int32_t *__restrict__ pos, 
     if (outlen) outlen[i] = k ? (int64_t)(h - l) : 0;
 }
 
+struct GatherRec { int64_t src, dst; int32_t n, pad; };     // one kept read: where its slice starts, where it goes, how long
+
 __global__ void kept_index_kernel(const int32_t *__restrict__ keepflag, const int32_t *__restrict__ kscan,
-                                  const int64_t *__restrict__ lscan, int64_t nreads,
-                                  int32_t *__restrict__ kept_index, int64_t *__restrict__ out_off)
+                                  const int64_t *__restrict__ lscan, const int64_t *__restrict__ off,
+                                  const int32_t *__restrict__ lo, const int32_t *__restrict__ hi, int64_t nreads,
+                                  int32_t *__restrict__ kept_index, int64_t *__restrict__ out_off,
+                                  GatherRec *__restrict__ rec)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > nreads) return;
     if (i == nreads) { out_off[kscan[nreads]] = lscan[nreads]; return; }
     if (keepflag[i]) {
-        kept_index[kscan[i]] = (int32_t)i;
-        out_off[kscan[i]] = lscan[i];
+        const int32_t t = kscan[i];
+        kept_index[t] = (int32_t)i;
+        out_off[t] = lscan[i];
+        GatherRec r;
+        r.src = off[i] + lo[i]; r.dst = lscan[i]; r.n = hi[i] - lo[i]; r.pad = 0;
+        rec[t] = r;
     }
 }
 
-// one warp per kept read: the seq and qual slices go to the packed outputs with 16-byte stores on the aligned middle
-// of the destination (itsx_internal.h: warp_copy)
+// eight lanes per kept read (trimmed ITS slices are ~130-250 bytes = 8-16 vectors): the seq and qual slices go to the packed
+// outputs with 16-byte stores on the aligned middle of the destination (itsx_internal.h: group_copy); one 24-byte record
+// per read replaces the five dependent index loads
+constexpr int GATHER_W = 8;
 __global__ void __launch_bounds__(256)
-gather_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual, const int64_t *__restrict__ off,
-              const int32_t *__restrict__ kept_index, const int64_t *__restrict__ out_off,
-              const int32_t *__restrict__ lo, const int32_t *__restrict__ hi, int64_t nkept,
-              uint8_t *__restrict__ out_seq, uint8_t *__restrict__ out_qual)
+gather_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual, const GatherRec *__restrict__ rec,
+              int64_t nkept, uint8_t *__restrict__ out_seq, uint8_t *__restrict__ out_qual)
 {
-    const int lane = threadIdx.x & 31;
-    int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & (GATHER_W - 1);
+    int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GATHER_W;
     if (t >= nkept) return;
-    const int32_t i = kept_index[t];
-    const int64_t src = off[i] + lo[i], dst = out_off[t];
-    const int n = hi[i] - lo[i];
-    warp_copy(seq + src, out_seq + dst, n, lane);
-    if (qual) warp_copy(qual + src, out_qual + dst, n, lane);
+    const GatherRec r = rec[t];
+    group_copy(seq + r.src, out_seq + r.dst, r.n, lane, GATHER_W);
+    if (qual) group_copy(qual + r.src, out_qual + r.dst, r.n, lane, GATHER_W);
 }
 
 }  // namespace
@@ -149,13 +155,13 @@ int trim_gather_dev(itsx_ctx *c, const uint8_t *d_seq, const uint8_t *d_qual, co
     CUDA_TRY(c, out_seq.ensure((size_t)std::max<int64_t>(tot, 1)));
     if (d_qual) CUDA_TRY(c, out_qual.ensure((size_t)std::max<int64_t>(tot, 1)));
     if (nreads == 0) { CUDA_TRY(c, cudaMemsetAsync(out_off.p, 0, 8, st)); return ITSX_OK; }
-    kept_index_kernel<<<nblk(nreads + 1, 256), 256, 0, st>>>(kf, ks, os, nreads, kept_index.as<int32_t>(),
-                                                             out_off.as<int64_t>());
+    CUDA_TRY(c, c->d_gather.ensure((size_t)std::max(nk, 1) * sizeof(GatherRec)));
+    kept_index_kernel<<<nblk(nreads + 1, 256), 256, 0, st>>>(kf, ks, os, d_off, d_lo, d_hi, nreads, kept_index.as<int32_t>(),
+                                                             out_off.as<int64_t>(), c->d_gather.as<GatherRec>());
     if (nk > 0)
-        gather_kernel<<<nblk((int64_t)nk * 32, 256), 256, 0, st>>>(d_seq, d_qual, d_off, kept_index.as<int32_t>(),
-                                                                   out_off.as<int64_t>(), d_lo, d_hi, nk,
-                                                                   out_seq.as<uint8_t>(),
-                                                                   d_qual ? out_qual.as<uint8_t>() : nullptr);
+        gather_kernel<<<nblk((int64_t)nk * GATHER_W, 256), 256, 0, st>>>(d_seq, d_qual, c->d_gather.as<GatherRec>(), nk,
+                                                                         out_seq.as<uint8_t>(),
+                                                                         d_qual ? out_qual.as<uint8_t>() : nullptr);
     c->launches += 2;
     CUDA_TRY(c, cudaGetLastError());
     return ITSX_OK;
