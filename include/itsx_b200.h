@@ -270,6 +270,19 @@ int  itsx_run_trim(itsx_ctx *ctx, const uint8_t *seq, const uint8_t *qual, const
  * qualities resident the run ends with the re-expansion and itsx_run_fetch copies its result out. */
 int  itsx_reads_upload(itsx_ctx *ctx, const uint8_t *seq, const int64_t *off, int64_t nreads);
 int  itsx_quals_upload(itsx_ctx *ctx, const uint8_t *qual);      /* qual[off[nreads]] of the resident reads */
+/* Streamed upload -- a FASTQ file too large to sit parsed in host memory (BASELINE configs[3]: 70 GB of text) arrives in
+ * chunks: the host reader parses a chunk into pinned buffers while the previous one is on its way (the reference streams
+ * the file through Biopython the same way, SeqSample.py:742-752, 908-949).  begin (hints size the first allocation) ->
+ * append chunk after chunk (off[nreads + 1] chunk-relative, off[0] = 0; qual may be NULL) -> end.  The reads are then
+ * resident exactly as after itsx_reads_upload [+ itsx_quals_upload].  itsx_reads_append returns once the chunk's
+ * buffers are free again. */
+int  itsx_reads_begin(itsx_ctx *ctx, int64_t nreads_hint, int64_t bases_hint);
+int  itsx_reads_append(itsx_ctx *ctx, const uint8_t *seq, const uint8_t *qual, const int64_t *off, int64_t nreads);
+int  itsx_reads_end(itsx_ctx *ctx, int64_t *nreads, int64_t *total_bases);
+/* ... and the chunked way out: keep filter + re-expansion of the resident reads [first, first + count) only (mode 0);
+ * kept_index is relative to `first`.  Output buffers: worst case count / count + 1 / the range's bases. */
+int  itsx_trim_gather_range(itsx_ctx *ctx, int mode, int64_t first, int64_t count, int64_t *n_kept, int64_t *total,
+                            int32_t *kept_index, int64_t *out_off, uint8_t *out_seq, uint8_t *out_qual);
 /* Several samples in one pass (the loop over samples of q2_itsxpress.py:273-333 runs one vsearch and one hmmsearch PER
  * SAMPLE: classes never span samples and domZ is per sample): sample_of_read[nreads] in [0, n_samples) for the resident
  * reads, set before itsx_derep_resident.  The search then counts reported hits per (sample, profile) -- itsx_nreported /

@@ -36,6 +36,26 @@ TEMP_FILE_POLICY = os.environ.get("ITSX_TEMP_FILES", "auto")      # auto | alway
 TEMP_FILE_AUTO_MAX_READS = 200_000
 _PLACEHOLDER = "# itsxpress-b200: not materialised for a large sample; rerun with --keeptemp or ITSX_TEMP_FILES=always\n"
 
+# A single-end / merged input larger than this is STREAMED: parsed chunk by chunk into the device (itsx_reads_begin /
+# append / end) and trimmed chunk by chunk on the way out, so neither the text nor its parsed arrays ever sit whole in
+# host memory (BASELINE configs[3] is 70 GB of FASTQ text; upstream streams through Biopython, SeqSample.py:742-752,
+# 908-949).  ITSX_STREAM=1 forces it, ITSX_STREAM=0 disables it.
+STREAM_MIN_BYTES = int(os.environ.get("ITSX_STREAM_MIN_BYTES", str(4 << 30)))
+
+
+def _stream_wanted(path):
+    mode = os.environ.get("ITSX_STREAM", "auto")
+    if mode == "1":
+        return True
+    if mode == "0":
+        return False
+    try:
+        size = os.path.getsize(path)
+    except OSError:
+        return False
+    return size * (4 if path.endswith((".gz", ".zst")) else 1) > STREAM_MIN_BYTES
+
+
 _CTX = None
 _GENERATION = 0           # bumped whenever the shared context's resident sample / search changes
 _SESSIONS = {}            # abspath of uc.txt / rep.fa / domtbl.txt  ->  _Session that wrote it
@@ -70,6 +90,9 @@ class _Session:
         self.pair_index = None
         self.pair_files = None     # (abspath R1, abspath R2)
         self.pair_batches = None   # (FastqBatch R1, FastqBatch R2)
+        self.streamed = False      # the reads went to the device chunk by chunk; no FastqBatch is held
+        self.n_reads = 0
+        self.chunk_bytes = None    # chunking of the streamed pass (the output pass repeats it)
 
     def ensure_seq_ids(self):
         if self.seq_ids is None and self.batch is not None and self.first is not None:
@@ -151,6 +174,8 @@ class SeqSample:
             self.rep_file = os.path.join(self.tempdir, "rep.fa")
             merged = getattr(self, "_merged", None)
             self._merged = None
+            if merged is None and _stream_wanted(self.seq_file):
+                return self._deduplicate_streamed()
             if merged is not None and merged[0] == os.path.abspath(self.seq_file):
                 batch, seq, off = merged[1:4]          # records _merge_reads just wrote to seq_file
             else:
@@ -195,6 +220,43 @@ class SeqSample:
             logging.exception("Could not perform dereplication on the GPU.")
             raise e
 
+    def _deduplicate_streamed(self):
+        """deduplicate() for a file that is not held in host memory: chunks of whole records are parsed (native scanner,
+        next block read / inflated on a background thread) and appended to the device-resident read set; uc.txt and
+        rep.fa are placeholders (the session carries the map)."""
+        global _GENERATION
+        ctx = get_context()
+        size = os.path.getsize(self.seq_file)
+        est_bases = (size * (4 if self.seq_file.endswith((".gz", ".zst")) else 1)) // 2
+        ctx.reads_begin(est_bases // 200, est_bases)
+        n = 0
+        for chunk in fq.stream_fastq(self.seq_file):
+            seq, off = chunk.seq_concat()
+            qual, _ = chunk.qual_concat()
+            ctx.reads_append(seq, qual, off)
+            n += chunk.n
+        n_dev, _ = ctx.reads_end()
+        assert n_dev == n
+        nu = ctx.derep_resident(build_search_set=True)
+        _GENERATION += 1
+        s = _Session()
+        s.streamed, s.n_reads, s.n_unique, s.chunk_bytes = True, n, nu, fq.STREAM_CHUNK_BYTES
+        s.derep_gen = _GENERATION
+        s.seq_path = os.path.abspath(self.seq_file)
+        s.files = False
+        s.rep = True               # (marks the session as holding the read -> representative map, on the device)
+        logging.info("uc.txt and rep.fa are one-line placeholders: %s was streamed to the GPU in chunks (%d reads); "
+                     "Dedup takes the read -> representative map from the GPU session." % (self.seq_file, n))
+        for path in (self.rep_file, self.uc_file):
+            with open(path, "w") as f:
+                f.write(_PLACEHOLDER)
+        fq.note_count(self.seq_file, n)
+        st = ctx.derep_stats()
+        logging.info("GPU dereplication: %d reads, %d unique sequences, %.2f ms on device" % (n, nu, st.ms_total))
+        self._session = s
+        _SESSIONS[os.path.abspath(self.uc_file)] = s
+        _SESSIONS[os.path.abspath(self.rep_file)] = s
+
     def _search(self, hmmfile, threads):
         """Profile-HMM search of every representative against every profile of ``hmmfile`` on the GPU with
         hmmsearch's thresholds ``-T 10 --F1 1e-6 --F2 1e-6 --F3 1e-6``; writes ``domtbl.txt``
@@ -237,7 +299,8 @@ class SeqSample:
             s.names, s.nseq = list(ctx.names), nseq
             # a search that was not fed from a resident derep session (rep.fa written by vsearch --cluster_size, or
             # by another process) has no device-side hand-off to ItsPosition / Dedup: its table is always written
-            if not resident or self._want_files(s.batch.n if s.batch is not None else nseq):
+            if not getattr(s, "streamed", False) and (not resident or
+                                                      self._want_files(s.batch.n if s.batch is not None else nseq)):
                 if seq_ids is None:
                     ids = s.ids
                     seq_ids = [ids[i] for i in s.first.tolist()]
@@ -648,6 +711,10 @@ class Dedup:
     def create_trimmed_seqs(self, outfile, gzipped, zstd_file, itspos, wri_file, tempdir, trim_ccs=False):
         """Write the reads of ``seq_file`` trimmed to the selected region, input order, plain / gz / zst
         (SeqSample.py:886-949)."""
+        ss = self._session
+        if (ss is not None and ss.streamed and os.path.abspath(self.seq_file) == ss.seq_path and
+                isinstance(itspos, ItsPosition) and itspos._session is ss and not trim_ccs):
+            return self._create_trimmed_seqs_streamed(outfile, gzipped, zstd_file, wri_file)
         if self._session is not None and self._session.batch is not None and \
                 os.path.abspath(self.seq_file) == self._session.seq_path:
             batch, ids = self._session.batch, None
@@ -659,6 +726,32 @@ class Dedup:
                 print("Total number of sequences that are empty: ", n_empty)
             return
         fq.write_compressed(outfile, text, gzipped=gzipped, zstd_file=zstd_file, n_records=len(ki))
+
+    def _create_trimmed_seqs_streamed(self, outfile, gzipped, zstd_file, wri_file):
+        """create_trimmed_seqs for a streamed session: the input is read a second time in the same chunks (only the titles
+        are needed from it); every chunk's kept slices come back from the device (itsx_trim_gather_range) and are
+        appended to the output."""
+        ss = self._session
+        if ss.derep_gen != _GENERATION:
+            raise RuntimeError("the GPU session that holds this streamed sample is no longer live")
+        ctx = get_context()
+        writer = fq.ChunkWriter(outfile, gzipped=gzipped, zstd_file=zstd_file) if wri_file else None
+        first = n_empty = 0
+        try:
+            for chunk in fq.stream_fastq(self.seq_file, ss.chunk_bytes):
+                nb = int(chunk.s_len.sum())
+                ki, oo, os_, oq = ctx.trim_gather_range(first, chunk.n, nb)
+                n_empty += int(np.count_nonzero(np.diff(oo) == 0))
+                if writer is not None:
+                    writer.write(fq.format_gathered(chunk, ki, oo, os_, oq), len(ki))
+                first += chunk.n
+        finally:
+            if writer is not None:
+                writer.close()
+        if first != ss.n_reads:
+            raise RuntimeError("the input changed between the two passes over %s" % self.seq_file)
+        if not wri_file and n_empty:
+            print("Total number of sequences that are empty: ", n_empty)
 
     def create_paired_trimmed_seqs(self, outfile1, outfile2, gzipped, zstd_file, itspos, wri_file, trim_ccs=False):
         """Write R1 and R2 trimmed but unmerged (for DADA2), input order (SeqSample.py:713-790)."""

@@ -89,7 +89,8 @@ SYMBOLS = [
     "itsx_nreported", "itsx_positions", "itsx_search_stage1", "itsx_search_seqs_stage1", "itsx_search_shard",
     "itsx_nreported_set", "itsx_search_stage2", "itsx_positions_set",
     "itsx_trim_set_map", "itsx_trim_bounds", "itsx_trim_gather", "itsx_run", "itsx_reads_upload", "itsx_run_resident",
-    "itsx_launch_count", "itsx_derep_map", "itsx_reads_set_samples", "itsx_trim_gather_resident", "itsx_run_trim", "itsx_quals_upload", "itsx_derep_resident", "itsx_run_fetch",
+    "itsx_launch_count", "itsx_reads_begin", "itsx_reads_append", "itsx_reads_end", "itsx_trim_gather_range",
+    "itsx_derep_map", "itsx_reads_set_samples", "itsx_trim_gather_resident", "itsx_run_trim", "itsx_quals_upload", "itsx_derep_resident", "itsx_run_fetch",
     "itsx_shard_plan", "itsx_shard_pack", "itsx_shard_owner_derep", "itsx_shard_answers", "itsx_shard_apply",
     "itsx_merge_default_params", "itsx_merge_pairs", "itsx_merge_fetch", "itsx_merge_get_stats",
     "itsx_host_last_error", "itsx_fastq_index", "itsx_bytes_gather", "itsx_fastq_format",
@@ -156,6 +157,10 @@ def lib():
     L.itsx_launch_count.restype = i64
     L.itsx_reads_set_samples.argtypes = [vp, vp, i32]
     L.itsx_derep_map.argtypes = [vp, vp, vp, vp]
+    L.itsx_reads_begin.argtypes = [vp, i64, i64]
+    L.itsx_reads_append.argtypes = [vp, vp, vp, vp, i64]
+    L.itsx_reads_end.argtypes = [vp, vp, vp]
+    L.itsx_trim_gather_range.argtypes = [vp, C.c_int, i64, i64, vp, vp, vp, vp, vp, vp]
     L.itsx_trim_gather_resident.argtypes = [vp, C.c_int, vp, vp]
     L.itsx_run_trim.argtypes = [vp, vp, vp, vp, i64, C.POINTER(SearchParams), vp, vp, vp, vp, vp, C.POINTER(RunStats)]
     L.itsx_quals_upload.argtypes = [vp, vp]
@@ -499,6 +504,30 @@ class Context:
         off = np.ascontiguousarray(off, dtype=np.int64)
         seq = np.ascontiguousarray(seq, dtype=np.uint8)
         self._chk(lib().itsx_reads_upload(self._h, _p(seq), _p(off), len(off) - 1))
+
+    def reads_begin(self, nreads_hint=0, bases_hint=0):
+        self._chk(lib().itsx_reads_begin(self._h, int(nreads_hint), int(bases_hint)))
+
+    def reads_append(self, seq, qual, off):
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        qual = None if qual is None else np.ascontiguousarray(qual, dtype=np.uint8)
+        self._chk(lib().itsx_reads_append(self._h, _p(seq), _p(qual), _p(off), len(off) - 1))
+
+    def reads_end(self):
+        n, tb = C.c_int64(), C.c_int64()
+        self._chk(lib().itsx_reads_end(self._h, C.byref(n), C.byref(tb)))
+        return int(n.value), int(tb.value)
+
+    def trim_gather_range(self, first, count, nbases, mode=0):
+        """(kept_index relative to first, out_off, out_seq, out_qual) of the resident reads [first, first + count);
+        nbases = bases of the range (worst-case output size)."""
+        nk, tot = C.c_int64(), C.c_int64()
+        ki, oo = np.empty(count, np.int32), np.empty(count + 1, np.int64)
+        os_, oq = np.empty(nbases, np.uint8), np.empty(nbases, np.uint8)
+        self._chk(lib().itsx_trim_gather_range(self._h, mode, int(first), int(count), C.byref(nk), C.byref(tot), _p(ki),
+                                               _p(oo), _p(os_), _p(oq)))
+        return ki[:nk.value], oo[:nk.value + 1], os_[:tot.value], oq[:tot.value]
 
     def quals_upload(self, qual):
         qual = np.ascontiguousarray(qual, dtype=np.uint8)

@@ -74,3 +74,33 @@ def decompress(data):
         return b"".join(parts)
     finally:
         L.ZSTD_freeDStream(ds)
+
+
+def decompress_stream(fh, block=1 << 20):
+    """Generator over the decoded bytes of a zstd file object, read in blocks (multi-frame files included)."""
+    L = _lib()
+    ds = L.ZSTD_createDStream()
+    L.ZSTD_initDStream(ds)
+    try:
+        osz = max(L.ZSTD_DStreamOutSize(), 1 << 20)
+        dst = C.create_string_buffer(osz)
+        rc = 0
+        while True:
+            raw = fh.read(block)
+            if not raw:
+                break
+            src = C.create_string_buffer(raw, len(raw))
+            ib = _Buf(C.cast(src, C.c_void_p), len(raw), 0)
+            full = False
+            while ib.pos < ib.size or full:
+                ob = _Buf(C.cast(dst, C.c_void_p), osz, 0)
+                rc = L.ZSTD_decompressStream(ds, C.byref(ob), C.byref(ib))
+                if L.ZSTD_isError(rc):
+                    raise ValueError("zstd: " + L.ZSTD_getErrorName(rc).decode())
+                if ob.pos:
+                    yield dst.raw[:ob.pos]
+                full = ob.pos == osz
+        if rc != 0:
+            raise ValueError("zstd: truncated input")
+    finally:
+        L.ZSTD_freeDStream(ds)

@@ -183,6 +183,7 @@ int itsx_reads_upload(itsx_ctx *c, const uint8_t *seq, const int64_t *off, int64
     c->r_gathered = false;
     c->have_samples = false;
     c->n_samples = 1;
+    c->stream_open = false;
     const size_t padded = ((size_t)total + 15) / 16 * 16 + 32;
     CUDA_TRY(c, c->d_ascii.ensure(padded));
     CUDA_TRY(c, c->d_off.ensure((size_t)(nreads + 1) * 8));
@@ -205,6 +206,124 @@ int itsx_reads_set_samples(itsx_ctx *c, const int32_t *sample_of_read, int32_t n
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->n_samples = n_samples;
     c->have_samples = true;
+    return ITSX_OK;
+}
+
+// ---- streamed upload: a file too large to parse in one piece arrives in chunks ------------------------------------
+__global__ void offset_append_kernel(const int64_t *__restrict__ chunk_off, int64_t n, int64_t base, int64_t *__restrict__ out)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j <= n) out[j] = chunk_off[j] + base;
+}
+
+int itsx_reads_begin(itsx_ctx *c, int64_t nreads_hint, int64_t bases_hint)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->nreads = 0;
+    c->total_bases = 0;
+    c->n_unique = 0;
+    c->map_external = false;
+    c->pos_valid = false;
+    c->qual_resident = false;
+    c->r_gathered = false;
+    c->have_samples = false;
+    c->n_samples = 1;
+    c->stream_open = true;
+    c->stream_qual = true;
+    c->stream_reads = c->stream_bases = 0;
+    CUDA_TRY(c, c->d_ascii.ensure((size_t)std::max<int64_t>(bases_hint, 1 << 20) + 64));
+    CUDA_TRY(c, c->d_qual.ensure((size_t)std::max<int64_t>(bases_hint, 1 << 20) + 64));
+    CUDA_TRY(c, c->d_off.ensure((size_t)(std::max<int64_t>(nreads_hint, 1024) + 1) * 8));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_off.p, 0, 8, c->stream));
+    return ITSX_OK;
+}
+
+int itsx_reads_append(itsx_ctx *c, const uint8_t *seq, const uint8_t *qual, const int64_t *off, int64_t nreads)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->stream_open) { c->err = "reads_append without itsx_reads_begin"; return ITSX_EINVAL; }
+    if (nreads < 0 || (nreads && (!seq || !off))) { c->err = "reads_append: null buffer"; return ITSX_EINVAL; }
+    if (nreads == 0) return ITSX_OK;
+    if (itsx_peek_i64(off) != 0) { c->err = "reads_append: the chunk's off[0] must be 0"; return ITSX_EINVAL; }
+    const int64_t nb = itsx_peek_i64(off + nreads);
+    cudaStream_t st = c->stream;
+    if (c->stream_reads + nreads >= 0x7fffffffLL) { c->err = "reads_append: more than 2^31-1 reads"; return ITSX_ELIMIT; }
+    // (DevBuf grows geometrically and keeps what is there)
+    CUDA_TRY(c, c->d_ascii.ensure((size_t)(c->stream_bases + nb) + 64, true, st));
+    CUDA_TRY(c, c->d_off.ensure((size_t)(c->stream_reads + nreads + 1) * 8, true, st));
+    static thread_local DevBuf t_off;
+    CUDA_TRY(c, t_off.ensure((size_t)(nreads + 1) * 8));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_ascii.as<uint8_t>() + c->stream_bases, seq, (size_t)nb, cudaMemcpyDefault, st));
+    if (qual && c->stream_qual) {
+        CUDA_TRY(c, c->d_qual.ensure((size_t)(c->stream_bases + nb) + 64, true, st));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_qual.as<uint8_t>() + c->stream_bases, qual, (size_t)nb, cudaMemcpyDefault, st));
+    } else {
+        c->stream_qual = false;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(t_off.p, off, (size_t)(nreads + 1) * 8, cudaMemcpyDefault, st));
+    offset_append_kernel<<<(unsigned)((nreads + 256) / 256), 256, 0, st>>>(t_off.as<int64_t>(), nreads, c->stream_bases,
+                                                                           c->d_off.as<int64_t>() + c->stream_reads);
+    c->launches++;
+    c->stream_reads += nreads;
+    c->stream_bases += nb;
+    // the staging copy of the offsets is reused by the next append: drain here (the caller's seq / qual buffers are then
+    // free as well; a double-buffering reader fills its OTHER buffer while this call runs on a worker thread)
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    return ITSX_OK;
+}
+
+int itsx_reads_end(itsx_ctx *c, int64_t *nreads, int64_t *total_bases)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (!c->stream_open) { c->err = "reads_end without itsx_reads_begin"; return ITSX_EINVAL; }
+    cudaStream_t st = c->stream;
+    const int64_t total = c->stream_bases;
+    const size_t padded = ((size_t)total + 15) / 16 * 16 + 32;
+    CUDA_TRY(c, c->d_ascii.ensure(padded, true, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_ascii.as<uint8_t>() + total, 'A', padded - (size_t)total, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    c->nreads = c->stream_reads;
+    c->total_bases = total;
+    c->qual_resident = c->stream_qual && c->stream_reads > 0;
+    c->stream_open = false;
+    if (nreads) *nreads = c->nreads;
+    if (total_bases) *total_bases = total;
+    return ITSX_OK;
+}
+
+/* re-expansion of the resident reads [first, first + count): what a chunked writer asks for, chunk after chunk */
+int itsx_trim_gather_range(itsx_ctx *c, int mode, int64_t first, int64_t count, int64_t *n_kept, int64_t *total,
+                           int32_t *kept_index, int64_t *out_off, uint8_t *out_seq, uint8_t *out_qual)
+{
+    CHECK_CTX(c);
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->stream_open) { c->err = "trim: a streamed upload is still open (itsx_reads_end)"; return ITSX_EINVAL; }
+    if (mode != 0) { c->err = "trim_gather_range: only mode 0 (the dereplicated reads themselves)"; return ITSX_EINVAL; }
+    if (c->map_external) { c->err = "trim_gather_range: no reads are resident"; return ITSX_EINVAL; }
+    if (c->npos != c->n_unique) { c->err = "trim: position table does not cover every unique sequence"; return ITSX_EINVAL; }
+    if (first < 0 || count < 0 || first + count > c->nreads) { c->err = "trim_gather_range: range outside the reads"; return ITSX_EINVAL; }
+    if (!n_kept || !total) return ITSX_EINVAL;
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, c->r_keep.ensure((size_t)count + 16));
+    CUDA_TRY(c, c->r_lo.ensure((size_t)count * 4 + 16));
+    CUDA_TRY(c, c->r_hi.ensure((size_t)count * 4 + 16));
+    int64_t nk = 0;
+    int rc = trim_bounds_dev(c, 0, nullptr, count, c->r_keep.as<uint8_t>(), c->r_lo.as<int32_t>(), c->r_hi.as<int32_t>(), &nk,
+                             first);
+    if (rc) return rc;
+    rc = trim_gather_dev(c, c->d_ascii.as<uint8_t>(), c->qual_resident ? c->d_qual.as<uint8_t>() : nullptr,
+                         c->d_off.as<int64_t>() + first, count, c->r_keep.as<uint8_t>(), c->r_lo.as<int32_t>(),
+                         c->r_hi.as<int32_t>(), n_kept, total, c->r_ki, c->r_oo, c->r_os, c->r_oq);
+    if (rc) return rc;
+    c->r_gathered = false;
+    if (kept_index && *n_kept) CUDA_TRY(c, cudaMemcpyAsync(kept_index, c->r_ki.p, (size_t)*n_kept * 4, cudaMemcpyDefault, st));
+    if (out_off) CUDA_TRY(c, cudaMemcpyAsync(out_off, c->r_oo.p, (size_t)(*n_kept + 1) * 8, cudaMemcpyDefault, st));
+    if (out_seq && *total) CUDA_TRY(c, cudaMemcpyAsync(out_seq, c->r_os.p, (size_t)*total, cudaMemcpyDefault, st));
+    if (out_qual && *total && c->qual_resident) CUDA_TRY(c, cudaMemcpyAsync(out_qual, c->r_oq.p, (size_t)*total, cudaMemcpyDefault, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
     return ITSX_OK;
 }
 
@@ -480,6 +599,7 @@ int itsx_trim_set_map(itsx_ctx *c, const int32_t *uid, int64_t nreads, int64_t n
 
 static int check_trim(itsx_ctx *c, int mode, int64_t nreads)
 {
+    if (c->stream_open) { c->err = "trim: a streamed upload is still open (itsx_reads_end)"; return ITSX_EINVAL; }
     if (mode < 0 || mode > 2) { c->err = "trim: mode must be 0, 1 or 2"; return ITSX_EINVAL; }
     if (nreads != c->nreads) { c->err = "trim: read count differs from the dereplicated set"; return ITSX_EINVAL; }
     if (c->npos != c->n_unique) { c->err = "trim: position table does not cover every unique sequence"; return ITSX_EINVAL; }

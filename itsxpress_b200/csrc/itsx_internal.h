@@ -177,6 +177,9 @@ struct itsx_ctx {
     // whole-path calls (itsx_run*): qualities of the resident reads, bounds and gathered slices of the last run
     DevBuf d_qual;
     bool qual_resident = false, r_gathered = false;
+    // streamed upload (itsx_reads_begin / append / end): reads and bases appended so far, every chunk brought qualities
+    bool stream_open = false, stream_qual = false;
+    int64_t stream_reads = 0, stream_bases = 0;
     DevBuf r_keep, r_lo, r_hi, r_ki, r_oo, r_os, r_oq, d_gather;
     int64_t r_nkept = 0, r_total = 0;
 
@@ -247,7 +250,7 @@ int search_build_seqs_from_host(itsx_ctx *c, const uint8_t *seq, const int64_t *
 int search_stage1(itsx_ctx *c);
 int search_stage2(itsx_ctx *c);
 int trim_bounds_dev(itsx_ctx *c, int mode, const int64_t *d_off_sliced, int64_t nreads,
-                    uint8_t *d_keep, int32_t *d_lo, int32_t *d_hi, int64_t *n_kept);
+                    uint8_t *d_keep, int32_t *d_lo, int32_t *d_hi, int64_t *n_kept, int64_t first = 0);
 int trim_gather_dev(itsx_ctx *c, const uint8_t *d_seq, const uint8_t *d_qual, const int64_t *d_off, int64_t nreads,
                     const uint8_t *d_keep, const int32_t *d_lo, const int32_t *d_hi,
                     int64_t *n_kept, int64_t *total, DevBuf &kept_index, DevBuf &out_off, DevBuf &out_seq,

@@ -99,11 +99,14 @@ gather_kernel(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
 }  // namespace
 
 int trim_bounds_dev(itsx_ctx *c, int mode, const int64_t *d_off_sliced, int64_t nreads,
-                    uint8_t *d_keep, int32_t *d_lo, int32_t *d_hi, int64_t *n_kept)
+                    uint8_t *d_keep, int32_t *d_lo, int32_t *d_hi, int64_t *n_kept, int64_t first)
 {
     cudaStream_t st = c->stream;
     if (!c->pos_valid) { c->err = "trim: no position table (run itsx_search or itsx_positions_set first)"; return ITSX_EINVAL; }
-    if (nreads != c->nreads) { c->err = "trim: read count differs from the dereplicated set"; return ITSX_EINVAL; }
+    if (first < 0 || nreads < 0 || first + nreads > c->nreads) {
+        c->err = "trim: read range outside the dereplicated set";
+        return ITSX_EINVAL;
+    }
     if (nreads == 0) { if (n_kept) *n_kept = 0; return ITSX_OK; }
     CUDA_TRY(c, c->d_flag.ensure((size_t)(nreads + 1) * 4));
     CUDA_TRY(c, c->d_scan.ensure((size_t)(nreads + 1) * 4));
@@ -111,8 +114,8 @@ int trim_bounds_dev(itsx_ctx *c, int mode, const int64_t *d_off_sliced, int64_t 
     CUDA_TRY(c, c->d_list2.ensure((size_t)(nreads + 1) * 8));
     int32_t *kf = c->d_flag.as<int32_t>(), *ks = c->d_scan.as<int32_t>();
     int64_t *ol = c->d_list.as<int64_t>(), *os = c->d_list2.as<int64_t>();
-    bounds_kernel<<<nblk(nreads, 256), 256, 0, st>>>(c->d_uid.as<int32_t>(), c->d_pos.as<int32_t>(), c->npos,
-                                                     d_off_sliced ? d_off_sliced : c->d_off.as<int64_t>(), nreads, mode,
+    bounds_kernel<<<nblk(nreads, 256), 256, 0, st>>>(c->d_uid.as<int32_t>() + first, c->d_pos.as<int32_t>(), c->npos,
+                                                     d_off_sliced ? d_off_sliced : c->d_off.as<int64_t>() + first, nreads, mode,
                                                      d_keep, d_lo, d_hi, kf, ol);
     CUDA_TRY(c, cudaMemsetAsync(kf + nreads, 0, 4, st));
     CUDA_TRY(c, cudaMemsetAsync(ol + nreads, 0, 8, st));

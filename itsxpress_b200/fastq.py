@@ -500,3 +500,120 @@ def write_compressed(path, data, gzipped=False, zstd_file=False, threads=None, n
             f.write(data)
     if n_records is not None:
         note_count(path, n_records)
+
+
+# ---- chunked reader / writer: a file never sits whole in host memory -------------------------------
+STREAM_CHUNK_BYTES = int(os.environ.get("ITSX_STREAM_CHUNK_BYTES", str(256 << 20)))
+
+
+def _raw_blocks(path, block):
+    """Decompressed bytes of ``path`` in blocks of about ``block`` bytes (plain, multi-member gzip, zstd)."""
+    if path.endswith(".gz"):
+        import zlib
+        with open(path, "rb") as f:
+            d = zlib.decompressobj(31)
+            while True:
+                raw = f.read(max(block // 4, 1 << 16))
+                if not raw:
+                    tail = d.flush()
+                    if tail:
+                        yield tail
+                    return
+                while raw:
+                    out = d.decompress(raw)
+                    if out:
+                        yield out
+                    if d.eof:                       # next gzip member
+                        raw = d.unused_data
+                        d = zlib.decompressobj(31)
+                    else:
+                        raw = b""
+    elif path.endswith(".zst"):
+        from . import _zstd
+        with open(path, "rb") as f:
+            for out in _zstd.decompress_stream(f, max(block // 4, 1 << 16)):
+                yield out
+    else:
+        with open(path, "rb") as f:
+            while True:
+                raw = f.read(block)
+                if not raw:
+                    return
+                yield raw
+
+
+def stream_fastq(path, chunk_bytes=None):
+    """Yield FastqBatch chunks of ``path`` in file order, each holding whole records and about ``chunk_bytes`` of
+    text.  Record boundaries are found by COUNTING lines from the start of the file (a quality line may begin with
+    '@', so no local pattern identifies a title line); the next block is read / inflated on a background thread while
+    the caller works on the current chunk."""
+    from concurrent.futures import ThreadPoolExecutor
+    chunk_bytes = chunk_bytes or STREAM_CHUNK_BYTES
+    blocks = _raw_blocks(path, chunk_bytes)
+    carry = b""
+    pool = ThreadPoolExecutor(1, thread_name_prefix="itsx-stream")
+    try:
+        nxt = pool.submit(next, blocks, None)
+        while True:
+            raw = nxt.result()
+            if raw is not None:
+                nxt = pool.submit(next, blocks, None)
+            data = carry + raw if raw is not None else carry
+            if raw is None:
+                if data.strip():
+                    yield parse_bytes(data)
+                return
+            if len(data) < chunk_bytes:
+                carry = data
+                continue
+            buf = np.frombuffer(data, np.uint8)
+            nl = np.flatnonzero(buf == 10)
+            whole = (len(nl) // 4) * 4
+            if whole == 0:
+                carry = data
+                continue
+            cut = int(nl[whole - 1]) + 1
+            carry = data[cut:]
+            yield parse_bytes(data[:cut])
+    finally:
+        pool.shutdown(wait=False, cancel_futures=True)
+
+
+class ChunkWriter:
+    """Appends FASTQ text chunk by chunk: plain, gzip (every chunk becomes independent members compressed on all cores:
+    a valid multi-member stream) or zstd (one frame per chunk: a valid multi-frame stream)."""
+
+    def __init__(self, path, gzipped=False, zstd_file=False):
+        self.path, self.gz, self.zst = path, gzipped, zstd_file
+        self.f = open(path, "wb")
+        self.n = 0
+
+    def write(self, data, n_records=0):
+        self.n += int(n_records)
+        if not data:
+            return
+        if self.gz:
+            import zlib
+            from concurrent.futures import ThreadPoolExecutor
+
+            def member(chunk):
+                co = zlib.compressobj(GZIP_LEVEL, zlib.DEFLATED, 31)
+                return co.compress(chunk) + co.flush()
+            step = 4 << 20
+            chunks = [data[i:i + step] for i in range(0, len(data), step)]
+            with ThreadPoolExecutor(max(1, os.cpu_count() or 1)) as ex:
+                for p in ex.map(member, chunks):
+                    self.f.write(p)
+        elif self.zst:
+            from . import _zstd
+            self.f.write(_zstd.compress(data))
+        else:
+            self.f.write(data)
+
+    def close(self):
+        if self.gz and self.f.tell() == 0:
+            import zlib
+            co = zlib.compressobj(GZIP_LEVEL, zlib.DEFLATED, 31)
+            self.f.write(co.compress(b"") + co.flush())          # an empty but valid gzip file
+        self.f.close()
+        note_count(self.path, self.n)

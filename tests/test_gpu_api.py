@@ -248,3 +248,23 @@ def test_pipeline_without_materialised_temp_files(tmp_path):
         outs.append(open(out, "rb").read())
         assert (os.path.getsize(s.dom_file) > 10000) == mat
     assert outs[0] == outs[1] and len(outs[0]) > 10000
+
+
+@pytest.mark.parametrize("suffix", ["", ".gz"])
+def test_cli_streamed_equals_whole_file(tmp_path, monkeypatch, suffix):
+    """the chunked path (ITSX_STREAM=1: itsx_reads_begin / append / end on the way in, two passes over the
+    input, itsx_trim_gather_range + an appending writer on the way out) writes the same bytes as the whole-file path --
+    the merged fixture through the CLI with chunks of ~20 records, plain and gzip output."""
+    from itsxpress_b200 import fastq as fq
+    from itsxpress_b200 import main as cli
+    from itsxpress_b200 import SeqSample
+    src = os.path.join(TD, "4774-1-MSITS3_merged.fastq")
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ITSX_STREAM", mode)
+        monkeypatch.setattr(fq, "STREAM_CHUNK_BYTES", 16_000)
+        out = str(tmp_path / ("o%s.fastq%s" % (mode, suffix)))
+        cli.main(args=cli.myparser().parse_args(["--fastq", src, "--single_end", "--outfile", out, "--region", "ITS2",
+                                                 "--taxa", "Metazoa", "--log", str(tmp_path / "l.txt")]))
+        outs[mode] = fq._open_bytes(out)
+    assert outs["0"] == outs["1"] and outs["0"].count(b"\n") // 4 > 150
