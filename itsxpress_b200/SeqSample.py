@@ -90,6 +90,7 @@ class _Session:
         self.pair_index = None
         self.pair_files = None     # (abspath R1, abspath R2)
         self.pair_batches = None   # (FastqBatch R1, FastqBatch R2)
+        self.sides_prefix = None   # (left, right) name prefixes the search already selected boundaries for
         self.streamed = False      # the reads went to the device chunk by chunk; no FastqBatch is held
         self.n_reads = 0
         self.chunk_bytes = None    # chunking of the streamed pass (the output pass repeats it)
@@ -280,18 +281,36 @@ class SeqSample:
             s = self._session
             resident = (s is not None and s.derep_gen == _GENERATION and
                         os.path.abspath(self.rep_file) in _SESSIONS and _SESSIONS[os.path.abspath(self.rep_file)] is s)
+            # Which profiles mark the left and which the right boundary is ItsPosition's business (it is told the region);
+            # but a runtime HMM file holds exactly the two name prefixes of its region (main.py:200-208: ITS2 3_/4_,
+            # ITS1 1_/2_, ALL 1_/4_), so they are read off the profile names here.  Knowing the sides during the search
+            # is what lets a large sample run in the compact row mode (itsx_search_params.keep_rows); a file with any
+            # other mix of prefixes is searched with every row kept and the sides set later.
+            pre = sorted({nm[:2] for nm in ctx.names})
+            sides_known = len(pre) == 2 and all(len(q) == 2 and q[0] in "1234" and q[1] == "_" for q in pre)
+            prm = _lib.default_params()
             if resident:
-                # representatives are already on the device, in first-occurrence order
-                ctx.set_sides(np.full(len(ctx.names), -1, np.int8))
-                ctx.search()
-                seq_ids = None
+                n_est = s.n_reads if s.streamed else s.batch.n
                 nseq = s.n_unique
             else:
                 seq_ids, seq, off = _read_fasta(self.rep_file)
+                n_est = nseq = len(seq_ids)
+            want_table = not getattr(s, "streamed", False) and (not resident or self._want_files(n_est))
+            if sides_known:
+                ctx.set_sides_by_prefix(pre[0], pre[1])
+                prm.keep_rows = 1 if want_table else int(os.environ.get("ITSX_KEEP_ROWS", "0"))
+            else:
+                ctx.set_sides(np.full(len(ctx.names), -1, np.int8))
+                prm.keep_rows = 1
+            if resident:
+                # representatives are already on the device, in first-occurrence order
+                ctx.search(prm)
+                seq_ids = None
+            else:
                 s = _Session()
-                ctx.search_seqs(seq, off)
-                nseq = len(seq_ids)
+                ctx.search_seqs(seq, off, prm)
                 self._session = s
+            s.sides_prefix = (pre[0], pre[1]) if sides_known else None
             _GENERATION += 1
             s.search_gen = _GENERATION
             if resident:
@@ -299,8 +318,7 @@ class SeqSample:
             s.names, s.nseq = list(ctx.names), nseq
             # a search that was not fed from a resident derep session (rep.fa written by vsearch --cluster_size, or
             # by another process) has no device-side hand-off to ItsPosition / Dedup: its table is always written
-            if not getattr(s, "streamed", False) and (not resident or
-                                                      self._want_files(s.batch.n if s.batch is not None else nseq)):
+            if want_table:
                 if seq_ids is None:
                     ids = s.ids
                     seq_ids = [ids[i] for i in s.first.tolist()]
@@ -451,8 +469,11 @@ class ItsPosition:
         s = _SESSIONS.get(os.path.abspath(domtable)) if isinstance(domtable, str) else None
         if s is not None and s.search_gen == _GENERATION and hasattr(self, "leftprefix"):
             ctx = get_context()
-            ctx.set_sides_by_prefix(self.leftprefix, self.rightprefix)
-            ctx.search_stage2()
+            if getattr(s, "sides_prefix", None) != (self.leftprefix, self.rightprefix):
+                # the search ran without (or with other) sides: apply this region's and redo the selection
+                ctx.set_sides_by_prefix(self.leftprefix, self.rightprefix)
+                ctx.search_stage2()
+                s.sides_prefix = (self.leftprefix, self.rightprefix)
             self._dev = ctx.positions(s.nseq)
             self._session = s
         else:

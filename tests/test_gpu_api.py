@@ -268,3 +268,23 @@ def test_cli_streamed_equals_whole_file(tmp_path, monkeypatch, suffix):
                                                  "--taxa", "Metazoa", "--log", str(tmp_path / "l.txt")]))
         outs[mode] = fq._open_bytes(out)
     assert outs["0"] == outs["1"] and outs["0"].count(b"\n") // 4 > 150
+
+
+def test_cli_compact_row_mode_equals_full_table(tmp_path, monkeypatch):
+    """Above 200 000 uniques the search keeps only undecided rows (itsx_search_params.keep_rows = 2), which needs the
+    boundary sides DURING the search: _search reads them off the runtime HMM's two name prefixes and ItsPosition then
+    takes the positions without a second selection pass.  Forced here on the fixture (ITSX_KEEP_ROWS=2, temp files not
+    materialised): same output bytes as the default path."""
+    from itsxpress_b200 import fastq as fq
+    from itsxpress_b200 import main as cli
+    src = os.path.join(TD, "4774-1-MSITS3_merged.fastq")
+    outs = {}
+    from itsxpress_b200 import SeqSample
+    monkeypatch.setattr(SeqSample, "TEMP_FILE_POLICY", "never")
+    for mode in ("1", "2"):
+        monkeypatch.setenv("ITSX_KEEP_ROWS", mode)
+        out = str(tmp_path / ("o%s.fastq" % mode))
+        cli.main(args=cli.myparser().parse_args(["--fastq", src, "--single_end", "--outfile", out, "--region", "ITS2",
+                                                 "--taxa", "Metazoa", "--log", str(tmp_path / "l.txt")]))
+        outs[mode] = open(out, "rb").read()
+    assert outs["1"] == outs["2"] and outs["1"].count(b"\n") // 4 > 150
