@@ -694,8 +694,8 @@ struct MdArgs {
 struct MdStreams { uint32_t x[MD_NSAMPLES]; };
 __host__ __device__ inline size_t md_clust_bytes(int maxrows)
 {
-    // per warp: n2sc per region row
-    size_t b = (size_t)(maxrows + 1) * 4;
+    // per warp: acc + cover count per row, raw (segment id, trace), last trace and trace count per cluster
+    size_t b = (size_t)(maxrows + 1) * 8 + (size_t)MD_MAXSEG * (4 + 2 + 2);
     return (b + 255) / 256 * 256;
 }
 __device__ __forceinline__ double md_rng(uint32_t &x)
@@ -980,27 +980,11 @@ __global__ void __launch_bounds__(128) mdtrace_kernel(const MdArgs a, const __gr
 // visited in trace order (float sums keep the oracle's order); the lanes share the search for an equal segment, the
 // positions of a domain, the link tests of the component walk and the endpoint counts. ----
 constexpr int MDC_WARPS = 4;
-constexpr int MDC_TILE = 32;                   // traces staged per tile
-constexpr int MDC_JP = 8;                      // positions per lane and pass (a pass covers 256 positions)
-static_assert(sizeof(MdTrace) == 100, "trace record layout");
-constexpr int MDC_CAP = MD_NSAMPLES * MD_MAXTDOM;     // 800 samples at most (< MD_MAXSEG: that cap never binds)
 struct MdClustSmem {
-    MdSeg    seg[MDC_CAP];
-    int16_t  asg[MDC_CAP];
-    int16_t  stack[MDC_CAP];
-    uint16_t rawid[MDC_CAP];                   // distinct-segment id of every sample, trace order
-    uint16_t rawtr[MDC_CAP];                   // its trace
-    union {
-        uint32_t stage[MDC_TILE * 25];         // 32 trace records (100 B each) while the sums are built ...
-        int32_t  ntrc[MDC_CAP];                // ... traces per cluster afterwards
-    };
+    MdSeg   seg[MD_MAXSEG];
+    int16_t asg[MD_MAXSEG];
+    int16_t stack[MD_MAXSEG];
 };
-static_assert(MDC_TILE * 25 >= MDC_CAP, "ntrc aliases the staging tile");
-// Round 1's version walked the 200 trace records with two dependent global loads per sample, kept the per-position sums
-// in global scratch (a read-modify-write round trip per sample) and counted traces per cluster through a global array on
-// one lane: 0.42 ms per region, IPC 0.09 per warp (ncu r2a: long_scoreboard 3.7, wait 2.8 per issue).  Here a tile of
-// trace records is staged in shared memory with coalesced loads, a lane owns positions (sums in registers, trace order
-// kept), and the per-cluster trace counts are shared-memory atomics over all samples.
 __global__ void __launch_bounds__(MDC_WARPS * 32) mdclust_kernel(const MdArgs a)
 {
     constexpr unsigned FULL = 0xffffffffu;
@@ -1009,105 +993,71 @@ __global__ void __launch_bounds__(MDC_WARPS * 32) mdclust_kernel(const MdArgs a)
     const int warp = blockIdx.x * MDC_WARPS + wid, nwarps = gridDim.x * MDC_WARPS;
     MdClustSmem &sm = ((MdClustSmem *)mdc_smem)[wid];
     char *scr = a.scratch + (size_t)warp * a.per_thread;
-    float *acc = (float *)scr;                               // [maxrows + 1]: n2sc per region position
+    float *acc = (float *)scr;                               // [maxrows + 1]
+    int32_t *cov = (int32_t *)(acc + (a.maxrows + 1));       // [maxrows + 1]
+    uint16_t *rawid = (uint16_t *)(cov + (a.maxrows + 1)), *rawtr = rawid + MD_MAXSEG;
+    int16_t *lasttr = (int16_t *)(rawtr + MD_MAXSEG), *ntrc = lasttr + MD_MAXSEG;
+    const int degen[16] = {1, 2, 4, 8, 5, 10, 3, 12, 6, 9, 11, 14, 7, 13, 15, 0};
     for (int r = a.r0 + warp; r < a.r1; r += nwarps) {
         const MdRegion g = md_region(a, r);
         const int Ld = g.Ld, ireg = g.ireg;
-        const uint32_t *trw = (const uint32_t *)(a.trace + (size_t)(r - a.r0) * MD_NSAMPLES);
+        const MdTrace *tr = a.trace + (size_t)(r - a.r0) * MD_NSAMPLES;
+        for (int pos = lane; pos <= Ld; pos += 32) { acc[pos] = 0.f; cov[pos] = 0; }
+        __syncwarp();
         int nseg = 0, nraw = 0;
-        for (int p0 = 0; p0 < Ld; p0 += 32 * MDC_JP) {
-            // this lane's positions of the pass: p0 + 1 + lane + 32 j; member mask of the residue (ACGT bits) per position
-            float accr[MDC_JP];
-            int covr[MDC_JP], msk[MDC_JP];
-#pragma unroll
-            for (int j = 0; j < MDC_JP; j++) {
-                const int pos = p0 + 1 + lane + 32 * j;
-                accr[j] = 0.f; covr[j] = 0;
-                int m = -1;                                            // position outside the region
-                if (pos <= Ld) {
-                    const uint32_t x = residue_at(g.w, ireg - 1 + pos - 1);
-                    // ACGT RYMK SWHB VDN*: members of every code as a 4-bit mask (A = 1, C = 2, G = 4, T = 8), 0 = other
-                    m = (int)((0x0FD7EB96C3A58421ull >> (4 * x)) & 15ull);
-                }
-                msk[j] = m;
-            }
-            for (int t0 = 0; t0 < MD_NSAMPLES; t0 += MDC_TILE) {
-                const int tn = min(MDC_TILE, MD_NSAMPLES - t0);
-                __syncwarp();
-                for (int wq = lane; wq < tn * 25; wq += 32) sm.stage[wq] = trw[(size_t)t0 * 25 + wq];
-                __syncwarp();
-                for (int tt = 0; tt < tn; tt++) {
-                    const uint32_t *rec = sm.stage + tt * 25;
-                    const int nd = (int)rec[0];
-                    for (int d = nd - 1; d >= 0; d--) {          // left to right
-                        const uint32_t w0 = rec[1 + d * 6], w1 = rec[2 + d * 6];
-                        const int from = (int)(w0 & 0xffffu), to = (int)(w0 >> 16);
-                        if (p0 == 0 && nraw < MD_MAXSEG) {
-                            // distinct segments of the ensemble: (i, j, k, m) and how many samples drew it
-                            const uint16_t si = (uint16_t)(from + ireg - 1), sj = (uint16_t)(to + ireg - 1);
-                            const unsigned long long want = (unsigned long long)si | ((unsigned long long)sj << 16) |
-                                                            ((unsigned long long)(w1 & 0xffffu) << 32);
-                            int u = -1;
-                            for (int u0 = 0; u0 < nseg && u < 0; u0 += 32) {
-                                const bool hit = u0 + lane < nseg &&
-                                    ((*(const unsigned long long *)&sm.seg[u0 + lane]) & 0xffffffffffffull) == want;
-                                const unsigned mm = __ballot_sync(FULL, hit);
-                                if (mm) u = u0 + __ffs(mm) - 1;
-                            }
-                            if (lane == 0) {
-                                if (u < 0) {
-                                    MdSeg sg;
-                                    sg.i = si; sg.j = sj; sg.k = (uint8_t)(w1 & 0xffu); sg.m = (uint8_t)((w1 >> 8) & 0xffu); sg.n = 1;
-                                    sm.seg[nseg] = sg;
-                                    sm.rawid[nraw] = (uint16_t)nseg;
-                                } else {
-                                    sm.seg[u].n++;
-                                    sm.rawid[nraw] = (uint16_t)u;
-                                }
-                                sm.rawtr[nraw] = (uint16_t)(t0 + tt);
-                            }
-                            if (u < 0) nseg++;
-                            nraw++;
-                            __syncwarp();
-                        }
-                        // null2 odds of this domain on the positions it covers (sums stay in trace order per position)
-                        if (from <= p0 + 32 * MDC_JP && to > p0) {
-                            const float q0 = __uint_as_float(rec[3 + d * 6]), q1 = __uint_as_float(rec[4 + d * 6]),
-                                        q2 = __uint_as_float(rec[5 + d * 6]), q3 = __uint_as_float(rec[6 + d * 6]);
-#pragma unroll
-                            for (int j = 0; j < MDC_JP; j++) {
-                                const int pos = p0 + 1 + lane + 32 * j;
-                                const int m = msk[j];
-                                if (m < 0 || pos < from || pos > to) continue;
-                                float v;
-                                if (m == 0) v = 1.0f;
-                                else if ((m & (m - 1)) == 0) v = (m & 1) ? q0 : (m & 2) ? q1 : (m & 4) ? q2 : q3;
-                                else {
-                                    float sa = 0.f;
-                                    int na = 0;
-                                    if (m & 1) { sa += q0; na++; }
-                                    if (m & 2) { sa += q1; na++; }
-                                    if (m & 4) { sa += q2; na++; }
-                                    if (m & 8) { sa += q3; na++; }
-                                    v = sa / (float)na;
-                                }
-                                accr[j] += v;
-                                covr[j]++;
-                            }
-                        }
+        for (int t = 0; t < MD_NSAMPLES; t++) {
+            const int nd = tr[t].nd;
+            for (int d = nd - 1; d >= 0; d--) {          // left to right
+                const MdDom dd = tr[t].d[d];
+                if (nraw < MD_MAXSEG) {
+                    const uint16_t si = (uint16_t)(dd.from + ireg - 1), sj = (uint16_t)(dd.to + ireg - 1);
+                    int u = -1;
+                    const unsigned long long want = (unsigned long long)si | ((unsigned long long)sj << 16) |
+                                                    ((unsigned long long)dd.k << 32) | ((unsigned long long)dd.m << 40);
+                    for (int u0 = 0; u0 < nseg && u < 0; u0 += 32) {
+                        const bool hit = u0 + lane < nseg &&
+                            ((*(const unsigned long long *)&sm.seg[u0 + lane]) & 0xffffffffffffull) == want;
+                        const unsigned m = __ballot_sync(FULL, hit);
+                        if (m) u = u0 + __ffs(m) - 1;
                     }
+                    if (lane == 0) {
+                        if (u < 0) {
+                            MdSeg sg;
+                            sg.i = si; sg.j = sj; sg.k = dd.k; sg.m = dd.m; sg.n = 1;
+                            sm.seg[nseg] = sg;
+                            rawid[nraw] = (uint16_t)nseg;
+                        } else {
+                            sm.seg[u].n++;
+                            rawid[nraw] = (uint16_t)u;
+                        }
+                        rawtr[nraw] = (uint16_t)t;
+                    }
+                    if (u < 0) nseg++;
+                    nraw++;
+                    __syncwarp();
                 }
-            }
-            // n2sc of this pass' positions
-#pragma unroll
-            for (int j = 0; j < MDC_JP; j++) {
-                const int pos = p0 + 1 + lane + 32 * j;
-                if (pos <= Ld)
-                    acc[pos] = logf_via_double((accr[j] + (float)(MD_NSAMPLES - covr[j])) / (float)MD_NSAMPLES);
+                for (int pos = dd.from + lane; pos <= dd.to; pos += 32) {
+                    const uint32_t x = residue_at(g.w, ireg - 1 + pos - 1);
+                    float v;
+                    if (x < 4) v = dd.n2[x];
+                    else if (x == 15) v = 1.0f;
+                    else {
+                        float sa = 0.f;
+                        int na = 0;
+                        for (int y = 0; y < 4; y++)
+                            if (degen[x] & (1 << y)) { sa += dd.n2[y]; na++; }
+                        v = sa / (float)na;
+                    }
+                    acc[pos] += v;
+                    cov[pos]++;
+                }
+                __syncwarp();        // the next sample may touch the same positions from other lanes
             }
         }
+        // n2sc of the region (kept in acc[]); the sum over the region in position order
+        for (int pos = 1 + lane; pos <= Ld; pos += 32)
+            acc[pos] = logf_via_double((acc[pos] + (float)(MD_NSAMPLES - cov[pos])) / (float)MD_NSAMPLES);
         __syncwarp();
-        // the sum of n2sc over the region in position order
         float regsum = 0.f;
         if (lane == 0)
             for (int pos = 1; pos <= Ld; pos++) regsum += acc[pos];
@@ -1138,23 +1088,19 @@ __global__ void __launch_bounds__(MDC_WARPS * 32) mdclust_kernel(const MdArgs a)
             }
             nc++;
         }
-        // traces that contribute to each cluster: a sample counts iff no earlier sample of ITS trace (they are
-        // consecutive, at most MD_MAXTDOM of them) fell into the same cluster
-        for (int c = lane; c < nc; c += 32) sm.ntrc[c] = 0;
-        __syncwarp();
-        for (int q = lane; q < nraw; q += 32) {
-            const int c = sm.asg[sm.rawid[q]];
-            const int tq = sm.rawtr[q];
-            bool first = true;
-            for (int b2 = 1; b2 < MD_MAXTDOM && q - b2 >= 0; b2++)
-                if (sm.rawtr[q - b2] == tq && sm.asg[sm.rawid[q - b2]] == c) first = false;
-            if (first) atomicAdd(&sm.ntrc[c], 1);
+        // traces that contribute to each cluster (samples are in trace order)
+        if (lane == 0) {
+            for (int c = 0; c < nc; c++) { lasttr[c] = -1; ntrc[c] = 0; }
+            for (int q = 0; q < nraw; q++) {
+                const int c = sm.asg[rawid[q]];
+                if (lasttr[c] != (int16_t)rawtr[q]) { ntrc[c]++; lasttr[c] = (int16_t)rawtr[q]; }
+            }
         }
         __syncwarp();
         int ci[16], cj[16];
         int nenv = 0;
         for (int c = 0; c < nc; c++) {
-            if ((float)sm.ntrc[c] / (float)MD_NSAMPLES < 0.25f) continue;
+            if ((float)ntrc[c] / (float)MD_NSAMPLES < 0.25f) continue;
             int ninc = 0;
             int imin = 1 << 30, imax = 0, jmin = 1 << 30, jmax = 0;
             for (int q = lane; q < nseg; q += 32) {
