@@ -53,7 +53,7 @@ typedef struct itsx_ctx itsx_ctx;
 typedef struct {
     float  T;        /* -T 10        per-sequence bit-score threshold              */
     double F1;       /* --F1 1e-6    MSV + bias filter P-value                      */
-    double F2;       /* --F2 1e-6    Viterbi filter (never runs when F1 == F2)      */
+    double F2;       /* --F2 1e-6    Viterbi filter: runs on F2 < P(MSV + bias) <= F1, i.e. never when F1 == F2 */
     double F3;       /* --F3 1e-6    Forward filter P-value                         */
     double domE;     /* 10.0         per-domain conditional E-value (hmmsearch default) */
     int32_t resolve_multidomain; /* 1 (default): regions flagged multidomain are resolved like p7_domaindef does
@@ -101,6 +101,10 @@ typedef struct {
     /* selected left / right boundaries (ItsPosition winners) whose envelope came out of a region flagged
      * multidomain -- the only rows whose coordinates depend on the stochastic-traceback ensemble */
     int64_t n_selected_multidomain;
+    /* Viterbi filter (runs only when F2 < F1): pairs it was run on, pairs left after it, DP cells, device time */
+    int64_t n_vit_run, n_past_vit;
+    double  vit_cells;
+    float   ms_vit, reserved2;
 } itsx_search_stats;
 
 typedef struct {

@@ -34,7 +34,8 @@ class SearchStats(C.Structure):
                [(n, C.c_double) for n in ("msv_cells", "bias_rows", "fwd_cells", "bck_cells", "env_cells")] + \
                [(n, C.c_float) for n in ("ms_msv", "ms_bias", "ms_fwd", "ms_mdom", "ms_env", "ms_final", "ms_total",
                                           "reserved")] + \
-               [("n_selected_multidomain", C.c_int64)]
+               [("n_selected_multidomain", C.c_int64), ("n_vit_run", C.c_int64), ("n_past_vit", C.c_int64),
+                ("vit_cells", C.c_double), ("ms_vit", C.c_float), ("reserved2", C.c_float)]
 
     def asdict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

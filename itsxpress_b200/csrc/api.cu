@@ -437,11 +437,7 @@ static int set_params(itsx_ctx *c, const itsx_search_params *prm)
 {
     if (prm) c->prm = *prm;
     else itsx_search_default_params(&c->prm);
-    if (c->prm.F2 < c->prm.F1) {
-        // the Viterbi filter would run for F1 < P <= ... only when F2 < F1; the reference never asks for it
-        c->err = "search: F2 < F1 (Viterbi filter stage) is not supported; the reference passes F1 == F2";
-        return ITSX_EINVAL;
-    }
+    if (!(c->prm.F1 >= 0 && c->prm.F2 >= 0 && c->prm.F3 >= 0)) { c->err = "search: negative filter threshold"; return ITSX_EINVAL; }
     return ITSX_OK;
 }
 int itsx_search_stage1(itsx_ctx *c, const itsx_search_params *prm)

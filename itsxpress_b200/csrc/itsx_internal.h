@@ -110,6 +110,7 @@ struct itsx_ctx {
     DevBuf d_etab;        // float  [P][ITSX_MAXM+1][16]: match odds
     DevBuf d_pscal;       // ProfScalars [P]
     DevBuf d_logsum;      // float [16000] p7_FLogsum table
+    DevBuf d_vtab, d_xwmove, d_vneed, d_vpass;   // Viterbi filter: int32 [P][VIT_WORDS] tables, int16 xw_move per length, per-entry flags
     DevBuf d_mdtab;       // float [P][ITSX_MAXM+2][8]: transitions out of node k + B->M_k (multidomain resolver)
     DevBuf d_mdlist, d_envdc, d_n2reg, d_mdscratch, d_mdreg, d_mdcell, d_mdtrace, d_mdres;   // multidomain worklist (+ count), per-envelope trace domcorrection, per-entry region n2sc sum
     std::vector<ProfConst> pconst;   // host copies handed to the per-profile launches
@@ -194,7 +195,7 @@ struct itsx_ctx {
 };
 
 enum { CNT_COLLIDE = 0, CNT_PAST_FWD, CNT_FWD_ROWS, CNT_BCK_ROWS, CNT_ENV_ROWS, CNT_DOM_OVERFLOW, CNT_MULTI,
-       CNT_HITS_REPORTED, CNT_DOM_REPORTED, CNT_MAX_ENVLEN, CNT_BIAS_ROWS, CNT_NDOM, CNT_SEL_MULTI, CNT_CERTAIN, CNT_N };
+       CNT_HITS_REPORTED, CNT_DOM_REPORTED, CNT_MAX_ENVLEN, CNT_BIAS_ROWS, CNT_NDOM, CNT_SEL_MULTI, CNT_CERTAIN, CNT_VIT_ROWS, CNT_VIT_RUN, CNT_N };
 
 #define CUDA_TRY(ctx, call)                                                                   \
     do {                                                                                      \

@@ -254,7 +254,7 @@ bias_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ n_ptr,
             int64_t s0, int ns,
             const uint32_t *__restrict__ seqw, const int64_t *__restrict__ woff, const int32_t *__restrict__ seqlen,
             const ProfScalars *__restrict__ pscal, const uint8_t *__restrict__ res,
-            const uint8_t *__restrict__ tjbtab, double F1, float *__restrict__ filtersc, uint8_t *__restrict__ flag2,
+            const uint8_t *__restrict__ tjbtab, double F1, double F2, float *__restrict__ filtersc, uint8_t *__restrict__ flag2,
             unsigned long long *__restrict__ counters)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,6 +298,7 @@ bias_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ n_ptr,
     const float fsc = logsc + (float)L * logf_via_double(p1) + logf_via_double(1.f - p1);
     filtersc[e] = fsc;
     bool pass = true;
+    double Pbias = 0.0;                 // an overflowed MSV score is +inf: P = 0
     const int r = res[(size_t)p * ns + sl];
     if (r != 255) {
         const int tjb = tjbtab[L];
@@ -305,10 +306,110 @@ bias_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ n_ptr,
         sc /= ps.scale_b;
         sc -= 3.0f;
         float seq_score = (float)((double)(sc - fsc) / kLn2);
-        pass = gumbel_surv((double)seq_score, (double)ps.ev[EV_MMU], (double)ps.ev[EV_MLAMBDA]) <= F1;
+        Pbias = gumbel_surv((double)seq_score, (double)ps.ev[EV_MMU], (double)ps.ev[EV_MLAMBDA]);
+        pass = Pbias <= F1;
     }
-    flag2[e] = pass ? 1 : 0;
+    flag2[e] = pass ? (Pbias > F2 ? 2 : 1) : 0;      // 2: p7_Pipeline would run the Viterbi filter on it (P > F2)
     if (L > 0) atomicAdd(&counters[CNT_BIAS_ROWS], (unsigned long long)L);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: Viterbi filter (HMMER impl_*/vitfilter.c, restated in oracle/ora_hmm.c:viterbi_filter): 16-bit scores in
+// 1/500-bit units around base 12000, saturating adds (-32768 = -inf), N / C / J loops free with a -3 nat correction,
+// overflow (a match cell at 32767) counts as a pass.  p7_Pipeline runs it only for  F2 < P(MSV + bias) <= F1, which the
+// reference's --F1 1e-6 --F2 1e-6 never allows (SeqSample.py:191-209); it is here so that the library is the whole
+// hmmsearch cascade under any thresholds (HMMER's own defaults are 0.02 / 1e-3 / 1e-5).  Thread per worklist entry of
+// the launch's profile, the row in registers like fb_kernel; max-plus in integers, so any evaluation order is bit-exact:
+// M and I descend in place, the D chain ascends.  add-with-floor = one VIADDMNMX; the upper clamp only matters where the
+// emission is added, and a row whose best match cell reaches 32767 ends the sequence.
+struct VitArgs {
+    const int32_t *list;      // this profile's slice of the pair list
+    const float   *filtersc;
+    const uint8_t *need;      // 2: P(bias) > F2, run the filter; 1: passes without it
+    int            count;
+    const int32_t *order;
+    int64_t        s0;
+    int            ns, prof;
+    const uint32_t *seqw;
+    const int64_t  *woff;
+    const int32_t  *seqlen;
+    const int32_t  *vtab;     // this profile: [MAXM + 2][8] transition words, then [16][48] emission words
+    const int16_t  *xwmove;   // per target length
+    int             xw_E;
+    float           vmu, vlambda;
+    double          F2;
+    uint8_t        *pass;     // out, per entry
+    unsigned long long *counters;
+};
+constexpr int VIT_T = 0, VIT_E = (MAXM + 2) * 8, VIT_WORDS = (MAXM + 2) * 8 + 16 * 48;
+enum { VT_BM = 0, VT_MM, VT_IM, VT_DM, VT_MD, VT_DD, VT_MI, VT_II };
+
+__global__ void __launch_bounds__(128, 3) vit_kernel(const VitArgs a)
+{
+    __shared__ __align__(16) int32_t s_v[VIT_WORDS];
+    for (int t = threadIdx.x; t < VIT_WORDS; t += blockDim.x) s_v[t] = a.vtab[t];
+    __syncthreads();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.count) return;
+    if (a.need[e] != 2) { a.pass[e] = 1; return; }
+    const int idx = a.list[e];
+    const int sl = idx - a.prof * a.ns;
+    const int64_t s = a.order[a.s0 + sl];
+    const int L = a.seqlen[s];
+    const uint32_t *w = a.seqw + a.woff[s];
+    constexpr int NEG = -32768;
+    int Mv[MAXM + 1], Iv[MAXM + 1], Dv[MAXM + 1];
+#pragma unroll
+    for (int k = 0; k <= MAXM; k++) Mv[k] = Iv[k] = Dv[k] = NEG;
+    const int xw_move = a.xwmove[L];
+    int xN = 12000, xB = xN + xw_move, xJ = NEG, xC = NEG;
+    bool ovf = false;
+    for (int i = 1; i <= L && !ovf; i++) {
+        const int32_t *em = s_v + VIT_E + residue_at(w, i - 1) * 48;
+        int xE = NEG;
+        // (the tables are loop-invariant shared-memory reads: without this fence the compiler hoists all 368 of them
+        // out of the row loop and spills them)
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int k = MAXM; k >= 1; k--) {
+            const int4 ta = *(const int4 *)(s_v + VIT_T + (k - 1) * 8), tb = *(const int4 *)(s_v + VIT_T + (k - 1) * 8 + 4);
+            const int4 ua = *(const int4 *)(s_v + VIT_T + k * 8), ub = *(const int4 *)(s_v + VIT_T + k * 8 + 4);
+            // slots: a = (BM, MM, IM, DM), b = (MD, DD, MI, II)
+            int sv = __viaddmax_s32(xB, ua.x, NEG);
+            sv = max(sv, __viaddmax_s32(Mv[k - 1], ta.y, NEG));
+            sv = max(sv, __viaddmax_s32(Iv[k - 1], ta.z, NEG));
+            sv = max(sv, __viaddmax_s32(Dv[k - 1], ta.w, NEG));
+            sv = __viaddmax_s32(sv, em[k], NEG);
+            const int iv = max(__viaddmax_s32(Mv[k], ub.z, NEG), __viaddmax_s32(Iv[k], ub.w, NEG));
+            Mv[k] = sv; Iv[k] = iv;
+            xE = max(xE, sv);
+            (void)tb;
+        }
+        int dcur = NEG;
+#pragma unroll
+        for (int k = 1; k <= MAXM; k++) {
+            const int4 tb = *(const int4 *)(s_v + VIT_T + (k - 1) * 8 + 4);
+            dcur = max(__viaddmax_s32(Mv[k - 1], tb.x, NEG), __viaddmax_s32(dcur, tb.y, NEG));
+            Dv[k] = dcur;
+        }
+        if (xE >= 32767) { ovf = true; break; }
+        xC = max(xC, xE + a.xw_E);
+        xJ = max(xJ, xE + a.xw_E);
+        xB = max(xJ + xw_move, xN + xw_move);
+    }
+    bool pass = true;
+    if (!ovf) {
+        pass = false;
+        if (xC > NEG) {
+            const float scale_w = 500.0f / (float)kLn2;
+            const float sc = ((float)xC + (float)xw_move - 12000.0f) / scale_w - 3.0f;
+            const float seq_score = (float)((double)(sc - a.filtersc[e]) / kLn2);
+            pass = gumbel_surv((double)seq_score, (double)a.vmu, (double)a.vlambda) <= a.F2;
+        }
+    }
+    a.pass[e] = pass ? 1 : 0;
+    atomicAdd(&a.counters[CNT_VIT_ROWS], (unsigned long long)L);
+    atomicAdd(&a.counters[CNT_VIT_RUN], 1ull);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1875,6 +1976,35 @@ int search_upload_profiles(itsx_ctx *c)
         for (int i = 0; i < 6; i++) q.ev[i] = h.ev[i];
         for (int x = 0; x < 16; x++) { q.eo[x][0] = h.eo[x][0]; q.eo[x][1] = h.eo[x][1]; }
     }
+    // Viterbi filter tables (oracle/ora_hmm.c:viterbi_filter; HMMER p7_oprofile word scores): wordify(ln p), -32768 = -inf
+    {
+        auto wordify = [](float sc) -> int32_t {
+            const float scale_w = 500.0f / (float)kLn2;
+            if (!(sc > -INFINITY)) return -32768;
+            sc = roundf(scale_w * sc);
+            if (sc >= 32767.0f) return 32767;
+            if (sc <= -32768.0f) return -32768;
+            return (int32_t)sc;
+        };
+        std::vector<int32_t> vtab((size_t)std::max(P, 1) * VIT_WORDS, -32768);
+        for (int p = 0; p < P; p++) {
+            const HostProfile &h = c->prof[p];
+            int32_t *T = vtab.data() + (size_t)p * VIT_WORDS + VIT_T, *E = vtab.data() + (size_t)p * VIT_WORDS + VIT_E;
+            for (int k = 1; k <= h.M; k++) {
+                const float *t = &h.tp[(size_t)k * 7];
+                T[k * 8 + VT_BM] = wordify(logf(h.bm[k]));
+                T[k * 8 + VT_MM] = wordify(logf(t[T_MM])); T[k * 8 + VT_IM] = wordify(logf(t[T_IM]));
+                T[k * 8 + VT_DM] = wordify(logf(t[T_DM])); T[k * 8 + VT_MD] = wordify(logf(t[T_MD]));
+                T[k * 8 + VT_DD] = wordify(logf(t[T_DD])); T[k * 8 + VT_MI] = wordify(logf(t[T_MI]));
+                T[k * 8 + VT_II] = wordify(logf(t[T_II]));
+                if (T[k * 8 + VT_II] == 0) T[k * 8 + VT_II] = -1;       // an II cost of 0 is not allowed in the filter
+                for (int x = 0; x < 16; x++) E[x * 48 + k] = wordify(h.msc[(size_t)k * 16 + x]);
+            }
+        }
+        CUDA_TRY(c, c->d_vtab.ensure(vtab.size() * 4));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_vtab.p, vtab.data(), vtab.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+    }
     CUDA_TRY(c, c->d_mdtab.ensure(mdtab.size() * 4));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_mdtab.p, mdtab.data(), mdtab.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(c, c->d_msvtab.ensure(msvtab.size() * 4));
@@ -1955,6 +2085,17 @@ static int build_seqs(itsx_ctx *c, const uint8_t *d_ascii, const int64_t *d_off,
         float p1 = (float)L / (float)(L + 1);
         nullsc[L] = (float)((float)L * log((double)p1) + log(1. - (double)p1));
         tjb[L] = msv_unbiased_byteify(scale_b, logf(3.0f / (float)(L + 3)));
+    }
+    {
+        std::vector<int16_t> xw((size_t)lmax + 1);
+        const float scale_w = 500.0f / (float)kLn2;
+        for (int L = 0; L <= lmax; L++) {
+            float sc = roundf(scale_w * logf(3.0f / ((float)L + 3.0f)));
+            xw[L] = (int16_t)(sc <= -32768.0f ? -32768 : sc >= 32767.0f ? 32767 : (int)sc);
+        }
+        CUDA_TRY(c, c->d_xwmove.ensure(((size_t)lmax + 1) * 2));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_xwmove.p, xw.data(), xw.size() * 2, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
     }
     CUDA_TRY(c, c->d_nullsc.ensure(((size_t)lmax + 1) * 4));
     CUDA_TRY(c, c->d_tjb.ensure((size_t)lmax + 1));
@@ -2148,7 +2289,7 @@ int search_stage1(itsx_ctx *c)
         bias_kernel<<<nblk(n1, 128), 128, 0, st>>>(c->d_list.as<int32_t>(), d_nsel, d_order, s0, ns, c->d_seqw.as<uint32_t>(),
                                                    c->d_seqwoff.as<int64_t>(), c->d_seqlen.as<int32_t>(),
                                                    c->d_pscal.as<ProfScalars>(), c->d_msvres.as<uint8_t>(),
-                                                   c->d_tjb.as<uint8_t>(), c->prm.F1, c->d_filtersc.as<float>(),
+                                                   c->d_tjb.as<uint8_t>(), c->prm.F1, c->prm.F2, c->d_filtersc.as<float>(),
                                                    c->d_ndom.as<uint8_t>(), cnt);
         CUDA_TRY(c, c->d_list2.ensure((size_t)n1 * 4 + 16));
         CUDA_TRY(c, c->d_fsc2.ensure((size_t)n1 * 4 + 16));
@@ -2178,6 +2319,77 @@ int search_stage1(itsx_ctx *c)
             cudaEventElapsedTime(&ms, ev[1], ev[2]); acc_ms[0] += ms;
             cudaEventElapsedTime(&ms, ev[2], ev[3]); acc_ms[1] += ms;
         }
+        if (n2 == 0) continue;
+
+        // ---- Viterbi filter: only for F2 < P(MSV + bias) <= F1 (never under the reference's F1 == F2) ----
+        if (c->prm.F2 < c->prm.F1) {
+            cudaEvent_t v0, v1;
+            CUDA_TRY(c, cudaEventCreate(&v0));
+            CUDA_TRY(c, cudaEventCreate(&v1));
+            CUDA_TRY(c, cudaEventRecord(v0, st));
+            // the "needs the filter" marks of the surviving entries, compacted like the list itself
+            CUDA_TRY(c, c->d_vneed.ensure((size_t)n1 + 16));
+            CUDA_TRY(c, c->d_vpass.ensure((size_t)n2 + 16));
+            int32_t *d_nsel3 = d_nsel + 2;
+            size_t tv = 0;
+            cub::DeviceSelect::Flagged(nullptr, tv, c->d_ndom.as<uint8_t>(), c->d_ndom.as<uint8_t>(), c->d_vneed.as<uint8_t>(),
+                                       d_nsel3, n1, st);
+            CUDA_TRY(c, c->d_tmp.ensure(tv));
+            cub::DeviceSelect::Flagged(c->d_tmp.p, tv, c->d_ndom.as<uint8_t>(), c->d_ndom.as<uint8_t>(),
+                                       c->d_vneed.as<uint8_t>(), d_nsel3, n1, st);
+            for (int p = 0; p < P; p++) {
+                const int b0 = h_bounds[p], cntp = h_bounds[p + 1] - b0;
+                if (cntp <= 0) continue;
+                VitArgs va;
+                va.list = c->d_list2.as<int32_t>() + b0; va.filtersc = c->d_fsc2.as<float>() + b0;
+                va.need = c->d_vneed.as<uint8_t>() + b0; va.count = cntp;
+                va.order = d_order; va.s0 = s0; va.ns = ns; va.prof = p;
+                va.seqw = c->d_seqw.as<uint32_t>(); va.woff = c->d_seqwoff.as<int64_t>(); va.seqlen = c->d_seqlen.as<int32_t>();
+                va.vtab = c->d_vtab.as<int32_t>() + (size_t)p * VIT_WORDS;
+                va.xwmove = c->d_xwmove.as<int16_t>();
+                {
+                    const float scale_w = 500.0f / (float)kLn2;
+                    va.xw_E = (int)roundf(scale_w * (-(float)kLn2));
+                }
+                va.vmu = c->prof[p].ev[EV_VMU]; va.vlambda = c->prof[p].ev[EV_VLAMBDA];
+                va.F2 = c->prm.F2;
+                va.pass = c->d_vpass.as<uint8_t>() + b0;
+                va.counters = cnt;
+                vit_kernel<<<nblk(cntp, 128), 128, 0, st>>>(va);
+                c->launches++;
+            }
+            // survivors: list2 / fsc2 compacted by the pass flags (through the bias stage's buffers, then back)
+            size_t t1 = 0, t2 = 0;
+            cub::DeviceSelect::Flagged(nullptr, t1, c->d_list2.as<int32_t>(), c->d_vpass.as<uint8_t>(), c->d_list.as<int32_t>(),
+                                       d_nsel3, n2, st);
+            cub::DeviceSelect::Flagged(nullptr, t2, c->d_fsc2.as<float>(), c->d_vpass.as<uint8_t>(), c->d_filtersc.as<float>(),
+                                       d_nsel3, n2, st);
+            CUDA_TRY(c, c->d_tmp.ensure(std::max(t1, t2)));
+            cub::DeviceSelect::Flagged(c->d_tmp.p, t1, c->d_list2.as<int32_t>(), c->d_vpass.as<uint8_t>(),
+                                       c->d_list.as<int32_t>(), d_nsel3, n2, st);
+            cub::DeviceSelect::Flagged(c->d_tmp.p, t2, c->d_fsc2.as<float>(), c->d_vpass.as<uint8_t>(),
+                                       c->d_filtersc.as<float>(), d_nsel3, n2, st);
+            int32_t n3 = 0;
+            CUDA_TRY(c, cudaMemcpyAsync(&n3, d_nsel3, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaStreamSynchronize(st));
+            if (n3 > 0) {
+                CUDA_TRY(c, cudaMemcpyAsync(c->d_list2.p, c->d_list.p, (size_t)n3 * 4, cudaMemcpyDeviceToDevice, st));
+                CUDA_TRY(c, cudaMemcpyAsync(c->d_fsc2.p, c->d_filtersc.p, (size_t)n3 * 4, cudaMemcpyDeviceToDevice, st));
+            }
+            bounds_kernel<<<nblk(P + 1, 128), 128, 0, st>>>(c->d_list2.as<int32_t>(), d_nsel3, ns, P, c->d_bounds.as<int32_t>());
+            c->launches += 3;
+            CUDA_TRY(c, cudaMemcpyAsync(h_bounds.data(), c->d_bounds.p, (size_t)(P + 1) * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaEventRecord(v1, st));
+            CUDA_TRY(c, cudaStreamSynchronize(st));
+            float msv = 0.f;
+            cudaEventElapsedTime(&msv, v0, v1);
+            ss.ms_vit += msv;
+            cudaEventDestroy(v0);
+            cudaEventDestroy(v1);
+            n2 = n3;
+            CUDA_TRY(c, cudaEventRecord(ev[3], st));        // (the Forward stage's clock starts here)
+        }
+        ss.n_past_vit += n2;
         if (n2 == 0) continue;
 
         // ---- Forward / Backward / regions: one launch per profile over side streams ----
@@ -2433,6 +2645,8 @@ int search_stage1(itsx_ctx *c)
     ss.n_multidomain_regions = (int64_t)h_cnt[CNT_MULTI];
     ss.n_dom_overflow = (int64_t)h_cnt[CNT_DOM_OVERFLOW];
     ss.bias_rows = (double)h_cnt[CNT_BIAS_ROWS];
+    ss.vit_cells = (double)h_cnt[CNT_VIT_ROWS] * MAXM;
+    ss.n_vit_run = (int64_t)h_cnt[CNT_VIT_RUN];
     ss.fwd_cells = (double)h_cnt[CNT_FWD_ROWS] * MAXM;
     ss.bck_cells = (double)h_cnt[CNT_BCK_ROWS] * MAXM;
     ss.env_cells = (double)h_cnt[CNT_ENV_ROWS] * MAXM * 2;

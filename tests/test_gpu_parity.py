@@ -184,6 +184,40 @@ def test_search_multidomain_regions(gpu_ctx, oracle, resolve):
     assert np.max(np.abs(rows["domcorrection"][md] - orows["domcorrection"][md])) <= 2e-3
 
 
+@pytest.mark.parametrize("thr", [(0.02, 1e-3, 1e-5), (0.3, 1e-4, 1e-5)])
+def test_viterbi_filter_stage(gpu_ctx, oracle, thr):
+    """K6, the 16-bit Viterbi filter.  Under the reference's --F1 1e-6 --F2 1e-6 it never runs (p7_Pipeline: only for
+    F2 < P <= F1); with HMMER's own default thresholds (0.02 / 1e-3 / 1e-5) and with a wide F1 it does.  The GPU stage
+    (vit_kernel: integer max-plus in 1/500-bit words, saturating at -32768, overflow = pass) against the oracle's
+    restatement of p7_ViterbiFilter, through the whole cascade: same rows, envelopes and positions, and the counters show
+    the stage ran and removed pairs."""
+    import synth
+    from itsxpress_b200 import _lib
+    seq, off, which, cfg = synth.make_config("c2_small", scale=0.05)
+    rng = np.random.default_rng(8)
+    rnd, roff = _rand_reads(rng, 150, 240, 260, dup_frac=0.0, n_frac=0.0)          # unrelated sequences: filter fodder
+    rep, _, _ = oracle.derep(seq, off)
+    useq, uoff, _ = _uniques(seq, off, rep)
+    s2 = np.concatenate([useq, rnd])
+    o2 = np.concatenate([uoff, uoff[-1] + roff[1:]]).astype(np.int64)
+    paths = [os.path.join(HMM_DIR, cfg["hmm_file"])]
+    pre = [cfg["left_prefix"], cfg["right_prefix"]]
+    n = gpu_ctx.load_profiles(paths, pre)
+    side = gpu_ctx.set_sides_by_prefix(*pre)
+    db = oracle.ProfileDB(paths, pre)
+    prm = _lib.default_params()
+    prm.F1, prm.F2, prm.F3 = thr
+    gpu_ctx.search_seqs(s2, o2, prm)
+    rows, st = gpu_ctx.hits(), gpu_ctx.search_stats()
+    oprm = oracle.default_params(0, 1)
+    oprm.F1, oprm.F2, oprm.F3 = thr
+    orows, onrep, ost = db.search(oracle.digitize(s2.tobytes()), o2, oprm)
+    assert st.n_vit_run > 100 and st.n_past_vit < st.n_past_bias and st.vit_cells > 0
+    assert st.n_past_msv == ost.n_past_msv and st.n_past_bias == ost.n_past_bias
+    assert st.n_past_fwd == ost.n_past_fwd              # downstream of the Viterbi filter: its pass set is the oracle's
+    _compare_search(gpu_ctx, oracle, rows, st, orows, onrep, ost, side, np.diff(o2).astype(np.int32))
+
+
 def test_search_random_sequences_no_hits(gpu_ctx, oracle):
     rng = np.random.default_rng(5)
     seq, off = _rand_reads(rng, 64, 300, 420, dup_frac=0.0, n_frac=0.0)
