@@ -520,14 +520,14 @@ def _raw_blocks(path, block):
                         yield tail
                     return
                 while raw:
-                    out = d.decompress(raw)
+                    out = d.decompress(raw, block)          # at most `block` bytes per call: memory stays bounded
                     if out:
                         yield out
-                    if d.eof:                       # next gzip member
+                    if d.eof:                               # next gzip member
                         raw = d.unused_data
                         d = zlib.decompressobj(31)
                     else:
-                        raw = b""
+                        raw = d.unconsumed_tail
     elif path.endswith(".zst"):
         from . import _zstd
         with open(path, "rb") as f:

@@ -15,6 +15,7 @@ from conftest import HMM_DIR, ROOT, TD
 
 from itsxpress_b200 import fastq as fq
 from itsxpress_b200 import main as cli
+from itsxpress_b200 import q2_itsxpress as q2
 from itsxpress_b200.SeqSample import Dedup, ItsPosition
 
 
@@ -105,6 +106,89 @@ def test_zstd_decoder_flushes_held_back_blocks_and_rejects_truncation():
     assert _zstd.decompress(blob) == a + b
     with pytest.raises(ValueError):
         _zstd.decompress(blob[:-7])
+
+
+def test_stream_fastq_chunks_equal_whole_file(tmp_path):
+    """the chunked reader cuts at record boundaries found by counting lines (a quality line may start with
+    '@' or '+'), over plain / multi-member gzip / multi-frame zstd input and for chunk sizes from a few records to the whole
+    file; the appending writer produces valid plain / multi-member gzip / multi-frame zstd streams."""
+    from itsxpress_b200 import _zstd
+    raw = gzip.open(SEQ, "rb").read()
+    raw += b"@tricky one\nACGTAC\n+\n@+@+@+\n@tricky two\nAC\n+tricky two\n+@\n"
+    whole = fq.parse_bytes(raw)
+    assert whole.n == 229
+    paths = {"plain": str(tmp_path / "a.fastq"), "gz": str(tmp_path / "a.fastq.gz"), "zst": str(tmp_path / "a.fastq.zst")}
+    open(paths["plain"], "wb").write(raw)
+    with open(paths["gz"], "wb") as f:
+        f.write(gzip.compress(raw[:50_001]) + gzip.compress(raw[50_001:]))            # two members, cut mid-record
+    open(paths["zst"], "wb").write(_zstd.compress(raw[:70_001]) + _zstd.compress(raw[70_001:]))
+    want_seq, want_titles = whole.seq_concat()[0], [whole.title(i) for i in range(whole.n)]
+    for kind, path in paths.items():
+        for chunk in (900, 7777, 65_536, 1 << 30):
+            seqs, titles, nchunks = [], [], 0
+            for b in fq.stream_fastq(path, chunk):
+                seqs.append(b.seq_concat()[0])
+                titles += [b.title(i) for i in range(b.n)]
+                nchunks += 1
+            assert titles == want_titles and np.array_equal(np.concatenate(seqs), want_seq), (kind, chunk)
+            assert nchunks > 50 if (chunk == 900 and kind != "zst") else nchunks >= 1
+    for kw, name in ((dict(gzipped=True), "o.gz"), (dict(zstd_file=True), "o.zst"), (dict(), "o.fq")):
+        w = fq.ChunkWriter(str(tmp_path / name), **kw)
+        w.write(raw[:30_000], 10)
+        w.write(b"", 0)
+        w.write(raw[30_000:], 219)
+        w.close()
+        assert fq._open_bytes(str(tmp_path / name)) == raw and fq.cached_count(str(tmp_path / name)) == 229
+    w = fq.ChunkWriter(str(tmp_path / "e.gz"), gzipped=True)
+    w.close()
+    assert gzip.open(str(tmp_path / "e.gz"), "rb").read() == b""
+    with pytest.raises(ValueError):
+        list(fq.stream_fastq(_write(tmp_path, "bad.fastq", raw[:-9]), 5000))             # truncated last record
+
+
+def _write(tmp_path, name, data):
+    p = str(tmp_path / name)
+    open(p, "wb").write(data)
+    return p
+
+
+def test_q2_batches_group_small_samples_only(tmp_path):
+    """consecutive small samples share a device pass up to the read budget; a sample that alone takes more
+    than an eighth of the budget goes alone (per-sample path with read-ahead); order is preserved."""
+    from collections import namedtuple
+    Row = namedtuple("Row", "Index forward reverse")
+    rows = []
+    for k, nbytes in enumerate([1000, 2000, 400_000, 1500, 1500, 1500, 90_000, 10]):
+        p = str(tmp_path / ("s%d.fastq" % k))
+        open(p, "wb").write(b"x" * nbytes)
+        rows.append(Row("S%d" % k, p, None))
+    groups = q2._batches(rows, False, 1200)          # budget in reads; plain files: ~250 bytes per read
+    names = [[r.Index for r in g] for g in groups]
+    assert names == [["S0", "S1"], ["S2"], ["S3", "S4", "S5"], ["S6"], ["S7"]]
+    assert [r for g in groups for r in g] == rows
+
+
+def test_counter_based_generator_blocks_are_consistent():
+    """synth_big: any block of the global sample can be produced on its own (what lets 8 ranks build configs[3] without
+    any of them holding it), the abundance law is the stated one, reads carry the boundary motifs' length range."""
+    import synth_big
+    S = synth_big.BigSample("c4", scale=0.00005)
+    seq, qual, off = S.block(0, S.N)
+    a, q, o = S.block(1234, 3456)
+    lo, hi = int(off[1234]), int(off[3456])
+    assert bytes(a.numpy()) == bytes(seq.numpy()[lo:hi]) and bytes(q.numpy()) == bytes(qual.numpy()[lo:hi])
+    assert np.array_equal(o.numpy(), off.numpy()[1234:3457] - lo)
+    offn, seqn = off.numpy(), seq.numpy()
+    reads = [seqn[offn[i]:offn[i + 1]].tobytes() for i in range(S.N)]
+    from collections import Counter
+    mult = Counter(Counter(reads).values())
+    assert mult == {1: S.U - (S.N - S.U), 2: S.N - S.U} and len(set(reads)) == S.U
+    lens = np.diff(offn)
+    assert lens.min() >= 330 and lens.max() <= 441 and set(seqn.tolist()) <= set(b"ACGTN")
+    Z = synth_big.BigSample("c3", scale=0.0003)
+    zs, _, zo = Z.block(0, Z.N, want_qual=False)
+    zr = [zs.numpy()[zo[i]:zo[i + 1]].tobytes() for i in range(Z.N)]
+    assert len(set(zr)) == Z.U and max(Counter(zr).values()) > 50          # Zipf: one unique dominates
 
 
 # ---- Dedup / ItsPosition from files -------------------------------------------------------------------------
@@ -509,6 +593,7 @@ def test_q2_loop_reads_next_sample_ahead(tmp_path, monkeypatch):
         shutil.copy(sample.forward, os.path.join(str(results), os.path.basename(sample.forward)))
 
     monkeypatch.setattr(q2, "_process_sample", stub)
+    monkeypatch.setattr(q2, "BATCH_READS", 0)          # the per-sample loop (small samples would share a device pass)
     q2.main_sharded(q2.PerSampleDir(str(src)), str(tmp_path / "o"), region="ITS2", taxa="M", rank=0, world=1)
     # at the start of a sample its own files (read ahead during the previous one) and the next sample's are pending
     assert [len(p) for p in pending] == [2, 4, 2] and not fq._PREFETCH
