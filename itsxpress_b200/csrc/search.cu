@@ -323,9 +323,9 @@ bias_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ n_ptr,
 // M and I descend in place, the D chain ascends.  add-with-floor = one VIADDMNMX; the upper clamp only matters where the
 // emission is added, and a row whose best match cell reaches 32767 ends the sequence.
 struct VitArgs {
-    const int32_t *list;      // this profile's slice of the pair list
+    const int32_t *list;      // the chunk's pair list (all profiles)
     const float   *filtersc;
-    const uint8_t *need;      // 2: P(bias) > F2, run the filter; 1: passes without it
+    const int32_t *vidx;      // this profile's entries that need the filter (P(bias) > F2): indices into list
     int            count;
     const int32_t *order;
     int64_t        s0;
@@ -349,9 +349,9 @@ __global__ void __launch_bounds__(128, 3) vit_kernel(const VitArgs a)
     __shared__ __align__(16) int32_t s_v[VIT_WORDS];
     for (int t = threadIdx.x; t < VIT_WORDS; t += blockDim.x) s_v[t] = a.vtab[t];
     __syncthreads();
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= a.count) return;
-    if (a.need[e] != 2) { a.pass[e] = 1; return; }
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.count) return;
+    const int e = a.vidx[j];
     const int idx = a.list[e];
     const int sl = idx - a.prof * a.ns;
     const int64_t s = a.order[a.s0 + sl];
@@ -410,6 +410,29 @@ __global__ void __launch_bounds__(128, 3) vit_kernel(const VitArgs a)
     a.pass[e] = pass ? 1 : 0;
     atomicAdd(&a.counters[CNT_VIT_ROWS], (unsigned long long)L);
     atomicAdd(&a.counters[CNT_VIT_RUN], 1ull);
+}
+
+__global__ void vneed_flag_kernel(const uint8_t *__restrict__ need, int n, uint8_t *__restrict__ run, uint8_t *__restrict__ pass)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    run[e] = need[e] == 2;
+    pass[e] = 1;                       // entries the filter does not look at pass
+}
+// lower_bound of p * ns among the pairs list[vidx[.]] (vidx ascending, list sorted by profile), p = 0..P
+__global__ void vbounds_kernel(const int32_t *__restrict__ list, const int32_t *__restrict__ vidx,
+                               const int32_t *__restrict__ n_ptr, int ns, int P, int32_t *__restrict__ bounds)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > P) return;
+    const int n = *n_ptr;
+    const long long key = (long long)p * ns;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if ((long long)list[vidx[mid]] < key) lo = mid + 1; else hi = mid;
+    }
+    bounds[p] = lo;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2337,12 +2360,36 @@ int search_stage1(itsx_ctx *c)
             CUDA_TRY(c, c->d_tmp.ensure(tv));
             cub::DeviceSelect::Flagged(c->d_tmp.p, tv, c->d_ndom.as<uint8_t>(), c->d_ndom.as<uint8_t>(),
                                        c->d_vneed.as<uint8_t>(), d_nsel3, n1, st);
+            // worklist of the entries the filter has to look at (full warps), its per-profile slices
+            CUDA_TRY(c, c->d_list.ensure((size_t)n2 * 4 * 2 + 64));
+            uint8_t *d_run = c->d_ndom.as<uint8_t>();              // (the bias flags are consumed: reuse as "run" marks)
+            vneed_flag_kernel<<<nblk(n2, 256), 256, 0, st>>>(c->d_vneed.as<uint8_t>(), n2, d_run, c->d_vpass.as<uint8_t>());
+            int32_t *d_vidx = c->d_list.as<int32_t>() + n2;         // second half of d_list (first half: compaction output below)
+            int32_t *d_nv = d_nsel + 3;
+            {
+                cub::CountingInputIterator<int32_t> iota0(0);
+                size_t tq = 0;
+                cub::DeviceSelect::Flagged(nullptr, tq, iota0, d_run, d_vidx, d_nv, n2, st);
+                CUDA_TRY(c, c->d_tmp.ensure(tq));
+                cub::DeviceSelect::Flagged(c->d_tmp.p, tq, iota0, d_run, d_vidx, d_nv, n2, st);
+            }
+            CUDA_TRY(c, c->d_bounds.ensure((size_t)(P + 1) * 8));
+            vbounds_kernel<<<nblk(P + 1, 128), 128, 0, st>>>(c->d_list2.as<int32_t>(), d_vidx, d_nv, ns, P,
+                                                             c->d_bounds.as<int32_t>() + (P + 1));
+            std::vector<int32_t> h_vb((size_t)P + 1);
+            CUDA_TRY(c, cudaMemcpyAsync(h_vb.data(), c->d_bounds.as<int32_t>() + (P + 1), (size_t)(P + 1) * 4,
+                                        cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaStreamSynchronize(st));
+            c->launches += 3;
+            CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
+            for (int l = 0; l < NLANE; l++) CUDA_TRY(c, cudaStreamWaitEvent(c->lanes[l], c->ev_a, 0));
+            int vrr = 0;
             for (int p = 0; p < P; p++) {
-                const int b0 = h_bounds[p], cntp = h_bounds[p + 1] - b0;
+                const int b0 = h_vb[p], cntp = h_vb[p + 1] - b0;
                 if (cntp <= 0) continue;
                 VitArgs va;
-                va.list = c->d_list2.as<int32_t>() + b0; va.filtersc = c->d_fsc2.as<float>() + b0;
-                va.need = c->d_vneed.as<uint8_t>() + b0; va.count = cntp;
+                va.list = c->d_list2.as<int32_t>(); va.filtersc = c->d_fsc2.as<float>();
+                va.vidx = d_vidx + b0; va.count = cntp;
                 va.order = d_order; va.s0 = s0; va.ns = ns; va.prof = p;
                 va.seqw = c->d_seqw.as<uint32_t>(); va.woff = c->d_seqwoff.as<int64_t>(); va.seqlen = c->d_seqlen.as<int32_t>();
                 va.vtab = c->d_vtab.as<int32_t>() + (size_t)p * VIT_WORDS;
@@ -2353,10 +2400,14 @@ int search_stage1(itsx_ctx *c)
                 }
                 va.vmu = c->prof[p].ev[EV_VMU]; va.vlambda = c->prof[p].ev[EV_VLAMBDA];
                 va.F2 = c->prm.F2;
-                va.pass = c->d_vpass.as<uint8_t>() + b0;
+                va.pass = c->d_vpass.as<uint8_t>();
                 va.counters = cnt;
-                vit_kernel<<<nblk(cntp, 128), 128, 0, st>>>(va);
+                vit_kernel<<<nblk(cntp, 128), 128, 0, c->lanes[vrr++ % NLANE]>>>(va);
                 c->launches++;
+            }
+            for (int l = 0; l < NLANE; l++) {
+                CUDA_TRY(c, cudaEventRecord(c->lane_ev[l], c->lanes[l]));
+                CUDA_TRY(c, cudaStreamWaitEvent(st, c->lane_ev[l], 0));
             }
             // survivors: list2 / fsc2 compacted by the pass flags (through the bias stage's buffers, then back)
             size_t t1 = 0, t2 = 0;
