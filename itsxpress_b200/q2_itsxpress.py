@@ -199,7 +199,7 @@ def _process_batch(rows, results, tempdir, threads, taxa, region, paired_in, pai
     """The samples `rows` through ONE derep + search pass; per sample the files the sequential loop writes."""
     import numpy as np
     from . import _lib
-    from .SeqSample import CCS_FWD, get_context  # noqa: F401
+    from .SeqSample import get_context
     from .definitions import REGION_PREFIXES, maxmismatches, vsearch_fastq_qmax
     ctx = get_context()
     items = []
