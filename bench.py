@@ -437,7 +437,7 @@ def run_single(args, rank, world, local):
         ctx.run_trim(pseq, pqual, poff, prm, out=outs)
 
     def step_e2e():
-        last["e2e"] = ctx.run_trim(pseq, pqual, poff, prm, out=outs)[1]
+        last["e2e_out"], last["e2e"] = ctx.run_trim(pseq, pqual, poff, prm, out=outs)
 
     ms_e2e_dev, ms_e2e_wall = timed(step_e2e, args.steps)
     clocks = clk.stop()
@@ -484,7 +484,11 @@ def run_single(args, rank, world, local):
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "stages": stages,
                 "hmm_gcups": {"msv": stages["msv"]["gcups"], "fwd_bwd": stages["fwd_bwd_decode"]["gcups"],
                               "envelope": stages["envelope"]["gcups"]},
-                "result": {"n_unique": int(rs.n_unique), "n_kept": int(rs.n_kept), "out_bytes": int(rs.out_bytes)},
+                "result": {"n_unique": int(rs.n_unique), "n_kept": int(rs.n_kept), "out_bytes": int(rs.out_bytes),
+                           # checksums of what the last e2e step returned (equal across builds of the same path)
+                           "crc32": {k: zlib.crc32(last["e2e_out"][k].tobytes())
+                                     for k in ("kept_index", "out_off", "out_seq", "out_qual")},
+                           "n_selected_multidomain": int(ss.n_selected_multidomain)},
                 "extra": {"cli_file_to_file": cli_extra}}
         emit(line)
 

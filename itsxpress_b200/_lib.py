@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libitsx_b200.so")
+# ITSX_B200_LIB: an experimental build of the same library (tools/build_variant.py); never another implementation
+LIB_PATH = os.environ.get("ITSX_B200_LIB") or os.path.join(_HERE, "libitsx_b200.so")
 _LIB = None
 
 MAXM = 45

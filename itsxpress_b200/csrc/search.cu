@@ -491,10 +491,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                  "}" ::"r"(bar), "r"(parity) : "memory");
 }
 
+#ifndef FB_DECODE_PF
+#define FB_DECODE_PF 16
+#endif
+#ifndef FB_DECODE_RING
+#define FB_DECODE_RING 0
+#endif
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void l1_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __global__ void __launch_bounds__(FB_THREADS, FB_CTAS_PER_SM)
 fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
 {
     __shared__ __align__(16) float s_e[16 * ESTRIDE];     // [residue code][node]: odds of the launch's profile
+#if FB_DECODE_RING > 0
+    __shared__ __align__(16) float s_ring[(FB_THREADS / 32) * FB_DECODE_RING * SPEC_C * 32];
+#endif
     for (int t = threadIdx.x; t < 16 * ESTRIDE; t += FB_THREADS) {
         const int x = t / ESTRIDE, k = t - x * ESTRIDE;
         s_e[t] = k <= MAXM ? a.etab[k * 16 + x] : 0.f;
@@ -717,10 +734,49 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
             bool triggered = false;
             int nmulti = 0;
             SPEC(0, 0) = 0.f; SPEC(0, 1) = 0.f;   // btot[0], etot[0]
+#if FB_DECODE_PF > 0
+            // rows FB_DECODE_PF ahead are pulled into L1 (CCTL.PF1: no register, no unrolling); the row-ahead register
+            // loads below then hit L1 instead of waiting out an HBM round trip per row
+#pragma unroll 1
+            for (int j = 2; j <= FB_DECODE_PF && j <= L; j++) {
+#pragma unroll
+                for (int cc = 0; cc < SPEC_C; cc++) l1_prefetch(&SPEC(j, cc));
+            }
+#endif
+#if FB_DECODE_RING > 0
+            // the rows come through a per-warp shared-memory ring filled by cp.async FB_DECODE_RING rows ahead
+            // (each lane copies and reads its own column: no cross-lane ordering needed)
+            float *ring = s_ring + ((size_t)(threadIdx.x >> 5) * FB_DECODE_RING * SPEC_C) * 32 + lane;
+#pragma unroll 1
+            for (int j = 1; j <= FB_DECODE_RING; j++) {
+                if (j <= L) {
+#pragma unroll
+                    for (int cc = 0; cc < SPEC_C; cc++) cp_async4(ring + ((j % FB_DECODE_RING) * SPEC_C + cc) * 32, &SPEC(j, cc));
+                }
+                cp_async_commit();
+            }
+            for (int j = 1; j <= L; j++) {
+                cp_async_wait<FB_DECODE_RING - 1>();
+                const float *rs = ring + (j % FB_DECODE_RING) * SPEC_C * 32;
+                const float v0 = rs[0], v1 = rs[32], v2 = rs[64], v3 = rs[96], v4 = rs[128];
+                if (j + FB_DECODE_RING <= L) {
+#pragma unroll
+                    for (int cc = 0; cc < SPEC_C; cc++)
+                        cp_async4(ring + ((j % FB_DECODE_RING) * SPEC_C + cc) * 32, &SPEC(j + FB_DECODE_RING, cc));
+                }
+                cp_async_commit();
+#else
             float r0 = SPEC(1, 0), r1 = SPEC(1, 1), r2 = SPEC(1, 2), r3 = SPEC(1, 3), r4 = SPEC(1, 4);
             for (int j = 1; j <= L; j++) {
+#if FB_DECODE_PF > 0
+                if (j + FB_DECODE_PF <= L) {
+#pragma unroll
+                    for (int cc = 0; cc < SPEC_C; cc++) l1_prefetch(&SPEC(j + FB_DECODE_PF, cc));
+                }
+#endif
                 const float v0 = r0, v1 = r1, v2 = r2, v3 = r3, v4 = r4;
                 if (j < L) { r0 = SPEC(j + 1, 0); r1 = SPEC(j + 1, 1); r2 = SPEC(j + 1, 2); r3 = SPEC(j + 1, 3); r4 = SPEC(j + 1, 4); }
+#endif
                 const float db = v0 * scaleproduct, de = v1 * scaleproduct;
                 const float btot_p = btot, etot_p = etot;
                 btot = btot + db;
@@ -773,7 +829,7 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
 //                   generator leap-frogged to substream t (x_(t 2^20)); the 200 lanes of a region read the same slab
 //                   (L1 / L2 resident); phases of the walk are warp-vote loops so lanes stay converged; a trace
 //                   leaves its domains (coordinates + null2 odds by trace) in a fixed 100-byte record
-//   mdclust_kernel  one thread per region: n2sc per position, distinct segments, single-linkage clustering,
+//   mdclust_kernel  one warp per region: n2sc per position, distinct segments, single-linkage clustering,
 //                   cluster envelopes (start order) with their domcorrection
 //   mdapply_kernel  one thread per worklist entry: the cluster envelopes replace the region in the entry's list.
 // The cluster envelopes carry bit 29 ("null2 done"): env_kernel still gives their unihit Forward score, final_kernel
@@ -783,10 +839,16 @@ constexpr int MD_MAXSEG = 1024;
 constexpr int MD_MAXTDOM = 4;                  // domains kept per trace
 constexpr int MD_W = MAXM + 1;
 constexpr int MD_STREAM_LOG2 = 20;
-struct alignas(8) MdSeg { uint16_t i, j; uint8_t k, m; uint16_t n; };        // distinct segment and how many traces sampled it
 struct MdRow { float pC0, pC1, pJ0, pJ1, pB0, pB1, nrmE, xB; };   // per row: normalised C / J / B choices, 1 / xE, xB
 struct MdDom { uint16_t from, to; uint8_t k, m; uint16_t pad; float n2[4]; };   // region-relative rows
-struct MdTrace { int32_t nd; MdDom d[MD_MAXTDOM]; };
+struct MdTrace { int32_t nd; MdDom d[MD_MAXTDOM]; };                             // a trace while it is walked (registers)
+// The traces of a region in HBM, arrays over the trace index so that 32 traces are written and read with coalesced
+// accesses: nd[200] | from, to [4][200] | k, m [4][200] | null2 odds [4][200] float4
+constexpr int MD_TRACE_FT = MD_NSAMPLES * 4;
+constexpr int MD_TRACE_KM = MD_TRACE_FT + MD_MAXTDOM * MD_NSAMPLES * 4;
+constexpr int MD_TRACE_N2 = MD_TRACE_KM + MD_MAXTDOM * MD_NSAMPLES * 4;
+constexpr int MD_TRACE_BYTES = MD_TRACE_N2 + MD_MAXTDOM * MD_NSAMPLES * 16;
+static_assert(MD_TRACE_N2 % 16 == 0 && MD_TRACE_BYTES % 16 == 0, "float4 alignment of the trace arrays");
 struct MdRes { int32_t n; float regsum; int32_t ci[ITSX_MAXDOM], cj[ITSX_MAXDOM]; float cdc[ITSX_MAXDOM]; };
 struct MdArgs {
     // regions of this chunk: [r0, r1) of the region list
@@ -807,7 +869,7 @@ struct MdArgs {
     const ProfScalars *pscal;
     float4         *cell;     // [row][MD_W]: (M, I, D, -)
     MdRow          *rowrec;   // [row]
-    MdTrace        *trace;    // [region - r0][MD_NSAMPLES]
+    char           *trace;    // [region - r0][MD_TRACE_BYTES]
     MdRes          *res;      // [region]
     char           *scratch;  // mdclust: per thread
     size_t          per_thread;
@@ -816,12 +878,6 @@ struct MdArgs {
     unsigned long long *counters;
 };
 struct MdStreams { uint32_t x[MD_NSAMPLES]; };
-__host__ __device__ inline size_t md_clust_bytes(int maxrows)
-{
-    // per warp: acc + cover count per row, raw (segment id, trace), last trace and trace count per cluster
-    size_t b = (size_t)(maxrows + 1) * 8 + (size_t)MD_MAXSEG * (4 + 2 + 2);
-    return (b + 255) / 256 * 256;
-}
 __device__ __forceinline__ double md_rng(uint32_t &x)
 {
     x = x * 69069u + 1u;
@@ -843,20 +899,6 @@ __device__ __forceinline__ int md_pick2(uint32_t &rng, float p0, float p1)
         c += p0; if (roll < (double)c) return 0;
         c += p1; if (roll < (double)c) return 1;
     }
-}
-// link_spsamples.  (float)nov / (float)n < 0.8f  is decided exactly by  5 nov < 4 n : for n < 2^16 the quotient is
-// either 4/5 (rounds to 0.8f, not smaller) or at least 1 / (5 n) > 3e-6 away from it, far more than a float ulp.
-__device__ __forceinline__ bool md_link(const MdSeg &a, const MdSeg &b)
-{
-    int nov = min((int)a.j, (int)b.j) - max((int)a.i, (int)b.i) + 1;
-    int n = min(a.j - a.i + 1, b.j - b.i + 1);
-    if (5 * nov < 4 * n) return false;
-    nov = min((int)a.m, (int)b.m) - max((int)a.k, (int)b.k) + 1;
-    n = min(a.m - a.k + 1, b.m - b.k + 1);
-    if (5 * nov < 4 * n) return false;
-    if (abs(((int)a.i - (int)a.k) - ((int)b.i - (int)b.k)) > 4) return false;
-    if (abs(((int)a.j - (int)a.m) - ((int)b.j - (int)b.m)) > 4) return false;
-    return true;
 }
 enum { MS_M = 0, MS_D, MS_I, MS_N, MS_C, MS_J, MS_E, MS_B, MS_S };
 
@@ -1096,143 +1138,284 @@ __global__ void __launch_bounds__(128) mdtrace_kernel(const MdArgs a, const __gr
             inJ = true;
         }
     }
-    if (act) a.trace[(size_t)(r - a.r0) * MD_NSAMPLES + t] = out;
+    if (act) {
+        char *tb = a.trace + (size_t)(r - a.r0) * MD_TRACE_BYTES;
+        ((int32_t *)tb)[t] = out.nd;
+        for (int d = 0; d < out.nd; d++) {
+            const MdDom &dd = out.d[d];
+            ((uint32_t *)(tb + MD_TRACE_FT))[d * MD_NSAMPLES + t] = (uint32_t)dd.from | ((uint32_t)dd.to << 16);
+            ((uint32_t *)(tb + MD_TRACE_KM))[d * MD_NSAMPLES + t] = (uint32_t)dd.k | ((uint32_t)dd.m << 8);
+            ((float4 *)(tb + MD_TRACE_N2))[d * MD_NSAMPLES + t] = make_float4(dd.n2[0], dd.n2[1], dd.n2[2], dd.n2[3]);
+        }
+    }
 #undef CELL
 }
 
-// ---- per region, one WARP: n2sc, distinct segments, single linkage clustering, cluster envelopes.  The samples are
-// visited in trace order (float sums keep the oracle's order); the lanes share the search for an equal segment, the
-// positions of a domain, the link tests of the component walk and the endpoint counts. ----
+// ---- per region, one WARP: n2sc, distinct segments, single linkage clustering, cluster envelopes.  Every phase is
+// lane-parallel and reads the trace records with coalesced loads, one round trip per 32 traces (the first version walked
+// the 200 records one after the other: two dependent HBM latencies per trace, 0.43 ms per region).  Only the float sums
+// keep the oracle's order (per position: samples in trace order; per envelope and per region: positions ascending).
+//   A. 32 traces per round: lanes load their trace's domains (left to right), scan the counts into the flat sample
+//      list (key + trace per sample, for B-D) and broadcast the domains one by one by shuffles; lanes own positions (four
+//      blocks of 32 per pass over the traces) and sum the null2 odds of the covering domains in registers
+//   B. distinct segments through a shared-memory hash table (the slot keeps the FIRST sample with that key, so the
+//      segments are numbered in order of first appearance like a serial scan would), multiplicities by atomics
+//   C. level-synchronous component search: lanes own unassigned segments and test them against the frontier
+//   D. traces per cluster by atomics; envelope end points from a histogram of the cluster's starts / ends
 constexpr int MDC_WARPS = 4;
+constexpr int MDC_CAP = 832;                   // >= MD_NSAMPLES * MD_MAXTDOM, a multiple of 32
+constexpr int MDC_HT = 1024;                   // hash slots (power of two > MDC_CAP); later the end-point histogram
+constexpr int MDC_PB = 4;                      // position blocks (of 32) per pass over the traces
+static_assert(MDC_CAP >= MD_NSAMPLES * MD_MAXTDOM && MDC_CAP % 32 == 0 && MDC_HT > MDC_CAP, "mdclust capacities");
 struct MdClustSmem {
-    MdSeg   seg[MD_MAXSEG];
-    int16_t asg[MD_MAXSEG];
-    int16_t stack[MD_MAXSEG];
+    unsigned long long skey[MDC_CAP];          // distinct segments: i | j << 16 | k << 32 | m << 40
+    uint32_t htab[MDC_HT];
+    uint32_t scount[MDC_CAP];                  // how many samples hit the segment
+    int16_t  asg[MDC_CAP];
+    int16_t  queue[MDC_CAP];                   // component search: assigned segments in discovery order
 };
+__host__ __device__ inline size_t md_clust_bytes(int maxrows)
+{
+    // per warp: sample keys, n2sc per row, sample -> slot / segment, sample -> trace
+    size_t b = (size_t)MDC_CAP * 8 + (size_t)(maxrows + 1) * 4 + (size_t)MDC_CAP * (2 + 1);
+    return (b + 255) / 256 * 256;
+}
+__device__ __forceinline__ bool md_link_key(unsigned long long ka, unsigned long long kb)
+{
+    const int ai = (int)(ka & 0xffffu), aj = (int)((ka >> 16) & 0xffffu), ak = (int)((ka >> 32) & 0xffu), am = (int)((ka >> 40) & 0xffu);
+    const int bi = (int)(kb & 0xffffu), bj = (int)((kb >> 16) & 0xffffu), bk = (int)((kb >> 32) & 0xffu), bm = (int)((kb >> 40) & 0xffu);
+    // link_spsamples.  (float)nov / (float)n < 0.8f  is decided exactly by  5 nov < 4 n : for n < 2^16 the quotient is
+    // either 4/5 (rounds to 0.8f, not smaller) or at least 1 / (5 n) > 3e-6 away from it, far more than a float ulp.
+    int nov = min(aj, bj) - max(ai, bi) + 1;
+    int n = min(aj - ai + 1, bj - bi + 1);
+    if (5 * nov < 4 * n) return false;
+    nov = min(am, bm) - max(ak, bk) + 1;
+    n = min(am - ak + 1, bm - bk + 1);
+    if (5 * nov < 4 * n) return false;
+    if (abs((ai - ak) - (bi - bk)) > 4) return false;
+    if (abs((aj - am) - (bj - bm)) > 4) return false;
+    return true;
+}
+// null2 odds of residue code x under a domain's (A, C, G, T) odds: IUPAC codes average their bases in base order
+__device__ __forceinline__ float md_null2_of(uint32_t x, float a, float c, float g, float t)
+{
+    if (x < 4) return x == 0 ? a : x == 1 ? c : x == 2 ? g : t;
+    if (x == 15) return 1.0f;
+    const uint32_t dmask = (uint32_t)(0x0FD7EB96C3A58421ull >> (4 * x)) & 15u;
+    float sa = 0.f;
+    int na = 0;
+    if (dmask & 1u) { sa += a; na++; }
+    if (dmask & 2u) { sa += c; na++; }
+    if (dmask & 4u) { sa += g; na++; }
+    if (dmask & 8u) { sa += t; na++; }
+    return sa / (float)na;
+}
 __global__ void __launch_bounds__(MDC_WARPS * 32) mdclust_kernel(const MdArgs a)
 {
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr uint32_t EMPTY = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char mdc_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int warp = blockIdx.x * MDC_WARPS + wid, nwarps = gridDim.x * MDC_WARPS;
+    const unsigned lt = (1u << lane) - 1u;
     MdClustSmem &sm = ((MdClustSmem *)mdc_smem)[wid];
     char *scr = a.scratch + (size_t)warp * a.per_thread;
-    float *acc = (float *)scr;                               // [maxrows + 1]
-    int32_t *cov = (int32_t *)(acc + (a.maxrows + 1));       // [maxrows + 1]
-    uint16_t *rawid = (uint16_t *)(cov + (a.maxrows + 1)), *rawtr = rawid + MD_MAXSEG;
-    int16_t *lasttr = (int16_t *)(rawtr + MD_MAXSEG), *ntrc = lasttr + MD_MAXSEG;
-    const int degen[16] = {1, 2, 4, 8, 5, 10, 3, 12, 6, 9, 11, 14, 7, 13, 15, 0};
+    unsigned long long *rkey = (unsigned long long *)scr;            // [MDC_CAP]
+    float *acc = (float *)(rkey + MDC_CAP);                          // [maxrows + 1]
+    uint16_t *rslot = (uint16_t *)(acc + (a.maxrows + 1));           // [MDC_CAP]: hash slot, then segment id
+    uint8_t *rtr = (uint8_t *)(rslot + MDC_CAP);                     // [MDC_CAP]: trace of the sample
     for (int r = a.r0 + warp; r < a.r1; r += nwarps) {
         const MdRegion g = md_region(a, r);
         const int Ld = g.Ld, ireg = g.ireg;
-        const MdTrace *tr = a.trace + (size_t)(r - a.r0) * MD_NSAMPLES;
-        for (int pos = lane; pos <= Ld; pos += 32) { acc[pos] = 0.f; cov[pos] = 0; }
-        __syncwarp();
-        int nseg = 0, nraw = 0;
-        for (int t = 0; t < MD_NSAMPLES; t++) {
-            const int nd = tr[t].nd;
-            for (int d = nd - 1; d >= 0; d--) {          // left to right
-                const MdDom dd = tr[t].d[d];
-                if (nraw < MD_MAXSEG) {
-                    const uint16_t si = (uint16_t)(dd.from + ireg - 1), sj = (uint16_t)(dd.to + ireg - 1);
-                    int u = -1;
-                    const unsigned long long want = (unsigned long long)si | ((unsigned long long)sj << 16) |
-                                                    ((unsigned long long)dd.k << 32) | ((unsigned long long)dd.m << 40);
-                    for (int u0 = 0; u0 < nseg && u < 0; u0 += 32) {
-                        const bool hit = u0 + lane < nseg &&
-                            ((*(const unsigned long long *)&sm.seg[u0 + lane]) & 0xffffffffffffull) == want;
-                        const unsigned m = __ballot_sync(FULL, hit);
-                        if (m) u = u0 + __ffs(m) - 1;
+        const char *tb = a.trace + (size_t)(r - a.r0) * MD_TRACE_BYTES;
+        const int32_t *t_nd = (const int32_t *)tb;
+        const uint32_t *t_ft = (const uint32_t *)(tb + MD_TRACE_FT), *t_km = (const uint32_t *)(tb + MD_TRACE_KM);
+        const float4 *t_n2 = (const float4 *)(tb + MD_TRACE_N2);
+        // ---- A. flat sample list + n2sc per position ----
+        int nraw = 0;
+        for (int pg = 1; pg <= Ld; pg += 32 * MDC_PB) {
+            const bool first_pass = pg == 1;
+            uint32_t x[MDC_PB];
+            float sum[MDC_PB];
+            int cover[MDC_PB];
+#pragma unroll
+            for (int b = 0; b < MDC_PB; b++) {
+                const int pos = pg + 32 * b + lane;
+                x[b] = pos <= Ld ? residue_at(g.w, ireg - 1 + pos - 1) : 15u;
+                sum[b] = 0.f; cover[b] = 0;
+            }
+            for (int t0 = 0; t0 < MD_NSAMPLES; t0 += 32) {
+                const int t = t0 + lane, tt = min(t, MD_NSAMPLES - 1);
+                const int nd = t < MD_NSAMPLES ? t_nd[tt] : 0;
+                // slot s = the trace's s-th domain from the left (the walk found them right to left)
+                uint32_t ft[MD_MAXTDOM];
+                float4 n2[MD_MAXTDOM];
+#pragma unroll
+                for (int sl = 0; sl < MD_MAXTDOM; sl++) {
+                    const int d = nd - 1 - sl;
+                    ft[sl] = 0u; n2[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (d >= 0) { ft[sl] = t_ft[d * MD_NSAMPLES + tt]; n2[sl] = t_n2[d * MD_NSAMPLES + tt]; }
+                }
+                if (first_pass) {
+                    int inc = nd;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(FULL, inc, o);
+                        if (lane >= o) inc += v;
                     }
-                    if (lane == 0) {
-                        if (u < 0) {
-                            MdSeg sg;
-                            sg.i = si; sg.j = sj; sg.k = dd.k; sg.m = dd.m; sg.n = 1;
-                            sm.seg[nseg] = sg;
-                            rawid[nraw] = (uint16_t)nseg;
-                        } else {
-                            sm.seg[u].n++;
-                            rawid[nraw] = (uint16_t)u;
+                    const int at = nraw + inc - nd;
+#pragma unroll
+                    for (int sl = 0; sl < MD_MAXTDOM; sl++) {
+                        if (sl < nd) {
+                            const uint32_t km = t_km[(nd - 1 - sl) * MD_NSAMPLES + tt];
+                            const unsigned long long si = (ft[sl] & 0xffffu) + (uint32_t)(ireg - 1), sj = (ft[sl] >> 16) + (uint32_t)(ireg - 1);
+                            rkey[at + sl] = (si & 0xffffu) | ((sj & 0xffffu) << 16) | ((unsigned long long)(km & 0xffffu) << 32);
+                            rtr[at + sl] = (uint8_t)t;
                         }
-                        rawtr[nraw] = (uint16_t)t;
                     }
-                    if (u < 0) nseg++;
-                    nraw++;
-                    __syncwarp();
+                    nraw += __shfl_sync(FULL, inc, 31);
                 }
-                for (int pos = dd.from + lane; pos <= dd.to; pos += 32) {
-                    const uint32_t x = residue_at(g.w, ireg - 1 + pos - 1);
-                    float v;
-                    if (x < 4) v = dd.n2[x];
-                    else if (x == 15) v = 1.0f;
-                    else {
-                        float sa = 0.f;
-                        int na = 0;
-                        for (int y = 0; y < 4; y++)
-                            if (degen[x] & (1 << y)) { sa += dd.n2[y]; na++; }
-                        v = sa / (float)na;
+                // the domains of the 32 traces one by one, in trace order
+                for (unsigned todo = __ballot_sync(FULL, nd > 0); todo; todo &= todo - 1u) {
+                    const int src = __ffs(todo) - 1;
+                    const int ndv = __shfl_sync(FULL, nd, src);
+#pragma unroll
+                    for (int sl = 0; sl < MD_MAXTDOM; sl++) {
+                        if (sl >= ndv) break;
+                        const uint32_t f = __shfl_sync(FULL, ft[sl], src);
+                        const int from = (int)(f & 0xffffu), to = (int)(f >> 16);
+                        if (to < pg || from >= pg + 32 * MDC_PB) continue;
+                        const float oa = __shfl_sync(FULL, n2[sl].x, src), oc = __shfl_sync(FULL, n2[sl].y, src);
+                        const float og = __shfl_sync(FULL, n2[sl].z, src), ot = __shfl_sync(FULL, n2[sl].w, src);
+#pragma unroll
+                        for (int b = 0; b < MDC_PB; b++) {
+                            const int p0 = pg + 32 * b;
+                            if (to < p0 || from > p0 + 31) continue;
+                            const int pos = p0 + lane;
+                            if (pos >= from && pos <= to) { sum[b] += md_null2_of(x[b], oa, oc, og, ot); cover[b]++; }
+                        }
                     }
-                    acc[pos] += v;
-                    cov[pos]++;
                 }
-                __syncwarp();        // the next sample may touch the same positions from other lanes
+            }
+#pragma unroll
+            for (int b = 0; b < MDC_PB; b++) {
+                const int pos = pg + 32 * b + lane;
+                if (pos <= Ld) acc[pos] = logf_via_double((sum[b] + (float)(MD_NSAMPLES - cover[b])) / (float)MD_NSAMPLES);
             }
         }
-        // n2sc of the region (kept in acc[]); the sum over the region in position order
-        for (int pos = 1 + lane; pos <= Ld; pos += 32)
-            acc[pos] = logf_via_double((acc[pos] + (float)(MD_NSAMPLES - cov[pos])) / (float)MD_NSAMPLES);
+        for (int h = lane; h < MDC_HT; h += 32) sm.htab[h] = EMPTY;
         __syncwarp();
+        // n2sc of the region: the sum in position order
         float regsum = 0.f;
         if (lane == 0)
             for (int pos = 1; pos <= Ld; pos++) regsum += acc[pos];
-        // single linkage clustering over the DISTINCT segments (same components as over all samples)
-        for (int q = lane; q < nseg; q += 32) sm.asg[q] = -1;
+        // ---- B. distinct segments ----
+        for (int q = lane; q < nraw; q += 32) {
+            const unsigned long long key = rkey[q];
+            uint32_t h = ((uint32_t)(key ^ (key >> 21)) * 0x9E3779B1u) >> 22;
+            for (;;) {
+                uint32_t cur = *(volatile uint32_t *)&sm.htab[h];
+                if (cur == EMPTY) {
+                    cur = atomicCAS(&sm.htab[h], EMPTY, (uint32_t)q);
+                    if (cur == EMPTY) break;
+                }
+                if (rkey[cur] == key) { atomicMin(&sm.htab[h], (uint32_t)q); break; }
+                h = (h + 1) & (MDC_HT - 1);
+            }
+            rslot[q] = (uint16_t)h;
+        }
         __syncwarp();
+        int nseg = 0;
+        for (int q0 = 0; q0 < nraw; q0 += 32) {
+            const int q = q0 + lane;
+            uint32_t h = 0;
+            bool first = false;
+            if (q < nraw) { h = rslot[q]; first = sm.htab[h] == (uint32_t)q; }
+            const unsigned m = __ballot_sync(FULL, first);
+            if (first) {
+                const int id = nseg + __popc(m & lt);
+                sm.skey[id] = rkey[q];
+                sm.scount[id] = 0u;
+                sm.asg[id] = -1;
+                sm.htab[h] = 0x80000000u | (uint32_t)id;
+            }
+            nseg += __popc(m);
+        }
+        __syncwarp();
+        for (int q = lane; q < nraw; q += 32) {
+            const uint32_t id = sm.htab[rslot[q]] & 0x7fffffffu;
+            rslot[q] = (uint16_t)id;
+            atomicAdd(&sm.scount[id], 1u);
+        }
+        __syncwarp();
+        // ---- C. single linkage clustering over the DISTINCT segments (same components as over all samples) ----
         int nc = 0;
         for (int q = 0; q < nseg; q++) {
             if (sm.asg[q] >= 0) continue;
-            int top = 0;
-            if (lane == 0) { sm.stack[0] = (int16_t)q; sm.asg[q] = (int16_t)nc; }
-            top = 1;
             __syncwarp();
-            while (top) {
-                const MdSeg v = sm.seg[sm.stack[--top]];
-                __syncwarp();
-                for (int b0 = 0; b0 < nseg; b0 += 32) {
+            if (lane == 0) { sm.queue[0] = (int16_t)q; sm.asg[q] = (int16_t)nc; }
+            __syncwarp();
+            int head = 0, tail = 1;
+            const int lo = q & ~31;                 // every segment below the seed already has its cluster
+            while (head < tail) {
+                int ntail = tail;
+                for (int b0 = lo; b0 < nseg; b0 += 32) {
                     const int bb = b0 + lane;
-                    const bool take = bb < nseg && sm.asg[bb] < 0 && md_link(v, sm.seg[bb]);
+                    bool take = false;
+                    if (bb < nseg && sm.asg[bb] < 0) {
+                        const unsigned long long kb = sm.skey[bb];
+                        for (int f = head; f < tail && !take; f++) take = md_link_key(sm.skey[sm.queue[f]], kb);
+                    }
                     const unsigned m = __ballot_sync(FULL, take);
                     if (take) {
                         sm.asg[bb] = (int16_t)nc;
-                        sm.stack[top + __popc(m & ((1u << lane) - 1u))] = (int16_t)bb;
+                        sm.queue[ntail + __popc(m & lt)] = (int16_t)bb;
                     }
-                    top += __popc(m);
+                    ntail += __popc(m);
                 }
                 __syncwarp();
+                head = tail;
+                tail = ntail;
             }
             nc++;
         }
-        // traces that contribute to each cluster (samples are in trace order)
-        if (lane == 0) {
-            for (int c = 0; c < nc; c++) { lasttr[c] = -1; ntrc[c] = 0; }
-            for (int q = 0; q < nraw; q++) {
-                const int c = sm.asg[rawid[q]];
-                if (lasttr[c] != (int16_t)rawtr[q]) { ntrc[c]++; lasttr[c] = (int16_t)rawtr[q]; }
+        __syncwarp();
+        // ---- D. traces per cluster (the samples of a trace are consecutive) ----
+        for (int c = lane; c < nc; c += 32) sm.htab[c] = 0u;
+        __syncwarp();
+        for (int q = lane; q < nraw; q += 32) {
+            const int c = sm.asg[rslot[q]], t = rtr[q];
+            bool dup = false;
+            for (int b = 1; b < MD_MAXTDOM && q - b >= 0 && !dup; b++) {
+                if (rtr[q - b] != t) break;
+                dup = sm.asg[rslot[q - b]] == c;
             }
+            if (!dup) atomicAdd(&sm.htab[c], 1u);
+        }
+        __syncwarp();
+        // clusters with posterior >= 0.25 (at most MD_NSAMPLES * MD_MAXTDOM / 50 = 16 of them), in cluster order
+        int npass = 0;
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+            const int c = c0 + lane;
+            const bool ok = c < nc && !((float)sm.htab[c] / (float)MD_NSAMPLES < 0.25f);
+            const unsigned m = __ballot_sync(FULL, ok);
+            if (ok && npass + __popc(m & lt) < 16) sm.queue[npass + __popc(m & lt)] = (int16_t)c;
+            npass = min(npass + __popc(m), 16);
         }
         __syncwarp();
         int ci[16], cj[16];
         int nenv = 0;
-        for (int c = 0; c < nc; c++) {
-            if ((float)ntrc[c] / (float)MD_NSAMPLES < 0.25f) continue;
+        for (int pc = 0; pc < npass; pc++) {
+            const int c = sm.queue[pc];
             int ninc = 0;
             int imin = 1 << 30, imax = 0, jmin = 1 << 30, jmax = 0;
             for (int q = lane; q < nseg; q += 32) {
                 if (sm.asg[q] != c) continue;
-                const MdSeg sgm = sm.seg[q];
-                ninc += sgm.n;
-                imin = min(imin, (int)sgm.i); imax = max(imax, (int)sgm.i);
-                jmin = min(jmin, (int)sgm.j); jmax = max(jmax, (int)sgm.j);
+                const unsigned long long k = sm.skey[q];
+                const int si = (int)(k & 0xffffu), sj = (int)((k >> 16) & 0xffffu);
+                ninc += (int)sm.scount[q];
+                imin = min(imin, si); imax = max(imax, si);
+                jmin = min(jmin, sj); jmax = max(jmax, sj);
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
@@ -1241,21 +1424,36 @@ __global__ void __launch_bounds__(MDC_WARPS * 32) mdclust_kernel(const MdArgs a)
                 jmin = min(jmin, __shfl_xor_sync(FULL, jmin, o)); jmax = max(jmax, __shfl_xor_sync(FULL, jmax, o));
             }
             const int thr = (int)ceilf((float)ninc * 0.02f);
-            int best_i, best_j;
-            for (best_i = imin; best_i <= imax; best_i++) {
-                int cnt = 0;
-                for (int q = lane; q < nseg; q += 32) cnt += (sm.asg[q] == c && (int)sm.seg[q].i == best_i) ? (int)sm.seg[q].n : 0;
+            // leftmost start / rightmost end whose count reaches thr: histogram of the cluster's end points
+            int best[2];
 #pragma unroll
-                for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
-                if (cnt >= thr) break;
+            for (int side = 0; side < 2; side++) {
+                const int vmin = side ? jmin : imin, vmax = side ? jmax : imax, span = vmax - vmin + 1;
+                int found = -1;
+                for (int w0 = 0; w0 < span && found < 0; w0 += MDC_HT) {      // one window unless the span is huge
+                    const int wn = min(span - w0, MDC_HT);
+                    __syncwarp();
+                    for (int h = lane; h < wn; h += 32) sm.htab[h] = 0u;
+                    __syncwarp();
+                    for (int q = lane; q < nseg; q += 32) {
+                        if (sm.asg[q] != c) continue;
+                        const unsigned long long k = sm.skey[q];
+                        const int v = side ? (int)((k >> 16) & 0xffffu) : (int)(k & 0xffffu);
+                        // the window counts from vmin upwards (starts) or from vmax downwards (ends)
+                        const int off = (side ? vmax - v : v - vmin) - w0;
+                        if (off >= 0 && off < wn) atomicAdd(&sm.htab[off], sm.scount[q]);
+                    }
+                    __syncwarp();
+                    for (int h0 = 0; h0 < wn && found < 0; h0 += 32) {
+                        const bool hit = h0 + lane < wn && (int)sm.htab[h0 + lane] >= thr;
+                        const unsigned m = __ballot_sync(FULL, hit);
+                        if (m) found = w0 + h0 + __ffs(m) - 1;
+                    }
+                }
+                if (found < 0) found = span;                     // the reference loop runs off the end
+                best[side] = side ? vmax - found : vmin + found;
             }
-            for (best_j = jmax; best_j >= jmin; best_j--) {
-                int cnt = 0;
-                for (int q = lane; q < nseg; q += 32) cnt += (sm.asg[q] == c && (int)sm.seg[q].j == best_j) ? (int)sm.seg[q].n : 0;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
-                if (cnt >= thr) break;
-            }
+            const int best_i = best[0], best_j = best[1];
             if (nenv < 16) {
                 int at = nenv;
                 while (at > 0 && (ci[at - 1] > best_i || (ci[at - 1] == best_i && cj[at - 1] > best_j))) {
@@ -2532,7 +2730,7 @@ int search_stage1(itsx_ctx *c)
                 ma.e_move = expf(-(float)kLn2);
                 ma.counters = cnt;
                 // chunks of regions: slabs (matrix + row tables) and trace records within a fixed HBM budget
-                const size_t row_bytes = (size_t)MD_W * 16 + sizeof(MdRow), reg_bytes = (size_t)MD_NSAMPLES * sizeof(MdTrace);
+                const size_t row_bytes = (size_t)MD_W * 16 + sizeof(MdRow), reg_bytes = (size_t)MD_TRACE_BYTES;
                 const size_t budget = (size_t)6 << 30;
                 for (int r0 = 0; r0 < NR;) {
                     int r1 = r0 + 1;
@@ -2546,12 +2744,14 @@ int search_stage1(itsx_ctx *c)
                     ma.r0 = r0; ma.r1 = r1; ma.row0 = h_row[r0];
                     ma.cell = c->d_mdcell.as<float4>();
                     ma.rowrec = (MdRow *)(c->d_mdcell.as<char>() + rows * MD_W * 16);
-                    ma.trace = c->d_mdtrace.as<MdTrace>();
+                    ma.trace = c->d_mdtrace.as<char>();
                     ma.maxrows = maxrows;
                     ma.per_thread = md_clust_bytes(maxrows);
                     const size_t cl_smem = sizeof(MdClustSmem) * MDC_WARPS;
                     CUDA_TRY(c, cudaFuncSetAttribute(mdclust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem));
-                    const int cl_ctas = std::min((r1 - r0 + MDC_WARPS - 1) / MDC_WARPS, c->sm_count * 4);
+                    int cl_per_sm = 0;      // resident CTAs per SM at this shared-memory size: the grid is ONE wave
+                    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cl_per_sm, mdclust_kernel, MDC_WARPS * 32, cl_smem));
+                    const int cl_ctas = std::min((r1 - r0 + MDC_WARPS - 1) / MDC_WARPS, c->sm_count * std::max(cl_per_sm, 1));
                     CUDA_TRY(c, c->d_mdscratch.ensure(ma.per_thread * (size_t)cl_ctas * MDC_WARPS));
                     ma.scratch = c->d_mdscratch.as<char>();
                     mdfwd_kernel<<<nblk(r1 - r0, 64), 64, 0, st>>>(ma);
