@@ -165,7 +165,7 @@ struct itsx_ctx {
 
     // scratch of the search stages
     DevBuf d_msvres, d_flag, d_scan, d_list, d_bounds, d_filtersc, d_list2, d_fsc2;
-    DevBuf d_fwdsc, d_spec, d_ndom, d_env, d_envoff, d_envwork, d_envout, d_envscratch, d_pairout;
+    DevBuf d_fwdsc, d_fbscale, d_spec, d_ndom, d_env, d_envoff, d_envwork, d_envout, d_envscratch, d_pairout;
     // paired-end merge (merge.cu): inputs, slotted and compacted outputs of the last itsx_merge_pairs
     DevBuf d_mg_fseq, d_mg_fqual, d_mg_foff, d_mg_rseq, d_mg_rqual, d_mg_roff, d_mg_tabs, d_mg_hist;
     DevBuf d_mg_mlen, d_mg_reason, d_mg_sseq, d_mg_squal, d_mg_flag, d_mg_len64, d_mg_kscan, d_mg_lscan;

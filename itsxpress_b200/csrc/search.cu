@@ -458,6 +458,7 @@ struct FbArgs {
     float          *fwdsc;    // out, per entry
     float          *bcksc;
     uint8_t        *ndom;     // out: number of envelopes (0 if the entry failed F3)
+    float          *scale;    // split decode: 1 / bN of every entry that passed F3 (fbdec_kernel's scaleproduct)
     int32_t        *env;      // out: [entry][MAXDOM][2], jenv carries the multidomain flag in bit 30
     unsigned long long *counters;
 };
@@ -494,24 +495,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 #ifndef FB_DECODE_PF
 #define FB_DECODE_PF 16
 #endif
-#ifndef FB_DECODE_RING
-#define FB_DECODE_RING 0
+// FB_SPLIT_DECODE: posterior decoding + region finding run as their own kernel (fbdec_kernel) over a slab that holds
+// every tile of the launch, instead of at the end of fb_kernel over a slab per resident warp
+#ifndef FB_SPLIT_DECODE
+#define FB_SPLIT_DECODE 0
 #endif
-__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void l1_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __global__ void __launch_bounds__(FB_THREADS, FB_CTAS_PER_SM)
 fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
 {
     __shared__ __align__(16) float s_e[16 * ESTRIDE];     // [residue code][node]: odds of the launch's profile
-#if FB_DECODE_RING > 0
-    __shared__ __align__(16) float s_ring[(FB_THREADS / 32) * FB_DECODE_RING * SPEC_C * 32];
-#endif
     for (int t = threadIdx.x; t < 16 * ESTRIDE; t += FB_THREADS) {
         const int x = t / ESTRIDE, k = t - x * ESTRIDE;
         s_e[t] = k <= MAXM ? a.etab[k * 16 + x] : 0.f;
@@ -521,10 +515,15 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
     const int warp_in_grid = (blockIdx.x * FB_THREADS + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * FB_THREADS) >> 5;
     const int ntiles = (a.count + 31) >> 5;
+#if !FB_SPLIT_DECODE
     float *sp = a.spec + (size_t)warp_in_grid * (size_t)(a.Lmax + 1) * SPEC_C * 32 + lane;
+#endif
 #define SPEC(row, c) sp[((size_t)(row) * SPEC_C + (c)) * 32]
 
     for (int tile = warp_in_grid; tile < ntiles; tile += nwarps) {
+#if FB_SPLIT_DECODE
+        float *sp = a.spec + (size_t)tile * (size_t)(a.Lmax + 1) * SPEC_C * 32 + lane;
+#endif
         const int ent = tile * 32 + lane;
         const bool valid = ent < a.count;
         int L = 0;
@@ -723,6 +722,16 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
             }
         }
 
+#if FB_SPLIT_DECODE
+        if (pass) {
+            a.bcksc[ent] = btotscale + logf_via_double(bN);
+            a.scale[ent] = 1.0f / bN;
+        }
+        if (valid) a.ndom[ent] = pass ? 1 : 0;      // fbdec_kernel replaces the mark by the number of envelopes
+    }
+#undef SPEC
+}
+#else
         // ------------------------------ decoding + regions ------------------------------
         int nd = 0;
         if (pass) {
@@ -743,29 +752,6 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
                 for (int cc = 0; cc < SPEC_C; cc++) l1_prefetch(&SPEC(j, cc));
             }
 #endif
-#if FB_DECODE_RING > 0
-            // the rows come through a per-warp shared-memory ring filled by cp.async FB_DECODE_RING rows ahead
-            // (each lane copies and reads its own column: no cross-lane ordering needed)
-            float *ring = s_ring + ((size_t)(threadIdx.x >> 5) * FB_DECODE_RING * SPEC_C) * 32 + lane;
-#pragma unroll 1
-            for (int j = 1; j <= FB_DECODE_RING; j++) {
-                if (j <= L) {
-#pragma unroll
-                    for (int cc = 0; cc < SPEC_C; cc++) cp_async4(ring + ((j % FB_DECODE_RING) * SPEC_C + cc) * 32, &SPEC(j, cc));
-                }
-                cp_async_commit();
-            }
-            for (int j = 1; j <= L; j++) {
-                cp_async_wait<FB_DECODE_RING - 1>();
-                const float *rs = ring + (j % FB_DECODE_RING) * SPEC_C * 32;
-                const float v0 = rs[0], v1 = rs[32], v2 = rs[64], v3 = rs[96], v4 = rs[128];
-                if (j + FB_DECODE_RING <= L) {
-#pragma unroll
-                    for (int cc = 0; cc < SPEC_C; cc++)
-                        cp_async4(ring + ((j % FB_DECODE_RING) * SPEC_C + cc) * 32, &SPEC(j + FB_DECODE_RING, cc));
-                }
-                cp_async_commit();
-#else
             float r0 = SPEC(1, 0), r1 = SPEC(1, 1), r2 = SPEC(1, 2), r3 = SPEC(1, 3), r4 = SPEC(1, 4);
             for (int j = 1; j <= L; j++) {
 #if FB_DECODE_PF > 0
@@ -776,7 +762,6 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
 #endif
                 const float v0 = r0, v1 = r1, v2 = r2, v3 = r3, v4 = r4;
                 if (j < L) { r0 = SPEC(j + 1, 0); r1 = SPEC(j + 1, 1); r2 = SPEC(j + 1, 2); r3 = SPEC(j + 1, 3); r4 = SPEC(j + 1, 4); }
-#endif
                 const float db = v0 * scaleproduct, de = v1 * scaleproduct;
                 const float btot_p = btot, etot_p = etot;
                 btot = btot + db;
@@ -818,6 +803,93 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
     }
 #undef SPEC
 }
+#endif
+
+
+#if FB_SPLIT_DECODE
+// K9a: posterior decoding + region finding of every entry that passed F3: one lane per entry over the launch's slab
+// ([tile][row][5][lane], coalesced 128-byte rows), light on registers so that many warps hide the row-to-row latency
+__global__ void __launch_bounds__(128) fbdec_kernel(const FbArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int ent = tile * 32 + lane;
+    if (ent >= a.count || a.ndom[ent] == 0) return;
+    const int idx = a.list[ent];
+    const int sl = idx - a.prof * a.ns;
+    const int64_t sq = a.order[a.s0 + sl];
+    const int L = a.seqlen[sq];
+    float *sp = a.spec + (size_t)tile * (size_t)(a.Lmax + 1) * SPEC_C * 32 + lane;
+#define SPEC(row, c) sp[((size_t)(row) * SPEC_C + (c)) * 32]
+    int nd = 0;
+    {
+    const float scaleproduct = a.scale[ent];
+    const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
+    float btot = 0.f, etot = 0.f;
+    int ri = -1;
+    bool triggered = false;
+    int nmulti = 0;
+    SPEC(0, 0) = 0.f; SPEC(0, 1) = 0.f;   // btot[0], etot[0]
+#if FB_DECODE_PF > 0
+    // rows FB_DECODE_PF ahead are pulled into L1 (CCTL.PF1: no register, no unrolling); the row-ahead register
+    // loads below then hit L1 instead of waiting out an HBM round trip per row
+#pragma unroll 1
+    for (int j = 2; j <= FB_DECODE_PF && j <= L; j++) {
+#pragma unroll
+        for (int cc = 0; cc < SPEC_C; cc++) l1_prefetch(&SPEC(j, cc));
+    }
+#endif
+    float r0 = SPEC(1, 0), r1 = SPEC(1, 1), r2 = SPEC(1, 2), r3 = SPEC(1, 3), r4 = SPEC(1, 4);
+    for (int j = 1; j <= L; j++) {
+#if FB_DECODE_PF > 0
+        if (j + FB_DECODE_PF <= L) {
+#pragma unroll
+            for (int cc = 0; cc < SPEC_C; cc++) l1_prefetch(&SPEC(j + FB_DECODE_PF, cc));
+        }
+#endif
+        const float v0 = r0, v1 = r1, v2 = r2, v3 = r3, v4 = r4;
+        if (j < L) { r0 = SPEC(j + 1, 0); r1 = SPEC(j + 1, 1); r2 = SPEC(j + 1, 2); r3 = SPEC(j + 1, 3); r4 = SPEC(j + 1, 4); }
+        const float db = v0 * scaleproduct, de = v1 * scaleproduct;
+        const float btot_p = btot, etot_p = etot;
+        btot = btot + db;
+        etot = etot + de;
+        float njcp = v2 * scaleproduct;
+        njcp += v3 * scaleproduct;
+        njcp += v4 * scaleproduct;
+        const float mocc = 1.f - njcp;
+        SPEC(j, 0) = btot; SPEC(j, 1) = etot;
+        if (!triggered) {
+            if (mocc - (btot - btot_p) < rt2) ri = j;
+            else if (ri == -1) ri = j;
+            if (mocc >= rt1) triggered = true;
+        } else if (mocc - (etot - etot_p) < rt2) {
+            float mx = -1.0f;
+            const float e0 = SPEC(ri - 1, 1);
+            for (int z = ri; z <= j; z++) {
+                const float x1 = SPEC(z, 1) - e0, x2 = btot - SPEC(z - 1, 0);
+                const float en = x1 < x2 ? x1 : x2;
+                if (en > mx) mx = en;
+            }
+            const int multi = mx >= rt3;
+            nmulti += multi;
+            if (nd < ITSX_MAXDOM) {
+                a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 0] = ri;
+                a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 1] = j | (multi << 30);
+                nd++;
+            } else {
+                atomicAdd(&a.counters[CNT_DOM_OVERFLOW], 1ull);
+            }
+            ri = -1;
+            triggered = false;
+        }
+    }
+    if (nmulti) atomicAdd(&a.counters[CNT_MULTI], (unsigned long long)nmulti);
+    atomicAdd(&a.counters[CNT_BCK_ROWS], (unsigned long long)L);
+    }
+    a.ndom[ent] = (uint8_t)nd;
+#undef SPEC
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // K9b: multidomain regions (p7_domaindef.c: region_trace_ensemble + p7_spensemble_Cluster), operation
@@ -835,7 +907,6 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
 // The cluster envelopes carry bit 29 ("null2 done"): env_kernel still gives their unihit Forward score, final_kernel
 // takes their domcorrection from envdc[] and the region-wide sum of the trace n2sc from n2reg[].
 constexpr int MD_NSAMPLES = 200;
-constexpr int MD_MAXSEG = 1024;
 constexpr int MD_MAXTDOM = 4;                  // domains kept per trace
 constexpr int MD_W = MAXM + 1;
 constexpr int MD_STREAM_LOG2 = 20;
@@ -1156,8 +1227,8 @@ __global__ void __launch_bounds__(128) mdtrace_kernel(const MdArgs a, const __gr
 // the 200 records one after the other: two dependent HBM latencies per trace, 0.43 ms per region).  Only the float sums
 // keep the oracle's order (per position: samples in trace order; per envelope and per region: positions ascending).
 //   A. 32 traces per round: lanes load their trace's domains (left to right), scan the counts into the flat sample
-//      list (key + trace per sample, for B-D) and broadcast the domains one by one by shuffles; lanes own positions (four
-//      blocks of 32 per pass over the traces) and sum the null2 odds of the covering domains in registers
+//      list (key + trace per sample, for B-D) and stage the round's samples in shared memory; then lanes own positions
+//      (up to four blocks of 32 per pass over the traces) and sum the null2 odds of the covering samples in registers
 //   B. distinct segments through a shared-memory hash table (the slot keeps the FIRST sample with that key, so the
 //      segments are numbered in order of first appearance like a serial scan would), multiplicities by atomics
 //   C. level-synchronous component search: lanes own unassigned segments and test them against the frontier
@@ -1168,7 +1239,7 @@ constexpr int MDC_HT = 1024;                   // hash slots (power of two > MDC
 constexpr int MDC_PB = 4;                      // position blocks (of 32) per pass over the traces
 static_assert(MDC_CAP >= MD_NSAMPLES * MD_MAXTDOM && MDC_CAP % 32 == 0 && MDC_HT > MDC_CAP, "mdclust capacities");
 struct MdClustSmem {
-    unsigned long long skey[MDC_CAP];          // distinct segments: i | j << 16 | k << 32 | m << 40
+    unsigned long long skey[MDC_CAP];          // distinct segments: i | j << 16 | (i - k) << 32 | (j - m) << 48
     uint32_t htab[MDC_HT];
     uint32_t scount[MDC_CAP];                  // how many samples hit the segment
     int16_t  asg[MDC_CAP];
@@ -1180,26 +1251,36 @@ __host__ __device__ inline size_t md_clust_bytes(int maxrows)
     size_t b = (size_t)MDC_CAP * 8 + (size_t)(maxrows + 1) * 4 + (size_t)MDC_CAP * (2 + 1);
     return (b + 255) / 256 * 256;
 }
-__device__ __forceinline__ bool md_link_key(unsigned long long ka, unsigned long long kb)
+// link_spsamples on segments stored as four 16-bit fields  i | j << 16 | (i - k) << 32 | (j - m) << 48  (the two
+// diagonals are what most pairs of different domains differ in, so they are tested first; the conjunction is the same).
+// (float)nov / (float)n < 0.8f  is decided exactly by  5 nov < 4 n : for n < 2^16 the quotient is either 4/5 (rounds to
+// 0.8f, not smaller) or at least 1 / (5 n) > 3e-6 away from it, far more than a float ulp.
+__device__ __forceinline__ unsigned long long md_seg_word(unsigned long long key)
 {
-    const int ai = (int)(ka & 0xffffu), aj = (int)((ka >> 16) & 0xffffu), ak = (int)((ka >> 32) & 0xffu), am = (int)((ka >> 40) & 0xffu);
-    const int bi = (int)(kb & 0xffffu), bj = (int)((kb >> 16) & 0xffffu), bk = (int)((kb >> 32) & 0xffu), bm = (int)((kb >> 40) & 0xffu);
-    // link_spsamples.  (float)nov / (float)n < 0.8f  is decided exactly by  5 nov < 4 n : for n < 2^16 the quotient is
-    // either 4/5 (rounds to 0.8f, not smaller) or at least 1 / (5 n) > 3e-6 away from it, far more than a float ulp.
+    const int i = (int)(key & 0xffffu), j = (int)((key >> 16) & 0xffffu), k = (int)((key >> 32) & 0xffu), m = (int)((key >> 40) & 0xffu);
+    return (unsigned long long)(uint32_t)(i | (j << 16)) |
+           ((unsigned long long)(uint32_t)(((i - k) & 0xffff) | (((j - m) & 0xffff) << 16)) << 32);
+}
+__device__ __forceinline__ bool md_link_word(unsigned long long wa, unsigned long long wb)
+{
+    const uint32_t alo = (uint32_t)wa, blo = (uint32_t)wb, ahi = (uint32_t)(wa >> 32), bhi = (uint32_t)(wb >> 32);
+    // differences of the 16-bit diagonal fields, modulo 2^16 (exact: positions are below 2^16, nodes below 2^8)
+    const int dd = (int)(short)(uint16_t)((ahi & 0xffffu) - (bhi & 0xffffu)), de = (int)(short)(uint16_t)((ahi >> 16) - (bhi >> 16));
+    if ((unsigned)(dd + 4) > 8u) return false;
+    if ((unsigned)(de + 4) > 8u) return false;
+    const int ai = (int)(alo & 0xffffu), aj = (int)(alo >> 16), bi = (int)(blo & 0xffffu), bj = (int)(blo >> 16);
     int nov = min(aj, bj) - max(ai, bi) + 1;
     int n = min(aj - ai + 1, bj - bi + 1);
     if (5 * nov < 4 * n) return false;
+    const int ak = (ai - (int)(ahi & 0xffffu)) & 0xffff, am = (aj - (int)(ahi >> 16)) & 0xffff;
+    const int bk = (bi - (int)(bhi & 0xffffu)) & 0xffff, bm = (bj - (int)(bhi >> 16)) & 0xffff;
     nov = min(am, bm) - max(ak, bk) + 1;
     n = min(am - ak + 1, bm - bk + 1);
-    if (5 * nov < 4 * n) return false;
-    if (abs((ai - ak) - (bi - bk)) > 4) return false;
-    if (abs((aj - am) - (bj - bm)) > 4) return false;
-    return true;
+    return 5 * nov >= 4 * n;
 }
-// null2 odds of residue code x under a domain's (A, C, G, T) odds: IUPAC codes average their bases in base order
-__device__ __forceinline__ float md_null2_of(uint32_t x, float a, float c, float g, float t)
+// null2 odds of an IUPAC residue code x under a domain's (A, C, G, T) odds: the average of its bases in base order; N is 1
+__device__ __noinline__ float md_null2_iupac(uint32_t x, float a, float c, float g, float t)
 {
-    if (x < 4) return x == 0 ? a : x == 1 ? c : x == 2 ? g : t;
     if (x == 15) return 1.0f;
     const uint32_t dmask = (uint32_t)(0x0FD7EB96C3A58421ull >> (4 * x)) & 15u;
     float sa = 0.f;
@@ -1209,6 +1290,40 @@ __device__ __forceinline__ float md_null2_of(uint32_t x, float a, float c, float
     if (dmask & 4u) { sa += g; na++; }
     if (dmask & 8u) { sa += t; na++; }
     return sa / (float)na;
+}
+// lanes own positions (pos0 + 32 b): the staged samples in order, each adds its odds where it covers the position
+template <int NB, bool PLAIN>
+__device__ __forceinline__ void md_accumulate(const uint32_t *st_ft, const float4 *st_n2, int count, int pos0,
+                                              const uint32_t (&x)[MDC_PB], float (&sum)[MDC_PB], int (&cover)[MDC_PB])
+{
+    static_assert(NB <= MDC_PB, "position blocks per pass");
+#pragma unroll 4
+    for (int q = 0; q < count; q++) {
+        const uint32_t f = st_ft[q];
+        const int from = (int)(f & 0xffffu), len = (int)(f >> 16) - from;
+        const float *o = (const float *)(st_n2 + q);
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            if ((unsigned)(pos0 + 32 * b - from) <= (unsigned)len) {
+                float v;
+                if (PLAIN || x[b] < 4u) v = o[x[b] & 3u];
+                else v = md_null2_iupac(x[b], o[0], o[1], o[2], o[3]);
+                sum[b] += v;
+                cover[b]++;
+            }
+        }
+    }
+}
+template <bool PLAIN>
+__device__ __forceinline__ void md_accumulate_nb(int nb, const uint32_t *st_ft, const float4 *st_n2, int count, int pos0,
+                                                 const uint32_t (&x)[MDC_PB], float (&sum)[MDC_PB], int (&cover)[MDC_PB])
+{
+    switch (nb) {
+    case 1: md_accumulate<1, PLAIN>(st_ft, st_n2, count, pos0, x, sum, cover); break;
+    case 2: md_accumulate<2, PLAIN>(st_ft, st_n2, count, pos0, x, sum, cover); break;
+    case 3: md_accumulate<3, PLAIN>(st_ft, st_n2, count, pos0, x, sum, cover); break;
+    default: md_accumulate<4, PLAIN>(st_ft, st_n2, count, pos0, x, sum, cover); break;
+    }
 }
 __global__ void __launch_bounds__(MDC_WARPS * 32) mdclust_kernel(const MdArgs a)
 {
@@ -1232,17 +1347,24 @@ __global__ void __launch_bounds__(MDC_WARPS * 32) mdclust_kernel(const MdArgs a)
         const uint32_t *t_ft = (const uint32_t *)(tb + MD_TRACE_FT), *t_km = (const uint32_t *)(tb + MD_TRACE_KM);
         const float4 *t_n2 = (const float4 *)(tb + MD_TRACE_N2);
         // ---- A. flat sample list + n2sc per position ----
+        // the samples of one round (32 traces, left to right within a trace) are staged in the segment area, which
+        // phase B only fills afterwards: from | to << 16 and the four null2 odds per sample
+        uint32_t *st_ft = (uint32_t *)sm.skey;                       // [32 * MD_MAXTDOM]
+        float4 *st_n2 = (float4 *)(sm.skey + 16 * MD_MAXTDOM);       // [32 * MD_MAXTDOM]
         int nraw = 0;
         for (int pg = 1; pg <= Ld; pg += 32 * MDC_PB) {
             const bool first_pass = pg == 1;
+            const int nb = min(MDC_PB, (Ld - pg + 32) >> 5);         // position blocks of this pass
             uint32_t x[MDC_PB];
             float sum[MDC_PB];
             int cover[MDC_PB];
+            bool plain = true;                     // no IUPAC / N residue among this pass's positions (warp-uniform)
 #pragma unroll
             for (int b = 0; b < MDC_PB; b++) {
                 const int pos = pg + 32 * b + lane;
-                x[b] = pos <= Ld ? residue_at(g.w, ireg - 1 + pos - 1) : 15u;
+                x[b] = pos <= Ld ? residue_at(g.w, ireg - 1 + pos - 1) : 0u;
                 sum[b] = 0.f; cover[b] = 0;
+                plain = plain && !__any_sync(FULL, x[b] >= 4u);
             }
             for (int t0 = 0; t0 < MD_NSAMPLES; t0 += 32) {
                 const int t = t0 + lane, tt = min(t, MD_NSAMPLES - 1);
@@ -1256,46 +1378,31 @@ __global__ void __launch_bounds__(MDC_WARPS * 32) mdclust_kernel(const MdArgs a)
                     ft[sl] = 0u; n2[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (d >= 0) { ft[sl] = t_ft[d * MD_NSAMPLES + tt]; n2[sl] = t_n2[d * MD_NSAMPLES + tt]; }
                 }
-                if (first_pass) {
-                    int inc = nd;
+                int inc = nd;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(FULL, inc, o);
-                        if (lane >= o) inc += v;
-                    }
-                    const int at = nraw + inc - nd;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const int at = inc - nd, count = __shfl_sync(FULL, inc, 31);
+                __syncwarp();                      // the previous round has been read
 #pragma unroll
-                    for (int sl = 0; sl < MD_MAXTDOM; sl++) {
-                        if (sl < nd) {
+                for (int sl = 0; sl < MD_MAXTDOM; sl++) {
+                    if (sl < nd) {
+                        st_ft[at + sl] = ft[sl];
+                        st_n2[at + sl] = n2[sl];
+                        if (first_pass) {
                             const uint32_t km = t_km[(nd - 1 - sl) * MD_NSAMPLES + tt];
                             const unsigned long long si = (ft[sl] & 0xffffu) + (uint32_t)(ireg - 1), sj = (ft[sl] >> 16) + (uint32_t)(ireg - 1);
-                            rkey[at + sl] = (si & 0xffffu) | ((sj & 0xffffu) << 16) | ((unsigned long long)(km & 0xffffu) << 32);
-                            rtr[at + sl] = (uint8_t)t;
-                        }
-                    }
-                    nraw += __shfl_sync(FULL, inc, 31);
-                }
-                // the domains of the 32 traces one by one, in trace order
-                for (unsigned todo = __ballot_sync(FULL, nd > 0); todo; todo &= todo - 1u) {
-                    const int src = __ffs(todo) - 1;
-                    const int ndv = __shfl_sync(FULL, nd, src);
-#pragma unroll
-                    for (int sl = 0; sl < MD_MAXTDOM; sl++) {
-                        if (sl >= ndv) break;
-                        const uint32_t f = __shfl_sync(FULL, ft[sl], src);
-                        const int from = (int)(f & 0xffffu), to = (int)(f >> 16);
-                        if (to < pg || from >= pg + 32 * MDC_PB) continue;
-                        const float oa = __shfl_sync(FULL, n2[sl].x, src), oc = __shfl_sync(FULL, n2[sl].y, src);
-                        const float og = __shfl_sync(FULL, n2[sl].z, src), ot = __shfl_sync(FULL, n2[sl].w, src);
-#pragma unroll
-                        for (int b = 0; b < MDC_PB; b++) {
-                            const int p0 = pg + 32 * b;
-                            if (to < p0 || from > p0 + 31) continue;
-                            const int pos = p0 + lane;
-                            if (pos >= from && pos <= to) { sum[b] += md_null2_of(x[b], oa, oc, og, ot); cover[b]++; }
+                            rkey[nraw + at + sl] = (si & 0xffffu) | ((sj & 0xffffu) << 16) | ((unsigned long long)(km & 0xffffu) << 32);
+                            rtr[nraw + at + sl] = (uint8_t)t;
                         }
                     }
                 }
+                if (first_pass) nraw += count;
+                __syncwarp();
+                if (plain) md_accumulate_nb<true>(nb, st_ft, st_n2, count, pg + lane, x, sum, cover);
+                else md_accumulate_nb<false>(nb, st_ft, st_n2, count, pg + lane, x, sum, cover);
             }
 #pragma unroll
             for (int b = 0; b < MDC_PB; b++) {
@@ -1303,6 +1410,7 @@ __global__ void __launch_bounds__(MDC_WARPS * 32) mdclust_kernel(const MdArgs a)
                 if (pos <= Ld) acc[pos] = logf_via_double((sum[b] + (float)(MD_NSAMPLES - cover[b])) / (float)MD_NSAMPLES);
             }
         }
+        __syncwarp();
         for (int h = lane; h < MDC_HT; h += 32) sm.htab[h] = EMPTY;
         __syncwarp();
         // n2sc of the region: the sum in position order
@@ -1334,7 +1442,7 @@ __global__ void __launch_bounds__(MDC_WARPS * 32) mdclust_kernel(const MdArgs a)
             const unsigned m = __ballot_sync(FULL, first);
             if (first) {
                 const int id = nseg + __popc(m & lt);
-                sm.skey[id] = rkey[q];
+                sm.skey[id] = md_seg_word(rkey[q]);
                 sm.scount[id] = 0u;
                 sm.asg[id] = -1;
                 sm.htab[h] = 0x80000000u | (uint32_t)id;
@@ -1364,7 +1472,7 @@ __global__ void __launch_bounds__(MDC_WARPS * 32) mdclust_kernel(const MdArgs a)
                     bool take = false;
                     if (bb < nseg && sm.asg[bb] < 0) {
                         const unsigned long long kb = sm.skey[bb];
-                        for (int f = head; f < tail && !take; f++) take = md_link_key(sm.skey[sm.queue[f]], kb);
+                        for (int f = head; f < tail && !take; f++) take = md_link_word(sm.skey[sm.queue[f]], kb);
                     }
                     const unsigned m = __ballot_sync(FULL, take);
                     if (take) {
@@ -2647,7 +2755,15 @@ int search_stage1(itsx_ctx *c)
         CUDA_TRY(c, c->d_ndom.ensure((size_t)n2 + 16));
         CUDA_TRY(c, c->d_env.ensure((size_t)n2 * ITSX_MAXDOM * 2 * 4));
         const size_t slab = (size_t)(Lmax + 1) * SPEC_C * 32 * 4;
+#if FB_SPLIT_DECODE
+        // the slab of a launch holds all its tiles (fbdec_kernel reads them back): a profile's worklist goes in pieces of
+        // at most two tiles per resident warp
+        const int fb_piece_tiles = fb_warps_per_lane * 2;
+        CUDA_TRY(c, c->d_spec.ensure(slab * (size_t)fb_piece_tiles * NLANE));
+        CUDA_TRY(c, c->d_fbscale.ensure((size_t)n2 * 4));
+#else
         CUDA_TRY(c, c->d_spec.ensure(slab * fb_warps_per_lane * NLANE));
+#endif
         CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
         for (int l = 0; l < NLANE; l++) CUDA_TRY(c, cudaStreamWaitEvent(c->lanes[l], c->ev_a, 0));
         int lane_rr = 0;
@@ -2671,11 +2787,28 @@ int search_stage1(itsx_ctx *c)
             fa.ndom = c->d_ndom.as<uint8_t>() + b0;
             fa.env = c->d_env.as<int32_t>() + (size_t)b0 * ITSX_MAXDOM * 2;
             fa.counters = cnt;
-            const int tiles = (cntp + 31) / 32;
+            fa.scale = nullptr;
             const int wpc = FB_THREADS / 32;
+#if FB_SPLIT_DECODE
+            fa.spec = (float *)(c->d_spec.as<char>() + slab * (size_t)fb_piece_tiles * l);
+            for (int e0 = 0; e0 < cntp; e0 += fb_piece_tiles * 32) {
+                FbArgs fp = fa;
+                fp.count = std::min(cntp - e0, fb_piece_tiles * 32);
+                fp.list = fa.list + e0; fp.filtersc = fa.filtersc + e0; fp.fwdsc = fa.fwdsc + e0; fp.bcksc = fa.bcksc + e0;
+                fp.ndom = fa.ndom + e0; fp.env = fa.env + (size_t)e0 * ITSX_MAXDOM * 2;
+                fp.scale = c->d_fbscale.as<float>() + b0 + e0;
+                const int tiles = (fp.count + 31) / 32;
+                const int ctas = std::min((tiles + wpc - 1) / wpc, c->sm_count * FB_CTAS_PER_SM);
+                fb_kernel<<<ctas, FB_THREADS, 0, c->lanes[l]>>>(c->pconst[p], fp);
+                fbdec_kernel<<<(tiles + 3) / 4, 128, 0, c->lanes[l]>>>(fp);
+                c->launches += 2;
+            }
+#else
+            const int tiles = (cntp + 31) / 32;
             const int ctas = std::min((tiles + wpc - 1) / wpc, c->sm_count * FB_CTAS_PER_SM);
             fb_kernel<<<ctas, FB_THREADS, 0, c->lanes[l]>>>(c->pconst[p], fa);
             c->launches++;
+#endif
         }
         for (int l = 0; l < NLANE; l++) {
             CUDA_TRY(c, cudaEventRecord(c->lane_ev[l], c->lanes[l]));
