@@ -112,7 +112,7 @@ struct itsx_ctx {
     DevBuf d_logsum;      // float [16000] p7_FLogsum table
     DevBuf d_vtab, d_xwmove, d_vneed, d_vpass;   // Viterbi filter: int32 [P][VIT_WORDS] tables, int16 xw_move per length, per-entry flags
     DevBuf d_mdtab;       // float [P][ITSX_MAXM+2][8]: transitions out of node k + B->M_k (multidomain resolver)
-    DevBuf d_mdlist, d_envdc, d_n2reg, d_mdscratch, d_mdreg, d_mdcell, d_mdtrace, d_mdres;   // multidomain worklist (+ count), per-envelope trace domcorrection, per-entry region n2sc sum
+    DevBuf d_mdlist, d_envdc, d_n2reg, d_mdreg, d_mdres, d_mdscratch[2], d_mdcell[2], d_mdtrace[2];   // multidomain worklist (+ count), per-envelope trace domcorrection, per-entry region n2sc sum
     std::vector<ProfConst> pconst;   // host copies handed to the per-profile launches
 
     // reads of the last derep (device resident)

@@ -43,6 +43,8 @@ constexpr int ENV_CTAS_PER_SM = 2;
 constexpr int SPEC_C = 5;                  // parser specials kept per row
 constexpr int ENV_ROWF = MAXM + 1;             // floats per envelope row: M[1..45] (cols 0..44), Eraw (col 45)
 constexpr int ENV_ROWBYTES = ENV_ROWF * 32 * 4;    // one row of one warp: 5 888 B, contiguous
+constexpr int ENV_RING = 2;                    // rows of the Backward read-back ring per warp (a power of two; 4 measured slower)
+static_assert((ENV_RING & (ENV_RING - 1)) == 0 && ENV_RING >= 2, "ring depth");
 constexpr double kLn2 = 0.69314718055994529;
 constexpr int ESTRIDE = 52;                // floats per residue row of the shared emission table (48 used)
 // e_k of residue row `er` (float4 view): one 128-bit shared load serves nodes 4q .. 4q+3
@@ -495,11 +497,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 #ifndef FB_DECODE_PF
 #define FB_DECODE_PF 16
 #endif
-// FB_SPLIT_DECODE: posterior decoding + region finding run as their own kernel (fbdec_kernel) over a slab that holds
-// every tile of the launch, instead of at the end of fb_kernel over a slab per resident warp
-#ifndef FB_SPLIT_DECODE
-#define FB_SPLIT_DECODE 0
-#endif
 __device__ __forceinline__ void l1_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __global__ void __launch_bounds__(FB_THREADS, FB_CTAS_PER_SM)
@@ -515,15 +512,11 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
     const int warp_in_grid = (blockIdx.x * FB_THREADS + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * FB_THREADS) >> 5;
     const int ntiles = (a.count + 31) >> 5;
-#if !FB_SPLIT_DECODE
-    float *sp = a.spec + (size_t)warp_in_grid * (size_t)(a.Lmax + 1) * SPEC_C * 32 + lane;
-#endif
 #define SPEC(row, c) sp[((size_t)(row) * SPEC_C + (c)) * 32]
 
     for (int tile = warp_in_grid; tile < ntiles; tile += nwarps) {
-#if FB_SPLIT_DECODE
+        // the slab of the launch holds every tile: fbdec_kernel reads the rows back
         float *sp = a.spec + (size_t)tile * (size_t)(a.Lmax + 1) * SPEC_C * 32 + lane;
-#endif
         const int ent = tile * 32 + lane;
         const bool valid = ent < a.count;
         int L = 0;
@@ -722,7 +715,6 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
             }
         }
 
-#if FB_SPLIT_DECODE
         if (pass) {
             a.bcksc[ent] = btotscale + logf_via_double(bN);
             a.scale[ent] = 1.0f / bN;
@@ -731,82 +723,7 @@ fb_kernel(const __grid_constant__ ProfConst pc, const FbArgs a)
     }
 #undef SPEC
 }
-#else
-        // ------------------------------ decoding + regions ------------------------------
-        int nd = 0;
-        if (pass) {
-            a.bcksc[ent] = btotscale + logf_via_double(bN);
-            const float scaleproduct = 1.0f / bN;
-            const float rt1 = 0.25f, rt2 = 0.10f, rt3 = 0.20f;
-            float btot = 0.f, etot = 0.f;
-            int ri = -1;
-            bool triggered = false;
-            int nmulti = 0;
-            SPEC(0, 0) = 0.f; SPEC(0, 1) = 0.f;   // btot[0], etot[0]
-#if FB_DECODE_PF > 0
-            // rows FB_DECODE_PF ahead are pulled into L1 (CCTL.PF1: no register, no unrolling); the row-ahead register
-            // loads below then hit L1 instead of waiting out an HBM round trip per row
-#pragma unroll 1
-            for (int j = 2; j <= FB_DECODE_PF && j <= L; j++) {
-#pragma unroll
-                for (int cc = 0; cc < SPEC_C; cc++) l1_prefetch(&SPEC(j, cc));
-            }
-#endif
-            float r0 = SPEC(1, 0), r1 = SPEC(1, 1), r2 = SPEC(1, 2), r3 = SPEC(1, 3), r4 = SPEC(1, 4);
-            for (int j = 1; j <= L; j++) {
-#if FB_DECODE_PF > 0
-                if (j + FB_DECODE_PF <= L) {
-#pragma unroll
-                    for (int cc = 0; cc < SPEC_C; cc++) l1_prefetch(&SPEC(j + FB_DECODE_PF, cc));
-                }
-#endif
-                const float v0 = r0, v1 = r1, v2 = r2, v3 = r3, v4 = r4;
-                if (j < L) { r0 = SPEC(j + 1, 0); r1 = SPEC(j + 1, 1); r2 = SPEC(j + 1, 2); r3 = SPEC(j + 1, 3); r4 = SPEC(j + 1, 4); }
-                const float db = v0 * scaleproduct, de = v1 * scaleproduct;
-                const float btot_p = btot, etot_p = etot;
-                btot = btot + db;
-                etot = etot + de;
-                float njcp = v2 * scaleproduct;
-                njcp += v3 * scaleproduct;
-                njcp += v4 * scaleproduct;
-                const float mocc = 1.f - njcp;
-                SPEC(j, 0) = btot; SPEC(j, 1) = etot;
-                if (!triggered) {
-                    if (mocc - (btot - btot_p) < rt2) ri = j;
-                    else if (ri == -1) ri = j;
-                    if (mocc >= rt1) triggered = true;
-                } else if (mocc - (etot - etot_p) < rt2) {
-                    float mx = -1.0f;
-                    const float e0 = SPEC(ri - 1, 1);
-                    for (int z = ri; z <= j; z++) {
-                        const float x1 = SPEC(z, 1) - e0, x2 = btot - SPEC(z - 1, 0);
-                        const float en = x1 < x2 ? x1 : x2;
-                        if (en > mx) mx = en;
-                    }
-                    const int multi = mx >= rt3;
-                    nmulti += multi;
-                    if (nd < ITSX_MAXDOM) {
-                        a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 0] = ri;
-                        a.env[((size_t)ent * ITSX_MAXDOM + nd) * 2 + 1] = j | (multi << 30);
-                        nd++;
-                    } else {
-                        atomicAdd(&a.counters[CNT_DOM_OVERFLOW], 1ull);
-                    }
-                    ri = -1;
-                    triggered = false;
-                }
-            }
-            if (nmulti) atomicAdd(&a.counters[CNT_MULTI], (unsigned long long)nmulti);
-            atomicAdd(&a.counters[CNT_BCK_ROWS], (unsigned long long)L);
-        }
-        if (valid) a.ndom[ent] = (uint8_t)nd;
-    }
-#undef SPEC
-}
-#endif
 
-
-#if FB_SPLIT_DECODE
 // K9a: posterior decoding + region finding of every entry that passed F3: one lane per entry over the launch's slab
 // ([tile][row][5][lane], coalesced 128-byte rows), light on registers so that many warps hide the row-to-row latency
 __global__ void __launch_bounds__(128) fbdec_kernel(const FbArgs a)
@@ -889,7 +806,6 @@ __global__ void __launch_bounds__(128) fbdec_kernel(const FbArgs a)
     a.ndom[ent] = (uint8_t)nd;
 #undef SPEC
 }
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // K9b: multidomain regions (p7_domaindef.c: region_trace_ensemble + p7_spensemble_Cluster), operation
@@ -1738,13 +1654,16 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
     // Backward reads the Forward rows back in reverse order: each warp streams its rows (ENV_ROWBYTES, contiguous)
     // into a two-deep shared-memory ring with bulk async copies, one row ahead of use.
     extern __shared__ __align__(128) unsigned char env_smem[];
-    float *ring = (float *)env_smem + (size_t)wid * 2 * ENV_ROWF * 32;
-    unsigned long long *bars = (unsigned long long *)(env_smem + (size_t)(ENV_THREADS / 32) * 2 * ENV_ROWBYTES) + wid * 2;
+    float *ring = (float *)env_smem + (size_t)wid * ENV_RING * ENV_ROWF * 32;
+    unsigned long long *bars = (unsigned long long *)(env_smem + (size_t)(ENV_THREADS / 32) * ENV_RING * ENV_ROWBYTES) + wid * ENV_RING;
     const uint32_t bar0 = smem_u32(bars), ring0 = smem_u32(ring);
-    if (lane == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); }
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < ENV_RING; b++) mbar_init(bar0 + b * 8, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    uint32_t phase[2] = {0u, 0u};
+    uint32_t phases = 0u;                      // bit b: parity the next wait on slot b expects
     const float *rowbase = a.scratch + (size_t)warp_in_grid * (size_t)(a.Ldmax + 1) * ENV_ROWF * 32;
     constexpr int C_E = MAXM;
 
@@ -1851,15 +1770,20 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
         asm volatile("fence.proxy.async;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-            if (Lw >= 1) tma_row_load(ring0 + (Lw & 1) * ENV_ROWBYTES, rowbase + (size_t)Lw * ENV_ROWF * 32, ENV_ROWBYTES, bar0 + (Lw & 1) * 8);
-            if (Lw >= 2) tma_row_load(ring0 + ((Lw - 1) & 1) * ENV_ROWBYTES, rowbase + (size_t)(Lw - 1) * ENV_ROWF * 32, ENV_ROWBYTES, bar0 + ((Lw - 1) & 1) * 8);
+#pragma unroll
+            for (int d = 0; d < ENV_RING; d++) {
+                const int row = Lw - d;
+                if (row >= 1)
+                    tma_row_load(ring0 + (row & (ENV_RING - 1)) * ENV_ROWBYTES, rowbase + (size_t)row * ENV_ROWF * 32, ENV_ROWBYTES,
+                                 bar0 + (row & (ENV_RING - 1)) * 8);
+            }
         }
         // raw E of row i-1 (rescale of the new Backward row) comes through a register, one row ahead
         float qE = (Lw >= 2 && Lw - 1 <= Ld) ? ROW(Lw - 1, C_E) : 0.f;
         for (int i = Lw; i >= 1; i--) {
-            const int b = i & 1;
-            mbar_wait(bar0 + b * 8, phase[b]);
-            phase[b] ^= 1u;
+            const int b = i & (ENV_RING - 1);
+            mbar_wait(bar0 + b * 8, (phases >> b) & 1u);
+            phases ^= 1u << b;
             const float *rs = ring + (size_t)b * ENV_ROWF * 32 + lane;
             const float cEp = qE;
             if (i >= 3 && i - 2 <= Ld) qE = ROW(i - 2, C_E);
@@ -1870,8 +1794,8 @@ env_kernel(const __grid_constant__ ProfConst pc, const EnvArgs a)
                 for (int k = 1; k <= MAXM; k++) nk[k] = fmaf(rs[(k - 1) * 32] * Mx[k], fS, nk[k]);
             }
             __syncwarp();
-            if (lane == 0 && i >= 3)
-                tma_row_load(ring0 + b * ENV_ROWBYTES, rowbase + (size_t)(i - 2) * ENV_ROWF * 32, ENV_ROWBYTES, bar0 + b * 8);
+            if (lane == 0 && i > ENV_RING)
+                tma_row_load(ring0 + b * ENV_ROWBYTES, rowbase + (size_t)(i - ENV_RING) * ENV_ROWF * 32, ENV_ROWBYTES, bar0 + b * 8);
             if (i <= Ld) {
                 if (i > 1) {
                     float fEp, fSp;
@@ -2755,15 +2679,11 @@ int search_stage1(itsx_ctx *c)
         CUDA_TRY(c, c->d_ndom.ensure((size_t)n2 + 16));
         CUDA_TRY(c, c->d_env.ensure((size_t)n2 * ITSX_MAXDOM * 2 * 4));
         const size_t slab = (size_t)(Lmax + 1) * SPEC_C * 32 * 4;
-#if FB_SPLIT_DECODE
         // the slab of a launch holds all its tiles (fbdec_kernel reads them back): a profile's worklist goes in pieces of
         // at most two tiles per resident warp
         const int fb_piece_tiles = fb_warps_per_lane * 2;
         CUDA_TRY(c, c->d_spec.ensure(slab * (size_t)fb_piece_tiles * NLANE));
         CUDA_TRY(c, c->d_fbscale.ensure((size_t)n2 * 4));
-#else
-        CUDA_TRY(c, c->d_spec.ensure(slab * fb_warps_per_lane * NLANE));
-#endif
         CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
         for (int l = 0; l < NLANE; l++) CUDA_TRY(c, cudaStreamWaitEvent(c->lanes[l], c->ev_a, 0));
         int lane_rr = 0;
@@ -2777,7 +2697,6 @@ int search_stage1(itsx_ctx *c)
             fa.count = cntp; fa.order = d_order; fa.s0 = s0; fa.ns = ns; fa.prof = p;
             fa.seqw = c->d_seqw.as<uint32_t>(); fa.woff = c->d_seqwoff.as<int64_t>(); fa.seqlen = c->d_seqlen.as<int32_t>();
             fa.etab = c->d_etab.as<float>() + (size_t)p * (MAXM + 1) * 16;
-            fa.spec = (float *)(c->d_spec.as<char>() + slab * fb_warps_per_lane * l);
             fa.Lmax = Lmax;
             fa.tau = c->prof[p].ev[EV_FTAU]; fa.lambda = c->prof[p].ev[EV_FLAMBDA];
             fa.F3 = c->prm.F3;
@@ -2789,7 +2708,6 @@ int search_stage1(itsx_ctx *c)
             fa.counters = cnt;
             fa.scale = nullptr;
             const int wpc = FB_THREADS / 32;
-#if FB_SPLIT_DECODE
             fa.spec = (float *)(c->d_spec.as<char>() + slab * (size_t)fb_piece_tiles * l);
             for (int e0 = 0; e0 < cntp; e0 += fb_piece_tiles * 32) {
                 FbArgs fp = fa;
@@ -2803,12 +2721,6 @@ int search_stage1(itsx_ctx *c)
                 fbdec_kernel<<<(tiles + 3) / 4, 128, 0, c->lanes[l]>>>(fp);
                 c->launches += 2;
             }
-#else
-            const int tiles = (cntp + 31) / 32;
-            const int ctas = std::min((tiles + wpc - 1) / wpc, c->sm_count * FB_CTAS_PER_SM);
-            fb_kernel<<<ctas, FB_THREADS, 0, c->lanes[l]>>>(c->pconst[p], fa);
-            c->launches++;
-#endif
         }
         for (int l = 0; l < NLANE; l++) {
             CUDA_TRY(c, cudaEventRecord(c->lane_ev[l], c->lanes[l]));
@@ -2862,36 +2774,59 @@ int search_stage1(itsx_ctx *c)
                 ma.res = c->d_mdres.as<MdRes>();
                 ma.e_move = expf(-(float)kLn2);
                 ma.counters = cnt;
-                // chunks of regions: slabs (matrix + row tables) and trace records within a fixed HBM budget
+                // chunks of regions: slabs (matrix + row tables) and trace records within a fixed HBM budget; consecutive
+                // chunks alternate between two side streams with their own buffers, so that the latency-bound Forward fill of
+                // one chunk runs under the issue-bound tracebacks / clustering of the other
                 const size_t row_bytes = (size_t)MD_W * 16 + sizeof(MdRow), reg_bytes = (size_t)MD_TRACE_BYTES;
-                const size_t budget = (size_t)6 << 30;
+                const size_t budget = (size_t)3 << 30;
+                struct MdChunk { int r0, r1, maxrows, ctas; size_t rows; };
+                std::vector<MdChunk> chunks;
+                const size_t cl_smem = sizeof(MdClustSmem) * MDC_WARPS;
+                CUDA_TRY(c, cudaFuncSetAttribute(mdclust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem));
+                int cl_per_sm = 0;      // resident CTAs per SM at this shared-memory size: the grid is ONE wave
+                CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cl_per_sm, mdclust_kernel, MDC_WARPS * 32, cl_smem));
+                size_t need_cell[2] = {0, 0}, need_trace[2] = {0, 0}, need_scr[2] = {0, 0};
                 for (int r0 = 0; r0 < NR;) {
                     int r1 = r0 + 1;
                     while (r1 < NR && (size_t)(h_row[r1 + 1] - h_row[r0]) * row_bytes + (size_t)(r1 + 1 - r0) * reg_bytes <= budget)
                         r1++;
-                    const size_t rows = (size_t)(h_row[r1] - h_row[r0]);
-                    int maxrows = 0;
-                    for (int r = r0; r < r1; r++) maxrows = std::max(maxrows, h_row[r + 1] - h_row[r]);
-                    CUDA_TRY(c, c->d_mdcell.ensure(rows * row_bytes));
-                    CUDA_TRY(c, c->d_mdtrace.ensure((size_t)(r1 - r0) * reg_bytes));
-                    ma.r0 = r0; ma.r1 = r1; ma.row0 = h_row[r0];
-                    ma.cell = c->d_mdcell.as<float4>();
-                    ma.rowrec = (MdRow *)(c->d_mdcell.as<char>() + rows * MD_W * 16);
-                    ma.trace = c->d_mdtrace.as<char>();
-                    ma.maxrows = maxrows;
-                    ma.per_thread = md_clust_bytes(maxrows);
-                    const size_t cl_smem = sizeof(MdClustSmem) * MDC_WARPS;
-                    CUDA_TRY(c, cudaFuncSetAttribute(mdclust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_smem));
-                    int cl_per_sm = 0;      // resident CTAs per SM at this shared-memory size: the grid is ONE wave
-                    CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cl_per_sm, mdclust_kernel, MDC_WARPS * 32, cl_smem));
-                    const int cl_ctas = std::min((r1 - r0 + MDC_WARPS - 1) / MDC_WARPS, c->sm_count * std::max(cl_per_sm, 1));
-                    CUDA_TRY(c, c->d_mdscratch.ensure(ma.per_thread * (size_t)cl_ctas * MDC_WARPS));
-                    ma.scratch = c->d_mdscratch.as<char>();
-                    mdfwd_kernel<<<nblk(r1 - r0, 64), 64, 0, st>>>(ma);
-                    mdtrace_kernel<<<nblk((int64_t)(r1 - r0) * MD_NSAMPLES, 128), 128, 0, st>>>(ma, streams);
-                    mdclust_kernel<<<cl_ctas, MDC_WARPS * 32, cl_smem, st>>>(ma);
-                    c->launches += 3;
+                    MdChunk ch;
+                    ch.r0 = r0; ch.r1 = r1; ch.rows = (size_t)(h_row[r1] - h_row[r0]); ch.maxrows = 0;
+                    for (int r = r0; r < r1; r++) ch.maxrows = std::max(ch.maxrows, h_row[r + 1] - h_row[r]);
+                    ch.ctas = std::min((r1 - r0 + MDC_WARPS - 1) / MDC_WARPS, c->sm_count * std::max(cl_per_sm, 1));
+                    const int par = (int)(chunks.size() & 1);
+                    need_cell[par] = std::max(need_cell[par], ch.rows * row_bytes);
+                    need_trace[par] = std::max(need_trace[par], (size_t)(r1 - r0) * reg_bytes);
+                    need_scr[par] = std::max(need_scr[par], md_clust_bytes(ch.maxrows) * (size_t)ch.ctas * MDC_WARPS);
+                    chunks.push_back(ch);
                     r0 = r1;
+                }
+                for (int par = 0; par < 2; par++) {
+                    CUDA_TRY(c, c->d_mdcell[par].ensure(need_cell[par]));
+                    CUDA_TRY(c, c->d_mdtrace[par].ensure(need_trace[par]));
+                    CUDA_TRY(c, c->d_mdscratch[par].ensure(need_scr[par]));
+                }
+                CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
+                for (int par = 0; par < 2; par++) CUDA_TRY(c, cudaStreamWaitEvent(c->lanes[par], c->ev_a, 0));
+                for (size_t ci = 0; ci < chunks.size(); ci++) {
+                    const MdChunk &ch = chunks[ci];
+                    const int par = (int)(ci & 1);
+                    cudaStream_t ms = c->lanes[par];
+                    ma.r0 = ch.r0; ma.r1 = ch.r1; ma.row0 = h_row[ch.r0];
+                    ma.cell = c->d_mdcell[par].as<float4>();
+                    ma.rowrec = (MdRow *)(c->d_mdcell[par].as<char>() + ch.rows * MD_W * 16);
+                    ma.trace = c->d_mdtrace[par].as<char>();
+                    ma.maxrows = ch.maxrows;
+                    ma.per_thread = md_clust_bytes(ch.maxrows);
+                    ma.scratch = c->d_mdscratch[par].as<char>();
+                    mdfwd_kernel<<<nblk(ch.r1 - ch.r0, 64), 64, 0, ms>>>(ma);
+                    mdtrace_kernel<<<nblk((int64_t)(ch.r1 - ch.r0) * MD_NSAMPLES, 128), 128, 0, ms>>>(ma, streams);
+                    mdclust_kernel<<<ch.ctas, MDC_WARPS * 32, cl_smem, ms>>>(ma);
+                    c->launches += 3;
+                }
+                for (int par = 0; par < 2; par++) {
+                    CUDA_TRY(c, cudaEventRecord(c->lane_ev[par], c->lanes[par]));
+                    CUDA_TRY(c, cudaStreamWaitEvent(st, c->lane_ev[par], 0));
                 }
                 mdapply_kernel<<<nblk(n2, 256), 256, 0, st>>>(c->d_ndom.as<uint8_t>(), c->d_env.as<int32_t>(), n2, d_base,
                                                              c->d_mdres.as<MdRes>(), c->d_envdc.as<float>(),
@@ -2937,7 +2872,7 @@ int search_stage1(itsx_ctx *c)
             // envelopes are at most Lmax long; scratch per resident warp
             const int Ldmax = Lmax;
             const size_t eslab = (size_t)(Ldmax + 1) * ENV_ROWF * 32 * 4;
-            const size_t env_smem = (size_t)(ENV_THREADS / 32) * (2 * ENV_ROWBYTES + 16);
+            const size_t env_smem = (size_t)(ENV_THREADS / 32) * ENV_RING * (ENV_ROWBYTES + 8);
             CUDA_TRY(c, cudaFuncSetAttribute(env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env_smem));
             CUDA_TRY(c, c->d_envscratch.ensure(eslab * env_warps_per_lane * NLANE));
             CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
