@@ -17,6 +17,7 @@
  *                        Dedup._get_paired_seq_generator            SeqSample.py:564-711
  *   itsx_merge_*         `vsearch --fastq_mergepairs` (paired input, the step in front of derep)
  *                                                                  SeqSample.py:266-365 (argv :314-349)
+ *   itsx_gzip_*          gzip.open(..., "wt") of the output writers    SeqSample.py:767-788, 926-949
  *
  * Conventions: plain C, no callbacks, no exceptions across the boundary.  Functions return
  * 0 on success and a negative ITSX_E* code on failure; itsx_last_error() gives the text.
@@ -248,6 +249,15 @@ int  itsx_merge_pairs(itsx_ctx *ctx, const uint8_t *fseq, const uint8_t *fqual, 
  * index (the title vsearch writes is R1's), out_off[n_merged+1], out_seq / out_qual [total].  Any may be NULL. */
 int  itsx_merge_fetch(itsx_ctx *ctx, int32_t *merged_index, int64_t *out_off, uint8_t *out_seq, uint8_t *out_qual);
 int  itsx_merge_get_stats(const itsx_ctx *ctx, itsx_merge_stats *st);
+
+/* ---- gzip writer (deflate.cu) ------------------------------------------------------------------------------------
+ * Replaces the compression inside the reference's output writers: gzip.open(outfile, "wt") around SeqIO.write in
+ * Dedup.create_trimmed_seqs / create_paired_trimmed_seqs (SeqSample.py:767-788, 926-949) and the .fastq.gz files of the
+ * QIIME 2 actions (q2_itsxpress.py:311-333).  src[n] (host or device) becomes a multi-member gzip stream in dst (every
+ * 32 768 input bytes one member with its own dynamic-Huffman deflate block, CRC-32 and ISIZE; a valid gzip file that any
+ * reader inflates to src).  cap must be at least itsx_gzip_bound(n); *dst_n receives the stream's length. */
+int64_t itsx_gzip_bound(int64_t n);
+int  itsx_gzip_compress(itsx_ctx *ctx, const uint8_t *src, int64_t n, uint8_t *dst, int64_t cap, int64_t *dst_n);
 
 /* ---- whole path, host buffers in / host buffers out (the calls bench.py's e2e leg times) --
  * Together they replace main.py:534-624 for one sample: deduplicate -> _search -> ItsPosition -> Dedup ->

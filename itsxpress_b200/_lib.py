@@ -95,6 +95,7 @@ SYMBOLS = [
     "itsx_derep_map", "itsx_reads_set_samples", "itsx_trim_gather_resident", "itsx_run_trim", "itsx_quals_upload", "itsx_derep_resident", "itsx_run_fetch",
     "itsx_shard_plan", "itsx_shard_pack", "itsx_shard_owner_derep", "itsx_shard_answers", "itsx_shard_apply",
     "itsx_merge_default_params", "itsx_merge_pairs", "itsx_merge_fetch", "itsx_merge_get_stats",
+    "itsx_gzip_bound", "itsx_gzip_compress",
     "itsx_host_last_error", "itsx_fastq_index", "itsx_bytes_gather", "itsx_fastq_format",
 ]
 
@@ -178,6 +179,9 @@ def lib():
     L.itsx_merge_pairs.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(MergeParams), vp, vp, vp, vp]
     L.itsx_merge_fetch.argtypes = [vp, vp, vp, vp, vp]
     L.itsx_merge_get_stats.argtypes = [vp, C.POINTER(MergeStats)]
+    L.itsx_gzip_bound.argtypes = [i64]
+    L.itsx_gzip_bound.restype = i64
+    L.itsx_gzip_compress.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
     L.itsx_host_last_error.restype = C.c_char_p
     L.itsx_fastq_index.restype = i64
     L.itsx_fastq_index.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp]
@@ -456,6 +460,18 @@ class Context:
         self._chk(L.itsx_trim_gather(self._h, mode, _p(seq), _p(qual), _p(off), nreads, C.byref(nk), C.byref(tot),
                                      _p(ki), _p(oo), _p(os_), _p(oq)))
         return ki, oo, os_, oq
+
+    # ---- gzip writer ----------------------------------------------------------------------------
+    def gzip_compress(self, data):
+        """``data`` (bytes-like or uint8 array) as a multi-member gzip stream compressed on the GPU; returns a uint8
+        array (a view of the exact length) that file.write() takes as it is."""
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+        L = lib()
+        cap = int(L.itsx_gzip_bound(a.size))
+        out = np.empty(cap, np.uint8)
+        n = C.c_int64()
+        self._chk(L.itsx_gzip_compress(self._h, _p(a) if a.size else None, a.size, _p(out), cap, C.byref(n)))
+        return out[:n.value]
 
     # ---- paired-end merge -----------------------------------------------------------------------
     def merge_pairs(self, fseq, fqual, foff, rseq, rqual, roff, params=None, fetch=True):

@@ -1,0 +1,215 @@
+// deflate.cu -- gzip writer on the GPU: the trimmed FASTQ text leaves the box as a multi-member gzip stream.
+//
+// Replaces the compression inside the reference's writers (gzip.open(..., "wt") around SeqIO.write,
+// SeqSample.py:767-788, 926-949; level 9 on one core) and the repo's own host writer (zlib level 6 on every core, which
+// bounded every .gz output: 9-12 MB/s per core, profiles/r1n_*, r2j_c5_artifact_n8.json).  The stream is a sequence of
+// independent gzip members of DFL_CHUNK input bytes, like BGZF / pigz -i: any gzip reader inflates it to the same bytes
+// (what parity is judged on; compressed bytes are not comparable even reference-vs-reference: headers carry mtime).
+//
+//   deflate_kernel   one CTA per member: LZ77 candidates from a shared-memory hash table filled in time slices, greedy
+//                    parse per thread, dynamic Huffman codes built by one thread, bit-parallel emission, CRC-32 by
+//                    register advance (deflate_core.h has the per-thread bodies; tools/deflate_emul.cpp runs the same
+//                    code on the CPU against zlib's inflate)
+//   gz_frame_kernel  members framed (header, block, CRC-32, ISIZE) back to back at their final offsets
+#include <algorithm>
+#include <vector>
+#include "deflate_core.h"
+#include "itsx_internal.h"
+
+namespace {
+
+constexpr int GZ_HEADER = 10, GZ_TRAILER = 8;
+constexpr int GZ_BATCH = 2048;                 // members per launch: 64 MB of text, 256 MB of tokens
+
+struct DflSmem {
+    uint8_t  buf[DFL_CHUNK + 16];
+    uint16_t cand[DFL_CHUNK];
+    uint32_t table[DFL_HASH_SIZE];
+    uint32_t freq_ll[288], freq_d[32];
+    uint8_t  len_ll[288], len_d[32];
+    uint16_t code_ll[288], code_d[32];
+    uint32_t ntok[DFL_THREADS];
+    uint32_t bits[DFL_THREADS + 1];
+    uint32_t hdr[DFL_HDR_WORDS];
+    uint32_t hdr_bits;
+    uint32_t crc_table[256];
+    uint32_t crc_part[DFL_THREADS / 32];
+    DflHuffScratch hs;
+};
+
+__global__ void __launch_bounds__(DFL_THREADS)
+deflate_kernel(const uint8_t *__restrict__ text, int64_t n, uint32_t *__restrict__ tokens, uint32_t *__restrict__ out,
+               uint32_t *__restrict__ out_bytes, uint32_t *__restrict__ crc_out)
+{
+    extern __shared__ __align__(16) unsigned char dfl_raw[];
+    DflSmem &sm = *(DflSmem *)dfl_raw;
+    const int t = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * DFL_CHUNK;
+    const int len = (int)min((int64_t)DFL_CHUNK, n - base);
+    DflShared S;
+    S.buf = sm.buf; S.len = len; S.cand = sm.cand; S.table = sm.table;
+    S.freq_ll = sm.freq_ll; S.freq_d = sm.freq_d; S.len_ll = sm.len_ll; S.len_d = sm.len_d;
+    S.code_ll = sm.code_ll; S.code_d = sm.code_d; S.ntok = sm.ntok; S.bits = sm.bits;
+    S.hdr = sm.hdr; S.hdr_bits = &sm.hdr_bits;
+    S.tokens = tokens + (size_t)blockIdx.x * DFL_CHUNK;
+    S.out = out + (size_t)blockIdx.x * DFL_OUT_WORDS;
+
+    // ---- 0. the chunk into shared memory (16-byte loads: text is the library's own allocation), tables cleared ----
+    {
+        const uint4 *src = (const uint4 *)(text + base);
+        uint4 *dst = (uint4 *)sm.buf;
+        const int nvec = len >> 4;
+        for (int v = t; v < nvec; v += DFL_THREADS) dst[v] = src[v];
+        for (int b = (nvec << 4) + t; b < len; b += DFL_THREADS) sm.buf[b] = text[base + b];
+        for (int b = len + t; b < len + 16 && b < DFL_CHUNK + 16; b += DFL_THREADS) sm.buf[b] = 0;
+    }
+    for (int h = t; h < DFL_HASH_SIZE; h += DFL_THREADS) sm.table[h] = 0u;
+    for (int i = t; i < 288; i += DFL_THREADS) sm.freq_ll[i] = 0u;
+    if (t < 32) sm.freq_d[t] = 0u;
+    sm.crc_table[t] = dfl_crc_table_entry((uint32_t)t);
+    for (int w = t; w < DFL_OUT_WORDS; w += DFL_THREADS) S.out[w] = 0u;
+    __syncthreads();
+
+    // ---- 1. match candidates, one time slice of DFL_THREADS positions after the other ----
+    for (int p0 = 0; p0 < len; p0 += DFL_THREADS) {
+        dfl_cand_lookup(S, p0 + t);
+        __syncthreads();
+        dfl_cand_enter(S, p0 + t);
+        __syncthreads();
+    }
+    // ---- 2. parse ----
+    dfl_parse(S, t);
+    __syncthreads();
+    // ---- 3. codes and header ----
+    if (t == 0) dfl_build_codes(S, sm.hs);
+    __syncthreads();
+    // ---- 4. sizes ----
+    dfl_count_bits(S, t);
+    __syncthreads();
+    if (t < 32) {
+        uint32_t mine[DFL_THREADS / 32], sum = 0;
+#pragma unroll
+        for (int k = 0; k < DFL_THREADS / 32; k++) { mine[k] = sm.bits[t * (DFL_THREADS / 32) + k]; sum += mine[k]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (t >= o) inc += v;
+        }
+        uint32_t run = inc - sum;
+#pragma unroll
+        for (int k = 0; k < DFL_THREADS / 32; k++) { sm.bits[t * (DFL_THREADS / 32) + k] = run; run += mine[k]; }
+        if (t == 31) sm.bits[DFL_THREADS] = inc;
+    }
+    __syncthreads();
+    const uint32_t body_bits = sm.bits[DFL_THREADS];
+    const uint32_t total_bits = sm.hdr_bits + body_bits + sm.len_ll[256];
+    const uint32_t dyn_bytes = (total_bits + 7u) >> 3;
+    const bool stored = dyn_bytes >= (uint32_t)len + 5u;
+    // ---- 5. emission ----
+    if (!stored) {
+        for (int w = t; w < (int)((sm.hdr_bits + 31u) >> 5); w += DFL_THREADS) atomicOr(&S.out[w], sm.hdr[w]);
+        dfl_emit(S, t, sm.hdr_bits + sm.bits[t]);
+        if (t == 0) {
+            DflBits b;
+            dfl_bits_start(b, S.out, sm.hdr_bits + body_bits);
+            dfl_bits_put(b, sm.code_ll[256], sm.len_ll[256]);
+            dfl_bits_finish(b);
+            out_bytes[blockIdx.x] = dyn_bytes;
+        }
+    } else {
+        uint8_t *o = (uint8_t *)S.out;
+        if (t == 0) {
+            o[0] = 1;                                      // BFINAL = 1, BTYPE = 00, padding to the byte
+            o[1] = (uint8_t)(len & 0xff); o[2] = (uint8_t)(len >> 8);
+            o[3] = (uint8_t)(~len & 0xff); o[4] = (uint8_t)((~len >> 8) & 0xff);
+            out_bytes[blockIdx.x] = (uint32_t)len + 5u;
+        }
+        for (int b = t; b < len; b += DFL_THREADS) o[5 + b] = sm.buf[b];
+    }
+    // ---- CRC-32 of the chunk ----
+    uint32_t c = dfl_crc_part(sm.buf, len, t, sm.crc_table);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
+    if ((t & 31) == 0) sm.crc_part[t >> 5] = c;
+    __syncthreads();
+    if (t == 0) {
+        uint32_t r = 0;
+#pragma unroll
+        for (int k = 0; k < DFL_THREADS / 32; k++) r ^= sm.crc_part[k];
+        crc_out[blockIdx.x] = r ^ 0xffffffffu;
+    }
+}
+
+// member m -> dst[off[m] ..): 10-byte header, deflate block, CRC-32, ISIZE
+__global__ void __launch_bounds__(128)
+gz_frame_kernel(const uint32_t *__restrict__ out, const uint32_t *__restrict__ out_bytes, const uint32_t *__restrict__ crc,
+                const int64_t *__restrict__ off, int64_t n, uint8_t *__restrict__ dst)
+{
+    const int m = blockIdx.x, t = threadIdx.x;
+    const uint32_t nb = out_bytes[m];
+    uint8_t *d = dst + off[m];
+    const uint8_t *src = (const uint8_t *)(out + (size_t)m * DFL_OUT_WORDS);
+    if (t < GZ_HEADER) {
+        // ID1 ID2 CM=8 FLG=0 MTIME=0 XFL=0 OS=255 (unknown)
+        const uint8_t hdr[GZ_HEADER] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff};
+        d[t] = hdr[t];
+    }
+    for (uint32_t b = t; b < nb; b += 128) d[GZ_HEADER + b] = src[b];
+    if (t < GZ_TRAILER) {
+        const int64_t base = (int64_t)m * DFL_CHUNK;
+        const uint32_t isize = (uint32_t)min((int64_t)DFL_CHUNK, n - base);
+        const uint32_t v = t < 4 ? crc[m] : isize;
+        d[GZ_HEADER + nb + t] = (uint8_t)(v >> (8 * (t & 3)));
+    }
+}
+
+}   // namespace
+
+extern "C" int64_t itsx_gzip_bound(int64_t n)
+{
+    const int64_t members = std::max<int64_t>(1, (n + DFL_CHUNK - 1) / DFL_CHUNK);
+    return n + members * (GZ_HEADER + GZ_TRAILER + 5);
+}
+
+extern "C" int itsx_gzip_compress(itsx_ctx *c, const uint8_t *src, int64_t n, uint8_t *dst, int64_t cap, int64_t *dst_n)
+{
+    if (!c || n < 0 || (n > 0 && !src) || !dst || !dst_n) return ITSX_EINVAL;
+    if (cap < itsx_gzip_bound(n)) { c->err = "itsx_gzip_compress: output buffer smaller than itsx_gzip_bound(n)"; return ITSX_ELIMIT; }
+    cudaStream_t st = c->stream;
+    CUDA_TRY(c, cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DflSmem)));
+    const int64_t members = std::max<int64_t>(1, (n + DFL_CHUNK - 1) / DFL_CHUNK);
+    int64_t written = 0;
+    std::vector<uint32_t> h_bytes;
+    std::vector<int64_t> h_off;
+    for (int64_t m0 = 0; m0 < members; m0 += GZ_BATCH) {
+        const int nm = (int)std::min<int64_t>(GZ_BATCH, members - m0);
+        const int64_t b0 = m0 * DFL_CHUNK, nb = std::min<int64_t>(n - b0, (int64_t)nm * DFL_CHUNK);
+        CUDA_TRY(c, c->d_gz_in.ensure((size_t)std::max<int64_t>(nb, 16) + 16));
+        CUDA_TRY(c, c->d_gz_tok.ensure((size_t)nm * DFL_CHUNK * 4));
+        CUDA_TRY(c, c->d_gz_out.ensure((size_t)nm * DFL_OUT_WORDS * 4));
+        CUDA_TRY(c, c->d_gz_meta.ensure((size_t)nm * 16 + 16));
+        uint32_t *d_bytes = c->d_gz_meta.as<uint32_t>(), *d_crc = d_bytes + nm;
+        int64_t *d_off = (int64_t *)(d_crc + nm);          // word offset 2 nm: 8-byte aligned
+        if (nb > 0) CUDA_TRY(c, cudaMemcpyAsync(c->d_gz_in.p, src + b0, (size_t)nb, cudaMemcpyDefault, st));
+        deflate_kernel<<<nm, DFL_THREADS, sizeof(DflSmem), st>>>(c->d_gz_in.as<uint8_t>(), nb, c->d_gz_tok.as<uint32_t>(),
+                                                                c->d_gz_out.as<uint32_t>(), d_bytes, d_crc);
+        c->launches++;
+        h_bytes.resize(nm);
+        h_off.resize(nm + 1);
+        CUDA_TRY(c, cudaMemcpyAsync(h_bytes.data(), d_bytes, (size_t)nm * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        h_off[0] = 0;
+        for (int m = 0; m < nm; m++) h_off[m + 1] = h_off[m] + GZ_HEADER + (int64_t)h_bytes[m] + GZ_TRAILER;
+        CUDA_TRY(c, c->d_gz_pack.ensure((size_t)h_off[nm]));
+        CUDA_TRY(c, cudaMemcpyAsync(d_off, h_off.data(), (size_t)nm * 8, cudaMemcpyHostToDevice, st));
+        gz_frame_kernel<<<nm, 128, 0, st>>>(c->d_gz_out.as<uint32_t>(), d_bytes, d_crc, d_off, nb, c->d_gz_pack.as<uint8_t>());
+        c->launches++;
+        CUDA_TRY(c, cudaMemcpyAsync(dst + written, c->d_gz_pack.p, (size_t)h_off[nm], cudaMemcpyDefault, st));
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        written += h_off[nm];
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    *dst_n = written;
+    return ITSX_OK;
+}

@@ -125,6 +125,7 @@ struct itsx_ctx {
     DevBuf d_collide;                 // collided read list
     DevBuf d_uid, d_first;            // int32 unique id per read; int32 first_read per unique
     DevBuf d_tmp;                     // cub temp storage
+    DevBuf d_gz_in, d_gz_tok, d_gz_out, d_gz_meta, d_gz_pack;   // gzip writer (deflate.cu): text, tokens, blocks, sizes / CRCs / offsets, framed members
     DevBuf d_counters;                // uint64 [32] device counters (see CNT_* below)
     DevBuf d_lut;                     // uint8 [256] ASCII -> residue code
     int64_t n_unique = 0;

@@ -10,6 +10,7 @@ characters in ASCII 33..126, otherwise ``ValueError``; output is ``@title\\nseq\
 import gzip
 import io
 import os
+import threading
 
 import numpy as np
 
@@ -469,28 +470,42 @@ def iter_records(source):
 
 
 GZIP_LEVEL = int(os.environ.get("ITSX_GZIP_LEVEL", "6"))     # upstream writes level 9 on one core (gzip.open default)
+# who compresses .gz output: "gpu" = itsx_gzip_compress (deflate.cu; a context of its own, so that a writer thread
+# never shares a stream with the search), "host" = zlib members on every host core.  The inflated bytes are the same.
+GZIP_BACKEND = os.environ.get("ITSX_GZIP", "gpu")
+_GZ_CTX = None
+_GZ_LOCK = threading.Lock()
+
+
+def gzip_members(data):
+    """``data`` as a valid multi-member gzip stream (a buffer file.write() accepts)."""
+    global _GZ_CTX
+    if GZIP_BACKEND == "gpu":
+        from . import _lib
+        with _GZ_LOCK:
+            if _GZ_CTX is None:
+                _GZ_CTX = _lib.Context(int(os.environ.get("ITSX_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+            return _GZ_CTX.gzip_compress(data)
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    def member(chunk):
+        co = zlib.compressobj(GZIP_LEVEL, zlib.DEFLATED, 31)
+        return co.compress(chunk) + co.flush()
+    step = 4 << 20
+    chunks = [data[i:i + step] for i in range(0, len(data), step)] or [b""]
+    with ThreadPoolExecutor(max(1, os.cpu_count() or 1)) as ex:
+        return b"".join(ex.map(member, chunks))
 
 
 def write_compressed(path, data, gzipped=False, zstd_file=False, threads=None, n_records=None):
-    """Write FASTQ bytes plain, as gzip (independent members compressed in parallel on every host core -- a valid
-    gzip stream whose DECOMPRESSED bytes are what parity is judged on; gzip headers carry mtime, so compressed bytes
-    are not reproducible even reference-vs-reference) or as one zstd frame.  On amplicon FASTQ zlib level 6 runs at
-    ~9 MB/s per core (level 9: ~4 MB/s, 1.5 % smaller), so the gzip writer is what bounds .gz output."""
+    """Write FASTQ bytes plain, as gzip (independent members -- a valid gzip stream whose DECOMPRESSED bytes are what
+    parity is judged on; gzip headers carry mtime, so compressed bytes are not reproducible even reference-vs-reference)
+    or as one zstd frame.  The members come from the GPU (gzip_members); on the host zlib level 6 runs at ~9 MB/s per
+    core on amplicon FASTQ (level 9: ~4 MB/s, 1.5 % smaller), which is what used to bound every .gz output."""
     if gzipped:
-        import zlib
-        from concurrent.futures import ThreadPoolExecutor
-        threads = threads or os.cpu_count() or 1
-
-        def member(chunk):
-            co = zlib.compressobj(GZIP_LEVEL, zlib.DEFLATED, 31)
-            return co.compress(chunk) + co.flush()
-        step = 4 << 20
-        chunks = [data[i:i + step] for i in range(0, len(data), step)] or [b""]
-        with ThreadPoolExecutor(max(1, threads)) as ex:
-            parts = list(ex.map(member, chunks))
         with open(path, "wb") as f:
-            for p in parts:
-                f.write(p)
+            f.write(gzip_members(data))
     elif zstd_file:
         from . import _zstd
         with open(path, "wb") as f:
@@ -593,17 +608,7 @@ class ChunkWriter:
         if not data:
             return
         if self.gz:
-            import zlib
-            from concurrent.futures import ThreadPoolExecutor
-
-            def member(chunk):
-                co = zlib.compressobj(GZIP_LEVEL, zlib.DEFLATED, 31)
-                return co.compress(chunk) + co.flush()
-            step = 4 << 20
-            chunks = [data[i:i + step] for i in range(0, len(data), step)]
-            with ThreadPoolExecutor(max(1, os.cpu_count() or 1)) as ex:
-                for p in ex.map(member, chunks):
-                    self.f.write(p)
+            self.f.write(gzip_members(data))
         elif self.zst:
             from . import _zstd
             self.f.write(_zstd.compress(data))
@@ -612,8 +617,6 @@ class ChunkWriter:
 
     def close(self):
         if self.gz and self.f.tell() == 0:
-            import zlib
-            co = zlib.compressobj(GZIP_LEVEL, zlib.DEFLATED, 31)
-            self.f.write(co.compress(b"") + co.flush())          # an empty but valid gzip file
+            self.f.write(gzip_members(b""))          # an empty but valid gzip file
         self.f.close()
         note_count(self.path, self.n)

@@ -13,6 +13,11 @@ HMM_DIR = os.path.join(ROOT, "itsxpress_b200", "ITSx_db", "HMMs")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run on the GPU box with -m gpu)")
+    # the CPU suite (-m "not gpu", or a box without a device) exercises the host side of the writers with zlib members;
+    # the GPU suite leaves the default: .gz output is compressed by itsx_gzip_compress (tests/test_gpu_gzip.py)
+    m = config.getoption("-m") or ""
+    if "not gpu" in m or (m.strip() != "gpu" and not _have_gpu()):
+        os.environ["ITSX_GZIP"] = "host"
 
 
 _HAVE_GPU = None

@@ -184,6 +184,39 @@ def test_search_multidomain_regions(gpu_ctx, oracle, resolve):
     assert np.max(np.abs(rows["domcorrection"][md] - orows["domcorrection"][md])) <= 2e-3
 
 
+def test_search_multidomain_long_regions_and_iupac(gpu_ctx, oracle):
+    """The resolver's less common paths: amplicons glued two and three times over (repeated boundary motifs => long
+    flagged regions that need several position blocks / passes and hold several clusters), with IUPAC codes and N
+    sprinkled into them (null2 odds averaged over the code's bases)."""
+    import synth
+    seq, off, which, cfg = synth.make_config("c2_small", scale=0.05)
+    rep, _, _ = oracle.derep(seq, off)
+    useq, uoff, _ = _uniques(seq, off, rep)
+    rng = np.random.default_rng(7)
+    n = len(uoff) - 1
+    parts = []
+    for i in range(0, min(n, 240), 2):
+        a, b = useq[uoff[i]:uoff[i + 1]], useq[uoff[i + 1]:uoff[i + 2]]
+        glued = [a, b] if i % 3 else [a, b, a]
+        v = np.concatenate(glued).copy()
+        if i % 4 == 0:
+            at = rng.choice(len(v), size=6, replace=False)
+            v[at] = np.frombuffer(b"NRYKMS", np.uint8)
+        parts.append(v)
+    s2 = np.concatenate(parts)
+    o2 = np.zeros(len(parts) + 1, np.int64)
+    o2[1:] = np.cumsum([len(p) for p in parts])
+    rows, st, orows, onrep, ost, side, db = _search_both(gpu_ctx, oracle, [cfg["hmm_file"]],
+                                                        [cfg["left_prefix"], cfg["right_prefix"]], s2, o2,
+                                                        cfg["left_prefix"], cfg["right_prefix"], 1)
+    assert ost.n_multidomain_regions > 100 and st.n_multidomain_regions == ost.n_multidomain_regions
+    md = orows["is_multidomain"] != 0
+    assert md.sum() > 100
+    _compare_search(gpu_ctx, oracle, rows, st, orows, onrep, ost, side, np.diff(o2).astype(np.int32))
+    assert np.array_equal(rows["ienv"][md], orows["ienv"][md]) and np.array_equal(rows["jenv"][md], orows["jenv"][md])
+    assert np.max(np.abs(rows["domcorrection"][md] - orows["domcorrection"][md])) <= 2e-3
+
+
 @pytest.mark.parametrize("thr", [(0.02, 1e-3, 1e-5), (0.3, 1e-4, 1e-5)])
 def test_viterbi_filter_stage(gpu_ctx, oracle, thr):
     """K6, the 16-bit Viterbi filter.  Under the reference's --F1 1e-6 --F2 1e-6 it never runs (p7_Pipeline: only for
