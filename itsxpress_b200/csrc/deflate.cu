@@ -6,9 +6,9 @@
 // independent gzip members of DFL_CHUNK input bytes, like BGZF / pigz -i: any gzip reader inflates it to the same bytes
 // (what parity is judged on; compressed bytes are not comparable even reference-vs-reference: headers carry mtime).
 //
-//   deflate_kernel   one CTA per member: LZ77 candidates from a shared-memory hash table filled in time slices, greedy
-//                    parse per thread, dynamic Huffman codes built by one thread, bit-parallel emission, CRC-32 by
-//                    register advance (deflate_core.h has the per-thread bodies; tools/deflate_emul.cpp runs the same
+//   deflate_kernel   one CTA per member: LZ77 hash chains from a shared-memory table filled in time slices, lazy parse
+//                    per thread with matches stitched across the threads' bytes, dynamic Huffman codes built by one
+//                    thread, bit-parallel emission, CRC-32 by register advance (deflate_core.h has the per-thread bodies; tools/deflate_emul.cpp runs the same
 //                    code on the CPU against zlib's inflate)
 //   gz_frame_kernel  members framed (header, block, CRC-32, ISIZE) back to back at their final offsets
 #include <algorithm>
@@ -28,7 +28,7 @@ struct DflSmem {
     uint32_t freq_ll[288], freq_d[32];
     uint8_t  len_ll[288], len_d[32];
     uint16_t code_ll[288], code_d[32];
-    uint32_t ntok[DFL_THREADS];
+    uint32_t ntok[DFL_THREADS], tbeg[DFL_THREADS], tend[DFL_THREADS], covered[DFL_THREADS];
     uint32_t bits[DFL_THREADS + 1];
     uint32_t hdr[DFL_HDR_WORDS];
     uint32_t hdr_bits;
@@ -49,9 +49,9 @@ deflate_kernel(const uint8_t *__restrict__ text, int64_t n, uint32_t *__restrict
     DflShared S;
     S.buf = sm.buf; S.len = len; S.cand = sm.cand; S.table = sm.table;
     S.freq_ll = sm.freq_ll; S.freq_d = sm.freq_d; S.len_ll = sm.len_ll; S.len_d = sm.len_d;
-    S.code_ll = sm.code_ll; S.code_d = sm.code_d; S.ntok = sm.ntok; S.bits = sm.bits;
+    S.code_ll = sm.code_ll; S.code_d = sm.code_d; S.ntok = sm.ntok; S.tbeg = sm.tbeg; S.tend = sm.tend; S.bits = sm.bits;
     S.hdr = sm.hdr; S.hdr_bits = &sm.hdr_bits;
-    S.tokens = tokens + (size_t)blockIdx.x * DFL_CHUNK;
+    S.tokens = tokens + (size_t)blockIdx.x * DFL_THREADS * DFL_TOKS;
     S.out = out + (size_t)blockIdx.x * DFL_OUT_WORDS;
 
     // ---- 0. the chunk into shared memory (16-byte loads: text is the library's own allocation), tables cleared ----
@@ -77,8 +77,26 @@ deflate_kernel(const uint8_t *__restrict__ text, int64_t n, uint32_t *__restrict
         dfl_cand_enter(S, p0 + t);
         __syncthreads();
     }
-    // ---- 2. parse ----
+    // ---- 2. parse; then what the threads before already cover (exclusive prefix maximum of the end positions) ----
     dfl_parse(S, t);
+    __syncthreads();
+    if (t < 32) {
+        uint32_t mine[DFL_THREADS / 32], mx = 0;
+#pragma unroll
+        for (int k = 0; k < DFL_THREADS / 32; k++) { mine[k] = sm.tend[t * (DFL_THREADS / 32) + k]; mx = max(mx, mine[k]); }
+        uint32_t inc = mx;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (t >= o) inc = max(inc, v);
+        }
+        uint32_t run = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (t == 0) run = 0;
+#pragma unroll
+        for (int k = 0; k < DFL_THREADS / 32; k++) { sm.covered[t * (DFL_THREADS / 32) + k] = run; run = max(run, mine[k]); }
+    }
+    __syncthreads();
+    dfl_stitch(S, t, sm.covered[t]);
     __syncthreads();
     // ---- 3. codes and header ----
     if (t == 0) dfl_build_codes(S, sm.hs);
@@ -186,7 +204,7 @@ extern "C" int itsx_gzip_compress(itsx_ctx *c, const uint8_t *src, int64_t n, ui
         const int nm = (int)std::min<int64_t>(GZ_BATCH, members - m0);
         const int64_t b0 = m0 * DFL_CHUNK, nb = std::min<int64_t>(n - b0, (int64_t)nm * DFL_CHUNK);
         CUDA_TRY(c, c->d_gz_in.ensure((size_t)std::max<int64_t>(nb, 16) + 16));
-        CUDA_TRY(c, c->d_gz_tok.ensure((size_t)nm * DFL_CHUNK * 4));
+        CUDA_TRY(c, c->d_gz_tok.ensure((size_t)nm * DFL_THREADS * DFL_TOKS * 4));
         CUDA_TRY(c, c->d_gz_out.ensure((size_t)nm * DFL_OUT_WORDS * 4));
         CUDA_TRY(c, c->d_gz_meta.ensure((size_t)nm * 16 + 16));
         uint32_t *d_bytes = c->d_gz_meta.as<uint32_t>(), *d_crc = d_bytes + nm;

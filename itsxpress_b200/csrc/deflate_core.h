@@ -7,8 +7,10 @@
 // separated by CTA barriers:
 //   1. candidates   positions in time slices of DFL_THREADS: look the 4-byte hash up (largest earlier position of the
 //                   slices before), then enter the slice's own positions (atomicMax => deterministic)
-//   2. parse        a thread parses its DFL_SUB bytes greedily (hash candidate vs. distance 1, matches end inside the
-//                   thread's bytes), tokens to HBM, symbol histograms by shared-memory atomics
+//   2. parse        a thread parses its DFL_SUB bytes (hash chain of up to DFL_MAX_CHAIN candidates vs. distance 1, one
+//                   step of lazy evaluation; its last match may run into the next threads' bytes), tokens to HBM;
+//      stitch       prefix maximum of the threads' end positions: a thread drops / cuts the tokens the threads before it
+//                   already cover, then counts its symbols by shared-memory atomics
 //   3. codes        one thread: length-limited Huffman code lengths (two-queue merge, weights halved until the depth
 //                   fits), canonical codes, the block header (code lengths with zero runs as symbols 17 / 18)
 //   4. sizes        bits of every thread's tokens, exclusive scan
@@ -32,6 +34,16 @@ constexpr int DFL_HASH_BITS = 13;
 constexpr int DFL_HASH_SIZE = 1 << DFL_HASH_BITS;
 constexpr int DFL_NLL = 286, DFL_ND = 30, DFL_NCL = 19;
 constexpr int DFL_MIN_HASH_MATCH = 4, DFL_MIN_RUN = 3, DFL_MAX_MATCH = 258;
+#ifndef DFL_MAX_CHAIN
+#define DFL_MAX_CHAIN 16                            // candidates tried per position (zlib level 3: 32, level 1: 4)
+#endif
+#ifndef DFL_NICE_MATCH
+#define DFL_NICE_MATCH 64                           // a match this long ends the search
+#endif
+#ifndef DFL_LAZY_MAX
+#define DFL_LAZY_MAX 32                             // matches shorter than this are compared with the one a byte later
+#endif
+constexpr int DFL_TOKS = DFL_SUB + 2;                // token slots of a thread: two spare ones in front (see dfl_stitch)
 constexpr int DFL_OUT_WORDS = (DFL_CHUNK + 64) / 4; // output words per chunk: a stored block needs CHUNK + 5 bytes
 constexpr int DFL_HDR_WORDS = 96;                   // the dynamic block header is at most ~ 2 600 bits
 constexpr uint32_t DFL_TOK_MATCH = 0x80000000u;     // token: literal byte | MATCH | (len - 3) << 16 | (dist - 1)
@@ -202,11 +214,13 @@ struct DflShared {
     uint32_t      *freq_ll, *freq_d;    // [288], [32]
     uint8_t       *len_ll, *len_d;      // [288], [32]
     uint16_t      *code_ll, *code_d;    // [288], [32]
-    uint32_t      *ntok;                // [DFL_THREADS]
+    uint32_t      *ntok;                // [DFL_THREADS]: tokens the thread emits ...
+    uint32_t      *tbeg;                // [DFL_THREADS]: ... from this slot of its DFL_TOKS
+    uint32_t      *tend;                // [DFL_THREADS]: position behind the thread's last token (>= its own end)
     uint32_t      *bits;                // [DFL_THREADS + 1]: token bits per thread, then their exclusive scan
     uint32_t      *hdr;                 // [DFL_HDR_WORDS]: the block header
     uint32_t      *hdr_bits;            // [1]
-    uint32_t      *tokens;              // HBM: [DFL_CHUNK]
+    uint32_t      *tokens;              // HBM: [DFL_THREADS * DFL_TOKS]
     uint32_t      *out;                 // HBM: [DFL_OUT_WORDS], zero on entry
 };
 
@@ -220,38 +234,100 @@ DFL_HD void dfl_cand_enter(const DflShared &S, int p)
     if (p + DFL_MIN_HASH_MATCH <= S.len) DFL_ATOMIC_MAX(&S.table[dfl_hash4(S.buf + p)], (uint32_t)(p + 1));
 }
 
-// phase 2: greedy parse of thread t's bytes
+// the best match at p (it may run past the thread's own bytes: dfl_stitch trims what follows): longest of the hash chain (at most DFL_MAX_CHAIN candidates, nearest
+// first) and of distance 1 (runs; preferred on ties: the cheapest distance)
+DFL_HD int dfl_find_match(const DflShared &S, int p, int &bdist)
+{
+    const int maxlen = S.len - p < DFL_MAX_MATCH ? S.len - p : DFL_MAX_MATCH;
+    int best = 0;
+    bdist = 0;
+    // cand[] links every position to the head of its hash before its own time slice: a chain of earlier positions
+    // with the same hash, nearest first (deterministic: it does not depend on the order threads ran in)
+    if (maxlen >= DFL_MIN_HASH_MATCH) {
+        int c = S.cand[p];
+        for (int tries = 0; c != 0 && tries < DFL_MAX_CHAIN; tries++) {
+            const uint8_t *q = S.buf + (c - 1);
+            if (q[best] == S.buf[p + best]) {                       // can only win if it matches one byte further
+                const int l = dfl_match_len(q, S.buf + p, maxlen);
+                if (l >= DFL_MIN_HASH_MATCH && l > best) { best = l; bdist = p - (c - 1); }
+                if (best >= DFL_NICE_MATCH || best == maxlen) break;
+            }
+            c = S.cand[c - 1];
+        }
+    }
+    if (p > 0 && maxlen >= DFL_MIN_RUN) {
+        const int l = dfl_match_len(S.buf + p - 1, S.buf + p, maxlen);
+        if (l >= DFL_MIN_RUN && l >= best) { best = l; bdist = 1; }
+    }
+    return best;
+}
+
+// phase 2a: parse of thread t's bytes, greedy with one step of lazy evaluation (a longer match one byte later wins).
+// The last match may run into the following threads' bytes; tend[t] says how far.
 DFL_HD void dfl_parse(const DflShared &S, int t)
 {
     int p = t * DFL_SUB;
     const int end = p + DFL_SUB < S.len ? p + DFL_SUB : S.len;
-    uint32_t *tok = S.tokens + t * DFL_SUB;
+    uint32_t *tok = S.tokens + t * DFL_TOKS + 2;
     uint32_t nt = 0;
+    int bdist = 0, best = p < end ? dfl_find_match(S, p, bdist) : 0;
     while (p < end) {
-        const int maxlen = end - p < DFL_MAX_MATCH ? end - p : DFL_MAX_MATCH;
-        int best = 0, bdist = 0;
-        const int c = S.cand[p];
-        if (c != 0 && maxlen >= DFL_MIN_HASH_MATCH) {
-            const int l = dfl_match_len(S.buf + (c - 1), S.buf + p, maxlen);
-            if (l >= DFL_MIN_HASH_MATCH) { best = l; bdist = p - (c - 1); }
+        bool literal = best == 0;
+        int ndist = 0, nbest = 0;
+        if (!literal && best < DFL_LAZY_MAX && p + 1 < end) {
+            nbest = dfl_find_match(S, p + 1, ndist);
+            if (nbest > best) literal = true;
         }
-        if (p > 0 && maxlen >= DFL_MIN_RUN) {
-            const int l = dfl_match_len(S.buf + p - 1, S.buf + p, maxlen);
-            if (l >= DFL_MIN_RUN && l >= best) { best = l; bdist = 1; }
-        }
-        if (best > 0) {
-            int eb, ev;
+        if (!literal) {
             tok[nt++] = DFL_TOK_MATCH | ((uint32_t)(best - 3) << 16) | (uint32_t)(bdist - 1);
-            DFL_ATOMIC_ADD(&S.freq_ll[dfl_len_sym(best, eb, ev)], 1u);
-            DFL_ATOMIC_ADD(&S.freq_d[dfl_dist_sym(bdist, eb, ev)], 1u);
             p += best;
+            best = p < end ? dfl_find_match(S, p, bdist) : 0;
         } else {
             tok[nt++] = S.buf[p];
-            DFL_ATOMIC_ADD(&S.freq_ll[S.buf[p]], 1u);
             p++;
+            if (nbest > 0) { best = nbest; bdist = ndist; }              // the match found one byte later
+            else best = p < end ? dfl_find_match(S, p, bdist) : 0;
         }
     }
     S.ntok[t] = nt;
+    S.tbeg[t] = 2;
+    S.tend[t] = (uint32_t)p;
+}
+
+// phase 2b: `covered` = how far the threads before t got (maximum of their tend).  Tokens that lie below it are dropped,
+// the one that crosses it is cut at the front (a match keeps its distance; fewer than 3 bytes left become literals in the
+// two spare slots); then the symbols of what the thread will emit are counted.
+DFL_HD void dfl_stitch(const DflShared &S, int t, uint32_t covered)
+{
+    uint32_t *tok = S.tokens + t * DFL_TOKS;
+    uint32_t beg = 2, nt = S.ntok[t];
+    uint32_t p = (uint32_t)(t * DFL_SUB);
+    while (nt > 0 && p < covered) {
+        const uint32_t k = tok[beg];
+        const uint32_t l = (k & DFL_TOK_MATCH) ? ((k >> 16) & 0xffu) + 3u : 1u;
+        if (p + l <= covered) { p += l; beg++; nt--; continue; }
+        // a match crosses the line: [p, p + l) with p < covered < p + l
+        const uint32_t left = p + l - covered;
+        if (left >= 3u) {
+            tok[beg] = DFL_TOK_MATCH | ((left - 3u) << 16) | (k & 0xffffu);
+        } else {
+            beg++; nt--;
+            for (uint32_t j = left; j > 0; j--) { tok[--beg] = S.buf[covered + j - 1]; nt++; }
+        }
+        break;
+    }
+    S.tbeg[t] = beg;
+    S.ntok[t] = nt;
+    for (uint32_t i = 0; i < nt; i++) {
+        const uint32_t k = tok[beg + i];
+        if (k & DFL_TOK_MATCH) {
+            int eb, ev;
+            DFL_ATOMIC_ADD(&S.freq_ll[dfl_len_sym((int)((k >> 16) & 0xffu) + 3, eb, ev)], 1u);
+            DFL_ATOMIC_ADD(&S.freq_d[dfl_dist_sym((int)(k & 0xffffu) + 1, eb, ev)], 1u);
+        } else {
+            DFL_ATOMIC_ADD(&S.freq_ll[k], 1u);
+        }
+    }
 }
 
 // phase 3 (one thread): code lengths, codes, block header.  BFINAL = 1: one block per gzip member.
@@ -310,7 +386,7 @@ DFL_HD void dfl_build_codes(const DflShared &S, DflHuffScratch &hs)
 // phase 4: bits of thread t's tokens
 DFL_HD void dfl_count_bits(const DflShared &S, int t)
 {
-    const uint32_t *tok = S.tokens + t * DFL_SUB;
+    const uint32_t *tok = S.tokens + t * DFL_TOKS + S.tbeg[t];
     const uint32_t nt = S.ntok[t];
     uint32_t nb = 0;
     for (uint32_t i = 0; i < nt; i++) {
@@ -329,7 +405,7 @@ DFL_HD void dfl_count_bits(const DflShared &S, int t)
 // phase 5: thread t writes its tokens at bit `start` of the output
 DFL_HD void dfl_emit(const DflShared &S, int t, uint32_t start)
 {
-    const uint32_t *tok = S.tokens + t * DFL_SUB;
+    const uint32_t *tok = S.tokens + t * DFL_TOKS + S.tbeg[t];
     const uint32_t nt = S.ntok[t];
     DflBits b;
     dfl_bits_start(b, S.out, start);

@@ -233,6 +233,16 @@ def _read_fastq_now(path):
     return batch
 
 
+# how many samples a multi-sample driver reads ahead (two files each, one thread per file: a single-member .gz inflates on
+# one core at ~200 MB/s, so one sample ahead leaves the other cores idle and the inflate bounds the artifact); the
+# default leaves about half the cores of the process's share to it, ITSX_READ_AHEAD overrides
+def _default_read_ahead():
+    cores = os.cpu_count() or 2
+    share = max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))))
+    return max(1, min(4, share // 4))
+
+
+READ_AHEAD = int(os.environ.get("ITSX_READ_AHEAD", "0")) or _default_read_ahead()
 # files being read ahead on background threads: abspath -> (Future[FastqBatch], size, mtime_ns)
 _PREFETCH = {}
 _PREFETCH_POOL = None
@@ -246,7 +256,7 @@ def prefetch(paths):
     global _PREFETCH_POOL
     from concurrent.futures import ThreadPoolExecutor
     if _PREFETCH_POOL is None:
-        _PREFETCH_POOL = ThreadPoolExecutor(2, thread_name_prefix="itsx-readahead")
+        _PREFETCH_POOL = ThreadPoolExecutor(2 * READ_AHEAD, thread_name_prefix="itsx-readahead")
     for p in paths:
         if not p:
             continue

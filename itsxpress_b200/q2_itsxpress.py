@@ -281,6 +281,9 @@ def _process_batch(rows, results, tempdir, threads, taxa, region, paired_in, pai
                             gzipped=True, zstd_file=False, n_records=outs[1][1])
 
 
+READ_AHEAD_BYTES = int(os.environ.get("ITSX_READ_AHEAD_BYTES", str(2 << 30)))
+
+
 def _can_batch(cluster_id, trim_ccs):
     return BATCH_READS > 0 and math.isclose(cluster_id, 1, rel_tol=1e-05) and not trim_ccs
 
@@ -298,9 +301,17 @@ def _run_rows(rows, results, tempdir, threads, taxa, region, paired_in, paired_o
             _process_batch(group, results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
                            allow_staggered_reads)
         else:
-            if gi + 1 < len(flat) and len(flat[gi + 1]) == 1:       # read the next sample's files while this one is on the GPU
-                nxt = flat[gi + 1][0]
-                fq.prefetch([nxt.forward, nxt.reverse if paired_in else None])
+            # read the next samples' files while this one is on the GPU (fq.READ_AHEAD of them, within ~2 GB of files)
+            ahead_bytes = 0
+            for gj in range(gi + 1, min(gi + 1 + fq.READ_AHEAD, len(flat))):
+                if len(flat[gj]) != 1:
+                    break
+                nxt = flat[gj][0]
+                files = [nxt.forward, nxt.reverse if paired_in else None]
+                ahead_bytes += sum(os.path.getsize(f) for f in files if f and os.path.exists(f))
+                if gj > gi + 1 and ahead_bytes > READ_AHEAD_BYTES:
+                    break
+                fq.prefetch(files)
             process(group[0], results, tempdir, threads, taxa, region, paired_in, paired_out, reversed_primers,
                     allow_staggered_reads, cluster_id, trim_ccs)
         done += [smp.Index for smp in group]

@@ -594,7 +594,17 @@ def test_q2_loop_reads_next_sample_ahead(tmp_path, monkeypatch):
 
     monkeypatch.setattr(q2, "_process_sample", stub)
     monkeypatch.setattr(q2, "BATCH_READS", 0)          # the per-sample loop (small samples would share a device pass)
+    monkeypatch.setattr(fq, "READ_AHEAD", 1)
     q2.main_sharded(q2.PerSampleDir(str(src)), str(tmp_path / "o"), region="ITS2", taxa="M", rank=0, world=1)
     # at the start of a sample its own files (read ahead during the previous one) and the next sample's are pending
     assert [len(p) for p in pending] == [2, 4, 2] and not fq._PREFETCH
     assert pending[0] == ["S1_1_L001_R1_001.fastq.gz", "S1_1_L001_R2_001.fastq.gz"]
+    # two samples ahead: both followers are being read when the first sample starts; a byte budget of zero keeps one
+    del pending[:]
+    monkeypatch.setattr(fq, "READ_AHEAD", 2)
+    q2.main_sharded(q2.PerSampleDir(str(src)), str(tmp_path / "o2"), region="ITS2", taxa="M", rank=0, world=1)
+    assert [len(p) for p in pending] == [4, 4, 2] and not fq._PREFETCH
+    del pending[:]
+    monkeypatch.setattr(q2, "READ_AHEAD_BYTES", 0)
+    q2.main_sharded(q2.PerSampleDir(str(src)), str(tmp_path / "o3"), region="ITS2", taxa="M", rank=0, world=1)
+    assert [len(p) for p in pending] == [2, 4, 2] and not fq._PREFETCH

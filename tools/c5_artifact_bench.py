@@ -48,6 +48,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=781_250)
     ap.add_argument("--distinct-per-rank", type=int, default=1)
     ap.add_argument("--dir", default="/tmp/itsx_c5")
+    ap.add_argument("--gzip", default="gpu", help="who deflates the outputs, timed one after the other on the same inputs: "
+                                                  "'gpu' (itsx_gzip_compress), 'host' (zlib members on the host cores) or 'host,gpu'")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -104,43 +106,49 @@ def main():
     q2.main_sharded(q2.PerSampleDir(warm), os.path.join(warm, "out"), region="ITS2", taxa="M", rank=0, world=1,
                     barrier=lambda: None)
     ctx = SeqSample.get_context()
-    l0 = ctx.launch_count()
-    barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    res, done = q2.main_sharded(q2.PerSampleDir(src), out, region="ITS2", taxa="M", paired_in=True, paired_out=True)
-    torch.cuda.synchronize()
-    barrier()
-    dt = time.perf_counter() - t0
-    launches = ctx.launch_count() - l0
-    t = torch.tensor([dt, float(launches), float(len(done))], dtype=torch.float64, device="cuda")
-    tmax = t.clone()
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    if rank == 0:
-        dt = float(tmax[0].item())
-        outs = [f for f in os.listdir(out) if f.endswith(".fastq.gz")]
-        in_bytes = sum(os.path.getsize(os.path.join(src, f)) for f in os.listdir(src) if f.endswith(".gz"))
-        out_bytes = sum(os.path.getsize(os.path.join(out, f)) for f in outs)
-        n_out = 0
-        with gzip.open(os.path.join(out, sorted(outs)[0]), "rb") as f:
-            for _ in f:
-                n_out += 1
-        print(json.dumps({
-            "metric": "read pairs/s, QIIME 2 trim-pair-output-unmerged, artifact in -> artifact out",
-            "value": a.samples * a.pairs / dt, "unit": "pairs/s", "n_gpus": world, "seconds": dt,
-            "config": {"workload": "BASELINE configs[4]: %d samples x %d read pairs (2 x 250 bp off 330-441 bp ITS2 amplicons, "
-                                   "5 %% unique within a sample), gzipped Casava files in and out, --region ITS2, profiles = "
-                                   "M.hmm 3_/4_ (F.hmm missing from the reference mount)" % (a.samples, a.pairs),
-                       "parallelism": "whole samples dealt to ranks (largest first), no data-path collective; per sample: "
-                                      "inflate -> GPU merge -> GPU derep -> GPU search -> GPU trim -> deflate",
-                       "distinct_samples": a.distinct_per_rank * world},
-            "samples_done": int(t[2].item()), "gpu_launches": int(t[1].item()),
-            "input_gz_bytes": in_bytes, "output_gz_bytes": out_bytes, "output_files": len(outs),
-            "records_in_first_output": n_out // 4, "synthesis_seconds_rank0": t_synth,
-            "bound": "host: gzip inflate of the inputs and deflate of the outputs (device time per sample ~0.1 s)"}))
-    barrier()
+    from itsxpress_b200 import fastq as fqmod
+    for backend in a.gzip.split(","):
+        fqmod.GZIP_BACKEND = backend
+        if rank == 0:
+            shutil.rmtree(out, ignore_errors=True)
+        barrier()
+        l0 = ctx.launch_count()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res, done = q2.main_sharded(q2.PerSampleDir(src), out, region="ITS2", taxa="M", paired_in=True, paired_out=True)
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        launches = ctx.launch_count() - l0
+        t = torch.tensor([dt, float(launches), float(len(done))], dtype=torch.float64, device="cuda")
+        tmax = t.clone()
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            dt = float(tmax[0].item())
+            outs = [f for f in os.listdir(out) if f.endswith(".fastq.gz")]
+            in_bytes = sum(os.path.getsize(os.path.join(src, f)) for f in os.listdir(src) if f.endswith(".gz"))
+            out_bytes = sum(os.path.getsize(os.path.join(out, f)) for f in outs)
+            n_out = 0
+            with gzip.open(os.path.join(out, sorted(outs)[0]), "rb") as f:
+                for _ in f:
+                    n_out += 1
+            print(json.dumps({
+                "metric": "read pairs/s, QIIME 2 trim-pair-output-unmerged, artifact in -> artifact out",
+                "value": a.samples * a.pairs / dt, "unit": "pairs/s", "n_gpus": world, "seconds": dt,
+                "config": {"workload": "BASELINE configs[4]: %d samples x %d read pairs (2 x 250 bp off 330-441 bp ITS2 amplicons, "
+                                       "5 %% unique within a sample), gzipped Casava files in and out, --region ITS2, profiles = "
+                                       "M.hmm 3_/4_ (F.hmm missing from the reference mount)" % (a.samples, a.pairs),
+                           "parallelism": "whole samples dealt to ranks (largest first), no data-path collective; per sample: "
+                                          "inflate -> GPU merge -> GPU derep -> GPU search -> GPU trim -> deflate",
+                           "distinct_samples": a.distinct_per_rank * world},
+                "gzip_backend": backend, "host_cores": os.cpu_count(), "samples_done": int(t[2].item()), "gpu_launches": int(t[1].item()),
+                "input_gz_bytes": in_bytes, "output_gz_bytes": out_bytes, "output_files": len(outs),
+                "records_in_first_output": n_out // 4, "synthesis_seconds_rank0": t_synth,
+                "bound": "host (device time per sample ~0.1 s): gzip inflate of the inputs" + (" and deflate of the outputs" if backend == "host" else ", FASTQ parsing / formatting")}))
+        barrier()
     if world > 1:
         dist.destroy_process_group()
 

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 #include "../itsxpress_b200/csrc/deflate_core.h"
 
@@ -30,7 +31,8 @@ int main(int argc, char **argv)
         if (len > 0) memcpy(buf.data(), in.data() + m * DFL_CHUNK, (size_t)len);
         std::vector<uint16_t> cand(DFL_CHUNK, 0), code_ll(288, 0), code_d(32, 0);
         std::vector<uint32_t> table(DFL_HASH_SIZE, 0), freq_ll(288, 0), freq_d(32, 0), ntok(DFL_THREADS, 0),
-            bits(DFL_THREADS + 1, 0), hdr(DFL_HDR_WORDS, 0), tokens(DFL_CHUNK, 0), out(DFL_OUT_WORDS, 0);
+            bits(DFL_THREADS + 1, 0), hdr(DFL_HDR_WORDS, 0), tokens(DFL_THREADS * DFL_TOKS, 0), out(DFL_OUT_WORDS, 0),
+            tbeg(DFL_THREADS, 0), tend(DFL_THREADS, 0);
         std::vector<uint8_t> len_ll(288, 0), len_d(32, 0);
         uint32_t hdr_bits = 0;
         DflShared S;
@@ -38,11 +40,18 @@ int main(int argc, char **argv)
         S.freq_ll = freq_ll.data(); S.freq_d = freq_d.data(); S.len_ll = len_ll.data(); S.len_d = len_d.data();
         S.code_ll = code_ll.data(); S.code_d = code_d.data(); S.ntok = ntok.data(); S.bits = bits.data();
         S.hdr = hdr.data(); S.hdr_bits = &hdr_bits; S.tokens = tokens.data(); S.out = out.data();
+        S.tbeg = tbeg.data(); S.tend = tend.data();
         for (int p0 = 0; p0 < len; p0 += DFL_THREADS) {
             for (int t = 0; t < DFL_THREADS; t++) dfl_cand_lookup(S, p0 + t);
             for (int t = 0; t < DFL_THREADS; t++) dfl_cand_enter(S, p0 + t);
         }
         for (int t = 0; t < DFL_THREADS; t++) dfl_parse(S, t);
+        {
+            std::vector<uint32_t> covered(DFL_THREADS, 0);          // exclusive prefix maximum of tend[]
+            uint32_t mx = 0;
+            for (int t = 0; t < DFL_THREADS; t++) { covered[t] = mx; mx = std::max(mx, tend[t]); }
+            for (int t = 0; t < DFL_THREADS; t++) dfl_stitch(S, t, covered[t]);
+        }
         static DflHuffScratch hs;
         dfl_build_codes(S, hs);
         for (int t = 0; t < DFL_THREADS; t++) dfl_count_bits(S, t);
