@@ -328,7 +328,8 @@ def cli_file_to_file(seq, qual, off, cfg):
                 dt = time.perf_counter() - t0
             out[tag] = {"reads_per_s": n / dt, "seconds": dt, "input_bytes": os.path.getsize(fq_in),
                         "output_bytes": os.path.getsize(os.path.join(tmp, name))}
-        out["note"] = "wall clock of itsxpress_b200.main.main(); bound by FASTQ parsing / formatting and gzip on the host"
+        out["note"] = ("wall clock of itsxpress_b200.main.main(); bound by FASTQ parsing / formatting on the host; .gz output is "
+                       "compressed on the GPU (itsx_gzip_compress)")
     except BaseException as e:          # the CLI ends in SystemExit on failure; the bench line must still come out
         out["error"] = "%s: %s" % (type(e).__name__, e)
     finally:
