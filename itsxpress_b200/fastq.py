@@ -496,6 +496,8 @@ def gzip_members(data):
             if _GZ_CTX is None:
                 _GZ_CTX = _lib.Context(int(os.environ.get("ITSX_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
             return _GZ_CTX.gzip_compress(data)
+    if GZIP_BACKEND != "host":
+        raise ValueError("ITSX_GZIP must be 'gpu' or 'host', not %r" % (GZIP_BACKEND,))
     import zlib
     from concurrent.futures import ThreadPoolExecutor
 
