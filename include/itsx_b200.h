@@ -254,8 +254,8 @@ int  itsx_merge_get_stats(const itsx_ctx *ctx, itsx_merge_stats *st);
  * Replaces the compression inside the reference's output writers: gzip.open(outfile, "wt") around SeqIO.write in
  * Dedup.create_trimmed_seqs / create_paired_trimmed_seqs (SeqSample.py:767-788, 926-949) and the .fastq.gz files of the
  * QIIME 2 actions (q2_itsxpress.py:311-333).  src[n] (host or device) becomes a multi-member gzip stream in dst (every
- * 32 768 input bytes one member with its own dynamic-Huffman deflate block, CRC-32 and ISIZE; a valid gzip file that any
- * reader inflates to src).  cap must be at least itsx_gzip_bound(n); *dst_n receives the stream's length. */
+ * 1 MiB of input one member of 32 byte-aligned dynamic-Huffman deflate blocks, with its CRC-32 and ISIZE; a valid gzip
+ * file that any reader inflates to src).  cap must be at least itsx_gzip_bound(n); *dst_n receives the stream's length. */
 int64_t itsx_gzip_bound(int64_t n);
 int  itsx_gzip_compress(itsx_ctx *ctx, const uint8_t *src, int64_t n, uint8_t *dst, int64_t cap, int64_t *dst_n);
 

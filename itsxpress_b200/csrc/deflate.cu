@@ -3,14 +3,15 @@
 // Replaces the compression inside the reference's writers (gzip.open(..., "wt") around SeqIO.write,
 // SeqSample.py:767-788, 926-949; level 9 on one core) and the repo's own host writer (zlib level 6 on every core, which
 // bounded every .gz output: 9-12 MB/s per core, profiles/r1n_*, r2j_c5_artifact_n8.json).  The stream is a sequence of
-// independent gzip members of DFL_CHUNK input bytes, like BGZF / pigz -i: any gzip reader inflates it to the same bytes
-// (what parity is judged on; compressed bytes are not comparable even reference-vs-reference: headers carry mtime).
+// gzip members of 1 MiB of input (DFL_GROUP deflate blocks of DFL_CHUNK bytes, each ending on a byte boundary like after
+// zlib's Z_SYNC_FLUSH / pigz): any gzip reader inflates it to the same bytes (what parity is judged on; compressed bytes
+// are not comparable even reference-vs-reference: headers carry mtime).
 //
-//   deflate_kernel   one CTA per member: LZ77 hash chains from a shared-memory table filled in time slices, lazy parse
+//   deflate_kernel   one CTA per block: LZ77 hash chains (reaching into the member's previous block) from a shared-memory table filled in time slices, lazy parse
 //                    per thread with matches stitched across the threads' bytes, dynamic Huffman codes built by one
 //                    thread, bit-parallel emission, CRC-32 by register advance (deflate_core.h has the per-thread bodies; tools/deflate_emul.cpp runs the same
 //                    code on the CPU against zlib's inflate)
-//   gz_frame_kernel  members framed (header, block, CRC-32, ISIZE) back to back at their final offsets
+//   gz_frame_kernel  blocks back to back at their final offsets, members framed (header; CRC-32 combined over the blocks, ISIZE)
 #include <algorithm>
 #include <vector>
 #include "deflate_core.h"
@@ -19,10 +20,11 @@
 namespace {
 
 constexpr int GZ_HEADER = 10, GZ_TRAILER = 8;
-constexpr int GZ_BATCH = 2048;                 // members per launch: 64 MB of text, 256 MB of tokens
+constexpr int GZ_BATCH = 2048;                 // blocks per launch: 64 MB of text, 266 MB of tokens
+static_assert(GZ_BATCH % DFL_GROUP == 0, "a launch starts on a member boundary");
 
 struct DflSmem {
-    uint8_t  buf[DFL_CHUNK + 16];
+    uint8_t  ext[DFL_HIST + DFL_CHUNK + 16];          // history of the previous block, then the chunk
     uint16_t cand[DFL_CHUNK];
     uint32_t table[DFL_HASH_SIZE];
     uint32_t freq_ll[288], freq_d[32];
@@ -46,22 +48,26 @@ deflate_kernel(const uint8_t *__restrict__ text, int64_t n, uint32_t *__restrict
     const int t = threadIdx.x;
     const int64_t base = (int64_t)blockIdx.x * DFL_CHUNK;
     const int len = (int)min((int64_t)DFL_CHUNK, n - base);
+    // blocks of a member: the launch starts on a member boundary (GZ_BATCH is a multiple of DFL_GROUP)
+    const bool first = blockIdx.x % DFL_GROUP == 0;
+    const bool final = blockIdx.x % DFL_GROUP == DFL_GROUP - 1 || blockIdx.x == gridDim.x - 1;
+    const int hist = first ? 0 : DFL_HIST;
     DflShared S;
-    S.buf = sm.buf; S.len = len; S.cand = sm.cand; S.table = sm.table;
+    S.buf = sm.ext + DFL_HIST; S.len = len; S.hist = hist; S.final = final ? 1 : 0; S.cand = sm.cand; S.table = sm.table;
     S.freq_ll = sm.freq_ll; S.freq_d = sm.freq_d; S.len_ll = sm.len_ll; S.len_d = sm.len_d;
     S.code_ll = sm.code_ll; S.code_d = sm.code_d; S.ntok = sm.ntok; S.tbeg = sm.tbeg; S.tend = sm.tend; S.bits = sm.bits;
     S.hdr = sm.hdr; S.hdr_bits = &sm.hdr_bits;
     S.tokens = tokens + (size_t)blockIdx.x * DFL_THREADS * DFL_TOKS;
     S.out = out + (size_t)blockIdx.x * DFL_OUT_WORDS;
 
-    // ---- 0. the chunk into shared memory (16-byte loads: text is the library's own allocation), tables cleared ----
+    // ---- 0. history + chunk into shared memory (16-byte loads: text is the library's own allocation), tables cleared ----
     {
-        const uint4 *src = (const uint4 *)(text + base);
-        uint4 *dst = (uint4 *)sm.buf;
-        const int nvec = len >> 4;
+        const uint4 *src = (const uint4 *)(text + base - hist);
+        uint4 *dst = (uint4 *)(sm.ext + DFL_HIST - hist);
+        const int nbytes = hist + len, nvec = nbytes >> 4;
         for (int v = t; v < nvec; v += DFL_THREADS) dst[v] = src[v];
-        for (int b = (nvec << 4) + t; b < len; b += DFL_THREADS) sm.buf[b] = text[base + b];
-        for (int b = len + t; b < len + 16 && b < DFL_CHUNK + 16; b += DFL_THREADS) sm.buf[b] = 0;
+        for (int b = (nvec << 4) + t; b < nbytes; b += DFL_THREADS) sm.ext[DFL_HIST - hist + b] = text[base - hist + b];
+        if (t < 16) sm.ext[DFL_HIST + len + t] = 0;
     }
     for (int h = t; h < DFL_HASH_SIZE; h += DFL_THREADS) sm.table[h] = 0u;
     for (int i = t; i < 288; i += DFL_THREADS) sm.freq_ll[i] = 0u;
@@ -70,7 +76,9 @@ deflate_kernel(const uint8_t *__restrict__ text, int64_t n, uint32_t *__restrict
     for (int w = t; w < DFL_OUT_WORDS; w += DFL_THREADS) S.out[w] = 0u;
     __syncthreads();
 
-    // ---- 1. match candidates, one time slice of DFL_THREADS positions after the other ----
+    // ---- 1. match candidates: the history enters the table, then one time slice of DFL_THREADS positions after the other ----
+    for (int a0 = 0; a0 < hist; a0 += DFL_THREADS) dfl_hist_enter(S, a0 + t);
+    __syncthreads();
     for (int p0 = 0; p0 < len; p0 += DFL_THREADS) {
         dfl_cand_lookup(S, p0 + t);
         __syncthreads();
@@ -122,7 +130,7 @@ deflate_kernel(const uint8_t *__restrict__ text, int64_t n, uint32_t *__restrict
     __syncthreads();
     const uint32_t body_bits = sm.bits[DFL_THREADS];
     const uint32_t total_bits = sm.hdr_bits + body_bits + sm.len_ll[256];
-    const uint32_t dyn_bytes = (total_bits + 7u) >> 3;
+    const uint32_t dyn_bytes = dfl_block_bytes(total_bits, S.final);
     const bool stored = dyn_bytes >= (uint32_t)len + 5u;
     // ---- 5. emission ----
     if (!stored) {
@@ -133,20 +141,21 @@ deflate_kernel(const uint8_t *__restrict__ text, int64_t n, uint32_t *__restrict
             dfl_bits_start(b, S.out, sm.hdr_bits + body_bits);
             dfl_bits_put(b, sm.code_ll[256], sm.len_ll[256]);
             dfl_bits_finish(b);
+            if (!S.final) dfl_sync_marker(S.out, total_bits);
             out_bytes[blockIdx.x] = dyn_bytes;
         }
     } else {
         uint8_t *o = (uint8_t *)S.out;
         if (t == 0) {
-            o[0] = 1;                                      // BFINAL = 1, BTYPE = 00, padding to the byte
+            o[0] = (uint8_t)S.final;                       // BFINAL, BTYPE = 00, padding to the byte (blocks start on one)
             o[1] = (uint8_t)(len & 0xff); o[2] = (uint8_t)(len >> 8);
             o[3] = (uint8_t)(~len & 0xff); o[4] = (uint8_t)((~len >> 8) & 0xff);
             out_bytes[blockIdx.x] = (uint32_t)len + 5u;
         }
-        for (int b = t; b < len; b += DFL_THREADS) o[5 + b] = sm.buf[b];
+        for (int b = t; b < len; b += DFL_THREADS) o[5 + b] = S.buf[b];
     }
     // ---- CRC-32 of the chunk ----
-    uint32_t c = dfl_crc_part(sm.buf, len, t, sm.crc_table);
+    uint32_t c = dfl_crc_part(S.buf, len, t, sm.crc_table);
 #pragma unroll
     for (int o = 16; o; o >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, o);
     if ((t & 31) == 0) sm.crc_part[t >> 5] = c;
@@ -159,26 +168,35 @@ deflate_kernel(const uint8_t *__restrict__ text, int64_t n, uint32_t *__restrict
     }
 }
 
-// member m -> dst[off[m] ..): 10-byte header, deflate block, CRC-32, ISIZE
+// block j -> dst[off[j] ..); the first block of a member puts the 10-byte header in front of itself, the last one the
+// CRC-32 of the member (its blocks' CRCs combined) and ISIZE behind itself
 __global__ void __launch_bounds__(128)
 gz_frame_kernel(const uint32_t *__restrict__ out, const uint32_t *__restrict__ out_bytes, const uint32_t *__restrict__ crc,
                 const int64_t *__restrict__ off, int64_t n, uint8_t *__restrict__ dst)
 {
-    const int m = blockIdx.x, t = threadIdx.x;
-    const uint32_t nb = out_bytes[m];
-    uint8_t *d = dst + off[m];
-    const uint8_t *src = (const uint8_t *)(out + (size_t)m * DFL_OUT_WORDS);
-    if (t < GZ_HEADER) {
-        // ID1 ID2 CM=8 FLG=0 MTIME=0 XFL=0 OS=255 (unknown)
-        const uint8_t hdr[GZ_HEADER] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff};
-        d[t] = hdr[t];
+    const int j = blockIdx.x, t = threadIdx.x;
+    const bool first = j % DFL_GROUP == 0, final = j % DFL_GROUP == DFL_GROUP - 1 || j == (int)gridDim.x - 1;
+    const uint32_t nb = out_bytes[j];
+    uint8_t *d = dst + off[j];
+    const uint8_t *src = (const uint8_t *)(out + (size_t)j * DFL_OUT_WORDS);
+    if (first) {
+        if (t < GZ_HEADER) {
+            // ID1 ID2 CM=8 FLG=0 MTIME=0 XFL=0 OS=255 (unknown)
+            const uint8_t hdr[GZ_HEADER] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff};
+            d[t] = hdr[t];
+        }
+        d += GZ_HEADER;
     }
-    for (uint32_t b = t; b < nb; b += 128) d[GZ_HEADER + b] = src[b];
-    if (t < GZ_TRAILER) {
-        const int64_t base = (int64_t)m * DFL_CHUNK;
-        const uint32_t isize = (uint32_t)min((int64_t)DFL_CHUNK, n - base);
-        const uint32_t v = t < 4 ? crc[m] : isize;
-        d[GZ_HEADER + nb + t] = (uint8_t)(v >> (8 * (t & 3)));
+    for (uint32_t b = t; b < nb; b += 128) d[b] = src[b];
+    if (final && t == 0) {
+        const int j0 = j - j % DFL_GROUP;
+        uint32_t c = 0, isize = 0;
+        for (int k = j0; k <= j; k++) {
+            const uint32_t lk = (uint32_t)min((int64_t)DFL_CHUNK, n - (int64_t)k * DFL_CHUNK);
+            c = k == j0 ? crc[k] : dfl_crc_combine(c, crc[k], lk);
+            isize += lk;
+        }
+        for (int b = 0; b < 4; b++) { d[nb + b] = (uint8_t)(c >> (8 * b)); d[nb + 4 + b] = (uint8_t)(isize >> (8 * b)); }
     }
 }
 
@@ -186,8 +204,9 @@ gz_frame_kernel(const uint32_t *__restrict__ out, const uint32_t *__restrict__ o
 
 extern "C" int64_t itsx_gzip_bound(int64_t n)
 {
-    const int64_t members = std::max<int64_t>(1, (n + DFL_CHUNK - 1) / DFL_CHUNK);
-    return n + members * (GZ_HEADER + GZ_TRAILER + 5);
+    const int64_t blocks = std::max<int64_t>(1, (n + DFL_CHUNK - 1) / DFL_CHUNK);
+    const int64_t members = (blocks + DFL_GROUP - 1) / DFL_GROUP;
+    return n + blocks * 5 + members * (GZ_HEADER + GZ_TRAILER);      // worst case: every block stored
 }
 
 extern "C" int itsx_gzip_compress(itsx_ctx *c, const uint8_t *src, int64_t n, uint8_t *dst, int64_t cap, int64_t *dst_n)
@@ -196,7 +215,7 @@ extern "C" int itsx_gzip_compress(itsx_ctx *c, const uint8_t *src, int64_t n, ui
     if (cap < itsx_gzip_bound(n)) { c->err = "itsx_gzip_compress: output buffer smaller than itsx_gzip_bound(n)"; return ITSX_ELIMIT; }
     cudaStream_t st = c->stream;
     CUDA_TRY(c, cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DflSmem)));
-    const int64_t members = std::max<int64_t>(1, (n + DFL_CHUNK - 1) / DFL_CHUNK);
+    const int64_t members = std::max<int64_t>(1, (n + DFL_CHUNK - 1) / DFL_CHUNK);      // blocks, in fact
     int64_t written = 0;
     std::vector<uint32_t> h_bytes;
     std::vector<int64_t> h_off;
@@ -218,7 +237,10 @@ extern "C" int itsx_gzip_compress(itsx_ctx *c, const uint8_t *src, int64_t n, ui
         CUDA_TRY(c, cudaMemcpyAsync(h_bytes.data(), d_bytes, (size_t)nm * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaStreamSynchronize(st));
         h_off[0] = 0;
-        for (int m = 0; m < nm; m++) h_off[m + 1] = h_off[m] + GZ_HEADER + (int64_t)h_bytes[m] + GZ_TRAILER;
+        for (int m = 0; m < nm; m++) {
+            const bool first = m % DFL_GROUP == 0, final = m % DFL_GROUP == DFL_GROUP - 1 || m == nm - 1;
+            h_off[m + 1] = h_off[m] + (first ? GZ_HEADER : 0) + (int64_t)h_bytes[m] + (final ? GZ_TRAILER : 0);
+        }
         CUDA_TRY(c, c->d_gz_pack.ensure((size_t)h_off[nm]));
         CUDA_TRY(c, cudaMemcpyAsync(d_off, h_off.data(), (size_t)nm * 8, cudaMemcpyHostToDevice, st));
         gz_frame_kernel<<<nm, 128, 0, st>>>(c->d_gz_out.as<uint32_t>(), d_bytes, d_crc, d_off, nb, c->d_gz_pack.as<uint8_t>());

@@ -3,10 +3,13 @@
 // with zlib (this container has no GPU; the kernel itself is exercised by tests/test_gpu_gzip.py on the GPU box).
 //
 // One CTA (DFL_THREADS threads) turns one chunk of DFL_CHUNK input bytes into ONE deflate block with its own dynamic
-// Huffman codes (or a stored block when that is smaller); the host frames every block as a gzip member.  Phases,
+// Huffman codes (or a stored block when that is smaller).  DFL_GROUP consecutive blocks form a gzip member: a block may
+// reach back into the previous block of its member (the deflate window), ends on a byte boundary (an empty stored block
+// behind it, zlib's Z_SYNC_FLUSH) so that the blocks are concatenated as bytes, and the last one carries BFINAL.  Phases,
 // separated by CTA barriers:
-//   1. candidates   positions in time slices of DFL_THREADS: look the 4-byte hash up (largest earlier position of the
-//                   slices before), then enter the slice's own positions (atomicMax => deterministic)
+//   1. candidates   the previous block's positions enter the 4-byte hash table; then positions in time slices of
+//                   DFL_THREADS: look the hash up (largest earlier position of the slices before), then enter the
+//                   slice's own positions (atomicMax => deterministic)
 //   2. parse        a thread parses its DFL_SUB bytes (hash chain of up to DFL_MAX_CHAIN candidates vs. distance 1, one
 //                   step of lazy evaluation; its last match may run into the next threads' bytes), tokens to HBM;
 //      stitch       prefix maximum of the threads' end positions: a thread drops / cuts the tokens the threads before it
@@ -29,7 +32,9 @@
 
 constexpr int DFL_THREADS = 256;
 constexpr int DFL_SUB = 128;                        // bytes parsed by one thread
-constexpr int DFL_CHUNK = DFL_THREADS * DFL_SUB;    // 32 768 input bytes per gzip member (= the deflate window)
+constexpr int DFL_CHUNK = DFL_THREADS * DFL_SUB;    // 32 768 input bytes per deflate block (= the deflate window)
+constexpr int DFL_GROUP = 32;                       // blocks per gzip member (1 MiB of input)
+constexpr int DFL_HIST = DFL_CHUNK;                 // bytes of the previous block a block may reach back into
 constexpr int DFL_HASH_BITS = 13;
 constexpr int DFL_HASH_SIZE = 1 << DFL_HASH_BITS;
 constexpr int DFL_NLL = 286, DFL_ND = 30, DFL_NCL = 19;
@@ -207,10 +212,12 @@ DFL_HD void dfl_huff_codes(const uint8_t *len, int n, uint16_t *code)
 
 // ---- the block's shared state (shared memory on the device, plain arrays in the emulation) ----
 struct DflShared {
-    const uint8_t *buf;                 // the chunk (+ 8 readable bytes behind it)
+    const uint8_t *buf;                 // the chunk (+ 8 readable bytes behind it); `hist` bytes of history in front of it
     int            len;
-    uint16_t      *cand;                // [DFL_CHUNK]: candidate position + 1, 0 = none
-    uint32_t      *table;               // [DFL_HASH_SIZE]: largest position + 1 entered so far
+    int            hist;                // 0 (first block of a member) or DFL_HIST
+    int            final;               // last block of its member: BFINAL = 1, no byte-alignment marker behind it
+    uint16_t      *cand;                // [DFL_CHUNK]: candidate position (counted from the start of the history) + 1, 0 = none
+    uint32_t      *table;               // [DFL_HASH_SIZE]: largest position (from the start of the history) + 1 entered so far
     uint32_t      *freq_ll, *freq_d;    // [288], [32]
     uint8_t       *len_ll, *len_d;      // [288], [32]
     uint16_t      *code_ll, *code_d;    // [288], [32]
@@ -224,14 +231,20 @@ struct DflShared {
     uint32_t      *out;                 // HBM: [DFL_OUT_WORDS], zero on entry
 };
 
-// phase 1, one time slice: p = slice * DFL_THREADS + t.  look-up first (barrier), then enter (barrier)
+// phase 1.  History first: every position of the previous block enters the table (any order: the maximum wins).  Then
+// one time slice after the other: p = slice * DFL_THREADS + t, look-up first (barrier), then enter (barrier).
+// Positions count from the start of the history: a = hist + p.
+DFL_HD void dfl_hist_enter(const DflShared &S, int a)
+{
+    if (a < S.hist) DFL_ATOMIC_MAX(&S.table[dfl_hash4(S.buf - S.hist + a)], (uint32_t)(a + 1));
+}
 DFL_HD void dfl_cand_lookup(const DflShared &S, int p)
 {
     if (p < S.len) S.cand[p] = (p + DFL_MIN_HASH_MATCH <= S.len) ? (uint16_t)S.table[dfl_hash4(S.buf + p)] : (uint16_t)0;
 }
 DFL_HD void dfl_cand_enter(const DflShared &S, int p)
 {
-    if (p + DFL_MIN_HASH_MATCH <= S.len) DFL_ATOMIC_MAX(&S.table[dfl_hash4(S.buf + p)], (uint32_t)(p + 1));
+    if (p + DFL_MIN_HASH_MATCH <= S.len) DFL_ATOMIC_MAX(&S.table[dfl_hash4(S.buf + p)], (uint32_t)(S.hist + p + 1));
 }
 
 // the best match at p (it may run past the thread's own bytes: dfl_stitch trims what follows): longest of the hash chain (at most DFL_MAX_CHAIN candidates, nearest
@@ -244,18 +257,22 @@ DFL_HD int dfl_find_match(const DflShared &S, int p, int &bdist)
     // cand[] links every position to the head of its hash before its own time slice: a chain of earlier positions
     // with the same hash, nearest first (deterministic: it does not depend on the order threads ran in)
     if (maxlen >= DFL_MIN_HASH_MATCH) {
+        const uint8_t *ext = S.buf - S.hist;
         int c = S.cand[p];
         for (int tries = 0; c != 0 && tries < DFL_MAX_CHAIN; tries++) {
-            const uint8_t *q = S.buf + (c - 1);
-            if (q[best] == S.buf[p + best]) {                       // can only win if it matches one byte further
+            const int a = c - 1, dist = S.hist + p - a;
+            if (dist > 32768) break;                                    // older ones are farther still
+            const uint8_t *q = ext + a;
+            if (q[best] == S.buf[p + best]) {                           // can only win if it matches one byte further
                 const int l = dfl_match_len(q, S.buf + p, maxlen);
-                if (l >= DFL_MIN_HASH_MATCH && l > best) { best = l; bdist = p - (c - 1); }
+                if (l >= DFL_MIN_HASH_MATCH && l > best) { best = l; bdist = dist; }
                 if (best >= DFL_NICE_MATCH || best == maxlen) break;
             }
-            c = S.cand[c - 1];
+            if (a < S.hist) break;                                      // the history has no links of its own
+            c = S.cand[a - S.hist];
         }
     }
-    if (p > 0 && maxlen >= DFL_MIN_RUN) {
+    if (S.hist + p > 0 && maxlen >= DFL_MIN_RUN) {
         const int l = dfl_match_len(S.buf + p - 1, S.buf + p, maxlen);
         if (l >= DFL_MIN_RUN && l >= best) { best = l; bdist = 1; }
     }
@@ -330,7 +347,7 @@ DFL_HD void dfl_stitch(const DflShared &S, int t, uint32_t covered)
     }
 }
 
-// phase 3 (one thread): code lengths, codes, block header.  BFINAL = 1: one block per gzip member.
+// phase 3 (one thread): code lengths, codes, block header
 DFL_HD void dfl_build_codes(const DflShared &S, DflHuffScratch &hs)
 {
     S.freq_ll[256] = 1;                                   // end of block
@@ -367,7 +384,7 @@ DFL_HD void dfl_build_codes(const DflShared &S, DflHuffScratch &hs)
     for (int i = 0; i < DFL_HDR_WORDS; i++) S.hdr[i] = 0;
     DflBits b;
     dfl_bits_start(b, S.hdr, 0);
-    dfl_bits_put(b, 1u, 1);                               // BFINAL
+    dfl_bits_put(b, S.final ? 1u : 0u, 1);                // BFINAL
     dfl_bits_put(b, 2u, 2);                               // BTYPE = dynamic Huffman
     dfl_bits_put(b, (uint32_t)(hlit - 257), 5);
     dfl_bits_put(b, (uint32_t)(hdist - 1), 5);
@@ -426,6 +443,20 @@ DFL_HD void dfl_emit(const DflShared &S, int t, uint32_t start)
     dfl_bits_finish(b);
 }
 
+// A block that is not the last of its member ends on a byte boundary: an empty stored block (BFINAL = 0, BTYPE = 00,
+// padding, LEN = 0, NLEN = 0xffff -- zlib's Z_SYNC_FLUSH) follows its end-of-block code.  The words are zero already, so
+// only the two 0xff bytes are written.  Returns the block's length in bytes; `total_bits` = bits up to the end-of-block code.
+DFL_HD uint32_t dfl_block_bytes(uint32_t total_bits, int final)
+{
+    if (final) return (total_bits + 7u) >> 3;
+    return ((total_bits + 3u + 7u) >> 3) + 4u;
+}
+DFL_HD void dfl_sync_marker(uint32_t *out, uint32_t total_bits)
+{
+    const uint32_t at = ((total_bits + 3u + 7u) >> 3) + 2u;          // byte offset of NLEN
+    for (uint32_t b = at; b < at + 2u; b++) DFL_ATOMIC_OR(&out[b >> 2], 0xffu << (8u * (b & 3u)));
+}
+
 // ---- CRC-32 (gzip): byte-wise register, and the advance of a register over m more bytes ----
 DFL_HD uint32_t dfl_crc_table_entry(uint32_t i)
 {
@@ -469,6 +500,13 @@ DFL_HD uint32_t dfl_crc_part(const uint8_t *buf, int len, int t, const uint32_t 
     const int after = len - end;
     if (after > 0 && c != 0u) c = dfl_multmodp(dfl_xpow8((uint32_t)after), c);
     return c;
+}
+
+// CRC-32 of A || B from the (finalised) CRC-32s of A and B and B's length: zlib's crc32_combine
+DFL_HD uint32_t dfl_crc_combine(uint32_t crc_a, uint32_t crc_b, uint32_t len_b)
+{
+    if (len_b == 0) return crc_a;
+    return dfl_multmodp(dfl_xpow8(len_b), crc_a) ^ crc_b;
 }
 
 #endif
