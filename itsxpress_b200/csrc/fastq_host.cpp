@@ -19,6 +19,15 @@ namespace {
 
 thread_local std::string g_host_err;
 
+// line ends of the buffer the counting call (cap == 0) has just scanned, kept for the filling call that follows it on the
+// same thread with the same buffer: the file is scanned once, not twice
+struct LineIndexCache {
+    const uint8_t *buf = nullptr;
+    int64_t nbytes = 0, nlines = 0;
+    std::vector<int64_t> lend;
+};
+thread_local LineIndexCache g_lines;
+
 int nthreads_for(int64_t work, int64_t grain)
 {
     int hw = (int)std::thread::hardware_concurrency();
@@ -48,47 +57,55 @@ extern "C" {
 const char *itsx_host_last_error(void) { return g_host_err.c_str(); }
 
 // Index the records of a 4-line FASTQ buffer.  With cap == 0 only the record count is returned (arrays may be
-// NULL).  Returns the number of records, or ITSX_EFORMAT with the reason in itsx_host_last_error().
+// NULL); the filling call that follows it on the same thread for the same (unchanged) buffer reuses its line scan.  Returns the number of records, or ITSX_EFORMAT with the reason in itsx_host_last_error().
 int64_t itsx_fastq_index(const uint8_t *buf, int64_t nbytes, int64_t cap, int64_t *t_off, int32_t *t_len,
                          int64_t *s_off, int32_t *s_len, int64_t *q_off)
 {
     g_host_err.clear();
     if (nbytes < 0 || (nbytes && !buf)) { g_host_err = "fastq_index: null buffer"; return ITSX_EINVAL; }
     if (nbytes == 0) return 0;
-    // pass 1: newline counts per chunk
-    const int nt = nthreads_for(nbytes, 8 << 20);
-    const int64_t step = (nbytes + nt - 1) / nt;
-    std::vector<int64_t> cnt((size_t)nt + 1, 0);
-    parallel_for(nt, 1, [&](int64_t a, int64_t b, int) {
-        for (int64_t t = a; t < b; t++) {
-            const uint8_t *p = buf + t * step, *e = buf + std::min(nbytes, (t + 1) * step);
-            int64_t c = 0;
-            while (p < e) {
-                const uint8_t *q = (const uint8_t *)memchr(p, '\n', (size_t)(e - p));
-                if (!q) break;
-                c++;
-                p = q + 1;
+    std::vector<int64_t> lend;
+    int64_t nlines = 0;
+    if (cap != 0 && g_lines.buf == buf && g_lines.nbytes == nbytes && !g_lines.lend.empty()) {
+        lend.swap(g_lines.lend);
+        nlines = g_lines.nlines;
+        g_lines = LineIndexCache();
+    } else {
+        // pass 1: newline counts per chunk
+        const int nt = nthreads_for(nbytes, 8 << 20);
+        const int64_t step = (nbytes + nt - 1) / nt;
+        std::vector<int64_t> cnt((size_t)nt + 1, 0);
+        parallel_for(nt, 1, [&](int64_t a, int64_t b, int) {
+            for (int64_t t = a; t < b; t++) {
+                const uint8_t *p = buf + t * step, *e = buf + std::min(nbytes, (t + 1) * step);
+                int64_t c = 0;
+                while (p < e) {
+                    const uint8_t *q = (const uint8_t *)memchr(p, '\n', (size_t)(e - p));
+                    if (!q) break;
+                    c++;
+                    p = q + 1;
+                }
+                cnt[(size_t)t + 1] = c;
             }
-            cnt[(size_t)t + 1] = c;
-        }
-    });
-    for (int t = 0; t < nt; t++) cnt[(size_t)t + 1] += cnt[(size_t)t];
-    int64_t nlines = cnt[(size_t)nt] + (buf[nbytes - 1] != '\n' ? 1 : 0);
-    // pass 2: line ends
-    std::vector<int64_t> lend((size_t)nlines);
-    parallel_for(nt, 1, [&](int64_t a, int64_t b, int) {
-        for (int64_t t = a; t < b; t++) {
-            const uint8_t *p = buf + t * step, *e = buf + std::min(nbytes, (t + 1) * step);
-            int64_t k = cnt[(size_t)t];
-            while (p < e) {
-                const uint8_t *q = (const uint8_t *)memchr(p, '\n', (size_t)(e - p));
-                if (!q) break;
-                lend[(size_t)k++] = q - buf;
-                p = q + 1;
+        });
+        for (int t = 0; t < nt; t++) cnt[(size_t)t + 1] += cnt[(size_t)t];
+        nlines = cnt[(size_t)nt] + (buf[nbytes - 1] != '\n' ? 1 : 0);
+        // pass 2: line ends
+        lend.resize((size_t)nlines);
+        parallel_for(nt, 1, [&](int64_t a, int64_t b, int) {
+            for (int64_t t = a; t < b; t++) {
+                const uint8_t *p = buf + t * step, *e = buf + std::min(nbytes, (t + 1) * step);
+                int64_t k = cnt[(size_t)t];
+                while (p < e) {
+                    const uint8_t *q = (const uint8_t *)memchr(p, '\n', (size_t)(e - p));
+                    if (!q) break;
+                    lend[(size_t)k++] = q - buf;
+                    p = q + 1;
+                }
             }
-        }
-    });
-    if (buf[nbytes - 1] != '\n') lend[(size_t)nlines - 1] = nbytes;
+        });
+        if (buf[nbytes - 1] != '\n') lend[(size_t)nlines - 1] = nbytes;
+    }
     // drop trailing blank lines
     auto lstart = [&](int64_t i) { return i == 0 ? (int64_t)0 : lend[(size_t)i - 1] + 1; };
     auto lstop = [&](int64_t i) {                     // exclusive end without '\r'
@@ -99,7 +116,11 @@ int64_t itsx_fastq_index(const uint8_t *buf, int64_t nbytes, int64_t cap, int64_
     while (nlines > 0 && lstop(nlines - 1) == lstart(nlines - 1)) nlines--;
     if (nlines % 4 != 0) { g_host_err = "FASTQ is truncated or not in 4-line format"; return ITSX_EFORMAT; }
     const int64_t n = nlines / 4;
-    if (cap == 0) return n;
+    if (cap == 0) {
+        g_lines.buf = buf; g_lines.nbytes = nbytes; g_lines.nlines = nlines;
+        g_lines.lend.swap(lend);
+        return n;
+    }
     if (cap < n) { g_host_err = "fastq_index: output arrays too small"; return ITSX_EINVAL; }
     std::atomic<int> bad(0);
     parallel_for(n, 1 << 14, [&](int64_t a, int64_t b, int) {
