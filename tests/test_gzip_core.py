@@ -58,3 +58,33 @@ def test_emulated_streams_inflate_to_the_input(tmp_path):
     name, data = gzip_cases()[-1]
     import zlib
     assert len(emulate(exe, tmp_path, data)) < 1.1 * len(zlib.compress(data, 1))
+
+
+def test_emulated_streams_at_block_member_and_window_boundaries(tmp_path):
+    """sizes around one block (32 768 bytes) and one member (32 blocks), repeats at distances around the 32 768-byte
+    window and around the longest match (258), and mixtures of literals, runs and copies"""
+    exe = build_emulator(tmp_path)
+    rng = np.random.default_rng(5)
+    C, G = 32768, 32
+    cases = []
+    for n in (C - 1, C + 1, 2 * C, G * C - 1, G * C, G * C + 1, (G + 1) * C + 5):
+        cases.append(("acgt %d" % n, bytes(rng.integers(65, 69, n, dtype=np.uint8))))
+    for dist in (1, 2, 3, 257, 258, 259, 32767, 32768, 32769):
+        block = bytes(rng.integers(0, 256, dist, dtype=np.uint8))
+        cases.append(("period %d" % dist, (block * (150000 // dist + 2))[:150000]))
+    for it in range(12):
+        out = bytearray()
+        target, alpha = int(rng.integers(1, 4 * C)), int(rng.integers(2, 257))
+        while len(out) < target:
+            k = rng.integers(0, 3)
+            if k == 0 or len(out) < 8:
+                out += bytes(rng.integers(0, alpha, int(rng.integers(1, 300)), dtype=np.uint8))
+            elif k == 1:
+                out += bytes([int(rng.integers(0, alpha))]) * int(rng.integers(1, 700))
+            else:
+                dist, ln = int(rng.integers(1, min(len(out), 70000) + 1)), int(rng.integers(3, 600))
+                for _ in range(ln):
+                    out.append(out[-dist])
+        cases.append(("mix %d" % it, bytes(out[:target])))
+    for name, data in cases:
+        assert gzip.decompress(emulate(exe, tmp_path, data)) == data, name
