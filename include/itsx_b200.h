@@ -250,6 +250,15 @@ int  itsx_merge_pairs(itsx_ctx *ctx, const uint8_t *fseq, const uint8_t *fqual, 
 int  itsx_merge_fetch(itsx_ctx *ctx, int32_t *merged_index, int64_t *out_off, uint8_t *out_seq, uint8_t *out_qual);
 int  itsx_merge_get_stats(const itsx_ctx *ctx, itsx_merge_stats *st);
 
+/* ---- gzip reader (inflate_host.cpp, host only) -----------------------------------------------------------------
+ * Replaces gzip.open(path, "rt") under SeqIO.parse (SeqSample.py:742-752, 767-788; main.py:295-330).  A gzip file
+ * src[n] (one or more members) is inflated into dst; whole members are decoded while they fit into cap bytes and their
+ * CRC-32 / ISIZE are checked.  Returns 0 when the whole input was consumed, 1 when the next member does not fit
+ * (*in_used / *out_used say how far it got, always at a member boundary: grow dst and call again with src + *in_used;
+ * *in_used == 0 means the first member alone is larger than cap), ITSX_EFORMAT for anything that is not a valid gzip
+ * stream. */
+int  itsx_gunzip(const uint8_t *src, int64_t n, uint8_t *dst, int64_t cap, int64_t *in_used, int64_t *out_used);
+
 /* ---- gzip writer (deflate.cu) ------------------------------------------------------------------------------------
  * Replaces the compression inside the reference's output writers: gzip.open(outfile, "wt") around SeqIO.write in
  * Dedup.create_trimmed_seqs / create_paired_trimmed_seqs (SeqSample.py:767-788, 926-949) and the .fastq.gz files of the
