@@ -251,13 +251,25 @@ int  itsx_merge_fetch(itsx_ctx *ctx, int32_t *merged_index, int64_t *out_off, ui
 int  itsx_merge_get_stats(const itsx_ctx *ctx, itsx_merge_stats *st);
 
 /* ---- gzip reader (inflate_host.cpp, host only) -----------------------------------------------------------------
- * Replaces gzip.open(path, "rt") under SeqIO.parse (SeqSample.py:742-752, 767-788; main.py:295-330).  A gzip file
- * src[n] (one or more members) is inflated into dst; whole members are decoded while they fit into cap bytes and their
- * CRC-32 / ISIZE are checked.  Returns 0 when the whole input was consumed, 1 when the next member does not fit
- * (*in_used / *out_used say how far it got, always at a member boundary: grow dst and call again with src + *in_used;
- * *in_used == 0 means the first member alone is larger than cap), ITSX_EFORMAT for anything that is not a valid gzip
- * stream. */
-int  itsx_gunzip(const uint8_t *src, int64_t n, uint8_t *dst, int64_t cap, int64_t *in_used, int64_t *out_used);
+ * Replaces gzip.open(path, "rt") under SeqIO.parse (SeqSample.py:742-752, 767-788; main.py:295-330), used like gzread:
+ * itsx_gz_open over the bytes of a gzip file (one or more members; the memory must stay valid until itsx_gz_close),
+ * then itsx_gz_read until it returns 0.  `threads` > 1 inflates ONE deflate stream on several host cores (chunks that
+ * find their own block starts, 16-bit symbols with markers for the unknown window, resolved front to back); 1 is a
+ * single-core decoder, 0 = every core.  itsx_gz_read fills dst with up to cap bytes and returns how many (it may return
+ * fewer than cap before the end), 0 at the end of the stream, or
+ * ITSX_EFORMAT for anything that is not a valid gzip stream (CRC-32 and ISIZE of every member are checked; the error is
+ * sticky).  `hist`: how many bytes right in front of dst are the output of the preceding calls, untouched (0 when dst is a
+ * fresh buffer): with 32 KB of them in place the stream is decoded straight into dst, otherwise through a bounce buffer
+ * until the call itself has written that much. */
+typedef struct itsx_gz itsx_gz;
+itsx_gz *itsx_gz_open(const uint8_t *src, int64_t n, int threads);
+int64_t  itsx_gz_read(itsx_gz *h, uint8_t *dst, int64_t cap, int64_t hist);
+int      itsx_gz_eof(const itsx_gz *h);
+/* chunking of the multi-core mode (compressed bytes per chunk, least input worth several cores; the tests shrink them) and
+ * its counters (what = 0: batches decoded on several cores, 1: chunks decoded again because a block start was none) */
+int      itsx_gz_tune(itsx_gz *h, int64_t chunk_min, int64_t chunk_max, int64_t par_min);
+int64_t  itsx_gz_stat(const itsx_gz *h, int what);
+void     itsx_gz_close(itsx_gz *h);
 
 /* ---- gzip writer (deflate.cu) ------------------------------------------------------------------------------------
  * Replaces the compression inside the reference's output writers: gzip.open(outfile, "wt") around SeqIO.write in

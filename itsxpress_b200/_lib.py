@@ -95,7 +95,8 @@ SYMBOLS = [
     "itsx_derep_map", "itsx_reads_set_samples", "itsx_trim_gather_resident", "itsx_run_trim", "itsx_quals_upload", "itsx_derep_resident", "itsx_run_fetch",
     "itsx_shard_plan", "itsx_shard_pack", "itsx_shard_owner_derep", "itsx_shard_answers", "itsx_shard_apply",
     "itsx_merge_default_params", "itsx_merge_pairs", "itsx_merge_fetch", "itsx_merge_get_stats",
-    "itsx_gzip_bound", "itsx_gzip_compress", "itsx_gunzip",
+    "itsx_gzip_bound", "itsx_gzip_compress",
+    "itsx_gz_open", "itsx_gz_read", "itsx_gz_eof", "itsx_gz_close", "itsx_gz_tune", "itsx_gz_stat",
     "itsx_host_last_error", "itsx_fastq_index", "itsx_bytes_gather", "itsx_fastq_format",
 ]
 
@@ -182,7 +183,16 @@ def lib():
     L.itsx_gzip_bound.argtypes = [i64]
     L.itsx_gzip_bound.restype = i64
     L.itsx_gzip_compress.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
-    L.itsx_gunzip.argtypes = [vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64)]
+    L.itsx_gz_open.argtypes = [vp, i64, C.c_int]
+    L.itsx_gz_open.restype = vp
+    L.itsx_gz_read.argtypes = [vp, vp, i64, i64]
+    L.itsx_gz_read.restype = i64
+    L.itsx_gz_eof.argtypes = [vp]
+    L.itsx_gz_close.argtypes = [vp]
+    L.itsx_gz_close.restype = None
+    L.itsx_gz_tune.argtypes = [vp, i64, i64, i64]
+    L.itsx_gz_stat.argtypes = [vp, C.c_int]
+    L.itsx_gz_stat.restype = i64
     L.itsx_host_last_error.restype = C.c_char_p
     L.itsx_fastq_index.restype = i64
     L.itsx_fastq_index.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp]

@@ -114,47 +114,83 @@ def _gather_numpy(buf, off, length):
     return buf[idx], out_off
 
 
-def gunzip(comp):
-    """A gzip file's bytes inflated by the native reader (csrc/inflate_host.cpp: about three times zlib's rate, CRC-32 and
-    ISIZE of every member checked) -> uint8 array.  Anything it does not accept goes to the gzip module, which inflates it
-    or raises what the reference would have raised (BadGzipFile, EOFError, zlib.error)."""
-    import ctypes as C
-    a = np.frombuffer(comp, dtype=np.uint8)
+def host_share():
+    """Host cores this process may use: all of them divided by the ranks that share the box."""
+    cores = os.cpu_count() or 2
+    return max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))))
+
+
+class GzReader:
+    """gzread-like reader over the bytes of a gzip file (csrc/inflate_host.cpp).  ``threads`` > 1 inflates a single
+    deflate stream on several cores; every member's CRC-32 and ISIZE are checked."""
+
+    def __init__(self, comp, threads=1, _tune=None):
+        import ctypes as C
+        self._a = comp if isinstance(comp, np.ndarray) else np.frombuffer(comp, dtype=np.uint8)     # keeps the input alive
+        self._L = _native()
+        self._h = self._L.itsx_gz_open(C.c_void_p(self._a.ctypes.data if self._a.size else 0), self._a.size, int(threads))
+        if not self._h:
+            raise MemoryError("itsx_gz_open")
+        if _tune:
+            self._L.itsx_gz_tune(self._h, *[int(v) for v in _tune])
+
+    def readinto(self, out, at=0, hist=0):
+        """Fill out[at:] (uint8 array); bytes written, 0 at the end of the stream, < 0 for a malformed stream.  ``hist``:
+        how many bytes in front of out[at] are the output of the preceding calls (0 for a fresh buffer)."""
+        import ctypes as C
+        return int(self._L.itsx_gz_read(self._h, C.c_void_p(out.ctypes.data + at), out.size - at, int(hist)))
+
+    def stat(self, what):
+        return int(self._L.itsx_gz_stat(self._h, what))
+
+    def close(self):
+        if self._h:
+            self._L.itsx_gz_close(self._h)
+            self._h = None
+        self._a = None
+
+    __del__ = close
+
+
+def gunzip(comp, threads=None, _tune=None):
+    """A gzip file's bytes inflated by the native reader -> uint8 array.  ``threads`` None: this process's share of the
+    host cores (one deflate stream is then inflated on several of them).  Anything the reader does not accept goes to
+    the gzip module, which inflates it or raises what the reference would have raised (BadGzipFile, EOFError,
+    zlib.error)."""
+    a = comp if isinstance(comp, np.ndarray) else np.frombuffer(comp, dtype=np.uint8)
     n = a.size
-    L = _native()
     if n >= 18:
         isize = int.from_bytes(a[-4:].tobytes(), "little")
         # one member (every Casava / Illumina file): ISIZE is the answer unless it wrapped; several: start from a guess
         cap = isize + 64 if isize >= n // 2 else 4 * n + (1 << 16)
-        out = np.empty(cap, np.uint8)
-        done_in, done_out = 0, 0
-        used_in, used_out = C.c_int64(), C.c_int64()
-        while True:
-            rc = L.itsx_gunzip(C.c_void_p(a.ctypes.data + done_in), n - done_in, C.c_void_p(out.ctypes.data + done_out),
-                               out.size - done_out, C.byref(used_in), C.byref(used_out))
-            if rc < 0:
-                break
-            done_in += used_in.value
-            done_out += used_out.value
-            if rc == 0:
-                return out[:done_out]
-            # the next member does not fit: grow by what the rest of the file is likely to need.  Deflate cannot expand
-            # more than 1032 : 1, so a buffer beyond that which is still too small means a damaged stream
-            rest = n - done_in
-            if out.size - done_out > 1032 * rest + (1 << 16):
-                break
-            ratio = max(done_out / max(done_in, 1), 4.0) if done_in else 8.0
-            grown = np.empty(int(done_out + rest * ratio * 1.25) + max(out.size, 1 << 20), np.uint8)
-            grown[:done_out] = out[:done_out]
-            out = grown
+        out = np.empty(max(cap, 1 << 16), np.uint8)
+        r = GzReader(a, host_share() if threads is None else threads, _tune)
+        try:
+            done = 0
+            while True:
+                if done == out.size:                        # grow; deflate cannot expand beyond 1032 : 1
+                    if out.size > 1032 * n + (1 << 16):
+                        break
+                    grown = np.empty(out.size + max(out.size // 2, 1 << 20), np.uint8)
+                    grown[:done] = out
+                    out = grown
+                k = r.readinto(out, done, done)
+                if k < 0:
+                    break
+                if k == 0:
+                    return out[:done]
+                done += k
+        finally:
+            r.close()
     return np.frombuffer(gzip.decompress(bytes(comp)), dtype=np.uint8)
 
 
-def _open_buffer(path):
-    """Decompressed content of ``path`` as a bytes-like object (a uint8 array for .gz: no copy behind the inflater)."""
+def _open_buffer(path, threads=None):
+    """Decompressed content of ``path`` as a bytes-like object (a uint8 array for .gz: no copy behind the inflater).
+    ``threads``: host cores the inflate of a .gz may use (None: this process's share)."""
     if path.endswith(".gz"):
         with open(path, "rb") as f:
-            return gunzip(f.read())
+            return gunzip(f.read(), threads)
     if path.endswith(".zst"):
         from . import _zstd
         with open(path, "rb") as f:
@@ -269,8 +305,8 @@ def cached_count(path):
     return hit[2] if (st.st_size, st.st_mtime_ns) == hit[:2] else None
 
 
-def _read_fastq_now(path):
-    batch = parse_bytes(_open_buffer(path))
+def _read_fastq_now(path, threads=None):
+    batch = parse_bytes(_open_buffer(path, threads))
     note_count(path, batch.n)
     return batch
 
@@ -309,7 +345,9 @@ def prefetch(paths):
             st = os.stat(p)
         except OSError:
             continue
-        _PREFETCH[key] = (_PREFETCH_POOL.submit(_read_fastq_now, p), st.st_size, st.st_mtime_ns)
+        # 2 x READ_AHEAD files are in flight: each inflates on its part of the cores (one core each on a small share, where
+        # the single-core decoder does the same work in half the core-seconds)
+        _PREFETCH[key] = (_PREFETCH_POOL.submit(_read_fastq_now, p, max(1, host_share() // (2 * READ_AHEAD))), st.st_size, st.st_mtime_ns)
 
 
 def drop_prefetched():
@@ -319,7 +357,11 @@ def drop_prefetched():
     _PREFETCH.clear()
 
 
-def read_fastq(path):
+def read_fastq(path, threads=None):
+    """The file as a FastqBatch.  ``threads``: host cores for the inflate of a .gz (None: this process's share, or the
+    read-ahead's per-file part of it while other files are being read ahead)."""
+    if threads is None and _PREFETCH:
+        threads = max(1, host_share() // (2 * READ_AHEAD))
     hit = _PREFETCH.pop(os.path.abspath(path), None)
     if hit is not None:
         fut, size, mtime = hit
@@ -329,18 +371,19 @@ def read_fastq(path):
                 return fut.result()
         except Exception:
             pass                        # fall through: the ordinary read reports the problem where it is expected
-    return _read_fastq_now(path)
+    return _read_fastq_now(path, threads)
 
 
 def read_fastq_many(paths):
-    """The files read, decompressed and scanned concurrently, one thread each (zlib and the native scanner release the
-    GIL): R1 and R2 of a pair arrive in the time of the slower one -- gzip inflates at ~200 MB/s on one core."""
+    """The files read, decompressed and scanned concurrently (the native inflater and scanner release the GIL), each
+    on its part of this process's cores: R1 and R2 of a pair arrive in the time of the slower one."""
     paths = list(paths)
     if len(paths) < 2:
         return [read_fastq(p) for p in paths]
     from concurrent.futures import ThreadPoolExecutor
+    per_file = None if _PREFETCH else max(1, host_share() // len(paths))
     with ThreadPoolExecutor(len(paths)) as ex:
-        return list(ex.map(read_fastq, paths))
+        return list(ex.map(lambda p: read_fastq(p, per_file), paths))
 
 
 def write_records(fh, batch, keep_idx, lo, hi):
@@ -575,28 +618,77 @@ def write_compressed(path, data, gzipped=False, zstd_file=False, threads=None, n
 STREAM_CHUNK_BYTES = int(os.environ.get("ITSX_STREAM_CHUNK_BYTES", str(256 << 20)))
 
 
+def _gz_blocks_zlib(path, block, skip=0):
+    """Inflated blocks of a gzip file through zlib (multi-member aware, zero padding between / behind members skipped as
+    the gzip module does), the first ``skip`` bytes left out."""
+    import zlib
+    with open(path, "rb") as f:
+        d, fresh = zlib.decompressobj(31), True
+        while True:
+            raw = f.read(max(block // 4, 1 << 16))
+            if not raw:
+                if not fresh and not d.eof:
+                    raise EOFError("Compressed file ended before the end-of-stream marker was reached")
+                return
+            while raw:
+                if fresh:
+                    raw = raw.lstrip(b"\0")
+                    if not raw:
+                        break
+                    fresh = False
+                out = d.decompress(raw, block)          # at most `block` bytes per call: memory stays bounded
+                if out:
+                    if skip >= len(out):
+                        skip -= len(out)
+                    else:
+                        yield out[skip:]
+                        skip = 0
+                if d.eof:                               # next gzip member
+                    raw = d.unused_data
+                    d, fresh = zlib.decompressobj(31), True
+                else:
+                    raw = d.unconsumed_tail
+
+
+def _gz_blocks(path, block):
+    """Inflated blocks of about ``block`` bytes of a gzip file: the file is mapped (never read whole) and inflated by
+    the native reader on this process's share of the cores.  A stream the reader does not accept is handed to zlib from
+    where the reader stopped, which inflates it or raises what the reference would have raised."""
+    import mmap
+    size = os.path.getsize(path)
+    if size == 0:
+        return
+    done = 0
+    with open(path, "rb") as f:
+        mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        try:
+            a = np.frombuffer(mm, dtype=np.uint8)
+            r = GzReader(a, host_share())
+            try:
+                while True:
+                    out = np.empty(max(int(block), 1), np.uint8)
+                    k = r.readinto(out)
+                    if k < 0:
+                        break
+                    if k == 0:
+                        return
+                    done += k
+                    yield out[:k].tobytes() if k < out.size else out.tobytes()
+            finally:
+                r.close()
+                del a
+        finally:
+            try:
+                mm.close()
+            except BufferError:
+                pass
+    yield from _gz_blocks_zlib(path, block, skip=done)
+
+
 def _raw_blocks(path, block):
     """Decompressed bytes of ``path`` in blocks of about ``block`` bytes (plain, multi-member gzip, zstd)."""
     if path.endswith(".gz"):
-        import zlib
-        with open(path, "rb") as f:
-            d = zlib.decompressobj(31)
-            while True:
-                raw = f.read(max(block // 4, 1 << 16))
-                if not raw:
-                    tail = d.flush()
-                    if tail:
-                        yield tail
-                    return
-                while raw:
-                    out = d.decompress(raw, block)          # at most `block` bytes per call: memory stays bounded
-                    if out:
-                        yield out
-                    if d.eof:                               # next gzip member
-                        raw = d.unused_data
-                        d = zlib.decompressobj(31)
-                    else:
-                        raw = d.unconsumed_tail
+        yield from _gz_blocks(path, block)
     elif path.endswith(".zst"):
         from . import _zstd
         with open(path, "rb") as f:
