@@ -37,7 +37,9 @@ constexpr uint32_t LMASK = (1u << LIT_TB) - 1, DMASK = (1u << DIST_TB) - 1;
 constexpr int WSIZE = 32768;
 enum : uint32_t { T_LIT = 0, T_LEN = 1, T_EOB = 2, T_SUB = 3, T_BAD = 4 };
 enum { R_END = 0, R_FULL = 1, R_STOP = 2 };                   // results of run(); negative = ITSX_E*
-// entry: value << 16 | type << 12 | extra << 8 | bits.  T_LIT: extra = number of literals (1 or 2), value = lit0 | lit1 << 8
+// entry: value << 16 | type << 12 | extra << 8 | bits.  T_LIT: extra = number of literals (1 or 2), value = lit0 | lit1 << 8.
+// T_LEN (lengths and distances): value = base, bits = code length + extra bits, so that ONE shift consumes both and the
+// extra bits are cut out of a copy of the bit buffer off the critical path
 inline uint32_t mk(uint32_t value, uint32_t type, uint32_t extra, uint32_t bits) { return value << 16 | type << 12 | extra << 8 | bits; }
 #define E_TYPE(e) (((e) >> 12) & 15u)
 #define E_XTRA(e) (((e) >> 8) & 15u)
@@ -73,10 +75,10 @@ bool build_table(const uint8_t *lens, int n, int tb, int kind, uint32_t *tab, in
     uint16_t rev[320];
     auto entry = [&](int sym, int bits) -> uint32_t {
         if (kind == 2) return mk((uint32_t)sym, T_LIT, 1, (uint32_t)bits);
-        if (kind == 1) return sym < 30 ? mk(DIST_BASE[sym], T_LEN, DIST_EXTRA[sym], (uint32_t)bits) : mk(0, T_BAD, 0, (uint32_t)bits);
+        if (kind == 1) return sym < 30 ? mk(DIST_BASE[sym], T_LEN, DIST_EXTRA[sym], (uint32_t)bits + DIST_EXTRA[sym]) : mk(0, T_BAD, 0, (uint32_t)bits);
         if (sym < 256) return mk((uint32_t)sym, T_LIT, 1, (uint32_t)bits);
         if (sym == 256) return mk(0, T_EOB, 0, (uint32_t)bits);
-        return sym < 286 ? mk(LEN_BASE[sym - 257], T_LEN, LEN_EXTRA[sym - 257], (uint32_t)bits) : mk(0, T_BAD, 0, (uint32_t)bits);
+        return sym < 286 ? mk(LEN_BASE[sym - 257], T_LEN, LEN_EXTRA[sym - 257], (uint32_t)bits + LEN_EXTRA[sym - 257]) : mk(0, T_BAD, 0, (uint32_t)bits);
     };
     bool any_long = false;
     for (int s = 0; s < n; s++) {
@@ -286,57 +288,60 @@ static inline __attribute__((always_inline)) int run_impl(Dec &s, T *&outp, T *h
                     int stop = 0;                        // 1: end of block, 2: bad stream
 #define REFILL() do { uint64_t w_; memcpy(&w_, in, 8); bb |= w_ << bc; in += (63 - bc) >> 3; bc |= 56; } while (0)
 #define EAT(e_) do { bb >>= E_BITS(e_); bc -= (int)E_BITS(e_); } while (0)
-                    while (in <= in_fast && out <= out_fast) {
+#define VAL(e_, saved_) (((e_) >> 16) + (uint32_t)(((saved_) >> (E_BITS(e_) - E_XTRA(e_))) & ((1u << E_XTRA(e_)) - 1)))
+                    if (in <= in_fast && out <= out_fast) {
                         REFILL();
-                        uint32_t e = lit[bb & LMASK];
-                        if (E_TYPE(e) == T_LIT) {
-                            // up to three look-ups (six literals) on one refill: 3 x 11 bits at most
-                            put2<T>(out, e >> 16); out += E_XTRA(e); EAT(e);
-                            e = lit[bb & LMASK];
+                        uint32_t e = lit[bb & LMASK];        // always the entry of the bits in front: looked up ahead of its use
+                        for (;;) {
                             if (E_TYPE(e) == T_LIT) {
+                                // up to three look-ups (six literals) on one refill: 3 x 11 bits at most
                                 put2<T>(out, e >> 16); out += E_XTRA(e); EAT(e);
                                 e = lit[bb & LMASK];
                                 if (E_TYPE(e) == T_LIT) {
                                     put2<T>(out, e >> 16); out += E_XTRA(e); EAT(e);
-                                    continue;
+                                    e = lit[bb & LMASK];
+                                    if (E_TYPE(e) == T_LIT) {
+                                        put2<T>(out, e >> 16); out += E_XTRA(e); EAT(e);
+                                        e = lit[bb & LMASK];
+                                    }
+                                }
+                            } else {
+                                if (__builtin_expect(E_TYPE(e) == T_SUB, 0)) {
+                                    bb >>= LIT_TB; bc -= LIT_TB;
+                                    e = lit[(e >> 16) + (bb & ((1u << E_XTRA(e)) - 1))];
+                                    if (E_TYPE(e) == T_LIT) { *out++ = (T)(e >> 16); EAT(e); e = lit[bb & LMASK]; goto next; }
+                                }
+                                if (__builtin_expect(E_TYPE(e) != T_LEN, 0)) { EAT(e); stop = E_TYPE(e) == T_EOB ? 1 : 2; break; }
+                                const uint32_t len = VAL(e, bb);
+                                EAT(e);
+                                uint32_t d = dist[bb & DMASK];
+                                if (__builtin_expect(E_TYPE(d) == T_SUB, 0)) {
+                                    bb >>= DIST_TB; bc -= DIST_TB;
+                                    d = dist[(d >> 16) + (bb & ((1u << E_XTRA(d)) - 1))];
+                                }
+                                if (__builtin_expect(E_TYPE(d) != T_LEN, 0)) { stop = 2; break; }
+                                const uint32_t distv = VAL(d, bb);
+                                EAT(d);
+                                e = lit[bb & LMASK];             // the next symbol's entry loads while the match is copied
+                                if (__builtin_expect((size_t)distv > (size_t)(out - hist_beg), 0)) { stop = 2; break; }
+                                T *o = out;
+                                const T *m = o - distv;
+                                out += len;
+                                if (distv >= W) {
+                                    uint64_t v;
+                                    memcpy(&v, m, 8); memcpy(o, &v, 8);
+                                    memcpy(&v, m + W, 8); memcpy(o + W, &v, 8);
+                                    for (uint32_t k = 2 * W; k < len; k += W) { memcpy(&v, m + k, 8); memcpy(o + k, &v, 8); }
+                                } else if (distv == 1) {
+                                    const T c = *m;
+                                    for (uint32_t k = 0; k < len; k++) o[k] = c;
+                                } else {
+                                    for (uint32_t k = 0; k < len; k++) o[k] = m[k];
                                 }
                             }
-                            REFILL();                    // e stays the entry of the low bits
-                        }
-                        if (__builtin_expect(E_TYPE(e) == T_SUB, 0)) {
-                            bb >>= LIT_TB; bc -= LIT_TB;
-                            e = lit[(e >> 16) + (bb & ((1u << E_XTRA(e)) - 1))];
-                            if (E_TYPE(e) == T_LIT) { *out++ = (T)(e >> 16); EAT(e); continue; }
-                        }
-                        EAT(e);
-                        if (__builtin_expect(E_TYPE(e) != T_LEN, 0)) { stop = E_TYPE(e) == T_EOB ? 1 : 2; break; }
-                        const uint32_t xl = E_XTRA(e);
-                        const uint32_t len = (e >> 16) + (uint32_t)(bb & ((1u << xl) - 1));
-                        bb >>= xl; bc -= (int)xl;
-                        uint32_t d = dist[bb & DMASK];
-                        if (__builtin_expect(E_TYPE(d) == T_SUB, 0)) {
-                            bb >>= DIST_TB; bc -= DIST_TB;
-                            d = dist[(d >> 16) + (bb & ((1u << E_XTRA(d)) - 1))];
-                        }
-                        if (__builtin_expect(E_TYPE(d) != T_LEN, 0)) { stop = 2; break; }
-                        EAT(d);
-                        const uint32_t xd = E_XTRA(d);
-                        const uint32_t distv = (d >> 16) + (uint32_t)(bb & ((1u << xd) - 1));
-                        bb >>= xd; bc -= (int)xd;
-                        if (__builtin_expect((size_t)distv > (size_t)(out - hist_beg), 0)) { stop = 2; break; }
-                        T *o = out;
-                        const T *m = o - distv;
-                        out += len;
-                        if (distv >= W) {
-                            uint64_t v;
-                            memcpy(&v, m, 8); memcpy(o, &v, 8);
-                            memcpy(&v, m + W, 8); memcpy(o + W, &v, 8);
-                            for (uint32_t k = 2 * W; k < len; k += W) { memcpy(&v, m + k, 8); memcpy(o + k, &v, 8); }
-                        } else if (distv == 1) {
-                            const T c = *m;
-                            for (uint32_t k = 0; k < len; k++) o[k] = c;
-                        } else {
-                            for (uint32_t k = 0; k < len; k++) o[k] = m[k];
+                        next:
+                            if (!(in <= in_fast && out <= out_fast)) break;      // (e has not been consumed)
+                            REFILL();
                         }
                     }
 #undef REFILL
@@ -352,6 +357,7 @@ static inline __attribute__((always_inline)) int run_impl(Dec &s, T *&outp, T *h
                 int used = 0;
                 uint32_t e = s.litp[bb & LMASK];
                 if (E_TYPE(e) == T_SUB) { bb >>= LIT_TB; used += LIT_TB; e = s.litp[(e >> 16) + (bb & ((1u << E_XTRA(e)) - 1))]; }
+                const uint64_t at_e = bb;                // (length extra bits are cut out of this)
                 bb >>= E_BITS(e); used += (int)E_BITS(e);
                 const uint32_t ty = E_TYPE(e);
                 if (ty == T_LIT) {
@@ -364,22 +370,19 @@ static inline __attribute__((always_inline)) int run_impl(Dec &s, T *&outp, T *h
                 }
                 if (ty == T_EOB) { s.bb = bb; s.bc -= used; break; }
                 if (ty != T_LEN) { outp = out; return ITSX_EFORMAT; }
-                const uint32_t xl = E_XTRA(e);
-                const uint32_t len = (e >> 16) + (uint32_t)(bb & ((1u << xl) - 1));
-                bb >>= xl; used += (int)xl;
+                const uint32_t len = VAL(e, at_e);
                 uint32_t d = s.distp[bb & DMASK];
                 if (E_TYPE(d) == T_SUB) { bb >>= DIST_TB; used += DIST_TB; d = s.distp[(d >> 16) + (bb & ((1u << E_XTRA(d)) - 1))]; }
                 if (E_TYPE(d) != T_LEN) { outp = out; return ITSX_EFORMAT; }
+                const uint32_t distv = VAL(d, bb);
                 bb >>= E_BITS(d); used += (int)E_BITS(d);
-                const uint32_t xd = E_XTRA(d);
-                const uint32_t distv = (d >> 16) + (uint32_t)(bb & ((1u << xd) - 1));
-                bb >>= xd; used += (int)xd;
                 if ((size_t)distv > (size_t)(out - hist_beg)) { outp = out; return ITSX_EFORMAT; }
                 if ((size_t)(out_end - out) < len) { outp = out; return R_FULL; }
                 for (uint32_t k = 0; k < len; k++) { *out = *(out - distv); out++; }
                 s.bb = bb; s.bc -= used;
             }
         }
+#undef VAL
         // end of a block
         s.phase = 0;
         if (s.overrun) { outp = out; return ITSX_EFORMAT; }
@@ -772,7 +775,17 @@ void translate_segment(Segment &g, uint8_t *dst)
     const uint16_t *sym = g.sym.data() + WSIZE;
     const uint8_t *win = g.window;
     const int64_t n = g.nout;
-    for (int64_t i = 0; i < n; i++) {
+    int64_t i = 0;
+    for (; i + 64 <= n; i += 64) {                  // markers are rare: 64 symbols without one are narrowed in one sweep
+        uint16_t any = 0;
+        for (int k = 0; k < 64; k++) any |= sym[i + k];
+        if (!(any & 0x8000)) {
+            for (int k = 0; k < 64; k++) dst[i + k] = (uint8_t)sym[i + k];
+        } else {
+            for (int k = 0; k < 64; k++) { const uint16_t v = sym[i + k]; dst[i + k] = v < 0x8000 ? (uint8_t)v : win[v - 0x8000]; }
+        }
+    }
+    for (; i < n; i++) {
         const uint16_t v = sym[i];
         dst[i] = v < 0x8000 ? (uint8_t)v : win[v - 0x8000];
     }

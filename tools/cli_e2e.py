@@ -46,6 +46,21 @@ def write_fastq(path, seq, off, qual, mate=1):
         f.write(out.tobytes())
 
 
+def gzip_one_member(data, level=1, piece=8 << 20):
+    """``data`` as ONE gzip member (what a sequencer writes: a single deflate stream), compressed on every core the way pigz
+    does it: independent raw-deflate pieces ending in a sync flush, concatenated, closed by an empty final block."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    def part(i):
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        return co.compress(data[i:i + piece]) + co.flush(zlib.Z_SYNC_FLUSH)
+    with ThreadPoolExecutor(os.cpu_count() or 1) as ex:
+        body = b"".join(ex.map(part, range(0, len(data), piece)))
+    return (bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3]) + body + b"\x03\x00" +
+            zlib.crc32(data).to_bytes(4, "little") + (len(data) & 0xffffffff).to_bytes(4, "little"))
+
+
 def paired(a):
     n = int(781_250 * a.scale)
     frag, foff, _, _ = synth.make_reads(5 * 1_000_003, n, max(300, n // 20), (330, 441), "M.hmm", "3_", "4_", zipf_s=1.2,
