@@ -1,7 +1,17 @@
 """Minimal zstd codec over the system libzstd (ctypes), standing in for the reference's `pyzstd`
 dependency (itsxpress/SeqSample.py:8, used at :727-729, :770-773, :916-921, :933-940).  Whole-buffer
-compress / decompress only -- that is all the FASTQ reader/writer needs."""
+compress / decompress only -- that is all the FASTQ reader/writer needs.  Large buffers are written as several
+independent frames compressed on all of this process's cores (a valid zstd stream: frames concatenate), and files made
+of several frames with known sizes are decoded frame-parallel; libzstd releases the GIL under ctypes."""
 import ctypes as C
+import os
+
+FRAME_BYTES = 8 << 20          # text per frame of a multi-frame output
+
+
+def _cores():
+    cores = os.cpu_count() or 2
+    return max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))))
 
 _L = None
 
@@ -28,6 +38,12 @@ def _lib():
         L.ZSTD_decompressStream.restype = C.c_size_t
         L.ZSTD_decompressStream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ZSTD_DStreamOutSize.restype = C.c_size_t
+        L.ZSTD_decompress.restype = C.c_size_t
+        L.ZSTD_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.ZSTD_findFrameCompressedSize.restype = C.c_size_t
+        L.ZSTD_findFrameCompressedSize.argtypes = [C.c_void_p, C.c_size_t]
+        L.ZSTD_getFrameContentSize.restype = C.c_ulonglong
+        L.ZSTD_getFrameContentSize.argtypes = [C.c_void_p, C.c_size_t]
         _L = L
     return _L
 
@@ -36,9 +52,8 @@ class _Buf(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("size", C.c_size_t), ("pos", C.c_size_t)]
 
 
-def compress(data, level=3):
+def _compress_frame(data, level):
     L = _lib()
-    data = bytes(data)
     cap = L.ZSTD_compressBound(len(data))
     out = C.create_string_buffer(cap)
     n = L.ZSTD_compress(out, cap, data, len(data), level)
@@ -47,10 +62,69 @@ def compress(data, level=3):
     return out.raw[:n]
 
 
-def decompress(data):
-    """Streaming decode (handles multi-frame files and frames without a content size)."""
+def compress(data, level=3, threads=None):
+    """``data`` as a zstd stream: one frame, or (above FRAME_BYTES, with more than one core) independent frames of
+    FRAME_BYTES compressed concurrently."""
+    data = bytes(data)
+    threads = _cores() if threads is None else threads
+    if len(data) <= FRAME_BYTES or threads <= 1:
+        return _compress_frame(data, level)
+    from concurrent.futures import ThreadPoolExecutor
+    view = memoryview(data)
+    with ThreadPoolExecutor(threads) as ex:
+        return b"".join(ex.map(lambda i: _compress_frame(bytes(view[i:i + FRAME_BYTES]), level), range(0, len(data), FRAME_BYTES)))
+
+
+def _frames(L, base, n):
+    """[(offset, compressed size, content size)] of a stream whose frames all state their content size, else None."""
+    out, at = [], 0
+    while at < n:
+        cs = L.ZSTD_findFrameCompressedSize(C.c_void_p(base + at), n - at)
+        if L.ZSTD_isError(cs) or cs == 0:
+            return None
+        us = L.ZSTD_getFrameContentSize(C.c_void_p(base + at), n - at)
+        if us >= (1 << 62):                 # ZSTD_CONTENTSIZE_UNKNOWN / _ERROR (also what a skippable frame reports as 0 is fine)
+            return None
+        out.append((at, int(cs), int(us)))
+        at += int(cs)
+    return out
+
+
+def decompress(data, threads=None):
+    """Whole-buffer decode.  A stream of several frames that state their sizes (what ``compress`` writes, pzstd, zstd -T
+    with --rsyncable ...) is decoded frame-parallel; everything else through the streaming decoder (multi-frame files and
+    frames without a content size included)."""
     L = _lib()
     data = bytes(data)
+    threads = _cores() if threads is None else threads
+    if threads > 1 and len(data) > (1 << 20):
+        src = C.create_string_buffer(data, len(data))
+        base = C.addressof(src)
+        fr = _frames(L, base, len(data))
+        if fr is not None and len(fr) > 1:
+            total = sum(f[2] for f in fr)
+            dst = C.create_string_buffer(max(total, 1))
+            dbase = C.addressof(dst)
+            offs, o = [], 0
+            for f in fr:
+                offs.append(o)
+                o += f[2]
+
+            def one(i):
+                at, cs, us = fr[i]
+                return L.ZSTD_decompress(C.c_void_p(dbase + offs[i]), us, C.c_void_p(base + at), cs), us
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(threads) as ex:
+                res = list(ex.map(one, range(len(fr))))
+            if all((not L.ZSTD_isError(r)) and r == us for r, us in res):
+                return dst.raw[:total]
+            # anything odd: the streaming decoder below reports it the usual way
+    return _decompress_streaming(data)
+
+
+def _decompress_streaming(data):
+    """Streaming decode (handles multi-frame files and frames without a content size)."""
+    L = _lib()
     ds = L.ZSTD_createDStream()
     L.ZSTD_initDStream(ds)
     try:

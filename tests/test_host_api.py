@@ -2,6 +2,7 @@
 C-ABI's shape.  They mirror the reference's own unit tests (tests/test_main_pytest.py, cited per test);
 nothing here launches a kernel."""
 import ctypes
+import ctypes as C
 import gzip
 import os
 import re
@@ -106,6 +107,20 @@ def test_zstd_decoder_flushes_held_back_blocks_and_rejects_truncation():
     assert _zstd.decompress(blob) == a + b
     with pytest.raises(ValueError):
         _zstd.decompress(blob[:-7])
+    # large buffers: several frames compressed concurrently, decoded frame-parallel or by the streaming decoder alike
+    big = bytes(rng.integers(65, 75, 3_000_000, dtype=np.uint8))
+    old_frame = _zstd.FRAME_BYTES
+    _zstd.FRAME_BYTES = 700_000
+    try:
+        blob = _zstd.compress(big, threads=4)
+    finally:
+        _zstd.FRAME_BYTES = old_frame
+    src = C.create_string_buffer(blob, len(blob))
+    assert len(_zstd._frames(_zstd._lib(), C.addressof(src), len(blob))) == 5
+    assert _zstd.decompress(blob, threads=4) == big and _zstd.decompress(blob, threads=1) == big
+    assert _zstd._decompress_streaming(blob) == big and _zstd.compress(big, threads=1) != blob
+    with pytest.raises(ValueError):
+        _zstd.decompress(blob[:len(blob) // 2], threads=4)
 
 
 def test_stream_fastq_chunks_equal_whole_file(tmp_path):
