@@ -179,12 +179,30 @@ def _check_fastqs(fastq, fastq2=None):
     for path in (fastq, fastq2):
         if not path:
             continue
-        with read_file(path) as handle:
-            head = []
-            for i, line in enumerate(handle):
-                head.append(line)
-                if i >= 7:
-                    break
+        if path.endswith(".zst"):
+            # only the first frame's first block is decoded (read_file would inflate the whole file for eight lines)
+            from . import _zstd
+            try:
+                text = b""
+                with open(path, "rb") as f:
+                    for part in _zstd.decompress_stream(f, 1 << 16):
+                        text += part
+                        if text.count(b"\n") >= 8:
+                            break
+            except FileNotFoundError as f:
+                logging.error("The input file {} could not be found.".format(path))
+                raise f
+            except Exception as g:
+                logging.error("There appears to be an issue reading the input file {}.".format(path))
+                raise g
+            head = text.decode().splitlines(keepends=True)[:8]
+        else:
+            with read_file(path) as handle:
+                head = []
+                for i, line in enumerate(handle):
+                    head.append(line)
+                    if i >= 7:
+                        break
         if not head:
             continue
         if not head[0].startswith("@"):

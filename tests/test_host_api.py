@@ -86,6 +86,20 @@ def test_check_fastqs_empty(tmp_path):
     cli._check_fastqs(str(p))
 
 
+def test_check_fastqs_reads_only_the_head_of_compressed_files(tmp_path):
+    from itsxpress_b200 import _zstd
+    raw = gzip.open(SEQ, "rb").read()
+    good, broken = str(tmp_path / "a.fastq.zst"), str(tmp_path / "b.fastq.zst")
+    open(good, "wb").write(_zstd.compress(raw))
+    open(broken, "wb").write(_zstd.compress(open(os.path.join(TD, "broken.fastq"), "rb").read()))
+    cli._check_fastqs(good)
+    cli._check_fastqs(SEQ)
+    with pytest.raises(ValueError):
+        cli._check_fastqs(broken)
+    with pytest.raises(Exception):
+        cli._check_fastqs(str(tmp_path / "missing.fastq.zst"))
+
+
 def test_zstd_and_gzip_writers(tmp_path):
     raw = gzip.open(SEQ, "rb").read()
     fq.write_compressed(str(tmp_path / "a.gz"), raw, gzipped=True)
