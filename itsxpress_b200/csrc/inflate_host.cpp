@@ -21,11 +21,15 @@
 // the gzip module, which raises what the reference would have raised.
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include "deflate_core.h"
 #include "itsx_internal.h"
 
@@ -440,11 +444,93 @@ uint32_t crc_update(uint32_t c, const uint8_t *p, size_t n)      // raw register
     while (n--) c = g_crc[0][(c ^ *p++) & 0xffu] ^ (c >> 8);
     return c;
 }
+#if defined(__x86_64__)
+// The same register advance by carry-less multiplication (Gopal et al., "Fast CRC computation for generic polynomials
+// using PCLMULQDQ"): four 128-bit lanes folded by x^512, then by x^128, then 128 -> 64 -> 32 bits with a Barrett
+// reduction; constants for the reflected polynomial 0xEDB88320.  n >= 64 and a multiple of 16.
+__attribute__((target("pclmul,sse4.1"))) uint32_t crc_update_clmul(uint32_t c, const uint8_t *p, size_t n)
+{
+    const __m128i k1k2 = _mm_set_epi64x(0x01c6e41596ll, 0x0154442bd4ll);
+    const __m128i k3k4 = _mm_set_epi64x(0x00ccaa009ell, 0x01751997d0ll);
+    const __m128i k5k0 = _mm_set_epi64x(0x0000000000ll, 0x0163cd6124ll);
+    const __m128i poly = _mm_set_epi64x(0x01f7011641ll, 0x01db710641ll);
+    __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
+    x1 = _mm_loadu_si128((const __m128i *)(p + 0x00));
+    x2 = _mm_loadu_si128((const __m128i *)(p + 0x10));
+    x3 = _mm_loadu_si128((const __m128i *)(p + 0x20));
+    x4 = _mm_loadu_si128((const __m128i *)(p + 0x30));
+    x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)c));
+    x0 = k1k2;
+    p += 64; n -= 64;
+    while (n >= 64) {
+        x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+        x7 = _mm_clmulepi64_si128(x3, x0, 0x00); x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+        x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+        x3 = _mm_clmulepi64_si128(x3, x0, 0x11); x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+        y5 = _mm_loadu_si128((const __m128i *)(p + 0x00)); y6 = _mm_loadu_si128((const __m128i *)(p + 0x10));
+        y7 = _mm_loadu_si128((const __m128i *)(p + 0x20)); y8 = _mm_loadu_si128((const __m128i *)(p + 0x30));
+        x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5); x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
+        x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7); x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
+        p += 64; n -= 64;
+    }
+    x0 = k3k4;
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+    while (n >= 16) {
+        x2 = _mm_loadu_si128((const __m128i *)p);
+        x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+        p += 16; n -= 16;
+    }
+    x2 = _mm_clmulepi64_si128(x1, x0, 0x10);
+    x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+    x1 = _mm_srli_si128(x1, 8);
+    x1 = _mm_xor_si128(x1, x2);
+    x0 = k5k0;
+    x2 = _mm_srli_si128(x1, 4);
+    x1 = _mm_and_si128(x1, x3);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    x0 = poly;
+    x2 = _mm_and_si128(x1, x3);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+    x2 = _mm_and_si128(x2, x3);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+bool have_clmul()
+{
+    // known answer first: the fast path is used only if it reproduces the table-driven register on this CPU
+    static const bool ok = [] {
+        if (!__builtin_cpu_supports("pclmul") || !__builtin_cpu_supports("sse4.1") || getenv("ITSX_NO_CLMUL")) return false;
+        crc_init();
+        uint8_t buf[256 + 48];
+        for (int i = 0; i < (int)sizeof buf; i++) buf[i] = (uint8_t)(i * 131 + 7);
+        for (size_t n : {(size_t)64, (size_t)80, (size_t)128, (size_t)304})
+            if (crc_update_clmul(0x12345678u, buf, n) != crc_update(0x12345678u, buf, n)) return false;
+        return true;
+    }();
+    return ok;
+}
+#else
+bool have_clmul() { return false; }
+uint32_t crc_update_clmul(uint32_t c, const uint8_t *, size_t) { return c; }
+#endif
+uint32_t crc_update_fast(uint32_t c, const uint8_t *p, size_t n)
+{
+    if (n >= 256 && have_clmul()) {
+        const size_t body = n & ~(size_t)15;
+        c = crc_update_clmul(c, p, body);
+        p += body; n -= body;
+    }
+    return crc_update(c, p, n);
+}
 // zlib's crc32(crc, buf, len): the finalised CRC of A || buf from the finalised CRC of A
-uint32_t crc32_z(uint32_t crc, const uint8_t *p, size_t n)
+uint32_t crc32_cont(uint32_t crc, const uint8_t *p, size_t n)
 {
     crc_init();
-    return crc_update(crc ^ 0xffffffffu, p, n) ^ 0xffffffffu;
+    return crc_update_fast(crc ^ 0xffffffffu, p, n) ^ 0xffffffffu;
 }
 // finalised CRC of A || B from those of A and B and B's length (any length): x^(8 len) by square and multiply
 uint32_t crc32_join(uint32_t crc_a, uint32_t crc_b, uint64_t len_b)
@@ -725,12 +811,12 @@ int64_t step_sequential(itsx_gz *h, uint8_t *dst, int64_t room)
     if (hist_in_place && room >= DIRECT_MIN_ROOM) {
         uint8_t *out = dst;
         CrcFollower fol;
-        const bool follow = room >= (8 << 20) && h->end - d.in > (2 << 20);
+        const bool follow = room >= (8 << 20) && h->end - d.in > (2 << 20) && !have_clmul();      // (13 GB/s inline needs no helper)
         if (follow) { d.progress = &fol.produced; d.prog_base = dst; fol.start(dst, h->mcrc); }
         rc = run(d, out, dst - need_hist, dst + room, INT64_MAX);
         d.progress = nullptr;
         const size_t n = (size_t)(out - dst);
-        h->mcrc = follow ? fol.finish((int64_t)n) : crc32_z(h->mcrc, dst, n);
+        h->mcrc = follow ? fol.finish((int64_t)n) : crc32_cont(h->mcrc, dst, n);
         h->mlen += n;
         push_window(h, dst, n);
         h->contig += n;
@@ -746,7 +832,7 @@ int64_t step_sequential(itsx_gz *h, uint8_t *dst, int64_t room)
         uint8_t *out = out0;
         rc = run(d, out, out0 - need_hist, out0 + IBUF_SPACE, INT64_MAX);
         const size_t n = (size_t)(out - out0);
-        h->mcrc = crc32_z(h->mcrc, out0, n);
+        h->mcrc = crc32_cont(h->mcrc, out0, n);
         h->mlen += n;
         push_window(h, out0, n);
         const size_t take = (size_t)std::min<int64_t>((int64_t)n, room);
@@ -791,8 +877,8 @@ void translate_segment(Segment &g, uint8_t *dst)
     }
     g.piece_crc.clear();
     int64_t at = 0;
-    for (const MemberEnd &me : g.ends) { g.piece_crc.push_back(crc32_z(0, dst + at, (size_t)(me.out_pos - at))); at = me.out_pos; }
-    g.piece_crc.push_back(crc32_z(0, dst + at, (size_t)(n - at)));
+    for (const MemberEnd &me : g.ends) { g.piece_crc.push_back(crc32_cont(0, dst + at, (size_t)(me.out_pos - at))); at = me.out_pos; }
+    g.piece_crc.push_back(crc32_cont(0, dst + at, (size_t)(n - at)));
 }
 
 // One batch of parallel decoding.  Returns bytes written to dst (the surplus goes to `pending`), < 0 on an error (the

@@ -202,3 +202,22 @@ def test_readers_use_the_native_gunzip(tmp_path):
         f.write(comp)
     with pytest.raises((zlib.error, EOFError)):
         b"".join(fq._raw_blocks(bad, 50000))
+
+
+def test_crc_paths_agree_without_carry_less_multiplication():
+    """CRC-32 runs by PCLMULQDQ folding where the CPU has it (checked against the table-driven register at start-up); without
+    it, slice-by-8 on a thread that follows the decoder.  ITSX_NO_CLMUL forces the second path (fresh process)."""
+    import subprocess
+    import sys
+    code = ("import sys, gzip, numpy as np; sys.path.insert(0, %r); from itsxpress_b200 import fastq as fq; "
+            "rng = np.random.default_rng(3); "
+            "data = bytes(rng.integers(33, 75, 12_000_000, dtype=np.uint8)); comp = gzip.compress(data, 1); "
+            "assert len(comp) > (3 << 20); "
+            "assert fq.gunzip(comp, 1).tobytes() == data and fq.gunzip(comp, 4).tobytes() == data; "
+            "bad = bytearray(comp); bad[-6] ^= 1; "
+            "import pytest; "
+            "pytest.raises(gzip.BadGzipFile, fq.gunzip, bytes(bad), 1); pytest.raises(gzip.BadGzipFile, fq.gunzip, bytes(bad), 4); "
+            "print('ok')" % ROOT)
+    for env in ({}, {"ITSX_NO_CLMUL": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]
