@@ -368,6 +368,10 @@ const char *itsx_host_last_error(void);
 /* cap == 0: count records only.  Returns the record count or ITSX_EFORMAT / ITSX_EINVAL. */
 int64_t itsx_fastq_index(const uint8_t *buf, int64_t nbytes, int64_t cap, int64_t *t_off, int32_t *t_len,
                          int64_t *s_off, int32_t *s_len, int64_t *q_off);
+/* Where a chunked reader may cut a piece of a 4-line FASTQ file that starts at a record boundary: the offset behind the
+ * last line whose number is a multiple of four (0: fewer than four lines).  Lines are counted, not recognised -- a quality
+ * line may begin with '@' (SeqSample.py:742-752 streams through Biopython, which counts too). */
+int64_t itsx_fastq_cut(const uint8_t *buf, int64_t nbytes);
 /* out_off[n+1] = prefix sums of len; out (may be NULL) = segments packed back to back.  Returns total bytes. */
 int64_t itsx_bytes_gather(const uint8_t *buf, const int64_t *off, const int32_t *len, int64_t n, uint8_t *out,
                           int64_t *out_off);

@@ -158,6 +158,30 @@ int64_t itsx_fastq_index(const uint8_t *buf, int64_t nbytes, int64_t cap, int64_
     return n;
 }
 
+// Offset behind the last line of buf whose number is a multiple of four (0: fewer than four lines): newlines are counted on
+// all threads, then the 0-3 lines of the unfinished record are stepped over from the end.
+int64_t itsx_fastq_cut(const uint8_t *buf, int64_t nbytes)
+{
+    if (nbytes <= 0 || !buf) return 0;
+    const int nt = nthreads_for(nbytes, 8 << 20);
+    std::vector<int64_t> part((size_t)nt + 1, 0);
+    parallel_for(nbytes, 8 << 20, [&](int64_t a, int64_t b, int t) {
+        int64_t c = 0;
+        for (int64_t i = a; i < b; i++) c += buf[i] == '\n';
+        part[(size_t)t] = c;
+    });
+    int64_t lines = 0;
+    for (int64_t c : part) lines += c;
+    if (lines < 4) return 0;
+    int64_t p = nbytes;                                   // behind the newline that ends line number `lines`
+    while (p > 0 && buf[p - 1] != '\n') p--;
+    for (int64_t k = lines % 4; k > 0; k--) {
+        p--;                                              // onto that newline, then back to the one before it
+        while (p > 0 && buf[p - 1] != '\n') p--;
+    }
+    return p;
+}
+
 // out_off[n+1] = prefix sums of len; out (if non-NULL) receives the segments packed back to back.
 // Returns the total number of bytes.
 int64_t itsx_bytes_gather(const uint8_t *buf, const int64_t *off, const int32_t *len, int64_t n, uint8_t *out,

@@ -711,7 +711,7 @@ def stream_fastq(path, chunk_bytes=None):
     from concurrent.futures import ThreadPoolExecutor
     chunk_bytes = chunk_bytes or STREAM_CHUNK_BYTES
     blocks = _raw_blocks(path, chunk_bytes)
-    carry = b""
+    parts, have = [], 0                    # text not yet handed out: the carry of the last cut + the blocks since
     pool = ThreadPoolExecutor(1, thread_name_prefix="itsx-stream")
     try:
         nxt = pool.submit(next, blocks, None)
@@ -719,23 +719,23 @@ def stream_fastq(path, chunk_bytes=None):
             raw = nxt.result()
             if raw is not None:
                 nxt = pool.submit(next, blocks, None)
-            data = carry + raw if raw is not None else carry
+                parts.append(raw)
+                have += len(raw)
+                if have < chunk_bytes:
+                    continue
+            data = parts[0] if len(parts) == 1 else b"".join(parts)
             if raw is None:
                 if data.strip():
                     yield parse_bytes(data)
                 return
-            if len(data) < chunk_bytes:
-                carry = data
-                continue
+            # cut behind the last line whose number is a multiple of four (lines counted on the host threads)
             buf = np.frombuffer(data, np.uint8)
-            nl = np.flatnonzero(buf == 10)
-            whole = (len(nl) // 4) * 4
-            if whole == 0:
-                carry = data
+            cut = int(_native().itsx_fastq_cut(_vp(buf), buf.size))
+            if cut == 0:
+                parts, have = [data], len(data)
                 continue
-            cut = int(nl[whole - 1]) + 1
-            carry = data[cut:]
-            yield parse_bytes(data[:cut])
+            parts, have = [data[cut:]], len(data) - cut
+            yield parse_bytes(memoryview(data)[:cut])
     finally:
         pool.shutdown(wait=False, cancel_futures=True)
 

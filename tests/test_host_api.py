@@ -137,6 +137,28 @@ def test_zstd_decoder_flushes_held_back_blocks_and_rejects_truncation():
         _zstd.decompress(blob[:len(blob) // 2], threads=4)
 
 
+def test_fastq_cut_is_behind_the_last_line_whose_number_is_a_multiple_of_four():
+    rng = np.random.default_rng(9)
+    L = fq._native()
+
+    def cut(b):
+        a = np.frombuffer(b, np.uint8)
+        return int(L.itsx_fastq_cut(fq._vp(a), a.size)) if a.size else 0
+
+    def want(b):
+        nl = [i for i, c in enumerate(b) if c == 10]
+        return nl[len(nl) // 4 * 4 - 1] + 1 if len(nl) >= 4 else 0
+    assert cut(b"") == 0 and cut(b"@a\nAC\n+\n") == 0 and cut(b"@a\nAC\n+\nII\n") == 11 and cut(b"@a\nAC\n+\nII\n@b") == 11
+    for _ in range(200):
+        n = int(rng.integers(1, 3000))
+        b = bytes(rng.choice(np.frombuffer(b"ACGT@+I\n\n", np.uint8), n))      # newline-rich, '@' anywhere
+        assert cut(b) == want(b), b
+    big = bytes(rng.choice(np.frombuffer(b"ACGTIIIIIIIIIIIIIIIIIIIIIII\n", np.uint8), 40_000_000))    # several threads
+    a = np.frombuffer(big, np.uint8)
+    nl = np.flatnonzero(a == 10)
+    assert cut(big) == int(nl[len(nl) // 4 * 4 - 1]) + 1
+
+
 def test_stream_fastq_chunks_equal_whole_file(tmp_path):
     """the chunked reader cuts at record boundaries found by counting lines (a quality line may start with
     '@' or '+'), over plain / multi-member gzip / multi-frame zstd input and for chunk sizes from a few records to the whole
