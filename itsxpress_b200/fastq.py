@@ -189,8 +189,23 @@ def _open_buffer(path, threads=None):
     """Decompressed content of ``path`` as a bytes-like object (a uint8 array for .gz: no copy behind the inflater).
     ``threads``: host cores the inflate of a .gz may use (None: this process's share)."""
     if path.endswith(".gz"):
+        import mmap
         with open(path, "rb") as f:
-            return gunzip(f.read(), threads)
+            if os.fstat(f.fileno()).st_size < (1 << 20):
+                return gunzip(f.read(), threads)
+            # mapped, not read: the inflating threads pull the pages in themselves (the map lives only for this call)
+            mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+            try:
+                a = np.frombuffer(mm, dtype=np.uint8)
+                try:
+                    return gunzip(a, threads)
+                finally:
+                    del a
+            finally:
+                try:
+                    mm.close()
+                except BufferError:          # (a reference to the view survived somewhere: the GC unmaps it later)
+                    pass
     if path.endswith(".zst"):
         from . import _zstd
         with open(path, "rb") as f:
