@@ -9,7 +9,8 @@
 //    carry TWO literals when both codes fit into the look-up (FASTQ is literal-dominated), matches copied in 8-byte
 //    words, BMI2 shifts when the CPU has them;
 //  * one deflate stream inflated on several cores (two passes, as pugz / rapidgzip do): the input is cut into chunks, every
-//    chunk but the first looks for the next deflate block header at bit granularity (strict header validation), decodes
+//    chunk but the first looks for the next deflate block header at bit granularity (strict header validation) or the
+//    next gzip member header, decodes
 //    from there into 16-bit symbols in which a back-reference that reaches in front of the chunk becomes a MARKER
 //    (0x8000 + position in the unknown 32 KB window), and stops at the block boundary where the next chunk started.  The
 //    chunks are then stitched in order (the end bit of one must be the start bit of the next; anything else is decoded
@@ -604,53 +605,78 @@ inline uint64_t peek_at(const uint8_t *beg, const uint8_t *end, int64_t bit)    
     else if (p < end) memcpy(&w, p, (size_t)(end - p));
     return w >> (bit & 7);
 }
-int64_t find_block(const uint8_t *beg, const uint8_t *end, int64_t from_bit, int64_t to_bit)
+// a dynamic block header (BTYPE = 2, either BFINAL) at bit p that a decoder would accept: HLIT / HDIST in range, a
+// COMPLETE code-length code, valid run-lengths, end-of-block present, complete literal and distance codes
+bool dyn_header_ok(const uint8_t *beg, const uint8_t *end, int64_t p)
 {
-    const int64_t last_bit = (int64_t)(end - beg) * 8 - 64 * 8;        // a block this close to the end is left to the predecessor
+    const uint64_t w = peek_at(beg, end, p);
+    if ((w & 6u) != 4u) return false;
+    const int hlit = (int)((w >> 3) & 31u) + 257, hdist = (int)((w >> 8) & 31u) + 1, hclen = (int)((w >> 13) & 15u) + 4;
+    if (hlit > 286 || hdist > 30) return false;
+    uint8_t cl[19] = {0};
+    const uint64_t w2 = peek_at(beg, end, p + 17);    // 19 x 3 = 57 bits
+    int kraft = 0;
+    for (int i = 0; i < hclen; i++) { const int l = (int)((w2 >> (3 * i)) & 7u); cl[CL_PERM[i]] = (uint8_t)l; if (l) kraft += 128 >> l; }
+    if (kraft != 128) return false;
+    uint32_t cltab[1 << 7];
+    if (!build_table(cl, 19, 7, 2, cltab, 1 << 7)) return false;
+    uint8_t lens[320];
+    int64_t q = p + 17 + 3 * hclen;
+    int i = 0;
+    bool ok = true;
+    while (i < hlit + hdist) {
+        uint64_t v = peek_at(beg, end, q);
+        const uint32_t e = cltab[v & 127u];
+        if (E_TYPE(e) == T_BAD) { ok = false; break; }
+        q += E_BITS(e); v >>= E_BITS(e);
+        const int sym = (int)(e >> 16);
+        if (sym < 16) { lens[i++] = (uint8_t)sym; continue; }
+        int rep, val = 0;
+        if (sym == 16) { if (i == 0) { ok = false; break; } val = lens[i - 1]; rep = 3 + (int)(v & 3u); q += 2; }
+        else if (sym == 17) { rep = 3 + (int)(v & 7u); q += 3; }
+        else { rep = 11 + (int)(v & 127u); q += 7; }
+        if (i + rep > hlit + hdist) { ok = false; break; }
+        while (rep--) lens[i++] = (uint8_t)val;
+    }
+    if (!ok || lens[256] == 0 || q >= (int64_t)(end - beg) * 8) return false;
+    // both codes complete (a single distance code or none at all is legal too)
+    int cnt[16] = {0}, left = 1, used = 0;
+    for (int k = 0; k < hlit; k++) cnt[lens[k]]++;
+    cnt[0] = 0;
+    for (int l = 1; l < 16 && left >= 0; l++) { left = (left << 1) - cnt[l]; used += cnt[l]; }
+    if (left != 0 || used < 2) return false;
+    memset(cnt, 0, sizeof cnt); left = 1; used = 0;
+    for (int k = 0; k < hdist; k++) cnt[lens[hlit + k]]++;
+    cnt[0] = 0;
+    for (int l = 1; l < 16 && left >= 0; l++) { left = (left << 1) - cnt[l]; used += cnt[l]; }
+    if (left < 0 || (left > 0 && used > 1)) return false;
+    return true;
+}
+
+// The first place in [from_bit, to_bit) where decoding can start: a non-final dynamic block header (any bit), or a gzip
+// member header (a byte boundary: magic, CM = 8, reserved flags clear, and a first block that is acceptable) -- BGZF and
+// other many-member files have one FINAL block per member.  -1 if none.
+int64_t find_start(const uint8_t *beg, const uint8_t *end, int64_t from_bit, int64_t to_bit, bool *is_header)
+{
+    const int64_t last_bit = (int64_t)(end - beg) * 8 - 64 * 8;        // this close to the end everything is left to the predecessor
     to_bit = std::min(to_bit, last_bit);
+    *is_header = false;
     for (int64_t p = from_bit; p < to_bit; p++) {
+        if ((p & 7) == 0) {
+            const uint8_t *q = beg + (p >> 3);
+            if (q[0] == 0x1f && q[1] == 0x8b && q[2] == 8 && !(q[3] & 0xe0)) {
+                const uint8_t *d = skip_member_header(q, end);
+                if (d && end - d > 16) {
+                    const int type = (d[0] >> 1) & 3;
+                    const bool ok = type == 1 || (type == 0 && ((d[1] | d[2] << 8) ^ (d[3] | d[4] << 8)) == 0xffff) ||
+                                    (type == 2 && dyn_header_ok(beg, end, (int64_t)(d - beg) * 8));
+                    if (ok) { *is_header = true; return p; }
+                }
+            }
+        }
         const uint64_t w = peek_at(beg, end, p);
         if ((w & 7u) != 4u) continue;                     // BFINAL = 0, BTYPE = 2
-        const int hlit = (int)((w >> 3) & 31u) + 257, hdist = (int)((w >> 8) & 31u) + 1, hclen = (int)((w >> 13) & 15u) + 4;
-        if (hlit > 286 || hdist > 30) continue;
-        uint8_t cl[19] = {0};
-        const uint64_t w2 = peek_at(beg, end, p + 17);    // 19 x 3 = 57 bits
-        int kraft = 0;
-        for (int i = 0; i < hclen; i++) { const int l = (int)((w2 >> (3 * i)) & 7u); cl[CL_PERM[i]] = (uint8_t)l; if (l) kraft += 128 >> l; }
-        if (kraft != 128) continue;
-        uint32_t cltab[1 << 7];
-        if (!build_table(cl, 19, 7, 2, cltab, 1 << 7)) continue;
-        uint8_t lens[320];
-        int64_t q = p + 17 + 3 * hclen;
-        int i = 0;
-        bool ok = true;
-        while (i < hlit + hdist) {
-            uint64_t v = peek_at(beg, end, q);
-            const uint32_t e = cltab[v & 127u];
-            if (E_TYPE(e) == T_BAD) { ok = false; break; }
-            q += E_BITS(e); v >>= E_BITS(e);
-            const int sym = (int)(e >> 16);
-            if (sym < 16) { lens[i++] = (uint8_t)sym; continue; }
-            int rep, val = 0;
-            if (sym == 16) { if (i == 0) { ok = false; break; } val = lens[i - 1]; rep = 3 + (int)(v & 3u); q += 2; }
-            else if (sym == 17) { rep = 3 + (int)(v & 7u); q += 3; }
-            else { rep = 11 + (int)(v & 127u); q += 7; }
-            if (i + rep > hlit + hdist) { ok = false; break; }
-            while (rep--) lens[i++] = (uint8_t)val;
-        }
-        if (!ok || lens[256] == 0 || q >= (int64_t)(end - beg) * 8) continue;
-        // both codes complete (a single distance code or none at all is legal too)
-        int cnt[16] = {0}, left = 1, used = 0;
-        for (int k = 0; k < hlit; k++) cnt[lens[k]]++;
-        cnt[0] = 0;
-        for (int l = 1; l < 16 && left >= 0; l++) { left = (left << 1) - cnt[l]; used += cnt[l]; }
-        if (left != 0 || used < 2) continue;
-        memset(cnt, 0, sizeof cnt); left = 1; used = 0;
-        for (int k = 0; k < hdist; k++) cnt[lens[hlit + k]]++;
-        cnt[0] = 0;
-        for (int l = 1; l < 16 && left >= 0; l++) { left = (left << 1) - cnt[l]; used += cnt[l]; }
-        if (left < 0 || (left > 0 && used > 1)) continue;
-        return p;
+        if (dyn_header_ok(beg, end, p)) return p;
     }
     return -1;
 }
@@ -894,7 +920,9 @@ int64_t batch_parallel(itsx_gz *h, uint8_t *dst, int64_t room)
     const int64_t batch_stop = to_end ? INT64_MAX : (pos_byte + (int64_t)nch * C) * 8;
     while ((int)h->segs.size() < nch) { h->segs.emplace_back(new Segment()); h->decs.emplace_back(new Dec()); }
     std::vector<std::atomic<int64_t>> starts(nch);
+    std::vector<char> start_hdr((size_t)nch, 0);         // (written before the release-store of starts[k])
     for (int k = 0; k < nch; k++) starts[k].store(-2);
+    start_hdr[0] = h->at_header;
     starts[0].store(h->pos_bit);
     const uint8_t *src = h->src, *end = h->end;
     const int64_t pos_bit = h->pos_bit;
@@ -912,11 +940,14 @@ int64_t batch_parallel(itsx_gz *h, uint8_t *dst, int64_t room)
         if (k > 0) {
             const int64_t a = (pos_byte + (int64_t)k * C) * 8;
             const int64_t b = (k + 1 < nch || !to_end) ? a + C * 8 : n_in * 8;
-            starts[k].store(find_block(src, end, a, b), std::memory_order_release);
-            if (starts[k].load() < 0) { g.start_bit = -1; return; }
+            bool hdr = false;
+            const int64_t st = find_start(src, end, a, b, &hdr);
+            start_hdr[(size_t)k] = hdr;
+            starts[k].store(st, std::memory_order_release);
+            if (st < 0) { g.start_bit = -1; return; }
         }
         const int64_t stop = stop_for(k);
-        decode_segment(g, *h->decs[k], src, end, k ? starts[k].load() : pos_bit, k ? false : at_header, stop, (size_t)(C * 7 / 2));
+        decode_segment(g, *h->decs[k], src, end, k ? starts[k].load() : pos_bit, k ? (bool)start_hdr[(size_t)k] : at_header, stop, (size_t)(C * 7 / 2));
     });
     // ---- stitch ----
     std::vector<Segment *> acc;
@@ -938,7 +969,7 @@ int64_t batch_parallel(itsx_gz *h, uint8_t *dst, int64_t room)
     while (j < nch && !cur->eof) {
         const int64_t s = starts[j].load();
         if (s < 0) { j++; continue; }
-        if (cur->end_bit == s && !cur->end_header) {
+        if (cur->end_bit == s && cur->end_header == (bool)start_hdr[(size_t)j]) {
             Segment *g = h->segs[j].get();
             if (g->err) return g->err;
             acc.push_back(g);

@@ -162,6 +162,30 @@ def test_one_stream_on_several_cores_survives_block_starts_that_are_none():
         fq.gunzip(bytes(bad), 4, (2048, 2048, 0))
 
 
+def test_many_small_members_start_chunks_at_member_headers():
+    """BGZF (bgzip, some sequencers): members of <= 64 KB with an extra field and ONE final block each -- there is no
+    non-final block header to find, so chunks of the multi-core mode start at member headers."""
+    data = _payloads()["fastq x12"][:900000]
+    members = []
+    for i in range(0, len(data), 30000):
+        piece = data[i:i + 30000]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(piece) + co.flush()
+        bsize = 12 + 6 + len(body) + 8 - 1
+        members.append(bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 66, 67, 2, 0]) + bsize.to_bytes(2, "little") + body +
+                       zlib.crc32(piece).to_bytes(4, "little") + len(piece).to_bytes(4, "little"))
+    comp = b"".join(members) + bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])   # BGZF EOF
+    assert gzip.decompress(comp) == data
+    for threads, tune in ((1, None), (4, (4096, 16384, 0)), (8, (2048, 2048, 0))):
+        got, (batches, _) = _read_all(comp, threads, tune, [1 << 21])
+        assert got == data and (batches > 0) == (threads > 1), (threads, tune)
+        assert fq.gunzip(comp, threads, tune).tobytes() == data
+    bad = bytearray(comp)
+    bad[len(members[0]) + len(members[1]) - 3] ^= 1                  # ISIZE of the second member
+    with pytest.raises(gzip.BadGzipFile):
+        fq.gunzip(bytes(bad), 4, (4096, 16384, 0))
+
+
 def test_damaged_streams_raise_what_the_gzip_module_raises():
     data = _payloads()["fastq"]
     comp = bytearray(_member(data, 6))
