@@ -245,3 +245,17 @@ def test_crc_paths_agree_without_carry_less_multiplication():
     for env in ({}, {"ITSX_NO_CLMUL": "1"}):
         r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]
+
+
+def test_the_bench_writes_its_gz_input_as_one_member():
+    """bench.py's gz-in / gz-out leg feeds the command line ONE gzip member, as a sequencer writes it (pieces compressed
+    concurrently the way pigz does it): a valid stream for zlib and for the native reader."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from cli_e2e import gzip_one_member
+    data = _payloads()["fastq x12"]
+    comp = gzip_one_member(data, piece=100_000)
+    d = zlib.decompressobj(31)
+    assert d.decompress(comp) == data and d.eof and d.unused_data == b""          # one member, nothing behind it
+    assert fq.gunzip(comp, 1).tobytes() == data and fq.gunzip(comp, 4, SMALL).tobytes() == data
+    assert gzip.decompress(gzip_one_member(b"")) == b""
