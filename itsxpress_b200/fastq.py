@@ -116,7 +116,10 @@ def _gather_numpy(buf, off, length):
 
 def host_share():
     """Host cores this process may use: all of them divided by the ranks that share the box."""
-    cores = os.cpu_count() or 2
+    try:
+        cores = len(os.sched_getaffinity(0))          # what this process may run on (containers, taskset)
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 2
     return max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))))
 
 
