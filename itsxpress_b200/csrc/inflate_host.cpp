@@ -661,22 +661,28 @@ int64_t find_start(const uint8_t *beg, const uint8_t *end, int64_t from_bit, int
     const int64_t last_bit = (int64_t)(end - beg) * 8 - 64 * 8;        // this close to the end everything is left to the predecessor
     to_bit = std::min(to_bit, last_bit);
     *is_header = false;
-    for (int64_t p = from_bit; p < to_bit; p++) {
-        if ((p & 7) == 0) {
-            const uint8_t *q = beg + (p >> 3);
-            if (q[0] == 0x1f && q[1] == 0x8b && q[2] == 8 && !(q[3] & 0xe0)) {
-                const uint8_t *d = skip_member_header(q, end);
-                if (d && end - d > 16) {
-                    const int type = (d[0] >> 1) & 3;
-                    const bool ok = type == 1 || (type == 0 && ((d[1] | d[2] << 8) ^ (d[3] | d[4] << 8)) == 0xffff) ||
-                                    (type == 2 && dyn_header_ok(beg, end, (int64_t)(d - beg) * 8));
-                    if (ok) { *is_header = true; return p; }
-                }
+    // byte by byte: one load serves the eight bit offsets (3 header bits + HLIT + HDIST = 13 bits, 20 with the offset)
+    for (int64_t byte = from_bit >> 3; byte * 8 < to_bit; byte++) {
+        const uint8_t *q = beg + byte;
+        if (byte * 8 >= from_bit && q[0] == 0x1f && q[1] == 0x8b && q[2] == 8 && !(q[3] & 0xe0)) {
+            const uint8_t *d = skip_member_header(q, end);
+            if (d && end - d > 16) {
+                const int type = (d[0] >> 1) & 3;
+                const bool ok = type == 1 || (type == 0 && ((d[1] | d[2] << 8) ^ (d[3] | d[4] << 8)) == 0xffff) ||
+                                (type == 2 && dyn_header_ok(beg, end, (int64_t)(d - beg) * 8));
+                if (ok) { *is_header = true; return byte * 8; }
             }
         }
-        const uint64_t w = peek_at(beg, end, p);
-        if ((w & 7u) != 4u) continue;                     // BFINAL = 0, BTYPE = 2
-        if (dyn_header_ok(beg, end, p)) return p;
+        uint32_t w4;
+        memcpy(&w4, q, 4);
+        for (int o = 0; o < 8; o++) {
+            const uint32_t w = w4 >> o;
+            if ((w & 7u) != 4u) continue;                 // BFINAL = 0, BTYPE = 2
+            if (((w >> 3) & 31u) > 29u || ((w >> 8) & 31u) > 29u) continue;       // HLIT, HDIST
+            const int64_t p = byte * 8 + o;
+            if (p < from_bit || p >= to_bit) continue;
+            if (dyn_header_ok(beg, end, p)) return p;
+        }
     }
     return -1;
 }
