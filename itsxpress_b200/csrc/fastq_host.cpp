@@ -11,7 +11,11 @@
 #include <atomic>
 #include <cstring>
 #include <string>
+#include <cstdlib>
 #include <thread>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 #include <vector>
 #include "itsx_internal.h"
 
@@ -28,12 +32,31 @@ struct LineIndexCache {
 };
 thread_local LineIndexCache g_lines;
 
+// host threads of this process: the cores it may run on, divided by the ranks that share the box (torchrun sets
+// LOCAL_WORLD_SIZE; eight ranks that each start 32 threads on a 32-core host only get in each other's way), at most 32;
+// ITSX_HOST_THREADS overrides
+int host_threads()
+{
+    static const int n = [] {
+        if (const char *e = getenv("ITSX_HOST_THREADS")) { const int v = atoi(e); if (v > 0) return std::min(v, 64); }
+        int hw = 0;
+#if defined(__linux__)
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0) hw = CPU_COUNT(&set);
+#endif
+        if (hw <= 0) hw = (int)std::thread::hardware_concurrency();
+        if (hw <= 0) hw = 4;
+        const char *w = getenv("LOCAL_WORLD_SIZE");
+        if (!w) w = getenv("WORLD_SIZE");
+        const int ranks = w ? std::max(1, atoi(w)) : 1;
+        return std::max(1, std::min(hw / ranks, 32));
+    }();
+    return n;
+}
+
 int nthreads_for(int64_t work, int64_t grain)
 {
-    int hw = (int)std::thread::hardware_concurrency();
-    if (hw <= 0) hw = 4;
-    hw = std::min(hw, 32);
-    return (int)std::max<int64_t>(1, std::min<int64_t>(hw, work / std::max<int64_t>(grain, 1)));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), work / std::max<int64_t>(grain, 1)));
 }
 
 template <typename F> void parallel_for(int64_t n, int64_t grain, F f)
