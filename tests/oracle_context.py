@@ -4,7 +4,8 @@ The product has no CPU path (a missing CUDA extension or device is an error); th
 above the C ABI -- the command line, SeqSample / ItsPosition / Dedup, the FASTQ readers and writers, the temp-file policy,
 streaming -- can be driven end to end by `-m "not gpu"` tests.  It implements the methods those flows call, with the same
 argument meaning and the same array layouts as the ctypes wrapper (itsxpress_b200/_lib.py); tests install it by
-monkeypatching `itsxpress_b200.SeqSample.get_context`.  Single-end flows only (whole file and streamed).
+monkeypatching `itsxpress_b200.SeqSample.get_context`.  Covered: single-end flows (whole file and streamed) and the
+paired flows of one sample (merge, merged and unmerged output); not the batched multi-sample pass.
 """
 import types
 
@@ -54,6 +55,31 @@ class OracleContext:
                 side[i] = 1
         self.set_sides(side)
         return side
+
+    # ---- paired-end merge ----
+    def merge_pairs(self, fseq, fqual, foff, rseq, rqual, roff, params=None, fetch=True):
+        self._note("merge_pairs")
+        foff = np.ascontiguousarray(foff, dtype=np.int64)
+        roff = np.ascontiguousarray(roff, dtype=np.int64)
+        if len(foff) != len(roff):
+            raise ValueError("R1 and R2 hold different numbers of records")
+        prm = self.O.merge_params()
+        if params is not None:
+            for k in ("maxdiffs", "allow_stagger", "qmax", "minovlen", "qmaxout", "qminout", "ascii", "maxee", "maxdiffpct"):
+                setattr(prm, k, getattr(params, k))
+        mlen, reason, slot_seq, slot_qual = self.O.merge_pairs(fseq, fqual, foff, rseq, rqual, roff, prm)
+        idx = np.flatnonzero(reason == 0).astype(np.int32)
+        oo = np.zeros(len(idx) + 1, np.int64)
+        np.cumsum(mlen[idx], out=oo[1:])
+        src = np.repeat((foff[:-1] + roff[:-1])[idx] - oo[:-1], mlen[idx]) + np.arange(int(oo[-1]), dtype=np.int64)
+        self._merge = (len(mlen), len(idx), np.bincount(reason, minlength=16))
+        if not fetch:
+            return mlen, reason, None, None, None, None
+        return mlen, reason, idx, oo, slot_seq[src], slot_qual[src]
+
+    def merge_stats(self):
+        n, m, by = self._merge
+        return types.SimpleNamespace(n_pairs=n, n_merged=m, by_reason=[int(v) for v in by], ms_kernel=0.0, bytes_in=0, bytes_out=0)
 
     # ---- derep ----
     def _derep(self):

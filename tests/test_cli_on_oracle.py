@@ -5,7 +5,8 @@ device (tests/oracle_context.py).  What the reference's own CLI tests do with vs
 
 Checked: the trimmed records equal an independent composition of the oracle's stages; plain / .gz / .zst inputs and outputs
 agree; the streamed path (chunks of a few KB) equals the whole-file path; with --keeptemp the files the reference's stages
-exchange are the real vsearch output of the fixture, byte for byte (uc.txt, rep.fa)."""
+exchange are the real vsearch output of the fixture, byte for byte (uc.txt, rep.fa); the paired command line (merged and
+unmerged output, BASELINE configs[0]) and the QIIME 2 paired actions on the reference's own per-sample directory."""
 import glob
 import gzip
 import os
@@ -129,3 +130,62 @@ def test_missing_profiles_and_broken_input_end_the_cli_with_status_1(on_oracle, 
                                                  "--taxa", "Fungi", "--log", os.path.join(str(tmp_path), "l.txt"),
                                                  "--tempdir", str(tmp_path)]))
     assert e.value.code == 1 and not os.path.exists(out)
+
+
+def test_paired_cli_merged_and_unmerged_output(oracle, on_oracle, tmp_path):
+    """BASELINE configs[0] (reference test_main_paired / test_main_paired_no_merge, tests/test_main_pytest.py:228-350) on the
+    bundled pair sample: the expectations of tests/test_gpu_merge.py::test_cli_paired_end_to_end, host code on the oracle."""
+    from test_gpu_merge import _oracle_pipeline
+    r1n, r2n = "4774-1-MSITS3_R1.fastq", "4774-1-MSITS3_R2.fastq"
+    b1, b2, fo, ro, midx, moff, mseq, mqual, rep, s_r, e_r, t_r = _oracle_pipeline(oracle, r1n, r2n, stagger=True)
+    out = str(tmp_path / "merged.fastq")
+    cli.main(args=cli.myparser().parse_args(["--fastq", os.path.join(TD, r1n), "--fastq2", os.path.join(TD, r2n),
+                                             "--outfile", out, "--region", "ITS2", "--taxa", "Metazoa",
+                                             "--log", str(tmp_path / "l1.txt"), "--tempdir", str(tmp_path)]))
+    keep, lo, hi = oracle.trim_bounds(moff, rep, s_r, e_r, t_r, mode=0)
+    ki = np.flatnonzero(keep)
+    assert len(ki) > 150
+    want = []
+    for k in ki:
+        a, b = int(moff[k] + lo[k]), int(moff[k] + hi[k])
+        want.append("@%s\n%s\n+\n%s\n" % (b1.title(int(midx[k])), mseq[a:b].tobytes().decode(), mqual[a:b].tobytes().decode()))
+    assert open(out).read() == "".join(want)
+    assert "merge_pairs" in on_oracle.calls
+    for ext in (".fastq.gz", ".fastq"):
+        o1, o2 = str(tmp_path / ("r1" + ext)), str(tmp_path / ("r2" + ext))
+        gz = ".gz" if ext.endswith(".gz") else ""
+        cli.main(args=cli.myparser().parse_args(["--fastq", os.path.join(TD, r1n + gz), "--fastq2", os.path.join(TD, r2n + gz),
+                                                 "--outfile", o1, "--outfile2", o2, "--region", "ITS2", "--taxa", "Metazoa",
+                                                 "--log", str(tmp_path / "l2.txt"), "--tempdir", str(tmp_path)]))
+        for path, batch, off_all, mode in ((o1, b1, fo, 2), (o2, b2, ro, 1)):
+            ln = np.diff(off_all)[midx]
+            off_m = np.zeros(len(midx) + 1, np.int64)
+            off_m[1:] = np.cumsum(ln)
+            keep, lo, hi = oracle.trim_bounds(off_m, rep, s_r, e_r, t_r, mode=mode, off_r2=off_m)
+            ki = np.flatnonzero(keep)
+            assert fq._open_bytes(path) == fq.format_records(batch, midx[ki], lo[ki], hi[ki]), (ext, mode)
+
+
+def test_q2_paired_actions_equal_the_cli(oracle, on_oracle, tmp_path, monkeypatch):
+    """trim-pair-output-unmerged and trim-pair on the reference's paired per-sample directory (q2_itsxpress.py:156-230): the
+    files and the MANIFEST the plugin would hand back, bytes equal to the command line's."""
+    from itsxpress_b200 import q2_itsxpress as q2
+    monkeypatch.setattr(q2, "BATCH_READS", 0)                 # the per-sample loop (the batched pass is GPU-suite territory)
+    src = os.path.join(TD, "paired", "445cf54a-bf06-4852-8010-13a60fa1598c", "data")
+    n1, n2 = "4774-1-MSITS3_0_L001_R1_001.fastq.gz", "4774-1-MSITS3_1_L001_R2_001.fastq.gz"
+    res = q2.trim_pair_output_unmerged(q2.PerSampleDir(src), region="ITS2", taxa="M")
+    o1, o2 = os.path.join(str(res), n1), os.path.join(str(res), n2)
+    c1, c2 = str(tmp_path / "c1.fastq"), str(tmp_path / "c2.fastq")
+    cli.main(args=cli.myparser().parse_args(["--fastq", os.path.join(src, n1), "--fastq2", os.path.join(src, n2),
+                                             "--outfile", c1, "--outfile2", c2, "--region", "ITS2", "--taxa", "Metazoa",
+                                             "--log", str(tmp_path / "l.txt"), "--tempdir", str(tmp_path)]))
+    assert fq._open_bytes(o1) == open(c1, "rb").read() and fq._open_bytes(o2) == open(c2, "rb").read()
+    assert fq.read_fastq(o1).n == fq.read_fastq(o2).n > 150
+    man = open(os.path.join(str(res), "MANIFEST")).read().splitlines()
+    assert man == ["sample-id,filename,direction", "4774-1-MSITS3,%s,forward" % n1, "4774-1-MSITS3,%s,reverse" % n2]
+    res = q2.trim_pair(q2.PerSampleDir(src), region="ITS2", taxa="M")
+    cm = str(tmp_path / "cm.fastq")
+    cli.main(args=cli.myparser().parse_args(["--fastq", os.path.join(src, n1), "--fastq2", os.path.join(src, n2),
+                                             "--outfile", cm, "--region", "ITS2", "--taxa", "Metazoa",
+                                             "--log", str(tmp_path / "l.txt"), "--tempdir", str(tmp_path)]))
+    assert fq._open_bytes(os.path.join(str(res), n1)) == open(cm, "rb").read()
