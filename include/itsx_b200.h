@@ -375,6 +375,22 @@ int64_t itsx_fastq_cut(const uint8_t *buf, int64_t nbytes);
 /* out_off[n+1] = prefix sums of len; out (may be NULL) = segments packed back to back.  Returns total bytes. */
 int64_t itsx_bytes_gather(const uint8_t *buf, const int64_t *off, const int32_t *len, int64_t n, uint8_t *out,
                           int64_t *out_off);
+/* The files vsearch hands to the next stage (SeqSample.py:104-119), from the arrays itsx_derep returns:
+ * itsx_fastq_labels = Biopython's record.id of every record (title.split(None, 1)[0]) as (offset into buf, length);
+ * itsx_uc_format = uc.txt of --fastx_uniques (S / H rows per cluster in `order`, then the C rows);
+ * itsx_repfa_format = rep.fa (>label, sequence wrapped at `width` = 80).  Both return the bytes written to dst or ITSX_ELIMIT. */
+int64_t itsx_fastq_labels(const uint8_t *buf, const int64_t *t_off, const int64_t *t_len, int64_t n, int64_t *lab_off,
+                          int32_t *lab_len);
+int64_t itsx_uc_format(const int32_t *rep, const uint8_t *strand, const int64_t *len, int64_t n, const int64_t *order, int64_t nc,
+                       const uint8_t *buf, const int64_t *lab_off, const int32_t *lab_len, uint8_t *dst, int64_t cap);
+int64_t itsx_repfa_format(const uint8_t *buf, const int64_t *s_off, const int64_t *s_len, const int64_t *lab_off,
+                          const int32_t *lab_len, const int64_t *order, int64_t nc, int32_t width, uint8_t *dst, int64_t cap);
+/* domtbl.txt body -- hmmsearch --domtblout rows (SeqSample.py:190; the six fields ItsPosition reads at :445-450 carry the
+ * computed values) -- from the rows of itsx_hits.  Labels: byte strings with offsets (no terminators); Z = searched
+ * sequences, nreported = itsx_nreported (domZ).  Returns the bytes written to dst, ITSX_ELIMIT if cap is too small. */
+int64_t itsx_domtbl_format(const itsx_dom_row *rows, int64_t nrows, const uint8_t *seq_lab, const int64_t *seq_off,
+                           const uint8_t *prof_lab, const int64_t *prof_off, const int32_t *prof_M, const int32_t *nreported,
+                           double Z, uint8_t *dst, int64_t cap);
 /* '@title\nseq\n+\nqual\n' for nkeep records (dst == NULL: size query); pre_ and suf_ (lp, ls bytes) are stitched to
  * every record's bases and qualities (--trim-ccs, SeqSample.py:601-622).  Returns the number of bytes. */
 int64_t itsx_fastq_format(const uint8_t *buf, const int64_t *t_off, const int32_t *t_len, const int32_t *keep_idx,

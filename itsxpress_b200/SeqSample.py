@@ -200,7 +200,7 @@ class SeqSample:
                 with open(self.rep_file, "wb") as f:
                     f.write(host.write_rep_fasta(batch, order, ids))
                 with open(self.uc_file, "wb") as f:
-                    f.write(host.write_uc(rep, strand, ids, batch.s_len, order))
+                    f.write(host.write_uc(rep, strand, ids, batch.s_len, order, batch=batch))
             else:
                 logging.info("uc.txt and rep.fa are one-line placeholders for this sample (%d reads > %d); Dedup takes "
                              "the read -> representative map from the GPU session. Use --keeptemp or "

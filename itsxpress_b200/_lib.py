@@ -97,7 +97,8 @@ SYMBOLS = [
     "itsx_merge_default_params", "itsx_merge_pairs", "itsx_merge_fetch", "itsx_merge_get_stats",
     "itsx_gzip_bound", "itsx_gzip_compress",
     "itsx_gz_open", "itsx_gz_read", "itsx_gz_eof", "itsx_gz_close", "itsx_gz_tune", "itsx_gz_stat",
-    "itsx_host_last_error", "itsx_fastq_index", "itsx_fastq_cut", "itsx_bytes_gather", "itsx_fastq_format",
+    "itsx_host_last_error", "itsx_fastq_index", "itsx_fastq_cut", "itsx_bytes_gather", "itsx_fastq_format", "itsx_domtbl_format",
+    "itsx_fastq_labels", "itsx_uc_format", "itsx_repfa_format",
 ]
 
 
@@ -194,6 +195,14 @@ def lib():
     L.itsx_gz_stat.argtypes = [vp, C.c_int]
     L.itsx_gz_stat.restype = i64
     L.itsx_host_last_error.restype = C.c_char_p
+    L.itsx_domtbl_format.restype = i64
+    L.itsx_domtbl_format.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, C.c_double, vp, i64]
+    L.itsx_fastq_labels.restype = i64
+    L.itsx_fastq_labels.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.itsx_uc_format.restype = i64
+    L.itsx_uc_format.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, i64]
+    L.itsx_repfa_format.restype = i64
+    L.itsx_repfa_format.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp, i64]
     L.itsx_fastq_cut.restype = i64
     L.itsx_fastq_cut.argtypes = [vp, i64]
     L.itsx_fastq_index.restype = i64

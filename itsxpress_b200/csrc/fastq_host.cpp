@@ -10,6 +10,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <unordered_map>
+#include <cstdio>
+#include <cmath>
 #include <string>
 #include <cstdlib>
 #include <thread>
@@ -256,6 +259,156 @@ int64_t itsx_fastq_format(const uint8_t *buf, const int64_t *t_off, const int32_
         }
     });
     return tot;
+}
+
+// domtbl.txt rows in hmmsearch's --domtblout layout from the rows itsx_hits returns (what host.write_domtbl did row by row
+// in Python: 25 us per row, minutes for a sample of 10^5 reads).  Labels come as byte strings with offsets (sequence i:
+// seq_lab[seq_off[i] .. seq_off[i + 1]), no terminator).  E-values as HMMER computes them: Z = searched sequences, domZ =
+// reported hits of the profile; alignment-derived columns are constants (include/itsx_b200.h).  Rows are formatted on the
+// host threads into private strings and copied to dst in order.  Returns the bytes written, or ITSX_ELIMIT if cap is too
+// small (nothing written then).
+int64_t itsx_domtbl_format(const itsx_dom_row *rows, int64_t nrows, const uint8_t *seq_lab, const int64_t *seq_off,
+                           const uint8_t *prof_lab, const int64_t *prof_off, const int32_t *prof_M, const int32_t *nreported,
+                           double Z, uint8_t *dst, int64_t cap)
+{
+    if (nrows < 0 || (nrows && (!rows || !seq_lab || !seq_off || !prof_lab || !prof_off || !prof_M || !nreported)) || !dst)
+        return ITSX_EINVAL;
+    // domains per (profile, sequence) hit and the running index of every row within its hit, in row order
+    std::vector<int32_t> k_in_hit((size_t)nrows), ndom((size_t)nrows);
+    {
+        std::unordered_map<int64_t, int32_t> count;
+        count.reserve((size_t)nrows / 2 + 16);
+        for (int64_t t = 0; t < nrows; t++) k_in_hit[(size_t)t] = ++count[(int64_t)rows[t].prof << 32 | (uint32_t)rows[t].seq];
+        for (int64_t t = 0; t < nrows; t++) ndom[(size_t)t] = count[(int64_t)rows[t].prof << 32 | (uint32_t)rows[t].seq];
+    }
+    const int nt = nthreads_for(nrows, 1 << 14);
+    std::vector<std::string> part((size_t)nt);
+    parallel_for(nrows, 1 << 14, [&](int64_t a, int64_t b, int t) {
+        std::string &o = part[(size_t)t];
+        o.reserve((size_t)(b - a) * 200);
+        char num[512];
+        for (int64_t r = a; r < b; r++) {
+            const itsx_dom_row &d = rows[r];
+            const int p = d.prof;
+            const double ev = exp(d.seq_lnP) * Z, cev = exp(d.lnP) * (double)nreported[p], iev = exp(d.lnP) * Z;
+            const int ls = (int)(seq_off[d.seq + 1] - seq_off[d.seq]), lp = (int)(prof_off[p + 1] - prof_off[p]);
+            o.append((const char *)seq_lab + seq_off[d.seq], (size_t)ls);
+            if (ls < 20) o.append((size_t)(20 - ls), ' ');
+            int n = snprintf(num, sizeof num, " %-10s %5d ", "-", d.tlen);
+            o.append(num, (size_t)n);
+            o.append((const char *)prof_lab + prof_off[p], (size_t)lp);
+            if (lp < 20) o.append((size_t)(20 - lp), ' ');
+            n = snprintf(num, sizeof num, " %-10s %5d %9.2g %6.1f %5.1f %3d %3d %9.2g %9.2g %6.1f %5.1f %5d %5d %5d %5d %5d %5d %4.2f %s\n",
+                         "-", prof_M[p], ev, (double)d.seq_score, 0.0, k_in_hit[(size_t)r], ndom[(size_t)r], cev, iev,
+                         (double)d.bitscore, 0.0, 1, prof_M[p], d.ienv, d.jenv, d.ienv, d.jenv, 0.0, "-");
+            o.append(num, (size_t)n);
+        }
+    });
+    int64_t total = 0;
+    for (const std::string &o : part) total += (int64_t)o.size();
+    if (total > cap) return ITSX_ELIMIT;
+    int64_t at = 0;
+    for (const std::string &o : part) { memcpy(dst + at, o.data(), o.size()); at += (int64_t)o.size(); }
+    return total;
+}
+
+// First whitespace-delimited token of every title (Biopython's record.id = title.split(None, 1)[0]): where it starts in buf
+// and how long it is (0 for a title without one).
+int64_t itsx_fastq_labels(const uint8_t *buf, const int64_t *t_off, const int64_t *t_len, int64_t n, int64_t *lab_off,
+                          int32_t *lab_len)
+{
+    if (n < 0 || (n && (!buf || !t_off || !t_len || !lab_off || !lab_len))) return ITSX_EINVAL;
+    auto ws = [](uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); };
+    parallel_for(n, 1 << 16, [&](int64_t a, int64_t b, int) {
+        for (int64_t i = a; i < b; i++) {
+            const uint8_t *p = buf + t_off[i], *e = p + t_len[i];
+            while (p < e && ws(*p)) p++;
+            const uint8_t *q = p;
+            while (q < e && !ws(*q)) q++;
+            lab_off[i] = (int64_t)(p - buf);
+            lab_len[i] = (int32_t)(q - p);
+        }
+    });
+    return n;
+}
+
+namespace {
+inline void put_int(std::string &o, int64_t v)
+{
+    char t[24];
+    int k = 0;
+    if (v < 0) { o.push_back('-'); v = -v; }
+    do { t[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (k) o.push_back(t[--k]);
+}
+}   // namespace
+
+// uc.txt as `vsearch --uc` writes it for --fastx_uniques (SeqSample.py:104-119): per cluster, in
+// `order`, an S row and the H rows of its other members in input order, then one C row per cluster.  rep[i] = read index of
+// read i's representative, strand[i] != 0 -> '-' (may be NULL), len[i] = sequence length, order[c] = representative of
+// cluster c, labels as itsx_fastq_labels returns them.  Returns the bytes written, ITSX_ELIMIT if cap is too small.
+int64_t itsx_uc_format(const int32_t *rep, const uint8_t *strand, const int64_t *len, int64_t n, const int64_t *order, int64_t nc,
+                       const uint8_t *buf, const int64_t *lab_off, const int32_t *lab_len, uint8_t *dst, int64_t cap)
+{
+    if (n < 0 || nc < 0 || (n && (!rep || !len || !buf || !lab_off || !lab_len)) || (nc && !order) || !dst) return ITSX_EINVAL;
+    std::vector<int64_t> cl((size_t)n, -1), cnt((size_t)nc + 1, 0);
+    for (int64_t c = 0; c < nc; c++) { if (order[c] < 0 || order[c] >= n) return ITSX_EINVAL; cl[(size_t)order[c]] = c; }
+    for (int64_t i = 0; i < n; i++) {
+        if (rep[i] < 0 || rep[i] >= n || cl[(size_t)rep[i]] < 0) return ITSX_EINVAL;
+        if (rep[i] != i) cnt[(size_t)cl[(size_t)rep[i]] + 1]++;
+    }
+    for (int64_t c = 0; c < nc; c++) cnt[(size_t)c + 1] += cnt[(size_t)c];
+    std::vector<int64_t> mem((size_t)cnt[(size_t)nc]), at(cnt.begin(), cnt.end() - 1);
+    for (int64_t i = 0; i < n; i++) if (rep[i] != i) mem[(size_t)at[(size_t)cl[(size_t)rep[i]]]++] = i;
+    std::string o;
+    o.reserve((size_t)n * 64);
+    auto label = [&](int64_t i) { o.append((const char *)buf + lab_off[i], (size_t)lab_len[i]); };
+    for (int64_t c = 0; c < nc; c++) {
+        const int64_t r = order[c];
+        o += "S\t"; put_int(o, c); o.push_back('\t'); put_int(o, len[r]); o += "\t*\t*\t*\t*\t*\t"; label(r); o += "\t*\n";
+        for (int64_t k = cnt[(size_t)c]; k < cnt[(size_t)c + 1]; k++) {
+            const int64_t i = mem[(size_t)k];
+            o += "H\t"; put_int(o, c); o.push_back('\t'); put_int(o, len[i]); o += "\t100.0\t";
+            o.push_back(strand && strand[i] ? '-' : '+');
+            o += "\t0\t0\t*\t"; label(i); o.push_back('\t'); label(r); o.push_back('\n');
+        }
+    }
+    for (int64_t c = 0; c < nc; c++) {
+        o += "C\t"; put_int(o, c); o.push_back('\t'); put_int(o, 1 + cnt[(size_t)c + 1] - cnt[(size_t)c]);
+        o += "\t*\t*\t*\t*\t*\t"; label(order[c]); o += "\t*\n";
+    }
+    if ((int64_t)o.size() > cap) return ITSX_ELIMIT;
+    memcpy(dst, o.data(), o.size());
+    return (int64_t)o.size();
+}
+
+// rep.fa as `vsearch --fastaout` writes it: '>label', then the sequence as stored, wrapped at `width` columns.
+int64_t itsx_repfa_format(const uint8_t *buf, const int64_t *s_off, const int64_t *s_len, const int64_t *lab_off,
+                          const int32_t *lab_len, const int64_t *order, int64_t nc, int32_t width, uint8_t *dst, int64_t cap)
+{
+    if (nc < 0 || width <= 0 || (nc && (!buf || !s_off || !s_len || !lab_off || !lab_len || !order)) || !dst) return ITSX_EINVAL;
+    std::vector<int64_t> at((size_t)nc + 1, 0);
+    for (int64_t c = 0; c < nc; c++) {
+        const int64_t r = order[c], L = s_len[r];
+        at[(size_t)c + 1] = at[(size_t)c] + 1 + lab_len[r] + 1 + L + (L + width - 1) / width;
+    }
+    if (at[(size_t)nc] > cap) return ITSX_ELIMIT;
+    parallel_for(nc, 1 << 12, [&](int64_t a, int64_t b, int) {
+        for (int64_t c = a; c < b; c++) {
+            const int64_t r = order[c];
+            uint8_t *o = dst + at[(size_t)c];
+            *o++ = '>';
+            memcpy(o, buf + lab_off[r], (size_t)lab_len[r]); o += lab_len[r];
+            *o++ = '\n';
+            const uint8_t *q = buf + s_off[r];
+            for (int64_t j = 0; j < s_len[r]; j += width) {
+                const int64_t k = std::min<int64_t>(width, s_len[r] - j);
+                memcpy(o, q + j, (size_t)k); o += k;
+                *o++ = '\n';
+            }
+        }
+    });
+    return at[(size_t)nc];
 }
 
 }  // extern "C"

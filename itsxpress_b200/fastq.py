@@ -23,13 +23,14 @@ class FastqBatch:
     s_off/s_len : sequence start / length (q_off: quality start; same length)
     """
 
-    __slots__ = ("buf", "t_off", "t_len", "s_off", "s_len", "q_off", "n", "_ids")
+    __slots__ = ("buf", "t_off", "t_len", "s_off", "s_len", "q_off", "n", "_ids", "_labels")
 
     def __init__(self, buf, t_off, t_len, s_off, s_len, q_off):
         self.buf, self.t_off, self.t_len = buf, t_off, t_len
         self.s_off, self.s_len, self.q_off = s_off, s_len, q_off
         self.n = len(t_off)
         self._ids = None
+        self._labels = None
 
     # -- flat views for the device path -------------------------------------------------------
     def seq_concat(self):
@@ -54,16 +55,28 @@ class FastqBatch:
         pos = np.where(nxt < len(ws), ws[np.minimum(nxt, len(ws) - 1)], np.iinfo(np.int64).max)
         return np.minimum(pos - self.t_off, self.t_len).astype(np.int64)
 
+    def labels(self):
+        """(offset into buf int64[n], length int32[n]) of every record's id -- the first whitespace-delimited token of
+        its title, Biopython's record.id -- found by the native scanner; cached."""
+        if self._labels is None:
+            lab_off, lab_len = np.empty(self.n, np.int64), np.empty(self.n, np.int32)
+            if self.n:
+                t_off = np.ascontiguousarray(self.t_off, dtype=np.int64)
+                t_len = np.ascontiguousarray(self.t_len, dtype=np.int64)
+                buf = np.ascontiguousarray(self.buf)
+                if _native().itsx_fastq_labels(_vp(buf), _vp(t_off), _vp(t_len), self.n, _vp(lab_off), _vp(lab_len)) < 0:
+                    raise ValueError("itsx_fastq_labels")
+            self._labels = (lab_off, lab_len)
+        return self._labels
+
     def ids(self):
-        """First whitespace-delimited token of every title (Biopython's record.id); cached."""
+        """First whitespace-delimited token of every title (Biopython's record.id) as str; cached."""
         if self._ids is None:
-            out = []
-            b = self.buf
-            for o, l in zip(self.t_off.tolist(), self.t_len.tolist()):
-                t = b[o:o + l].tobytes()
-                sp = t.split(None, 1)
-                out.append(sp[0].decode("ascii", "replace") if sp else "")
-            self._ids = out
+            lab_off, lab_len = self.labels()
+            packed, off = _gather(self.buf, lab_off, lab_len)
+            text = packed.tobytes().decode("ascii", "replace")          # one character per byte, valid or not
+            o = off.tolist()
+            self._ids = [text[o[k]:o[k + 1]] for k in range(self.n)]
         return self._ids
 
     def seq(self, i):

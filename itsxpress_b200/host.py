@@ -22,7 +22,45 @@ def cluster_order(rep_index, ids):
     return first[np.asarray(order, dtype=np.int64)] if len(order) else first
 
 
+def _ascii_labels(batch):
+    """the batch's labels (offset, length) if every label byte is ASCII (the native emitters copy bytes, the Python ones
+    encode the decoded ids), else None"""
+    lab_off, lab_len = batch.labels()
+    if batch.n:
+        from .fastq import _gather
+        packed, _ = _gather(batch.buf, lab_off, lab_len)
+        if packed.size and int(packed.max()) > 127:
+            return None
+    return lab_off, lab_len
+
+
+def _vp(a):
+    import ctypes
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
 def write_rep_fasta(batch, order, ids, width=80):
+    """rep.fa as `vsearch --fastaout`: '>label' then the sequence as stored, wrapped at 80 columns (native formatter;
+    ``write_rep_fasta_py`` is the reference of the format)."""
+    from . import _lib
+    lab = _ascii_labels(batch)
+    order = np.ascontiguousarray(order, dtype=np.int64)
+    if lab is None:
+        return write_rep_fasta_py(batch, order, ids, width)
+    s_off = np.ascontiguousarray(batch.s_off, dtype=np.int64)
+    s_len = np.ascontiguousarray(batch.s_len, dtype=np.int64)
+    buf = np.ascontiguousarray(batch.buf)
+    L = s_len[order] if len(order) else np.zeros(0, np.int64)
+    cap = int((L + L // width + 4).sum() + lab[1][order].sum()) + 64 if len(order) else 64
+    dst = np.empty(cap, np.uint8)
+    n = _lib.lib().itsx_repfa_format(_vp(buf), _vp(s_off), _vp(s_len), _vp(lab[0]), _vp(lab[1]), _vp(order), len(order),
+                                     int(width), _vp(dst), cap)
+    if n < 0:
+        return write_rep_fasta_py(batch, order, ids, width)
+    return dst[:n].tobytes()
+
+
+def write_rep_fasta_py(batch, order, ids, width=80):
     """rep.fa as `vsearch --fastaout`: '>label' then the sequence as stored, wrapped at 80 columns."""
     out = []
     for i in np.asarray(order).tolist():
@@ -33,7 +71,31 @@ def write_rep_fasta(batch, order, ids, width=80):
     return b"".join(out)
 
 
-def write_uc(rep_index, strand, ids, lengths, order):
+def write_uc(rep_index, strand, ids, lengths, order, batch=None):
+    """uc.txt as `vsearch --uc` for --fastx_uniques: per cluster an S row then its H rows in input order, then one C row
+    per cluster; 10 tab-separated columns.  With the ``batch`` the ids come from, the native formatter writes it
+    (``write_uc_py`` is the reference of the format: 4 us per read)."""
+    lab = _ascii_labels(batch) if batch is not None else None
+    if lab is None:
+        return write_uc_py(rep_index, strand, ids, lengths, order)
+    from . import _lib
+    rep = np.ascontiguousarray(rep_index, dtype=np.int32)
+    st = None if strand is None else np.ascontiguousarray(strand, dtype=np.uint8)
+    ln = np.ascontiguousarray(lengths, dtype=np.int64)
+    order = np.ascontiguousarray(order, dtype=np.int64)
+    buf = np.ascontiguousarray(batch.buf)
+    n = len(rep)
+    maxlab = int(lab[1].max()) if n else 0
+    cap = n * (2 * maxlab + 64) + 2 * len(order) * (maxlab + 64) + 64
+    dst = np.empty(cap, np.uint8)
+    got = _lib.lib().itsx_uc_format(_vp(rep), None if st is None else _vp(st), _vp(ln), n, _vp(order), len(order), _vp(buf),
+                                    _vp(lab[0]), _vp(lab[1]), _vp(dst), cap)
+    if got < 0:
+        return write_uc_py(rep_index, strand, ids, lengths, order)
+    return dst[:got].tobytes()
+
+
+def write_uc_py(rep_index, strand, ids, lengths, order):
     """uc.txt as `vsearch --uc` for --fastx_uniques: per cluster an S row then its H rows in input order,
     then one C row per cluster; 10 tab-separated columns."""
     rep_index = np.asarray(rep_index)
@@ -70,7 +132,42 @@ def _g2(x):
     return "%9.2g" % x
 
 
+DOMTBL_FOOTER = "#\n# Program:         itsxpress-b200 (hmmsearch-compatible table)\n# [ok]\n"
+
+
+def _labels(names):
+    """byte strings back to back + int64 offsets, or None if a label is not ASCII (padding is per character)"""
+    try:
+        enc = [n.encode("ascii") for n in names]
+    except UnicodeEncodeError:
+        return None
+    off = np.zeros(len(enc) + 1, np.int64)
+    np.cumsum([len(e) for e in enc], out=off[1:])
+    return np.frombuffer(b"".join(enc) + b"\0", np.uint8), off, max([len(e) for e in enc], default=0)
+
+
 def write_domtbl(rows, seq_ids, prof_names, prof_M, nseq_total, nreported):
+    """domtbl.txt in hmmsearch's --domtblout layout: the native formatter (csrc/fastq_host.cpp, all host threads; the
+    Python loop below costs 25 us per row -- 6 s for a sample of 20 000 reads, a minute at 200 000), byte-identical to
+    ``write_domtbl_py``, which stays as the reference of the format and for labels that are not ASCII."""
+    from . import _lib
+    rows = np.ascontiguousarray(rows)
+    sl, pl = _labels(seq_ids), _labels(prof_names)
+    if sl is None or pl is None or rows.dtype != _lib.ROW_DTYPE:
+        return write_domtbl_py(rows, seq_ids, prof_names, prof_M, nseq_total, nreported)
+    M = np.ascontiguousarray(prof_M, dtype=np.int32)
+    nrep = np.ascontiguousarray(nreported, dtype=np.int32)
+    cap = len(rows) * (max(sl[2], 20) + max(pl[2], 20) + 320) + 64
+    dst = np.empty(cap, np.uint8)
+    vp = lambda a: a.ctypes.data_as(_lib.C.c_void_p)
+    n = _lib.lib().itsx_domtbl_format(vp(rows), len(rows), vp(sl[0]), vp(sl[1]), vp(pl[0]), vp(pl[1]), vp(M), vp(nrep),
+                                      float(nseq_total), vp(dst), cap)
+    if n < 0:
+        return write_domtbl_py(rows, seq_ids, prof_names, prof_M, nseq_total, nreported)
+    return DOMTBL_HEADER.encode() + dst[:n].tobytes() + DOMTBL_FOOTER.encode()
+
+
+def write_domtbl_py(rows, seq_ids, prof_names, prof_M, nseq_total, nreported):
     """domtbl.txt rows in hmmsearch's --domtblout layout (whitespace separated, 22 fields + description).
 
     The six fields ItsPosition reads (SeqSample.py:445-450: target name, tlen, query name, domain score,
@@ -103,5 +200,5 @@ def write_domtbl(rows, seq_ids, prof_names, prof_M, nseq_total, nreported):
             _g2(ev), float(r["seq_score"]), 0.0, int(k_in_hit[t]), int(ndom_of[t]),
             _g2(cev), _g2(iev), float(r["bitscore"]), 0.0,
             1, int(prof_M[p]), int(r["ienv"]), int(r["jenv"]), int(r["ienv"]), int(r["jenv"]), 0.0, "-"))
-    out.append("#\n# Program:         itsxpress-b200 (hmmsearch-compatible table)\n# [ok]\n")
+    out.append(DOMTBL_FOOTER)
     return "".join(out).encode()

@@ -324,6 +324,72 @@ class _Mock:
         return self.pos
 
 
+def test_native_ids_uc_and_rep_fasta_equal_the_python_ones():
+    """record.id = title.split(None, 1)[0] from the native label scanner; uc.txt / rep.fa from the native emitters equal the
+    Python reference emitters byte for byte (tricky titles, both strands, clusters of every size, 80-column wrapping), and
+    titles with non-ASCII bytes take the Python path."""
+    from itsxpress_b200 import host
+    rng = np.random.default_rng(23)
+    titles = ["r%d desc %d" % (i, i) for i in range(400)]
+    titles[3], titles[4], titles[5], titles[6], titles[7] = " lead space", "\ttab first", "id\ttab", "", "onlyid"
+    recs, seqs = [], []
+    for i, t in enumerate(titles):
+        L = int(rng.choice([1, 79, 80, 81, 160, 161, 250]))
+        s = "".join(rng.choice(list("ACGT"), L))
+        seqs.append(s)
+        recs.append("@%s\n%s\n+\n%s\n" % (t, s, "I" * L))
+    b = fq.parse_bytes("".join(recs).encode())
+    want_ids = [(t.split(None, 1) or [""])[0] for t in titles]
+    assert b.ids() == want_ids
+    lab_off, lab_len = b.labels()
+    assert [b.buf[o:o + l].tobytes().decode() for o, l in zip(lab_off.tolist(), lab_len.tolist())] == want_ids
+    rep = np.arange(b.n, dtype=np.int32)
+    for i in range(b.n):                                   # clusters of many sizes; representatives are first occurrences
+        if i % 3 and i > 10:
+            rep[i] = rep[int(rng.integers(0, i))]
+    strand = rng.integers(0, 2, b.n).astype(np.uint8)
+    order = host.cluster_order(rep, b.ids())
+    assert host.write_uc(rep, strand, b.ids(), b.s_len, order, batch=b) == host.write_uc_py(rep, strand, b.ids(), b.s_len, order)
+    assert host.write_uc(rep, None, b.ids(), b.s_len, order, batch=b) == host.write_uc_py(rep, None, b.ids(), b.s_len, order)
+    assert host.write_rep_fasta(b, order, b.ids()) == host.write_rep_fasta_py(b, order, b.ids())
+    assert host.write_rep_fasta(b, order[:0], b.ids()) == b"" and host.write_uc(rep[:0], None, [], b.s_len[:0], order[:0], batch=fq.parse_bytes(b"")) == b""
+    odd = fq.parse_bytes("@r\u00e9sum\u00e9 1\nACGT\n+\nIIII\n@plain\nAC\n+\nII\n".encode("latin-1"))
+    r2 = np.array([0, 1], np.int32)
+    assert host.write_uc(r2, None, odd.ids(), odd.s_len, np.array([0, 1]), batch=odd) == host.write_uc_py(r2, None, odd.ids(), odd.s_len, [0, 1])
+    assert host.write_rep_fasta(odd, np.array([0, 1]), odd.ids()) == host.write_rep_fasta_py(odd, [0, 1], odd.ids())
+
+
+def test_native_domtbl_formatter_equals_the_python_one():
+    """csrc/fastq_host.cpp::itsx_domtbl_format against host.write_domtbl_py, byte for byte: label padding (shorter than, equal
+    to and longer than the 20-column field), E-values from 1e-300 to 1e+5 and 0, scores that overflow their field width,
+    several domains per hit (running index / count), rows out of hit order, many rows (several threads)."""
+    from itsxpress_b200 import _lib, host
+    rng = np.random.default_rng(17)
+    nseq, nprof, n = 300, 7, 60000
+    seq_ids = ["s%d" % i + "x" * int(rng.integers(0, 30)) for i in range(nseq)]
+    seq_ids[0], seq_ids[1] = "a" * 20, "b" * 19
+    prof_names = ["3_left_%d" % i + "y" * (5 * i) for i in range(nprof)]
+    M = rng.integers(20, 46, nprof).astype(np.int32)
+    nrep = rng.integers(0, 1000, nprof).astype(np.int32)
+    rows = np.zeros(n, dtype=_lib.ROW_DTYPE)
+    rows["seq"] = rng.integers(0, nseq, n)
+    rows["prof"] = rng.integers(0, nprof, n)
+    rows["ienv"] = rng.integers(1, 400, n)
+    rows["jenv"] = rows["ienv"] + rng.integers(0, 60, n)
+    rows["tlen"] = rng.integers(50, 100000, n)
+    rows["bitscore"] = (rng.normal(30, 40, n)).astype(np.float32)
+    rows["seq_score"] = (rng.normal(30, 4000, n)).astype(np.float32)
+    rows["lnP"] = -rng.exponential(30, n) * rng.choice([0.01, 1, 25], n)
+    rows["seq_lnP"] = -rng.exponential(30, n) * rng.choice([0.01, 1, 25], n)
+    rows["lnP"][:5] = [-1e4, 0.0, -745.0, -709.0, 11.0]
+    for k in (0, 1, 17, 2000, n):
+        a = host.write_domtbl(rows[:k], seq_ids, prof_names, M, nseq, nrep)
+        assert a == host.write_domtbl_py(rows[:k], seq_ids, prof_names, M, nseq, nrep), k
+    # labels that are not ASCII take the Python path (padding counts characters)
+    odd = ["\ufffdid"] + seq_ids[1:]
+    assert host.write_domtbl(rows[:50], odd, prof_names, M, nseq, nrep) == host.write_domtbl_py(rows[:50], odd, prof_names, M, nseq, nrep)
+
+
 def _dedup_seq1():
     d = Dedup(uc_file=UC, rep_file=REP, seq_file=SEQ)
     d.matchdict = {"seq1": "seq1"}
