@@ -9,6 +9,7 @@
 // the title, len(seq) == len(qual), qualities in ASCII 33..126, otherwise an error).
 #include <algorithm>
 #include <atomic>
+#include <charconv>
 #include <cstring>
 #include <unordered_map>
 #include <cstdio>
@@ -276,17 +277,71 @@ int64_t itsx_domtbl_format(const itsx_dom_row *rows, int64_t nrows, const uint8_
     // domains per (profile, sequence) hit and the running index of every row within its hit, in row order
     std::vector<int32_t> k_in_hit((size_t)nrows), ndom((size_t)nrows);
     {
-        std::unordered_map<int64_t, int32_t> count;
-        count.reserve((size_t)nrows / 2 + 16);
-        for (int64_t t = 0; t < nrows; t++) k_in_hit[(size_t)t] = ++count[(int64_t)rows[t].prof << 32 | (uint32_t)rows[t].seq];
-        for (int64_t t = 0; t < nrows; t++) ndom[(size_t)t] = count[(int64_t)rows[t].prof << 32 | (uint32_t)rows[t].seq];
+        // open addressing over (profile, sequence): slot = first row of the hit, count kept at that row's ndom
+        size_t cap2 = 16;
+        while (cap2 < (size_t)nrows * 2) cap2 <<= 1;
+        std::vector<int64_t> slot(cap2, -1);
+        std::vector<int64_t> head((size_t)nrows);
+        auto key_of = [&](int64_t t) { return (uint64_t)(uint32_t)rows[t].prof << 32 | (uint32_t)rows[t].seq; };
+        for (int64_t t = 0; t < nrows; t++) {
+            const uint64_t k = key_of(t);
+            if (t > 0 && key_of(t - 1) == k) {                    // (the rows of a hit normally follow each other)
+                head[(size_t)t] = head[(size_t)t - 1];
+            } else {
+                size_t h = (size_t)((k * 0x9e3779b97f4a7c15ull) >> 20) & (cap2 - 1);
+                while (slot[h] >= 0 && key_of(slot[h]) != k) h = (h + 1) & (cap2 - 1);
+                if (slot[h] < 0) { slot[h] = t; ndom[(size_t)t] = 0; }
+                head[(size_t)t] = slot[h];
+            }
+            k_in_hit[(size_t)t] = ++ndom[(size_t)head[(size_t)t]];
+        }
+        for (int64_t t = 0; t < nrows; t++) ndom[(size_t)t] = ndom[(size_t)head[(size_t)t]];
     }
     const int nt = nthreads_for(nrows, 1 << 14);
     std::vector<std::string> part((size_t)nt);
+    // glibc's printf spends ~1 us per floating-point conversion; the three "%9.2g" go through std::to_chars (same digits:
+    // the shortest-round-trip machinery rounds the exact value to 2 significant digits as printf does), "%6.1f" of a score
+    // (a float, so 10 x it is exact in a double) through rint (ties to even, like printf), integers by hand
+    auto pad_int = [](std::string &o, int64_t v, int width) {
+        char t[24];
+        int k = 0;
+        const bool neg = v < 0;
+        uint64_t u = neg ? (uint64_t)(-v) : (uint64_t)v;
+        do { t[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+        if (neg) t[k++] = '-';
+        for (int i = k; i < width; i++) o.push_back(' ');
+        while (k) o.push_back(t[--k]);
+    };
+    auto put_g2 = [](std::string &o, double v) {                    // "%9.2g"
+        char t[64];
+        int n;
+        if (std::isfinite(v)) {
+            const auto r = std::to_chars(t, t + sizeof t, v, std::chars_format::general, 2);
+            n = (int)(r.ptr - t);
+        } else {
+            n = snprintf(t, sizeof t, "%.2g", v);
+        }
+        for (int i = n; i < 9; i++) o.push_back(' ');
+        o.append(t, (size_t)n);
+    };
+    auto put_f1 = [&](std::string &o, double v, int width) {        // "%<width>.1f" of a value whose tenfold is exact
+        if (!std::isfinite(v) || fabs(v) > 1e15) { char t[400]; const int n = snprintf(t, sizeof t, "%*.1f", width, v); o.append(t, (size_t)n); return; }
+        const double r = nearbyint(v * 10.0);                        // (round-to-nearest-even is the default mode)
+        const bool neg = std::signbit(v);
+        const uint64_t u = (uint64_t)fabs(r);
+        char t[32];
+        int k = 0;
+        t[k++] = (char)('0' + u % 10);
+        t[k++] = '.';
+        uint64_t w = u / 10;
+        do { t[k++] = (char)('0' + w % 10); w /= 10; } while (w);
+        if (neg) t[k++] = '-';
+        for (int i = k; i < width; i++) o.push_back(' ');
+        while (k) o.push_back(t[--k]);
+    };
     parallel_for(nrows, 1 << 14, [&](int64_t a, int64_t b, int t) {
         std::string &o = part[(size_t)t];
         o.reserve((size_t)(b - a) * 200);
-        char num[512];
         for (int64_t r = a; r < b; r++) {
             const itsx_dom_row &d = rows[r];
             const int p = d.prof;
@@ -294,14 +349,29 @@ int64_t itsx_domtbl_format(const itsx_dom_row *rows, int64_t nrows, const uint8_
             const int ls = (int)(seq_off[d.seq + 1] - seq_off[d.seq]), lp = (int)(prof_off[p + 1] - prof_off[p]);
             o.append((const char *)seq_lab + seq_off[d.seq], (size_t)ls);
             if (ls < 20) o.append((size_t)(20 - ls), ' ');
-            int n = snprintf(num, sizeof num, " %-10s %5d ", "-", d.tlen);
-            o.append(num, (size_t)n);
+            o += " -          ";                                   // " %-10s " of "-"
+            pad_int(o, d.tlen, 5);
+            o.push_back(' ');
             o.append((const char *)prof_lab + prof_off[p], (size_t)lp);
             if (lp < 20) o.append((size_t)(20 - lp), ' ');
-            n = snprintf(num, sizeof num, " %-10s %5d %9.2g %6.1f %5.1f %3d %3d %9.2g %9.2g %6.1f %5.1f %5d %5d %5d %5d %5d %5d %4.2f %s\n",
-                         "-", prof_M[p], ev, (double)d.seq_score, 0.0, k_in_hit[(size_t)r], ndom[(size_t)r], cev, iev,
-                         (double)d.bitscore, 0.0, 1, prof_M[p], d.ienv, d.jenv, d.ienv, d.jenv, 0.0, "-");
-            o.append(num, (size_t)n);
+            o += " -          ";
+            pad_int(o, prof_M[p], 5); o.push_back(' ');
+            put_g2(o, ev); o.push_back(' ');
+            put_f1(o, (double)d.seq_score, 6);
+            o += "   0.0 ";                                        // " %5.1f " of the bias column
+            pad_int(o, k_in_hit[(size_t)r], 3); o.push_back(' ');
+            pad_int(o, ndom[(size_t)r], 3); o.push_back(' ');
+            put_g2(o, cev); o.push_back(' ');
+            put_g2(o, iev); o.push_back(' ');
+            put_f1(o, (double)d.bitscore, 6);
+            o += "   0.0 ";
+            pad_int(o, 1, 5); o.push_back(' ');
+            pad_int(o, prof_M[p], 5); o.push_back(' ');
+            pad_int(o, d.ienv, 5); o.push_back(' ');
+            pad_int(o, d.jenv, 5); o.push_back(' ');
+            pad_int(o, d.ienv, 5); o.push_back(' ');
+            pad_int(o, d.jenv, 5);
+            o += " 0.00 -\n";
         }
     });
     int64_t total = 0;

@@ -158,13 +158,16 @@ def write_domtbl(rows, seq_ids, prof_names, prof_M, nseq_total, nreported):
     M = np.ascontiguousarray(prof_M, dtype=np.int32)
     nrep = np.ascontiguousarray(nreported, dtype=np.int32)
     cap = len(rows) * (max(sl[2], 20) + max(pl[2], 20) + 320) + 64
-    dst = np.empty(cap, np.uint8)
-    vp = lambda a: a.ctypes.data_as(_lib.C.c_void_p)
-    n = _lib.lib().itsx_domtbl_format(vp(rows), len(rows), vp(sl[0]), vp(sl[1]), vp(pl[0]), vp(pl[1]), vp(M), vp(nrep),
-                                      float(nseq_total), vp(dst), cap)
+    head, foot = DOMTBL_HEADER.encode(), DOMTBL_FOOTER.encode()
+    dst = np.empty(len(head) + cap + len(foot), np.uint8)          # header, rows and footer in place: one copy out
+    dst[:len(head)] = np.frombuffer(head, np.uint8)
+    body = dst[len(head):]
+    n = _lib.lib().itsx_domtbl_format(_vp(rows), len(rows), _vp(sl[0]), _vp(sl[1]), _vp(pl[0]), _vp(pl[1]), _vp(M), _vp(nrep),
+                                      float(nseq_total), _vp(body), cap)
     if n < 0:
         return write_domtbl_py(rows, seq_ids, prof_names, prof_M, nseq_total, nreported)
-    return DOMTBL_HEADER.encode() + dst[:n].tobytes() + DOMTBL_FOOTER.encode()
+    body[n:n + len(foot)] = np.frombuffer(foot, np.uint8)
+    return dst[:len(head) + n + len(foot)].tobytes()
 
 
 def write_domtbl_py(rows, seq_ids, prof_names, prof_M, nseq_total, nreported):
