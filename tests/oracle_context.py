@@ -5,7 +5,8 @@ above the C ABI -- the command line, SeqSample / ItsPosition / Dedup, the FASTQ 
 streaming -- can be driven end to end by `-m "not gpu"` tests.  It implements the methods those flows call, with the same
 argument meaning and the same array layouts as the ctypes wrapper (itsxpress_b200/_lib.py); tests install it by
 monkeypatching `itsxpress_b200.SeqSample.get_context`.  Covered: single-end flows (whole file and streamed) and the
-paired flows of one sample (merge, merged and unmerged output); not the batched multi-sample pass.
+paired flows of one sample (merge, merged and unmerged output), and the batched pass of several samples (classes and
+domZ per sample).
 """
 import types
 
@@ -26,6 +27,7 @@ class OracleContext:
         self._uid = self._first = None
         self._pos = None
         self._map = None
+        self._sample, self._nsamples = None, 1
 
     def _note(self, name):
         self.calls.append(name)
@@ -83,15 +85,57 @@ class OracleContext:
 
     # ---- derep ----
     def _derep(self):
-        rep, strand, nu = self.O.derep(self._seq, self._off)
+        if self._sample is None:
+            rep, strand, nu = self.O.derep(self._seq, self._off)
+        else:
+            # several samples in one pass: classes never span samples (itsx_reads_set_samples)
+            n = len(self._off) - 1
+            rep, strand = np.arange(n, dtype=np.int32), np.zeros(n, np.uint8)
+            for k in range(self._nsamples):
+                idx = np.flatnonzero(self._sample == k)
+                if not len(idx):
+                    continue
+                parts = [self._seq[self._off[i]:self._off[i + 1]] for i in idx]
+                o = np.zeros(len(idx) + 1, np.int64)
+                o[1:] = np.cumsum([len(p) for p in parts])
+                r, st, _ = self.O.derep(np.concatenate(parts), o)
+                rep[idx], strand[idx] = idx[r], st
+            nu = int(np.count_nonzero(rep == np.arange(n)))
         self._rep, self._strand = rep, strand
         self._first = np.flatnonzero(rep == np.arange(len(rep))).astype(np.int32)
         self._uid = np.searchsorted(self._first, rep).astype(np.int32)
         assert len(self._first) == nu
         return nu
 
+    def reads_upload(self, seq, off):
+        self._note("reads_upload")
+        self._seq = np.array(seq, dtype=np.uint8)
+        self._off = np.array(off, dtype=np.int64)
+        self._qual, self._sample = None, None
+
+    def set_samples(self, sample_of_read, n_samples):
+        self._sample, self._nsamples = np.array(sample_of_read, dtype=np.int32), int(n_samples)
+
+    def quals_upload(self, qual):
+        self._qual = np.array(qual, dtype=np.uint8)
+        assert len(self._qual) == len(self._seq)
+
+    def derep_map(self, n):
+        assert n == len(self._rep)
+        return self._rep.copy(), self._strand.copy(), self._uid.copy()
+
+    def trim_gather_resident(self, mode=0):
+        self._note("trim_gather_resident")
+        keep, lo, hi = self.O.trim_bounds(self._off, self._uid, self._pos["start"], self._pos["stop"], self._pos["tlen"], mode=mode)
+        self._fetch = self._gather(keep, lo, hi, self._seq, self._qual, self._off)
+        return len(self._fetch[0]), int(self._fetch[1][-1])
+
+    def run_fetch(self, out=None):
+        return self._fetch
+
     def derep(self, seq, off):
         self._note("derep")
+        self._sample = None
         self._seq = np.ascontiguousarray(seq, dtype=np.uint8)
         self._off = np.ascontiguousarray(off, dtype=np.int64)
         self._qual = None
@@ -109,6 +153,7 @@ class OracleContext:
     def reads_begin(self, nreads_hint=0, bases_hint=0):
         self._note("reads_begin")
         self._parts = []
+        self._sample = None
 
     def reads_append(self, seq, qual, off):
         self._note("reads_append")
@@ -144,12 +189,28 @@ class OracleContext:
         self.search_stage2()
 
     def search(self, params=None):
-        """the resident uniques, first-occurrence order"""
+        """the resident uniques, first-occurrence order; with several samples resident every sample is searched on its own
+        (its own domZ), the positions are those of all uniques in resident order"""
         self._note("search")
         parts = [self._seq[self._off[i]:self._off[i + 1]] for i in self._first]
         uoff = np.zeros(len(parts) + 1, np.int64)
         uoff[1:] = np.cumsum([len(p) for p in parts])
-        self._run_search(np.concatenate(parts) if parts else np.zeros(0, np.uint8), uoff, params)
+        if self._sample is None:
+            self._run_search(np.concatenate(parts) if parts else np.zeros(0, np.uint8), uoff, params)
+        else:
+            names = ["start", "stop", "tlen", "left_score10", "left_from", "left_to", "right_score10", "right_from", "right_to"]
+            pos = {k: np.full(len(parts), -1, np.int32) for k in names}
+            of_unique = self._sample[self._first]
+            for k in range(self._nsamples):
+                u = np.flatnonzero(of_unique == k)
+                if not len(u):
+                    continue
+                o = np.zeros(len(u) + 1, np.int64)
+                o[1:] = np.cumsum([len(parts[i]) for i in u])
+                self._run_search(np.concatenate([parts[i] for i in u]), o, params)
+                for name in names:
+                    pos[name][u] = self._pos[name]
+            self._pos, self._seqlen = pos, np.diff(uoff).astype(np.int32)
         self._map = (self._uid, None)          # the resident derep map feeds the trim (trim_gather_range)
 
     def search_seqs(self, seq, off, params=None):

@@ -189,3 +189,33 @@ def test_q2_paired_actions_equal_the_cli(oracle, on_oracle, tmp_path, monkeypatc
                                              "--outfile", cm, "--region", "ITS2", "--taxa", "Metazoa",
                                              "--log", str(tmp_path / "l.txt"), "--tempdir", str(tmp_path)]))
     assert fq._open_bytes(os.path.join(str(res), n1)) == open(cm, "rb").read()
+
+
+@pytest.mark.parametrize("action", ["pair-unmerged", "pair"])
+def test_q2_batched_samples_equal_the_per_sample_loop(oracle, on_oracle, tmp_path, action, monkeypatch):
+    """SURVEY 8(f3), host side: the samples of an artifact grouped into shared passes (q2_itsxpress._process_batch: reads of
+    all samples concatenated, one derep + search, outputs split by sample) write the same files as the sequential loop
+    (q2_itsxpress.py:273-333) -- the same artifact as tests/test_gpu_merge.py uses on the device."""
+    from itsxpress_b200 import q2_itsxpress as q2
+    from test_gpu_merge import _make_artifact
+    art = _make_artifact(str(tmp_path / "in"), [60, 17, 40, 0, 25])
+    fn = q2.trim_pair_output_unmerged if action == "pair-unmerged" else q2.trim_pair
+    monkeypatch.setattr(q2, "BATCH_READS", 0)
+    ref = fn(q2.PerSampleDir(art), region="ITS2", taxa="M")
+    assert "set_samples" not in on_oracle.calls and "reads_upload" not in on_oracle.calls
+    monkeypatch.setattr(q2, "BATCH_READS", 4_000_000)
+    one = fn(q2.PerSampleDir(art), region="ITS2", taxa="M")
+    assert on_oracle.calls.count("reads_upload") == 1
+    monkeypatch.setattr(q2, "BATCH_READS", 90)               # several batches
+    few = fn(q2.PerSampleDir(art), region="ITS2", taxa="M")
+    names = sorted(f for f in os.listdir(str(ref)) if f.endswith(".gz"))
+    assert len(names) == (10 if action == "pair-unmerged" else 5)
+    total = 0
+    for got in (one, few):
+        assert sorted(f for f in os.listdir(str(got)) if f.endswith(".gz")) == names
+        for n in names:
+            want = fq._open_bytes(os.path.join(str(ref), n))
+            assert fq._open_bytes(os.path.join(str(got), n)) == want, n
+            total += len(want)
+        assert open(os.path.join(str(got), "MANIFEST")).read() == open(os.path.join(str(ref), "MANIFEST")).read()
+    assert total > 20_000
