@@ -77,6 +77,9 @@ def myparser():
     return parser
 
 
+_RUNTIME_HMM_CACHE = {}
+
+
 def create_runtime_hmm(taxa, region, tempdir):
     """Write ``<tempdir>/runtime_selected.hmm`` holding only the profiles whose NAME starts with the region's
     two prefixes, taken from the taxon's file (or every taxon file in ``taxa_dict`` order for "All"); missing
@@ -88,11 +91,14 @@ def create_runtime_hmm(taxa, region, tempdir):
         files = [taxa_dict.get(taxa, taxa)]
     prefixes = REGION_PREFIXES.get(region, ("1_", "2_", "3_", "4_"))
     target = os.path.join(tempdir, "runtime_selected.hmm")
-    with open(target, "w") as out:
-        for name in files:
-            path = os.path.join(hmm_dir, name)
-            if not os.path.exists(path):
-                continue
+    # a multi-sample driver asks for the same selection once per sample (q2_itsxpress.py:273-296): the text is kept,
+    # keyed by the files it came from (path, size, mtime)
+    present = [os.path.join(hmm_dir, name) for name in files if os.path.exists(os.path.join(hmm_dir, name))]
+    key = (tuple(prefixes), tuple((p, os.path.getsize(p), os.stat(p).st_mtime_ns) for p in present))
+    text = _RUNTIME_HMM_CACHE.get(key)
+    if text is None:
+        parts = []
+        for path in present:
             with open(path, "r") as src:
                 block, wanted = [], False
                 for line in src:
@@ -101,8 +107,13 @@ def create_runtime_hmm(taxa, region, tempdir):
                         wanted = True
                     if line.strip() == "//":
                         if wanted:
-                            out.writelines(block)
+                            parts.extend(block)
                         block, wanted = [], False
+        text = "".join(parts)
+        _RUNTIME_HMM_CACHE.clear()              # one selection at a time is all a run uses
+        _RUNTIME_HMM_CACHE[key] = text
+    with open(target, "w") as out:
+        out.write(text)
     return target
 
 
