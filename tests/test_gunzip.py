@@ -2,7 +2,6 @@
 header extras, buffers that have to grow, damaged streams (which must end up as the gzip module's own errors), reads into
 buffers of any size, and ONE deflate stream inflated on several cores (chunking shrunk so that small inputs take that
 path; block starts that are none; members ending inside chunks)."""
-import ctypes as C
 import gzip
 import io
 import os

@@ -23,7 +23,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import HMM_DIR, ROOT, TD
+from conftest import HMM_DIR, TD
 
 REP_FA = os.path.join(TD, "ex_tmpdir", "rep.fa")
 REF = "/root/reference"          # exists in the build container only; never on the GPU box (these tests are not gpu-marked)
