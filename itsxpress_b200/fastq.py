@@ -44,17 +44,6 @@ class FastqBatch:
         o = int(self.t_off[i])
         return self.buf[o:o + int(self.t_len[i])].tobytes().decode("ascii", "replace")
 
-    def id_lengths(self):
-        """Length of the first whitespace-delimited token of every title, vectorised (titles never start with
-        white space in practice; a leading blank gives an empty id, as str.split would not -- callers that care
-        use ids())."""
-        ws = np.flatnonzero((self.buf == 32) | (self.buf == 9))
-        if len(ws) == 0 or self.n == 0:
-            return self.t_len.astype(np.int64)
-        nxt = np.searchsorted(ws, self.t_off)
-        pos = np.where(nxt < len(ws), ws[np.minimum(nxt, len(ws) - 1)], np.iinfo(np.int64).max)
-        return np.minimum(pos - self.t_off, self.t_len).astype(np.int64)
-
     def labels(self):
         """(offset into buf int64[n], length int32[n]) of every record's id -- the first whitespace-delimited token of
         its title, Biopython's record.id -- found by the native scanner; cached."""
