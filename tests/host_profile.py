@@ -5,8 +5,10 @@ replaced by constant answers, under cProfile.  What is left is the product's hos
 the inter-stage files, formatting, compression (ITSX_GZIP_LEVEL=0 takes zlib out of the picture, as the GPU writer does on
 the box), file output.  This is how the Python row loop of domtbl.txt (25 us per row) was found.
 
-  python tools/host_profile.py cli  --reads 200000 [--gz]
-  python tools/host_profile.py q2   --samples 6 --pairs 50000
+  python tests/host_profile.py cli  --reads 200000 [--gz]
+  python tests/host_profile.py q2   --samples 6 --pairs 50000
+
+(Lives under tests/ because it executes the oracle: only tests, smoke() and the bench's CPU legs may.)
 """
 import argparse
 import cProfile
