@@ -11,6 +11,9 @@
 #include <atomic>
 #include <charconv>
 #include <cstring>
+#include <new>
+#include <mutex>
+#include <exception>
 #include <unordered_map>
 #include <cstdio>
 #include <cmath>
@@ -63,18 +66,28 @@ int nthreads_for(int64_t work, int64_t grain)
     return (int)std::max<int64_t>(1, std::min<int64_t>(host_threads(), work / std::max<int64_t>(grain, 1)));
 }
 
+// f(a, b, t) over [0, n) cut into one range per thread.  What a worker throws (bad_alloc) is rethrown in the caller after
+// all threads have been joined; a thread that cannot be started has its range run by the caller.
 template <typename F> void parallel_for(int64_t n, int64_t grain, F f)
 {
     const int nt = nthreads_for(n, grain);
     if (nt <= 1) { f(0, n, 0); return; }
     std::vector<std::thread> th;
+    std::exception_ptr err;
+    std::mutex mu;
+    auto guarded = [&](int64_t a, int64_t b, int t) {
+        try { f(a, b, t); }
+        catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
+    };
     const int64_t step = (n + nt - 1) / nt;
     for (int t = 0; t < nt; t++) {
         const int64_t a = t * step, b = std::min(n, a + step);
         if (a >= b) break;
-        th.emplace_back([=] { f(a, b, t); });
+        try { th.emplace_back([&guarded, a, b, t] { guarded(a, b, t); }); }
+        catch (...) { guarded(a, b, t); }
     }
     for (auto &x : th) x.join();
+    if (err) std::rethrow_exception(err);
 }
 
 }  // namespace
@@ -187,7 +200,7 @@ int64_t itsx_fastq_index(const uint8_t *buf, int64_t nbytes, int64_t cap, int64_
 
 // Offset behind the last line of buf whose number is a multiple of four (0: fewer than four lines): newlines are counted on
 // all threads, then the 0-3 lines of the unfinished record are stepped over from the end.
-int64_t itsx_fastq_cut(const uint8_t *buf, int64_t nbytes)
+static int64_t fastq_cut_impl(const uint8_t *buf, int64_t nbytes)
 {
     if (nbytes <= 0 || !buf) return 0;
     const int nt = nthreads_for(nbytes, 8 << 20);
@@ -268,7 +281,7 @@ int64_t itsx_fastq_format(const uint8_t *buf, const int64_t *t_off, const int32_
 // reported hits of the profile; alignment-derived columns are constants (include/itsx_b200.h).  Rows are formatted on the
 // host threads into private strings and copied to dst in order.  Returns the bytes written, or ITSX_ELIMIT if cap is too
 // small (nothing written then).
-int64_t itsx_domtbl_format(const itsx_dom_row *rows, int64_t nrows, const uint8_t *seq_lab, const int64_t *seq_off,
+static int64_t domtbl_format_impl(const itsx_dom_row *rows, int64_t nrows, const uint8_t *seq_lab, const int64_t *seq_off,
                            const uint8_t *prof_lab, const int64_t *prof_off, const int32_t *prof_M, const int32_t *nreported,
                            double Z, uint8_t *dst, int64_t cap)
 {
@@ -384,7 +397,7 @@ int64_t itsx_domtbl_format(const itsx_dom_row *rows, int64_t nrows, const uint8_
 
 // First whitespace-delimited token of every title (Biopython's record.id = title.split(None, 1)[0]): where it starts in buf
 // and how long it is (0 for a title without one).
-int64_t itsx_fastq_labels(const uint8_t *buf, const int64_t *t_off, const int64_t *t_len, int64_t n, int64_t *lab_off,
+static int64_t fastq_labels_impl(const uint8_t *buf, const int64_t *t_off, const int64_t *t_len, int64_t n, int64_t *lab_off,
                           int32_t *lab_len)
 {
     if (n < 0 || (n && (!buf || !t_off || !t_len || !lab_off || !lab_len))) return ITSX_EINVAL;
@@ -417,7 +430,7 @@ inline void put_int(std::string &o, int64_t v)
 // `order`, an S row and the H rows of its other members in input order, then one C row per cluster.  rep[i] = read index of
 // read i's representative, strand[i] != 0 -> '-' (may be NULL), len[i] = sequence length, order[c] = representative of
 // cluster c, labels as itsx_fastq_labels returns them.  Returns the bytes written, ITSX_ELIMIT if cap is too small.
-int64_t itsx_uc_format(const int32_t *rep, const uint8_t *strand, const int64_t *len, int64_t n, const int64_t *order, int64_t nc,
+static int64_t uc_format_impl(const int32_t *rep, const uint8_t *strand, const int64_t *len, int64_t n, const int64_t *order, int64_t nc,
                        const uint8_t *buf, const int64_t *lab_off, const int32_t *lab_len, uint8_t *dst, int64_t cap)
 {
     if (n < 0 || nc < 0 || (n && (!rep || !len || !buf || !lab_off || !lab_len)) || (nc && !order) || !dst) return ITSX_EINVAL;
@@ -453,7 +466,7 @@ int64_t itsx_uc_format(const int32_t *rep, const uint8_t *strand, const int64_t 
 }
 
 // rep.fa as `vsearch --fastaout` writes it: '>label', then the sequence as stored, wrapped at `width` columns.
-int64_t itsx_repfa_format(const uint8_t *buf, const int64_t *s_off, const int64_t *s_len, const int64_t *lab_off,
+static int64_t repfa_format_impl(const uint8_t *buf, const int64_t *s_off, const int64_t *s_len, const int64_t *lab_off,
                           const int32_t *lab_len, const int64_t *order, int64_t nc, int32_t width, uint8_t *dst, int64_t cap)
 {
     if (nc < 0 || width <= 0 || (nc && (!buf || !s_off || !s_len || !lab_off || !lab_len || !order)) || !dst) return ITSX_EINVAL;
@@ -479,6 +492,47 @@ int64_t itsx_repfa_format(const uint8_t *buf, const int64_t *s_off, const int64_
         }
     });
     return at[(size_t)nc];
+}
+
+// ---- no exception crosses the C ABI: the formatters above allocate (strings, vectors) and start threads ----
+int64_t itsx_fastq_cut(const uint8_t *buf, int64_t nbytes)
+{
+    try { return fastq_cut_impl(buf, nbytes); }
+    catch (const std::bad_alloc &) { return ITSX_ELIMIT; }
+    catch (...) { return ITSX_EINVAL; }
+}
+
+int64_t itsx_domtbl_format(const itsx_dom_row *rows, int64_t nrows, const uint8_t *seq_lab, const int64_t *seq_off,
+                           const uint8_t *prof_lab, const int64_t *prof_off, const int32_t *prof_M, const int32_t *nreported,
+                           double Z, uint8_t *dst, int64_t cap)
+{
+    try { return domtbl_format_impl(rows, nrows, seq_lab, seq_off, prof_lab, prof_off, prof_M, nreported, Z, dst, cap); }
+    catch (const std::bad_alloc &) { return ITSX_ELIMIT; }
+    catch (...) { return ITSX_EINVAL; }
+}
+
+int64_t itsx_fastq_labels(const uint8_t *buf, const int64_t *t_off, const int64_t *t_len, int64_t n, int64_t *lab_off,
+                          int32_t *lab_len)
+{
+    try { return fastq_labels_impl(buf, t_off, t_len, n, lab_off, lab_len); }
+    catch (const std::bad_alloc &) { return ITSX_ELIMIT; }
+    catch (...) { return ITSX_EINVAL; }
+}
+
+int64_t itsx_uc_format(const int32_t *rep, const uint8_t *strand, const int64_t *len, int64_t n, const int64_t *order, int64_t nc,
+                       const uint8_t *buf, const int64_t *lab_off, const int32_t *lab_len, uint8_t *dst, int64_t cap)
+{
+    try { return uc_format_impl(rep, strand, len, n, order, nc, buf, lab_off, lab_len, dst, cap); }
+    catch (const std::bad_alloc &) { return ITSX_ELIMIT; }
+    catch (...) { return ITSX_EINVAL; }
+}
+
+int64_t itsx_repfa_format(const uint8_t *buf, const int64_t *s_off, const int64_t *s_len, const int64_t *lab_off,
+                          const int32_t *lab_len, const int64_t *order, int64_t nc, int32_t width, uint8_t *dst, int64_t cap)
+{
+    try { return repfa_format_impl(buf, s_off, s_len, lab_off, lab_len, order, nc, width, dst, cap); }
+    catch (const std::bad_alloc &) { return ITSX_ELIMIT; }
+    catch (...) { return ITSX_EINVAL; }
 }
 
 }  // extern "C"

@@ -24,7 +24,10 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <memory>
+#include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -879,12 +882,26 @@ int64_t step_sequential(itsx_gz *h, uint8_t *dst, int64_t room)
     return wrote;
 }
 
+// f(0 .. n-1) on n threads (the caller's is one of them).  What a worker throws (bad_alloc under memory pressure) is
+// rethrown here after every thread has been joined; a thread that cannot be started has its share run by the caller.
 template <typename F> void on_threads(int n, F f)
 {
     std::vector<std::thread> th;
-    for (int t = 1; t < n; t++) th.emplace_back([=] { f(t); });
-    f(0);
+    std::exception_ptr err;
+    std::mutex mu;
+    auto guarded = [&](int t) {
+        try { f(t); }
+        catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
+    };
+    std::vector<int> inline_share;
+    for (int t = 1; t < n; t++) {
+        try { th.emplace_back([&guarded, t] { guarded(t); }); }
+        catch (...) { inline_share.push_back(t); }
+    }
+    guarded(0);
+    for (int t : inline_share) guarded(t);
     for (auto &x : th) x.join();
+    if (err) std::rethrow_exception(err);
 }
 
 // symbols -> bytes through the window in front of the segment; CRC-32 of the pieces between member ends
@@ -1058,7 +1075,8 @@ extern "C" {
 itsx_gz *itsx_gz_open(const uint8_t *src, int64_t n, int threads)
 {
     if ((!src && n) || n < 0) return nullptr;
-    itsx_gz *h = new itsx_gz();
+    itsx_gz *h = new (std::nothrow) itsx_gz();
+    if (!h) return nullptr;
     h->src = src; h->end = src + n;
     h->threads = threads > 0 ? std::min(threads, 64) : hw_threads();
     memset(h->window, 0, WSIZE);
@@ -1066,10 +1084,8 @@ itsx_gz *itsx_gz_open(const uint8_t *src, int64_t n, int threads)
     return h;
 }
 
-int64_t itsx_gz_read(itsx_gz *h, uint8_t *dst, int64_t cap, int64_t hist)
+static int64_t gz_read_impl(itsx_gz *h, uint8_t *dst, int64_t cap, int64_t hist)
 {
-    if (!h || (!dst && cap > 0) || cap < 0 || hist < 0) return ITSX_EINVAL;
-    if (h->err) return h->err;
     int64_t done = 0;
     h->contig = (uint64_t)hist;
     if (h->pend_at < h->pending.size()) {
@@ -1093,6 +1109,18 @@ int64_t itsx_gz_read(itsx_gz *h, uint8_t *dst, int64_t cap, int64_t hist)
         done += r;
     }
     return done;
+}
+
+int64_t itsx_gz_read(itsx_gz *h, uint8_t *dst, int64_t cap, int64_t hist)
+{
+    if (!h || (!dst && cap > 0) || cap < 0 || hist < 0) return ITSX_EINVAL;
+    if (h->err) return h->err;
+    try {
+        return gz_read_impl(h, dst, cap, hist);
+    } catch (...) {                                   // out of memory in a decoder thread: no exception crosses the C ABI
+        h->err = ITSX_ELIMIT;
+        return ITSX_ELIMIT;
+    }
 }
 
 int itsx_gz_tune(itsx_gz *h, int64_t chunk_min, int64_t chunk_max, int64_t par_min)
