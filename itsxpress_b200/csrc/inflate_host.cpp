@@ -882,26 +882,38 @@ int64_t step_sequential(itsx_gz *h, uint8_t *dst, int64_t room)
     return wrote;
 }
 
-// f(0 .. n-1) on n threads (the caller's is one of them).  What a worker throws (bad_alloc under memory pressure) is
-// rethrown here after every thread has been joined; a thread that cannot be started has its share run by the caller.
-template <typename F> void on_threads(int n, F f)
+// f(0 .. n-1) on n threads (the caller's is one of them).  All or nothing: the workers wait behind a gate until every
+// thread exists (chunks wait for each other's block starts, so a missing thread would stall the rest); if one cannot be
+// started nothing is run and false comes back.  What a worker throws (bad_alloc under memory pressure) is rethrown here
+// after every thread has been joined.
+template <typename F> bool on_threads(int n, F f)
 {
     std::vector<std::thread> th;
     std::exception_ptr err;
     std::mutex mu;
+    std::atomic<int> gate{0};
     auto guarded = [&](int t) {
         try { f(t); }
         catch (...) { std::lock_guard<std::mutex> g(mu); if (!err) err = std::current_exception(); }
     };
-    std::vector<int> inline_share;
     for (int t = 1; t < n; t++) {
-        try { th.emplace_back([&guarded, t] { guarded(t); }); }
-        catch (...) { inline_share.push_back(t); }
+        try {
+            th.emplace_back([&guarded, &gate, t] {
+                int g;
+                while ((g = gate.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+                if (g > 0) guarded(t);
+            });
+        } catch (...) {
+            gate.store(-1, std::memory_order_release);
+            for (auto &x : th) x.join();
+            return false;
+        }
     }
+    gate.store(1, std::memory_order_release);
     guarded(0);
-    for (int t : inline_share) guarded(t);
     for (auto &x : th) x.join();
     if (err) std::rethrow_exception(err);
+    return true;
 }
 
 // symbols -> bytes through the window in front of the segment; CRC-32 of the pieces between member ends
@@ -958,7 +970,7 @@ int64_t batch_parallel(itsx_gz *h, uint8_t *dst, int64_t room)
         }
         return batch_stop;
     };
-    on_threads(nch, [&](int k) {
+    const bool started = on_threads(nch, [&](int k) {
         Segment &g = *h->segs[k];
         if (k > 0) {
             const int64_t a = (pos_byte + (int64_t)k * C) * 8;
@@ -972,6 +984,7 @@ int64_t batch_parallel(itsx_gz *h, uint8_t *dst, int64_t room)
         const int64_t stop = stop_for(k);
         decode_segment(g, *h->decs[k], src, end, k ? starts[k].load() : pos_bit, k ? (bool)start_hdr[(size_t)k] : at_header, stop, (size_t)(C * 7 / 2));
     });
+    if (!started) return -1;                                 // (the single-core decoder goes on from here)
     // ---- stitch ----
     std::vector<Segment *> acc;
     Segment *cur = h->segs[0].get();
@@ -1030,9 +1043,8 @@ int64_t batch_parallel(itsx_gz *h, uint8_t *dst, int64_t room)
         int64_t o = 0;
         for (size_t i = 0; i < acc.size(); i++) { off[i] = o; o += acc[i]->nout; }
         std::atomic<size_t> next{0};
-        on_threads(std::min<int>(nch, (int)acc.size()), [&](int) {
-            for (size_t i; (i = next.fetch_add(1)) < acc.size();) translate_segment(*acc[i], base + off[i]);
-        });
+        auto work = [&](int) { for (size_t i; (i = next.fetch_add(1)) < acc.size();) translate_segment(*acc[i], base + off[i]); };
+        if (!on_threads(std::min<int>(nch, (int)acc.size()), work)) work(0);
     }
     // ---- members: CRC-32 and ISIZE ----
     uint32_t mcrc = h->mcrc;
