@@ -203,6 +203,9 @@ def _process_batch(rows, results, tempdir, threads, taxa, region, paired_in, pai
     from .definitions import REGION_PREFIXES, maxmismatches, vsearch_fastq_qmax
     ctx = get_context()
     items = []
+    # every file of the batch is read / inflated / scanned on the read-ahead threads while the loop below merges the
+    # samples one after the other (the batch holds all of them in memory anyway)
+    fq.prefetch([f for sample in rows for f in (sample.forward, sample.reverse if paired_in else None)])
     for sample in rows:
         sobj_check = (sample.forward, sample.reverse if paired_in else None)
         try:

@@ -72,6 +72,7 @@ def main():
     ap.add_argument("--samples", type=int, default=6)
     ap.add_argument("--pairs", type=int, default=50000)
     ap.add_argument("--gz", action="store_true", help="cli: .gz input and output")
+    ap.add_argument("--batched", action="store_true", help="q2: small samples share device passes (the default of the driver)")
     ap.add_argument("--top", type=int, default=14)
     a = ap.parse_args()
     O.lib()
@@ -110,7 +111,8 @@ def main():
                 lines.append("S%d,%s,%s" % (k, fn, d))
         with open(os.path.join(art, "MANIFEST"), "w") as f:
             f.write("\n".join(lines) + "\n")
-        q2.BATCH_READS = 0
+        if not a.batched:
+            q2.BATCH_READS = 0
         units, what = a.samples * a.pairs, "pairs"
 
         def run():
