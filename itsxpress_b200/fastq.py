@@ -199,7 +199,10 @@ def _open_buffer(path, threads=None):
             if os.fstat(f.fileno()).st_size < (1 << 20):
                 return gunzip(f.read(), threads)
             # mapped, not read: the inflating threads pull the pages in themselves (the map lives only for this call)
-            mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+            try:
+                mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+            except (OSError, ValueError):          # a file system that cannot map: read it
+                return gunzip(f.read(), threads)
             try:
                 a = np.frombuffer(mm, dtype=np.uint8)
                 try:
@@ -680,7 +683,13 @@ def _gz_blocks(path, block):
         return
     done = 0
     with open(path, "rb") as f:
-        mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        try:
+            mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        except (OSError, ValueError):              # a file system that cannot map: zlib streams it
+            mm = None
+        if mm is None:
+            yield from _gz_blocks_zlib(path, block)
+            return
         try:
             a = np.frombuffer(mm, dtype=np.uint8)
             r = GzReader(a, host_share())
