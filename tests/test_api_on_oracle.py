@@ -78,3 +78,62 @@ def test_q2_trim_pair_actions(on_oracle, tmp_path, monkeypatch):
 
 def test_q2_main_sharded_single_rank_equals_action(on_oracle, tmp_path):
     M.test_q2_main_sharded_single_rank_equals_action(tmp_path)
+
+
+# ---- the reference's own engine-dependent tests (tests/test_main_pytest.py), same names; --taxa Metazoa stands in for Fungi
+# (F.hmm is missing from the mount), so the record counts are this taxon's, not the reference's 235 / 226 ----
+import os  # noqa: E402
+
+from conftest import TD  # noqa: E402
+
+
+def _cli(tmp_path, *argv):
+    from itsxpress_b200 import fastq as fq
+    from itsxpress_b200 import main as cli
+    out = str(tmp_path / "testout.fastq")
+    cli.main(args=cli.myparser().parse_args(list(argv) + ["--outfile", out, "--region", "ITS2", "--taxa", "Metazoa", "--threads", "1",
+                                                          "--log", str(tmp_path / "log.txt"), "--tempdir", str(tmp_path)]))
+    return fq.read_fastq(out).n
+
+
+def test_seq_sample_not_paired(on_oracle, tmp_path):                       # reference :165-171
+    from itsxpress_b200.main import create_runtime_hmm
+    sobj = SeqSample.SeqSampleNotPaired(fastq=os.path.join(TD, "4774-1-MSITS3_merged.fastq"), tempdir=str(tmp_path))
+    sobj.deduplicate(threads=1)
+    sobj._search(hmmfile=create_runtime_hmm("Metazoa", "ITS2", str(tmp_path)), threads=1)
+    assert os.path.getsize(sobj.dom_file) > 10000 and os.path.getsize(sobj.uc_file) > 1000
+
+
+def test_seq_sample_paired_not_interleaved(on_oracle, tmp_path):           # reference :183-193
+    from itsxpress_b200.main import create_runtime_hmm
+    sobj = SeqSample.SeqSamplePairedNotInterleaved(fastq=os.path.join(TD, "4774-1-MSITS3_R1.fastq"), tempdir=str(tmp_path),
+                                                   fastq2=os.path.join(TD, "4774-1-MSITS3_R2.fastq"))
+    sobj._merge_reads(stagger=True, threads=1)
+    sobj.deduplicate(threads=1)
+    sobj._search(hmmfile=create_runtime_hmm("Metazoa", "ITS2", str(tmp_path)), threads=1)
+    assert os.path.getsize(sobj.seq_file) > 100000 and os.path.getsize(sobj.dom_file) > 10000
+
+
+def test_main_paired(on_oracle, tmp_path):                                  # reference :226-253 (235 with Fungi)
+    n = _cli(tmp_path, "--fastq", os.path.join(TD, "4774-1-MSITS3_R1.fastq"), "--fastq2", os.path.join(TD, "4774-1-MSITS3_R2.fastq"))
+    assert 150 < n <= 250
+
+
+def test_main_paired_high_qual(on_oracle, tmp_path):                        # reference :256-285: quality scores above 41
+    """The reference asserts nothing here but that the run ends (its count is commented out): most base qualities of this
+    pair file were overwritten with Q49, so nearly every overlap scores below the merger's minimum (4 of 250 pairs merge
+    in the restatement) -- what the test guards is --fastq_qmax 93: qualities above 41 are not an error."""
+    n = _cli(tmp_path, "--fastq", os.path.join(TD, "high_qual_scores_R1.fastq.gz"), "--fastq2",
+             os.path.join(TD, "high_qual_scores_R2.fastq.gz"))
+    assert 0 <= n <= 250 and "merge_pairs" in on_oracle.calls
+
+
+def test_main_merged(on_oracle, tmp_path):                                  # reference :288-314 (226 with Fungi)
+    n = _cli(tmp_path, "--fastq", os.path.join(TD, "4774-1-MSITS3_merged.fastq"), "--single_end")
+    assert 150 < n <= 227
+
+
+def test_main_paired_no_cluster(on_oracle, tmp_path):                       # reference :317-347: --cluster_id 1
+    n = _cli(tmp_path, "--fastq", os.path.join(TD, "4774-1-MSITS3_R1.fastq"), "--fastq2", os.path.join(TD, "4774-1-MSITS3_R2.fastq"),
+             "--cluster_id", "1")
+    assert 150 < n <= 250
