@@ -53,13 +53,15 @@ class _Buf(C.Structure):
 
 
 def _compress_frame(data, level):
+    import numpy as np
     L = _lib()
     cap = L.ZSTD_compressBound(len(data))
-    out = C.create_string_buffer(cap)
-    n = L.ZSTD_compress(out, cap, data, len(data), level)
+    out = np.empty(cap, np.uint8)                      # (create_string_buffer would zero-fill it first)
+    src = np.frombuffer(data, np.uint8)
+    n = L.ZSTD_compress(C.c_void_p(out.ctypes.data), cap, C.c_void_p(src.ctypes.data if len(data) else 0), len(data), level)
     if L.ZSTD_isError(n):
         raise ValueError("zstd: " + L.ZSTD_getErrorName(n).decode())
-    return out.raw[:n]
+    return out[:n].tobytes()
 
 
 def compress(data, level=3, threads=None):
@@ -90,21 +92,22 @@ def _frames(L, base, n):
     return out
 
 
-def decompress(data, threads=None):
+def decompress(data, threads=None, as_array=False):
     """Whole-buffer decode.  A stream of several frames that state their sizes (what ``compress`` writes, pzstd, zstd -T
     with --rsyncable ...) is decoded frame-parallel; everything else through the streaming decoder (multi-frame files and
-    frames without a content size included)."""
+    frames without a content size included).  ``as_array``: a uint8 array instead of bytes (no copy of the result)."""
+    import numpy as np
     L = _lib()
     data = bytes(data)
     threads = _cores() if threads is None else threads
-    if threads > 1 and len(data) > (1 << 20):
-        src = C.create_string_buffer(data, len(data))
-        base = C.addressof(src)
+    if len(data) > (1 << 20):
+        src = np.frombuffer(data, np.uint8)
+        base = src.ctypes.data
         fr = _frames(L, base, len(data))
-        if fr is not None and len(fr) > 1:
+        if fr is not None and (len(fr) > 1 or as_array):
             total = sum(f[2] for f in fr)
-            dst = C.create_string_buffer(max(total, 1))
-            dbase = C.addressof(dst)
+            dst = np.empty(max(total, 1), np.uint8)
+            dbase = dst.ctypes.data
             offs, o = [], 0
             for f in fr:
                 offs.append(o)
@@ -113,13 +116,17 @@ def decompress(data, threads=None):
             def one(i):
                 at, cs, us = fr[i]
                 return L.ZSTD_decompress(C.c_void_p(dbase + offs[i]), us, C.c_void_p(base + at), cs), us
-            from concurrent.futures import ThreadPoolExecutor
-            with ThreadPoolExecutor(threads) as ex:
-                res = list(ex.map(one, range(len(fr))))
+            if threads > 1 and len(fr) > 1:
+                from concurrent.futures import ThreadPoolExecutor
+                with ThreadPoolExecutor(threads) as ex:
+                    res = list(ex.map(one, range(len(fr))))
+            else:
+                res = [one(i) for i in range(len(fr))]
             if all((not L.ZSTD_isError(r)) and r == us for r, us in res):
-                return dst.raw[:total]
+                return dst[:total] if as_array else dst[:total].tobytes()
             # anything odd: the streaming decoder below reports it the usual way
-    return _decompress_streaming(data)
+    out = _decompress_streaming(data)
+    return np.frombuffer(out, np.uint8) if as_array else out
 
 
 def _decompress_streaming(data):

@@ -217,7 +217,7 @@ def _open_buffer(path, threads=None):
     if path.endswith(".zst"):
         from . import _zstd
         with open(path, "rb") as f:
-            return _zstd.decompress(f.read())
+            return _zstd.decompress(f.read(), as_array=True)
     with open(path, "rb") as f:
         return f.read()
 

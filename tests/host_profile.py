@@ -72,6 +72,7 @@ def main():
     ap.add_argument("--samples", type=int, default=6)
     ap.add_argument("--pairs", type=int, default=50000)
     ap.add_argument("--gz", action="store_true", help="cli: .gz input and output")
+    ap.add_argument("--zst", action="store_true", help="cli: .zst input and output")
     ap.add_argument("--batched", action="store_true", help="q2: small samples share device passes (the default of the driver)")
     ap.add_argument("--top", type=int, default=14)
     a = ap.parse_args()
@@ -87,7 +88,12 @@ def main():
             with open(src, "rb") as f, open(src + ".gz", "wb") as g:
                 g.write(gzip_one_member(f.read()))
             src += ".gz"
-        argv = ["--fastq", src, "--single_end", "--outfile", os.path.join(tmp, "out.fastq" + (".gz" if a.gz else "")), "--region", "ITS1",
+        if a.zst:
+            from itsxpress_b200 import _zstd
+            with open(src, "rb") as f, open(src + ".zst", "wb") as g:
+                g.write(_zstd.compress(f.read()))
+            src += ".zst"
+        argv = ["--fastq", src, "--single_end", "--outfile", os.path.join(tmp, "out.fastq" + (".gz" if a.gz else ".zst" if a.zst else "")), "--region", "ITS1",
                 "--taxa", "Metazoa", "--log", os.path.join(tmp, "log.txt"), "--tempdir", tmp]
         units, what = len(off) - 1, "reads"
 
