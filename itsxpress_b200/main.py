@@ -134,10 +134,14 @@ def _logger_setup(logfile):
     try:
         logging.basicConfig(level=logging.DEBUG, format="%(asctime)s %(name)-12s %(levelname)-8s %(message)s",
                             datefmt="%m-%d %H:%M", filename=logfile, filemode="w")
-        console = logging.StreamHandler()
-        console.setLevel(logging.INFO)
-        console.setFormatter(logging.Formatter("%(asctime)s: %(levelname)-8s %(message)s"))
-        logging.getLogger("").addHandler(console)
+        root = logging.getLogger("")
+        if not any(getattr(h, "_itsxpress_console", False) for h in root.handlers):
+            # (one console handler per process: main() may run several times in one -- tests, the bench, drivers)
+            console = logging.StreamHandler()
+            console.setLevel(logging.INFO)
+            console.setFormatter(logging.Formatter("%(asctime)s: %(levelname)-8s %(message)s"))
+            console._itsxpress_console = True
+            root.addHandler(console)
     except Exception as e:
         print("An error occurred setting up logging")
         raise e
