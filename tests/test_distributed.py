@@ -102,3 +102,42 @@ def test_q2_samples_dealt_to_ranks(tmp_path, world):
     assert man[0] == "sample-id,filename,direction" and len(man) == 1 + 14
     assert sorted(l.split(",")[1] for l in man[1:]) == sorted(l.split(",")[1] for l in lines[1:])
     assert q2.deal_samples([5, 5, 5, 5], 2) == [0, 1, 0, 1] and q2.deal_samples([], 4) == []
+
+
+def test_q2_main_sharded_two_ranks_real_pipeline_on_the_oracle(tmp_path, oracle, monkeypatch):
+    """The same over gloo with the REAL per-sample / batched pipeline on every rank (the CPU oracle stands in for each
+    rank's device, tests/oracle_context.py): the files two ranks write into the shared directory are, byte for byte, the
+    files one process writes -- samples of 17..60 pairs that share sequences, one of them empty."""
+    from itsxpress_b200 import SeqSample
+    from itsxpress_b200 import fastq as fq
+    from itsxpress_b200 import q2_itsxpress as q2
+    from oracle_context import OracleContext
+    from test_gpu_merge import _make_artifact
+    art = _make_artifact(str(tmp_path / "in"), [60, 17, 40, 0, 25])
+    out = tmp_path / "out"
+    world, port = 2, 29791
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "dist_q2_worker.py"), art, str(out), "oracle"],
+                                      env=env))
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    mine = [open(str(out / ("rank%d.txt" % r))).read().split() for r in range(world)]
+    assert sorted(sum(mine, [])) == ["S0", "S1", "S2", "S3", "S4"] and all(mine)
+    ctx = OracleContext(oracle)
+    monkeypatch.setattr(SeqSample, "get_context", lambda: ctx)
+    monkeypatch.setenv("ITSX_GZIP", "host")
+    SeqSample.reset_sessions()
+    ref = q2.trim_pair_output_unmerged(q2.PerSampleDir(art), region="ITS2", taxa="M")
+    names = sorted(f for f in os.listdir(str(ref)) if f.endswith(".gz"))
+    assert len(names) == 10 and sorted(f for f in os.listdir(str(out)) if f.endswith(".gz")) == names
+    total = 0
+    for n in names:
+        want = fq._open_bytes(os.path.join(str(ref), n))
+        assert fq._open_bytes(os.path.join(str(out), n)) == want, n
+        total += len(want)
+    assert total > 20_000
+    assert open(str(out / "MANIFEST")).read() == open(os.path.join(str(ref), "MANIFEST")).read()
+    SeqSample.reset_sessions()
