@@ -410,7 +410,7 @@ class SeqSamplePairedNotInterleaved(SeqSample):
                 raise
             except (ValueError, _lib.ItsxError) as e:
                 raise subprocess.CalledProcessError(1, argv, stderr=str(e).encode("utf-8")) from e
-            data = fq.format_gathered(b1, idx, out_off, out_seq, out_qual)
+            data = fq.format_gathered(b1, idx, out_off, out_seq, out_qual, as_array=True)
             with open(seq_file, "wb") as f:
                 f.write(data)
             # deduplicate() takes the merged records from here instead of reading seq.fq back and scanning it again
@@ -727,7 +727,7 @@ class Dedup:
         pre = (CCS_FWD, b"~" * len(CCS_FWD)) if trim_ccs else None
         suf = (CCS_REV, b"~" * len(CCS_REV)) if trim_ccs else None
         n_empty = int(np.count_nonzero(np.diff(oo) == 0))
-        return fq.format_gathered(batch, ki, oo, os_, oq, prefix=pre, suffix=suf), ki, n_empty
+        return fq.format_gathered(batch, ki, oo, os_, oq, prefix=pre, suffix=suf, as_array=True), ki, n_empty
 
     def create_trimmed_seqs(self, outfile, gzipped, zstd_file, itspos, wri_file, tempdir, trim_ccs=False):
         """Write the reads of ``seq_file`` trimmed to the selected region, input order, plain / gz / zst
@@ -764,7 +764,7 @@ class Dedup:
                 ki, oo, os_, oq = ctx.trim_gather_range(first, chunk.n, nb)
                 n_empty += int(np.count_nonzero(np.diff(oo) == 0))
                 if writer is not None:
-                    writer.write(fq.format_gathered(chunk, ki, oo, os_, oq), len(ki))
+                    writer.write(fq.format_gathered(chunk, ki, oo, os_, oq, as_array=True), len(ki))
                 first += chunk.n
         finally:
             if writer is not None:

@@ -454,14 +454,15 @@ def _scatter(dst, dst_off, src, src_off, length):
     dst[np.repeat(dst_off, length) + within] = src[np.repeat(src_off.astype(np.int64), length) + within]
 
 
-def format_gathered(batch, keep_idx, out_off, out_seq, out_qual, prefix=None, suffix=None):
+def format_gathered(batch, keep_idx, out_off, out_seq, out_qual, prefix=None, suffix=None, as_array=False):
     """FASTQ text from slices already gathered back to back on the device (itsx_trim_gather):
     record t = title of batch[keep_idx[t]], bases out_seq[out_off[t]:out_off[t+1]], same for qualities.
     prefix / suffix: (bases, quals) byte strings stitched to every record (--trim-ccs, SeqSample.py:601-622).
-    Native, multi-threaded (csrc/fastq_host.cpp)."""
+    Native, multi-threaded (csrc/fastq_host.cpp).  ``as_array``: the uint8 array the formatter filled instead of a bytes
+    copy of it (the writers, the GPU gzip stage and the scanner take either)."""
     n = len(keep_idx)
     if n == 0:
-        return b""
+        return np.zeros(0, np.uint8) if as_array else b""
     ki = np.ascontiguousarray(keep_idx, dtype=np.int32)
     oo = np.ascontiguousarray(out_off, dtype=np.int64)
     os_ = np.ascontiguousarray(out_seq, dtype=np.uint8)
@@ -477,7 +478,7 @@ def format_gathered(batch, keep_idx, out_off, out_seq, out_qual, prefix=None, su
     total = L.itsx_fastq_format(*args, None)
     dst = np.empty(total, np.uint8)
     L.itsx_fastq_format(*args, _vp(dst))
-    return dst.tobytes()
+    return dst if as_array else dst.tobytes()
 
 
 def batch_of_gathered(data, batch, keep_idx, out_off):
@@ -780,7 +781,7 @@ class ChunkWriter:
 
     def write(self, data, n_records=0):
         self.n += int(n_records)
-        if not data:
+        if len(data) == 0:
             return
         if self.gz:
             self.f.write(gzip_members(data))

@@ -259,7 +259,7 @@ def _process_batch(rows, results, tempdir, threads, taxa, region, paired_in, pai
             a, b = np.searchsorted(ki, starts[k]), np.searchsorted(ki, starts[k + 1])
             kept_local = ki[a:b] - starts[k]
             text = fq.format_gathered(it["b1"], it["idx"][kept_local], oo[a:b + 1] - oo[a], os_[oo[a]:oo[b]],
-                                      oq[oo[a]:oo[b]])
+                                      oq[oo[a]:oo[b]], as_array=True)
             out_fwd = os.path.join(str(results), pathlib.Path(it["sample"].forward).name)
             fq.write_compressed(out_fwd, text, gzipped=True, zstd_file=False, n_records=len(kept_local))
         return
@@ -276,7 +276,7 @@ def _process_batch(rows, results, tempdir, threads, taxa, region, paired_in, pai
             ctx.trim_set_map(uid_pair, nu)
             ctx.positions_set(start, stop, tlen)
             kk, oo, os_, oq = ctx.trim_gather(b.n, mode=mode, seq=raw[0], qual=raw[1], off=raw[2])
-            outs.append((fq.format_gathered(b, kk, oo, os_, oq), len(kk)))
+            outs.append((fq.format_gathered(b, kk, oo, os_, oq, as_array=True), len(kk)))
         # as upstream (q2_itsxpress.py:311-323): the trimmed r1 goes under the forward file's name, r2 under the reverse's
         fq.write_compressed(os.path.join(str(results), pathlib.Path(it["sample"].forward).name), outs[0][0],
                             gzipped=True, zstd_file=False, n_records=outs[0][1])
