@@ -115,7 +115,11 @@ def test_q2_main_sharded_two_ranks_real_pipeline_on_the_oracle(tmp_path, oracle,
     from test_gpu_merge import _make_artifact
     art = _make_artifact(str(tmp_path / "in"), [60, 17, 40, 0, 25])
     out = tmp_path / "out"
-    world, port = 2, 29791
+    import socket
+    with socket.socket() as sock:                       # a port nobody holds right now
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    world = 2
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
